@@ -1,0 +1,912 @@
+/* TEST INFRASTRUCTURE ONLY -- never linked into, imported by or executed from the product path.
+ *
+ * oracle/pf2_oracle.c : plain-C (C99) CPU restatement of PANSFEM2's SIMP topology-optimisation hot path.
+ * It exists so that the parity tests have a checker that travels to the GPU box as SOURCE (the live reference,
+ * oracle/_ref/libpf2ref.so, needs /root/reference to be rebuilt).  Each function cites the reference lines it
+ * restates (paths relative to /root/reference) and keeps the reference's floating-point evaluation ORDER, so on
+ * identical inputs it agrees with the reference to the last bit or two (pinned in tests/test_oracle_pinned.py
+ * against the reference's golden VTKs, its MMA known-answer tests and the live reference).
+ *
+ * Pinning status: PINNED (golden vectors tests/golden/*.npz generated from the reference's committed outputs
+ * sample/optimize/Density_{OC,MMA}.vtk, sample/solid/result_linear.vtk; KATs from src/Optimize/Solver/test_MMA*.cpp).
+ *
+ * Data model: flat arrays.  coords[nnode*dim], conn[nelem*npe], nodetoglobal[nnode*ndof] (-1 = Dirichlet).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include <time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+enum { EQ_PLANESTRAIN = 0, EQ_SOLID = 1, EQ_HEAT = 2 };
+enum { FILTER_DENSITY = 0, FILTER_HEAVISIDE = 1 };
+enum { OPT_OC = 0, OPT_MMA = 1 };
+
+static double now_s(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+static int ndof_of(int eq) { return eq == EQ_PLANESTRAIN ? 2 : (eq == EQ_SOLID ? 3 : 1); }
+static int dim_of(int eq) { return eq == EQ_SOLID ? 3 : 2; }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Shape functions and quadrature.
+ * ShapeFunction4Square::dNdr  src/FEM/Controller/ShapeFunction.h:186-191
+ * ShapeFunction8Cubic::dNdr   src/FEM/Controller/ShapeFunction.h:318-329
+ * Gauss4Square points         src/FEM/Controller/GaussIntegration.h:143-148  (order (-,-),(+,-),(-,+),(+,+))
+ * Gauss8Cubic points          src/FEM/Controller/GaussIntegration.h:231-240  (bottom CCW, top CCW); all weights 1.
+ * ---------------------------------------------------------------------------------------------------------- */
+static void dndr_q4(const double* r, double* d /* 2x4 */) {
+    d[0] = -0.25 * (1.0 - r[1]); d[1] = 0.25 * (1.0 - r[1]); d[2] = 0.25 * (1.0 + r[1]); d[3] = -0.25 * (1.0 + r[1]);
+    d[4] = -0.25 * (1.0 - r[0]); d[5] = -0.25 * (1.0 + r[0]); d[6] = 0.25 * (1.0 + r[0]); d[7] = 0.25 * (1.0 - r[0]);
+}
+static void dndr_h8(const double* r, double* d /* 3x8 */) {
+    static const double sx[8] = { -1, 1, 1, -1, -1, 1, 1, -1 };
+    static const double sy[8] = { -1, -1, 1, 1, -1, -1, 1, 1 };
+    static const double sz[8] = { -1, -1, -1, -1, 1, 1, 1, 1 };
+    for (int n = 0; n < 8; n++) {
+        /* the reference writes e.g. -0.125*(1-r1)*(1-r2); sign*0.125*(1 + s*r) evaluates to the same doubles */
+        d[n]      = sx[n] * 0.125 * (1.0 + sy[n] * r[1]) * (1.0 + sz[n] * r[2]);
+        d[8 + n]  = sy[n] * 0.125 * (1.0 + sz[n] * r[2]) * (1.0 + sx[n] * r[0]);
+        d[16 + n] = sz[n] * 0.125 * (1.0 + sx[n] * r[0]) * (1.0 + sy[n] * r[1]);
+    }
+}
+static void gauss_point(int dim, int g, double* r) {
+    const double a = 1.0 / sqrt(3.0);
+    if (dim == 2) {
+        static const int s[4][2] = { { -1, -1 }, { 1, -1 }, { -1, 1 }, { 1, 1 } };
+        r[0] = s[g][0] * a; r[1] = s[g][1] * a;
+    } else {
+        static const int s[8][3] = { { -1, -1, -1 }, { 1, -1, -1 }, { 1, 1, -1 }, { -1, 1, -1 },
+                                     { -1, -1, 1 }, { 1, -1, 1 }, { 1, 1, 1 }, { -1, 1, 1 } };
+        r[0] = s[g][0] * a; r[1] = s[g][1] * a; r[2] = s[g][2] * a;
+    }
+}
+
+/* C(m x n) = A(m x k) * B(k x n), Matrix<T>::operator*  src/LinearAlgebra/Models/Matrix.h:243-255 */
+static void matmul(int m, int k, int n, const double* A, const double* B, double* Cm) {
+    for (int i = 0; i < m; i++)
+        for (int j = 0; j < n; j++) {
+            double v = 0.0;
+            for (int l = 0; l < k; l++) v += A[i * k + l] * B[l * n + j];
+            Cm[i * n + j] = v;
+        }
+}
+/* Determinant (Matrix.h:326-342) and Inverse = adjugate/det (Matrix.h:346-360) for d = 2, 3 */
+static double det_d(int d, const double* v) {
+    if (d == 2) return v[0] * v[3] - v[1] * v[2];
+    return -v[8] * v[1] * v[3] - v[7] * v[5] * v[0] - v[2] * v[4] * v[6] + v[6] * v[1] * v[5] + v[7] * v[3] * v[2] + v[0] * v[4] * v[8];
+}
+static void inv_d(int d, const double* v, double* inv) {
+    double det = det_d(d, v);
+    for (int i = 0; i < d; i++)
+        for (int j = 0; j < d; j++) {
+            /* Cofactor(j, i): drop row j and column i */
+            double minor[4];
+            int c = 0;
+            for (int a = 0; a < d; a++) {
+                if (a == j) continue;
+                for (int b = 0; b < d; b++) {
+                    if (b == i) continue;
+                    minor[c++] = v[a * d + b];
+                }
+            }
+            double cd = (d == 2) ? minor[0] : (minor[0] * minor[3] - minor[1] * minor[2]);
+            inv[i * d + j] = (((i + j) & 1) ? -1.0 : 1.0) * cd;
+        }
+    for (int i = 0; i < d * d; i++) inv[i] /= det;
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Element matrices.
+ * PlaneStrainStiffness           src/FEM/Equation/PlaneStrain.h:21-58
+ * SolidLinearIsotropicElastic    src/FEM/Equation/Solid.h:21-64
+ * HeatTransfer                   src/FEM/Equation/HeatTransfer.h:20-43
+ * xe: npe x dim coordinates of the element's nodes.  Ke: (npe*ndof)^2 row-major.
+ * Accumulation order kept: Ke += ((((B^T D) B) J) t) w0 w1 [w2]   (PlaneStrain.h:56, Solid.h:62, HeatTransfer.h:41)
+ * ---------------------------------------------------------------------------------------------------------- */
+void orc_element_matrix(int eq, const double* xe, double E, double V, double t, double* Ke) {
+    const int dim = dim_of(eq), npe = (eq == EQ_SOLID) ? 8 : 4, ndof = ndof_of(eq), m = npe * ndof;
+    const int ns = (eq == EQ_PLANESTRAIN) ? 3 : (eq == EQ_SOLID ? 6 : dim);
+    double D[36];
+    memset(D, 0, sizeof D);
+    if (eq == EQ_PLANESTRAIN) {
+        D[0] = 1.0 - V; D[1] = V; D[3] = V; D[4] = 1.0 - V; D[8] = 0.5 * (1.0 - 2.0 * V);
+        double f = E / ((1.0 - 2.0 * V) * (1.0 + V));
+        for (int i = 0; i < 9; i++) D[i] *= f;
+    } else if (eq == EQ_SOLID) {
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) D[i * 6 + j] = (i == j) ? 1.0 - V : V;
+        for (int i = 3; i < 6; i++) D[i * 6 + i] = 0.5 * (1.0 - 2.0 * V);
+        double f = E / ((1.0 + V) * (1.0 - 2.0 * V));
+        for (int i = 0; i < 36; i++) D[i] *= f;
+    }
+    memset(Ke, 0, sizeof(double) * m * m);
+    const int ng = (dim == 2) ? 4 : 8;
+    for (int g = 0; g < ng; g++) {
+        double r[3], dNdr[24], dXdr[9], inv[9], dNdX[24];
+        gauss_point(dim, g, r);
+        if (dim == 2) dndr_q4(r, dNdr); else dndr_h8(r, dNdr);
+        matmul(dim, npe, dim, dNdr, xe, dXdr);
+        double J = det_d(dim, dXdr);
+        inv_d(dim, dXdr, inv);
+        matmul(dim, dim, npe, inv, dNdr, dNdX);
+        double B[6 * 24], Bt[24 * 6], BtD[24 * 6], BtDB[24 * 24];
+        memset(B, 0, sizeof B);
+        if (eq == EQ_PLANESTRAIN) {
+            for (int n = 0; n < npe; n++) {
+                B[0 * m + 2 * n] = dNdX[n];             /* row 0: dN/dx */
+                B[1 * m + 2 * n + 1] = dNdX[npe + n];   /* row 1: dN/dy */
+                B[2 * m + 2 * n] = dNdX[npe + n]; B[2 * m + 2 * n + 1] = dNdX[n];
+            }
+        } else if (eq == EQ_SOLID) {
+            for (int n = 0; n < npe; n++) {
+                double dx = dNdX[n], dy = dNdX[8 + n], dz = dNdX[16 + n];
+                B[0 * m + 3 * n] = dx; B[1 * m + 3 * n + 1] = dy; B[2 * m + 3 * n + 2] = dz;
+                B[3 * m + 3 * n] = dy; B[3 * m + 3 * n + 1] = dx;            /* gamma_xy */
+                B[4 * m + 3 * n + 1] = dz; B[4 * m + 3 * n + 2] = dy;        /* gamma_yz */
+                B[5 * m + 3 * n] = dz; B[5 * m + 3 * n + 2] = dx;            /* gamma_zx */
+            }
+        } else {
+            memcpy(B, dNdX, sizeof(double) * dim * npe);
+        }
+        for (int i = 0; i < ns; i++) for (int j = 0; j < m; j++) Bt[j * ns + i] = B[i * m + j];
+        double w = 1.0; /* IC::Weights are all 1.0 */
+        if (eq == EQ_HEAT) {
+            matmul(m, ns, m, Bt, B, BtDB);
+            for (int i = 0; i < m * m; i++) Ke[i] += BtDB[i] * J * E * t * w * w;    /* E carries alpha */
+        } else {
+            matmul(m, ns, ns, Bt, D, BtD);
+            matmul(m, ns, m, BtD, B, BtDB);
+            if (eq == EQ_PLANESTRAIN) for (int i = 0; i < m * m; i++) Ke[i] += BtDB[i] * J * t * w * w;
+            else for (int i = 0; i < m * m; i++) Ke[i] += BtDB[i] * J * w * w * w;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Boundary conditions and numbering.
+ * SetDirichlet   src/FEM/Controller/BoundaryCondition.h:20-25  (mark -1, store value in u)
+ * Renumbering    src/FEM/Controller/Assembling.h:175-186       (node-major, dof-minor running index)
+ * ---------------------------------------------------------------------------------------------------------- */
+int orc_dofmap(int nnode, int ndof, int nfixed, const int* fnode, const int* fdof, const double* fval,
+               int* nodetoglobal, double* ufixed /* nnode*ndof, may be NULL */) {
+    size_t n = (size_t)nnode * ndof;
+    memset(nodetoglobal, 0, n * sizeof(int));
+    if (ufixed) memset(ufixed, 0, n * sizeof(double));
+    for (int i = 0; i < nfixed; i++) {
+        nodetoglobal[(size_t)fnode[i] * ndof + fdof[i]] = -1;
+        if (ufixed) ufixed[(size_t)fnode[i] * ndof + fdof[i]] = fval[i];
+    }
+    int k = 0;
+    for (size_t i = 0; i < n; i++) if (nodetoglobal[i] != -1) nodetoglobal[i] = k++;
+    return k;
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Assembly.
+ * Assembling(K,F,u,Ke,...)  src/FEM/Controller/Assembling.h:47-66  with LILCSR::get/set (LILCSR.h:92-114)
+ * CSR(LILCSR&)              src/LinearAlgebra/Models/CSR.h:93-105  (per-row sort by column)
+ * Assembling(F,q,...)       src/FEM/Controller/Assembling.h:152-158 (nodal loads)
+ * The reference inserts every Ke entry (zeros too) so the pattern is the full element connectivity, and each stored
+ * value is the left-to-right sum over elements in ascending element order starting from T() -- reproduced here by
+ * building the sorted pattern first and then accumulating in element order (same adds, same order, no LIL scans).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int n;          /* KDEGREE */
+    int* indptr;    /* n+1 */
+    int* indices;   /* nnz */
+    double* data;   /* nnz */
+    double* F;      /* n */
+} orc_system;
+
+static int cmp_int(const void* a, const void* b) { int x = *(const int*)a, y = *(const int*)b; return (x > y) - (x < y); }
+
+static int find_col(const orc_system* S, int row, int col) {
+    int lo = S->indptr[row], hi = S->indptr[row + 1] - 1;
+    while (lo <= hi) {
+        int mid = (lo + hi) >> 1;
+        if (S->indices[mid] == col) return mid;
+        if (S->indices[mid] < col) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+}
+
+orc_system* orc_pattern(int nnode, int ndof, int npe, int nelem, const int* conn, const int* nodetoglobal, int kdegree) {
+    /* node -> adjacent nodes (sorted unique), via node -> elements */
+    int* cnt = (int*)calloc((size_t)nnode + 1, sizeof(int));
+    for (size_t i = 0; i < (size_t)nelem * npe; i++) cnt[conn[i] + 1]++;
+    for (int i = 0; i < nnode; i++) cnt[i + 1] += cnt[i];
+    int* n2e = (int*)malloc(sizeof(int) * (size_t)nelem * npe);
+    int* cur = (int*)malloc(sizeof(int) * (size_t)nnode);
+    memcpy(cur, cnt, sizeof(int) * (size_t)nnode);
+    for (int e = 0; e < nelem; e++) for (int a = 0; a < npe; a++) n2e[cur[conn[(size_t)e * npe + a]]++] = e;
+    orc_system* S = (orc_system*)calloc(1, sizeof(orc_system));
+    S->n = kdegree;
+    S->indptr = (int*)calloc((size_t)kdegree + 1, sizeof(int));
+    int maxadj = 0;
+    for (int i = 0; i < nnode; i++) if (cnt[i + 1] - cnt[i] > maxadj) maxadj = cnt[i + 1] - cnt[i];
+    int* tmp = (int*)malloc(sizeof(int) * (size_t)(maxadj * npe + 1));
+    for (int pass = 0; pass < 2; pass++) {
+        for (int i = 0; i < nnode; i++) {
+            int k = 0;
+            for (int q = cnt[i]; q < cnt[i + 1]; q++) for (int a = 0; a < npe; a++) tmp[k++] = conn[(size_t)n2e[q] * npe + a];
+            qsort(tmp, k, sizeof(int), cmp_int);
+            int u = 0;
+            for (int q = 0; q < k; q++) if (q == 0 || tmp[q] != tmp[q - 1]) tmp[u++] = tmp[q];
+            int rowlen = 0;
+            for (int q = 0; q < u; q++) for (int d = 0; d < ndof; d++) if (nodetoglobal[(size_t)tmp[q] * ndof + d] != -1) rowlen++;
+            for (int d = 0; d < ndof; d++) {
+                int r = nodetoglobal[(size_t)i * ndof + d];
+                if (r == -1) continue;
+                if (pass == 0) S->indptr[r + 1] = rowlen;
+                else {
+                    int p = S->indptr[r];
+                    for (int q = 0; q < u; q++) for (int dd = 0; dd < ndof; dd++) {
+                        int c = nodetoglobal[(size_t)tmp[q] * ndof + dd];
+                        if (c != -1) S->indices[p++] = c;
+                    }
+                }
+            }
+        }
+        if (pass == 0) {
+            for (int r = 0; r < kdegree; r++) S->indptr[r + 1] += S->indptr[r];
+            S->indices = (int*)malloc(sizeof(int) * (size_t)S->indptr[kdegree]);
+            S->data = (double*)calloc((size_t)S->indptr[kdegree], sizeof(double));
+            S->F = (double*)calloc((size_t)kdegree, sizeof(double));
+        }
+    }
+    free(tmp); free(cur); free(n2e); free(cnt);
+    return S;
+}
+
+void orc_system_free(orc_system* S) {
+    if (!S) return;
+    free(S->indptr); free(S->indices); free(S->data); free(S->F); free(S);
+}
+int orc_system_rows(const orc_system* S) { return S->n; }
+long long orc_system_nnz(const orc_system* S) { return S->indptr[S->n]; }
+void orc_system_get(const orc_system* S, int* indptr, int* indices, double* data, double* F) {
+    if (indptr) memcpy(indptr, S->indptr, sizeof(int) * ((size_t)S->n + 1));
+    if (indices) memcpy(indices, S->indices, sizeof(int) * (size_t)S->indptr[S->n]);
+    if (data) memcpy(data, S->data, sizeof(double) * (size_t)S->indptr[S->n]);
+    if (F) memcpy(F, S->F, sizeof(double) * (size_t)S->n);
+}
+orc_system* orc_system_from_csr(int n, const int* indptr, const int* indices, const double* data) {
+    orc_system* S = (orc_system*)calloc(1, sizeof(orc_system));
+    S->n = n;
+    S->indptr = (int*)malloc(sizeof(int) * ((size_t)n + 1));
+    memcpy(S->indptr, indptr, sizeof(int) * ((size_t)n + 1));
+    size_t nnz = (size_t)indptr[n];
+    S->indices = (int*)malloc(sizeof(int) * nnz);
+    memcpy(S->indices, indices, sizeof(int) * nnz);
+    S->data = (double*)malloc(sizeof(double) * nnz);
+    memcpy(S->data, data, sizeof(double) * nnz);
+    S->F = (double*)calloc((size_t)n, sizeof(double));
+    return S;
+}
+
+/* numeric assembly into an existing pattern; Emod = per-element modulus; times[2] = {element, scatter} */
+void orc_assemble_numeric(orc_system* S, int eq, const double* coords, int nelem, const int* conn,
+                          const int* nodetoglobal, const double* ufixed, const double* Emod, double V, double t,
+                          int nload, const int* lnode, const int* ldof, const double* lval, double* times) {
+    const int dim = dim_of(eq), npe = (eq == EQ_SOLID) ? 8 : 4, ndof = ndof_of(eq), m = npe * ndof;
+    memset(S->data, 0, sizeof(double) * (size_t)S->indptr[S->n]);
+    memset(S->F, 0, sizeof(double) * (size_t)S->n);
+    double Ke[576], xe[24], te = 0, ts = 0;
+    for (int e = 0; e < nelem; e++) {
+        const int* el = conn + (size_t)e * npe;
+        double t0 = now_s();
+        for (int a = 0; a < npe; a++) for (int d = 0; d < dim; d++) xe[a * dim + d] = coords[(size_t)el[a] * dim + d];
+        orc_element_matrix(eq, xe, Emod[e], V, t, Ke);
+        double t1 = now_s();
+        for (int i = 0; i < npe; i++) for (int di = 0; di < ndof; di++) {
+            int r = nodetoglobal[(size_t)el[i] * ndof + di];
+            if (r == -1) continue;
+            for (int j = 0; j < npe; j++) for (int dj = 0; dj < ndof; dj++) {
+                int c = nodetoglobal[(size_t)el[j] * ndof + dj];
+                double v = Ke[(i * ndof + di) * m + (j * ndof + dj)];
+                if (c != -1) S->data[find_col(S, r, c)] += v;                       /* Assembling.h:55 */
+                else S->F[r] -= v * ufixed[(size_t)el[j] * ndof + dj];               /* Assembling.h:59 */
+            }
+        }
+        double t2 = now_s();
+        te += t1 - t0; ts += t2 - t1;
+    }
+    for (int i = 0; i < nload; i++) {                                                /* Assembling.h:152-158 */
+        int r = nodetoglobal[(size_t)lnode[i] * ndof + ldof[i]];
+        if (r != -1) S->F[r] += lval[i];
+    }
+    if (times) { times[0] = te; times[1] = ts; }
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * CSR<T>::operator*   src/LinearAlgebra/Models/CSR.h:109-122 (the reference's only OpenMP loop)
+ * ---------------------------------------------------------------------------------------------------------- */
+void orc_spmv(const orc_system* S, const double* x, double* y) {
+    const int n = S->n;
+#pragma omp parallel for
+    for (int i = 0; i < n; ++i) {
+        double v = 0.0;
+        for (int j = S->indptr[i], je = S->indptr[i + 1]; j < je; ++j) v += S->data[j] * x[S->indices[j]];
+        y[i] = v;
+    }
+}
+static double dot(int n, const double* a, const double* b) {   /* std::inner_product: serial left-to-right */
+    double s = 0.0;
+    for (int i = 0; i < n; i++) s = s + a[i] * b[i];
+    return s;
+}
+/* CSR::get(i,i) (CSR.h:155-167) -> 0 if the diagonal is structurally absent; GetDiagonal CG.h:398-404 */
+static double diag_of(const orc_system* S, int i) { int p = find_col(S, i, i); return p < 0 ? 0.0 : S->data[p]; }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * ILU0     src/LinearAlgebra/Solvers/CG.h:258-284   (row-wise; unit-L strictly lower + U with diagonal in A's pattern)
+ * PreILU0  src/LinearAlgebra/Solvers/CG.h:289-315
+ * The reference scans k over ALL rows with two binary searches per k; only k in row i's pattern with j in row k's
+ * pattern contribute, in ascending k, until k reaches min(i,j) -- so iterating row i's own column list is the same
+ * sequence of subtractions.
+ * ---------------------------------------------------------------------------------------------------------- */
+orc_system* orc_ilu0(const orc_system* A) {
+    orc_system* M = orc_system_from_csr(A->n, A->indptr, A->indices, A->data);
+    for (int i = 0; i < A->n; i++) {
+        for (int n = A->indptr[i]; n < A->indptr[i + 1]; n++) {
+            int j = A->indices[n];
+            double qij = A->data[n];
+            int lim = (i <= j) ? i : j;
+            for (int q = A->indptr[i]; q < A->indptr[i + 1]; q++) {
+                int k = A->indices[q];
+                if (k >= lim) break;
+                int pkj = find_col(A, k, j);
+                if (pkj >= 0) qij -= M->data[q] * M->data[pkj];
+            }
+            if (i > j) qij /= M->data[find_col(A, j, j)];
+            M->data[n] = qij;
+        }
+    }
+    return M;
+}
+void orc_preilu0(const orc_system* M, const double* b, double* v) {
+    const int n = M->n;
+    if (v != b) memcpy(v, b, sizeof(double) * (size_t)n);
+    for (int i = 0; i < n; i++)
+        for (int k = M->indptr[i]; k < M->indptr[i + 1]; k++) {
+            if (M->indices[k] < i) v[i] -= M->data[k] * v[M->indices[k]]; else break;
+        }
+    for (int i = n - 1; i >= 0; i--) {
+        for (int k = M->indptr[i + 1] - 1; k >= M->indptr[i]; k--) {
+            if (M->indices[k] > i) v[i] -= M->data[k] * v[M->indices[k]]; else break;
+        }
+        v[i] /= diag_of(M, i);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * CG         src/LinearAlgebra/Solvers/CG.h:124-154
+ * ScalingCG  src/LinearAlgebra/Solvers/CG.h:420-453  (Jacobi: GetDiagonal :398, Scaling :409)
+ * ILU0CG     src/LinearAlgebra/Solvers/CG.h:320-352
+ * kind: 0 CG, 1 ScalingCG, 2 ILU0CG (M required).  x0 = 0; stop when ||r||_2 < eps*||b||_2 on the recursively
+ * updated residual; returns the number of iterations performed (k+1 at convergence, itrmax on failure) and the final
+ * ||r||/||b|| in *relres.
+ * ---------------------------------------------------------------------------------------------------------- */
+int orc_solve(const orc_system* A, const orc_system* M, int kind, const double* b, int itrmax, double eps, double* x, double* relres) {
+    const int n = A->n;
+    double* r = (double*)malloc(sizeof(double) * n), *p = (double*)malloc(sizeof(double) * n);
+    double* z = (double*)malloc(sizeof(double) * n), *Ap = (double*)malloc(sizeof(double) * n);
+    double* D = (double*)malloc(sizeof(double) * n);
+    for (int i = 0; i < n; i++) { x[i] = 0.0; D[i] = (kind == 1) ? diag_of(A, i) : 1.0; }
+    orc_spmv(A, x, Ap);
+    for (int i = 0; i < n; i++) r[i] = b[i] - Ap[i];
+    if (kind == 0) memcpy(z, r, sizeof(double) * n);
+    else if (kind == 1) for (int i = 0; i < n; i++) z[i] = r[i] / D[i];
+    else orc_preilu0(M, r, z);
+    memcpy(p, z, sizeof(double) * n);
+    double bnorm = sqrt(dot(n, b, b));
+    double rho = dot(n, z, r);
+    int it = itrmax;
+    double rnorm = sqrt(dot(n, r, r));
+    for (int k = 0; k < itrmax; ++k) {
+        orc_spmv(A, p, Ap);
+        double alpha = rho / dot(n, p, Ap);
+        for (int i = 0; i < n; i++) x[i] = x[i] + alpha * p[i];
+        for (int i = 0; i < n; i++) r[i] = r[i] + (-alpha) * Ap[i];
+        double rho1;
+        if (kind == 0) { rho1 = dot(n, r, r); }
+        else {
+            if (kind == 1) for (int i = 0; i < n; i++) z[i] = r[i] / D[i]; else orc_preilu0(M, r, z);
+            rho1 = dot(n, z, r);
+        }
+        double beta = rho1 / rho;
+        const double* zz = (kind == 0) ? r : z;
+        for (int i = 0; i < n; i++) p[i] = beta * p[i] + zz[i];
+        rho = rho1;
+        rnorm = (kind == 0) ? sqrt(rho) : sqrt(dot(n, r, r));
+        if (rnorm < eps * bnorm) { it = k + 1; break; }
+    }
+    if (relres) *relres = rnorm / bnorm;
+    free(r); free(p); free(z); free(Ap); free(D);
+    return it;
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Filters.
+ * HeavisideFilter::GetFilteredVariables     src/Optimize/Filter/HeavisideFilter.h:61-73
+ * HeavisideFilter::GetFilteredSensitivitis  src/Optimize/Filter/HeavisideFilter.h:77-99
+ * DensityFilter::GetFilteredVariables       src/Optimize/Filter/DensityFilter.h:45-56
+ * DensityFilter::GetFilteredSensitivitis    src/Optimize/Filter/DensityFilter.h:60-71
+ * ---------------------------------------------------------------------------------------------------------- */
+void orc_filter_apply(int kind, int n, const long long* rowptr, const int* nbr, const double* w, double beta,
+                      const double* s, double* rho) {
+    for (int i = 0; i < n; i++) {
+        double wssum = 0.0, wsum = 0.0;
+        for (long long j = rowptr[i]; j < rowptr[i + 1]; j++) { wssum += w[j] * s[nbr[j]]; wsum += w[j]; }
+        if (kind == FILTER_HEAVISIDE) rho[i] = 0.5 * (tanh(0.5 * beta) + tanh(beta * (wssum / wsum - 0.5))) / tanh(0.5 * beta);
+        else rho[i] = wssum / wsum;
+    }
+}
+void orc_filter_sens(int kind, int n, const long long* rowptr, const int* nbr, const double* w, double beta,
+                     const double* s, const double* dfdrho, double* dfds) {
+    double* dr = (double*)malloc(sizeof(double) * n);
+    for (int i = 0; i < n; i++) {
+        if (kind == FILTER_HEAVISIDE) {
+            double wssum = 0.0, wsum = 0.0;
+            for (long long j = rowptr[i]; j < rowptr[i + 1]; j++) { wssum += w[j] * s[nbr[j]]; wsum += w[j]; }
+            dr[i] = 0.5 * beta * (1.0 - pow(tanh(beta * (wssum / wsum - 0.5)), 2.0)) / tanh(0.5 * beta);
+        } else dr[i] = 1.0;
+    }
+    for (int i = 0; i < n; i++) {
+        double acc = 0.0, wsum = 0.0;
+        for (long long j = rowptr[i]; j < rowptr[i + 1]; j++) {
+            if (kind == FILTER_HEAVISIDE) acc += dfdrho[nbr[j]] * dr[nbr[j]] * w[j];
+            else acc += dfdrho[nbr[j]] * w[j];
+            wsum += w[j];
+        }
+        dfds[i] = acc / wsum;       /* normalised by the RECEIVING row's weight sum, as the reference does */
+    }
+    free(dr);
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * OC::UpdateVariables  src/Optimize/Solver/OC.h:78-107, constraint functor of sample_optimize_density_oc.cpp:198-207
+ * (filter + volume).  xk updated in place; returns the number of bisection steps; *lambda_out = last lambda tried.
+ * ---------------------------------------------------------------------------------------------------------- */
+int orc_oc_update(int n, double iota, double lmin, double lmax, double leps, double move,
+                  int fkind, const long long* rowptr, const int* nbr, const double* w, double beta,
+                  double weightlimit, double scale1, double* xk, const double* dfdx, const double* dgdx, double* lambda_out) {
+    double lambda0 = lmin, lambda1 = lmax, lambda = 0.0;
+    double* xkp1 = (double*)calloc(n, sizeof(double)), *rho = (double*)malloc(sizeof(double) * n);
+    int steps = 0;
+    while ((lambda1 - lambda0) / (lambda1 + lambda0) > leps) {
+        lambda = 0.5 * (lambda1 + lambda0);
+        for (int i = 0; i < n; i++) {
+            double v = pow(-dfdx[i] / (dgdx[i] * lambda), iota) * xk[i];
+            double lo = fmax(0.0, (1.0 - move) * xk[i]), hi = fmin(1.0, (1.0 + move) * xk[i]);
+            if (v < lo) v = lo; else if (v > hi) v = hi;
+            xkp1[i] = v;
+        }
+        orc_filter_apply(fkind, n, rowptr, nbr, w, beta, xkp1, rho);
+        double g = 0.0;
+        for (int i = 0; i < n; i++) g += scale1 * rho[i] / (weightlimit * n);
+        g = g - 1.0 * scale1;
+        if (g > 0.0) lambda0 = lambda; else lambda1 = lambda;
+        steps++;
+    }
+    memcpy(xk, xkp1, sizeof(double) * n);
+    if (lambda_out) *lambda_out = lambda;
+    free(xkp1); free(rho);
+    return steps;
+}
+/* OC::IsConvergence OC.h:68-73 == MMA::IsConvergence MMA.h:108-113 */
+int orc_is_convergence(double f, double fprev, double eps) { return fabs(f - fprev) / (f + fprev) < eps; }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * MMA  src/Optimize/Solver/MMA.h:117-419 (UpdateVariables), :423-461 (KKTNorm), :465-509 (solvels)
+ * State (xkm1, xkm2, L, U, k) lives in orc_mma.  General m; the n > m branch (:260-291) and the n <= m branch
+ * (:292-330) are both restated.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int n, m, k;
+    double a0, *a, *c, *d, *xmin, *xmax, *xkm1, *xkm2, *L, *U;
+    double raa0, albefa, move, asyinit, asydecr, asyincr;
+    int newton_steps, halvings;
+} orc_mma;
+
+orc_mma* orc_mma_create(int n, int m, double a0, const double* a, const double* c, const double* d, const double* xmin, const double* xmax) {
+    orc_mma* M = (orc_mma*)calloc(1, sizeof(orc_mma));
+    M->n = n; M->m = m; M->a0 = a0;
+#define DUP(dst, src, cnt) dst = (double*)malloc(sizeof(double) * (cnt)); memcpy(dst, src, sizeof(double) * (cnt))
+    DUP(M->a, a, m); DUP(M->c, c, m); DUP(M->d, d, m); DUP(M->xmin, xmin, n); DUP(M->xmax, xmax, n);
+#undef DUP
+    M->xkm1 = (double*)calloc(n, sizeof(double)); M->xkm2 = (double*)calloc(n, sizeof(double));
+    M->L = (double*)calloc(n, sizeof(double)); M->U = (double*)calloc(n, sizeof(double));
+    M->raa0 = 1.0e-5; M->albefa = 0.1; M->move = 0.5; M->asyinit = 0.5; M->asydecr = 0.7; M->asyincr = 1.2;   /* MMA.h:80-85 */
+    return M;
+}
+void orc_mma_free(orc_mma* M) {
+    if (!M) return;
+    free(M->a); free(M->c); free(M->d); free(M->xmin); free(M->xmax); free(M->xkm1); free(M->xkm2); free(M->L); free(M->U); free(M);
+}
+void orc_mma_setparameters(orc_mma* M, double raa0, double albefa, double move, double asyinit, double asydecr, double asyincr) {
+    M->raa0 = raa0; M->albefa = albefa; M->move = move; M->asyinit = asyinit; M->asydecr = asydecr; M->asyincr = asyincr;
+}
+void orc_mma_stats(const orc_mma* M, int* newton, int* halvings) { *newton = M->newton_steps; *halvings = M->halvings; }
+
+static void solvels(int N, double* A, double* b, double* x) {    /* MMA.h:465-509, A row-major N x N, destroyed */
+    for (int i = 0; i < N - 1; i++) {
+        double pivot = fabs(A[i * N + i]);
+        int pi = i;
+        for (int j = i + 1; j < N; j++) if (pivot < fabs(A[j * N + i])) { pivot = fabs(A[j * N + i]); pi = j; }
+        if (pi != i) {
+            double tmp = b[i]; b[i] = b[pi]; b[pi] = tmp;
+            for (int j = i; j < N; j++) { tmp = A[i * N + j]; A[i * N + j] = A[pi * N + j]; A[pi * N + j] = tmp; }
+        }
+        for (int j = i + 1; j < N; j++) {
+            for (int k = i + 1; k < N; k++) A[j * N + k] -= A[i * N + k] * A[j * N + i] / A[i * N + i];
+            b[j] -= b[i] * A[j * N + i] / A[i * N + i];
+        }
+    }
+    for (int i = N - 1; i >= 0; i--) {
+        x[i] = b[i];
+        for (int j = N - 1; j > i; j--) x[i] -= x[j] * A[i * N + j];
+        x[i] /= A[i * N + i];
+    }
+}
+
+static double kktnorm(const orc_mma* M, const double* x, const double* y, double z, const double* lam, const double* gsi,
+                      const double* ita, const double* mu, double zeta, const double* s, double eps,
+                      const double* p, const double* q, const double* p0, const double* q0, const double* alpha,
+                      const double* beta, const double* b) {
+    const int n = M->n, m = M->m;
+    double norm = 0.0;
+    double* g = (double*)calloc(m, sizeof(double));
+    double* pl = (double*)malloc(sizeof(double) * n), *ql = (double*)malloc(sizeof(double) * n);
+    for (int j = 0; j < n; j++) {
+        pl[j] = p0[j]; ql[j] = q0[j];
+        for (int i = 0; i < m; i++) {
+            pl[j] += lam[i] * p[(size_t)i * n + j];
+            ql[j] += lam[i] * q[(size_t)i * n + j];
+            g[i] += p[(size_t)i * n + j] / (M->U[j] - x[j]) + q[(size_t)i * n + j] / (x[j] - M->L[j]);
+        }
+    }
+    for (int j = 0; j < n; j++) {
+        norm += pow(pl[j] / pow(M->U[j] - x[j], 2.0) - ql[j] / pow(x[j] - M->L[j], 2.0) - gsi[j] + ita[j], 2.0);
+        norm += pow(gsi[j] * (x[j] - alpha[j]) - eps, 2.0);
+        norm += pow(ita[j] * (beta[j] - x[j]) - eps, 2.0);
+    }
+    double la = 0.0;
+    for (int i = 0; i < m; i++) {
+        norm += pow(M->c[i] + M->d[i] * y[i] - lam[i] - mu[i], 2.0);
+        norm += pow(g[i] - M->a[i] * z - y[i] + s[i] - b[i], 2.0);
+        norm += pow(mu[i] * y[i] - eps, 2.0);
+        norm += pow(lam[i] * s[i] - eps, 2.0);
+        la = la + lam[i] * M->a[i];
+    }
+    norm += pow(M->a0 - zeta - la, 2.0);
+    norm += pow(zeta * z - eps, 2.0);
+    free(g); free(pl); free(ql);
+    return sqrt(norm);
+}
+
+static double max2(double a, double b) { return a < b ? b : a; }     /* std::max semantics */
+static double min2(double a, double b) { return b < a ? b : a; }
+
+void orc_mma_update(orc_mma* M, double* xk, const double* dfdx, const double* gval, const double* dgdx /* m x n */) {
+    const int n = M->n, m = M->m;
+    double *L = M->L, *U = M->U;
+    /* asymptotes MMA.h:119-142 */
+    if (M->k < 2) {
+        for (int j = 0; j < n; j++) {
+            double w = M->xmax[j] - M->xmin[j];
+            L[j] = xk[j] - M->asyinit * w; U[j] = xk[j] + M->asyinit * w;
+            L[j] = min2(max2(xk[j] - 10.0 * w, L[j]), xk[j] - 0.01 * w);
+            U[j] = min2(max2(xk[j] + 0.01 * w, U[j]), xk[j] + 10.0 * w);
+        }
+    } else {
+        for (int j = 0; j < n; j++) {
+            double w = M->xmax[j] - M->xmin[j];
+            double tmp = (xk[j] - M->xkm1[j]) * (M->xkm1[j] - M->xkm2[j]);
+            double fac = tmp < 0.0 ? M->asydecr : (tmp > 0.0 ? M->asyincr : 1.0);
+            if (fac != 1.0) {
+                L[j] = xk[j] - fac * (M->xkm1[j] - L[j]); U[j] = xk[j] + fac * (U[j] - M->xkm1[j]);
+            } else {
+                L[j] = xk[j] - (M->xkm1[j] - L[j]); U[j] = xk[j] + (U[j] - M->xkm1[j]);
+            }
+            L[j] = min2(max2(xk[j] - 10.0 * w, L[j]), xk[j] - 0.01 * w);
+            U[j] = min2(max2(xk[j] + 0.01 * w, U[j]), xk[j] + 10.0 * w);
+        }
+    }
+#define VEC(name, cnt) double* name = (double*)calloc((size_t)(cnt), sizeof(double))
+    VEC(alpha, n); VEC(beta, n); VEC(p0, n); VEC(q0, n); VEC(p, (size_t)m * n); VEC(q, (size_t)m * n); VEC(b, m);
+    for (int j = 0; j < n; j++) {   /* MMA.h:145-160 */
+        double w = M->xmax[j] - M->xmin[j];
+        alpha[j] = max2(max2(M->xmin[j], L[j] + M->albefa * (xk[j] - L[j])), xk[j] - M->move * w);
+        beta[j] = min2(min2(M->xmax[j], U[j] - M->albefa * (U[j] - xk[j])), xk[j] + M->move * w);
+        double dp = max2(dfdx[j], 0.0), dm = max2(-dfdx[j], 0.0);
+        p0[j] = pow(U[j] - xk[j], 2.0) * (1.001 * dp + 0.001 * dm + M->raa0 / w);
+        q0[j] = pow(xk[j] - L[j], 2.0) * (0.001 * dp + 1.001 * dm + M->raa0 / w);
+    }
+    for (int i = 0; i < m; i++) {   /* MMA.h:163-175 */
+        b[i] = -gval[i];
+        for (int j = 0; j < n; j++) {
+            double w = M->xmax[j] - M->xmin[j];
+            double dp = max2(dgdx[(size_t)i * n + j], 0.0), dm = max2(-dgdx[(size_t)i * n + j], 0.0);
+            p[(size_t)i * n + j] = pow(U[j] - xk[j], 2.0) * (1.001 * dp + 0.001 * dm + M->raa0 / w);
+            q[(size_t)i * n + j] = pow(xk[j] - L[j], 2.0) * (0.001 * dp + 1.001 * dm + M->raa0 / w);
+            b[i] += p[(size_t)i * n + j] / (U[j] - xk[j]) + q[(size_t)i * n + j] / (xk[j] - L[j]);
+        }
+    }
+    /* initial point MMA.h:178-197 */
+    double eps = 1.0, z = 1.0, zeta = 1.0;
+    VEC(x, n); VEC(y, m); VEC(lam, m); VEC(s, m); VEC(gsi, n); VEC(ita, n); VEC(mu, m);
+    for (int i = 0; i < m; i++) { y[i] = 1.0; lam[i] = 1.0; s[i] = 1.0; mu[i] = max2(1.0, 0.5 * M->c[i]); }
+    for (int j = 0; j < n; j++) {
+        x[j] = 0.5 * (alpha[j] + beta[j]);
+        gsi[j] = max2(1.0, 1.0 / (x[j] - alpha[j]));
+        ita[j] = max2(1.0, 1.0 / (beta[j] - x[j]));
+    }
+    VEC(pl, n); VEC(ql, n); VEC(G, (size_t)m * n); VEC(Dx, n); VEC(dtx, n);
+    VEC(Dy, m); VEC(Dlam, m); VEC(dty, m); VEC(dtlam, m); VEC(Dlamy, m); VEC(dtlamy, m);
+    VEC(dx, n); VEC(dy, m); VEC(dlam, m); VEC(dgsi, n); VEC(dita, n); VEC(dmu, m); VEC(ds, m);
+    VEC(xn, n); VEC(yn, m); VEC(lamn, m); VEC(gsin, n); VEC(itan, n); VEC(mun, m); VEC(sn, m);
+    const int NS = (n > m ? m : n) + 1;
+    VEC(A, (size_t)NS * NS); VEC(B, NS); VEC(sol, NS);
+    M->newton_steps = 0; M->halvings = 0;
+    for (int l = 0; eps > 1.0e-7; l++) {    /* MMA.h:199 */
+        for (int j = 0; j < n; j++) {
+            pl[j] = p0[j]; ql[j] = q0[j];
+            for (int i = 0; i < m; i++) { pl[j] += lam[i] * p[(size_t)i * n + j]; ql[j] += lam[i] * q[(size_t)i * n + j]; }
+        }
+        for (int i = 0; i < m; i++) for (int j = 0; j < n; j++)
+            G[(size_t)i * n + j] = p[(size_t)i * n + j] / pow(U[j] - x[j], 2.0) - q[(size_t)i * n + j] / pow(x[j] - L[j], 2.0);
+        for (int j = 0; j < n; j++) {
+            Dx[j] = 2.0 * pl[j] / pow(U[j] - x[j], 3.0) + 2.0 * ql[j] / pow(x[j] - L[j], 3.0) + gsi[j] / (x[j] - alpha[j]) + ita[j] / (beta[j] - x[j]);
+            dtx[j] = pl[j] / pow(U[j] - x[j], 2.0) - ql[j] / pow(x[j] - L[j], 2.0) - eps / (x[j] - alpha[j]) + eps / (beta[j] - x[j]);
+        }
+        double la = 0.0;
+        for (int i = 0; i < m; i++) {
+            Dy[i] = M->d[i] + mu[i] / y[i];
+            Dlam[i] = s[i] / lam[i];
+            dty[i] = M->c[i] + M->d[i] * y[i] - lam[i] - eps / y[i];
+            la = la + lam[i] * M->a[i];
+        }
+        double dtz = M->a0 - eps / z - la;
+        for (int i = 0; i < m; i++) {
+            dtlam[i] = -M->a[i] * z - y[i] - b[i] + eps / lam[i];
+            for (int j = 0; j < n; j++) dtlam[i] += p[(size_t)i * n + j] / (U[j] - x[j]) + q[(size_t)i * n + j] / (x[j] - L[j]);
+            Dlamy[i] = Dlam[i] + 1.0 / Dy[i];
+            dtlamy[i] = dtlam[i] + dty[i] / Dy[i];
+        }
+        double dz;
+        memset(A, 0, sizeof(double) * (size_t)NS * NS);
+        if (n > m) {   /* MMA.h:260-291 */
+            const int N = m + 1;
+            for (int ii = 0; ii < m; ii++) {
+                for (int jj = 0; jj < m; jj++) for (int kk = 0; kk < n; kk++) A[ii * N + jj] += G[(size_t)ii * n + kk] * G[(size_t)jj * n + kk] / Dx[kk];
+                A[ii * N + ii] += Dlamy[ii];
+                A[ii * N + m] = M->a[ii];
+                A[m * N + ii] = M->a[ii];
+            }
+            A[m * N + m] = -zeta / z;
+            for (int ii = 0; ii < m; ii++) {
+                B[ii] = dtlamy[ii];
+                for (int jj = 0; jj < n; jj++) B[ii] -= G[(size_t)ii * n + jj] * dtx[jj] / Dx[jj];
+            }
+            B[m] = dtz;
+            solvels(N, A, B, sol);
+            for (int i = 0; i < m; i++) dlam[i] = sol[i];
+            dz = sol[m];
+            for (int j = 0; j < n; j++) {
+                dx[j] = -dtx[j] / Dx[j];
+                for (int i = 0; i < m; i++) dx[j] -= G[(size_t)i * n + j] * dlam[i] / Dx[j];
+            }
+        } else {       /* MMA.h:292-330 */
+            const int N = n + 1;
+            for (int ii = 0; ii < n; ii++) {
+                for (int jj = 0; jj < n; jj++) for (int kk = 0; kk < m; kk++) A[ii * N + jj] += G[(size_t)kk * n + ii] * G[(size_t)kk * n + jj] / Dlamy[kk];
+                A[ii * N + ii] += Dx[ii];
+                for (int jj = 0; jj < m; jj++) {
+                    A[ii * N + n] -= G[(size_t)jj * n + ii] * M->a[jj] / Dlamy[jj];
+                    A[n * N + ii] -= G[(size_t)jj * n + ii] * M->a[jj] / Dlamy[jj];
+                    A[n * N + n] += M->a[jj] * M->a[jj] / Dlamy[jj];
+                }
+            }
+            A[n * N + n] += zeta / z;
+            for (int ii = 0; ii < n; ii++) {
+                B[ii] = -dtx[ii];
+                for (int jj = 0; jj < m; jj++) B[ii] -= G[(size_t)jj * n + ii] * dtlamy[jj] / Dlamy[jj];
+            }
+            B[n] = -dtz;
+            for (int jj = 0; jj < m; jj++) B[n] += M->a[jj] * dtlamy[jj] / Dlamy[jj];
+            solvels(N, A, B, sol);
+            for (int j = 0; j < n; j++) dx[j] = sol[j];
+            dz = sol[n];
+            for (int i = 0; i < m; i++) {
+                dlam[i] = -M->a[i] * dz / Dlamy[i] + dtlamy[i] / Dlamy[i];
+                for (int j = 0; j < n; j++) dlam[i] += G[(size_t)i * n + j] * dx[j] / Dlamy[i];
+            }
+        }
+        for (int i = 0; i < m; i++) {   /* MMA.h:332-336 */
+            dy[i] = dlam[i] / Dy[i] - dty[i] / Dy[i];
+            dmu[i] = -mu[i] * dy[i] / y[i] - mu[i] + eps / y[i];
+            ds[i] = -s[i] * dlam[i] / lam[i] - s[i] + eps / lam[i];
+        }
+        for (int j = 0; j < n; j++) {
+            dgsi[j] = -gsi[j] * dx[j] / (x[j] - alpha[j]) - gsi[j] + eps / (x[j] - alpha[j]);
+            dita[j] = ita[j] * dx[j] / (beta[j] - x[j]) - ita[j] + eps / (beta[j] - x[j]);
+        }
+        double dzeta = -zeta * dz / z - zeta + eps / z;
+        double txmax = 0.0;             /* MMA.h:346-360 */
+        for (int j = 0; j < n; j++) {
+            double t = max2(max2(-1.01 * dx[j] / (x[j] - alpha[j]), 1.01 * dx[j] / (beta[j] - x[j])), max2(-1.01 * dgsi[j] / gsi[j], -1.01 * dita[j] / ita[j]));
+            if (txmax < t) txmax = t;
+        }
+        double tymax = 0.0;
+        for (int i = 0; i < m; i++) {
+            double t = max2(max2(-1.01 * dy[i] / y[i], -1.01 * dlam[i] / lam[i]), max2(-1.01 * dmu[i] / mu[i], -1.01 * ds[i] / s[i]));
+            if (tymax < t) tymax = t;
+        }
+        double tau = 1.0 / max2(max2(max2(1.0, txmax), max2(tymax, -1.01 * dz / z)), -1.01 * dzeta / zeta);
+        double dwl = kktnorm(M, x, y, z, lam, gsi, ita, mu, zeta, s, eps, p, q, p0, q0, alpha, beta, b);
+        double zn = z, zetan = zeta, dwl1 = 0.0;
+        for (int ll = 0; ll < 50; ll++) {   /* MMA.h:371-391 */
+            for (int j = 0; j < n; j++) { xn[j] = x[j] + tau * dx[j]; gsin[j] = gsi[j] + tau * dgsi[j]; itan[j] = ita[j] + tau * dita[j]; }
+            for (int i = 0; i < m; i++) { yn[i] = y[i] + tau * dy[i]; lamn[i] = lam[i] + tau * dlam[i]; mun[i] = mu[i] + tau * dmu[i]; sn[i] = s[i] + tau * ds[i]; }
+            zn = z + tau * dz; zetan = zeta + tau * dzeta;
+            dwl1 = kktnorm(M, xn, yn, zn, lamn, gsin, itan, mun, zetan, sn, eps, p, q, p0, q0, alpha, beta, b);
+            if (dwl1 < dwl) break;
+            tau *= 0.5;
+            M->halvings++;
+        }
+        memcpy(x, xn, sizeof(double) * n); memcpy(gsi, gsin, sizeof(double) * n); memcpy(ita, itan, sizeof(double) * n);
+        memcpy(y, yn, sizeof(double) * m); memcpy(lam, lamn, sizeof(double) * m); memcpy(mu, mun, sizeof(double) * m); memcpy(s, sn, sizeof(double) * m);
+        z = zn; zeta = zetan;
+        M->newton_steps++;
+        /* MMA.h:405-410: KKTNorm(accepted point) is the value just computed for the accepted trial */
+        if (dwl1 < 0.9 * eps) eps *= 0.1;
+    }
+    M->k++;                                     /* MMA.h:414-418 */
+    memcpy(M->xkm2, M->xkm1, sizeof(double) * n);
+    memcpy(M->xkm1, xk, sizeof(double) * n);
+    memcpy(xk, x, sizeof(double) * n);
+    free(alpha); free(beta); free(p0); free(q0); free(p); free(q); free(b);
+    free(x); free(y); free(lam); free(s); free(gsi); free(ita); free(mu);
+    free(pl); free(ql); free(G); free(Dx); free(dtx); free(Dy); free(Dlam); free(dty); free(dtlam); free(Dlamy); free(dtlamy);
+    free(dx); free(dy); free(dlam); free(dgsi); free(dita); free(dmu); free(ds);
+    free(xn); free(yn); free(lamn); free(gsin); free(itan); free(mun); free(sn); free(A); free(B); free(sol);
+#undef VEC
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Reaction / compliance / sensitivity passes of the drivers:
+ *   sample/optimize/sample_optimize_density_oc.cpp:136-162  (General.h:82-96 ElementVector, Assembling.h:119,163)
+ * r = K_full(rho) u by element scatter in element order; f = scale0 * sum_nodes u_n . r_n (inner_product of
+ * Vector<T>, i.e. per-node dot then serial sum); dfdrho_i = -scale0 p (E1-E0) rho_i^(p-1) ue^T Ke(E=1) ue.
+ * ---------------------------------------------------------------------------------------------------------- */
+double orc_compliance_sens(int eq, int nnode, const double* coords, int nelem, const int* conn, const double* u /* nnode*ndof */,
+                           const double* rho, double E0, double E1, double V, double t, double p, double scale0,
+                           double* r_out /* nnode*ndof */, double* dfdrho) {
+    const int dim = dim_of(eq), npe = (eq == EQ_SOLID) ? 8 : 4, ndof = ndof_of(eq), m = npe * ndof;
+    double Ke[576], xe[24], ue[24], Keue[24];
+    memset(r_out, 0, sizeof(double) * (size_t)nnode * ndof);
+    for (int e = 0; e < nelem; e++) {
+        const int* el = conn + (size_t)e * npe;
+        for (int a = 0; a < npe; a++) for (int d = 0; d < dim; d++) xe[a * dim + d] = coords[(size_t)el[a] * dim + d];
+        for (int a = 0; a < npe; a++) for (int d = 0; d < ndof; d++) ue[a * ndof + d] = u[(size_t)el[a] * ndof + d];
+        double E = E1 * pow(rho[e], p) + E0 * (1.0 - pow(rho[e], p));
+        orc_element_matrix(eq, xe, E, V, t, Ke);
+        for (int i = 0; i < m; i++) { double v = 0.0; for (int j = 0; j < m; j++) v += Ke[i * m + j] * ue[j]; Keue[i] = v; }
+        for (int a = 0; a < npe; a++) for (int d = 0; d < ndof; d++) r_out[(size_t)el[a] * ndof + d] += Keue[a * ndof + d];
+        if (dfdrho) {
+            orc_element_matrix(eq, xe, 1.0, V, t, Ke);
+            for (int i = 0; i < m; i++) { double v = 0.0; for (int j = 0; j < m; j++) v += Ke[i * m + j] * ue[j]; Keue[i] = v; }
+            double w = 0.0;
+            for (int i = 0; i < m; i++) w += ue[i] * Keue[i];
+            dfdrho[e] = -scale0 * p * (-E0 + E1) * pow(rho[e], p - 1.0) * w;
+        }
+    }
+    double f = 0.0;
+    for (int i = 0; i < nnode; i++) {
+        double d = 0.0;
+        for (int k = 0; k < ndof; k++) d += u[(size_t)i * ndof + k] * r_out[(size_t)i * ndof + k];
+        f = f + d;
+    }
+    return scale0 * f;
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * The SIMP design loop  sample/optimize/sample_optimize_density_oc.cpp:83-208 / ..._mma.cpp:83-204
+ * params / optp / outputs exactly as ref_simp_run in oracle/ref_shim.cpp; hist[5*k] = {f, g, seconds, converged, cg_iters}.
+ * phase[8] = {filter, assembly, (unused), solve, reaction+sensitivity, (unused), filter-sens, update}.
+ * ---------------------------------------------------------------------------------------------------------- */
+int orc_simp_run(int eq, int nnode, const double* coords, int nelem, const int* conn,
+                 int nfixed, const int* fnode, const int* fdof, const double* fval,
+                 int nload, const int* lnode, const int* ldof, const double* lval,
+                 int fkind, const long long* rowptr, const int* nbr, const double* w,
+                 int opt_kind, const double* optp, const double* params, int niter, int check_convergence,
+                 double* s, double* rho, double* u_out, double* r_out, double* hist, double* phase) {
+    const int npe = (eq == EQ_SOLID) ? 8 : 4, ndof = ndof_of(eq);
+    const double E0 = params[0], E1 = params[1], V = params[2], p = params[3], weightlimit = params[4];
+    const double scale0 = params[5], scale1 = params[6], thick = params[7];
+    double beta = params[8];
+    const int beta_period = (int)params[9], itrmax = (int)params[10];
+    const double cgeps = params[11];
+    const size_t nd = (size_t)nnode * ndof;
+    int* n2g = (int*)malloc(sizeof(int) * nd);
+    double* ufix = (double*)malloc(sizeof(double) * nd);
+    int kdeg = orc_dofmap(nnode, ndof, nfixed, fnode, fdof, fval, n2g, ufix);
+    orc_system* S = orc_pattern(nnode, ndof, npe, nelem, conn, n2g, kdeg);
+    double* Emod = (double*)malloc(sizeof(double) * nelem), *sol = (double*)malloc(sizeof(double) * kdeg);
+    double* dfdrho = (double*)malloc(sizeof(double) * nelem), *dgdrho = (double*)malloc(sizeof(double) * nelem);
+    double* dfds = (double*)malloc(sizeof(double) * nelem), *dgds = (double*)malloc(sizeof(double) * nelem);
+    double* u = (double*)malloc(sizeof(double) * nd);
+    orc_mma* mma = NULL;
+    double fprev = 0.0, epsvalue = 1.0e-5;   /* OC.h:49-50 */
+    if (opt_kind == OPT_MMA) {
+        double* xmin = (double*)malloc(sizeof(double) * nelem), *xmax = (double*)malloc(sizeof(double) * nelem);
+        for (int i = 0; i < nelem; i++) { xmin[i] = optp[11]; xmax[i] = optp[12]; }
+        mma = orc_mma_create(nelem, 1, optp[7], &optp[8], &optp[9], &optp[10], xmin, xmax);
+        orc_mma_setparameters(mma, optp[0], optp[1], optp[2], optp[3], optp[4], optp[5]);
+        epsvalue = optp[6];
+        free(xmin); free(xmax);
+    }
+    if (phase) memset(phase, 0, sizeof(double) * 8);
+    int k = 0;
+    for (; k < niter; k++) {
+        double tstart = now_s(), t0 = tstart, t1;
+        if (beta_period > 0 && k % beta_period == 0) beta *= 2.0;
+        orc_filter_apply(fkind, nelem, rowptr, nbr, w, beta, s, rho);
+        double g = 0.0;
+        for (int i = 0; i < nelem; i++) { g += scale1 * rho[i] / (weightlimit * nelem); dgdrho[i] = scale1 / (weightlimit * nelem); }
+        g -= 1.0 * scale1;
+        t1 = now_s(); if (phase) phase[0] += t1 - t0; t0 = t1;
+        for (int i = 0; i < nelem; i++) Emod[i] = E1 * pow(rho[i], p) + E0 * (1.0 - pow(rho[i], p));
+        orc_assemble_numeric(S, eq, coords, nelem, conn, n2g, ufix, Emod, V, thick, nload, lnode, ldof, lval, NULL);
+        t1 = now_s(); if (phase) phase[1] += t1 - t0; t0 = t1;
+        double relres;
+        int its = orc_solve(S, NULL, 1, S->F, itrmax, cgeps, sol, &relres);
+        for (size_t i = 0; i < nd; i++) u[i] = (n2g[i] != -1) ? sol[n2g[i]] : ufix[i];   /* Disassembling Assembling.h:163 */
+        t1 = now_s(); if (phase) phase[3] += t1 - t0; t0 = t1;
+        double f = orc_compliance_sens(eq, nnode, coords, nelem, conn, u, rho, E0, E1, V, thick, p, scale0, r_out, dfdrho);
+        t1 = now_s(); if (phase) phase[4] += t1 - t0; t0 = t1;
+        orc_filter_sens(fkind, nelem, rowptr, nbr, w, beta, s, dfdrho, dfds);
+        orc_filter_sens(fkind, nelem, rowptr, nbr, w, beta, s, dgdrho, dgds);
+        t1 = now_s(); if (phase) phase[6] += t1 - t0; t0 = t1;
+        hist[5 * k + 0] = f; hist[5 * k + 1] = g; hist[5 * k + 3] = 0; hist[5 * k + 4] = its;
+        if (check_convergence && orc_is_convergence(f, fprev, epsvalue)) {
+            hist[5 * k + 2] = now_s() - tstart; hist[5 * k + 3] = 1;
+            k++;
+            break;
+        }
+        if (opt_kind == OPT_OC) {
+            orc_oc_update(nelem, optp[0], optp[1], optp[2], optp[3], optp[4], fkind, rowptr, nbr, w, beta, weightlimit, scale1, s, dfds, dgds, NULL);
+        } else {
+            orc_mma_update(mma, s, dfds, &g, dgds);
+        }
+        fprev = f;
+        t1 = now_s(); if (phase) phase[7] += t1 - t0;
+        hist[5 * k + 2] = now_s() - tstart;
+    }
+    if (u_out) memcpy(u_out, u, sizeof(double) * nd);
+    orc_system_free(S); orc_mma_free(mma);
+    free(n2g); free(ufix); free(Emod); free(sol); free(dfdrho); free(dgdrho); free(dfds); free(dgds); free(u);
+    return k;
+}

@@ -1,0 +1,477 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into, imported by or executed from the product path.
+//
+// oracle/ref_shim.cpp : a thin extern "C" shim around the UNMODIFIED reference headers.
+// It #includes the headers where they lie under /root/reference/src (path given with
+// -I at build time, see oracle/Makefile); no reference source is copied into this repo.
+// The shared object it builds (oracle/_ref/libpf2ref.so) is used
+//   * by tests/ as the live oracle for the CUDA path and for the C restatement
+//     (oracle/pf2_oracle.c),
+//   * by bench.py's cpu_baseline / --impl reference legs as the timed CPU reference.
+//
+// Every entry point names the reference routine it drives (file:line relative to
+// /root/reference).
+
+// CSR<T>/LILCSR<T> keep indptr/indices/data private (src/LinearAlgebra/Models/CSR.h:72-74);
+// the shim must read them to hand fixtures to the tests.
+#include <vector>
+#include <utility>
+#include <algorithm>
+#include <numeric>
+#include <cmath>
+#include <cstring>
+#include <cstdio>
+#include <chrono>
+#include <iostream>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <cassert>
+#include <omp.h>
+#define private public
+#include "LinearAlgebra/Models/Vector.h"
+#include "LinearAlgebra/Models/Matrix.h"
+#include "LinearAlgebra/Models/LILCSR.h"
+#include "LinearAlgebra/Models/CSR.h"
+#undef private
+#include "LinearAlgebra/Solvers/CG.h"
+#include "FEM/Equation/PlaneStrain.h"
+#include "FEM/Equation/Solid.h"
+#include "FEM/Equation/HeatTransfer.h"
+#include "FEM/Equation/General.h"
+#include "FEM/Controller/ShapeFunction.h"
+#include "FEM/Controller/GaussIntegration.h"
+#include "FEM/Controller/BoundaryCondition.h"
+#include "FEM/Controller/Assembling.h"
+#include "Optimize/Solver/OC.h"
+#include "Optimize/Solver/MMA.h"
+#include "Optimize/Filter/HeavisideFilter.h"
+#include "Optimize/Filter/DensityFilter.h"
+#include "PrePost/Mesher/SquareMesh.h"
+
+using namespace PANSFEM2;
+
+namespace {
+
+enum { EQ_PLANESTRAIN = 0, EQ_SOLID = 1, EQ_HEAT = 2 };
+enum { FILTER_DENSITY = 0, FILTER_HEAVISIDE = 1 };
+enum { OPT_OC = 0, OPT_MMA = 1 };
+
+double now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// silence the reference's std::cout chatter (OC.h:101 prints lambda, CG.h:147 prints iterations)
+struct Quiet {
+    std::streambuf* old;
+    std::ostringstream sink;
+    Quiet() : old(std::cout.rdbuf(sink.rdbuf())) {}
+    ~Quiet() { std::cout.rdbuf(old); }
+};
+
+int ndof_of(int eq) { return eq == EQ_PLANESTRAIN ? 2 : (eq == EQ_SOLID ? 3 : 1); }
+
+// One element matrix through the reference's own template selection
+// (PlaneStrain.h:21, Solid.h:21, HeatTransfer.h:20 with ShapeFunction4Square/8Cubic + Gauss4Square/8Cubic).
+void element_matrix(int eq, Matrix<double>& Ke, std::vector<std::vector<std::pair<int, int> > >& n2e,
+                    const std::vector<int>& element, std::vector<Vector<double> >& x, double E, double V, double t) {
+    if (eq == EQ_PLANESTRAIN) {
+        PlaneStrainStiffness<double, ShapeFunction4Square, Gauss4Square>(Ke, n2e, element, { 0, 1 }, x, E, V, t);
+    } else if (eq == EQ_SOLID) {
+        SolidLinearIsotropicElastic<double, ShapeFunction8Cubic, Gauss8Cubic>(Ke, n2e, element, { 0, 1, 2 }, x, E, V);
+    } else {
+        HeatTransfer<double, ShapeFunction4Square, Gauss4Square>(Ke, n2e, element, { 0 }, x, E, t);
+    }
+}
+
+std::vector<Vector<double> > make_nodes(int dim, int nnode, const double* coords) {
+    std::vector<Vector<double> > x(nnode);
+    for (int i = 0; i < nnode; i++) {
+        std::vector<double> c(coords + (size_t)dim * i, coords + (size_t)dim * (i + 1));
+        x[i] = Vector<double>(c);
+    }
+    return x;
+}
+
+std::vector<std::vector<int> > make_elements(int npe, int nelem, const int* conn) {
+    std::vector<std::vector<int> > e(nelem);
+    for (int i = 0; i < nelem; i++) e[i] = std::vector<int>(conn + (size_t)npe * i, conn + (size_t)npe * (i + 1));
+    return e;
+}
+
+typedef std::vector<std::pair<std::pair<int, int>, double> > BCList;
+BCList make_bc(int n, const int* node, const int* dof, const double* val) {
+    BCList l(n);
+    for (int i = 0; i < n; i++) l[i] = { { node[i], dof[i] }, val[i] };
+    return l;
+}
+
+struct RefSystem {
+    CSR<double>* K = nullptr;
+    std::vector<double> F;
+    std::vector<std::vector<int> > nodetoglobal;
+    ~RefSystem() { delete K; }
+};
+
+struct RefFilter {
+    int kind;
+    int n;
+    HeavisideFilter<double>* h = nullptr;
+    DensityFilter<double>* d = nullptr;
+    ~RefFilter() { delete h; delete d; }
+    std::vector<double> apply(double beta, const std::vector<double>& s) {
+        if (kind == FILTER_HEAVISIDE) { h->UpdateBeta(beta); return h->GetFilteredVariables(s); }
+        return d->GetFilteredVariables(s);
+    }
+    std::vector<double> sens(double beta, const std::vector<double>& s, const std::vector<double>& dfdrho) {
+        if (kind == FILTER_HEAVISIDE) { h->UpdateBeta(beta); return h->GetFilteredSensitivitis(s, dfdrho); }
+        return d->GetFilteredSensitivitis(s, dfdrho);
+    }
+};
+
+RefFilter* make_filter(int kind, int n, const long long* rowptr, const int* nbr, const double* w) {
+    std::vector<std::vector<int> > neighbors(n);
+    std::vector<std::vector<double> > ww(n);
+    for (int i = 0; i < n; i++) {
+        neighbors[i].assign(nbr + rowptr[i], nbr + rowptr[i + 1]);
+        ww[i].assign(w + rowptr[i], w + rowptr[i + 1]);
+    }
+    RefFilter* f = new RefFilter();
+    f->kind = kind; f->n = n;
+    if (kind == FILTER_HEAVISIDE) f->h = new HeavisideFilter<double>(n, neighbors, ww);
+    else f->d = new DensityFilter<double>(n, neighbors, ww);
+    return f;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ref_num_threads() { return omp_get_max_threads(); }
+void ref_set_num_threads(int n) { omp_set_num_threads(n); }
+
+// ---- element routines: PlaneStrain.h:21-58 / Solid.h:21-64 / HeatTransfer.h:20-43 ----
+// xe: npe*dim coordinates of the element's nodes; Ke_out: (npe*ndof)^2 row-major.
+int ref_element_matrix(int eq, int dim, int npe, const double* xe, double E, double V, double t, double* Ke_out) {
+    std::vector<Vector<double> > x = make_nodes(dim, npe, xe);
+    std::vector<int> element(npe);
+    std::iota(element.begin(), element.end(), 0);
+    Matrix<double> Ke;
+    std::vector<std::vector<std::pair<int, int> > > n2e;
+    element_matrix(eq, Ke, n2e, element, x, E, V, t);
+    int m = npe * ndof_of(eq);
+    for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) Ke_out[i * m + j] = Ke(i, j);
+    return m;
+}
+
+// ---- SetDirichlet (BoundaryCondition.h:20) + Renumbering (Assembling.h:175) + element loop with
+//      Assembling (Assembling.h:47-66) + nodal loads (Assembling.h:152) + CSR(LILCSR&) (CSR.h:93-105) ----
+// Emod: per-element modulus (already SIMP-interpolated by the caller); times[3] = {element, assembling, tocsr}.
+void* ref_assemble(int eq, int dim, int nnode, const double* coords, int npe, int nelem, const int* conn,
+                   int nfixed, const int* fnode, const int* fdof, const double* fval,
+                   int nload, const int* lnode, const int* ldof, const double* lval,
+                   const double* Emod, double V, double t, double* times) {
+    int ndof = ndof_of(eq);
+    std::vector<Vector<double> > x = make_nodes(dim, nnode, coords);
+    std::vector<std::vector<int> > elements = make_elements(npe, nelem, conn);
+    BCList ufixed = make_bc(nfixed, fnode, fdof, fval), qfixed = make_bc(nload, lnode, ldof, lval);
+
+    RefSystem* sys = new RefSystem();
+    std::vector<Vector<double> > u(nnode, Vector<double>(ndof));
+    sys->nodetoglobal = std::vector<std::vector<int> >(nnode, std::vector<int>(ndof, 0));
+    SetDirichlet(u, sys->nodetoglobal, ufixed);
+    int KDEGREE = Renumbering(sys->nodetoglobal);
+    LILCSR<double> K(KDEGREE, KDEGREE);
+    sys->F = std::vector<double>(KDEGREE, 0.0);
+    double te = 0, ta = 0;
+    for (int i = 0; i < nelem; i++) {
+        std::vector<std::vector<std::pair<int, int> > > n2e;
+        Matrix<double> Ke;
+        double t0 = now();
+        element_matrix(eq, Ke, n2e, elements[i], x, Emod[i], V, t);
+        double t1 = now();
+        Assembling(K, sys->F, u, Ke, sys->nodetoglobal, n2e, elements[i]);
+        double t2 = now();
+        te += t1 - t0; ta += t2 - t1;
+    }
+    Assembling(sys->F, qfixed, sys->nodetoglobal);
+    double t3 = now();
+    sys->K = new CSR<double>(K);
+    double t4 = now();
+    if (times) { times[0] = te; times[1] = ta; times[2] = t4 - t3; }
+    return sys;
+}
+
+void* ref_system_from_csr(int n, const int* indptr, const int* indices, const double* data) {
+    RefSystem* sys = new RefSystem();
+    sys->K = new CSR<double>(n, n);
+    sys->K->indptr.assign(indptr, indptr + n + 1);
+    sys->K->indices.assign(indices, indices + indptr[n]);
+    sys->K->data.assign(data, data + indptr[n]);
+    sys->F.assign(n, 0.0);
+    return sys;
+}
+void ref_system_free(void* h) { delete (RefSystem*)h; }
+int ref_system_rows(void* h) { return ((RefSystem*)h)->K->ROWS; }
+long long ref_system_nnz(void* h) { return (long long)((RefSystem*)h)->K->data.size(); }
+void ref_system_get(void* h, int* indptr, int* indices, double* data, double* F) {
+    RefSystem* s = (RefSystem*)h;
+    if (indptr) std::copy(s->K->indptr.begin(), s->K->indptr.end(), indptr);
+    if (indices) std::copy(s->K->indices.begin(), s->K->indices.end(), indices);
+    if (data) std::copy(s->K->data.begin(), s->K->data.end(), data);
+    if (F) std::copy(s->F.begin(), s->F.end(), F);
+}
+void ref_system_nodetoglobal(void* h, int* out) {
+    RefSystem* s = (RefSystem*)h;
+    size_t k = 0;
+    for (auto& n : s->nodetoglobal) for (int d : n) out[k++] = d;
+}
+
+// ---- CSR<T>::operator* (CSR.h:109-122) ----
+void ref_spmv(void* h, const double* x, double* y, int repeat, double* seconds) {
+    RefSystem* s = (RefSystem*)h;
+    std::vector<double> xv(x, x + s->K->COLS), yv;
+    double t0 = now();
+    for (int r = 0; r < (repeat > 0 ? repeat : 1); r++) yv = (*s->K) * xv;
+    double t1 = now();
+    if (seconds) *seconds = (t1 - t0) / (repeat > 0 ? repeat : 1);
+    std::copy(yv.begin(), yv.end(), y);
+}
+
+// ---- CG (CG.h:124-154), ScalingCG (CG.h:420-453), ILU0 (CG.h:258-284), PreILU0 (:289-315), ILU0CG (:320-352) ----
+// kind: 0 = CG, 1 = ScalingCG, 2 = ILU0CG (factor computed here, timed separately in seconds[1]).
+void ref_solve(void* h, int kind, const double* b, int itrmax, double eps, double* x, double* seconds) {
+    RefSystem* s = (RefSystem*)h;
+    Quiet q;
+    std::vector<double> bv(b, b + s->K->ROWS), xv;
+    double t0 = now(), tf = 0;
+    if (kind == 0) xv = CG(*s->K, bv, itrmax, eps);
+    else if (kind == 1) xv = ScalingCG(*s->K, bv, itrmax, eps);
+    else {
+        CSR<double> M = ILU0(*s->K);
+        tf = now() - t0;
+        t0 = now();
+        xv = ILU0CG(*s->K, M, bv, itrmax, eps);
+    }
+    double t1 = now();
+    if (seconds) { seconds[0] = t1 - t0; seconds[1] = tf; }
+    std::copy(xv.begin(), xv.end(), x);
+}
+void* ref_ilu0(void* h) {
+    RefSystem* s = (RefSystem*)h;
+    RefSystem* m = new RefSystem();
+    m->K = new CSR<double>(ILU0(*s->K));
+    m->F.assign(s->K->ROWS, 0.0);
+    return m;
+}
+void ref_preilu0(void* hM, const double* b, double* x) {
+    RefSystem* m = (RefSystem*)hM;
+    std::vector<double> bv(b, b + m->K->ROWS);
+    std::vector<double> xv = PreILU0(*m->K, bv);
+    std::copy(xv.begin(), xv.end(), x);
+}
+
+// ---- filters: HeavisideFilter.h:61-99, DensityFilter.h:45-71 ----
+void* ref_filter_create(int kind, int n, const long long* rowptr, const int* nbr, const double* w) {
+    return make_filter(kind, n, rowptr, nbr, w);
+}
+void ref_filter_free(void* h) { delete (RefFilter*)h; }
+void ref_filter_apply(void* h, double beta, const double* s, double* rho) {
+    RefFilter* f = (RefFilter*)h;
+    std::vector<double> r = f->apply(beta, std::vector<double>(s, s + f->n));
+    std::copy(r.begin(), r.end(), rho);
+}
+void ref_filter_sens(void* h, double beta, const double* s, const double* dfdrho, double* dfds) {
+    RefFilter* f = (RefFilter*)h;
+    std::vector<double> r = f->sens(beta, std::vector<double>(s, s + f->n), std::vector<double>(dfdrho, dfdrho + f->n));
+    std::copy(r.begin(), r.end(), dfds);
+}
+
+// ---- OC (OC.h:46-107) with the sample's constraint functor (sample_optimize_density_oc.cpp:198-207) ----
+void* ref_oc_create(int n, double iota, double lmin, double lmax, double leps, double move) {
+    return new OC<double>(n, iota, lmin, lmax, leps, move, std::vector<double>(n, 0.01), std::vector<double>(n, 1.0));
+}
+void ref_oc_free(void* h) { delete (OC<double>*)h; }
+int ref_oc_isconvergence(void* h, double f) { return ((OC<double>*)h)->IsConvergence(f) ? 1 : 0; }
+void ref_oc_update(void* h, void* hfilter, double beta, double weightlimit, double scale1, int n, double* s,
+                   double f, const double* dfds, double g, const double* dgds) {
+    Quiet q;
+    OC<double>* oc = (OC<double>*)h;
+    RefFilter* filter = (RefFilter*)hfilter;
+    std::vector<double> sv(s, s + n);
+    oc->UpdateVariables(sv, f, std::vector<double>(dfds, dfds + n), g, std::vector<double>(dgds, dgds + n),
+        [&](std::vector<double> _xkp1) {
+            double gg = 0.0;
+            std::vector<double> rho = filter->apply(beta, _xkp1);
+            for (int i = 0; i < n; i++) gg += scale1 * rho[i] / (weightlimit * n);
+            return gg - 1.0 * scale1;
+        });
+    std::copy(sv.begin(), sv.end(), s);
+}
+
+// ---- MMA (MMA.h:64-419) ----
+void* ref_mma_create(int n, int m, double a0, const double* a, const double* c, const double* d,
+                     const double* xmin, const double* xmax) {
+    return new MMA<double>(n, m, a0, std::vector<double>(a, a + m), std::vector<double>(c, c + m),
+                           std::vector<double>(d, d + m), std::vector<double>(xmin, xmin + n),
+                           std::vector<double>(xmax, xmax + n));
+}
+void ref_mma_free(void* h) { delete (MMA<double>*)h; }
+void ref_mma_setparameters(void* h, double raa0, double albefa, double move, double asyinit, double asydecr,
+                           double asyincr, double epsvalue) {
+    ((MMA<double>*)h)->SetParameters(raa0, albefa, move, asyinit, asydecr, asyincr, epsvalue);
+}
+int ref_mma_isconvergence(void* h, double f) { return ((MMA<double>*)h)->IsConvergence(f) ? 1 : 0; }
+void ref_mma_update(void* h, int n, int m, double* x, double f, const double* dfdx, const double* g, const double* dgdx) {
+    std::vector<double> xv(x, x + n);
+    std::vector<std::vector<double> > dg(m);
+    for (int i = 0; i < m; i++) dg[i].assign(dgdx + (size_t)i * n, dgdx + (size_t)(i + 1) * n);
+    ((MMA<double>*)h)->UpdateVariables(xv, f, std::vector<double>(dfdx, dfdx + n), std::vector<double>(g, g + m), dg);
+    std::copy(xv.begin(), xv.end(), x);
+}
+
+// ---- the SIMP design loop of sample/optimize/sample_optimize_density_{oc,mma}.cpp:83-208 on a caller-supplied
+//      mesh (so the same driver serves plane strain Q4, heat Q4 and solid hex8).  The loop body follows the
+//      sample line by line; only VTK output is dropped and timings added.
+// params: [0]=E0 [1]=E1 [2]=V [3]=p [4]=weightlimit [5]=scale0 [6]=scale1 [7]=thickness [8]=beta0
+//         [9]=beta_period (design iterations between beta doublings; <=0: never) [10]=cg itrmax [11]=cg eps
+// oc: [iota,lmin,lmax,leps,move]; mma: [raa0,albefa,move,asyinit,asydecr,asyincr,epsvalue,a0,a,c,d,xmin,xmax]
+// outputs: s (in/out, nelem), rho (nelem), u (nnode*ndof), r (nnode*ndof), hist[4*niter] = {f, g, seconds, converged}
+//          phase[8] accumulates {filter, element+assembling, tocsr, solve, reaction, sensitivity, filter-sens, update}
+// returns the number of design iterations performed (the converged iteration counts, as in the sample).
+int ref_simp_run(int eq, int dim, int nnode, const double* coords, int npe, int nelem, const int* conn,
+                 int nfixed, const int* fnode, const int* fdof, const double* fval,
+                 int nload, const int* lnode, const int* ldof, const double* lval,
+                 int filter_kind, const long long* rowptr, const int* nbr, const double* w,
+                 int opt_kind, const double* optp, const double* params, int niter, int check_convergence,
+                 double* s_io, double* rho_out, double* u_out, double* r_out, double* hist, double* phase) {
+    Quiet q;
+    int ndof = ndof_of(eq);
+    std::vector<Vector<double> > x = make_nodes(dim, nnode, coords);
+    std::vector<std::vector<int> > elements = make_elements(npe, nelem, conn);
+    BCList ufixed = make_bc(nfixed, fnode, fdof, fval), qfixed = make_bc(nload, lnode, ldof, lval);
+    RefFilter* filter = make_filter(filter_kind, nelem, rowptr, nbr, w);
+    std::vector<double> s(s_io, s_io + nelem);
+
+    double E0 = params[0], E1 = params[1], Poisson = params[2], p = params[3], weightlimit = params[4];
+    double scale0 = params[5], scale1 = params[6], thick = params[7], beta = params[8];
+    int beta_period = (int)params[9];
+    int itrmax = (int)params[10];
+    double cgeps = params[11];
+
+    OC<double>* oc = nullptr;
+    MMA<double>* mma = nullptr;
+    if (opt_kind == OPT_OC) {
+        oc = new OC<double>(nelem, optp[0], optp[1], optp[2], optp[3], optp[4], std::vector<double>(nelem, 0.01), std::vector<double>(nelem, 1.0));
+    } else {
+        mma = new MMA<double>(nelem, 1, optp[7], std::vector<double>(1, optp[8]), std::vector<double>(1, optp[9]),
+                              std::vector<double>(1, optp[10]), std::vector<double>(nelem, optp[11]), std::vector<double>(nelem, optp[12]));
+        mma->SetParameters(optp[0], optp[1], optp[2], optp[3], optp[4], optp[5], optp[6]);
+    }
+    if (phase) for (int i = 0; i < 8; i++) phase[i] = 0;
+
+    int k = 0;
+    std::vector<double> rho;
+    std::vector<Vector<double> > u, r;
+    for (; k < niter; k++) {
+        double tstart = now(), t0 = tstart, t1;
+        if (beta_period > 0 && k % beta_period == 0) beta *= 2.0;
+        rho = filter->apply(beta, s);
+        double g = 0.0;
+        std::vector<double> dgdrho(nelem, 0.0);
+        for (int i = 0; i < nelem; i++) {
+            g += scale1 * rho[i] / (weightlimit * nelem);
+            dgdrho[i] = scale1 / (weightlimit * nelem);
+        }
+        g -= 1.0 * scale1;
+        t1 = now(); if (phase) phase[0] += t1 - t0; t0 = t1;
+
+        u = std::vector<Vector<double> >(nnode, Vector<double>(ndof));
+        std::vector<std::vector<int> > nodetoglobal(nnode, std::vector<int>(ndof, 0));
+        SetDirichlet(u, nodetoglobal, ufixed);
+        int KDEGREE = Renumbering(nodetoglobal);
+        LILCSR<double> K(KDEGREE, KDEGREE);
+        std::vector<double> F(KDEGREE, 0.0);
+        for (int i = 0; i < nelem; i++) {
+            double E = E1 * pow(rho[i], p) + E0 * (1.0 - pow(rho[i], p));
+            std::vector<std::vector<std::pair<int, int> > > n2e;
+            Matrix<double> Ke;
+            element_matrix(eq, Ke, n2e, elements[i], x, E, Poisson, thick);
+            Assembling(K, F, u, Ke, nodetoglobal, n2e, elements[i]);
+        }
+        Assembling(F, qfixed, nodetoglobal);
+        t1 = now(); if (phase) phase[1] += t1 - t0; t0 = t1;
+        CSR<double> Kmod(K);
+        t1 = now(); if (phase) phase[2] += t1 - t0; t0 = t1;
+        std::vector<double> result = ScalingCG(Kmod, F, itrmax, cgeps);
+        Disassembling(u, result, nodetoglobal);
+        t1 = now(); if (phase) phase[3] += t1 - t0; t0 = t1;
+
+        RemoveBoundaryConditions(nodetoglobal);
+        KDEGREE = Renumbering(nodetoglobal);
+        std::vector<double> RF(KDEGREE, 0.0);
+        r = std::vector<Vector<double> >(nnode, Vector<double>(ndof));
+        for (int i = 0; i < nelem; i++) {
+            double E = E1 * pow(rho[i], p) + E0 * (1.0 - pow(rho[i], p));
+            std::vector<std::vector<std::pair<int, int> > > n2e;
+            Matrix<double> Ke;
+            element_matrix(eq, Ke, n2e, elements[i], x, E, Poisson, thick);
+            Vector<double> Keue = Ke * ElementVector(u, n2e, elements[i]);
+            Assembling(RF, Keue, nodetoglobal, n2e, elements[i]);
+        }
+        Disassembling(r, RF, nodetoglobal);
+        double f = scale0 * std::inner_product(u.begin(), u.end(), r.begin(), 0.0);
+        t1 = now(); if (phase) phase[4] += t1 - t0; t0 = t1;
+
+        std::vector<double> dfdrho(nelem, 0.0);
+        for (int i = 0; i < nelem; i++) {
+            std::vector<std::vector<std::pair<int, int> > > n2e;
+            Matrix<double> Ke;
+            element_matrix(eq, Ke, n2e, elements[i], x, 1.0, Poisson, thick);
+            Vector<double> ue = ElementVector(u, n2e, elements[i]);
+            dfdrho[i] = -scale0 * p * (-E0 + E1) * pow(rho[i], p - 1.0) * (ue * (Ke * ue));
+        }
+        t1 = now(); if (phase) phase[5] += t1 - t0; t0 = t1;
+        std::vector<double> dfds = filter->sens(beta, s, dfdrho);
+        std::vector<double> dgds = filter->sens(beta, s, dgdrho);
+        t1 = now(); if (phase) phase[6] += t1 - t0; t0 = t1;
+
+        hist[4 * k + 0] = f; hist[4 * k + 1] = g; hist[4 * k + 3] = 0;
+        bool conv = oc ? oc->IsConvergence(f) : mma->IsConvergence(f);
+        if (check_convergence && conv) {
+            hist[4 * k + 2] = now() - tstart; hist[4 * k + 3] = 1;
+            k++;
+            break;
+        }
+        if (oc) {
+            oc->UpdateVariables(s, f, dfds, g, dgds, [&](std::vector<double> _xkp1) {
+                double gg = 0.0;
+                std::vector<double> rr = filter->apply(beta, _xkp1);
+                for (int i = 0; i < nelem; i++) gg += scale1 * rr[i] / (weightlimit * nelem);
+                return gg - 1.0 * scale1;
+            });
+        } else {
+            mma->UpdateVariables(s, f, dfds, { g }, { dgds });
+        }
+        t1 = now(); if (phase) phase[7] += t1 - t0;
+        hist[4 * k + 2] = now() - tstart;
+    }
+    std::copy(s.begin(), s.end(), s_io);
+    if (rho_out) std::copy(rho.begin(), rho.end(), rho_out);
+    for (int i = 0; i < nnode; i++) for (int d = 0; d < ndof; d++) {
+        if (u_out) u_out[(size_t)i * ndof + d] = u[i](d);
+        if (r_out) r_out[(size_t)i * ndof + d] = r[i](d);
+    }
+    delete filter; delete oc; delete mma;
+    return k;
+}
+
+// ---- SquareMesh<T> (SquareMesh.h:62-207): numbering fixture for the product mesher ----
+void ref_squaremesh(double lx, double ly, int nx, int ny, double* coords, int* conn) {
+    SquareMesh<double> mesh(lx, ly, nx, ny);
+    std::vector<Vector<double> > x = mesh.GenerateNodes();
+    std::vector<std::vector<int> > e = mesh.GenerateElements();
+    for (size_t i = 0; i < x.size(); i++) { coords[2 * i] = x[i](0); coords[2 * i + 1] = x[i](1); }
+    for (size_t i = 0; i < e.size(); i++) for (int j = 0; j < 4; j++) conn[4 * i + j] = e[i][j];
+}
+
+}  // extern "C"

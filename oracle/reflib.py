@@ -1,0 +1,261 @@
+"""TEST INFRASTRUCTURE ONLY.  ctypes binding of oracle/_ref/libpf2ref.so (the UNMODIFIED reference headers behind
+an extern "C" shim, oracle/ref_shim.cpp).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module; the product path (pansfem2_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libpf2ref.so")
+
+EQ_PLANESTRAIN, EQ_SOLID, EQ_HEAT = 0, 1, 2
+FILTER_DENSITY, FILTER_HEAVISIDE = 0, 1
+OPT_OC, OPT_MMA = 0, 1
+NDOF = {EQ_PLANESTRAIN: 2, EQ_SOLID: 3, EQ_HEAT: 1}
+
+_lib = None
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError(f"{LIB_PATH} missing: run `make -C oracle ref` where /root/reference exists")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.ref_assemble.restype = C.c_void_p
+        _lib.ref_system_from_csr.restype = C.c_void_p
+        _lib.ref_ilu0.restype = C.c_void_p
+        _lib.ref_filter_create.restype = C.c_void_p
+        _lib.ref_oc_create.restype = C.c_void_p
+        _lib.ref_mma_create.restype = C.c_void_p
+        _lib.ref_system_nnz.restype = C.c_longlong
+    return _lib
+
+
+def _p(a, dtype):
+    if a is None:
+        return None
+    assert a.dtype == dtype and a.flags["C_CONTIGUOUS"], (a.dtype, dtype)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def num_threads() -> int:
+    return lib().ref_num_threads()
+
+
+def set_num_threads(n: int):
+    lib().ref_set_num_threads(int(n))
+
+
+def element_matrix(eq, xe, E, V=0.3, t=1.0):
+    xe = _f64(xe)
+    npe, dim = xe.shape
+    m = npe * NDOF[eq]
+    Ke = np.zeros((m, m))
+    lib().ref_element_matrix(eq, dim, npe, _p(xe, np.float64), C.c_double(E), C.c_double(V), C.c_double(t), _p(Ke, np.float64))
+    return Ke
+
+
+class System:
+    """Reference CSR<double> + F held on the C++ side."""
+
+    def __init__(self, handle):
+        self.h = C.c_void_p(handle)
+        self.times = None
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.ref_system_free(self.h)
+            self.h = None
+
+    @property
+    def rows(self):
+        return lib().ref_system_rows(self.h)
+
+    @property
+    def nnz(self):
+        return lib().ref_system_nnz(self.h)
+
+    def arrays(self):
+        n, nnz = self.rows, self.nnz
+        indptr = np.zeros(n + 1, np.int32)
+        indices = np.zeros(nnz, np.int32)
+        data = np.zeros(nnz)
+        F = np.zeros(n)
+        lib().ref_system_get(self.h, _p(indptr, np.int32), _p(indices, np.int32), _p(data, np.float64), _p(F, np.float64))
+        return indptr, indices, data, F
+
+    def nodetoglobal(self, nnode, ndof):
+        out = np.zeros((nnode, ndof), np.int32)
+        lib().ref_system_nodetoglobal(self.h, _p(out, np.int32))
+        return out
+
+    def spmv(self, x, repeat=1):
+        x = _f64(x)
+        y = np.zeros(self.rows)
+        sec = C.c_double(0)
+        lib().ref_spmv(self.h, _p(x, np.float64), _p(y, np.float64), repeat, C.byref(sec))
+        return y, sec.value
+
+    def solve(self, kind, b, itrmax=100000, eps=1e-10):
+        """kind: 0 CG, 1 ScalingCG, 2 ILU0CG.  Returns (x, seconds_solve, seconds_factor)."""
+        b = _f64(b)
+        x = np.zeros(self.rows)
+        sec = (C.c_double * 2)()
+        lib().ref_solve(self.h, kind, _p(b, np.float64), itrmax, C.c_double(eps), _p(x, np.float64), sec)
+        return x, sec[0], sec[1]
+
+    def ilu0(self):
+        return System(lib().ref_ilu0(self.h))
+
+    def preilu0(self, b):
+        b = _f64(b)
+        x = np.zeros(self.rows)
+        lib().ref_preilu0(self.h, _p(b, np.float64), _p(x, np.float64))
+        return x
+
+
+def system_from_csr(indptr, indices, data):
+    indptr, indices, data = _i32(indptr), _i32(indices), _f64(data)
+    return System(lib().ref_system_from_csr(len(indptr) - 1, _p(indptr, np.int32), _p(indices, np.int32), _p(data, np.float64)))
+
+
+def assemble(eq, coords, conn, fixed, loads, Emod, V=0.3, t=1.0):
+    coords, conn = _f64(coords), _i32(conn)
+    fn, fd, fv = _i32(fixed[0]), _i32(fixed[1]), _f64(fixed[2])
+    ln, ld, lv = _i32(loads[0]), _i32(loads[1]), _f64(loads[2])
+    Emod = _f64(Emod)
+    times = (C.c_double * 3)()
+    h = lib().ref_assemble(eq, coords.shape[1], coords.shape[0], _p(coords, np.float64), conn.shape[1], conn.shape[0],
+                           _p(conn, np.int32), len(fn), _p(fn, np.int32), _p(fd, np.int32), _p(fv, np.float64),
+                           len(ln), _p(ln, np.int32), _p(ld, np.int32), _p(lv, np.float64),
+                           _p(Emod, np.float64), C.c_double(V), C.c_double(t), times)
+    s = System(h)
+    s.times = {"element": times[0], "assembling": times[1], "tocsr": times[2]}
+    return s
+
+
+class Filter:
+    def __init__(self, kind, rowptr, nbr, w):
+        self.rowptr, self.nbr, self.w = _i64(rowptr), _i32(nbr), _f64(w)
+        self.n = len(self.rowptr) - 1
+        self.kind = kind
+        self.h = C.c_void_p(lib().ref_filter_create(kind, self.n, _p(self.rowptr, np.int64), _p(self.nbr, np.int32), _p(self.w, np.float64)))
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.ref_filter_free(self.h)
+            self.h = None
+
+    def apply(self, beta, s):
+        s = _f64(s)
+        rho = np.zeros(self.n)
+        lib().ref_filter_apply(self.h, C.c_double(beta), _p(s, np.float64), _p(rho, np.float64))
+        return rho
+
+    def sens(self, beta, s, dfdrho):
+        s, dfdrho = _f64(s), _f64(dfdrho)
+        out = np.zeros(self.n)
+        lib().ref_filter_sens(self.h, C.c_double(beta), _p(s, np.float64), _p(dfdrho, np.float64), _p(out, np.float64))
+        return out
+
+
+class OC:
+    def __init__(self, n, iota, lmin, lmax, leps, move):
+        self.n = n
+        self.h = C.c_void_p(lib().ref_oc_create(n, C.c_double(iota), C.c_double(lmin), C.c_double(lmax), C.c_double(leps), C.c_double(move)))
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.ref_oc_free(self.h)
+            self.h = None
+
+    def is_convergence(self, f):
+        return bool(lib().ref_oc_isconvergence(self.h, C.c_double(f)))
+
+    def update(self, filt: Filter, beta, weightlimit, scale1, s, f, dfds, g, dgds):
+        s = _f64(s).copy()
+        dfds, dgds = _f64(dfds), _f64(dgds)
+        lib().ref_oc_update(self.h, filt.h, C.c_double(beta), C.c_double(weightlimit), C.c_double(scale1), self.n,
+                            _p(s, np.float64), C.c_double(f), _p(dfds, np.float64), C.c_double(g), _p(dgds, np.float64))
+        return s
+
+
+class MMA:
+    def __init__(self, n, m, a0, a, c, d, xmin, xmax):
+        self.n, self.m = n, m
+        a, c, d = _f64(a), _f64(c), _f64(d)
+        xmin = _f64(np.broadcast_to(xmin, (n,)))
+        xmax = _f64(np.broadcast_to(xmax, (n,)))
+        self.h = C.c_void_p(lib().ref_mma_create(n, m, C.c_double(a0), _p(a, np.float64), _p(c, np.float64), _p(d, np.float64),
+                                                 _p(xmin, np.float64), _p(xmax, np.float64)))
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.ref_mma_free(self.h)
+            self.h = None
+
+    def set_parameters(self, raa0, albefa, move, asyinit, asydecr, asyincr, epsvalue):
+        lib().ref_mma_setparameters(self.h, *[C.c_double(v) for v in (raa0, albefa, move, asyinit, asydecr, asyincr, epsvalue)])
+
+    def is_convergence(self, f):
+        return bool(lib().ref_mma_isconvergence(self.h, C.c_double(f)))
+
+    def update(self, x, f, dfdx, g, dgdx):
+        x = _f64(x).copy()
+        dfdx, g, dgdx = _f64(dfdx), _f64(g), _f64(dgdx)
+        lib().ref_mma_update(self.h, self.n, self.m, _p(x, np.float64), C.c_double(f), _p(dfdx, np.float64), _p(g, np.float64), _p(dgdx, np.float64))
+        return x
+
+
+def simp_run(eq, coords, conn, fixed, loads, filter_kind, nbrs, opt_kind, optp, params, niter, s0, check_convergence=True):
+    """Drive ref_simp_run (the sample's design loop).  Returns dict(s, rho, u, r, hist, phase, iters)."""
+    coords, conn = _f64(coords), _i32(conn)
+    nnode, dim = coords.shape
+    nelem, npe = conn.shape
+    ndof = NDOF[eq]
+    fn, fd, fv = _i32(fixed[0]), _i32(fixed[1]), _f64(fixed[2])
+    ln, ld, lv = _i32(loads[0]), _i32(loads[1]), _f64(loads[2])
+    rowptr, nbr, w = _i64(nbrs[0]), _i32(nbrs[1]), _f64(nbrs[2])
+    optp, params = _f64(optp), _f64(params)
+    s = _f64(s0).copy()
+    rho = np.zeros(nelem)
+    u = np.zeros((nnode, ndof))
+    r = np.zeros((nnode, ndof))
+    hist = np.zeros((niter, 4))
+    phase = np.zeros(8)
+    it = lib().ref_simp_run(eq, dim, nnode, _p(coords, np.float64), npe, nelem, _p(conn, np.int32),
+                            len(fn), _p(fn, np.int32), _p(fd, np.int32), _p(fv, np.float64),
+                            len(ln), _p(ln, np.int32), _p(ld, np.int32), _p(lv, np.float64),
+                            filter_kind, _p(rowptr, np.int64), _p(nbr, np.int32), _p(w, np.float64),
+                            opt_kind, _p(optp, np.float64), _p(params, np.float64), niter, int(check_convergence),
+                            _p(s, np.float64), _p(rho, np.float64), _p(u, np.float64), _p(r, np.float64),
+                            _p(hist, np.float64), _p(phase, np.float64))
+    return dict(s=s, rho=rho, u=u, r=r, hist=hist[:it], phase=phase, iters=it)
+
+
+def squaremesh(lx, ly, nx, ny):
+    coords = np.zeros(((nx + 1) * (ny + 1), 2))
+    conn = np.zeros((nx * ny, 4), np.int32)
+    lib().ref_squaremesh(C.c_double(lx), C.c_double(ly), nx, ny, _p(coords, np.float64), _p(conn, np.int32))
+    return coords, conn

@@ -1,0 +1,112 @@
+"""Synthetic structured problems for the SIMP hot path.  Host-side set-up only.
+
+``cantilever2d`` is the problem of /root/reference/sample/optimize/sample_optimize_density_oc.cpp:24-80 at any
+resolution (C1 = 60x40 exactly as shipped, C2 = 2000x1000, the 2M-dof headline = 1000x1000);
+``heat2d`` is config 3, ``cantilever3d`` configs 4-5 (our x-major hex mesher).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import mesher
+
+EQ_PLANESTRAIN, EQ_SOLID, EQ_HEAT = 0, 1, 2
+FILTER_DENSITY, FILTER_HEAVISIDE = 0, 1
+OPT_OC, OPT_MMA = 0, 1
+NDOF = {EQ_PLANESTRAIN: 2, EQ_SOLID: 3, EQ_HEAT: 1}
+
+
+@dataclass
+class Problem:
+    name: str
+    eq: int
+    coords: np.ndarray          # nnode x dim
+    conn: np.ndarray            # nelem x npe (int32)
+    fixed: tuple                # (node, dof, value)
+    loads: tuple                # (node, dof, value)
+    nbrs: tuple                 # filter neighbour lists (rowptr int64, nbr int32, w f64)
+    grid: tuple                 # element counts per axis
+    filter_kind: int = FILTER_HEAVISIDE
+    opt_kind: int = OPT_OC
+    # sample_optimize_density_oc.cpp:69-78
+    E0: float = 1.0e-4
+    E1: float = 2.1e5
+    poisson: float = 0.3
+    penal: float = 3.0
+    weightlimit: float = 0.5
+    scale0: float = 1.0e5
+    scale1: float = 1.0
+    thickness: float = 1.0
+    beta0: float = 0.5
+    beta_period: int = 40
+    cg_itrmax: int = 100000
+    cg_eps: float = 1.0e-10
+    # OC(n, 0.5, 0, 1e4, 1e-3, 0.15, ...) sample_optimize_density_oc.cpp:80
+    oc: tuple = (0.5, 0.0, 1.0e4, 1.0e-3, 0.15)
+    # MMA(n,1,a0=1,a={0},c={1e4},d={0},xmin=.01,xmax=1) + SetParameters(1e-5,.1,.2,.5,.7,1.2,1e-6)  ..._mma.cpp:80-85
+    mma: tuple = (1.0e-5, 0.1, 0.2, 0.5, 0.7, 1.2, 1.0e-6, 1.0, 0.0, 1.0e4, 0.0, 0.01, 1.0)
+    s0: float = 0.5
+    extra: dict = field(default_factory=dict)
+
+    @property
+    def ndof(self):
+        return NDOF[self.eq]
+
+    @property
+    def nnode(self):
+        return self.coords.shape[0]
+
+    @property
+    def nelem(self):
+        return self.conn.shape[0]
+
+    def params(self):
+        return np.array([self.E0, self.E1, self.poisson, self.penal, self.weightlimit, self.scale0, self.scale1,
+                         self.thickness, self.beta0, float(self.beta_period), float(self.cg_itrmax), self.cg_eps])
+
+    def optp(self):
+        return np.array(self.oc if self.opt_kind == OPT_OC else self.mma, dtype=np.float64)
+
+    def free_dofs(self):
+        return self.nnode * self.ndof - len(self.fixed[0])
+
+
+def cantilever2d(nx=60, ny=40, opt_kind=OPT_OC, filter_kind=FILTER_HEAVISIDE, radius=1.5) -> Problem:
+    lx, ly = float(nx), float(ny)
+    coords, conn = mesher.square_mesh(lx, ly, nx, ny)
+    fixed = mesher.fixed_list(coords, [0, 1], lambda x: np.abs(x[:, 0]) < 1.0e-5)
+    ln, ld, lv = mesher.fixed_list(coords, [1], lambda x: (np.abs(x[:, 0] - lx) < 1.0e-5) & (np.abs(x[:, 1] - ly / 2) < 1.0e-5), -1.0)
+    nbrs = mesher.filter_neighbors_2d(nx, ny, lx, ly, radius)
+    return Problem(f"cantilever2d_{nx}x{ny}", EQ_PLANESTRAIN, coords, conn, fixed, (ln, ld, lv), nbrs, (nx, ny),
+                   filter_kind=filter_kind, opt_kind=opt_kind)
+
+
+def heat2d(nx=64, ny=64, opt_kind=OPT_OC, filter_kind=FILTER_DENSITY, radius=1.5) -> Problem:
+    """Config 3: Q4 heat conduction, k(rho) = k0 + (k1-k0) rho^p, sink on the middle 10% of the left edge,
+    uniform nodal heat load 1/nnode on all free nodes, volume fraction 0.4."""
+    lx, ly = float(nx), float(ny)
+    coords, conn = mesher.square_mesh(lx, ly, nx, ny)
+    fixed = mesher.fixed_list(coords, [0], lambda x: (np.abs(x[:, 0]) < 1.0e-5) & (np.abs(x[:, 1] - ly / 2) <= 0.05 * ly + 1.0e-9))
+    nnode = coords.shape[0]
+    is_fixed = np.zeros(nnode, bool)
+    is_fixed[fixed[0]] = True
+    ln = np.nonzero(~is_fixed)[0].astype(np.int32)
+    loads = (ln, np.zeros_like(ln), np.full(ln.shape, 1.0 / nnode))
+    nbrs = mesher.filter_neighbors_2d(nx, ny, lx, ly, radius)
+    return Problem(f"heat2d_{nx}x{ny}", EQ_HEAT, coords, conn, fixed, loads, nbrs, (nx, ny),
+                   filter_kind=filter_kind, opt_kind=opt_kind, E0=1.0e-3, E1=1.0, weightlimit=0.4, scale0=1.0,
+                   beta_period=0)
+
+
+def cantilever3d(nx=16, ny=8, nz=8, opt_kind=OPT_OC, filter_kind=FILTER_DENSITY, radius=1.5) -> Problem:
+    """Configs 4-5: hex8 cantilever, clamp the x=0 face (3 dofs), unit -y load spread over the line x=lx, y=ly/2."""
+    lx, ly, lz = float(nx), float(ny), float(nz)
+    coords, conn = mesher.box_mesh(lx, ly, lz, nx, ny, nz)
+    fixed = mesher.fixed_list(coords, [0, 1, 2], lambda x: np.abs(x[:, 0]) < 1.0e-5)
+    sel = lambda x: (np.abs(x[:, 0] - lx) < 1.0e-5) & (np.abs(x[:, 1] - ly / 2) < 1.0e-5)
+    ln, ld, lv = mesher.fixed_list(coords, [1], sel, -1.0 / (nz + 1))
+    nbrs = mesher.filter_neighbors_3d(nx, ny, nz, lx, ly, lz, radius)
+    return Problem(f"cantilever3d_{nx}x{ny}x{nz}", EQ_SOLID, coords, conn, fixed, (ln, ld, lv), nbrs, (nx, ny, nz),
+                   filter_kind=filter_kind, opt_kind=opt_kind, beta_period=0)

@@ -1,0 +1,161 @@
+"""Generate tests/golden/*.npz from the reference tree (run in the build container where /root/reference exists):
+
+    python tests/golden/make_golden.py
+
+Sources (all under /root/reference, nothing is copied verbatim - values are parsed into arrays):
+  * sample/optimize/Density_OC.vtk  / Density_MMA.vtk : committed final-iteration outputs of
+    sample_optimize_density_{oc,mma}.cpp (VECTORS u, VECTORS r, SCALARS s = filtered rho), 6 significant digits.
+  * sample/solid/result_linear.vtk + {Node,Element,Dirichlet,Neumann}.csv : hex8 50x5x5 cantilever solved by
+    sample/solid/sample_linear.cpp (SolidLinearIsotropicElastic + ScalingCG).
+  * src/Optimize/Solver/test_MMA.cpp, test_MMA_3.cpp, test_MMA_TOY2.cpp : the print-only known-answer mains are
+    compiled UNMODIFIED and their stdout parsed (iterates per outer iteration).
+  * live reference (oracle/_ref/libpf2ref.so): unit-element matrices, C1 iteration history, a 12x8 system's CSR,
+    ILU0 factors and solver outputs - the fixtures the GPU box checks the C restatement against.
+"""
+from __future__ import annotations
+
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+from oracle import reflib  # noqa: E402
+from pansfem2_b200 import problems  # noqa: E402
+
+
+def parse_vtk_fields(path):
+    lines = open(path).read().split("\n")
+    out, i = {}, 0
+    while i < len(lines):
+        ln = lines[i]
+        if ln.startswith("VECTORS") or ln.startswith("SCALARS"):
+            name = ln.split()[1]
+            i += 1 if ln.startswith("VECTORS") else 2
+            rows = []
+            while i < len(lines) and lines[i].strip() and not lines[i][0].isalpha():
+                rows.append([float(v) for v in lines[i].split()])
+                i += 1
+            out[name] = np.array(rows).squeeze()
+            continue
+        i += 1
+    return out
+
+
+def csv_rows(path):
+    rows = [r.strip().split(",") for r in open(path).read().strip().split("\n")[1:]]
+    return rows
+
+
+def golden_simp():
+    for tag in ("OC", "MMA"):
+        f = parse_vtk_fields(f"{REF}/sample/optimize/Density_{tag}.vtk")
+        np.savez_compressed(f"{OUT}/density_{tag.lower()}.npz", u=f["u"][:, :2], r=f["r"][:, :2], rho=f["s"])
+        print(tag, {k: v.shape for k, v in f.items()})
+
+
+def golden_solid():
+    nodes = np.array([[float(v) for v in r[1:4]] for r in csv_rows(f"{REF}/sample/solid/Node.csv")])
+    elems = np.array([[int(v) for v in r[1:9]] for r in csv_rows(f"{REF}/sample/solid/Element.csv")], dtype=np.int32)
+    fn, fd, fv = [], [], []
+    for r in csv_rows(f"{REF}/sample/solid/Dirichlet.csv"):
+        for d, tok in enumerate(r[1:4]):
+            if tok != "free":
+                fn.append(int(r[0])); fd.append(d); fv.append(float(tok))
+    ln, ld, lv = [], [], []
+    for r in csv_rows(f"{REF}/sample/solid/Neumann.csv"):
+        for d, tok in enumerate(r[1:4]):
+            if tok != "free":
+                ln.append(int(r[0])); ld.append(d); lv.append(float(tok))
+    f = parse_vtk_fields(f"{REF}/sample/solid/result_linear.vtk")
+    np.savez_compressed(f"{OUT}/solid_linear.npz", coords=nodes, conn=elems,
+                        fix_node=np.array(fn, np.int32), fix_dof=np.array(fd, np.int32), fix_val=np.array(fv),
+                        load_node=np.array(ln, np.int32), load_dof=np.array(ld, np.int32), load_val=np.array(lv),
+                        u=f["u"])
+    print("solid", nodes.shape, elems.shape, len(fn), len(ln), np.abs(f["u"]).max())
+
+
+def golden_mma_kat():
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for name in ("test_MMA", "test_MMA_3", "test_MMA_TOY2"):
+            exe = os.path.join(tmp, name)
+            subprocess.run(["g++", "-O3", "-fopenmp", f"{REF}/src/Optimize/Solver/{name}.cpp", "-o", exe], check=True)
+            txt = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+            rows = []
+            for ln in txt.split("\n"):
+                if ln.startswith("k ="):
+                    nums = [float(v) for v in re.findall(r"[-+]?\d*\.?\d+(?:[eE][-+]?\d+)?", ln)]
+                    rows.append(nums)
+            width = max(len(r) for r in rows)
+            out[name] = np.array([r for r in rows if len(r) == width])
+            print(name, out[name].shape, out[name][-1])
+    np.savez_compressed(f"{OUT}/mma_kat.npz", **out)
+
+
+def golden_live():
+    """Fixtures produced by the live reference so the GPU box (no /root/reference) can still pin the C restatement."""
+    reflib.set_num_threads(1)
+    d = {}
+    # unit elements and a distorted one each
+    q4 = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], float)
+    q4d = np.array([[0.1, -0.2], [1.3, 0.1], [1.1, 1.4], [-0.2, 0.9]], float)
+    h8 = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    rng = np.random.default_rng(20201017)
+    h8d = h8 * np.array([1.3, 0.8, 1.1]) + 0.15 * rng.uniform(-1, 1, h8.shape)
+    d["q4"], d["q4d"], d["h8"], d["h8d"] = q4, q4d, h8, h8d
+    d["ke_ps_q4"] = reflib.element_matrix(reflib.EQ_PLANESTRAIN, q4, 1.0, 0.3, 1.0)
+    d["ke_ps_q4d"] = reflib.element_matrix(reflib.EQ_PLANESTRAIN, q4d, 2.5, 0.3, 0.7)
+    d["ke_heat_q4"] = reflib.element_matrix(reflib.EQ_HEAT, q4, 1.0, 0.0, 1.0)
+    d["ke_heat_q4d"] = reflib.element_matrix(reflib.EQ_HEAT, q4d, 2.5, 0.0, 0.7)
+    d["ke_solid_h8"] = reflib.element_matrix(reflib.EQ_SOLID, h8, 1.0, 0.3, 1.0)
+    d["ke_solid_h8d"] = reflib.element_matrix(reflib.EQ_SOLID, h8d, 2.5, 0.3, 1.0)
+    # small plane-strain system with a non-zero Dirichlet value (exercises the F lift, Assembling.h:59)
+    P = problems.cantilever2d(12, 8)
+    fixed = (P.fixed[0], P.fixed[1], np.where(P.fixed[1] == 0, 0.01, -0.02))
+    Emod = rng.uniform(0.5, 2.0, P.nelem)
+    S = reflib.assemble(P.eq, P.coords, P.conn, fixed, P.loads, Emod)
+    indptr, indices, data, F = S.arrays()
+    d.update(sys_Emod=Emod, sys_fixval=fixed[2], sys_indptr=indptr, sys_indices=indices, sys_data=data, sys_F=F)
+    for kind, nm in ((0, "cg"), (1, "scalingcg"), (2, "ilu0cg")):
+        d[f"sys_x_{nm}"] = S.solve(kind, F)[0]
+    M = S.ilu0()
+    d["sys_ilu0_data"] = M.arrays()[2]
+    d["sys_preilu0"] = M.preilu0(F)
+    # filters / OC on the same mesh
+    s = rng.uniform(0.05, 1.0, P.nelem)
+    dfdrho = -rng.uniform(0.1, 2.0, P.nelem)
+    for kind, nm in ((reflib.FILTER_DENSITY, "density"), (reflib.FILTER_HEAVISIDE, "heaviside")):
+        flt = reflib.Filter(kind, *P.nbrs)
+        d[f"flt_{nm}_rho"] = flt.apply(2.0, s)
+        d[f"flt_{nm}_sens"] = flt.sens(2.0, s, dfdrho)
+        oc = reflib.OC(P.nelem, *P.oc)
+        dgds = flt.sens(2.0, s, np.full(P.nelem, 1.0 / (0.5 * P.nelem)))
+        d[f"oc_{nm}_x"] = oc.update(flt, 2.0, 0.5, 1.0, s, 1.0, d[f"flt_{nm}_sens"], 0.1, dgds)
+        d[f"oc_{nm}_dgds"] = dgds
+    d["flt_s"], d["flt_dfdrho"] = s, dfdrho
+    # C1 history (objective/constraint per design iteration) for OC and MMA, first 12 iterations + final state
+    for opt, nm in ((problems.OPT_OC, "oc"), (problems.OPT_MMA, "mma")):
+        P1 = problems.cantilever2d(60, 40, opt_kind=opt)
+        R = reflib.simp_run(P1.eq, P1.coords, P1.conn, P1.fixed, P1.loads, P1.filter_kind, P1.nbrs, P1.opt_kind,
+                            P1.optp(), P1.params(), 12, np.full(P1.nelem, 0.5), check_convergence=False)
+        d[f"c1_{nm}_hist"] = R["hist"][:, :2]
+        d[f"c1_{nm}_s12"] = R["s"]
+        d[f"c1_{nm}_rho12"] = R["rho"]
+        print("c1", nm, R["hist"][:3, :2], R["hist"][-1, :2])
+    np.savez_compressed(f"{OUT}/live_reference.npz", **d)
+    print("live fixtures:", len(d))
+
+
+if __name__ == "__main__":
+    golden_simp()
+    golden_solid()
+    golden_mma_kat()
+    golden_live()
