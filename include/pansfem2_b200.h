@@ -1,0 +1,203 @@
+/* pansfem2_b200.h -- C ABI of libpansfem2_b200.so, the B200 (sm_100a) implementation of PANSFEM2's SIMP
+ * topology-optimisation hot path.
+ *
+ * PANSFEM2 has no FFI of its own: its public surface is a header-only C++ template library.  This ABI is what the
+ * header mirror under pansfem2_b200/src/ (same relative paths, names and signatures as the reference's src/) binds
+ * for T = double; each entry point cites the reference interface it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every handle is opaque; no exceptions cross the boundary
+ *   - every function returns 0 on success or a PF2_E_* code; pf2_last_error() gives the message (thread local)
+ *   - "_host" arguments are host pointers, "_dev" arguments are device pointers obtained from pf2_malloc
+ *   - all work is enqueued on the context's stream; calls that return host results synchronise that stream
+ *   - indices are int32 (as the reference, CSR.h:72-73); CSR row pointers are int64 on the device side so that
+ *     config 5 (nnz = 3.45e9) is representable
+ *   - there is NO CPU fallback: without a CUDA device pf2_ctx_create fails with PF2_E_NODEVICE
+ */
+#ifndef PANSFEM2_B200_H
+#define PANSFEM2_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PF2_OK 0
+#define PF2_E_INVALID 1    /* bad argument (the reference asserts, e.g. PlaneStrain.h:22) */
+#define PF2_E_CUDA 2       /* CUDA runtime error */
+#define PF2_E_NODEVICE 3   /* no usable CUDA device */
+#define PF2_E_NOCONV 4     /* solver hit itrmax (the reference prints "Convergence:faild", CG.h:152,451) */
+#define PF2_E_UNSUPPORTED 5
+
+/* equation / element selection == the reference's template arguments
+ *   PF2_EQ_PLANESTRAIN : PlaneStrainStiffness<double, ShapeFunction4Square, Gauss4Square>        (PlaneStrain.h:21)
+ *   PF2_EQ_SOLID       : SolidLinearIsotropicElastic<double, ShapeFunction8Cubic, Gauss8Cubic>   (Solid.h:21)
+ *   PF2_EQ_HEAT        : HeatTransfer<double, ShapeFunction4Square, Gauss4Square>                (HeatTransfer.h:20) */
+enum { PF2_EQ_PLANESTRAIN = 0, PF2_EQ_SOLID = 1, PF2_EQ_HEAT = 2 };
+/* solver selection: CG (CG.h:124), ScalingCG (CG.h:420), ILU0CG (CG.h:320) */
+enum { PF2_SOLVER_CG = 0, PF2_SOLVER_SCALINGCG = 1, PF2_SOLVER_ILU0CG = 2 };
+/* DensityFilter (DensityFilter.h:45-71), HeavisideFilter (HeavisideFilter.h:61-99) */
+enum { PF2_FILTER_DENSITY = 0, PF2_FILTER_HEAVISIDE = 1 };
+/* OC (OC.h:78), MMA (MMA.h:117) */
+enum { PF2_OPT_OC = 0, PF2_OPT_MMA = 1 };
+
+typedef struct pf2_ctx pf2_ctx;
+typedef struct pf2_mesh pf2_mesh;
+typedef struct pf2_dofmap pf2_dofmap;
+typedef struct pf2_csr pf2_csr;
+typedef struct pf2_filter pf2_filter;
+typedef struct pf2_oc pf2_oc;
+typedef struct pf2_mma pf2_mma;
+typedef struct pf2_simp pf2_simp;
+
+const char* pf2_last_error(void);
+const char* pf2_version(void);
+
+/* ---- context, memory ------------------------------------------------------------------------------------ */
+/* stream: a cudaStream_t to enqueue on (e.g. torch's current stream) or NULL to create a private one. */
+int pf2_ctx_create(int device, void* stream, pf2_ctx** out);
+int pf2_ctx_destroy(pf2_ctx* ctx);
+int pf2_ctx_sync(pf2_ctx* ctx);
+int pf2_ctx_device_info(pf2_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+/* number of kernels this library has launched on the context since creation (bench.py's gpu_launches) */
+int pf2_ctx_launch_count(pf2_ctx* ctx, long long* out);
+int pf2_malloc(pf2_ctx* ctx, size_t bytes, void** dev_out);
+int pf2_free(pf2_ctx* ctx, void* dev);
+int pf2_memcpy_h2d(pf2_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int pf2_memcpy_d2h(pf2_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+int pf2_memset(pf2_ctx* ctx, void* dst_dev, int value, size_t bytes);
+/* pinned host staging (cudaHostAlloc) for the end-to-end path */
+int pf2_host_alloc(size_t bytes, void** host_out);
+int pf2_host_free(void* host);
+/* device-side stopwatch on the context's stream (CUDA events) */
+int pf2_timer_start(pf2_ctx* ctx);
+int pf2_timer_stop(pf2_ctx* ctx, double* milliseconds);
+/* write `bytes` of scratch to evict L2 between timed repetitions */
+int pf2_flush_l2(pf2_ctx* ctx);
+
+/* ---- mesh, boundary conditions, numbering ------------------------------------------------------------------ */
+/* coords: nnode*dim doubles (std::vector<Vector<T>> flattened), conn: nelem*npe node ids
+ * (std::vector<std::vector<int>> flattened).  dim/npe: 2/4 (Q4) or 3/8 (hex8). */
+int pf2_mesh_create(pf2_ctx* ctx, int dim, int nnode, const double* coords_host, int npe, int nelem,
+                    const int* conn_host, pf2_mesh** out);
+int pf2_mesh_destroy(pf2_mesh* mesh);
+/* SetDirichlet (BoundaryCondition.h:20-25) + Renumbering (Assembling.h:175-186): fixed dofs get -1, free dofs are
+ * numbered node-major / dof-minor.  *kdegree_out = KDEGREE.  nfixed = 0 reproduces RemoveBoundaryConditions
+ * (BoundaryCondition.h:66-72) followed by Renumbering. */
+int pf2_dofmap_create(pf2_ctx* ctx, int nnode, int ndof, int nfixed, const int* fix_node_host, const int* fix_dof_host,
+                      const double* fix_val_host, int* kdegree_out, pf2_dofmap** out);
+int pf2_dofmap_destroy(pf2_dofmap* map);
+int pf2_dofmap_get(pf2_dofmap* map, int* nodetoglobal_host /* nnode*ndof */);
+
+/* ---- sparse matrix: LILCSR<T> build then CSR<T> (LILCSR.h:92-114, CSR.h:93-105) --------------------------- */
+/* Symbolic phase, once per mesh + boundary conditions: the full element-connectivity pattern (the reference
+ * inserts explicit zeros, Assembling.h:55), sorted columns, plus the precomputed scatter map. */
+int pf2_csr_pattern(pf2_ctx* ctx, pf2_mesh* mesh, pf2_dofmap* map, pf2_csr** out);
+/* CSR<T> from caller arrays (the per-element legacy path assembles on the host through LILCSR<T>). */
+int pf2_csr_upload(pf2_ctx* ctx, int rows, const int* indptr_host, const int* indices_host, const double* data_host,
+                   pf2_csr** out);
+int pf2_csr_destroy(pf2_csr* A);
+int pf2_csr_info(pf2_csr* A, int* rows, long long* nnz);
+/* indptr as int64 (rows+1), indices int32 (nnz), data (nnz), F (rows): any may be NULL */
+int pf2_csr_download(pf2_csr* A, long long* indptr_host, int* indices_host, double* data_host, double* F_host);
+int pf2_csr_set_values(pf2_csr* A, const double* data_host);
+/* device views for composing with other calls: right-hand side F (rows) and values (nnz) */
+int pf2_csr_device_F(pf2_csr* A, double** F_dev);
+int pf2_csr_device_data(pf2_csr* A, double** data_dev);
+
+/* Numeric phase = the element loop of the drivers (sample_optimize_density_oc.cpp:122-129):
+ *   Ke = element routine(E_i) ; Assembling(K,F,u,Ke,...) (Assembling.h:47-66) ; Assembling(F,q,...) (Assembling.h:152)
+ * modulus_dev: per-element modulus E_i (nelem) or NULL to derive it from rho_dev by SIMP interpolation
+ *   E_i = E1*rho^p + E0*(1-rho^p)  (driver :123).  params = {E0, E1, poisson, p, thickness}. */
+int pf2_assemble(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq, const double* modulus_dev, const double* rho_dev,
+                 const double params[5], int nload, const int* load_node_host, const int* load_dof_host,
+                 const double* load_val_host);
+/* one element matrix, host in / host out: the reference's per-element call kept for parity
+ * (PlaneStrain.h:21-58, Solid.h:21-64, HeatTransfer.h:20-43).  xe: npe*dim, Ke_out: (npe*ndof)^2 row-major. */
+int pf2_element_matrix(pf2_ctx* ctx, int eq, const double* xe_host, double E, double V, double t, double* Ke_host);
+
+/* ---- CSR<T>::operator* (CSR.h:109-122) ------------------------------------------------------------------------ */
+int pf2_spmv(pf2_csr* A, const double* x_dev, double* y_dev);
+int pf2_spmv_host(pf2_csr* A, const double* x_host, double* y_host);
+/* micro-benchmark hook: run SpMV `reps` times with kernel variant `variant` (0 = auto), device-timed */
+int pf2_spmv_bench(pf2_csr* A, int variant, int reps, int flush_l2, double* ms_per_spmv);
+
+/* ---- CG / ScalingCG / ILU0CG (CG.h:124-154, 420-453, 320-352); ILU0 / PreILU0 (CG.h:258-315) ---------------- */
+/* x0 = 0; stop when ||r||_2 < eps*||b||_2 on the recursive residual.  Returns PF2_E_NOCONV at itrmax (x holds
+ * the last iterate, as the reference returns it). */
+int pf2_solve(pf2_csr* A, int solver, const double* b_dev, double* x_dev, int itrmax, double eps, int* iters_out,
+              double* relres_out);
+int pf2_solve_host(pf2_csr* A, int solver, const double* b_host, double* x_host, int itrmax, double eps,
+                   int* iters_out, double* relres_out);
+/* ILU(0) factors of A (unit-L strictly lower + U with diagonal in A's pattern), cached on A until values change */
+int pf2_ilu0_factor(pf2_csr* A);
+int pf2_ilu0_download(pf2_csr* A, double* data_host);
+int pf2_ilu0_solve_host(pf2_csr* A, const double* b_host, double* x_host);   /* PreILU0 */
+
+/* Disassembling (Assembling.h:163-171): free dofs from the solution, fixed dofs keep their Dirichlet value */
+int pf2_disassemble(pf2_dofmap* map, const double* x_dev, double* u_nodal_dev);
+
+/* ---- filters -------------------------------------------------------------------------------------------------- */
+/* neighbors / w as the reference's ragged lists flattened to CSR form (rowptr has n+1 entries) */
+int pf2_filter_create(pf2_ctx* ctx, int kind, int n, const long long* rowptr_host, const int* nbr_host,
+                      const double* w_host, pf2_filter** out);
+int pf2_filter_destroy(pf2_filter* f);
+int pf2_filter_set_beta(pf2_filter* f, double beta);                       /* HeavisideFilter::UpdateBeta */
+int pf2_filter_apply(pf2_filter* f, const double* s_dev, double* rho_dev); /* GetFilteredVariables */
+int pf2_filter_sens(pf2_filter* f, const double* s_dev, const double* dfdrho_dev, double* dfds_dev); /* GetFilteredSensitivitis */
+int pf2_filter_apply_host(pf2_filter* f, const double* s_host, double* rho_host);
+int pf2_filter_sens_host(pf2_filter* f, const double* s_host, const double* dfdrho_host, double* dfds_host);
+
+/* ---- reaction / compliance / sensitivity passes (sample_optimize_density_oc.cpp:136-162) -------------------- */
+/* f = scale0 * u^T K_full(rho) u ; dfdrho_i = -scale0*p*(E1-E0)*rho_i^(p-1) * ue^T Ke(E=1) ue ;
+ * r_nodal_dev (optional) = K_full(rho) u.  params = {E0, E1, poisson, p, thickness, scale0}. */
+int pf2_compliance_sens(pf2_mesh* mesh, int eq, const double* u_nodal_dev, const double* rho_dev, const double params[6],
+                        double* f_out, double* dfdrho_dev, double* r_nodal_dev);
+
+/* ---- OC (OC.h:46-107) ----------------------------------------------------------------------------------------- */
+int pf2_oc_create(pf2_ctx* ctx, int n, double iota, double lambdamin, double lambdamax, double lambdaeps,
+                  double movelimit, pf2_oc** out);
+int pf2_oc_destroy(pf2_oc* oc);
+int pf2_oc_is_convergence(pf2_oc* oc, double f, int* converged);           /* OC::IsConvergence OC.h:68-73 */
+/* UpdateVariables with the drivers' constraint functor g(x) = scale1*sum(filter(x))/(weightlimit*n) - scale1
+ * (sample_optimize_density_oc.cpp:198-207) evaluated on the device.  x_dev updated in place. */
+int pf2_oc_update(pf2_oc* oc, pf2_filter* filter, double weightlimit, double scale1, double* x_dev, double f,
+                  const double* dfdx_dev, const double* dgdx_dev, int* steps_out, double* lambda_out);
+
+/* ---- MMA (MMA.h:64-509) --------------------------------------------------------------------------------------- */
+int pf2_mma_create(pf2_ctx* ctx, int n, int m, double a0, const double* a_host, const double* c_host,
+                   const double* d_host, const double* xmin_host, const double* xmax_host, pf2_mma** out);
+int pf2_mma_destroy(pf2_mma* mma);
+int pf2_mma_set_parameters(pf2_mma* mma, double raa0, double albefa, double move, double asyinit, double asydecr,
+                           double asyincr, double epsvalue);
+int pf2_mma_is_convergence(pf2_mma* mma, double f, int* converged);
+/* UpdateVariables(xk, f, dfdx, g[m], dgdx[m][n]); dgdx_dev is m*n row-major.  x_dev updated in place. */
+int pf2_mma_update(pf2_mma* mma, double* x_dev, double f, const double* dfdx_dev, const double* g_host,
+                   const double* dgdx_dev, int* newton_steps_out);
+
+/* ---- the device-resident design loop (sample_optimize_density_{oc,mma}.cpp:83-208) ------------------------- */
+/* params[12] = {E0,E1,poisson,p,weightlimit,scale0,scale1,thickness,beta0,beta_period,cg_itrmax,cg_eps}
+ * optp: OC {iota,lmin,lmax,leps,move} or MMA {raa0,albefa,move,asyinit,asydecr,asyincr,epsvalue,a0,a,c,d,xmin,xmax} */
+int pf2_simp_create(pf2_ctx* ctx, pf2_mesh* mesh, pf2_dofmap* map, pf2_csr* A, pf2_filter* filter, int eq, int opt_kind,
+                    const double* optp, const double params[12], int nload, const int* load_node_host,
+                    const int* load_dof_host, const double* load_val_host, pf2_simp** out);
+int pf2_simp_destroy(pf2_simp* S);
+int pf2_simp_set_design(pf2_simp* S, const double* s_host);
+int pf2_simp_set_solver(pf2_simp* S, int solver);
+/* One design iteration; the design never leaves the device.  stats[8] = {f, g, converged, cg_iters, cg_relres,
+ * optimizer_steps, beta, k}.  When `converged` is set the design was NOT updated (the driver breaks, :192-195). */
+int pf2_simp_iterate(pf2_simp* S, int check_convergence, double stats[8]);
+/* The same iteration through host buffers (end-to-end path): uploads s, runs, downloads s, rho. */
+int pf2_simp_iterate_host(pf2_simp* S, int check_convergence, const double* s_in_host, double* s_out_host,
+                          double* rho_out_host, double stats[8]);
+int pf2_simp_get(pf2_simp* S, double* s_host, double* rho_host, double* u_nodal_host, double* r_nodal_host);
+/* per-phase device time of the last iteration, ms: {filter, assemble, solve, compliance+sens, filter-sens, update} */
+int pf2_simp_phase_ms(pf2_simp* S, double ms[6]);
+int pf2_simp_cg_stats(pf2_simp* S, double* spmv_ms_avg, long long* spmv_calls);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANSFEM2_B200_H */

@@ -1,0 +1,433 @@
+"""ctypes binding of libpansfem2_b200.so (C ABI: include/pansfem2_b200.h).
+
+Plumbing for tests and bench.py only - a C++ user binds the same ABI through the header mirror under
+pansfem2_b200/src.  There is no CPU fallback: if the shared library is missing or no CUDA device is present every
+entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpansfem2_b200.so")
+
+EQ_PLANESTRAIN, EQ_SOLID, EQ_HEAT = 0, 1, 2
+SOLVER_CG, SOLVER_SCALINGCG, SOLVER_ILU0CG = 0, 1, 2
+FILTER_DENSITY, FILTER_HEAVISIDE = 0, 1
+OPT_OC, OPT_MMA = 0, 1
+E_NOCONV = 4
+NDOF = {EQ_PLANESTRAIN: 2, EQ_SOLID: 3, EQ_HEAT: 1}
+
+_lib = None
+
+
+class Pf2Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"pansfem2_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing - build it with `python -m pansfem2_b200.build` "
+                               "(pansfem2_b200 has no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.pf2_last_error.restype = C.c_char_p
+        _lib.pf2_version.restype = C.c_char_p
+    return _lib
+
+
+def _ck(rc, allow=()):
+    if rc != 0 and rc not in allow:
+        raise Pf2Error(rc, lib().pf2_last_error().decode())
+    return rc
+
+
+def _p(a, dtype):
+    if a is None:
+        return None
+    assert a.dtype == dtype and a.flags["C_CONTIGUOUS"], (a.dtype, dtype)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+class DeviceArray:
+    """A device buffer owned through pf2_malloc / pf2_free."""
+
+    def __init__(self, ctx, count, dtype=np.float64):
+        self.ctx, self.count, self.dtype = ctx, int(count), np.dtype(dtype)
+        self.ptr = C.c_void_p()
+        _ck(lib().pf2_malloc(ctx.h, C.c_size_t(self.count * self.dtype.itemsize), C.byref(self.ptr)))
+
+    @classmethod
+    def from_host(cls, ctx, arr):
+        arr = np.ascontiguousarray(arr)
+        d = cls(ctx, arr.size, arr.dtype)
+        d.upload(arr)
+        return d
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=self.dtype)
+        assert arr.size == self.count
+        _ck(lib().pf2_memcpy_h2d(self.ctx.h, self.ptr, arr.ctypes.data_as(C.c_void_p), C.c_size_t(arr.nbytes)))
+
+    def download(self):
+        out = np.empty(self.count, self.dtype)
+        _ck(lib().pf2_memcpy_d2h(self.ctx.h, out.ctypes.data_as(C.c_void_p), self.ptr, C.c_size_t(out.nbytes)))
+        return out
+
+    def free(self):
+        if self.ptr:
+            lib().pf2_free(self.ctx.h, self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    def __init__(self, device=0, stream=None):
+        self.h = C.c_void_p()
+        _ck(lib().pf2_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(self.h)))
+
+    def sync(self):
+        _ck(lib().pf2_ctx_sync(self.h))
+
+    def launch_count(self):
+        v = C.c_longlong(0)
+        _ck(lib().pf2_ctx_launch_count(self.h, C.byref(v)))
+        return v.value
+
+    def device_info(self):
+        sm, ma, mi, mem = C.c_int(0), C.c_int(0), C.c_int(0), C.c_size_t(0)
+        _ck(lib().pf2_ctx_device_info(self.h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)))
+        return dict(sm_count=sm.value, cc=(ma.value, mi.value), total_mem=mem.value)
+
+    def timer_start(self):
+        _ck(lib().pf2_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double(0)
+        _ck(lib().pf2_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self):
+        _ck(lib().pf2_flush_l2(self.h))
+
+    def array(self, arr):
+        return DeviceArray.from_host(self, arr)
+
+    def empty(self, count, dtype=np.float64):
+        return DeviceArray(self, count, dtype)
+
+    def element_matrix(self, eq, xe, E, V=0.3, t=1.0):
+        xe = _f64(xe)
+        m = xe.shape[0] * NDOF[eq]
+        Ke = np.zeros((m, m))
+        _ck(lib().pf2_element_matrix(self.h, eq, _p(xe, np.float64), C.c_double(E), C.c_double(V), C.c_double(t), _p(Ke, np.float64)))
+        return Ke
+
+    def close(self):
+        if self.h:
+            lib().pf2_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class Mesh:
+    def __init__(self, ctx, coords, conn):
+        coords, conn = _f64(coords), _i32(conn)
+        self.ctx, self.nnode, self.dim = ctx, coords.shape[0], coords.shape[1]
+        self.nelem, self.npe = conn.shape
+        self.h = C.c_void_p()
+        _ck(lib().pf2_mesh_create(ctx.h, self.dim, self.nnode, _p(coords, np.float64), self.npe, self.nelem, _p(conn, np.int32), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().pf2_mesh_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class DofMap:
+    def __init__(self, ctx, nnode, ndof, fixed):
+        fn, fd, fv = _i32(fixed[0]), _i32(fixed[1]), _f64(fixed[2])
+        self.ctx, self.nnode, self.ndof = ctx, nnode, ndof
+        self.h = C.c_void_p()
+        k = C.c_int(0)
+        _ck(lib().pf2_dofmap_create(ctx.h, nnode, ndof, len(fn), _p(fn, np.int32), _p(fd, np.int32), _p(fv, np.float64), C.byref(k), C.byref(self.h)))
+        self.kdegree = k.value
+
+    def get(self):
+        out = np.zeros((self.nnode, self.ndof), np.int32)
+        _ck(lib().pf2_dofmap_get(self.h, _p(out, np.int32)))
+        return out
+
+    def disassemble(self, x_dev, u_dev):
+        _ck(lib().pf2_disassemble(self.h, x_dev.ptr, u_dev.ptr))
+
+    def close(self):
+        if self.h:
+            lib().pf2_dofmap_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class Csr:
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, handle
+        r, nnz = C.c_int(0), C.c_longlong(0)
+        _ck(lib().pf2_csr_info(self.h, C.byref(r), C.byref(nnz)))
+        self.rows, self.nnz = r.value, nnz.value
+
+    @classmethod
+    def pattern(cls, ctx, mesh, dofmap):
+        h = C.c_void_p()
+        _ck(lib().pf2_csr_pattern(ctx.h, mesh.h, dofmap.h, C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def upload(cls, ctx, indptr, indices, data):
+        indptr, indices, data = _i32(indptr), _i32(indices), _f64(data)
+        h = C.c_void_p()
+        _ck(lib().pf2_csr_upload(ctx.h, len(indptr) - 1, _p(indptr, np.int32), _p(indices, np.int32), _p(data, np.float64), C.byref(h)))
+        return cls(ctx, h)
+
+    def download(self):
+        indptr, indices = np.zeros(self.rows + 1, np.int64), np.zeros(self.nnz, np.int32)
+        data, F = np.zeros(self.nnz), np.zeros(self.rows)
+        _ck(lib().pf2_csr_download(self.h, _p(indptr, np.int64), _p(indices, np.int32), _p(data, np.float64), _p(F, np.float64)))
+        return indptr, indices, data, F
+
+    def assemble(self, mesh, dofmap, eq, params, loads, modulus=None, rho=None):
+        """params = (E0, E1, poisson, p, thickness); modulus / rho are DeviceArrays."""
+        ln, ld, lv = _i32(loads[0]), _i32(loads[1]), _f64(loads[2])
+        prm = (C.c_double * 5)(*params)
+        _ck(lib().pf2_assemble(self.h, mesh.h, dofmap.h, eq, modulus.ptr if modulus is not None else None,
+                               rho.ptr if rho is not None else None, prm, len(ln), _p(ln, np.int32), _p(ld, np.int32), _p(lv, np.float64)))
+
+    def spmv_host(self, x):
+        x = _f64(x)
+        y = np.zeros(self.rows)
+        _ck(lib().pf2_spmv_host(self.h, _p(x, np.float64), _p(y, np.float64)))
+        return y
+
+    def spmv_bench(self, variant=0, reps=20, flush_l2=True):
+        ms = C.c_double(0)
+        _ck(lib().pf2_spmv_bench(self.h, variant, reps, int(flush_l2), C.byref(ms)))
+        return ms.value
+
+    def solve_host(self, solver, b, itrmax=100000, eps=1e-10, raise_noconv=True):
+        b = _f64(b)
+        x = np.zeros(self.rows)
+        it, rr = C.c_int(0), C.c_double(0)
+        rc = _ck(lib().pf2_solve_host(self.h, solver, _p(b, np.float64), _p(x, np.float64), int(itrmax), C.c_double(eps), C.byref(it), C.byref(rr)),
+                 allow=() if raise_noconv else (E_NOCONV,))
+        return x, it.value, rr.value
+
+    def solve(self, solver, b_dev, x_dev, itrmax=100000, eps=1e-10):
+        it, rr = C.c_int(0), C.c_double(0)
+        _ck(lib().pf2_solve(self.h, solver, b_dev.ptr if isinstance(b_dev, DeviceArray) else b_dev, x_dev.ptr, int(itrmax), C.c_double(eps),
+                            C.byref(it), C.byref(rr)))
+        return it.value, rr.value
+
+    def device_F(self):
+        p = C.c_void_p()
+        _ck(lib().pf2_csr_device_F(self.h, C.byref(p)))
+        return p
+
+    def ilu0(self):
+        _ck(lib().pf2_ilu0_factor(self.h))
+        data = np.zeros(self.nnz)
+        _ck(lib().pf2_ilu0_download(self.h, _p(data, np.float64)))
+        return data
+
+    def ilu0_solve_host(self, b):
+        b = _f64(b)
+        x = np.zeros(self.rows)
+        _ck(lib().pf2_ilu0_solve_host(self.h, _p(b, np.float64), _p(x, np.float64)))
+        return x
+
+    def close(self):
+        if self.h:
+            lib().pf2_csr_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class Filter:
+    def __init__(self, ctx, kind, rowptr, nbr, w):
+        rowptr, nbr, w = _i64(rowptr), _i32(nbr), _f64(w)
+        self.ctx, self.n, self.kind = ctx, len(rowptr) - 1, kind
+        self.h = C.c_void_p()
+        _ck(lib().pf2_filter_create(ctx.h, kind, self.n, _p(rowptr, np.int64), _p(nbr, np.int32), _p(w, np.float64), C.byref(self.h)))
+
+    def set_beta(self, beta):
+        _ck(lib().pf2_filter_set_beta(self.h, C.c_double(beta)))
+
+    def apply_host(self, s):
+        s = _f64(s)
+        rho = np.zeros(self.n)
+        _ck(lib().pf2_filter_apply_host(self.h, _p(s, np.float64), _p(rho, np.float64)))
+        return rho
+
+    def sens_host(self, s, dfdrho):
+        s, dfdrho = _f64(s), _f64(dfdrho)
+        out = np.zeros(self.n)
+        _ck(lib().pf2_filter_sens_host(self.h, _p(s, np.float64), _p(dfdrho, np.float64), _p(out, np.float64)))
+        return out
+
+    def close(self):
+        if self.h:
+            lib().pf2_filter_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class OC:
+    def __init__(self, ctx, n, iota, lmin, lmax, leps, move):
+        self.ctx, self.n = ctx, n
+        self.h = C.c_void_p()
+        _ck(lib().pf2_oc_create(ctx.h, n, *[C.c_double(v) for v in (iota, lmin, lmax, leps, move)], C.byref(self.h)))
+
+    def is_convergence(self, f):
+        v = C.c_int(0)
+        _ck(lib().pf2_oc_is_convergence(self.h, C.c_double(f), C.byref(v)))
+        return bool(v.value)
+
+    def update_host(self, filt, weightlimit, scale1, x, f, dfdx, dgdx):
+        xd, fd, gd = self.ctx.array(_f64(x)), self.ctx.array(_f64(dfdx)), self.ctx.array(_f64(dgdx))
+        steps, lam = C.c_int(0), C.c_double(0)
+        _ck(lib().pf2_oc_update(self.h, filt.h, C.c_double(weightlimit), C.c_double(scale1), xd.ptr, C.c_double(f), fd.ptr, gd.ptr,
+                                C.byref(steps), C.byref(lam)))
+        return xd.download(), steps.value, lam.value
+
+    def close(self):
+        if self.h:
+            lib().pf2_oc_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class MMA:
+    def __init__(self, ctx, n, m, a0, a, c, d, xmin, xmax):
+        self.ctx, self.n, self.m = ctx, n, m
+        a, c, d = _f64(a), _f64(c), _f64(d)
+        xmin = _f64(np.broadcast_to(xmin, (n,)))
+        xmax = _f64(np.broadcast_to(xmax, (n,)))
+        self.h = C.c_void_p()
+        _ck(lib().pf2_mma_create(ctx.h, n, m, C.c_double(a0), _p(a, np.float64), _p(c, np.float64), _p(d, np.float64),
+                                 _p(xmin, np.float64), _p(xmax, np.float64), C.byref(self.h)))
+
+    def set_parameters(self, raa0, albefa, move, asyinit, asydecr, asyincr, epsvalue):
+        _ck(lib().pf2_mma_set_parameters(self.h, *[C.c_double(v) for v in (raa0, albefa, move, asyinit, asydecr, asyincr, epsvalue)]))
+
+    def is_convergence(self, f):
+        v = C.c_int(0)
+        _ck(lib().pf2_mma_is_convergence(self.h, C.c_double(f), C.byref(v)))
+        return bool(v.value)
+
+    def update_host(self, x, f, dfdx, g, dgdx):
+        xd, fd, gd = self.ctx.array(_f64(x)), self.ctx.array(_f64(dfdx)), self.ctx.array(_f64(dgdx).ravel())
+        g = _f64(g)
+        steps = C.c_int(0)
+        _ck(lib().pf2_mma_update(self.h, xd.ptr, C.c_double(f), fd.ptr, _p(g, np.float64), gd.ptr, C.byref(steps)))
+        return xd.download(), steps.value
+
+    def close(self):
+        if self.h:
+            lib().pf2_mma_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+def compliance_sens(mesh, eq, u_dev, rho_dev, params6, want_r=False):
+    """params6 = (E0, E1, poisson, p, thickness, scale0).  Returns (f, dfdrho, r or None) as host arrays."""
+    ctx = mesh.ctx
+    dfd = ctx.empty(mesh.nelem)
+    r = ctx.empty(mesh.nnode * NDOF[eq]) if want_r else None
+    f = C.c_double(0)
+    prm = (C.c_double * 6)(*params6)
+    _ck(lib().pf2_compliance_sens(mesh.h, eq, u_dev.ptr, rho_dev.ptr, prm, C.byref(f), dfd.ptr, r.ptr if r is not None else None))
+    return f.value, dfd.download(), (r.download().reshape(mesh.nnode, -1) if r is not None else None)
+
+
+class Simp:
+    """The device-resident design loop for a pansfem2_b200.problems.Problem."""
+
+    def __init__(self, ctx, problem, solver=SOLVER_SCALINGCG):
+        P = problem
+        self.ctx, self.P = ctx, P
+        self.mesh = Mesh(ctx, P.coords, P.conn)
+        self.dofmap = DofMap(ctx, P.nnode, P.ndof, P.fixed)
+        self.A = Csr.pattern(ctx, self.mesh, self.dofmap)
+        self.filter = Filter(ctx, P.filter_kind, *P.nbrs)
+        ln, ld, lv = _i32(P.loads[0]), _i32(P.loads[1]), _f64(P.loads[2])
+        optp, params = _f64(P.optp()), _f64(P.params())
+        self.h = C.c_void_p()
+        _ck(lib().pf2_simp_create(ctx.h, self.mesh.h, self.dofmap.h, self.A.h, self.filter.h, P.eq, P.opt_kind, _p(optp, np.float64),
+                                  _p(params, np.float64), len(ln), _p(ln, np.int32), _p(ld, np.int32), _p(lv, np.float64), C.byref(self.h)))
+        _ck(lib().pf2_simp_set_solver(self.h, solver))
+        self.set_design(np.full(P.nelem, P.s0))
+
+    def set_design(self, s):
+        s = _f64(s)
+        _ck(lib().pf2_simp_set_design(self.h, _p(s, np.float64)))
+
+    @staticmethod
+    def _stats(st):
+        return dict(f=st[0], g=st[1], converged=bool(st[2]), cg_iters=int(st[3]), cg_relres=st[4], opt_steps=int(st[5]), beta=st[6], k=int(st[7]))
+
+    def iterate(self, check_convergence=True):
+        st = (C.c_double * 8)()
+        _ck(lib().pf2_simp_iterate(self.h, int(check_convergence), st))
+        return self._stats(st)
+
+    def iterate_host(self, s_in, s_out, rho_out, check_convergence=True):
+        """End-to-end variant: s_in / s_out / rho_out are host numpy arrays (pinned or not)."""
+        st = (C.c_double * 8)()
+        _ck(lib().pf2_simp_iterate_host(self.h, int(check_convergence), _p(s_in, np.float64) if s_in is not None else None,
+                                        _p(s_out, np.float64), _p(rho_out, np.float64), st))
+        return self._stats(st)
+
+    def get(self, want_r=False):
+        P = self.P
+        s, rho = np.zeros(P.nelem), np.zeros(P.nelem)
+        u = np.zeros((P.nnode, P.ndof))
+        r = np.zeros((P.nnode, P.ndof)) if want_r else None
+        _ck(lib().pf2_simp_get(self.h, _p(s, np.float64), _p(rho, np.float64), _p(u, np.float64), _p(r, np.float64) if want_r else None))
+        return dict(s=s, rho=rho, u=u, r=r)
+
+    def phase_ms(self):
+        ms = (C.c_double * 6)()
+        _ck(lib().pf2_simp_phase_ms(self.h, ms))
+        return dict(zip(("filter", "assemble", "solve", "sens", "filter_sens", "update"), list(ms)))
+
+    def close(self):
+        if self.h:
+            lib().pf2_simp_destroy(self.h)
+            self.h = C.c_void_p()
+        for o in (self.filter, self.A, self.dofmap, self.mesh):
+            o.close()
+
+
+def pinned_empty(count, dtype=np.float64):
+    """numpy view over cudaHostAlloc'ed memory (for the end-to-end path)."""
+    dtype = np.dtype(dtype)
+    p = C.c_void_p()
+    _ck(lib().pf2_host_alloc(C.c_size_t(count * dtype.itemsize), C.byref(p)))
+    buf = (C.c_char * (count * dtype.itemsize)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=count)
+    return arr

@@ -1,0 +1,334 @@
+// csr.cu -- CSR<T> on the device: upload/download and y = A*x (replaces CSR<T>::operator*, CSR.h:109-122).
+//
+// HBM layout: indptr int64[rows+1], indices int32[nnz], data fp64[nnz] -- the reference's three arrays, contiguous.
+// Algorithmic bytes per SpMV: 12*nnz (value + column index) + 24*rows (int64 row pointer, x read once, y written once).
+//
+// Two kernels, picked per matrix by plan_spmv():
+//   * stream  : a CTA owns `stream_rows` consecutive rows, streams their nonzeros (values, indices) with fully
+//               coalesced 128-byte loads, multiplies by the gathered x and parks the products in shared memory;
+//               sub-groups of threads then fold each row from shared memory.  Row length never affects coalescing, which
+//               is what short FEM rows (9/18 nnz) need to get near the HBM roofline.
+//   * vector  : TPR lanes per row (2..32) with a shuffle reduction; used when a CTA's rows do not fit in shared memory.
+// Both optionally fuse the dot product x.y (p.Ap of CG, CG.h:433) into the epilogue.
+#include "types.cuh"
+
+namespace pf2 {
+
+constexpr int kStreamCap = 4608;   // products per CTA in shared memory (36 KB): 256 rows x 18 nnz
+
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
+__device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
+
+// ---- streaming kernel ------------------------------------------------------------------------------------------
+// G = threads cooperating on one row in the fold phase; a CTA covers kThreads/G rows per tile.
+template <int G, bool DOT>
+__global__ void __launch_bounds__(kThreads)
+spmv_stream_kernel(int rows, const long long* __restrict__ indptr, const int* __restrict__ indices,
+                   const double* __restrict__ data, const double* __restrict__ x, double* __restrict__ y,
+                   const CgState* __restrict__ st, double* dot_out, double* partials, unsigned int* ticket) {
+    if (DOT && st != nullptr && st->done) return;
+    __shared__ double prod[kStreamCap];
+    __shared__ long long s_range[2];
+    constexpr int RPB = kThreads / G;   // rows per CTA tile
+    const int ntiles = (rows + RPB - 1) / RPB;
+    double dot = 0.0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int r0 = tile * RPB;
+        const int r1 = min(r0 + RPB, rows);
+        if (threadIdx.x == 0) { s_range[0] = indptr[r0]; s_range[1] = indptr[r1]; }
+        __syncthreads();
+        const long long s = s_range[0];
+        const int cnt = (int)(s_range[1] - s);
+        // phase 1: coalesced stream of the tile's nonzeros
+#pragma unroll 4
+        for (int j = threadIdx.x; j < cnt; j += kThreads) {
+            const double v = ld_stream(data + s + j);
+            const int c = ld_stream(indices + s + j);
+            prod[j] = v * __ldg(x + c);
+        }
+        __syncthreads();
+        // phase 2: fold rows out of shared memory
+        const int lr = threadIdx.x / G, g = threadIdx.x % G;
+        const int row = r0 + lr;
+        double acc = 0.0;
+        if (row < r1) {
+            const int b = (int)(indptr[row] - s), e = (int)(indptr[row + 1] - s);
+            for (int j = b + g; j < e; j += G) acc += prod[j];
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, G);
+        if (row < r1 && g == 0) {
+            y[row] = acc;
+            if (DOT) dot += acc * x[row];
+        }
+        __syncthreads();
+    }
+    if (DOT) {
+        double v[1] = { dot };
+        if (grid_sum_last<1>(v, partials, ticket) && threadIdx.x == 0) *dot_out = v[0];
+    }
+}
+
+// ---- vector kernel ---------------------------------------------------------------------------------------------
+template <int TPR, bool DOT>
+__global__ void __launch_bounds__(kThreads)
+spmv_vector_kernel(int rows, const long long* __restrict__ indptr, const int* __restrict__ indices,
+                   const double* __restrict__ data, const double* __restrict__ x, double* __restrict__ y,
+                   const CgState* __restrict__ st, double* dot_out, double* partials, unsigned int* ticket) {
+    if (DOT && st != nullptr && st->done) return;
+    constexpr int RPB = kThreads / TPR;
+    const int lr = threadIdx.x / TPR, lane = threadIdx.x % TPR;
+    double dot = 0.0;
+    for (long long row = (long long)blockIdx.x * RPB + lr; row < rows; row += (long long)gridDim.x * RPB) {
+        const long long s = indptr[row], e = indptr[row + 1];
+        double acc = 0.0;
+#pragma unroll 2
+        for (long long j = s + lane; j < e; j += TPR) acc += ld_stream(data + j) * __ldg(x + ld_stream(indices + j));
+#pragma unroll
+        for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, TPR);
+        if (lane == 0) {
+            y[row] = acc;
+            if (DOT) dot += acc * x[row];
+        }
+    }
+    if (DOT) {
+        double v[1] = { dot };
+        if (grid_sum_last<1>(v, partials, ticket) && threadIdx.x == 0) *dot_out = v[0];
+    }
+}
+
+// row statistics + diagonal offsets (GetDiagonal's A.get(i,i), CG.h:398-404 / CSR.h:155-167, resolved once)
+__global__ void csr_rowinfo_kernel(int rows, const long long* __restrict__ indptr, const int* __restrict__ indices,
+                                   int* __restrict__ diagpos, int* maxrow) {
+    int m = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += gridDim.x * blockDim.x) {
+        const long long s = indptr[i], e = indptr[i + 1];
+        m = max(m, (int)(e - s));
+        long long lo = s, hi = e - 1;
+        int pos = -1;
+        while (lo <= hi) {
+            long long mid = (lo + hi) >> 1;
+            int c = indices[mid];
+            if (c == i) { pos = (int)(mid - s); break; }
+            if (c < i) lo = mid + 1; else hi = mid - 1;
+        }
+        diagpos[i] = pos;
+    }
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(maxrow, m);
+}
+
+__global__ void widen_indptr_kernel(int n, const int* __restrict__ in, long long* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in[i];
+}
+
+int csr_finalize_structure(pf2_csr* A) {
+    pf2_ctx* c = A->ctx;
+    PF2_TRY(dev_alloc(&A->diagpos, (size_t)A->rows));
+    int* d_max = nullptr;
+    PF2_TRY(dev_alloc(&d_max, 1));
+    PF2_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), c->stream));
+    csr_rowinfo_kernel<<<c->grid_for(A->rows), kThreads, 0, c->stream>>>(A->rows, A->indptr, A->indices, A->diagpos, d_max);
+    PF2_LAUNCH_CHECK();
+    c->launches++;
+    PF2_CUDA(cudaMemcpyAsync(&A->max_row, d_max, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PF2_CUDA(cudaStreamSynchronize(c->stream));
+    PF2_CUDA(cudaFree(d_max));
+    A->spmv_variant = 0;
+    return PF2_OK;
+}
+
+// variant encoding: 1..5 = vector TPR 2,4,8,16,32 ; 11..15 = stream with G = 1,2,4,8,16 threads per row
+static void plan_spmv(pf2_csr* A) {
+    if (A->spmv_variant) return;
+    const double mean = A->rows ? (double)A->nnz / A->rows : 1.0;
+    // stream: pick the smallest fold group G such that a tile's rows surely fit in shared memory
+    int G = 1;
+    while (G <= 16 && (long long)(kThreads / G) * A->max_row > kStreamCap) G *= 2;
+    if (G <= 16) {
+        // prefer a few threads per row once rows get long so the fold phase stays short
+        while (G < 16 && mean / G > 12.0 && (kThreads / (G * 2)) >= 8) G *= 2;
+        A->spmv_variant = 11 + (G == 1 ? 0 : G == 2 ? 1 : G == 4 ? 2 : G == 8 ? 3 : 4);
+    } else {
+        A->spmv_variant = mean <= 3 ? 1 : mean <= 6 ? 2 : mean <= 12 ? 3 : mean <= 24 ? 4 : 5;
+    }
+}
+
+template <bool DOT>
+static int launch_spmv(pf2_csr* A, int variant, const double* x, double* y, const CgState* st, double* dot_out) {
+    pf2_ctx* c = A->ctx;
+    const int grid_cap = c->sm_count * 6;
+#define ARGS A->rows, A->indptr, A->indices, A->data, x, y, st, dot_out, c->red.partials, c->red.ticket
+#define VEC(T)                                                                                               \
+    {                                                                                                        \
+        long long nb = ((long long)A->rows + (kThreads / T) - 1) / (kThreads / T);                              \
+        int grid = (int)std::min<long long>(std::max<long long>(nb, 1), DOT ? std::min(grid_cap * 2, kMaxBlocks) : (long long)c->sm_count * 64); \
+        spmv_vector_kernel<T, DOT><<<grid, kThreads, 0, c->stream>>>(ARGS);                                   \
+    }
+#define STR(Gv)                                                                                              \
+    {                                                                                                        \
+        long long nb = ((long long)A->rows + (kThreads / Gv) - 1) / (kThreads / Gv);                            \
+        int grid = (int)std::min<long long>(std::max<long long>(nb, 1), std::min(grid_cap, kMaxBlocks));        \
+        spmv_stream_kernel<Gv, DOT><<<grid, kThreads, 0, c->stream>>>(ARGS);                                  \
+    }
+    switch (variant) {
+        case 1: VEC(2) break;
+        case 2: VEC(4) break;
+        case 3: VEC(8) break;
+        case 4: VEC(16) break;
+        case 5: VEC(32) break;
+        case 11: STR(1) break;
+        case 12: STR(2) break;
+        case 13: STR(4) break;
+        case 14: STR(8) break;
+        case 15: STR(16) break;
+        default: set_error("unknown SpMV variant %d", variant); return PF2_E_INVALID;
+    }
+#undef ARGS
+#undef VEC
+#undef STR
+    PF2_LAUNCH_CHECK();
+    c->launches++;
+    return PF2_OK;
+}
+
+static bool variant_ok(const pf2_csr* A, int variant) {
+    if (variant >= 1 && variant <= 5) return true;
+    if (variant >= 11 && variant <= 15) {
+        int G = 1 << (variant - 11);
+        return (long long)(kThreads / G) * A->max_row <= kStreamCap;
+    }
+    return false;
+}
+
+int spmv(pf2_csr* A, const double* x, double* y) {
+    plan_spmv(A);
+    return launch_spmv<false>(A, A->spmv_variant, x, y, nullptr, nullptr);
+}
+int spmv_dot(pf2_csr* A, const double* x, double* y, const CgState* st, double* dot_out) {
+    plan_spmv(A);
+    return launch_spmv<true>(A, A->spmv_variant, x, y, st, dot_out);
+}
+
+}  // namespace pf2
+
+using namespace pf2;
+
+extern "C" {
+
+int pf2_csr_upload(pf2_ctx* ctx, int rows, const int* indptr_host, const int* indices_host, const double* data_host, pf2_csr** out) {
+    PF2_CHECK(ctx && out && rows >= 0 && indptr_host, "bad arguments");
+    PF2_CUDA(cudaSetDevice(ctx->device));
+    pf2_csr* A = new pf2_csr();
+    A->ctx = ctx;
+    A->rows = rows;
+    A->nnz = indptr_host[rows];
+    PF2_TRY(dev_alloc(&A->indptr, (size_t)rows + 1));
+    PF2_TRY(dev_alloc(&A->indices, (size_t)A->nnz));
+    PF2_TRY(dev_alloc(&A->data, (size_t)A->nnz));
+    PF2_TRY(dev_alloc(&A->F, (size_t)rows));
+    int* tmp = nullptr;
+    PF2_TRY(dev_alloc(&tmp, (size_t)rows + 1));
+    PF2_CUDA(cudaMemcpyAsync(tmp, indptr_host, sizeof(int) * ((size_t)rows + 1), cudaMemcpyHostToDevice, ctx->stream));
+    widen_indptr_kernel<<<ctx->grid_for(rows + 1), kThreads, 0, ctx->stream>>>(rows + 1, tmp, A->indptr);
+    PF2_LAUNCH_CHECK();
+    ctx->launches++;
+    PF2_CUDA(cudaMemcpyAsync(A->indices, indices_host, sizeof(int) * (size_t)A->nnz, cudaMemcpyHostToDevice, ctx->stream));
+    if (data_host) PF2_CUDA(cudaMemcpyAsync(A->data, data_host, sizeof(double) * (size_t)A->nnz, cudaMemcpyHostToDevice, ctx->stream));
+    else PF2_CUDA(cudaMemsetAsync(A->data, 0, sizeof(double) * (size_t)A->nnz, ctx->stream));
+    PF2_CUDA(cudaMemsetAsync(A->F, 0, sizeof(double) * (size_t)rows, ctx->stream));
+    PF2_CUDA(cudaStreamSynchronize(ctx->stream));
+    PF2_CUDA(cudaFree(tmp));
+    PF2_TRY(csr_finalize_structure(A));
+    *out = A;
+    return PF2_OK;
+}
+
+int pf2_csr_destroy(pf2_csr* A) {
+    if (!A) return PF2_OK;
+    cudaSetDevice(A->ctx->device);
+    cudaStreamSynchronize(A->ctx->stream);
+    void* ptrs[] = { A->indptr, A->indices, A->data, A->F, A->diagpos, A->bmap, A->r, A->p, A->z, A->y, A->xw, A->bw, A->st,
+                     A->ilu, A->level_rows, A->level_rows_u };
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (A->h_st) cudaFreeHost(A->h_st);
+    for (int i = 0; i < 2; i++) if (A->ev[i]) cudaEventDestroy(A->ev[i]);
+    delete A;
+    return PF2_OK;
+}
+
+int pf2_csr_info(pf2_csr* A, int* rows, long long* nnz) {
+    if (rows) *rows = A->rows;
+    if (nnz) *nnz = A->nnz;
+    return PF2_OK;
+}
+
+int pf2_csr_download(pf2_csr* A, long long* indptr_host, int* indices_host, double* data_host, double* F_host) {
+    cudaStream_t s = A->ctx->stream;
+    if (indptr_host) PF2_CUDA(cudaMemcpyAsync(indptr_host, A->indptr, sizeof(long long) * ((size_t)A->rows + 1), cudaMemcpyDeviceToHost, s));
+    if (indices_host) PF2_CUDA(cudaMemcpyAsync(indices_host, A->indices, sizeof(int) * (size_t)A->nnz, cudaMemcpyDeviceToHost, s));
+    if (data_host) PF2_CUDA(cudaMemcpyAsync(data_host, A->data, sizeof(double) * (size_t)A->nnz, cudaMemcpyDeviceToHost, s));
+    if (F_host) PF2_CUDA(cudaMemcpyAsync(F_host, A->F, sizeof(double) * (size_t)A->rows, cudaMemcpyDeviceToHost, s));
+    PF2_CUDA(cudaStreamSynchronize(s));
+    return PF2_OK;
+}
+
+int pf2_csr_set_values(pf2_csr* A, const double* data_host) {
+    PF2_CUDA(cudaMemcpyAsync(A->data, data_host, sizeof(double) * (size_t)A->nnz, cudaMemcpyHostToDevice, A->ctx->stream));
+    PF2_CUDA(cudaStreamSynchronize(A->ctx->stream));
+    A->ilu_valid = false;
+    return PF2_OK;
+}
+int pf2_csr_device_F(pf2_csr* A, double** F_dev) { *F_dev = A->F; return PF2_OK; }
+int pf2_csr_device_data(pf2_csr* A, double** data_dev) { *data_dev = A->data; return PF2_OK; }
+
+int pf2_spmv(pf2_csr* A, const double* x_dev, double* y_dev) { return spmv(A, x_dev, y_dev); }
+
+int pf2_spmv_host(pf2_csr* A, const double* x_host, double* y_host) {
+    pf2_ctx* c = A->ctx;
+    double *x = nullptr, *y = nullptr;
+    PF2_TRY(dev_alloc(&x, (size_t)A->rows));
+    PF2_TRY(dev_alloc(&y, (size_t)A->rows));
+    PF2_CUDA(cudaMemcpyAsync(x, x_host, sizeof(double) * (size_t)A->rows, cudaMemcpyHostToDevice, c->stream));
+    int rc = spmv(A, x, y);
+    if (rc == PF2_OK) {
+        PF2_CUDA(cudaMemcpyAsync(y_host, y, sizeof(double) * (size_t)A->rows, cudaMemcpyDeviceToHost, c->stream));
+        PF2_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    cudaFree(x); cudaFree(y);
+    return rc;
+}
+
+int pf2_spmv_bench(pf2_csr* A, int variant, int reps, int flush_l2, double* ms_per_spmv) {
+    pf2_ctx* c = A->ctx;
+    plan_spmv(A);
+    if (variant == 0) variant = A->spmv_variant;
+    if (!variant_ok(A, variant)) { set_error("SpMV variant %d not applicable (max row %d)", variant, A->max_row); return PF2_E_UNSUPPORTED; }
+    double *x = nullptr, *y = nullptr;
+    PF2_TRY(dev_alloc(&x, (size_t)A->rows));
+    PF2_TRY(dev_alloc(&y, (size_t)A->rows));
+    std::vector<double> hx(A->rows);
+    for (int i = 0; i < A->rows; i++) hx[i] = 1.0 + 1e-3 * (i % 97);
+    PF2_CUDA(cudaMemcpyAsync(x, hx.data(), sizeof(double) * (size_t)A->rows, cudaMemcpyHostToDevice, c->stream));
+    for (int i = 0; i < 3; i++) PF2_TRY(launch_spmv<false>(A, variant, x, y, nullptr, nullptr));
+    double total = 0;
+    if (flush_l2) {
+        for (int i = 0; i < reps; i++) {
+            PF2_TRY(pf2_flush_l2(c));
+            PF2_TRY(pf2_timer_start(c));
+            PF2_TRY(launch_spmv<false>(A, variant, x, y, nullptr, nullptr));
+            double ms;
+            PF2_TRY(pf2_timer_stop(c, &ms));
+            total += ms;
+        }
+    } else {
+        PF2_TRY(pf2_timer_start(c));
+        for (int i = 0; i < reps; i++) PF2_TRY(launch_spmv<false>(A, variant, x, y, nullptr, nullptr));
+        PF2_TRY(pf2_timer_stop(c, &total));
+    }
+    *ms_per_spmv = total / reps;
+    cudaFree(x); cudaFree(y);
+    return PF2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,180 @@
+// element.cuh -- device-side element kinematics for Q4 and hex8 with 2x2 / 2x2x2 Gauss quadrature.
+//
+// Restates, with register-resident 2x2 / 3x3 algebra instead of heap Matrix<T> temporaries:
+//   ShapeFunction4Square::dNdr (ShapeFunction.h:186-191), ShapeFunction8Cubic::dNdr (ShapeFunction.h:318-329)
+//   Gauss4Square / Gauss8Cubic points, unit weights (GaussIntegration.h:143-157, 231-253)
+//   dXdr = dNdr*X ; J = det ; dNdX = dXdr^-1 * dNdr   (PlaneStrain.h:44-47, Solid.h:47-50, HeatTransfer.h:36-39)
+//   with Determinant / adjugate inverse as Matrix.h:326-360.
+// B^T D B is never formed as dense products: for the isotropic D / C of PlaneStrain.h:37-41 and Solid.h:37-44 the
+// (node a, node b) block is  K_ab[i][j] = c_n*ga_i*gb_i + mu*sum_{k!=i} ga_k*gb_k  (i == j)
+//                                     = lam*ga_i*gb_j + mu*ga_j*gb_i               (i != j)
+// with g = dN/dX, c_n = (1-V)c, lam = V c, mu = (1-2V)c/2, c = E/((1+V)(1-2V)); the strain order of Solid.h:52-60
+// (xx,yy,zz,xy,yz,zx) is what makes the shear terms pair up this way.
+#pragma once
+#include "common.cuh"
+
+namespace pf2 {
+
+#define PF2_INV_SQRT3 0.57735026918962584   // 1.0/sqrt(3.0) as GaussIntegration.h evaluates it
+
+// ---- Q4 -------------------------------------------------------------------------------------------------------
+// Gauss point g of Gauss4Square: (-,-),(+,-),(-,+),(+,+)
+__device__ __forceinline__ void q4_gauss(int g, double& r0, double& r1) {
+    r0 = (g & 1) ? PF2_INV_SQRT3 : -PF2_INV_SQRT3;
+    r1 = (g & 2) ? PF2_INV_SQRT3 : -PF2_INV_SQRT3;
+}
+// X: 4 nodes x 2.  Outputs dN/dX (gx[n], gy[n]) and det J.
+__device__ __forceinline__ void q4_grad(const double (&X)[4][2], double r0, double r1, double (&gx)[4], double (&gy)[4], double& det) {
+    const double d0[4] = { -0.25 * (1.0 - r1), 0.25 * (1.0 - r1), 0.25 * (1.0 + r1), -0.25 * (1.0 + r1) };
+    const double d1[4] = { -0.25 * (1.0 - r0), -0.25 * (1.0 + r0), 0.25 * (1.0 + r0), 0.25 * (1.0 - r0) };
+    double J00 = 0.0, J01 = 0.0, J10 = 0.0, J11 = 0.0;
+#pragma unroll
+    for (int n = 0; n < 4; n++) {
+        J00 += d0[n] * X[n][0]; J01 += d0[n] * X[n][1];
+        J10 += d1[n] * X[n][0]; J11 += d1[n] * X[n][1];
+    }
+    det = J00 * J11 - J01 * J10;
+    const double i00 = J11 / det, i01 = -J01 / det, i10 = -J10 / det, i11 = J00 / det;
+#pragma unroll
+    for (int n = 0; n < 4; n++) {
+        gx[n] = i00 * d0[n] + i01 * d1[n];
+        gy[n] = i10 * d0[n] + i11 * d1[n];
+    }
+}
+
+// ---- hex8 ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double h8_sx(int n) { return ((n + 1) & 2) ? 1.0 : -1.0; }   // -,+,+,-,-,+,+,-
+__device__ __forceinline__ double h8_sy(int n) { return (n & 2) ? 1.0 : -1.0; }         // -,-,+,+,-,-,+,+
+__device__ __forceinline__ double h8_sz(int n) { return (n & 4) ? 1.0 : -1.0; }         // -,-,-,-,+,+,+,+
+// Gauss8Cubic orders its points like the nodes (bottom CCW, top CCW)
+__device__ __forceinline__ void h8_gauss(int g, double& r0, double& r1, double& r2) {
+    r0 = h8_sx(g) * PF2_INV_SQRT3; r1 = h8_sy(g) * PF2_INV_SQRT3; r2 = h8_sz(g) * PF2_INV_SQRT3;
+}
+__device__ __forceinline__ void h8_grad(const double (&X)[8][3], double r0, double r1, double r2,
+                                        double (&gx)[8], double (&gy)[8], double (&gz)[8], double& det) {
+    double d0[8], d1[8], d2[8];
+    double J[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } };
+#pragma unroll
+    for (int n = 0; n < 8; n++) {
+        const double sx = h8_sx(n), sy = h8_sy(n), sz = h8_sz(n);
+        d0[n] = sx * 0.125 * (1.0 + sy * r1) * (1.0 + sz * r2);
+        d1[n] = sy * 0.125 * (1.0 + sz * r2) * (1.0 + sx * r0);
+        d2[n] = sz * 0.125 * (1.0 + sx * r0) * (1.0 + sy * r1);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { J[0][k] += d0[n] * X[n][k]; J[1][k] += d1[n] * X[n][k]; J[2][k] += d2[n] * X[n][k]; }
+    }
+    det = -J[2][2] * J[0][1] * J[1][0] - J[2][1] * J[1][2] * J[0][0] - J[0][2] * J[1][1] * J[2][0]
+          + J[2][0] * J[0][1] * J[1][2] + J[2][1] * J[1][0] * J[0][2] + J[0][0] * J[1][1] * J[2][2];
+    // adjugate / det
+    const double i00 = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / det;
+    const double i01 = -(J[0][1] * J[2][2] - J[0][2] * J[2][1]) / det;
+    const double i02 = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
+    const double i10 = -(J[1][0] * J[2][2] - J[1][2] * J[2][0]) / det;
+    const double i11 = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det;
+    const double i12 = -(J[0][0] * J[1][2] - J[0][2] * J[1][0]) / det;
+    const double i20 = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det;
+    const double i21 = -(J[0][0] * J[2][1] - J[0][1] * J[2][0]) / det;
+    const double i22 = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+#pragma unroll
+    for (int n = 0; n < 8; n++) {
+        gx[n] = i00 * d0[n] + i01 * d1[n] + i02 * d2[n];
+        gy[n] = i10 * d0[n] + i11 * d1[n] + i12 * d2[n];
+        gz[n] = i20 * d0[n] + i21 * d1[n] + i22 * d2[n];
+    }
+}
+
+// isotropic coefficients for unit modulus
+struct Iso {
+    double cn, lam, mu;
+    __device__ __forceinline__ Iso(double V) {
+        const double c = 1.0 / ((1.0 + V) * (1.0 - 2.0 * V));
+        cn = (1.0 - V) * c; lam = V * c; mu = 0.5 * (1.0 - 2.0 * V) * c;
+    }
+};
+
+// SIMP interpolation of the drivers (sample_optimize_density_oc.cpp:123)
+__device__ __forceinline__ double simp_modulus(double rho, double E0, double E1, double p) {
+    const double rp = pow(rho, p);
+    return E1 * rp + E0 * (1.0 - rp);
+}
+
+// Rows of local node `a` of the element matrix for unit modulus (scaled by the caller).
+// acc[i][b*NDOF + j], i = dof of node a.
+template <int EQ> struct ElemTraits;
+template <> struct ElemTraits<PF2_EQ_PLANESTRAIN> { static constexpr int DIM = 2, NPE = 4, NDOF = 2; };
+template <> struct ElemTraits<PF2_EQ_HEAT> { static constexpr int DIM = 2, NPE = 4, NDOF = 1; };
+template <> struct ElemTraits<PF2_EQ_SOLID> { static constexpr int DIM = 3, NPE = 8, NDOF = 3; };
+
+__device__ __forceinline__ void planestrain_rows(const double (&X)[4][2], int a, double V, double t, double (&acc)[2][8]) {
+    const Iso c(V);
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = 0.0;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        double r0, r1, gx[4], gy[4], det;
+        q4_gauss(g, r0, r1);
+        q4_grad(X, r0, r1, gx, gy, det);
+        const double w = det * t;
+        double ax = gx[0], ay = gy[0];
+#pragma unroll
+        for (int n = 1; n < 4; n++) if (n == a) { ax = gx[n]; ay = gy[n]; }
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            acc[0][2 * b]     += (c.cn * ax * gx[b] + c.mu * ay * gy[b]) * w;
+            acc[0][2 * b + 1] += (c.lam * ax * gy[b] + c.mu * ay * gx[b]) * w;
+            acc[1][2 * b]     += (c.lam * ay * gx[b] + c.mu * ax * gy[b]) * w;
+            acc[1][2 * b + 1] += (c.cn * ay * gy[b] + c.mu * ax * gx[b]) * w;
+        }
+    }
+}
+
+__device__ __forceinline__ void heat_rows(const double (&X)[4][2], int a, double t, double (&acc)[1][4]) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[0][j] = 0.0;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        double r0, r1, gx[4], gy[4], det;
+        q4_gauss(g, r0, r1);
+        q4_grad(X, r0, r1, gx, gy, det);
+        const double w = det * t;
+        double ax = gx[0], ay = gy[0];
+#pragma unroll
+        for (int n = 1; n < 4; n++) if (n == a) { ax = gx[n]; ay = gy[n]; }
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[0][b] += (ax * gx[b] + ay * gy[b]) * w;
+    }
+}
+
+__device__ __forceinline__ void solid_rows(const double (&X)[8][3], int a, double V, double (&acc)[3][24]) {
+    const Iso c(V);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 24; j++) acc[i][j] = 0.0;
+#pragma unroll 1
+    for (int g = 0; g < 8; g++) {
+        double r0, r1, r2, gx[8], gy[8], gz[8], det;
+        h8_gauss(g, r0, r1, r2);
+        h8_grad(X, r0, r1, r2, gx, gy, gz, det);
+        double ga[3] = { gx[0], gy[0], gz[0] };
+#pragma unroll
+        for (int n = 1; n < 8; n++) if (n == a) { ga[0] = gx[n]; ga[1] = gy[n]; ga[2] = gz[n]; }
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const double gb[3] = { gx[b], gy[b], gz[b] };
+            const double dotab = ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2];
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    const double v = (i == j) ? (c.cn * ga[i] * gb[i] + c.mu * (dotab - ga[i] * gb[i]))
+                                              : (c.lam * ga[i] * gb[j] + c.mu * ga[j] * gb[i]);
+                    acc[i][3 * b + j] += v * det;
+                }
+        }
+    }
+}
+
+}  // namespace pf2

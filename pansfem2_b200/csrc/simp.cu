@@ -1,0 +1,208 @@
+// simp.cu -- the device-resident SIMP design loop.
+//
+// One pf2_simp_iterate call is one pass of the loop body of sample/optimize/sample_optimize_density_oc.cpp:83-208
+// (and ..._mma.cpp, identical up to the optimiser call) with every field -- design s, density rho, K, F, u,
+// sensitivities -- resident in HBM from the first iteration to the last:
+//    :85-88   beta doubling                        host scalar
+//    :93      rho = filter(s)                      filter_apply (+ volume sum for :99-105)
+//    :113-129 BCs, element loop, Assembling, loads assemble_device   (numbering and pattern were built once)
+//    :131-133 CSR, ScalingCG, Disassembling        solve + disassemble
+//    :136-162 reaction, compliance, sensitivities  compliance_sens_device
+//    :168-169 filtered sensitivities               filter_sens (dfds and dgds in one pass)
+//    :192-195 IsConvergence                        host compare of two scalars
+//    :198-207 OC / MMA update                      oc_update / mma_update
+// Only scalars (f, g, iteration counts, done flags) cross to the host.
+#include "types.cuh"
+
+namespace pf2 {
+int assemble_device(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq, const double* modulus_dev, const double* rho_dev,
+                    const double params[5], int nload, const int* load_node_dev, const int* load_dof_dev, const double* load_val_dev);
+int compliance_sens_device(pf2_mesh* mesh, int eq, const double* u_nodal, const double* rho, const double params[6], double* f_dev,
+                           double* dfdrho, double* r_nodal);
+int solve(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out);
+int filter_apply(pf2_filter* f, const double* s, double* rho, double* sum_out, OcState* oc);
+int filter_sens(pf2_filter* f, const double* s, const double* g1, double* out1, const double* g2, double c2, double* out2);
+int oc_update(pf2_oc* oc, pf2_filter* filter, double weightlimit, double scale1, double* x, double f, const double* dfdx,
+              const double* dgdx, int* steps_out, double* lambda_out);
+int mma_update(pf2_mma* mm, double* xk, double f, const double* dfdx, const double* g_host, const double* dgdx, int* newton_out);
+}  // namespace pf2
+
+using namespace pf2;
+
+struct pf2_simp {
+    pf2_ctx* ctx = nullptr;
+    pf2_mesh* mesh = nullptr;
+    pf2_dofmap* map = nullptr;
+    pf2_csr* A = nullptr;
+    pf2_filter* filter = nullptr;
+    pf2_oc* oc = nullptr;
+    pf2_mma* mma = nullptr;
+    int eq = 0, opt_kind = 0, solver = PF2_SOLVER_SCALINGCG;
+    int n = 0, ndof = 0;
+    double E0, E1, V, p, weightlimit, scale0, scale1, thick, beta;
+    int beta_period = 0, itrmax = 100000;
+    double cgeps = 1.0e-10;
+    int k = 0;
+    int nload = 0;
+    int *ld_node = nullptr, *ld_dof = nullptr;
+    double* ld_val = nullptr;
+    double *s = nullptr, *rho = nullptr, *xsol = nullptr, *u = nullptr, *r_nodal = nullptr, *dfdrho = nullptr, *dfds = nullptr, *dgds = nullptr;
+    cudaEvent_t ev[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    double phase_ms[6] = { 0, 0, 0, 0, 0, 0 };
+};
+
+static int simp_iterate(pf2_simp* S, int check_convergence, double stats[8]) {
+    pf2_ctx* c = S->ctx;
+    cudaStream_t s = c->stream;
+    PF2_CUDA(cudaSetDevice(c->device));
+    PF2_CUDA(cudaEventRecord(S->ev[0], s));
+    if (S->beta_period > 0 && S->k % S->beta_period == 0) S->beta *= 2.0;       // driver :85-88
+    S->filter->beta = S->beta;
+    PF2_TRY(filter_apply(S->filter, S->s, S->rho, c->scalars + 1, nullptr));
+    PF2_CUDA(cudaEventRecord(S->ev[1], s));
+    const double ap[5] = { S->E0, S->E1, S->V, S->p, S->thick };
+    PF2_TRY(assemble_device(S->A, S->mesh, S->map, S->eq, nullptr, S->rho, ap, S->nload, S->ld_node, S->ld_dof, S->ld_val));
+    PF2_CUDA(cudaEventRecord(S->ev[2], s));
+    int iters = 0;
+    double relres = 0.0;
+    int rc = solve(S->A, S->solver, S->A->F, S->xsol, S->itrmax, S->cgeps, &iters, &relres);
+    if (rc != PF2_OK && rc != PF2_E_NOCONV) return rc;      // non-convergence: the reference prints and carries on
+    PF2_TRY(pf2_disassemble(S->map, S->xsol, S->u));
+    PF2_CUDA(cudaEventRecord(S->ev[3], s));
+    const double sp[6] = { S->E0, S->E1, S->V, S->p, S->thick, S->scale0 };
+    PF2_TRY(compliance_sens_device(S->mesh, S->eq, S->u, S->rho, sp, c->scalars, S->dfdrho, nullptr));
+    PF2_CUDA(cudaEventRecord(S->ev[4], s));
+    const double dgdrho = S->scale1 / (S->weightlimit * S->n);                  // driver :104
+    PF2_TRY(filter_sens(S->filter, S->s, S->dfdrho, S->dfds, nullptr, dgdrho, S->dgds));
+    PF2_CUDA(cudaEventRecord(S->ev[5], s));
+    PF2_CUDA(cudaMemcpyAsync(c->h_scalars, c->scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    PF2_CUDA(cudaStreamSynchronize(s));
+    const double f = c->h_scalars[0];
+    const double g = S->scale1 * c->h_scalars[1] / (S->weightlimit * S->n) - 1.0 * S->scale1;   // driver :99-105
+    int converged = 0;
+    if (S->oc) PF2_TRY(pf2_oc_is_convergence(S->oc, f, &converged));
+    else PF2_TRY(pf2_mma_is_convergence(S->mma, f, &converged));
+    int opt_steps = 0;
+    if (!(check_convergence && converged)) {
+        if (S->oc) PF2_TRY(oc_update(S->oc, S->filter, S->weightlimit, S->scale1, S->s, f, S->dfds, S->dgds, &opt_steps, nullptr));
+        else PF2_TRY(mma_update(S->mma, S->s, f, S->dfds, &g, S->dgds, &opt_steps));
+    }
+    PF2_CUDA(cudaEventRecord(S->ev[6], s));
+    PF2_CUDA(cudaEventSynchronize(S->ev[6]));
+    for (int i = 0; i < 6; i++) {
+        float ms = 0;
+        PF2_CUDA(cudaEventElapsedTime(&ms, S->ev[i], S->ev[i + 1]));
+        S->phase_ms[i] = ms;
+    }
+    if (stats) {
+        stats[0] = f; stats[1] = g; stats[2] = (check_convergence && converged) ? 1.0 : 0.0; stats[3] = iters; stats[4] = relres;
+        stats[5] = opt_steps; stats[6] = S->beta; stats[7] = S->k;
+    }
+    S->k++;
+    return PF2_OK;
+}
+
+extern "C" {
+
+int pf2_simp_create(pf2_ctx* ctx, pf2_mesh* mesh, pf2_dofmap* map, pf2_csr* A, pf2_filter* filter, int eq, int opt_kind,
+                    const double* optp, const double params[12], int nload, const int* load_node_host,
+                    const int* load_dof_host, const double* load_val_host, pf2_simp** out) {
+    PF2_CHECK(ctx && mesh && map && A && filter && optp && params && out, "null argument");
+    PF2_CHECK(filter->n == mesh->nelem, "filter size must equal the element count");
+    PF2_CHECK(opt_kind == PF2_OPT_OC || opt_kind == PF2_OPT_MMA, "unknown optimiser");
+    PF2_CUDA(cudaSetDevice(ctx->device));
+    pf2_simp* S = new pf2_simp();
+    S->ctx = ctx; S->mesh = mesh; S->map = map; S->A = A; S->filter = filter; S->eq = eq; S->opt_kind = opt_kind;
+    S->n = mesh->nelem; S->ndof = map->ndof;
+    S->E0 = params[0]; S->E1 = params[1]; S->V = params[2]; S->p = params[3]; S->weightlimit = params[4];
+    S->scale0 = params[5]; S->scale1 = params[6]; S->thick = params[7]; S->beta = params[8];
+    S->beta_period = (int)params[9]; S->itrmax = (int)params[10]; S->cgeps = params[11];
+    const size_t n = (size_t)S->n, nd = (size_t)mesh->nnode * map->ndof;
+    PF2_TRY(dev_alloc(&S->s, n)); PF2_TRY(dev_alloc(&S->rho, n)); PF2_TRY(dev_alloc(&S->dfdrho, n));
+    PF2_TRY(dev_alloc(&S->dfds, n)); PF2_TRY(dev_alloc(&S->dgds, n));
+    PF2_TRY(dev_alloc(&S->xsol, (size_t)A->rows)); PF2_TRY(dev_alloc(&S->u, nd)); PF2_TRY(dev_alloc(&S->r_nodal, nd));
+    PF2_CUDA(cudaMemsetAsync(S->s, 0, sizeof(double) * n, ctx->stream));
+    S->nload = nload;
+    if (nload > 0) {
+        PF2_TRY(dev_alloc(&S->ld_node, (size_t)nload)); PF2_TRY(dev_alloc(&S->ld_dof, (size_t)nload)); PF2_TRY(dev_alloc(&S->ld_val, (size_t)nload));
+        PF2_CUDA(cudaMemcpyAsync(S->ld_node, load_node_host, sizeof(int) * (size_t)nload, cudaMemcpyHostToDevice, ctx->stream));
+        PF2_CUDA(cudaMemcpyAsync(S->ld_dof, load_dof_host, sizeof(int) * (size_t)nload, cudaMemcpyHostToDevice, ctx->stream));
+        PF2_CUDA(cudaMemcpyAsync(S->ld_val, load_val_host, sizeof(double) * (size_t)nload, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (opt_kind == PF2_OPT_OC) {
+        PF2_TRY(pf2_oc_create(ctx, S->n, optp[0], optp[1], optp[2], optp[3], optp[4], &S->oc));
+    } else {
+        std::vector<double> xmin(n, optp[11]), xmax(n, optp[12]);
+        PF2_TRY(pf2_mma_create(ctx, S->n, 1, optp[7], &optp[8], &optp[9], &optp[10], xmin.data(), xmax.data(), &S->mma));
+        PF2_TRY(pf2_mma_set_parameters(S->mma, optp[0], optp[1], optp[2], optp[3], optp[4], optp[5], optp[6]));
+    }
+    for (int i = 0; i < 7; i++) PF2_CUDA(cudaEventCreate(&S->ev[i]));
+    PF2_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = S;
+    return PF2_OK;
+}
+
+int pf2_simp_destroy(pf2_simp* S) {
+    if (!S) return PF2_OK;
+    cudaStreamSynchronize(S->ctx->stream);
+    pf2_oc_destroy(S->oc);
+    pf2_mma_destroy(S->mma);
+    void* ptrs[] = { S->s, S->rho, S->xsol, S->u, S->r_nodal, S->dfdrho, S->dfds, S->dgds, S->ld_node, S->ld_dof, S->ld_val };
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < 7; i++) if (S->ev[i]) cudaEventDestroy(S->ev[i]);
+    delete S;
+    return PF2_OK;
+}
+
+int pf2_simp_set_design(pf2_simp* S, const double* s_host) {
+    PF2_CUDA(cudaMemcpyAsync(S->s, s_host, sizeof(double) * (size_t)S->n, cudaMemcpyHostToDevice, S->ctx->stream));
+    PF2_CUDA(cudaStreamSynchronize(S->ctx->stream));
+    return PF2_OK;
+}
+int pf2_simp_set_solver(pf2_simp* S, int solver) {
+    PF2_CHECK(solver >= 0 && solver <= 2, "unknown solver");
+    S->solver = solver;
+    return PF2_OK;
+}
+
+int pf2_simp_iterate(pf2_simp* S, int check_convergence, double stats[8]) { return simp_iterate(S, check_convergence, stats); }
+
+int pf2_simp_iterate_host(pf2_simp* S, int check_convergence, const double* s_in_host, double* s_out_host, double* rho_out_host, double stats[8]) {
+    cudaStream_t s = S->ctx->stream;
+    const size_t bytes = sizeof(double) * (size_t)S->n;
+    if (s_in_host) PF2_CUDA(cudaMemcpyAsync(S->s, s_in_host, bytes, cudaMemcpyHostToDevice, s));
+    PF2_TRY(simp_iterate(S, check_convergence, stats));
+    if (s_out_host) PF2_CUDA(cudaMemcpyAsync(s_out_host, S->s, bytes, cudaMemcpyDeviceToHost, s));
+    if (rho_out_host) PF2_CUDA(cudaMemcpyAsync(rho_out_host, S->rho, bytes, cudaMemcpyDeviceToHost, s));
+    PF2_CUDA(cudaStreamSynchronize(s));
+    return PF2_OK;
+}
+
+int pf2_simp_get(pf2_simp* S, double* s_host, double* rho_host, double* u_nodal_host, double* r_nodal_host) {
+    pf2_ctx* c = S->ctx;
+    cudaStream_t s = c->stream;
+    const size_t nb = sizeof(double) * (size_t)S->n, ndb = sizeof(double) * (size_t)S->mesh->nnode * S->ndof;
+    if (s_host) PF2_CUDA(cudaMemcpyAsync(s_host, S->s, nb, cudaMemcpyDeviceToHost, s));
+    if (rho_host) PF2_CUDA(cudaMemcpyAsync(rho_host, S->rho, nb, cudaMemcpyDeviceToHost, s));
+    if (u_nodal_host) PF2_CUDA(cudaMemcpyAsync(u_nodal_host, S->u, ndb, cudaMemcpyDeviceToHost, s));
+    if (r_nodal_host) {
+        // reaction forces r = K_full(rho) u (driver :136-150), recomputed on demand (the VTK dump is off the hot path)
+        const double sp[6] = { S->E0, S->E1, S->V, S->p, S->thick, S->scale0 };
+        PF2_TRY(compliance_sens_device(S->mesh, S->eq, S->u, S->rho, sp, c->scalars + 2, nullptr, S->r_nodal));
+        PF2_CUDA(cudaMemcpyAsync(r_nodal_host, S->r_nodal, ndb, cudaMemcpyDeviceToHost, s));
+    }
+    PF2_CUDA(cudaStreamSynchronize(s));
+    return PF2_OK;
+}
+
+int pf2_simp_phase_ms(pf2_simp* S, double ms[6]) {
+    for (int i = 0; i < 6; i++) ms[i] = S->phase_ms[i];
+    return PF2_OK;
+}
+int pf2_simp_cg_stats(pf2_simp* S, double* spmv_ms_avg, long long* spmv_calls) {
+    if (spmv_ms_avg) *spmv_ms_avg = S->A->spmv_calls ? S->A->spmv_ms_total / S->A->spmv_calls : 0.0;
+    if (spmv_calls) *spmv_calls = S->A->spmv_calls;
+    return PF2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,390 @@
+// solver.cu -- CG / ScalingCG / ILU0CG on the device (replaces CG.h:124-154, 420-453, 320-352) and
+//              ILU0 / PreILU0 (CG.h:258-315) with level scheduling.
+//
+// One iteration of the Jacobi-preconditioned solver is three memory-bound kernels:
+//   K1  y = A p, fused p.y                                   (spmv_dot, csr.cu)        12*nnz + 24*n bytes
+//   K2  alpha = rho/p.y ; x += alpha p ; r -= alpha y ; z = r/D ; z.r, r.r ; last CTA: beta, convergence, counter
+//                                                                                       read x,p,r,y,D write x,r,z = 64*n
+//   K3  p = beta p + z                                                                  24*n
+// alpha, beta, the residual norms, the iteration counter and the `done` flag live in device memory (CgState); the
+// host only polls `done` once per chunk of iterations, one chunk behind the GPU, so the queue never drains.
+// After convergence every kernel early-exits, so x is exactly the iterate the reference returns (CG.h:443-448).
+#include "types.cuh"
+
+namespace pf2 {
+
+int spmv(pf2_csr* A, const double* x, double* y);
+int spmv_dot(pf2_csr* A, const double* x, double* y, const CgState* st, double* dot_out);
+
+// x0 = 0 ; r = b - A*x0 = b ; z = M^-1 r ; p = z ; bb = b.b ; rho = z.r ; rr = r.r      (CG.h:422-428)
+// MODE 0: no preconditioner, 1: Jacobi (z = r / diag), 2: ILU (z filled in later)
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+cg_init_kernel(int n, const double* __restrict__ b, const long long* __restrict__ indptr, const int* __restrict__ diagpos,
+               const double* __restrict__ data, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
+               double* __restrict__ p, CgState* st, int maxit, double eps, double* partials, unsigned int* ticket) {
+    double v[2] = { 0.0, 0.0 };
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double bi = b[i];
+        x[i] = 0.0;
+        r[i] = bi;
+        double zi = bi;
+        if (MODE == 1) {
+            const int dp = diagpos[i];
+            const double d = dp >= 0 ? data[indptr[i] + dp] : 0.0;
+            zi = bi / d;
+        }
+        if (MODE != 2) { z[i] = zi; p[i] = zi; v[1] += zi * bi; }
+        v[0] += bi * bi;
+    }
+    if (grid_sum_last<2>(v, partials, ticket) && threadIdx.x == 0) {
+        st->bb = v[0]; st->rr = v[0]; st->rho = v[1]; st->pAp = 0.0; st->beta = 0.0; st->zr_new = 0.0;
+        st->iter = 0; st->done = 0; st->maxit = maxit; st->eps = eps;
+    }
+}
+
+// the scalar tail of one iteration: beta = rho'/rho ; rho = rho' ; convergence test ||r|| < eps*||b||   (CG.h:437-448)
+__device__ __forceinline__ void cg_finalize(CgState* st, double zr, double rr) {
+    st->beta = zr / st->rho;
+    st->rho = zr;
+    st->rr = rr;
+    st->iter = st->iter + 1;
+    if (sqrt(rr) < st->eps * sqrt(st->bb)) st->done = 1;
+}
+
+// K2.  MODE 0/1 finish the iteration here; MODE 2 (ILU) only updates x, r and r.r -- z comes from the triangular solves.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+cg_update_kernel(int n, const double* __restrict__ p, const double* __restrict__ y, const long long* __restrict__ indptr,
+                 const int* __restrict__ diagpos, const double* __restrict__ data, double* __restrict__ x,
+                 double* __restrict__ r, double* __restrict__ z, CgState* st, double* partials, unsigned int* ticket) {
+    if (st->done) return;
+    const double alpha = st->rho / st->pAp;
+    double v[2] = { 0.0, 0.0 };
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        x[i] = x[i] + alpha * p[i];
+        const double ri = r[i] + (-alpha) * y[i];
+        r[i] = ri;
+        v[1] += ri * ri;
+        if (MODE == 0) { v[0] += ri * ri; }
+        else if (MODE == 1) {
+            const int dp = diagpos[i];
+            const double d = dp >= 0 ? data[indptr[i] + dp] : 0.0;
+            const double zi = ri / d;
+            z[i] = zi;
+            v[0] += zi * ri;
+        }
+    }
+    if (grid_sum_last<2>(v, partials, ticket) && threadIdx.x == 0) {
+        if (MODE == 2) st->rr = v[1];
+        else cg_finalize(st, v[0], v[1]);
+    }
+}
+
+// ILU path: rho' = z.r after the triangular solves, then the scalar tail
+__global__ void __launch_bounds__(kThreads)
+cg_dot_finalize_kernel(int n, const double* __restrict__ z, const double* __restrict__ r, CgState* st, int init,
+                       const double* __restrict__ zsrc, double* __restrict__ p, double* partials, unsigned int* ticket) {
+    if (!init && st->done) return;
+    double v[1] = { 0.0 };
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        v[0] += z[i] * r[i];
+        if (init) p[i] = zsrc[i];
+    }
+    if (grid_sum_last<1>(v, partials, ticket) && threadIdx.x == 0) {
+        if (init) st->rho = v[0];
+        else cg_finalize(st, v[0], st->rr);
+    }
+}
+
+// K3: p = beta p + z   (xeaxpy, CG.h:41-49); MODE 0 uses r as z
+__global__ void __launch_bounds__(kThreads)
+cg_pupdate_kernel(int n, const double* __restrict__ z, double* __restrict__ p, const CgState* __restrict__ st) {
+    // the iteration that set `done` still updated p in the reference; x is what matters and it is frozen, so skip
+    if (st->done) return;
+    const double beta = st->beta;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = beta * p[i] + z[i];
+}
+
+// ---- ILU(0) ----------------------------------------------------------------------------------------------------
+// Row i depends on rows k < i that appear in its pattern.  Levels are computed on the host once per pattern; one
+// thread factors one row of the current level following the reference's entry order exactly (CG.h:262-281).
+__global__ void ilu0_level_kernel(int nrows_level, const int* __restrict__ rows_of_level, const long long* __restrict__ indptr,
+                                  const int* __restrict__ indices, const int* __restrict__ diagpos,
+                                  const double* __restrict__ a, double* __restrict__ q) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nrows_level) return;
+    const int i = rows_of_level[t];
+    const long long s = indptr[i], e = indptr[i + 1];
+    for (long long n = s; n < e; n++) {
+        const int j = indices[n];
+        double qij = a[n];
+        const int lim = (i <= j) ? i : j;
+        for (long long qq = s; qq < e; qq++) {
+            const int k = indices[qq];
+            if (k >= lim) break;
+            // find j in row k
+            long long lo = indptr[k], hi = indptr[k + 1] - 1;
+            while (lo <= hi) {
+                long long mid = (lo + hi) >> 1;
+                int cc = indices[mid];
+                if (cc == j) { qij -= q[qq] * q[mid]; break; }
+                if (cc < j) lo = mid + 1; else hi = mid - 1;
+            }
+        }
+        if (i > j) qij /= q[indptr[j] + diagpos[j]];
+        q[n] = qij;
+    }
+}
+
+// one level of the forward (unit-L) or backward (U) substitution of PreILU0 (CG.h:289-315); one thread per row
+template <bool FORWARD>
+__global__ void ilu0_sweep_level_kernel(int nrows_level, const int* __restrict__ rows_of_level,
+                                        const long long* __restrict__ indptr, const int* __restrict__ indices,
+                                        const int* __restrict__ diagpos, const double* __restrict__ q,
+                                        double* __restrict__ v, const CgState* __restrict__ st) {
+    if (st != nullptr && st->done) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nrows_level) return;
+    const int i = rows_of_level[t];
+    const long long s = indptr[i], e = indptr[i + 1];
+    double vi = v[i];
+    if (FORWARD) {
+        for (long long k = s; k < e; k++) {
+            const int c = indices[k];
+            if (c < i) vi -= q[k] * v[c]; else break;
+        }
+    } else {
+        for (long long k = e - 1; k >= s; k--) {
+            const int c = indices[k];
+            if (c > i) vi -= q[k] * v[c]; else break;
+        }
+        vi /= q[s + diagpos[i]];
+    }
+    v[i] = vi;
+}
+
+static int ensure_workspace(pf2_csr* A) {
+    if (A->r) return PF2_OK;
+    const size_t n = (size_t)A->rows;
+    PF2_TRY(dev_alloc(&A->r, n)); PF2_TRY(dev_alloc(&A->p, n)); PF2_TRY(dev_alloc(&A->z, n)); PF2_TRY(dev_alloc(&A->y, n));
+    PF2_TRY(dev_alloc(&A->st, 1));
+    PF2_CUDA(cudaHostAlloc((void**)&A->h_st, 2 * sizeof(CgState), cudaHostAllocDefault));
+    PF2_CUDA(cudaEventCreateWithFlags(&A->ev[0], cudaEventDisableTiming));
+    PF2_CUDA(cudaEventCreateWithFlags(&A->ev[1], cudaEventDisableTiming));
+    return PF2_OK;
+}
+
+// host-side level schedule of the strictly-lower (forward) and strictly-upper (backward) dependency graphs
+static int schedule_levels(pf2_csr* A, const std::vector<long long>& indptr, const std::vector<int>& indices, bool lower,
+                           std::vector<int>& ptr, int** d_rows) {
+    const int n = A->rows;
+    std::vector<int> level(n, 0);
+    int maxl = 0;
+    if (lower) {
+        for (int i = 0; i < n; i++) {
+            int l = 0;
+            for (long long k = indptr[i]; k < indptr[i + 1] && indices[k] < i; k++) l = std::max(l, level[indices[k]] + 1);
+            level[i] = l; maxl = std::max(maxl, l);
+        }
+    } else {
+        for (int i = n - 1; i >= 0; i--) {
+            int l = 0;
+            for (long long k = indptr[i + 1] - 1; k >= indptr[i] && indices[k] > i; k--) l = std::max(l, level[indices[k]] + 1);
+            level[i] = l; maxl = std::max(maxl, l);
+        }
+    }
+    const int L = n ? maxl + 1 : 0;
+    ptr.assign((size_t)L + 1, 0);
+    std::vector<int> rows(n);
+    for (int i = 0; i < n; i++) ptr[level[i] + 1]++;
+    for (int l = 0; l < L; l++) ptr[l + 1] += ptr[l];
+    std::vector<int> cur(ptr.begin(), ptr.begin() + L);
+    for (int i = 0; i < n; i++) rows[cur[level[i]]++] = i;
+    PF2_TRY(dev_alloc(d_rows, (size_t)n));
+    PF2_CUDA(cudaMemcpy(*d_rows, rows.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
+    return PF2_OK;
+}
+
+static int build_levels(pf2_csr* A) {
+    if (A->level_rows) return PF2_OK;
+    pf2_ctx* c = A->ctx;
+    const int n = A->rows;
+    std::vector<long long> indptr((size_t)n + 1);
+    std::vector<int> indices((size_t)A->nnz);
+    PF2_CUDA(cudaMemcpyAsync(indptr.data(), A->indptr, sizeof(long long) * ((size_t)n + 1), cudaMemcpyDeviceToHost, c->stream));
+    PF2_CUDA(cudaMemcpyAsync(indices.data(), A->indices, sizeof(int) * (size_t)A->nnz, cudaMemcpyDeviceToHost, c->stream));
+    PF2_CUDA(cudaStreamSynchronize(c->stream));
+    PF2_TRY(schedule_levels(A, indptr, indices, true, A->h_level_ptr, &A->level_rows));
+    PF2_TRY(schedule_levels(A, indptr, indices, false, A->h_level_ptr_u, &A->level_rows_u));
+    return PF2_OK;
+}
+
+int ilu0_factor(pf2_csr* A) {
+    if (A->ilu_valid) return PF2_OK;
+    pf2_ctx* c = A->ctx;
+    PF2_TRY(build_levels(A));
+    if (!A->ilu) PF2_TRY(dev_alloc(&A->ilu, (size_t)A->nnz));
+    const int L = (int)A->h_level_ptr.size() - 1;
+    for (int l = 0; l < L; l++) {
+        const int cnt = A->h_level_ptr[l + 1] - A->h_level_ptr[l];
+        ilu0_level_kernel<<<(cnt + 127) / 128, 128, 0, c->stream>>>(cnt, A->level_rows + A->h_level_ptr[l], A->indptr, A->indices,
+                                                                    A->diagpos, A->data, A->ilu);
+        c->launches++;
+    }
+    PF2_LAUNCH_CHECK();
+    A->ilu_valid = true;
+    return PF2_OK;
+}
+
+// v = (LU)^-1 v in place
+int ilu0_apply(pf2_csr* A, double* v, const CgState* st) {
+    pf2_ctx* c = A->ctx;
+    const int L = (int)A->h_level_ptr.size() - 1, Lu = (int)A->h_level_ptr_u.size() - 1;
+    for (int l = 1; l < L; l++) {      // level 0 rows have no strictly-lower entries
+        const int cnt = A->h_level_ptr[l + 1] - A->h_level_ptr[l];
+        ilu0_sweep_level_kernel<true><<<(cnt + 127) / 128, 128, 0, c->stream>>>(cnt, A->level_rows + A->h_level_ptr[l], A->indptr,
+                                                                                A->indices, A->diagpos, A->ilu, v, st);
+        c->launches++;
+    }
+    for (int l = 0; l < Lu; l++) {
+        const int cnt = A->h_level_ptr_u[l + 1] - A->h_level_ptr_u[l];
+        ilu0_sweep_level_kernel<false><<<(cnt + 127) / 128, 128, 0, c->stream>>>(cnt, A->level_rows_u + A->h_level_ptr_u[l], A->indptr,
+                                                                                 A->indices, A->diagpos, A->ilu, v, st);
+        c->launches++;
+    }
+    PF2_LAUNCH_CHECK();
+    return PF2_OK;
+}
+
+// enqueue one iteration
+static int enqueue_iteration(pf2_csr* A, int solver, double* x) {
+    pf2_ctx* c = A->ctx;
+    const int n = A->rows;
+    const int grid = c->grid_for(n, 2);
+    PF2_TRY(spmv_dot(A, A->p, A->y, A->st, &A->st->pAp));
+#define UPD(M) cg_update_kernel<M><<<grid, kThreads, 0, c->stream>>>(n, A->p, A->y, A->indptr, A->diagpos, A->data, x, A->r, A->z, A->st, c->red.partials, c->red.ticket)
+    if (solver == PF2_SOLVER_CG) { UPD(0); }
+    else if (solver == PF2_SOLVER_SCALINGCG) { UPD(1); }
+    else {
+        UPD(2);
+        c->launches++;
+        PF2_CUDA(cudaMemcpyAsync(A->z, A->r, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+        PF2_TRY(ilu0_apply(A, A->z, A->st));
+        cg_dot_finalize_kernel<<<grid, kThreads, 0, c->stream>>>(n, A->z, A->r, A->st, 0, nullptr, nullptr, c->red.partials, c->red.ticket);
+    }
+#undef UPD
+    c->launches++;
+    cg_pupdate_kernel<<<grid, kThreads, 0, c->stream>>>(n, solver == PF2_SOLVER_CG ? A->r : A->z, A->p, A->st);
+    c->launches++;
+    PF2_LAUNCH_CHECK();
+    return PF2_OK;
+}
+
+int solve(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out) {
+    pf2_ctx* c = A->ctx;
+    PF2_CHECK(solver >= 0 && solver <= 2, "unknown solver");
+    PF2_CHECK(itrmax >= 0, "itrmax");
+    PF2_CUDA(cudaSetDevice(c->device));
+    PF2_TRY(ensure_workspace(A));
+    const int n = A->rows;
+    const int grid = c->grid_for(n, 2);
+    if (solver == PF2_SOLVER_ILU0CG) PF2_TRY(ilu0_factor(A));
+#define INIT(M) cg_init_kernel<M><<<grid, kThreads, 0, c->stream>>>(n, b, A->indptr, A->diagpos, A->data, x, A->r, A->z, A->p, A->st, itrmax, eps, c->red.partials, c->red.ticket)
+    if (solver == PF2_SOLVER_CG) { INIT(0); }
+    else if (solver == PF2_SOLVER_SCALINGCG) { INIT(1); }
+    else {
+        INIT(2);
+        c->launches++;
+        PF2_CUDA(cudaMemcpyAsync(A->z, A->r, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+        PF2_TRY(ilu0_apply(A, A->z, nullptr));
+        cg_dot_finalize_kernel<<<grid, kThreads, 0, c->stream>>>(n, A->z, A->r, A->st, 1, A->z, A->p, c->red.partials, c->red.ticket);
+    }
+#undef INIT
+    c->launches++;
+    PF2_LAUNCH_CHECK();
+
+    // chunked enqueue; poll `done` one chunk behind
+    const int chunk = (solver == PF2_SOLVER_ILU0CG) ? 4 : 32;
+    int enq = 0, slot = 0;
+    bool have_prev = false;
+    CgState last;
+    memset(&last, 0, sizeof last);
+    bool finished = false;
+    while (!finished) {
+        const int todo = std::min(chunk, itrmax - enq);
+        for (int k = 0; k < todo; k++) PF2_TRY(enqueue_iteration(A, solver, x));
+        enq += todo;
+        PF2_CUDA(cudaMemcpyAsync(&A->h_st[slot], A->st, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+        PF2_CUDA(cudaEventRecord(A->ev[slot], c->stream));
+        if (have_prev) {
+            PF2_CUDA(cudaEventSynchronize(A->ev[slot ^ 1]));
+            last = A->h_st[slot ^ 1];
+            if (last.done) finished = true;
+        }
+        if (!finished && (enq >= itrmax || todo == 0)) {
+            PF2_CUDA(cudaEventSynchronize(A->ev[slot]));
+            last = A->h_st[slot];
+            finished = true;
+        }
+        have_prev = true;
+        slot ^= 1;
+    }
+    PF2_CUDA(cudaStreamSynchronize(c->stream));
+    // the freshest state (the chunk in flight may have converged)
+    PF2_CUDA(cudaMemcpyAsync(&A->h_st[0], A->st, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+    PF2_CUDA(cudaStreamSynchronize(c->stream));
+    last = A->h_st[0];
+    if (iters_out) *iters_out = last.iter;
+    if (relres_out) *relres_out = sqrt(last.rr) / sqrt(last.bb);
+    if (!last.done) {
+        set_error("Convergence:faild after %d iterations (relres %.3e)", last.iter, sqrt(last.rr) / sqrt(last.bb));
+        return PF2_E_NOCONV;
+    }
+    return PF2_OK;
+}
+
+}  // namespace pf2
+
+using namespace pf2;
+
+extern "C" {
+
+int pf2_solve(pf2_csr* A, int solver, const double* b_dev, double* x_dev, int itrmax, double eps, int* iters_out, double* relres_out) {
+    return solve(A, solver, b_dev, x_dev, itrmax, eps, iters_out, relres_out);
+}
+
+int pf2_solve_host(pf2_csr* A, int solver, const double* b_host, double* x_host, int itrmax, double eps, int* iters_out, double* relres_out) {
+    pf2_ctx* c = A->ctx;
+    const size_t n = (size_t)A->rows;
+    if (!A->xw) { PF2_TRY(dev_alloc(&A->xw, n)); PF2_TRY(dev_alloc(&A->bw, n)); }
+    PF2_CUDA(cudaMemcpyAsync(A->bw, b_host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    int rc = solve(A, solver, A->bw, A->xw, itrmax, eps, iters_out, relres_out);
+    if (rc != PF2_OK && rc != PF2_E_NOCONV) return rc;
+    PF2_CUDA(cudaMemcpyAsync(x_host, A->xw, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    PF2_CUDA(cudaStreamSynchronize(c->stream));
+    return rc;
+}
+
+int pf2_ilu0_factor(pf2_csr* A) { return ilu0_factor(A); }
+
+int pf2_ilu0_download(pf2_csr* A, double* data_host) {
+    PF2_CHECK(A->ilu_valid, "call pf2_ilu0_factor first");
+    PF2_CUDA(cudaMemcpyAsync(data_host, A->ilu, sizeof(double) * (size_t)A->nnz, cudaMemcpyDeviceToHost, A->ctx->stream));
+    PF2_CUDA(cudaStreamSynchronize(A->ctx->stream));
+    return PF2_OK;
+}
+
+int pf2_ilu0_solve_host(pf2_csr* A, const double* b_host, double* x_host) {
+    pf2_ctx* c = A->ctx;
+    PF2_TRY(ilu0_factor(A));
+    const size_t n = (size_t)A->rows;
+    if (!A->xw) { PF2_TRY(dev_alloc(&A->xw, n)); PF2_TRY(dev_alloc(&A->bw, n)); }
+    PF2_CUDA(cudaMemcpyAsync(A->xw, b_host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    PF2_TRY(ilu0_apply(A, A->xw, nullptr));
+    PF2_CUDA(cudaMemcpyAsync(x_host, A->xw, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    PF2_CUDA(cudaStreamSynchronize(c->stream));
+    return PF2_OK;
+}
+
+}  // extern "C"

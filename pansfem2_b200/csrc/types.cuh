@@ -1,0 +1,134 @@
+// types.cuh -- the opaque handle types behind the C ABI.  All arrays are device pointers unless prefixed h_.
+#pragma once
+#include "common.cuh"
+
+struct pf2_mesh {
+    pf2_ctx* ctx = nullptr;
+    int dim = 0, nnode = 0, npe = 0, nelem = 0;
+    double* coords = nullptr;   // nnode*dim, node-major (AoS as std::vector<Vector<T>>)
+    int* conn = nullptr;        // nelem*npe
+};
+
+struct pf2_dofmap {
+    pf2_ctx* ctx = nullptr;
+    int nnode = 0, ndof = 0, kdegree = 0;
+    int* n2g = nullptr;         // nnode*ndof : -1 = Dirichlet, else global row (node-major, dof-minor)
+    double* ufix = nullptr;     // nnode*ndof : prescribed value on fixed dofs, 0 elsewhere
+};
+
+namespace pf2 {
+// device-resident state of one Krylov solve (CG.h:124-154 / 420-453 / 320-352)
+struct CgState {
+    double rho;      // z.r of the current residual (Mrkrk)
+    double pAp;
+    double rr;       // r.r
+    double bb;       // b.b
+    double beta;
+    double zr_new;   // scratch for the ILU path
+    int iter;        // iterations completed
+    int done;        // 1 = converged (x frozen), kernels early-exit
+    int maxit;
+    int pad;
+    double eps;
+};
+}  // namespace pf2
+
+struct pf2_csr {
+    pf2_ctx* ctx = nullptr;
+    int rows = 0;
+    long long nnz = 0;
+    long long* indptr = nullptr;   // rows+1 (int64: config 5 has nnz > 2^31)
+    int* indices = nullptr;        // nnz, sorted within a row
+    double* data = nullptr;        // nnz
+    double* F = nullptr;           // rows: right-hand side assembled next to K
+    int* diagpos = nullptr;        // rows: offset of the diagonal inside the row, -1 if structurally absent (CSR.h:155-167)
+    int max_row = 0;               // longest row
+    // scatter map of the symbolic phase (pattern-built matrices only)
+    int* bmap = nullptr;           // [(e*npe+a)*npe + b] : column offset of node b's first free dof in node a's rows
+    int map_npe = 0, map_ndof = 0, map_nelem = 0;
+    // SpMV plan
+    int spmv_variant = 0;          // 0 = not planned
+    int stream_rows = 0;           // rows per block of the streaming kernel
+    // Krylov workspace (lazily allocated)
+    double *r = nullptr, *p = nullptr, *z = nullptr, *y = nullptr, *xw = nullptr, *bw = nullptr;
+    pf2::CgState* st = nullptr;
+    pf2::CgState* h_st = nullptr;  // pinned, 2 slots
+    cudaEvent_t ev[2] = { nullptr, nullptr };
+    // ILU(0)
+    double* ilu = nullptr;         // factors in A's pattern
+    bool ilu_valid = false;
+    int* level_rows = nullptr;     // rows sorted by dependency level of the forward (unit-L) sweep
+    int* level_rows_u = nullptr;   // ... of the backward (U) sweep
+    std::vector<int> h_level_ptr, h_level_ptr_u;   // host: first row of each level in the arrays above
+    // instrumentation
+    double spmv_ms_total = 0;
+    long long spmv_calls = 0;
+};
+
+struct pf2_filter {
+    pf2_ctx* ctx = nullptr;
+    int kind = 0, n = 0;
+    long long nnb = 0;
+    double beta = 1.0;              // HeavisideFilter ctor default (HeavisideFilter.h:37,46)
+    long long* rowptr = nullptr;
+    int* nbr = nullptr;
+    double* w = nullptr;
+    double* dr = nullptr;           // scratch: d rho / d s~ (Heaviside chain rule)
+    double *hs = nullptr, *hr = nullptr, *hd = nullptr;   // staging for the _host entry points
+};
+
+
+namespace pf2 {
+struct OcState {
+    double l0, l1, lambda;
+    double eps, volscale, volshift;   // g = volscale * sum(rho) - volshift
+    int steps, done;
+};
+
+}  // namespace pf2
+
+struct pf2_oc {
+    pf2_ctx* ctx = nullptr;
+    int n = 0, k = 0;
+    double iota, lmin, lmax, leps, move;
+    double previousvalue = 0.0, epsvalue = 1.0e-5;   // OC.h:49-50
+    double* xnew = nullptr;
+    double* rho = nullptr;
+    pf2::OcState* st = nullptr;
+    pf2::OcState* h_st = nullptr;   // pinned, 2 slots
+    cudaEvent_t ev[2] = { nullptr, nullptr };
+};
+
+
+namespace pf2 {
+constexpr int kMaxM = 4;
+
+struct MmaSmall {
+    double a0, a[kMaxM], c[kMaxM], d[kMaxM];
+    double y[kMaxM], lam[kMaxM], s[kMaxM], mu[kMaxM], z, zeta;
+    double dy[kMaxM], dlam[kMaxM], ds[kMaxM], dmu[kMaxM], dz, dzeta;
+    double b[kMaxM];
+    double eps, tau, tymax, dwl, dwl1;
+    int accept, ll, halvings, newton;
+};
+
+struct MmaParams {
+    double raa0, albefa, move, asyinit, asydecr, asyincr;
+};
+
+}  // namespace pf2
+
+struct pf2_mma {
+    pf2_ctx* ctx = nullptr;
+    int n = 0, m = 0, k = 0;
+    double previousvalue = 0.0, epsvalue = 1.0e-5;       // MMA.h:67-68
+    pf2::MmaParams P = { 1.0e-5, 0.1, 0.5, 0.5, 0.7, 1.2 };   // MMA.h:80-85
+    double *xmin = nullptr, *xmax = nullptr, *xkm1 = nullptr, *xkm2 = nullptr, *L = nullptr, *U = nullptr;
+    double *alpha = nullptr, *beta = nullptr, *p0 = nullptr, *q0 = nullptr, *p = nullptr, *q = nullptr;
+    double *x = nullptr, *gsi = nullptr, *ita = nullptr, *xn = nullptr, *gsin = nullptr, *itan = nullptr;
+    double *dx = nullptr, *dgsi = nullptr, *dita = nullptr, *Dx = nullptr, *dtx = nullptr;
+    double* gval = nullptr;
+    pf2::MmaSmall* S = nullptr;
+    pf2::MmaSmall* h_S = nullptr;   // pinned
+};
+

@@ -1,0 +1,443 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the oracle on the same inputs.
+
+Checker = oracle/pf2_oracle.c (pinned bit-identical to the reference in tests/test_oracle_pinned.py), the committed
+golden fixtures, and - when oracle/_ref/libpf2ref.so travelled to the box - the live reference itself.
+Tolerances (BASELINE.json north_star): CSR values / solutions fp64 with relative residual 1e-10, compliance 1e-8
+relative, density after N design iterations 1e-6 max-abs.  Unit element matrices ~1e-13 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import portlib as orc
+from oracle import reflib
+from pansfem2_b200 import capi, problems
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def live(golden_dir):
+    return np.load(os.path.join(golden_dir, "live_reference.npz"))
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# element routines (PlaneStrain.h:21, Solid.h:21, HeatTransfer.h:20)
+# ---------------------------------------------------------------------------------------------------------------
+def test_element_matrices_vs_reference_fixture(ctx, live):
+    cases = [("ke_ps_q4", capi.EQ_PLANESTRAIN, "q4", 1.0, 0.3, 1.0), ("ke_ps_q4d", capi.EQ_PLANESTRAIN, "q4d", 2.5, 0.3, 0.7),
+             ("ke_heat_q4", capi.EQ_HEAT, "q4", 1.0, 0.0, 1.0), ("ke_heat_q4d", capi.EQ_HEAT, "q4d", 2.5, 0.0, 0.7),
+             ("ke_solid_h8", capi.EQ_SOLID, "h8", 1.0, 0.3, 1.0), ("ke_solid_h8d", capi.EQ_SOLID, "h8d", 2.5, 0.3, 1.0)]
+    for key, eq, xkey, E, V, t in cases:
+        Ke = ctx.element_matrix(eq, live[xkey], E, V, t)
+        assert rel(Ke, live[key]) < 1e-13, key
+        assert np.abs(Ke - Ke.T).max() < 1e-13 * np.abs(Ke).max()
+
+
+def test_element_matrices_random_vs_oracle(ctx):
+    rng = np.random.default_rng(3)
+    q4 = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], float)
+    h8 = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    for _ in range(5):
+        xq = q4 * rng.uniform(0.5, 2.0, 2) + 0.2 * rng.uniform(-1, 1, q4.shape)
+        xh = h8 * rng.uniform(0.5, 2.0, 3) + 0.15 * rng.uniform(-1, 1, h8.shape)
+        E, V, t = rng.uniform(0.1, 1e5), rng.uniform(0.0, 0.45), rng.uniform(0.5, 2.0)
+        for eq, x in ((capi.EQ_PLANESTRAIN, xq), (capi.EQ_HEAT, xq), (capi.EQ_SOLID, xh)):
+            assert rel(ctx.element_matrix(eq, x, E, V, t), orc.element_matrix(eq, x, E, V, t)) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# numbering, symbolic pattern, numeric assembly (BoundaryCondition.h:20, Assembling.h:47-66,152,175; CSR.h:93)
+# ---------------------------------------------------------------------------------------------------------------
+def _assemble_gpu(ctx, P, fixed, Emod, V=0.3, t=1.0):
+    mesh = capi.Mesh(ctx, P.coords, P.conn)
+    dm = capi.DofMap(ctx, P.nnode, P.ndof, fixed)
+    A = capi.Csr.pattern(ctx, mesh, dm)
+    A.assemble(mesh, dm, P.eq, (0.0, 0.0, V, 1.0, t), P.loads, modulus=ctx.array(Emod))
+    return mesh, dm, A
+
+
+@pytest.mark.parametrize("make", [lambda: problems.cantilever2d(12, 8), lambda: problems.heat2d(10, 6),
+                                  lambda: problems.cantilever3d(4, 3, 2), lambda: problems.cantilever2d(60, 40)])
+def test_assembly_vs_oracle(ctx, make):
+    P = make()
+    rng = np.random.default_rng(11)
+    Emod = rng.uniform(0.5, 2.0, P.nelem)
+    # non-zero Dirichlet values exercise the lift into F (Assembling.h:59)
+    fixed = (P.fixed[0], P.fixed[1], rng.uniform(-0.02, 0.02, len(P.fixed[0])))
+    mesh, dm, A = _assemble_gpu(ctx, P, fixed, Emod)
+    So, n2g, ufix, _ = orc.assemble(P.eq, P.coords, P.conn, fixed, P.loads, Emod)
+    indptr, indices, data, F = A.download()
+    oi, oj, od, oF = So.arrays()
+    assert dm.kdegree == So.rows and np.array_equal(dm.get(), n2g)
+    assert np.array_equal(indptr, oi) and np.array_equal(indices, oj)          # bit-exact index work
+    assert rel(data, od) < 1e-13
+    assert np.abs(F - oF).max() <= 1e-13 * max(np.abs(oF).max(), 1.0)
+    for o in (A, dm, mesh):
+        o.close()
+
+
+def test_assembly_vs_live_reference_fixture(ctx, live):
+    P = problems.cantilever2d(12, 8)
+    fixed = (P.fixed[0], P.fixed[1], live["sys_fixval"])
+    mesh, dm, A = _assemble_gpu(ctx, P, fixed, live["sys_Emod"])
+    indptr, indices, data, F = A.download()
+    assert np.array_equal(indptr, live["sys_indptr"]) and np.array_equal(indices, live["sys_indices"])
+    assert rel(data, live["sys_data"]) < 1e-13 and rel(F, live["sys_F"]) < 1e-13
+    for o in (A, dm, mesh):
+        o.close()
+
+
+def test_remove_boundary_conditions_numbering(ctx):
+    """nfixed = 0 == RemoveBoundaryConditions + Renumbering (BoundaryCondition.h:66, Assembling.h:175)."""
+    dm = capi.DofMap(ctx, 7, 3, (np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0)))
+    assert dm.kdegree == 21 and np.array_equal(dm.get().ravel(), np.arange(21))
+    dm.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SpMV and the Krylov solvers (CSR.h:109; CG.h:124, 420, 320, 258, 289)
+# ---------------------------------------------------------------------------------------------------------------
+def test_spmv_all_kernel_variants(ctx):
+    rng = np.random.default_rng(5)
+    for P in (problems.cantilever2d(40, 30), problems.heat2d(33, 17), problems.cantilever3d(6, 5, 4)):
+        So, *_ = orc.assemble(P.eq, P.coords, P.conn, P.fixed, P.loads, rng.uniform(0.5, 2, P.nelem))
+        indptr, indices, data, F = So.arrays()
+        A = capi.Csr.upload(ctx, indptr, indices, data)
+        x = rng.uniform(-1, 1, So.rows)
+        y_ref = So.spmv(x)
+        assert rel(A.spmv_host(x), y_ref) < 1e-14
+        ok = 0
+        for variant in (1, 2, 3, 4, 5, 11, 12, 13, 14, 15):
+            try:
+                A.spmv_bench(variant, reps=1, flush_l2=False)
+                ok += 1
+            except capi.Pf2Error as e:
+                assert e.code == 5
+        assert ok >= 6
+        A.close()
+
+
+def test_spmv_ragged_and_empty_rows(ctx):
+    rng = np.random.default_rng(9)
+    n = 1000
+    lens = rng.integers(0, 40, n)
+    lens[::7] = 0                     # structurally empty rows
+    lens[5] = 300                     # one long row
+    indptr = np.zeros(n + 1, np.int32)
+    indptr[1:] = np.cumsum(lens)
+    indices = np.concatenate([np.sort(rng.choice(n, l, replace=False)) for l in lens]).astype(np.int32)
+    data = rng.uniform(-1, 1, indptr[-1])
+    x = rng.uniform(-1, 1, n)
+    So = orc.system_from_csr(indptr, indices, data)
+    A = capi.Csr.upload(ctx, indptr, indices, data)
+    assert np.abs(A.spmv_host(x) - So.spmv(x)).max() < 1e-13
+    A.close()
+
+
+@pytest.mark.parametrize("solver,name", [(capi.SOLVER_CG, "cg"), (capi.SOLVER_SCALINGCG, "scalingcg"), (capi.SOLVER_ILU0CG, "ilu0cg")])
+def test_solvers_vs_live_reference_fixture(ctx, live, solver, name):
+    A = capi.Csr.upload(ctx, live["sys_indptr"], live["sys_indices"], live["sys_data"])
+    x, it, relres = A.solve_host(solver, live["sys_F"])
+    assert relres < 1e-10
+    xr = live[f"sys_x_{name}"]
+    assert np.abs(x - xr).max() < 1e-9 * np.abs(xr).max()
+    So = orc.system_from_csr(live["sys_indptr"], live["sys_indices"], live["sys_data"])
+    _, it_o, _ = So.solve(solver, live["sys_F"])
+    assert abs(it - it_o) <= max(2, it_o // 50)       # same algorithm => same iteration count up to rounding
+    A.close()
+
+
+def test_ilu0_factor_and_apply(ctx, live):
+    A = capi.Csr.upload(ctx, live["sys_indptr"], live["sys_indices"], live["sys_data"])
+    q = A.ilu0()
+    assert rel(q, live["sys_ilu0_data"]) < 1e-12
+    assert rel(A.ilu0_solve_host(live["sys_F"]), live["sys_preilu0"]) < 1e-11
+    A.close()
+
+
+def test_scalingcg_c1_system_iterations(ctx):
+    """60x40 plane-strain cantilever, uniform E: the reference needs CG 368 / ScalingCG 357 / ILU0CG 95."""
+    P = problems.cantilever2d(60, 40)
+    So, n2g, ufix, _ = orc.assemble(P.eq, P.coords, P.conn, P.fixed, P.loads, np.full(P.nelem, 2.1e5))
+    indptr, indices, data, F = So.arrays()
+    A = capi.Csr.upload(ctx, indptr, indices, data)
+    xs = {}
+    for solver, expect in ((capi.SOLVER_CG, 368), (capi.SOLVER_SCALINGCG, 357), (capi.SOLVER_ILU0CG, 95)):
+        x, it, relres = A.solve_host(solver, F)
+        assert relres < 1e-10 and abs(it - (expect + 1)) <= 8, (solver, it)
+        xs[solver] = x
+        r = F - So.spmv(x)
+        assert np.linalg.norm(r) < 2e-10 * np.linalg.norm(F)       # true residual, not only the recursive one
+    assert np.abs(xs[0] - xs[1]).max() < 1e-9 * np.abs(xs[1]).max()
+    assert np.abs(xs[2] - xs[1]).max() < 1e-9 * np.abs(xs[1]).max()
+    A.close()
+
+
+def test_solver_nonconvergence_reports_like_reference(ctx, live):
+    A = capi.Csr.upload(ctx, live["sys_indptr"], live["sys_indices"], live["sys_data"])
+    with pytest.raises(capi.Pf2Error) as e:
+        A.solve_host(capi.SOLVER_SCALINGCG, live["sys_F"], itrmax=5)
+    assert e.value.code == capi.E_NOCONV and "Convergence:faild" in str(e.value)
+    x, it, relres = A.solve_host(capi.SOLVER_SCALINGCG, live["sys_F"], itrmax=5, raise_noconv=False)
+    So = orc.system_from_csr(live["sys_indptr"], live["sys_indices"], live["sys_data"])
+    xo, ito, _ = So.solve(1, live["sys_F"], itrmax=5)
+    assert it == 5 and rel(x, xo) < 1e-10        # the last iterate is returned, as the reference does
+    A.close()
+
+
+def test_solid_hex8_golden_result_linear_vtk(ctx, golden_dir):
+    """sample/solid/sample_linear.cpp end to end on the device vs the committed result_linear.vtk."""
+    g = np.load(os.path.join(golden_dir, "solid_linear.npz"))
+    fixed = (g["fix_node"], g["fix_dof"], g["fix_val"])
+    loads = (g["load_node"], g["load_dof"], g["load_val"])
+    mesh = capi.Mesh(ctx, g["coords"], g["conn"])
+    dm = capi.DofMap(ctx, len(g["coords"]), 3, fixed)
+    A = capi.Csr.pattern(ctx, mesh, dm)
+    A.assemble(mesh, dm, capi.EQ_SOLID, (0.0, 0.0, 0.3, 1.0, 1.0), loads, modulus=ctx.array(np.full(len(g["conn"]), 210000.0)))
+    x = ctx.empty(A.rows)
+    u = ctx.empty(len(g["coords"]) * 3)
+    it, relres = A.solve(capi.SOLVER_SCALINGCG, A.device_F(), x)
+    dm.disassemble(x, u)
+    uh = u.download().reshape(-1, 3)
+    assert relres < 1e-10 and abs(np.abs(uh).max() - 1.48963) < 1e-5
+    np.testing.assert_allclose(uh, g["u"], rtol=6e-6, atol=1e-9)
+    for o in (A, dm, mesh):
+        o.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# filters, OC, MMA (DensityFilter.h, HeavisideFilter.h, OC.h, MMA.h)
+# ---------------------------------------------------------------------------------------------------------------
+def test_filters_vs_live_reference_fixture(ctx, live):
+    P = problems.cantilever2d(12, 8)
+    s, dfdrho = live["flt_s"], live["flt_dfdrho"]
+    for kind, nm in ((capi.FILTER_DENSITY, "density"), (capi.FILTER_HEAVISIDE, "heaviside")):
+        f = capi.Filter(ctx, kind, *P.nbrs)
+        f.set_beta(2.0)
+        assert np.abs(f.apply_host(s) - live[f"flt_{nm}_rho"]).max() < 1e-14
+        assert rel(f.sens_host(s, dfdrho), live[f"flt_{nm}_sens"]) < 1e-13
+        oc = capi.OC(ctx, P.nelem, *P.oc)
+        x, steps, lam = oc.update_host(f, 0.5, 1.0, s, 1.0, live[f"flt_{nm}_sens"], live[f"oc_{nm}_dgds"])
+        xo, steps_o, lam_o = orc.oc_update(P.oc, kind, P.nbrs, 2.0, 0.5, 1.0, s, live[f"flt_{nm}_sens"], live[f"oc_{nm}_dgds"])
+        assert steps == steps_o and lam == lam_o                    # identical bisection path
+        assert np.abs(x - live[f"oc_{nm}_x"]).max() < 1e-13
+        oc.close(); f.close()
+
+
+def test_filter_ragged_3d_vs_oracle(ctx):
+    P = problems.cantilever3d(7, 5, 3)
+    rng = np.random.default_rng(2)
+    s, d = rng.uniform(0.01, 1, P.nelem), -rng.uniform(0, 3, P.nelem)
+    for kind in (capi.FILTER_DENSITY, capi.FILTER_HEAVISIDE):
+        f = capi.Filter(ctx, kind, *P.nbrs)
+        f.set_beta(4.0)
+        assert np.abs(f.apply_host(s) - orc.filter_apply(kind, P.nbrs, 4.0, s)).max() < 1e-14
+        assert rel(f.sens_host(s, d), orc.filter_sens(kind, P.nbrs, 4.0, s, d)) < 1e-13
+        f.close()
+
+
+def test_mma_known_answer_svanberg_beam(ctx, golden_dir):
+    """src/Optimize/Solver/test_MMA.cpp on the device, iterate by iterate against the reference's printed output."""
+    kat = np.load(os.path.join(golden_dir, "mma_kat.npz"))["test_MMA"]
+    C1, C2 = 0.0624, 1.0
+    coef = np.array([61.0, 37.0, 19.0, 7.0, 1.0])
+    mma = capi.MMA(ctx, 5, 1, 1.0, [0.0], [1000.0], [1.0], 1.0, 10.0)
+    mma.set_parameters(1.0e-5, 0.1, 0.5, 0.5, 0.7, 1.2, 1.0e-5)
+    s = np.full(5, 5.0)
+    for k in range(len(kat)):
+        f = C1 * s.sum()
+        g = (coef * s ** -3.0).sum() - C2
+        np.testing.assert_allclose(np.concatenate([[f, g], s]), kat[k, 1:], rtol=2e-5, atol=2e-9)
+        if mma.is_convergence(f):
+            break
+        s, steps = mma.update_host(s, f, np.full(5, C1), [g], (-3.0 * coef * s ** -4.0)[None, :])
+        assert 3 <= steps <= 200
+    assert k == len(kat) - 1 and abs(f - 1.33996) < 1e-5
+    mma.close()
+
+
+def test_mma_two_bar_truss_n_le_m(ctx):
+    """test_MMA_3.cpp (n = m = 2, MMA.h:292-330 branch) against the oracle, iterate by iterate."""
+    def funcs(s):
+        x1, x2 = s
+        rt = np.sqrt(1.0 + x2 * x2)
+        f = x1 * rt
+        df = np.array([rt, x1 * x2 / rt])
+        c2 = 0.124
+        g = np.array([c2 * rt * (8.0 / x1 + 1.0 / (x1 * x2)) - 1.0, c2 * rt * (8.0 / x1 - 1.0 / (x1 * x2)) - 1.0])
+        dg = np.array([[c2 * rt * (-8.0 / x1 ** 2 - 1.0 / (x1 ** 2 * x2)), c2 * (x2 / rt * (8.0 / x1 + 1.0 / (x1 * x2)) - rt / (x1 * x2 ** 2))],
+                       [c2 * rt * (-8.0 / x1 ** 2 + 1.0 / (x1 ** 2 * x2)), c2 * (x2 / rt * (8.0 / x1 - 1.0 / (x1 * x2)) + rt / (x1 * x2 ** 2))]])
+        return f, df, g, dg
+    xmin, xmax = np.array([0.2, 0.1]), np.array([4.0, 1.6])
+    md = capi.MMA(ctx, 2, 2, 1.0, [0.0, 0.0], [1000.0, 1000.0], [1.0, 1.0], xmin, xmax)
+    md.set_parameters(1.0e-5, 0.1, 0.5, 0.5, 0.7, 1.2, 1.0e-5)
+    mo = orc.MMA(2, 2, 1.0, [0.0, 0.0], [1000.0, 1000.0], [1.0, 1.0], xmin, xmax)
+    mo.set_parameters(1.0e-5, 0.1, 0.5, 0.5, 0.7, 1.2)
+    sd = so = np.array([1.5, 0.5])
+    for k in range(8):
+        f, df, g, dg = funcs(so)
+        so = mo.update(so, df, g, dg)
+        f, df, g, dg = funcs(sd)
+        sd, _ = md.update_host(sd, f, df, g, dg)
+        assert np.abs(sd - so).max() < 1e-7
+    assert abs(funcs(sd)[0] - 1.50865) < 1e-3
+    md.close()
+
+
+def test_mma_large_n_vs_oracle(ctx):
+    """n >> m branch (MMA.h:260-291) on a SIMP-like problem, three consecutive updates (asymptote history included)."""
+    rng = np.random.default_rng(4)
+    n = 5000
+    x = rng.uniform(0.2, 0.8, n)
+    md = capi.MMA(ctx, n, 1, 1.0, [0.0], [1.0e4], [0.0], 0.01, 1.0)
+    md.set_parameters(1.0e-5, 0.1, 0.2, 0.5, 0.7, 1.2, 1.0e-6)
+    mo = orc.MMA(n, 1, 1.0, [0.0], [1.0e4], [0.0], 0.01, 1.0)
+    mo.set_parameters(1.0e-5, 0.1, 0.2, 0.5, 0.7, 1.2)
+    xd = xo = x
+    for k in range(4):
+        dfdx = -rng.uniform(0.1, 5.0, n)
+        dgdx = np.full(n, 1.0 / (0.5 * n)) * rng.uniform(0.9, 1.1, n)
+        g = np.array([xo.sum() / (0.5 * n) - 1.0])
+        xo2 = mo.update(xo, dfdx, g, dgdx[None, :])
+        xd2, steps = md.update_host(xd, 1.0, dfdx, g, dgdx[None, :])
+        assert np.abs(xd2 - xo2).max() < 1e-7, k
+        assert abs(steps - mo.stats()[0]) <= 2
+        xd = xo = xo2                   # keep both on the oracle's path so differences do not compound
+        md_x = None
+    md.close()
+
+
+def test_mma_two_constraints_vs_oracle(ctx):
+    rng = np.random.default_rng(8)
+    n, m = 800, 2
+    x = rng.uniform(0.3, 0.7, n)
+    md = capi.MMA(ctx, n, m, 1.0, [0.0, 0.0], [1.0e3, 1.0e3], [1.0, 1.0], 0.01, 1.0)
+    mo = orc.MMA(n, m, 1.0, [0.0, 0.0], [1.0e3, 1.0e3], [1.0, 1.0], 0.01, 1.0)
+    dfdx = -rng.uniform(0.1, 5.0, n)
+    dg = np.stack([np.full(n, 1.0 / (0.5 * n)), rng.uniform(0.5, 1.5, n) / n])
+    g = np.array([x.sum() / (0.5 * n) - 1.0, (dg[1] * x).sum() - 0.6])
+    xo = mo.update(x, dfdx, g, dg)
+    xd, _ = md.update_host(x, 1.0, dfdx, g, dg)
+    assert np.abs(xd - xo).max() < 1e-7
+    md.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reaction / compliance / sensitivity passes and the fused design loop
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("make", [lambda: problems.cantilever2d(12, 8), lambda: problems.heat2d(10, 6), lambda: problems.cantilever3d(4, 3, 2)])
+def test_compliance_and_sensitivity_vs_oracle(ctx, make):
+    P = make()
+    rng = np.random.default_rng(6)
+    rho = rng.uniform(0.05, 1.0, P.nelem)
+    u = rng.uniform(-1, 1, (P.nnode, P.ndof)) * 1e-3
+    mesh = capi.Mesh(ctx, P.coords, P.conn)
+    f, dfdrho, r = capi.compliance_sens(mesh, P.eq, ctx.array(u.ravel()), ctx.array(rho), (P.E0, P.E1, P.poisson, P.penal, P.thickness, P.scale0), want_r=True)
+    fo, ro, dfo = orc.compliance_sens(P.eq, P.coords, P.conn, u, rho, P.E0, P.E1, P.poisson, P.thickness, P.penal, P.scale0)
+    assert abs(f - fo) < 1e-12 * abs(fo)
+    assert rel(dfdrho, dfo) < 1e-12 and rel(r, ro) < 1e-12
+    mesh.close()
+
+
+@pytest.mark.parametrize("opt,tag", [(problems.OPT_OC, "oc"), (problems.OPT_MMA, "mma")])
+def test_simp_c1_first_iterations_vs_live_reference(ctx, live, opt, tag):
+    """Config 1 (sample_optimize_density_{oc,mma}.cpp), 12 design iterations, against the live-reference history."""
+    P = problems.cantilever2d(60, 40, opt_kind=opt)
+    S = capi.Simp(ctx, P)
+    hist = []
+    for k in range(12):
+        st = S.iterate(check_convergence=False)
+        assert st["cg_relres"] < 1e-10
+        hist.append((st["f"], st["g"]))
+    hist = np.array(hist)
+    np.testing.assert_allclose(hist[:, 0], live[f"c1_{tag}_hist"][:, 0], rtol=1e-8)          # compliance 1e-8 relative
+    np.testing.assert_allclose(hist[:, 1], live[f"c1_{tag}_hist"][:, 1], rtol=0, atol=1e-9)
+    out = S.get()
+    assert np.abs(out["s"] - live[f"c1_{tag}_s12"]).max() < 1e-6                              # density 1e-6 max-abs
+    assert np.abs(out["rho"] - live[f"c1_{tag}_rho12"]).max() < 1e-6
+    S.close()
+
+
+@pytest.mark.parametrize("opt,tag,niter", [(problems.OPT_OC, "oc", 66), (problems.OPT_MMA, "mma", 56)])
+def test_simp_c1_full_run_vs_golden_vtk(ctx, golden_dir, opt, tag, niter):
+    """The whole sample run on the device reproduces the committed Density_{OC,MMA}.vtk (6 significant digits)."""
+    g = np.load(os.path.join(golden_dir, f"density_{tag}.npz"))
+    P = problems.cantilever2d(60, 40, opt_kind=opt)
+    S = capi.Simp(ctx, P)
+    k = 0
+    for k in range(500):
+        st = S.iterate(check_convergence=True)
+        if st["converged"]:
+            break
+    assert k + 1 == niter
+    out = S.get(want_r=True)
+    assert np.abs(out["rho"] - g["rho"]).max() < 2e-6
+    np.testing.assert_allclose(out["u"], g["u"], rtol=1e-5, atol=1e-11)
+    np.testing.assert_allclose(out["r"], g["r"], rtol=1e-5, atol=1e-7)
+    S.close()
+
+
+@pytest.mark.parametrize("make,niter", [(lambda: problems.heat2d(24, 24), 6),
+                                         (lambda: problems.cantilever3d(10, 6, 4, opt_kind=problems.OPT_MMA), 5),
+                                         (lambda: problems.cantilever3d(8, 4, 4, opt_kind=problems.OPT_OC, filter_kind=problems.FILTER_HEAVISIDE), 5),
+                                         (lambda: problems.cantilever2d(40, 20, opt_kind=problems.OPT_MMA, filter_kind=problems.FILTER_DENSITY), 8)])
+def test_simp_other_configs_vs_oracle(ctx, make, niter):
+    """Scaled-down configs 2-5 (heat Q4 + OC, hex8 + MMA / OC, plane strain + MMA + density filter) vs the oracle loop."""
+    P = make()
+    R = orc.simp_run(P.eq, P.coords, P.conn, P.fixed, P.loads, P.filter_kind, P.nbrs, P.opt_kind, P.optp(), P.params(), niter,
+                     np.full(P.nelem, P.s0), check_convergence=False)
+    S = capi.Simp(ctx, P)
+    for k in range(niter):
+        st = S.iterate(check_convergence=False)
+        assert abs(st["f"] - R["hist"][k, 0]) < 1e-8 * abs(R["hist"][k, 0]), k
+        assert abs(st["cg_iters"] - R["hist"][k, 4]) <= max(3, R["hist"][k, 4] // 40)
+    out = S.get()
+    assert np.abs(out["s"] - R["s"]).max() < 1e-6
+    assert np.abs(out["u"] - R["u"]).max() < 1e-8 * np.abs(R["u"]).max()
+    S.close()
+
+
+def test_simp_host_buffer_entry_point_matches_device_loop(ctx):
+    P = problems.cantilever2d(30, 20)
+    S1, S2 = capi.Simp(ctx, P), capi.Simp(ctx, P)
+    s = np.full(P.nelem, P.s0)
+    s_out, rho_out = np.zeros(P.nelem), np.zeros(P.nelem)
+    for k in range(3):
+        a = S1.iterate(check_convergence=False)
+        b = S2.iterate_host(s, s_out, rho_out, check_convergence=False)
+        assert a["f"] == b["f"]
+        s = s_out.copy()
+    assert np.array_equal(S1.get()["s"], s_out)
+    S1.close(); S2.close()
+
+
+@pytest.mark.skipif(not reflib.available(), reason="live reference not shipped")
+def test_live_reference_spot_check(ctx):
+    """When oracle/_ref travelled to the box: CUDA path vs the UNMODIFIED reference on a fresh random system."""
+    reflib.set_num_threads(1)
+    rng = np.random.default_rng(31)
+    P = problems.cantilever2d(24, 10)
+    Emod = rng.uniform(1.0, 3.0, P.nelem)
+    Sr = reflib.assemble(P.eq, P.coords, P.conn, P.fixed, P.loads, Emod)
+    mesh, dm, A = _assemble_gpu(ctx, P, P.fixed, Emod)
+    _, _, data, F = A.download()
+    ri, rj, rd, rF = Sr.arrays()
+    assert rel(data, rd) < 1e-13 and rel(F, rF) < 1e-13
+    x, it, relres = A.solve_host(capi.SOLVER_SCALINGCG, F)
+    xr = Sr.solve(1, rF)[0]
+    assert np.abs(x - xr).max() < 1e-9 * np.abs(xr).max()
+    for o in (A, dm, mesh):
+        o.close()
