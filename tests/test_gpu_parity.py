@@ -418,9 +418,9 @@ def test_simp_host_buffer_entry_point_matches_device_loop(ctx):
     for k in range(3):
         a = S1.iterate(check_convergence=False)
         b = S2.iterate_host(s, s_out, rho_out, check_convergence=False)
-        assert a["f"] == b["f"]
+        assert abs(a["f"] - b["f"]) < 1e-10 * abs(a["f"])       # fp64 atomics in assembly: run-to-run order differs
         s = s_out.copy()
-    assert np.array_equal(S1.get()["s"], s_out)
+    assert np.abs(S1.get()["s"] - s_out).max() < 1e-9
     S1.close(); S2.close()
 
 

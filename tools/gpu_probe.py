@@ -15,8 +15,12 @@ from pansfem2_b200 import capi, problems  # noqa: E402
 def main():
     args = sys.argv[1:]
     kind = args[0] if args else "2d"
+    iters = 2
+    if "--iters" in args:
+        i = args.index("--iters")
+        iters = int(args[i + 1])
+        args = args[:i] + args[i + 2:]
     dims = [int(a) for a in args[1:] if a.isdigit()]
-    iters = int(args[args.index("--iters") + 1]) if "--iters" in args else 2
     t0 = time.time()
     if kind == "2d":
         P = problems.cantilever2d(*(dims or [1000, 1000]), opt_kind=problems.OPT_MMA, filter_kind=problems.FILTER_DENSITY)
