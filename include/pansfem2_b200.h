@@ -121,6 +121,9 @@ int pf2_element_matrix(pf2_ctx* ctx, int eq, const double* xe_host, double E, do
 /* ---- CSR<T>::operator* (CSR.h:109-122) ------------------------------------------------------------------------ */
 int pf2_spmv(pf2_csr* A, const double* x_dev, double* y_dev);
 int pf2_spmv_host(pf2_csr* A, const double* x_host, double* y_host);
+/* kernel selection override for tests / tuning: 0 = auto; 1-5 vector, 11-15 shared-memory stream, 21-26 TMA pipeline */
+int pf2_spmv_set_variant(pf2_csr* A, int variant);
+int pf2_spmv_set_tma_tuning(pf2_csr* A, int stages, int ctas_per_sm);
 /* micro-benchmark hook: run SpMV `reps` times with kernel variant `variant` (0 = auto), device-timed */
 int pf2_spmv_bench(pf2_csr* A, int variant, int reps, int flush_l2, double* ms_per_spmv);
 
@@ -131,6 +134,10 @@ int pf2_solve(pf2_csr* A, int solver, const double* b_dev, double* x_dev, int it
               double* relres_out);
 int pf2_solve_host(pf2_csr* A, int solver, const double* b_host, double* x_host, int itrmax, double eps,
                    int* iters_out, double* relres_out);
+/* sampled per-kernel device times of the Krylov loop (CUDA events around one iteration per chunk):
+ * out = {spmv+dot ms, update ms, p-update ms, samples, total iterations, SpMV variant, rows, nnz} */
+int pf2_csr_solver_stats(pf2_csr* A, double out[8]);
+int pf2_csr_solver_stats_reset(pf2_csr* A);
 /* ILU(0) factors of A (unit-L strictly lower + U with diagonal in A's pattern), cached on A until values change */
 int pf2_ilu0_factor(pf2_csr* A);
 int pf2_ilu0_download(pf2_csr* A, double* data_host);

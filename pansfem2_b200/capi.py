@@ -228,6 +228,12 @@ class Csr:
         _ck(lib().pf2_spmv_host(self.h, _p(x, np.float64), _p(y, np.float64)))
         return y
 
+    def set_spmv_variant(self, variant):
+        _ck(lib().pf2_spmv_set_variant(self.h, int(variant)))
+
+    def set_tma_tuning(self, stages, ctas_per_sm):
+        _ck(lib().pf2_spmv_set_tma_tuning(self.h, int(stages), int(ctas_per_sm)))
+
     def spmv_bench(self, variant=0, reps=20, flush_l2=True):
         ms = C.c_double(0)
         _ck(lib().pf2_spmv_bench(self.h, variant, reps, int(flush_l2), C.byref(ms)))
@@ -246,6 +252,14 @@ class Csr:
         _ck(lib().pf2_solve(self.h, solver, b_dev.ptr if isinstance(b_dev, DeviceArray) else b_dev, x_dev.ptr, int(itrmax), C.c_double(eps),
                             C.byref(it), C.byref(rr)))
         return it.value, rr.value
+
+    def solver_stats(self, reset=False):
+        st = (C.c_double * 8)()
+        _ck(lib().pf2_csr_solver_stats(self.h, st))
+        if reset:
+            _ck(lib().pf2_csr_solver_stats_reset(self.h))
+        return dict(spmv_ms=st[0], update_ms=st[1], pupdate_ms=st[2], samples=int(st[3]), iters=int(st[4]), variant=int(st[5]),
+                    rows=int(st[6]), nnz=int(st[7]))
 
     def device_F(self):
         p = C.c_void_p()

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <utility>
 #include <algorithm>
 #include <cmath>
 #include "../../include/pansfem2_b200.h"
@@ -67,6 +68,20 @@ struct pf2_ctx {
     void* flush_buf = nullptr;        // L2 flush scratch
     size_t flush_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    size_t l2_persist_max = 0;        // cudaDevAttrMaxPersistingL2CacheSize
+    size_t l2_window_max = 0;         // cudaDevAttrMaxAccessPolicyWindowSize
+    bool l2_persist_enabled = false;  // PF2_L2_PERSIST=1 enables the access-policy window around Krylov solves
+    std::vector<std::pair<const void*, int>> occ_cache;
+    // one full wave of a persistent kernel: resident CTAs per SM (occupancy API) x SM count
+    int wave_grid(const void* kernel, int block, size_t smem = 0) {
+        for (auto& kv : occ_cache) if (kv.first == kernel) return kv.second;
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        int g = per_sm * sm_count;
+        if (g > pf2::kMaxBlocks) g = (pf2::kMaxBlocks / sm_count) * sm_count;
+        occ_cache.push_back({ kernel, g });
+        return g;
+    }
     // grid size for n work items with `per` items per thread, capped to a few waves of the machine
     int grid_for(long long n, int per = 1, int waves = 8) const {
         long long b = (n + (long long)pf2::kThreads * per - 1) / ((long long)pf2::kThreads * per);

@@ -11,6 +11,7 @@
 //   * vector  : TPR lanes per row (2..32) with a shuffle reduction; used when a CTA's rows do not fit in shared memory.
 // Both optionally fuse the dot product x.y (p.Ap of CG, CG.h:433) into the epilogue.
 #include "types.cuh"
+#include "spmv_tma.cuh"
 
 namespace pf2 {
 
@@ -79,14 +80,19 @@ spmv_vector_kernel(int rows, const long long* __restrict__ indptr, const int* __
     constexpr int RPB = kThreads / TPR;
     const int lr = threadIdx.x / TPR, lane = threadIdx.x % TPR;
     double dot = 0.0;
-    for (long long row = (long long)blockIdx.x * RPB + lr; row < rows; row += (long long)gridDim.x * RPB) {
-        const long long s = indptr[row], e = indptr[row + 1];
+    // the trip count is CTA-uniform so that the sub-warp shuffles below always see all 32 lanes
+    for (long long base = (long long)blockIdx.x * RPB; base < rows; base += (long long)gridDim.x * RPB) {
+        const long long row = base + lr;
+        const bool valid = row < rows;
         double acc = 0.0;
-#pragma unroll 2
-        for (long long j = s + lane; j < e; j += TPR) acc += ld_stream(data + j) * __ldg(x + ld_stream(indices + j));
+        if (valid) {
+            const long long s = indptr[row], e = indptr[row + 1];
+#pragma unroll 4
+            for (long long j = s + lane; j < e; j += TPR) acc += ld_stream(data + j) * __ldg(x + ld_stream(indices + j));
+        }
 #pragma unroll
         for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, TPR);
-        if (lane == 0) {
+        if (valid && lane == 0) {
             y[row] = acc;
             if (DOT) dot += acc * x[row];
         }
@@ -138,37 +144,50 @@ int csr_finalize_structure(pf2_csr* A) {
     return PF2_OK;
 }
 
-// variant encoding: 1..5 = vector TPR 2,4,8,16,32 ; 11..15 = stream with G = 1,2,4,8,16 threads per row
+// variant encoding: 1..5 = vector TPR 2,4,8,16,32 ; 11..15 = stream with G = 1,2,4,8,16 threads per row ;
+//                   21..26 = TMA pipeline with G = 1,2,4,8,16,32
 static void plan_spmv(pf2_csr* A) {
     if (A->spmv_variant) return;
     const double mean = A->rows ? (double)A->nnz / A->rows : 1.0;
-    // stream: pick the smallest fold group G such that a tile's rows surely fit in shared memory
-    int G = 1;
-    while (G <= 16 && (long long)(kThreads / G) * A->max_row > kStreamCap) G *= 2;
-    if (G <= 16) {
-        // prefer a few threads per row once rows get long so the fold phase stays short
-        while (G < 16 && mean / G > 12.0 && (kThreads / (G * 2)) >= 8) G *= 2;
-        A->spmv_variant = 11 + (G == 1 ? 0 : G == 2 ? 1 : G == 4 ? 2 : G == 8 ? 3 : 4);
-    } else {
-        A->spmv_variant = mean <= 3 ? 1 : mean <= 6 ? 2 : mean <= 12 ? 3 : mean <= 24 ? 4 : 5;
+    // Measured inside the PCG loop on B200 (tools/cg_sweep.py, profiles/r01_cg_sweep_*.txt): the sub-warp vector kernel
+    // with ~2-3 nonzeros per lane wins; the shared-memory stream and TMA-pipeline kernels stay selectable (11-15, 21-26).
+    A->spmv_variant = mean <= 4 ? 1 : mean <= 10 ? 2 : mean <= 24 ? 3 : mean <= 48 ? 4 : 5;
+}
+
+template <int G, bool DOT>
+static int launch_tma(pf2_csr* A, const double* x, double* y, const CgState* st, double* dot_out) {
+    pf2_ctx* c = A->ctx;
+    static bool configured = false;
+    if (!configured) {
+        PF2_CUDA(cudaFuncSetAttribute(spmv_tma_kernel<G, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
     }
+    const int rpb = kConsumers / G;
+    const int cap = tma_cap_for(rpb, A->max_row);
+    const int stages = std::max(2, std::min(A->tma_stages, kMaxStages));
+    const size_t smem = tma_smem_bytes(cap, stages);
+    int per_sm = std::max(1, std::min(A->tma_ctas_per_sm, (int)((220 * 1024) / smem)));
+    const int ntiles = (A->rows + rpb - 1) / rpb;
+    const int grid = std::max(1, std::min(ntiles, c->sm_count * per_sm));
+    spmv_tma_kernel<G, DOT><<<grid, kTmaThreads, smem, c->stream>>>(A->rows, A->indptr, A->indices, A->data, x, y, st, dot_out,
+                                                                   c->red.partials, c->red.ticket, cap, stages);
+    return PF2_OK;
 }
 
 template <bool DOT>
 static int launch_spmv(pf2_csr* A, int variant, const double* x, double* y, const CgState* st, double* dot_out) {
     pf2_ctx* c = A->ctx;
-    const int grid_cap = c->sm_count * 6;
 #define ARGS A->rows, A->indptr, A->indices, A->data, x, y, st, dot_out, c->red.partials, c->red.ticket
 #define VEC(T)                                                                                               \
     {                                                                                                        \
         long long nb = ((long long)A->rows + (kThreads / T) - 1) / (kThreads / T);                              \
-        int grid = (int)std::min<long long>(std::max<long long>(nb, 1), DOT ? std::min(grid_cap * 2, kMaxBlocks) : (long long)c->sm_count * 64); \
+        int grid = (int)std::min<long long>(std::max<long long>(nb, 1), DOT ? (long long)c->wave_grid((const void*)spmv_vector_kernel<T, DOT>, kThreads) : (long long)c->sm_count * 64); \
         spmv_vector_kernel<T, DOT><<<grid, kThreads, 0, c->stream>>>(ARGS);                                   \
     }
 #define STR(Gv)                                                                                              \
     {                                                                                                        \
         long long nb = ((long long)A->rows + (kThreads / Gv) - 1) / (kThreads / Gv);                            \
-        int grid = (int)std::min<long long>(std::max<long long>(nb, 1), std::min(grid_cap, kMaxBlocks));        \
+        int grid = (int)std::min<long long>(std::max<long long>(nb, 1), (long long)c->wave_grid((const void*)spmv_stream_kernel<Gv, DOT>, kThreads)); \
         spmv_stream_kernel<Gv, DOT><<<grid, kThreads, 0, c->stream>>>(ARGS);                                  \
     }
     switch (variant) {
@@ -182,6 +201,12 @@ static int launch_spmv(pf2_csr* A, int variant, const double* x, double* y, cons
         case 13: STR(4) break;
         case 14: STR(8) break;
         case 15: STR(16) break;
+        case 21: PF2_TRY((launch_tma<1, DOT>(A, x, y, st, dot_out))); break;
+        case 22: PF2_TRY((launch_tma<2, DOT>(A, x, y, st, dot_out))); break;
+        case 23: PF2_TRY((launch_tma<4, DOT>(A, x, y, st, dot_out))); break;
+        case 24: PF2_TRY((launch_tma<8, DOT>(A, x, y, st, dot_out))); break;
+        case 25: PF2_TRY((launch_tma<16, DOT>(A, x, y, st, dot_out))); break;
+        case 26: PF2_TRY((launch_tma<32, DOT>(A, x, y, st, dot_out))); break;
         default: set_error("unknown SpMV variant %d", variant); return PF2_E_INVALID;
     }
 #undef ARGS
@@ -197,6 +222,10 @@ static bool variant_ok(const pf2_csr* A, int variant) {
     if (variant >= 11 && variant <= 15) {
         int G = 1 << (variant - 11);
         return (long long)(kThreads / G) * A->max_row <= kStreamCap;
+    }
+    if (variant >= 21 && variant <= 26) {
+        int G = 1 << (variant - 21);
+        return (long long)(kConsumers / G) * A->max_row <= kTileNnz;
     }
     return false;
 }
@@ -223,9 +252,13 @@ int pf2_csr_upload(pf2_ctx* ctx, int rows, const int* indptr_host, const int* in
     A->ctx = ctx;
     A->rows = rows;
     A->nnz = indptr_host[rows];
-    PF2_TRY(dev_alloc(&A->indptr, (size_t)rows + 1));
-    PF2_TRY(dev_alloc(&A->indices, (size_t)A->nnz));
-    PF2_TRY(dev_alloc(&A->data, (size_t)A->nnz));
+    // spare entries: the TMA SpMV reads 16-byte aligned windows that may run a few entries past the end
+    PF2_TRY(dev_alloc(&A->indptr, (size_t)rows + 1 + kCsrPad));
+    PF2_TRY(dev_alloc(&A->indices, (size_t)A->nnz + kCsrPad));
+    PF2_TRY(dev_alloc(&A->data, (size_t)A->nnz + kCsrPad));
+    PF2_CUDA(cudaMemsetAsync(A->indptr + rows, 0, sizeof(long long) * (1 + kCsrPad), ctx->stream));
+    PF2_CUDA(cudaMemsetAsync(A->indices + A->nnz, 0, sizeof(int) * kCsrPad, ctx->stream));
+    PF2_CUDA(cudaMemsetAsync(A->data + A->nnz, 0, sizeof(double) * kCsrPad, ctx->stream));
     PF2_TRY(dev_alloc(&A->F, (size_t)rows));
     int* tmp = nullptr;
     PF2_TRY(dev_alloc(&tmp, (size_t)rows + 1));
@@ -248,11 +281,12 @@ int pf2_csr_destroy(pf2_csr* A) {
     if (!A) return PF2_OK;
     cudaSetDevice(A->ctx->device);
     cudaStreamSynchronize(A->ctx->stream);
-    void* ptrs[] = { A->indptr, A->indices, A->data, A->F, A->diagpos, A->bmap, A->r, A->p, A->z, A->y, A->xw, A->bw, A->st,
+    void* ptrs[] = { A->indptr, A->indices, A->data, A->F, A->diagpos, A->bmap, A->slab, A->xw, A->bw, A->st,
                      A->ilu, A->level_rows, A->level_rows_u };
     for (void* p : ptrs) if (p) cudaFree(p);
     if (A->h_st) cudaFreeHost(A->h_st);
     for (int i = 0; i < 2; i++) if (A->ev[i]) cudaEventDestroy(A->ev[i]);
+    for (int i = 0; i < 2; i++) for (int j = 0; j < 4; j++) if (A->pev[i][j]) cudaEventDestroy(A->pev[i][j]);
     delete A;
     return PF2_OK;
 }
@@ -297,6 +331,18 @@ int pf2_spmv_host(pf2_csr* A, const double* x_host, double* y_host) {
     }
     cudaFree(x); cudaFree(y);
     return rc;
+}
+
+int pf2_spmv_set_tma_tuning(pf2_csr* A, int stages, int ctas_per_sm) {
+    A->tma_stages = stages; A->tma_ctas_per_sm = ctas_per_sm;
+    return PF2_OK;
+}
+
+int pf2_spmv_set_variant(pf2_csr* A, int variant) {
+    if (variant == 0) { A->spmv_variant = 0; plan_spmv(A); return PF2_OK; }
+    if (!variant_ok(A, variant)) { set_error("SpMV variant %d not applicable (max row %d)", variant, A->max_row); return PF2_E_UNSUPPORTED; }
+    A->spmv_variant = variant;
+    return PF2_OK;
 }
 
 int pf2_spmv_bench(pf2_csr* A, int variant, int reps, int flush_l2, double* ms_per_spmv) {

@@ -39,6 +39,13 @@ int pf2_ctx_create(int device, void* stream, pf2_ctx** out) {
     c->cc_major = prop.major;
     c->cc_minor = prop.minor;
     c->total_mem = prop.totalGlobalMem;
+    c->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+    c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    const char* env = getenv("PF2_L2_PERSIST");
+    c->l2_persist_enabled = (env && env[0] == '1');   // opt-in: the set-aside slows the sub-warp SpMV kernels (r01 sweep)
+    if (c->l2_persist_enabled && c->l2_persist_max > 0) {
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->l2_persist_max) != cudaSuccess) { cudaGetLastError(); c->l2_persist_enabled = false; }
+    }
     if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
     else { PF2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     PF2_TRY(pf2::dev_alloc(&c->red.partials, (size_t)pf2::kMaxBlocks * pf2::kMaxTerms));

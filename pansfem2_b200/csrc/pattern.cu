@@ -281,17 +281,18 @@ int pf2_csr_pattern(pf2_ctx* ctx, pf2_mesh* mesh, pf2_dofmap* map, pf2_csr** out
     pf2_csr* A = new pf2_csr();
     A->ctx = ctx;
     A->rows = map->kdegree;
-    PF2_TRY(dev_alloc(&A->indptr, (size_t)A->rows + 1));
-    PF2_CUDA(cudaMemsetAsync(A->indptr, 0, sizeof(long long) * ((size_t)A->rows + 1), s));
+    PF2_TRY(dev_alloc(&A->indptr, (size_t)A->rows + 1 + kCsrPad));
+    PF2_CUDA(cudaMemsetAsync(A->indptr, 0, sizeof(long long) * ((size_t)A->rows + 1 + kCsrPad), s));
     rowlen_kernel<<<gnode, kThreads, 0, s>>>(nnode, ndof, map->n2g, rowlen, A->indptr);
     PF2_LAUNCH_CHECK();
     PF2_TRY(inclusive_scan_inplace(ctx, A->indptr, (size_t)A->rows + 1));
     PF2_CUDA(cudaMemcpyAsync(&A->nnz, A->indptr + A->rows, sizeof(long long), cudaMemcpyDeviceToHost, s));
     PF2_CUDA(cudaStreamSynchronize(s));
-    PF2_TRY(dev_alloc(&A->indices, (size_t)A->nnz));
-    PF2_TRY(dev_alloc(&A->data, (size_t)A->nnz));
+    PF2_TRY(dev_alloc(&A->indices, (size_t)A->nnz + kCsrPad));
+    PF2_TRY(dev_alloc(&A->data, (size_t)A->nnz + kCsrPad));
     PF2_TRY(dev_alloc(&A->F, (size_t)A->rows));
-    PF2_CUDA(cudaMemsetAsync(A->data, 0, sizeof(double) * (size_t)A->nnz, s));
+    PF2_CUDA(cudaMemsetAsync(A->indices + A->nnz, 0, sizeof(int) * kCsrPad, s));
+    PF2_CUDA(cudaMemsetAsync(A->data, 0, sizeof(double) * ((size_t)A->nnz + kCsrPad), s));
     PF2_CUDA(cudaMemsetAsync(A->F, 0, sizeof(double) * (size_t)A->rows, s));
     fill_indices_kernel<<<ctx->grid_for((long long)nnode * ndof), kThreads, 0, s>>>(nnode, ndof, map->n2g, adj_ptr, adj, A->indptr, A->indices);
     PF2_LAUNCH_CHECK();

@@ -200,8 +200,10 @@ int pf2_simp_phase_ms(pf2_simp* S, double ms[6]) {
     return PF2_OK;
 }
 int pf2_simp_cg_stats(pf2_simp* S, double* spmv_ms_avg, long long* spmv_calls) {
-    if (spmv_ms_avg) *spmv_ms_avg = S->A->spmv_calls ? S->A->spmv_ms_total / S->A->spmv_calls : 0.0;
-    if (spmv_calls) *spmv_calls = S->A->spmv_calls;
+    double st[8];
+    PF2_TRY(pf2_csr_solver_stats(S->A, st));
+    if (spmv_ms_avg) *spmv_ms_avg = st[0];
+    if (spmv_calls) *spmv_calls = (long long)st[4];
     return PF2_OK;
 }
 

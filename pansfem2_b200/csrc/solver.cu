@@ -21,8 +21,9 @@ int spmv_dot(pf2_csr* A, const double* x, double* y, const CgState* st, double* 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 cg_init_kernel(int n, const double* __restrict__ b, const long long* __restrict__ indptr, const int* __restrict__ diagpos,
-               const double* __restrict__ data, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
-               double* __restrict__ p, CgState* st, int maxit, double eps, double* partials, unsigned int* ticket) {
+               const double* __restrict__ data, double* __restrict__ dvec, double* __restrict__ x, double* __restrict__ r,
+               double* __restrict__ z, double* __restrict__ p, CgState* st, int maxit, double eps, double* partials,
+               unsigned int* ticket) {
     double v[2] = { 0.0, 0.0 };
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double bi = b[i];
@@ -31,7 +32,8 @@ cg_init_kernel(int n, const double* __restrict__ b, const long long* __restrict_
         double zi = bi;
         if (MODE == 1) {
             const int dp = diagpos[i];
-            const double d = dp >= 0 ? data[indptr[i] + dp] : 0.0;
+            const double d = dp >= 0 ? data[indptr[i] + dp] : 0.0;      // GetDiagonal (CG.h:398-404), gathered once per solve
+            dvec[i] = d;
             zi = bi / d;
         }
         if (MODE != 2) { z[i] = zi; p[i] = zi; v[1] += zi * bi; }
@@ -55,9 +57,9 @@ __device__ __forceinline__ void cg_finalize(CgState* st, double zr, double rr) {
 // K2.  MODE 0/1 finish the iteration here; MODE 2 (ILU) only updates x, r and r.r -- z comes from the triangular solves.
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
-cg_update_kernel(int n, const double* __restrict__ p, const double* __restrict__ y, const long long* __restrict__ indptr,
-                 const int* __restrict__ diagpos, const double* __restrict__ data, double* __restrict__ x,
-                 double* __restrict__ r, double* __restrict__ z, CgState* st, double* partials, unsigned int* ticket) {
+cg_update_kernel(int n, const double* __restrict__ p, const double* __restrict__ y, const double* __restrict__ dvec,
+                 double* __restrict__ x, double* __restrict__ r, double* __restrict__ z, CgState* st, double* partials,
+                 unsigned int* ticket) {
     if (st->done) return;
     const double alpha = st->rho / st->pAp;
     double v[2] = { 0.0, 0.0 };
@@ -68,9 +70,7 @@ cg_update_kernel(int n, const double* __restrict__ p, const double* __restrict__
         v[1] += ri * ri;
         if (MODE == 0) { v[0] += ri * ri; }
         else if (MODE == 1) {
-            const int dp = diagpos[i];
-            const double d = dp >= 0 ? data[indptr[i] + dp] : 0.0;
-            const double zi = ri / d;
+            const double zi = ri / dvec[i];
             z[i] = zi;
             v[0] += zi * ri;
         }
@@ -167,8 +167,11 @@ __global__ void ilu0_sweep_level_kernel(int nrows_level, const int* __restrict__
 static int ensure_workspace(pf2_csr* A) {
     if (A->r) return PF2_OK;
     const size_t n = (size_t)A->rows;
-    PF2_TRY(dev_alloc(&A->r, n)); PF2_TRY(dev_alloc(&A->p, n)); PF2_TRY(dev_alloc(&A->z, n)); PF2_TRY(dev_alloc(&A->y, n));
+    const size_t np = (n + 31) & ~(size_t)31;     // keep every vector 256-byte aligned inside the slab
+    PF2_TRY(dev_alloc(&A->slab, 5 * np));
+    A->r = A->slab; A->p = A->slab + np; A->z = A->slab + 2 * np; A->y = A->slab + 3 * np; A->dvec = A->slab + 4 * np;
     PF2_TRY(dev_alloc(&A->st, 1));
+    for (int i = 0; i < 2; i++) for (int j = 0; j < 4; j++) PF2_CUDA(cudaEventCreate(&A->pev[i][j]));
     PF2_CUDA(cudaHostAlloc((void**)&A->h_st, 2 * sizeof(CgState), cudaHostAllocDefault));
     PF2_CUDA(cudaEventCreateWithFlags(&A->ev[0], cudaEventDisableTiming));
     PF2_CUDA(cudaEventCreateWithFlags(&A->ev[1], cudaEventDisableTiming));
@@ -258,12 +261,38 @@ int ilu0_apply(pf2_csr* A, double* v, const CgState* st) {
 }
 
 // enqueue one iteration
-static int enqueue_iteration(pf2_csr* A, int solver, double* x) {
+// keep the Krylov vectors resident in L2 while the matrix streams through (evict-first loads): the vectors are a third
+// of the bytes of a Jacobi-PCG iteration on 2-D problems
+static void l2_window(pf2_csr* A, bool on) {
+    pf2_ctx* c = A->ctx;
+    if (!c->l2_persist_enabled || c->l2_persist_max == 0 || c->l2_window_max == 0 || !A->slab) return;
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof attr);
+    if (on) {
+        const size_t np = (((size_t)A->rows) + 31) & ~(size_t)31;
+        size_t bytes = 5 * np * sizeof(double);
+        if (bytes > c->l2_window_max) bytes = c->l2_window_max;
+        attr.accessPolicyWindow.base_ptr = A->slab;
+        attr.accessPolicyWindow.num_bytes = bytes;
+        double ratio = (double)c->l2_persist_max / (double)bytes;
+        attr.accessPolicyWindow.hitRatio = (float)(ratio > 1.0 ? 1.0 : ratio);
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    } else {
+        attr.accessPolicyWindow.num_bytes = 0;
+    }
+    if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+    if (!on) { if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError(); }
+}
+
+// enqueue one iteration; `pev` (4 events) brackets the three kernels when this iteration is a timing sample
+static int enqueue_iteration(pf2_csr* A, int solver, double* x, cudaEvent_t* pev) {
     pf2_ctx* c = A->ctx;
     const int n = A->rows;
-    const int grid = c->grid_for(n, 2);
+    if (pev) PF2_CUDA(cudaEventRecord(pev[0], c->stream));
     PF2_TRY(spmv_dot(A, A->p, A->y, A->st, &A->st->pAp));
-#define UPD(M) cg_update_kernel<M><<<grid, kThreads, 0, c->stream>>>(n, A->p, A->y, A->indptr, A->diagpos, A->data, x, A->r, A->z, A->st, c->red.partials, c->red.ticket)
+    if (pev) PF2_CUDA(cudaEventRecord(pev[1], c->stream));
+#define UPD(M) cg_update_kernel<M><<<std::min(c->grid_for(n, 2), c->wave_grid((const void*)cg_update_kernel<M>, kThreads)), kThreads, 0, c->stream>>>(n, A->p, A->y, A->dvec, x, A->r, A->z, A->st, c->red.partials, c->red.ticket)
     if (solver == PF2_SOLVER_CG) { UPD(0); }
     else if (solver == PF2_SOLVER_SCALINGCG) { UPD(1); }
     else {
@@ -271,14 +300,25 @@ static int enqueue_iteration(pf2_csr* A, int solver, double* x) {
         c->launches++;
         PF2_CUDA(cudaMemcpyAsync(A->z, A->r, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
         PF2_TRY(ilu0_apply(A, A->z, A->st));
-        cg_dot_finalize_kernel<<<grid, kThreads, 0, c->stream>>>(n, A->z, A->r, A->st, 0, nullptr, nullptr, c->red.partials, c->red.ticket);
+        cg_dot_finalize_kernel<<<std::min(c->grid_for(n, 2), c->wave_grid((const void*)cg_dot_finalize_kernel, kThreads)), kThreads, 0, c->stream>>>(n, A->z, A->r, A->st, 0, nullptr, nullptr, c->red.partials, c->red.ticket);
     }
 #undef UPD
     c->launches++;
-    cg_pupdate_kernel<<<grid, kThreads, 0, c->stream>>>(n, solver == PF2_SOLVER_CG ? A->r : A->z, A->p, A->st);
+    if (pev) PF2_CUDA(cudaEventRecord(pev[2], c->stream));
+    cg_pupdate_kernel<<<std::min(c->grid_for(n, 2), c->wave_grid((const void*)cg_pupdate_kernel, kThreads)), kThreads, 0, c->stream>>>(n, solver == PF2_SOLVER_CG ? A->r : A->z, A->p, A->st);
     c->launches++;
+    if (pev) PF2_CUDA(cudaEventRecord(pev[3], c->stream));
     PF2_LAUNCH_CHECK();
     return PF2_OK;
+}
+
+static void harvest_profile(pf2_csr* A, int slot) {
+    if (!A->pev_armed[slot]) return;
+    A->pev_armed[slot] = false;
+    float ms[3];
+    for (int j = 0; j < 3; j++) if (cudaEventElapsedTime(&ms[j], A->pev[slot][j], A->pev[slot][j + 1]) != cudaSuccess) { cudaGetLastError(); return; }
+    for (int j = 0; j < 3; j++) A->prof_ms[j] += ms[j];
+    A->prof_samples++;
 }
 
 int solve(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out) {
@@ -288,9 +328,10 @@ int solve(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double
     PF2_CUDA(cudaSetDevice(c->device));
     PF2_TRY(ensure_workspace(A));
     const int n = A->rows;
-    const int grid = c->grid_for(n, 2);
+    const int grid = std::min(c->grid_for(n, 2), c->sm_count * 4);
     if (solver == PF2_SOLVER_ILU0CG) PF2_TRY(ilu0_factor(A));
-#define INIT(M) cg_init_kernel<M><<<grid, kThreads, 0, c->stream>>>(n, b, A->indptr, A->diagpos, A->data, x, A->r, A->z, A->p, A->st, itrmax, eps, c->red.partials, c->red.ticket)
+    l2_window(A, true);
+#define INIT(M) cg_init_kernel<M><<<grid, kThreads, 0, c->stream>>>(n, b, A->indptr, A->diagpos, A->data, A->dvec, x, A->r, A->z, A->p, A->st, itrmax, eps, c->red.partials, c->red.ticket)
     if (solver == PF2_SOLVER_CG) { INIT(0); }
     else if (solver == PF2_SOLVER_SCALINGCG) { INIT(1); }
     else {
@@ -313,13 +354,18 @@ int solve(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double
     bool finished = false;
     while (!finished) {
         const int todo = std::min(chunk, itrmax - enq);
-        for (int k = 0; k < todo; k++) PF2_TRY(enqueue_iteration(A, solver, x));
+        for (int k = 0; k < todo; k++) {
+            const bool sample = (k == todo / 2) && enq > 0;
+            PF2_TRY(enqueue_iteration(A, solver, x, sample ? A->pev[slot] : nullptr));
+            if (sample) A->pev_armed[slot] = true;
+        }
         enq += todo;
         PF2_CUDA(cudaMemcpyAsync(&A->h_st[slot], A->st, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
         PF2_CUDA(cudaEventRecord(A->ev[slot], c->stream));
         if (have_prev) {
             PF2_CUDA(cudaEventSynchronize(A->ev[slot ^ 1]));
             last = A->h_st[slot ^ 1];
+            if (!last.done) harvest_profile(A, slot ^ 1); else A->pev_armed[slot ^ 1] = false;
             if (last.done) finished = true;
         }
         if (!finished && (enq >= itrmax || todo == 0)) {
@@ -331,10 +377,13 @@ int solve(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double
         slot ^= 1;
     }
     PF2_CUDA(cudaStreamSynchronize(c->stream));
+    A->pev_armed[0] = A->pev_armed[1] = false;
+    l2_window(A, false);
     // the freshest state (the chunk in flight may have converged)
     PF2_CUDA(cudaMemcpyAsync(&A->h_st[0], A->st, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
     PF2_CUDA(cudaStreamSynchronize(c->stream));
     last = A->h_st[0];
+    A->total_iters += last.iter;
     if (iters_out) *iters_out = last.iter;
     if (relres_out) *relres_out = sqrt(last.rr) / sqrt(last.bb);
     if (!last.done) {
@@ -364,6 +413,18 @@ int pf2_solve_host(pf2_csr* A, int solver, const double* b_host, double* x_host,
     PF2_CUDA(cudaMemcpyAsync(x_host, A->xw, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
     PF2_CUDA(cudaStreamSynchronize(c->stream));
     return rc;
+}
+
+int pf2_csr_solver_stats(pf2_csr* A, double out[8]) {
+    const double k = A->prof_samples ? 1.0 / (double)A->prof_samples : 0.0;
+    out[0] = A->prof_ms[0] * k; out[1] = A->prof_ms[1] * k; out[2] = A->prof_ms[2] * k;
+    out[3] = (double)A->prof_samples; out[4] = (double)A->total_iters; out[5] = (double)A->spmv_variant;
+    out[6] = (double)A->rows; out[7] = (double)A->nnz;
+    return PF2_OK;
+}
+int pf2_csr_solver_stats_reset(pf2_csr* A) {
+    A->prof_ms[0] = A->prof_ms[1] = A->prof_ms[2] = 0.0; A->prof_samples = 0; A->total_iters = 0;
+    return PF2_OK;
 }
 
 int pf2_ilu0_factor(pf2_csr* A) { return ilu0_factor(A); }

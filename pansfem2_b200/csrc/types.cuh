@@ -17,6 +17,7 @@ struct pf2_dofmap {
 };
 
 namespace pf2 {
+constexpr int kCsrPad = 8;   // spare entries behind indptr / indices / data (see spmv_tma.cuh)
 // device-resident state of one Krylov solve (CG.h:124-154 / 420-453 / 320-352)
 struct CgState {
     double rho;      // z.r of the current residual (Mrkrk)
@@ -48,9 +49,9 @@ struct pf2_csr {
     int map_npe = 0, map_ndof = 0, map_nelem = 0;
     // SpMV plan
     int spmv_variant = 0;          // 0 = not planned
-    int stream_rows = 0;           // rows per block of the streaming kernel
+    int tma_stages = 3, tma_ctas_per_sm = 4;   // TMA pipeline depth and residency target
     // Krylov workspace (lazily allocated)
-    double *r = nullptr, *p = nullptr, *z = nullptr, *y = nullptr, *xw = nullptr, *bw = nullptr;
+    double *r = nullptr, *p = nullptr, *z = nullptr, *y = nullptr, *dvec = nullptr, *xw = nullptr, *bw = nullptr;
     pf2::CgState* st = nullptr;
     pf2::CgState* h_st = nullptr;  // pinned, 2 slots
     cudaEvent_t ev[2] = { nullptr, nullptr };
@@ -60,9 +61,13 @@ struct pf2_csr {
     int* level_rows = nullptr;     // rows sorted by dependency level of the forward (unit-L) sweep
     int* level_rows_u = nullptr;   // ... of the backward (U) sweep
     std::vector<int> h_level_ptr, h_level_ptr_u;   // host: first row of each level in the arrays above
-    // instrumentation
-    double spmv_ms_total = 0;
-    long long spmv_calls = 0;
+    double* slab = nullptr;        // r | p | z | y | dvec contiguous (one L2 access-policy window)
+    // instrumentation: every chunk one iteration is bracketed by events (sampled per-kernel device time)
+    cudaEvent_t pev[2][4] = { { nullptr, nullptr, nullptr, nullptr }, { nullptr, nullptr, nullptr, nullptr } };
+    bool pev_armed[2] = { false, false };
+    double prof_ms[3] = { 0, 0, 0 };   // spmv+dot, update, p-update
+    long long prof_samples = 0;
+    long long total_iters = 0;
 };
 
 struct pf2_filter {

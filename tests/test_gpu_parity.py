@@ -112,7 +112,7 @@ def test_remove_boundary_conditions_numbering(ctx):
 # ---------------------------------------------------------------------------------------------------------------
 def test_spmv_all_kernel_variants(ctx):
     rng = np.random.default_rng(5)
-    for P in (problems.cantilever2d(40, 30), problems.heat2d(33, 17), problems.cantilever3d(6, 5, 4)):
+    for P in (problems.cantilever2d(40, 30), problems.heat2d(33, 17), problems.cantilever3d(6, 4, 5)):
         So, *_ = orc.assemble(P.eq, P.coords, P.conn, P.fixed, P.loads, rng.uniform(0.5, 2, P.nelem))
         indptr, indices, data, F = So.arrays()
         A = capi.Csr.upload(ctx, indptr, indices, data)
@@ -120,13 +120,17 @@ def test_spmv_all_kernel_variants(ctx):
         y_ref = So.spmv(x)
         assert rel(A.spmv_host(x), y_ref) < 1e-14
         ok = 0
-        for variant in (1, 2, 3, 4, 5, 11, 12, 13, 14, 15):
+        for variant in (1, 2, 3, 4, 5, 11, 12, 13, 14, 15, 21, 22, 23, 24, 25, 26):
             try:
-                A.spmv_bench(variant, reps=1, flush_l2=False)
-                ok += 1
+                A.set_spmv_variant(variant)
             except capi.Pf2Error as e:
                 assert e.code == 5
-        assert ok >= 6
+                continue
+            assert rel(A.spmv_host(x), y_ref) < 1e-14, variant
+            xs, it, rr = A.solve_host(capi.SOLVER_SCALINGCG, F)          # the fused p.Ap epilogue of every variant
+            assert rr < 1e-10, variant
+            ok += 1
+        assert ok >= 8
         A.close()
 
 
