@@ -251,6 +251,7 @@ int assemble_device(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq, const d
         c->launches++;
     }
     A->ilu_valid = false;
+    A->sell_values_valid = false;
     return PF2_OK;
 }
 

@@ -12,6 +12,8 @@
 // Both optionally fuse the dot product x.y (p.Ap of CG, CG.h:433) into the epilogue.
 #include "types.cuh"
 #include "spmv_tma.cuh"
+#include "spmv_sell.cuh"
+#include <cub/cub.cuh>
 
 namespace pf2 {
 
@@ -146,11 +148,14 @@ int csr_finalize_structure(pf2_csr* A) {
 
 // variant encoding: 1..5 = vector TPR 2,4,8,16,32 ; 11..15 = stream with G = 1,2,4,8,16 threads per row ;
 //                   21..26 = TMA pipeline with G = 1,2,4,8,16,32
+static int sell_build(pf2_csr* A);
 static void plan_spmv(pf2_csr* A) {
     if (A->spmv_variant) return;
     const double mean = A->rows ? (double)A->nnz / A->rows : 1.0;
-    // Measured inside the PCG loop on B200 (tools/cg_sweep.py, profiles/r01_cg_sweep_*.txt): the sub-warp vector kernel
-    // with ~2-3 nonzeros per lane wins; the shared-memory stream and TMA-pipeline kernels stay selectable (11-15, 21-26).
+    // Measured inside the PCG loop on B200 (tools/cg_sweep.py, profiles/r01_cg_sweep_*.json): the SELL-32 thread-per-row
+    // kernel wins whenever padding is small (FEM rows are near-uniform); otherwise the sub-warp CSR kernel with 2-3
+    // nonzeros per lane.  The shared-memory stream and TMA-pipeline kernels stay selectable (11-15, 21-26).
+    if (A->rows >= 64 && sell_build(A) == PF2_OK && (double)A->sell_entries <= 1.15 * (double)A->nnz) { A->spmv_variant = 31; return; }
     A->spmv_variant = mean <= 4 ? 1 : mean <= 10 ? 2 : mean <= 24 ? 3 : mean <= 48 ? 4 : 5;
 }
 
@@ -171,6 +176,54 @@ static int launch_tma(pf2_csr* A, const double* x, double* y, const CgState* st,
     const int grid = std::max(1, std::min(ntiles, c->sm_count * per_sm));
     spmv_tma_kernel<G, DOT><<<grid, kTmaThreads, smem, c->stream>>>(A->rows, A->indptr, A->indices, A->data, x, y, st, dot_out,
                                                                    c->red.partials, c->red.ticket, cap, stages);
+    return PF2_OK;
+}
+
+static int sell_build(pf2_csr* A) {
+    if (A->sell_ptr) return PF2_OK;
+    pf2_ctx* c = A->ctx;
+    const int nslices = (A->rows + kSellC - 1) / kSellC;
+    PF2_TRY(dev_alloc(&A->sell_ptr, (size_t)nslices + 1));
+    sell_slice_len_kernel<<<c->grid_for(nslices), kThreads, 0, c->stream>>>(A->rows, nslices, A->indptr, A->sell_ptr);
+    PF2_LAUNCH_CHECK();
+    void* tmp = nullptr;
+    size_t bytes = 0;
+    PF2_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, A->sell_ptr, A->sell_ptr, nslices + 1, c->stream));
+    PF2_CUDA(cudaMalloc(&tmp, bytes ? bytes : 8));
+    PF2_CUDA(cub::DeviceScan::InclusiveSum(tmp, bytes, A->sell_ptr, A->sell_ptr, nslices + 1, c->stream));
+    PF2_CUDA(cudaMemcpyAsync(&A->sell_entries, A->sell_ptr + nslices, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    PF2_CUDA(cudaStreamSynchronize(c->stream));
+    PF2_CUDA(cudaFree(tmp));
+    PF2_TRY(dev_alloc(&A->sell_idx, (size_t)A->sell_entries));
+    PF2_TRY(dev_alloc(&A->sell_val, (size_t)A->sell_entries));
+    sell_fill_kernel<<<c->grid_for(A->rows), kThreads, 0, c->stream>>>(A->rows, A->indptr, A->indices, A->sell_ptr, A->sell_idx);
+    PF2_LAUNCH_CHECK();
+    c->launches += 4;
+    A->sell_values_valid = false;
+    return PF2_OK;
+}
+
+int sell_refresh(pf2_csr* A) {
+    PF2_TRY(sell_build(A));
+    pf2_ctx* c = A->ctx;
+    const int nslices = (A->rows + kSellC - 1) / kSellC;
+    sell_values_kernel<<<std::min((nslices + 7) / 8, c->sm_count * 16), kThreads, 0, c->stream>>>(A->rows, A->indptr, A->data, A->sell_ptr, A->sell_val);
+    sell_pad_tail_kernel<<<1, kThreads, 0, c->stream>>>(A->rows, nslices, A->sell_ptr, A->sell_idx, A->sell_val);
+    PF2_LAUNCH_CHECK();
+    c->launches += 2;
+    A->sell_values_valid = true;
+    return PF2_OK;
+}
+
+template <bool DOT>
+static int launch_sell(pf2_csr* A, const double* x, double* y, const CgState* st, double* dot_out) {
+    pf2_ctx* c = A->ctx;
+    if (!A->sell_values_valid) PF2_TRY(sell_refresh(A));
+    const int nslices = (A->rows + kSellC - 1) / kSellC;
+    const int nb = (nslices + (kThreads / 32) - 1) / (kThreads / 32);
+    const int grid = std::max(1, std::min(nb, c->wave_grid((const void*)spmv_sell_kernel<DOT>, kThreads)));
+    spmv_sell_kernel<DOT><<<grid, kThreads, 0, c->stream>>>(A->rows, A->sell_ptr, A->sell_idx, A->sell_val, x, y, st, dot_out,
+                                                          c->red.partials, c->red.ticket);
     return PF2_OK;
 }
 
@@ -201,6 +254,7 @@ static int launch_spmv(pf2_csr* A, int variant, const double* x, double* y, cons
         case 13: STR(4) break;
         case 14: STR(8) break;
         case 15: STR(16) break;
+        case 31: PF2_TRY((launch_sell<DOT>(A, x, y, st, dot_out))); break;
         case 21: PF2_TRY((launch_tma<1, DOT>(A, x, y, st, dot_out))); break;
         case 22: PF2_TRY((launch_tma<2, DOT>(A, x, y, st, dot_out))); break;
         case 23: PF2_TRY((launch_tma<4, DOT>(A, x, y, st, dot_out))); break;
@@ -223,6 +277,7 @@ static bool variant_ok(const pf2_csr* A, int variant) {
         int G = 1 << (variant - 11);
         return (long long)(kThreads / G) * A->max_row <= kStreamCap;
     }
+    if (variant == 31) return true;
     if (variant >= 21 && variant <= 26) {
         int G = 1 << (variant - 21);
         return (long long)(kConsumers / G) * A->max_row <= kTileNnz;
@@ -281,7 +336,7 @@ int pf2_csr_destroy(pf2_csr* A) {
     if (!A) return PF2_OK;
     cudaSetDevice(A->ctx->device);
     cudaStreamSynchronize(A->ctx->stream);
-    void* ptrs[] = { A->indptr, A->indices, A->data, A->F, A->diagpos, A->bmap, A->slab, A->xw, A->bw, A->st,
+    void* ptrs[] = { A->indptr, A->indices, A->data, A->F, A->diagpos, A->bmap, A->slab, A->xw, A->bw, A->st, A->sell_ptr, A->sell_idx, A->sell_val,
                      A->ilu, A->level_rows, A->level_rows_u };
     for (void* p : ptrs) if (p) cudaFree(p);
     if (A->h_st) cudaFreeHost(A->h_st);
@@ -311,6 +366,7 @@ int pf2_csr_set_values(pf2_csr* A, const double* data_host) {
     PF2_CUDA(cudaMemcpyAsync(A->data, data_host, sizeof(double) * (size_t)A->nnz, cudaMemcpyHostToDevice, A->ctx->stream));
     PF2_CUDA(cudaStreamSynchronize(A->ctx->stream));
     A->ilu_valid = false;
+    A->sell_values_valid = false;
     return PF2_OK;
 }
 int pf2_csr_device_F(pf2_csr* A, double** F_dev) { *F_dev = A->F; return PF2_OK; }

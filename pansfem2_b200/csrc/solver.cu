@@ -55,6 +55,7 @@ __device__ __forceinline__ void cg_finalize(CgState* st, double zr, double rr) {
 }
 
 // K2.  MODE 0/1 finish the iteration here; MODE 2 (ILU) only updates x, r and r.r -- z comes from the triangular solves.
+// Two elements per thread with 128-bit loads/stores (all vectors are 16-byte aligned; an odd tail is handled scalar).
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 cg_update_kernel(int n, const double* __restrict__ p, const double* __restrict__ y, const double* __restrict__ dvec,
@@ -63,17 +64,37 @@ cg_update_kernel(int n, const double* __restrict__ p, const double* __restrict__
     if (st->done) return;
     const double alpha = st->rho / st->pAp;
     double v[2] = { 0.0, 0.0 };
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int n2 = n >> 1;
+    const double2* p2 = reinterpret_cast<const double2*>(p);
+    const double2* y2 = reinterpret_cast<const double2*>(y);
+    const double2* d2 = reinterpret_cast<const double2*>(dvec);
+    double2* x2 = reinterpret_cast<double2*>(x);
+    double2* r2 = reinterpret_cast<double2*>(r);
+    double2* z2 = reinterpret_cast<double2*>(z);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
+        const double2 pp = p2[i], yy = y2[i];
+        double2 xx = x2[i], rr = r2[i];
+        xx.x = xx.x + alpha * pp.x; xx.y = xx.y + alpha * pp.y;
+        rr.x = rr.x + (-alpha) * yy.x; rr.y = rr.y + (-alpha) * yy.y;
+        x2[i] = xx; r2[i] = rr;
+        v[1] += rr.x * rr.x + rr.y * rr.y;
+        if (MODE == 0) { v[0] += rr.x * rr.x + rr.y * rr.y; }
+        else if (MODE == 1) {
+            const double2 dd = d2[i];
+            double2 zz;
+            zz.x = rr.x / dd.x; zz.y = rr.y / dd.y;
+            z2[i] = zz;
+            v[0] += zz.x * rr.x + zz.y * rr.y;
+        }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int i = n - 1;
         x[i] = x[i] + alpha * p[i];
         const double ri = r[i] + (-alpha) * y[i];
         r[i] = ri;
         v[1] += ri * ri;
-        if (MODE == 0) { v[0] += ri * ri; }
-        else if (MODE == 1) {
-            const double zi = ri / dvec[i];
-            z[i] = zi;
-            v[0] += zi * ri;
-        }
+        if (MODE == 0) v[0] += ri * ri;
+        else if (MODE == 1) { const double zi = ri / dvec[i]; z[i] = zi; v[0] += zi * ri; }
     }
     if (grid_sum_last<2>(v, partials, ticket) && threadIdx.x == 0) {
         if (MODE == 2) st->rr = v[1];
@@ -103,7 +124,16 @@ cg_pupdate_kernel(int n, const double* __restrict__ z, double* __restrict__ p, c
     // the iteration that set `done` still updated p in the reference; x is what matters and it is frozen, so skip
     if (st->done) return;
     const double beta = st->beta;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = beta * p[i] + z[i];
+    const int n2 = n >> 1;
+    const double2* z2 = reinterpret_cast<const double2*>(z);
+    double2* p2 = reinterpret_cast<double2*>(p);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
+        const double2 zz = z2[i];
+        double2 pp = p2[i];
+        pp.x = beta * pp.x + zz.x; pp.y = beta * pp.y + zz.y;
+        p2[i] = pp;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = beta * p[n - 1] + z[n - 1];
 }
 
 // ---- ILU(0) ----------------------------------------------------------------------------------------------------
@@ -292,7 +322,7 @@ static int enqueue_iteration(pf2_csr* A, int solver, double* x, cudaEvent_t* pev
     if (pev) PF2_CUDA(cudaEventRecord(pev[0], c->stream));
     PF2_TRY(spmv_dot(A, A->p, A->y, A->st, &A->st->pAp));
     if (pev) PF2_CUDA(cudaEventRecord(pev[1], c->stream));
-#define UPD(M) cg_update_kernel<M><<<std::min(c->grid_for(n, 2), c->wave_grid((const void*)cg_update_kernel<M>, kThreads)), kThreads, 0, c->stream>>>(n, A->p, A->y, A->dvec, x, A->r, A->z, A->st, c->red.partials, c->red.ticket)
+#define UPD(M) cg_update_kernel<M><<<std::min(c->grid_for(n, 4), c->wave_grid((const void*)cg_update_kernel<M>, kThreads)), kThreads, 0, c->stream>>>(n, A->p, A->y, A->dvec, x, A->r, A->z, A->st, c->red.partials, c->red.ticket)
     if (solver == PF2_SOLVER_CG) { UPD(0); }
     else if (solver == PF2_SOLVER_SCALINGCG) { UPD(1); }
     else {
@@ -305,7 +335,7 @@ static int enqueue_iteration(pf2_csr* A, int solver, double* x, cudaEvent_t* pev
 #undef UPD
     c->launches++;
     if (pev) PF2_CUDA(cudaEventRecord(pev[2], c->stream));
-    cg_pupdate_kernel<<<std::min(c->grid_for(n, 2), c->wave_grid((const void*)cg_pupdate_kernel, kThreads)), kThreads, 0, c->stream>>>(n, solver == PF2_SOLVER_CG ? A->r : A->z, A->p, A->st);
+    cg_pupdate_kernel<<<std::min(c->grid_for(n, 4), c->wave_grid((const void*)cg_pupdate_kernel, kThreads)), kThreads, 0, c->stream>>>(n, solver == PF2_SOLVER_CG ? A->r : A->z, A->p, A->st);
     c->launches++;
     if (pev) PF2_CUDA(cudaEventRecord(pev[3], c->stream));
     PF2_LAUNCH_CHECK();
@@ -328,6 +358,7 @@ int solve(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double
     PF2_CUDA(cudaSetDevice(c->device));
     PF2_TRY(ensure_workspace(A));
     const int n = A->rows;
+    PF2_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 7) == 0, "x must be 16-byte aligned (pf2_malloc gives 256)");
     const int grid = std::min(c->grid_for(n, 2), c->sm_count * 4);
     if (solver == PF2_SOLVER_ILU0CG) PF2_TRY(ilu0_factor(A));
     l2_window(A, true);

@@ -1,0 +1,107 @@
+// spmv_sell.cuh -- sliced-ELL (SELL-32) mirror of the CSR matrix and its SpMV kernel.
+//
+// Why: the sub-warp CSR kernel is limited by the L1/LSU, not by DRAM (ncu: l1tex 64 % busy, long-scoreboard stalls at
+// full occupancy, DRAM 49 %; profiles/r01_ncu_full_cg_kernels_vector8.txt): 8 lanes share one row, so a warp's value /
+// index loads hit 4 separate row segments and its x gathers ~12 sectors.  In SELL-32 a slice is 32 consecutive rows
+// stored column-major: lane l owns row l of the slice, the k-th value / index loads of a warp are one contiguous
+// 256 B / 128 B line, and because consecutive FEM rows have consecutive columns the k-th gather of a warp spans
+// ~256 contiguous bytes of x.  No shuffles, 18 independent loads per lane (unrolled) keep > 100 KB per SM in flight.
+// Padding (rows shorter than the slice's longest) is zero-valued with the row's own column, so it is harmless.
+// CSR stays the canonical storage (assembly, download, ILU0): sell_val is refreshed from CSR data before a solve
+// (one 16 B/nnz pass, < 0.1 % of a solve).  Algorithmic bytes stay 12*nnz + 24*rows; the stored entries are
+// sell_entries >= nnz (ratio reported as `sell_fill`).
+#pragma once
+#include "types.cuh"
+
+namespace pf2 {
+
+constexpr int kSellC = 32;
+
+__global__ void sell_slice_len_kernel(int rows, int nslices, const long long* __restrict__ indptr, long long* __restrict__ slice_ptr) {
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nslices; s += gridDim.x * blockDim.x) {
+        int m = 0;
+        for (int r = s * kSellC; r < min(rows, (s + 1) * kSellC); r++) m = max(m, (int)(indptr[r + 1] - indptr[r]));
+        slice_ptr[s + 1] = (long long)m * kSellC;
+        if (s == 0) slice_ptr[0] = 0;
+    }
+}
+
+// fill indices (pattern) and the CSR->SELL position of every stored entry
+__global__ void sell_fill_kernel(int rows, const long long* __restrict__ indptr, const int* __restrict__ indices,
+                                 const long long* __restrict__ slice_ptr, int* __restrict__ sell_idx) {
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+        const int s = r / kSellC, l = r % kSellC;
+        const long long base = slice_ptr[s];
+        const int width = (int)((slice_ptr[s + 1] - base) / kSellC);
+        const long long b = indptr[r];
+        const int len = (int)(indptr[r + 1] - b);
+        for (int k = 0; k < width; k++) sell_idx[base + (long long)k * kSellC + l] = (k < len) ? indices[b + k] : r;
+    }
+}
+// padding lanes of the last slice (rows beyond `rows`)
+__global__ void sell_pad_tail_kernel(int rows, int nslices, const long long* __restrict__ slice_ptr, int* __restrict__ sell_idx, double* __restrict__ sell_val) {
+    const int s = nslices - 1;
+    const long long base = slice_ptr[s];
+    const int width = (int)((slice_ptr[s + 1] - base) / kSellC);
+    for (int t = threadIdx.x; t < width * kSellC; t += blockDim.x) {
+        const int l = t % kSellC;
+        if (s * kSellC + l >= rows) { sell_idx[base + t] = 0; sell_val[base + t] = 0.0; }
+    }
+}
+__global__ void sell_values_kernel(int rows, const long long* __restrict__ indptr, const double* __restrict__ data,
+                                   const long long* __restrict__ slice_ptr, double* __restrict__ sell_val) {
+    // one warp per slice: lane l copies row l; reads are strided (row-contiguous), writes coalesced
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int nslices = (rows + kSellC - 1) / kSellC;
+    for (int s = warp; s < nslices; s += nwarps) {
+        const int r = s * kSellC + lane;
+        const long long base = slice_ptr[s];
+        const int width = (int)((slice_ptr[s + 1] - base) / kSellC);
+        long long b = 0;
+        int len = 0;
+        if (r < rows) { b = indptr[r]; len = (int)(indptr[r + 1] - b); }
+        for (int k = 0; k < width; k++) sell_val[base + (long long)k * kSellC + lane] = (k < len) ? data[b + k] : 0.0;
+    }
+}
+
+template <bool DOT>
+__global__ void __launch_bounds__(kThreads)
+spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* __restrict__ sell_idx, const double* __restrict__ sell_val,
+                 const double* __restrict__ x, double* __restrict__ y, const CgState* __restrict__ st, double* dot_out,
+                 double* partials, unsigned int* ticket) {
+    if (DOT && st != nullptr && st->done) return;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int nslices = (rows + kSellC - 1) / kSellC;
+    double dot = 0.0;
+    for (int s = warp; s < nslices; s += nwarps) {
+        const long long base = slice_ptr[s];
+        const int width = (int)((slice_ptr[s + 1] - base) / kSellC);
+        const double* v = sell_val + base + lane;
+        const int* c = sell_idx + base + lane;
+        double acc = 0.0;
+        int k = 0;
+        for (; k + 6 <= width; k += 6) {
+            double vv[6];
+            int cc[6];
+#pragma unroll
+            for (int u = 0; u < 6; u++) { vv[u] = __ldcs(v + (k + u) * kSellC); cc[u] = __ldcs(c + (k + u) * kSellC); }
+#pragma unroll
+            for (int u = 0; u < 6; u++) acc += vv[u] * __ldg(x + cc[u]);
+        }
+        for (; k < width; k++) acc += __ldcs(v + k * kSellC) * __ldg(x + __ldcs(c + k * kSellC));
+        const int r = s * kSellC + lane;
+        if (r < rows) {
+            y[r] = acc;
+            if (DOT) dot += acc * x[r];
+        }
+    }
+    if (DOT) {
+        double vsum[1] = { dot };
+        if (grid_sum_last<1>(vsum, partials, ticket) && threadIdx.x == 0) *dot_out = vsum[0];
+    }
+}
+
+}  // namespace pf2

@@ -50,6 +50,12 @@ struct pf2_csr {
     // SpMV plan
     int spmv_variant = 0;          // 0 = not planned
     int tma_stages = 3, tma_ctas_per_sm = 4;   // TMA pipeline depth and residency target
+    // SELL-32 mirror (variant 31): slice pointers, column-major indices / values, stored entries
+    long long* sell_ptr = nullptr;
+    int* sell_idx = nullptr;
+    double* sell_val = nullptr;
+    long long sell_entries = 0;
+    bool sell_values_valid = false;
     // Krylov workspace (lazily allocated)
     double *r = nullptr, *p = nullptr, *z = nullptr, *y = nullptr, *dvec = nullptr, *xw = nullptr, *bw = nullptr;
     pf2::CgState* st = nullptr;

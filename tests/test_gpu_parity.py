@@ -120,7 +120,7 @@ def test_spmv_all_kernel_variants(ctx):
         y_ref = So.spmv(x)
         assert rel(A.spmv_host(x), y_ref) < 1e-14
         ok = 0
-        for variant in (1, 2, 3, 4, 5, 11, 12, 13, 14, 15, 21, 22, 23, 24, 25, 26):
+        for variant in (1, 2, 3, 4, 5, 11, 12, 13, 14, 15, 21, 22, 23, 24, 25, 26, 31):
             try:
                 A.set_spmv_variant(variant)
             except capi.Pf2Error as e:
