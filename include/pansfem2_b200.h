@@ -141,7 +141,9 @@ int pf2_csr_solver_stats_reset(pf2_csr* A);
 /* ILU(0) factors of A (unit-L strictly lower + U with diagonal in A's pattern), cached on A until values change */
 int pf2_ilu0_factor(pf2_csr* A);
 int pf2_ilu0_download(pf2_csr* A, double* data_host);
-int pf2_ilu0_solve_host(pf2_csr* A, const double* b_host, double* x_host);   /* PreILU0 */
+int pf2_ilu0_solve_host(pf2_csr* A, const double* b_host, double* x_host);   /* PreILU0 with A's cached factors */
+/* PreILU0(M, b) (CG.h:289-315) where the VALUES of M are the factors (what the reference's ILU0 returns) */
+int pf2_preilu0_host(pf2_csr* M, const double* b_host, double* x_host);
 
 /* Disassembling (Assembling.h:163-171): free dofs from the solution, fixed dofs keep their Dirichlet value */
 int pf2_disassemble(pf2_dofmap* map, const double* x_dev, double* u_nodal_dev);
@@ -172,6 +174,12 @@ int pf2_oc_is_convergence(pf2_oc* oc, double f, int* converged);           /* OC
  * (sample_optimize_density_oc.cpp:198-207) evaluated on the device.  x_dev updated in place. */
 int pf2_oc_update(pf2_oc* oc, pf2_filter* filter, double weightlimit, double scale1, double* x_dev, double f,
                   const double* dfdx_dev, const double* dgdx_dev, int* steps_out, double* lambda_out);
+/* one OC candidate x+(lambda) (OC.h:85-92), host in / host out: lets a caller-supplied constraint functor drive the
+ * bisection on the host exactly as OC<T>::UpdateVariables<F> does */
+int pf2_oc_candidate_host(pf2_oc* oc, const double* x_host, const double* dfdx_host, const double* dgdx_host, double lambda,
+                          double* xnew_host);
+/* bookkeeping of UpdateVariables (OC.h:104-105) for callers that ran the bisection themselves */
+int pf2_oc_commit(pf2_oc* oc, double f);
 
 /* ---- MMA (MMA.h:64-509) --------------------------------------------------------------------------------------- */
 int pf2_mma_create(pf2_ctx* ctx, int n, int m, double a0, const double* a_host, const double* c_host,

@@ -302,9 +302,8 @@ int pf2_assemble(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq, const doub
 int pf2_element_matrix(pf2_ctx* ctx, int eq, const double* xe_host, double E, double V, double t, double* Ke_host) {
     PF2_CHECK(ctx && xe_host && Ke_host && eq >= 0 && eq <= 2, "bad arguments");
     const int npe = eq_npe(eq), dim = eq_dim(eq), m = npe * eq_ndof(eq);
-    double *xe = nullptr, *Ke = nullptr;
-    PF2_TRY(dev_alloc(&xe, (size_t)npe * dim));
-    PF2_TRY(dev_alloc(&Ke, (size_t)m * m));
+    if (!ctx->elem_scratch) PF2_TRY(dev_alloc(&ctx->elem_scratch, (size_t)24 + 576));
+    double *xe = ctx->elem_scratch, *Ke = ctx->elem_scratch + 24;
     PF2_CUDA(cudaMemcpyAsync(xe, xe_host, sizeof(double) * npe * dim, cudaMemcpyHostToDevice, ctx->stream));
     if (eq == PF2_EQ_PLANESTRAIN) element_matrix_kernel<PF2_EQ_PLANESTRAIN><<<1, 32, 0, ctx->stream>>>(xe, E, V, t, Ke);
     else if (eq == PF2_EQ_SOLID) element_matrix_kernel<PF2_EQ_SOLID><<<1, 32, 0, ctx->stream>>>(xe, E, V, t, Ke);
@@ -313,7 +312,6 @@ int pf2_element_matrix(pf2_ctx* ctx, int eq, const double* xe_host, double E, do
     ctx->launches++;
     PF2_CUDA(cudaMemcpyAsync(Ke_host, Ke, sizeof(double) * m * m, cudaMemcpyDeviceToHost, ctx->stream));
     PF2_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(xe); cudaFree(Ke);
     return PF2_OK;
 }
 

@@ -65,6 +65,7 @@ struct pf2_ctx {
     pf2::ReduceScratch red;
     double* scalars = nullptr;        // device scratch for small results (64 doubles)
     double* h_scalars = nullptr;      // pinned mirror
+    double* elem_scratch = nullptr;   // per-element legacy call: coordinates in, Ke out
     void* flush_buf = nullptr;        // L2 flush scratch
     size_t flush_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -67,6 +67,7 @@ int pf2_ctx_destroy(pf2_ctx* c) {
     cudaStreamSynchronize(c->stream);
     cudaFree(c->red.partials); cudaFree(c->red.ticket); cudaFree(c->scalars); cudaFreeHost(c->h_scalars);
     if (c->flush_buf) cudaFree(c->flush_buf);
+    if (c->elem_scratch) cudaFree(c->elem_scratch);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;

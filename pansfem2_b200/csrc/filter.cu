@@ -275,6 +275,29 @@ int pf2_oc_is_convergence(pf2_oc* oc, double f, int* converged) {
     *converged = fabs(f - oc->previousvalue) / (f + oc->previousvalue) < oc->epsvalue;   // OC.h:68-73
     return PF2_OK;
 }
+int pf2_oc_candidate_host(pf2_oc* oc, const double* x_host, const double* dfdx_host, const double* dgdx_host, double lambda, double* xnew_host) {
+    pf2_ctx* c = oc->ctx;
+    const size_t n = (size_t)oc->n, nb = sizeof(double) * n;
+    double* buf = nullptr;
+    PF2_TRY(dev_alloc(&buf, 3 * n));
+    PF2_CUDA(cudaMemcpyAsync(buf, x_host, nb, cudaMemcpyHostToDevice, c->stream));
+    PF2_CUDA(cudaMemcpyAsync(buf + n, dfdx_host, nb, cudaMemcpyHostToDevice, c->stream));
+    PF2_CUDA(cudaMemcpyAsync(buf + 2 * n, dgdx_host, nb, cudaMemcpyHostToDevice, c->stream));
+    // a bisection state whose midpoint is exactly `lambda`
+    OcState stt;
+    memset(&stt, 0, sizeof stt);
+    stt.l0 = lambda; stt.l1 = lambda;
+    PF2_CUDA(cudaMemcpyAsync(oc->st, &stt, sizeof(OcState), cudaMemcpyHostToDevice, c->stream));
+    oc_candidate_kernel<<<c->grid_for(oc->n), kThreads, 0, c->stream>>>(oc->n, buf, buf + n, buf + 2 * n, oc->iota, oc->move, oc->st, oc->xnew);
+    PF2_LAUNCH_CHECK();
+    c->launches++;
+    PF2_CUDA(cudaMemcpyAsync(xnew_host, oc->xnew, nb, cudaMemcpyDeviceToHost, c->stream));
+    PF2_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(buf);
+    return PF2_OK;
+}
+int pf2_oc_commit(pf2_oc* oc, double f) { oc->previousvalue = f; oc->k++; return PF2_OK; }
+
 int pf2_oc_update(pf2_oc* oc, pf2_filter* filter, double weightlimit, double scale1, double* x_dev, double f,
                   const double* dfdx_dev, const double* dgdx_dev, int* steps_out, double* lambda_out) {
     return oc_update(oc, filter, weightlimit, scale1, x_dev, f, dfdx_dev, dgdx_dev, steps_out, lambda_out);

@@ -270,14 +270,15 @@ int ilu0_factor(pf2_csr* A) {
     return PF2_OK;
 }
 
-// v = (LU)^-1 v in place
-int ilu0_apply(pf2_csr* A, double* v, const CgState* st) {
+// v = (LU)^-1 v in place; `factors` defaults to A's cached ILU(0)
+int ilu0_apply(pf2_csr* A, double* v, const CgState* st, const double* factors = nullptr) {
     pf2_ctx* c = A->ctx;
+    const double* q = factors ? factors : A->ilu;
     const int L = (int)A->h_level_ptr.size() - 1, Lu = (int)A->h_level_ptr_u.size() - 1;
     for (int l = 1; l < L; l++) {      // level 0 rows have no strictly-lower entries
         const int cnt = A->h_level_ptr[l + 1] - A->h_level_ptr[l];
         ilu0_sweep_level_kernel<true><<<(cnt + 127) / 128, 128, 0, c->stream>>>(cnt, A->level_rows + A->h_level_ptr[l], A->indptr,
-                                                                                A->indices, A->diagpos, A->ilu, v, st);
+                                                                                A->indices, A->diagpos, q, v, st);
         c->launches++;
     }
     for (int l = 0; l < Lu; l++) {
@@ -464,6 +465,18 @@ int pf2_ilu0_download(pf2_csr* A, double* data_host) {
     PF2_CHECK(A->ilu_valid, "call pf2_ilu0_factor first");
     PF2_CUDA(cudaMemcpyAsync(data_host, A->ilu, sizeof(double) * (size_t)A->nnz, cudaMemcpyDeviceToHost, A->ctx->stream));
     PF2_CUDA(cudaStreamSynchronize(A->ctx->stream));
+    return PF2_OK;
+}
+
+int pf2_preilu0_host(pf2_csr* M, const double* b_host, double* x_host) {
+    pf2_ctx* c = M->ctx;
+    PF2_TRY(build_levels(M));
+    const size_t n = (size_t)M->rows;
+    if (!M->xw) { PF2_TRY(dev_alloc(&M->xw, n)); PF2_TRY(dev_alloc(&M->bw, n)); }
+    PF2_CUDA(cudaMemcpyAsync(M->xw, b_host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    PF2_TRY(ilu0_apply(M, M->xw, nullptr, M->data));
+    PF2_CUDA(cudaMemcpyAsync(x_host, M->xw, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    PF2_CUDA(cudaStreamSynchronize(c->stream));
     return PF2_OK;
 }
 

@@ -1,0 +1,131 @@
+//  pansfem2_b200/src/B200/Batched.h
+//  The batched, device-resident entry points of the hot path, carrying the reference's template selection as tags.
+//  A driver that used to loop `for element: Eq<T,SF,IC>(Ke,...); Assembling(K,F,u,Ke,...)` calls AssembleBatched<Eq<SF,IC>> once;
+//  a driver that used to run the whole design iteration on the host (sample_optimize_density_oc.cpp:83-208) steps a DesignLoop.
+#pragma once
+#include <vector>
+#include <utility>
+#include <memory>
+#include "ElementSelect.h"
+#include "../LinearAlgebra/Models/CSR.h"
+
+namespace PANSFEM2 { namespace B200 {
+    //  equation tags == the reference's element routines with their template arguments
+    template<template<class>class SF, template<class>class IC>
+    struct PlaneStrainStiffnessTag { static_assert(IsQ4Gauss4<SF, IC>::value, "Q4 + Gauss4Square"); static const int eq = PF2_EQ_PLANESTRAIN; static const int ndof = 2; };
+    template<template<class>class SF, template<class>class IC>
+    struct SolidLinearIsotropicElasticTag { static_assert(IsH8Gauss8<SF, IC>::value, "Hex8 + Gauss8Cubic"); static const int eq = PF2_EQ_SOLID; static const int ndof = 3; };
+    template<template<class>class SF, template<class>class IC>
+    struct HeatTransferTag { static_assert(IsQ4Gauss4<SF, IC>::value, "Q4 + Gauss4Square"); static const int eq = PF2_EQ_HEAT; static const int ndof = 1; };
+
+    typedef std::vector<std::pair<std::pair<int, int>, double> > BcList;
+    inline void SplitBc(const BcList& _bc, std::vector<int>& _node, std::vector<int>& _dof, std::vector<double>& _val) {
+        for (const auto& b : _bc) { _node.push_back(b.first.first); _dof.push_back(b.first.second); _val.push_back(b.second); }
+    }
+
+    //  mesh + Dirichlet numbering + symbolic CSR pattern on the device: built once, reused every design iteration
+    class Model {
+public:
+        Model(std::vector<Vector<double> >& _x, const std::vector<std::vector<int> >& _elements, int _ndof, const BcList& _ufixed)
+            : mesh(nullptr), dofmap(nullptr), pattern(nullptr), nnode((int)_x.size()), nelem((int)_elements.size()), ndof(_ndof), KDEGREE(0) {
+            const int dim = _x[0].SIZE(), npe = (int)_elements[0].size();
+            std::vector<double> coords((size_t)nnode*dim);
+            for (int i = 0; i < nnode; i++) for (int d = 0; d < dim; d++) coords[(size_t)i*dim + d] = _x[i](d);
+            std::vector<int> conn((size_t)nelem*npe);
+            for (int e = 0; e < nelem; e++) for (int a = 0; a < npe; a++) conn[(size_t)e*npe + a] = _elements[e][a];
+            Check(pf2_mesh_create(Device::Context(), dim, nnode, coords.data(), npe, nelem, conn.data(), &mesh), "pf2_mesh_create");
+            std::vector<int> fn, fd; std::vector<double> fv;
+            SplitBc(_ufixed, fn, fd, fv);
+            Check(pf2_dofmap_create(Device::Context(), nnode, _ndof, (int)fn.size(), fn.data(), fd.data(), fv.data(), &KDEGREE, &dofmap), "pf2_dofmap_create");
+            Check(pf2_csr_pattern(Device::Context(), mesh, dofmap, &pattern), "pf2_csr_pattern");
+        }
+        ~Model() { pf2_csr_destroy(pattern); pf2_dofmap_destroy(dofmap); pf2_mesh_destroy(mesh); }
+        Model(const Model&) = delete;
+        Model& operator=(const Model&) = delete;
+
+        //  nodetoglobal exactly as SetDirichlet + Renumbering produce it
+        std::vector<std::vector<int> > NodeToGlobal() const {
+            std::vector<int> flat((size_t)nnode*ndof);
+            Check(pf2_dofmap_get(dofmap, flat.data()), "pf2_dofmap_get");
+            std::vector<std::vector<int> > n2g(nnode, std::vector<int>(ndof));
+            for (int i = 0; i < nnode; i++) for (int d = 0; d < ndof; d++) n2g[i][d] = flat[(size_t)i*ndof + d];
+            return n2g;
+        }
+        pf2_mesh* mesh;
+        pf2_dofmap* dofmap;
+        pf2_csr* pattern;
+        const int nnode, nelem, ndof;
+        int KDEGREE;
+    };
+
+    //  element loop + Assembling(K,F,u,Ke,...) + Assembling(F,q,...) of the drivers in one call; returns K's device handle
+    //  (owned by the model) and fills F.  _modulus[e] is the per-element E (or conductivity); _V, _t as the element routine takes.
+    template<class EQTAG>
+    inline pf2_csr* AssembleBatched(Model& _model, const std::vector<double>& _modulus, double _V, double _t, const BcList& _qfixed, std::vector<double>& _F) {
+        Buffer E;
+        E.Upload(_modulus);
+        std::vector<int> ln, ld; std::vector<double> lv;
+        SplitBc(_qfixed, ln, ld, lv);
+        const double params[5] = { 0.0, 0.0, _V, 1.0, _t };
+        Check(pf2_assemble(_model.pattern, _model.mesh, _model.dofmap, EQTAG::eq, E.Get(), nullptr, params, (int)ln.size(), ln.data(), ld.data(), lv.data()), "pf2_assemble");
+        _F.resize(_model.KDEGREE);
+        Check(pf2_csr_download(_model.pattern, nullptr, nullptr, nullptr, _F.data()), "pf2_csr_download");
+        return _model.pattern;
+    }
+
+    //  solve K u = F on the device with K still resident; kind = PF2_SOLVER_*
+    inline std::vector<double> SolveResident(pf2_csr* _K, int _solver, const std::vector<double>& _F, int _itrmax, double _eps, int* _iters = nullptr) {
+        std::vector<double> x(_F.size());
+        double relres = 0.0;
+        int iters = 0;
+        const int rc = pf2_solve_host(_K, _solver, _F.data(), x.data(), _itrmax, _eps, &iters, &relres);
+        Check(rc, "pf2_solve_host");
+        if (rc == PF2_E_NOCONV) std::cout << "\nConvergence:faild" << std::endl;
+        if (_iters) *_iters = iters;
+        return x;
+    }
+
+    //  the SIMP design loop of sample/optimize/sample_optimize_density_{oc,mma}.cpp with every field resident on the device
+    struct SimpParameters {
+        double E0 = 0.0001, E1 = 210000.0, Poisson = 0.3, p = 3.0, weightlimit = 0.5, scale0 = 1.0e5, scale1 = 1.0, thickness = 1.0;
+        double beta0 = 0.5; int beta_period = 40; int cg_itrmax = 100000; double cg_eps = 1.0e-10;
+    };
+    struct IterationReport { double f, g; bool converged; int cg_iterations; double cg_relres; int optimizer_steps; double beta; int k; };
+
+    template<class EQTAG>
+    class DesignLoop {
+public:
+        //  _filter: a mirrored DensityFilter<double> / HeavisideFilter<double>; _optimizer: PF2_OPT_OC with {iota,lmin,lmax,leps,move}
+        //  or PF2_OPT_MMA with {raa0,albefa,move,asyinit,asydecr,asyincr,epsvalue,a0,a,c,d,xmin,xmax}
+        template<class FILTER>
+        DesignLoop(Model& _model, const FILTER& _filter, int _optimizer, const std::vector<double>& _optp, const SimpParameters& _prm, const BcList& _qfixed, const std::vector<double>& _s0)
+            : model(_model), handle(nullptr) {
+            std::vector<int> ln, ld; std::vector<double> lv;
+            SplitBc(_qfixed, ln, ld, lv);
+            const double params[12] = { _prm.E0, _prm.E1, _prm.Poisson, _prm.p, _prm.weightlimit, _prm.scale0, _prm.scale1, _prm.thickness,
+                                        _prm.beta0, (double)_prm.beta_period, (double)_prm.cg_itrmax, _prm.cg_eps };
+            Check(pf2_simp_create(Device::Context(), model.mesh, model.dofmap, model.pattern, _filter.Device(), EQTAG::eq, _optimizer, _optp.data(), params,
+                                  (int)ln.size(), ln.data(), ld.data(), lv.data(), &handle), "pf2_simp_create");
+            Check(pf2_simp_set_design(handle, _s0.data()), "pf2_simp_set_design");
+        }
+        ~DesignLoop() { pf2_simp_destroy(handle); }
+        DesignLoop(const DesignLoop&) = delete;
+
+        IterationReport Iterate(bool _checkconvergence = true) {
+            double st[8];
+            Check(pf2_simp_iterate(handle, _checkconvergence ? 1 : 0, st), "pf2_simp_iterate");
+            return IterationReport{ st[0], st[1], st[2] != 0.0, (int)st[3], st[4], (int)st[5], st[6], (int)st[7] };
+        }
+        //  fields of the last iteration in the reference's containers (for the VTK dump)
+        void Get(std::vector<double>& _s, std::vector<double>& _rho, std::vector<Vector<double> >& _u, std::vector<Vector<double> >& _r) {
+            _s.resize(model.nelem); _rho.resize(model.nelem);
+            std::vector<double> u((size_t)model.nnode*model.ndof), r((size_t)model.nnode*model.ndof);
+            Check(pf2_simp_get(handle, _s.data(), _rho.data(), u.data(), r.data()), "pf2_simp_get");
+            _u.assign(model.nnode, Vector<double>(model.ndof)); _r.assign(model.nnode, Vector<double>(model.ndof));
+            for (int i = 0; i < model.nnode; i++) for (int d = 0; d < model.ndof; d++) { _u[i](d) = u[(size_t)i*model.ndof + d]; _r[i](d) = r[(size_t)i*model.ndof + d]; }
+        }
+private:
+        Model& model;
+        pf2_simp* handle;
+    };
+} }

@@ -1,0 +1,99 @@
+"""The C++ side of the drop-in boundary on the GPU.
+
+  * sample_optimize_density_batched : our driver on the batched, device-resident API (pansfem2_b200/src/B200/Batched.h)
+  * dropin_density_oc / dropin_solid_linear : the reference's UNMODIFIED drivers (sample/optimize/sample_optimize_density_oc.cpp,
+    sample/solid/sample_linear.cpp) compiled against the header mirror pansfem2_b200/src instead of the reference's src/
+    (built by pansfem2_b200/build_cpp.py where /root/reference exists; the binaries travel to the GPU box).
+Outputs are the reference's own VTK files, compared with the committed goldens at their 6 printed digits.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "pansfem2_b200", "bin")
+
+
+def parse_vtk(path):
+    lines = open(path).read().split("\n")
+    out, i = {}, 0
+    while i < len(lines):
+        ln = lines[i]
+        if ln.startswith("VECTORS") or ln.startswith("SCALARS"):
+            name = ln.split()[1]
+            i += 1 if ln.startswith("VECTORS") else 2
+            rows = []
+            while i < len(lines) and lines[i].strip() and not lines[i][0].isalpha():
+                rows.append([float(v) for v in lines[i].split()])
+                i += 1
+            out[name] = np.array(rows).squeeze()
+            continue
+        i += 1
+    return out
+
+
+def need(name):
+    exe = os.path.join(BIN, name)
+    if not os.path.exists(exe):
+        pytest.skip(f"{exe} not built (python -m pansfem2_b200.build_cpp)")
+    return exe
+
+
+@pytest.mark.parametrize("opt,tag,iters", [("oc", "oc", 66), ("mma", "mma", 56)])
+def test_batched_driver_reproduces_golden_vtk(tmp_path, golden_dir, opt, tag, iters):
+    exe = need("sample_optimize_density_batched")
+    out = tmp_path / "result.vtk"
+    r = subprocess.run([exe, opt, "60", "40", str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Optimized" in r.stdout and f"k = {iters - 1}\t" in r.stdout and f"k = {iters}\t" not in r.stdout
+    got, g = parse_vtk(out), np.load(os.path.join(golden_dir, f"density_{tag}.npz"))
+    assert np.abs(got["s"] - g["rho"]).max() < 2e-6
+    np.testing.assert_allclose(got["u"][:, :2], g["u"], rtol=1e-5, atol=1e-11)
+    np.testing.assert_allclose(got["r"][:, :2], g["r"], rtol=1e-5, atol=1e-7)
+
+
+def test_unmodified_reference_oc_driver_on_the_header_mirror(tmp_path, golden_dir):
+    exe = need("dropin_density_oc")
+    (tmp_path / "sample" / "optimize").mkdir(parents=True)
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Optimized" in r.stdout
+    files = sorted((tmp_path / "sample" / "optimize").glob("result*.vtk"), key=lambda p: int(p.stem[6:]))
+    assert len(files) == 66                       # k = 0..65, as the reference run
+    got, g = parse_vtk(files[-1]), np.load(os.path.join(golden_dir, "density_oc.npz"))
+    assert np.abs(got["s"] - g["rho"]).max() < 2e-6
+    np.testing.assert_allclose(got["u"][:, :2], g["u"], rtol=1e-5, atol=1e-11)
+    np.testing.assert_allclose(got["r"][:, :2], g["r"], rtol=1e-5, atol=1e-7)
+
+
+def test_unmodified_reference_solid_driver_on_the_header_mirror(tmp_path, golden_dir):
+    exe = need("dropin_solid_linear")
+    g = np.load(os.path.join(golden_dir, "solid_linear.npz"))
+    d = tmp_path / "sample" / "solid"
+    d.mkdir(parents=True)
+    with open(d / "Node.csv", "w") as f:
+        f.write("ID,x0,x1,x2\n")
+        for i, c in enumerate(g["coords"]):
+            f.write(f"{i},{c[0]:.17g},{c[1]:.17g},{c[2]:.17g}\n")
+    with open(d / "Element.csv", "w") as f:
+        f.write("ID,n0,n1,n3,n4,n5,n6,n7,n8\n")
+        for i, e in enumerate(g["conn"]):
+            f.write(f"{i}," + ",".join(str(int(v)) for v in e) + "\n")
+    for name, (nn, dd, vv), hdr in (("Dirichlet.csv", (g["fix_node"], g["fix_dof"], g["fix_val"]), "idn,u,v,w"),
+                                    ("Neumann.csv", (g["load_node"], g["load_dof"], g["load_val"]), "idn,fx,fy,fz")):
+        rows = {}
+        for n, dof, v in zip(nn, dd, vv):
+            rows.setdefault(int(n), ["free"] * 3)[int(dof)] = f"{v:.17g}"
+        with open(d / name, "w") as f:
+            f.write(hdr + "\n")
+            for n in sorted(rows):
+                f.write(f"{n}," + ",".join(rows[n]) + "\n")
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = parse_vtk(d / "result_linear.vtk")
+    assert abs(np.abs(got["u"]).max() - 1.48963) < 1e-5
+    np.testing.assert_allclose(got["u"], g["u"], rtol=6e-6, atol=1e-9)
