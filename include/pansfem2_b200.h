@@ -212,6 +212,20 @@ int pf2_simp_get(pf2_simp* S, double* s_host, double* rho_host, double* u_nodal_
 int pf2_simp_phase_ms(pf2_simp* S, double ms[6]);
 int pf2_simp_cg_stats(pf2_simp* S, double* spmv_ms_avg, long long* spmv_calls);
 
+/* ---- multi-GPU: row-block (x-slab) partition over the GPUs of one box (no counterpart in the reference, whose only
+ *      parallelism is the OpenMP loop of CSR.h:114) ----------------------------------------------------------------- */
+typedef struct pf2_dist pf2_dist;
+/* rank 0 creates the 128-byte NCCL id and hands it to the other ranks through any channel (torch.distributed, MPI, a file) */
+int pf2_dist_unique_id(char out[128]);
+int pf2_dist_create(pf2_ctx* ctx, int rank, int nranks, const char id[128], pf2_dist** out);
+int pf2_dist_destroy(pf2_dist* d);
+int pf2_dist_allreduce_sum(pf2_dist* d, double* dev, int count);
+/* halo = {sendL_off, recvL_off, cntL, sendR_off, recvR_off, cntR}: contiguous ranges exchanged with rank-1 / rank+1 */
+int pf2_dist_halo(pf2_dist* d, double* vec_dev, const int halo[6]);
+/* Mark a LOCAL matrix (local mesh = owned element planes + one ghost plane per side) as one row block of a partitioned
+ * system: rows [own_lo, own_hi) are owned; pf2_solve then runs the distributed PCG (halo exchange of p + allreduces). */
+int pf2_csr_set_partition(pf2_csr* A, pf2_dist* d, int own_lo, int own_hi, const int halo[6]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -437,6 +437,40 @@ class Simp:
             o.close()
 
 
+class Dist:
+    """Row-block partition over the GPUs of one box.  `group` is an initialised torch.distributed process group (any
+    backend): it is only used to hand rank 0's NCCL id to the other ranks."""
+
+    def __init__(self, ctx, rank, world):
+        import torch
+        import torch.distributed as tdist
+        self.ctx, self.rank, self.world = ctx, rank, world
+        idbuf = (C.c_char * 128)()
+        if rank == 0:
+            _ck(lib().pf2_dist_unique_id(idbuf))
+        obj = [bytes(idbuf.raw) if rank == 0 else None]
+        tdist.broadcast_object_list(obj, src=0)
+        idbuf.raw = obj[0]
+        self.h = C.c_void_p()
+        _ck(lib().pf2_dist_create(ctx.h, rank, world, idbuf, C.byref(self.h)))
+
+    def allreduce(self, dev, count):
+        _ck(lib().pf2_dist_allreduce_sum(self.h, dev.ptr, int(count)))
+
+    def halo(self, dev, halo6):
+        h = (C.c_int * 6)(*[int(v) for v in halo6])
+        _ck(lib().pf2_dist_halo(self.h, dev.ptr, h))
+
+    def set_partition(self, A, own_rows, row_halo):
+        h = (C.c_int * 6)(*[int(v) for v in row_halo])
+        _ck(lib().pf2_csr_set_partition(A.h, self.h, int(own_rows[0]), int(own_rows[1]), h))
+
+    def close(self):
+        if self.h:
+            lib().pf2_dist_destroy(self.h)
+            self.h = C.c_void_p()
+
+
 def pinned_empty(count, dtype=np.float64):
     """numpy view over cudaHostAlloc'ed memory (for the end-to-end path)."""
     dtype = np.dtype(dtype)

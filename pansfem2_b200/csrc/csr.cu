@@ -28,7 +28,7 @@ template <int G, bool DOT>
 __global__ void __launch_bounds__(kThreads)
 spmv_stream_kernel(int rows, const long long* __restrict__ indptr, const int* __restrict__ indices,
                    const double* __restrict__ data, const double* __restrict__ x, double* __restrict__ y,
-                   const CgState* __restrict__ st, double* dot_out, double* partials, unsigned int* ticket) {
+                   const CgState* __restrict__ st, double* dot_out, double* partials, unsigned int* ticket, int dot_lo, int dot_hi) {
     if (DOT && st != nullptr && st->done) return;
     __shared__ double prod[kStreamCap];
     __shared__ long long s_range[2];
@@ -62,7 +62,7 @@ spmv_stream_kernel(int rows, const long long* __restrict__ indptr, const int* __
         for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, G);
         if (row < r1 && g == 0) {
             y[row] = acc;
-            if (DOT) dot += acc * x[row];
+            if (DOT && row >= dot_lo && row < dot_hi) dot += acc * x[row];
         }
         __syncthreads();
     }
@@ -77,7 +77,7 @@ template <int TPR, bool DOT>
 __global__ void __launch_bounds__(kThreads)
 spmv_vector_kernel(int rows, const long long* __restrict__ indptr, const int* __restrict__ indices,
                    const double* __restrict__ data, const double* __restrict__ x, double* __restrict__ y,
-                   const CgState* __restrict__ st, double* dot_out, double* partials, unsigned int* ticket) {
+                   const CgState* __restrict__ st, double* dot_out, double* partials, unsigned int* ticket, int dot_lo, int dot_hi) {
     if (DOT && st != nullptr && st->done) return;
     constexpr int RPB = kThreads / TPR;
     const int lr = threadIdx.x / TPR, lane = threadIdx.x % TPR;
@@ -96,7 +96,7 @@ spmv_vector_kernel(int rows, const long long* __restrict__ indptr, const int* __
         for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, TPR);
         if (valid && lane == 0) {
             y[row] = acc;
-            if (DOT) dot += acc * x[row];
+            if (DOT && row >= dot_lo && row < dot_hi) dot += acc * x[row];
         }
     }
     if (DOT) {
@@ -175,7 +175,7 @@ static int launch_tma(pf2_csr* A, const double* x, double* y, const CgState* st,
     const int ntiles = (A->rows + rpb - 1) / rpb;
     const int grid = std::max(1, std::min(ntiles, c->sm_count * per_sm));
     spmv_tma_kernel<G, DOT><<<grid, kTmaThreads, smem, c->stream>>>(A->rows, A->indptr, A->indices, A->data, x, y, st, dot_out,
-                                                                   c->red.partials, c->red.ticket, cap, stages);
+                                                                   c->red.partials, c->red.ticket, cap, stages, A->own_lo, A->own_hi);
     return PF2_OK;
 }
 
@@ -223,14 +223,14 @@ static int launch_sell(pf2_csr* A, const double* x, double* y, const CgState* st
     const int nb = (nslices + (kThreads / 32) - 1) / (kThreads / 32);
     const int grid = std::max(1, std::min(nb, c->wave_grid((const void*)spmv_sell_kernel<DOT>, kThreads)));
     spmv_sell_kernel<DOT><<<grid, kThreads, 0, c->stream>>>(A->rows, A->sell_ptr, A->sell_idx, A->sell_val, x, y, st, dot_out,
-                                                          c->red.partials, c->red.ticket);
+                                                          c->red.partials, c->red.ticket, A->own_lo, A->own_hi);
     return PF2_OK;
 }
 
 template <bool DOT>
 static int launch_spmv(pf2_csr* A, int variant, const double* x, double* y, const CgState* st, double* dot_out) {
     pf2_ctx* c = A->ctx;
-#define ARGS A->rows, A->indptr, A->indices, A->data, x, y, st, dot_out, c->red.partials, c->red.ticket
+#define ARGS A->rows, A->indptr, A->indices, A->data, x, y, st, dot_out, c->red.partials, c->red.ticket, A->own_lo, A->own_hi
 #define VEC(T)                                                                                               \
     {                                                                                                        \
         long long nb = ((long long)A->rows + (kThreads / T) - 1) / (kThreads / T);                              \
@@ -306,6 +306,7 @@ int pf2_csr_upload(pf2_ctx* ctx, int rows, const int* indptr_host, const int* in
     pf2_csr* A = new pf2_csr();
     A->ctx = ctx;
     A->rows = rows;
+    A->own_lo = 0; A->own_hi = rows;
     A->nnz = indptr_host[rows];
     // spare entries: the TMA SpMV reads 16-byte aligned windows that may run a few entries past the end
     PF2_TRY(dev_alloc(&A->indptr, (size_t)rows + 1 + kCsrPad));

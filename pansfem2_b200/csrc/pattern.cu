@@ -281,6 +281,7 @@ int pf2_csr_pattern(pf2_ctx* ctx, pf2_mesh* mesh, pf2_dofmap* map, pf2_csr** out
     pf2_csr* A = new pf2_csr();
     A->ctx = ctx;
     A->rows = map->kdegree;
+    A->own_lo = 0; A->own_hi = A->rows;
     PF2_TRY(dev_alloc(&A->indptr, (size_t)A->rows + 1 + kCsrPad));
     PF2_CUDA(cudaMemsetAsync(A->indptr, 0, sizeof(long long) * ((size_t)A->rows + 1 + kCsrPad), s));
     rowlen_kernel<<<gnode, kThreads, 0, s>>>(nnode, ndof, map->n2g, rowlen, A->indptr);

@@ -352,9 +352,13 @@ static void harvest_profile(pf2_csr* A, int slot) {
     A->prof_samples++;
 }
 
+int ensure_workspace_pub(pf2_csr* A) { return ensure_workspace(A); }
+int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out);
+
 int solve(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out) {
     pf2_ctx* c = A->ctx;
     PF2_CHECK(solver >= 0 && solver <= 2, "unknown solver");
+    if (A->dist) { PF2_CUDA(cudaSetDevice(c->device)); return solve_dist(A, solver, b, x, itrmax, eps, iters_out, relres_out); }
     PF2_CHECK(itrmax >= 0, "itrmax");
     PF2_CUDA(cudaSetDevice(c->device));
     PF2_TRY(ensure_workspace(A));

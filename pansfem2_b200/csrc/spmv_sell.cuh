@@ -69,7 +69,7 @@ template <bool DOT>
 __global__ void __launch_bounds__(kThreads)
 spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* __restrict__ sell_idx, const double* __restrict__ sell_val,
                  const double* __restrict__ x, double* __restrict__ y, const CgState* __restrict__ st, double* dot_out,
-                 double* partials, unsigned int* ticket) {
+                 double* partials, unsigned int* ticket, int dot_lo, int dot_hi) {
     if (DOT && st != nullptr && st->done) return;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -95,7 +95,7 @@ spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* _
         const int r = s * kSellC + lane;
         if (r < rows) {
             y[r] = acc;
-            if (DOT) dot += acc * x[r];
+            if (DOT && r >= dot_lo && r < dot_hi) dot += acc * x[r];
         }
     }
     if (DOT) {

@@ -74,7 +74,7 @@ template <int G, bool DOT>
 __global__ void __launch_bounds__(kTmaThreads, 4)
 spmv_tma_kernel(int rows, const long long* __restrict__ indptr, const int* __restrict__ indices, const double* __restrict__ data,
                 const double* __restrict__ x, double* __restrict__ y, const CgState* __restrict__ st, double* dot_out,
-                double* partials, unsigned int* ticket, int cap, int stages) {
+                double* partials, unsigned int* ticket, int cap, int stages, int dot_lo, int dot_hi) {
     if (DOT && st != nullptr && st->done) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const size_t stage_bytes = tma_stage_bytes(cap);
@@ -143,7 +143,7 @@ spmv_tma_kernel(int rows, const long long* __restrict__ indptr, const int* __res
         for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, G);
         if (lr < nr && g == 0) {
             y[r0 + lr] = acc;
-            if (DOT) dot += acc * x[r0 + lr];
+            if (DOT && r0 + lr >= dot_lo && r0 + lr < dot_hi) dot += acc * x[r0 + lr];
         }
         // the stage was written through the generic proxy (products); order that before the next bulk copy into it
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -26,6 +26,7 @@ struct CgState {
     double bb;       // b.b
     double beta;
     double zr_new;   // scratch for the ILU path
+    double red[4];   // partial sums awaiting an allreduce (multi-GPU)
     int iter;        // iterations completed
     int done;        // 1 = converged (x frozen), kernels early-exit
     int maxit;
@@ -34,9 +35,16 @@ struct CgState {
 };
 }  // namespace pf2
 
+struct pf2_dist;
+
 struct pf2_csr {
     pf2_ctx* ctx = nullptr;
     int rows = 0;
+    // row-block partition (multi-GPU): rows [own_lo, own_hi) are owned, the rest are ghost rows whose x entries arrive
+    // by halo exchange; single GPU: [0, rows)
+    int own_lo = 0, own_hi = 0;
+    pf2_dist* dist = nullptr;
+    int halo[6] = { 0, 0, 0, 0, 0, 0 };   // sendL_off, recvL_off, cntL, sendR_off, recvR_off, cntR (row offsets)
     long long nnz = 0;
     long long* indptr = nullptr;   // rows+1 (int64: config 5 has nnz > 2^31)
     int* indices = nullptr;        // nnz, sorted within a row
