@@ -465,6 +465,12 @@ class Dist:
         h = (C.c_int * 6)(*[int(v) for v in row_halo])
         _ck(lib().pf2_csr_set_partition(A.h, self.h, int(own_rows[0]), int(own_rows[1]), h))
 
+    def set_simp_partition(self, simp, slab, n_global_elems):
+        """simp: capi.Simp built on slab.local; also partitions its matrix."""
+        self.set_partition(simp.A, slab.own_rows, slab.row_halo)
+        h = (C.c_int * 6)(*[int(v) for v in slab.elem_halo])
+        _ck(lib().pf2_simp_set_partition(simp.h, self.h, int(slab.own_elems[0]), int(slab.own_elems[1]), h, C.c_longlong(int(n_global_elems))))
+
     def close(self):
         if self.h:
             lib().pf2_dist_destroy(self.h)

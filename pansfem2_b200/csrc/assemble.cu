@@ -105,7 +105,7 @@ template <int EQ>
 __global__ void __launch_bounds__(kThreads)
 sens_kernel(int nelem, const double* __restrict__ coords, const int* __restrict__ conn, const double* __restrict__ u,
             const double* __restrict__ rho, double E0, double E1, double V, double p, double t, double scale0,
-            double* __restrict__ dfdrho, double* r_nodal, double* f_out, double* partials, unsigned int* ticket) {
+            double* __restrict__ dfdrho, double* r_nodal, double* f_out, double* partials, unsigned int* ticket, int sum_lo, int sum_hi) {
     constexpr int DIM = ElemTraits<EQ>::DIM, NPE = ElemTraits<EQ>::NPE, NDOF = ElemTraits<EQ>::NDOF;
     const Iso c(V);
     double fsum = 0.0;
@@ -183,7 +183,7 @@ sens_kernel(int nelem, const double* __restrict__ coords, const int* __restrict_
         }
         const double rh = rho[e];
         const double E = simp_modulus(rh, E0, E1, p);
-        fsum += E * w;
+        if (e >= sum_lo && e < sum_hi) fsum += E * w;
         if (dfdrho) dfdrho[e] = -scale0 * p * (-E0 + E1) * pow(rh, p - 1.0) * w;
         if (r_nodal) {
 #pragma unroll
@@ -264,7 +264,7 @@ int compliance_sens_device(pf2_mesh* mesh, int eq, const double* u_nodal, const 
     if (r_nodal) PF2_CUDA(cudaMemsetAsync(r_nodal, 0, sizeof(double) * (size_t)mesh->nnode * ndof, s));
     const int grid = c->grid_for(mesh->nelem);
 #define LAUNCH(EQ) sens_kernel<EQ><<<grid, kThreads, 0, s>>>(mesh->nelem, mesh->coords, mesh->conn, u_nodal, rho, params[0], params[1], \
-                                                           params[2], params[3], params[4], params[5], dfdrho, r_nodal, f_dev, c->red.partials, c->red.ticket)
+                                                           params[2], params[3], params[4], params[5], dfdrho, r_nodal, f_dev, c->red.partials, c->red.ticket, mesh->own_elem_lo, mesh->own_elem_hi)
     if (eq == PF2_EQ_PLANESTRAIN) LAUNCH(PF2_EQ_PLANESTRAIN);
     else if (eq == PF2_EQ_SOLID) LAUNCH(PF2_EQ_SOLID);
     else LAUNCH(PF2_EQ_HEAT);

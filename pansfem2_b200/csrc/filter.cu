@@ -12,16 +12,28 @@
 
 namespace pf2 {
 
+int dist_halo(pf2_dist* d, double* vec, const int halo[6]);
+int dist_allreduce(pf2_dist* d, double* dev, int count);
+
 __device__ __forceinline__ double heaviside(double st, double beta) {
     return 0.5 * (tanh(0.5 * beta) + tanh(beta * (st - 0.5))) / tanh(0.5 * beta);
 }
+
+// OC.h:94-98 then the loop condition OC.h:82
+__device__ __forceinline__ void oc_decide(OcState* oc, double rho_sum) {
+    const double g = oc->volscale * rho_sum - oc->volshift;
+    if (g > 0.0) oc->l0 = oc->lambda; else oc->l1 = oc->lambda;
+    oc->steps = oc->steps + 1;
+    if (!((oc->l1 - oc->l0) / (oc->l1 + oc->l0) > oc->eps)) oc->done = 1;
+}
+__global__ void oc_decide_kernel(OcState* oc) { if (!oc->done) oc_decide(oc, oc->partial); }
 
 // rho = filter(s); optionally the grid-wide sum of rho (volume constraint) with an OC bisection decision.
 template <int KIND, bool SUM>
 __global__ void __launch_bounds__(kThreads)
 filter_apply_kernel(int n, const long long* __restrict__ rowptr, const int* __restrict__ nbr, const double* __restrict__ w,
                     double beta, const double* __restrict__ s, double* __restrict__ rho, double* sum_out, OcState* oc,
-                    double* partials, unsigned int* ticket) {
+                    double* partials, unsigned int* ticket, int sum_lo, int sum_hi) {
     if (oc != nullptr && oc->done) return;
     double acc = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -34,18 +46,15 @@ filter_apply_kernel(int n, const long long* __restrict__ rowptr, const int* __re
         const double st = wssum / wsum;
         const double r = (KIND == PF2_FILTER_HEAVISIDE) ? heaviside(st, beta) : st;
         rho[i] = r;
-        acc += r;
+        if (i >= sum_lo && i < sum_hi) acc += r;
     }
     if (SUM) {
         double v[1] = { acc };
         if (grid_sum_last<1>(v, partials, ticket) && threadIdx.x == 0) {
             if (sum_out) *sum_out = v[0];
             if (oc) {
-                // OC.h:94-98 then the loop condition OC.h:82
-                const double g = oc->volscale * v[0] - oc->volshift;
-                if (g > 0.0) oc->l0 = oc->lambda; else oc->l1 = oc->lambda;
-                oc->steps = oc->steps + 1;
-                if (!((oc->l1 - oc->l0) / (oc->l1 + oc->l0) > oc->eps)) oc->done = 1;
+                if (oc->defer) oc->partial = v[0];
+                else oc_decide(oc, v[0]);
             }
         }
     }
@@ -110,7 +119,7 @@ int filter_apply(pf2_filter* f, const double* s, double* rho, double* sum_out, O
     pf2_ctx* c = f->ctx;
     const int grid = c->grid_for(f->n);
     const bool sum = sum_out != nullptr || oc != nullptr;
-#define FA(K, S) filter_apply_kernel<K, S><<<grid, kThreads, 0, c->stream>>>(f->n, f->rowptr, f->nbr, f->w, f->beta, s, rho, sum_out, oc, c->red.partials, c->red.ticket)
+#define FA(K, S) filter_apply_kernel<K, S><<<grid, kThreads, 0, c->stream>>>(f->n, f->rowptr, f->nbr, f->w, f->beta, s, rho, sum_out, oc, c->red.partials, c->red.ticket, f->sum_lo, f->sum_hi)
     if (f->kind == PF2_FILTER_HEAVISIDE) { if (sum) FA(PF2_FILTER_HEAVISIDE, true); else FA(PF2_FILTER_HEAVISIDE, false); }
     else { if (sum) FA(PF2_FILTER_DENSITY, true); else FA(PF2_FILTER_DENSITY, false); }
 #undef FA
@@ -127,6 +136,7 @@ int filter_sens(pf2_filter* f, const double* s, const double* g1, double* out1, 
         if (!f->dr) PF2_TRY(dev_alloc(&f->dr, (size_t)f->n));
         heaviside_slope_kernel<<<grid, kThreads, 0, c->stream>>>(f->n, f->rowptr, f->nbr, f->w, f->beta, s, f->dr);
         c->launches++;
+        if (f->dist) PF2_TRY(dist_halo(f->dist, f->dr, f->ehalo));      // ghost planes' slopes come from their owners
         filter_sens_kernel<true><<<grid, kThreads, 0, c->stream>>>(f->n, f->rowptr, f->nbr, f->w, f->dr, g1, out1, g2, c2, out2);
     } else {
         filter_sens_kernel<false><<<grid, kThreads, 0, c->stream>>>(f->n, f->rowptr, f->nbr, f->w, nullptr, g1, out1, g2, c2, out2);
@@ -149,8 +159,10 @@ int oc_update(pf2_oc* oc, pf2_filter* filter, double weightlimit, double scale1,
     OcState init;
     init.l0 = oc->lmin; init.l1 = oc->lmax; init.lambda = 0.0; init.eps = oc->leps;
     // g(x) = sum_i scale1*rho_i/(weightlimit*n) - 1.0*scale1   (driver :199-206)
-    init.volscale = scale1 / (weightlimit * n); init.volshift = 1.0 * scale1;
+    init.volscale = scale1 / (weightlimit * (double)(oc->n_global ? oc->n_global : n)); init.volshift = 1.0 * scale1;
     init.steps = 0;
+    init.partial = 0.0; init.pad = 0;
+    init.defer = filter->dist ? 1 : 0;
     init.done = !((init.l1 - init.l0) / (init.l1 + init.l0) > init.eps);
     oc->h_st[0] = init;
     PF2_CUDA(cudaMemcpyAsync(oc->st, &oc->h_st[0], sizeof(OcState), cudaMemcpyHostToDevice, c->stream));
@@ -165,6 +177,11 @@ int oc_update(pf2_oc* oc, pf2_filter* filter, double weightlimit, double scale1,
             oc_candidate_kernel<<<grid, kThreads, 0, c->stream>>>(n, x, dfdx, dgdx, oc->iota, oc->move, oc->st, oc->xnew);
             c->launches++;
             PF2_TRY(filter_apply(filter, oc->xnew, oc->rho, nullptr, oc->st));
+            if (filter->dist) {
+                PF2_TRY(dist_allreduce(filter->dist, &oc->st->partial, 1));
+                oc_decide_kernel<<<1, 1, 0, c->stream>>>(oc->st);
+                c->launches++;
+            }
         }
         PF2_LAUNCH_CHECK();
         enq += chunk;
@@ -203,6 +220,7 @@ int pf2_filter_create(pf2_ctx* ctx, int kind, int n, const long long* rowptr_hos
     PF2_CUDA(cudaSetDevice(ctx->device));
     pf2_filter* f = new pf2_filter();
     f->ctx = ctx; f->kind = kind; f->n = n; f->nnb = rowptr_host[n];
+    f->sum_lo = 0; f->sum_hi = n;
     PF2_TRY(dev_alloc(&f->rowptr, (size_t)n + 1));
     PF2_TRY(dev_alloc(&f->nbr, (size_t)f->nnb));
     PF2_TRY(dev_alloc(&f->w, (size_t)f->nnb));

@@ -168,6 +168,7 @@ int pf2_mesh_create(pf2_ctx* ctx, int dim, int nnode, const double* coords_host,
     PF2_CUDA(cudaSetDevice(ctx->device));
     pf2_mesh* m = new pf2_mesh();
     m->ctx = ctx; m->dim = dim; m->nnode = nnode; m->npe = npe; m->nelem = nelem;
+    m->own_elem_lo = 0; m->own_elem_hi = nelem;
     PF2_TRY(dev_alloc(&m->coords, (size_t)nnode * dim));
     PF2_TRY(dev_alloc(&m->conn, (size_t)nelem * npe));
     PF2_CUDA(cudaMemcpyAsync(m->coords, coords_host, sizeof(double) * (size_t)nnode * dim, cudaMemcpyHostToDevice, ctx->stream));

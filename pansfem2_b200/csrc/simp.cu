@@ -25,6 +25,8 @@ int filter_sens(pf2_filter* f, const double* s, const double* g1, double* out1, 
 int oc_update(pf2_oc* oc, pf2_filter* filter, double weightlimit, double scale1, double* x, double f, const double* dfdx,
               const double* dgdx, int* steps_out, double* lambda_out);
 int mma_update(pf2_mma* mm, double* xk, double f, const double* dfdx, const double* g_host, const double* dgdx, int* newton_out);
+int dist_halo(pf2_dist* d, double* vec, const int halo[6]);
+int dist_allreduce(pf2_dist* d, double* dev, int count);
 }  // namespace pf2
 
 using namespace pf2;
@@ -49,16 +51,24 @@ struct pf2_simp {
     double *s = nullptr, *rho = nullptr, *xsol = nullptr, *u = nullptr, *r_nodal = nullptr, *dfdrho = nullptr, *dfds = nullptr, *dgds = nullptr;
     cudaEvent_t ev[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
     double phase_ms[6] = { 0, 0, 0, 0, 0, 0 };
+    // multi-GPU (row-block partition): this object drives ONE slab; n_global = elements of the whole problem
+    pf2_dist* dist = nullptr;
+    int ehalo[6] = { 0, 0, 0, 0, 0, 0 };
+    long long n_global = 0;
 };
 
 static int simp_iterate(pf2_simp* S, int check_convergence, double stats[8]) {
     pf2_ctx* c = S->ctx;
     cudaStream_t s = c->stream;
+    pf2_dist* d = S->dist;
+    const double nglob = (double)(S->n_global ? S->n_global : S->n);
     PF2_CUDA(cudaSetDevice(c->device));
     PF2_CUDA(cudaEventRecord(S->ev[0], s));
     if (S->beta_period > 0 && S->k % S->beta_period == 0) S->beta *= 2.0;       // driver :85-88
     S->filter->beta = S->beta;
+    if (d) PF2_TRY(dist_halo(d, S->s, S->ehalo));                              // ghost element planes of the design
     PF2_TRY(filter_apply(S->filter, S->s, S->rho, c->scalars + 1, nullptr));
+    if (d) { PF2_TRY(dist_allreduce(d, c->scalars + 1, 1)); PF2_TRY(dist_halo(d, S->rho, S->ehalo)); }
     PF2_CUDA(cudaEventRecord(S->ev[1], s));
     const double ap[5] = { S->E0, S->E1, S->V, S->p, S->thick };
     PF2_TRY(assemble_device(S->A, S->mesh, S->map, S->eq, nullptr, S->rho, ap, S->nload, S->ld_node, S->ld_dof, S->ld_val));
@@ -67,25 +77,31 @@ static int simp_iterate(pf2_simp* S, int check_convergence, double stats[8]) {
     double relres = 0.0;
     int rc = solve(S->A, S->solver, S->A->F, S->xsol, S->itrmax, S->cgeps, &iters, &relres);
     if (rc != PF2_OK && rc != PF2_E_NOCONV) return rc;      // non-convergence: the reference prints and carries on
+    if (d) PF2_TRY(dist_halo(d, S->xsol, S->A->halo));                         // displacements of the ghost node planes
     PF2_TRY(pf2_disassemble(S->map, S->xsol, S->u));
     PF2_CUDA(cudaEventRecord(S->ev[3], s));
     const double sp[6] = { S->E0, S->E1, S->V, S->p, S->thick, S->scale0 };
     PF2_TRY(compliance_sens_device(S->mesh, S->eq, S->u, S->rho, sp, c->scalars, S->dfdrho, nullptr));
+    if (d) { PF2_TRY(dist_allreduce(d, c->scalars, 1)); PF2_TRY(dist_halo(d, S->dfdrho, S->ehalo)); }
     PF2_CUDA(cudaEventRecord(S->ev[4], s));
-    const double dgdrho = S->scale1 / (S->weightlimit * S->n);                  // driver :104
+    const double dgdrho = S->scale1 / (S->weightlimit * nglob);                 // driver :104
     PF2_TRY(filter_sens(S->filter, S->s, S->dfdrho, S->dfds, nullptr, dgdrho, S->dgds));
+    if (d) { PF2_TRY(dist_halo(d, S->dfds, S->ehalo)); PF2_TRY(dist_halo(d, S->dgds, S->ehalo)); }
     PF2_CUDA(cudaEventRecord(S->ev[5], s));
     PF2_CUDA(cudaMemcpyAsync(c->h_scalars, c->scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
     PF2_CUDA(cudaStreamSynchronize(s));
     const double f = c->h_scalars[0];
-    const double g = S->scale1 * c->h_scalars[1] / (S->weightlimit * S->n) - 1.0 * S->scale1;   // driver :99-105
+    const double g = S->scale1 * c->h_scalars[1] / (S->weightlimit * nglob) - 1.0 * S->scale1;   // driver :99-105
     int converged = 0;
     if (S->oc) PF2_TRY(pf2_oc_is_convergence(S->oc, f, &converged));
     else PF2_TRY(pf2_mma_is_convergence(S->mma, f, &converged));
     int opt_steps = 0;
     if (!(check_convergence && converged)) {
         if (S->oc) PF2_TRY(oc_update(S->oc, S->filter, S->weightlimit, S->scale1, S->s, f, S->dfds, S->dgds, &opt_steps, nullptr));
-        else PF2_TRY(mma_update(S->mma, S->s, f, S->dfds, &g, S->dgds, &opt_steps));
+        else {
+            if (d) { set_error("MMA on a partitioned design is not built yet: use OC (config 5)"); return PF2_E_UNSUPPORTED; }
+            PF2_TRY(mma_update(S->mma, S->s, f, S->dfds, &g, S->dgds, &opt_steps));
+        }
     }
     PF2_CUDA(cudaEventRecord(S->ev[6], s));
     PF2_CUDA(cudaEventSynchronize(S->ev[6]));
@@ -159,6 +175,17 @@ int pf2_simp_set_design(pf2_simp* S, const double* s_host) {
     PF2_CUDA(cudaStreamSynchronize(S->ctx->stream));
     return PF2_OK;
 }
+int pf2_simp_set_partition(pf2_simp* S, pf2_dist* d, int own_elem_lo, int own_elem_hi, const int elem_halo[6], long long n_global_elems) {
+    PF2_CHECK(S && d && elem_halo && own_elem_lo >= 0 && own_elem_lo <= own_elem_hi && own_elem_hi <= S->n && n_global_elems >= S->n - 0, "bad partition");
+    PF2_CHECK(S->A->dist == d, "call pf2_csr_set_partition on the matrix first");
+    S->dist = d; S->n_global = n_global_elems;
+    for (int i = 0; i < 6; i++) { S->ehalo[i] = elem_halo[i]; S->filter->ehalo[i] = elem_halo[i]; }
+    S->filter->dist = d; S->filter->sum_lo = own_elem_lo; S->filter->sum_hi = own_elem_hi;
+    S->mesh->own_elem_lo = own_elem_lo; S->mesh->own_elem_hi = own_elem_hi;
+    if (S->oc) S->oc->n_global = n_global_elems;
+    return PF2_OK;
+}
+
 int pf2_simp_set_solver(pf2_simp* S, int solver) {
     PF2_CHECK(solver >= 0 && solver <= 2, "unknown solver");
     S->solver = solver;

@@ -5,6 +5,7 @@
 struct pf2_mesh {
     pf2_ctx* ctx = nullptr;
     int dim = 0, nnode = 0, npe = 0, nelem = 0;
+    int own_elem_lo = 0, own_elem_hi = 0;   // multi-GPU: owned elements (compliance is summed over them only)
     double* coords = nullptr;   // nnode*dim, node-major (AoS as std::vector<Vector<T>>)
     int* conn = nullptr;        // nelem*npe
 };
@@ -94,6 +95,10 @@ struct pf2_filter {
     double* w = nullptr;
     double* dr = nullptr;           // scratch: d rho / d s~ (Heaviside chain rule)
     double *hs = nullptr, *hr = nullptr, *hd = nullptr;   // staging for the _host entry points
+    // multi-GPU: elements [sum_lo, sum_hi) are owned (volume sums run over them only); ghost planes arrive by halo exchange
+    int sum_lo = 0, sum_hi = 0;
+    pf2_dist* dist = nullptr;
+    int ehalo[6] = { 0, 0, 0, 0, 0, 0 };
 };
 
 
@@ -101,7 +106,9 @@ namespace pf2 {
 struct OcState {
     double l0, l1, lambda;
     double eps, volscale, volshift;   // g = volscale * sum(rho) - volshift
+    double partial;                   // multi-GPU: this rank's volume sum awaiting the allreduce
     int steps, done;
+    int defer, pad;                   // defer = 1: the decision is taken by oc_decide_kernel after the allreduce
 };
 
 }  // namespace pf2
@@ -109,6 +116,7 @@ struct OcState {
 struct pf2_oc {
     pf2_ctx* ctx = nullptr;
     int n = 0, k = 0;
+    long long n_global = 0;         // design variables of the whole (partitioned) problem; = n on one GPU
     double iota, lmin, lmax, leps, move;
     double previousvalue = 0.0, epsvalue = 1.0e-5;   // OC.h:49-50
     double* xnew = nullptr;

@@ -1,0 +1,68 @@
+"""torchrun script: the row-partitioned SIMP design loop (OC) on N GPUs vs the single-GPU loop of the same problem.
+    torchrun --nproc-per-node N tools/dist_simp_check.py [2d NX NY | 3d NX NY NZ | heat NX NY] [--iters K] [--big]"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from pansfem2_b200 import capi, partition, problems  # noqa: E402
+
+rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local_rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+argv = sys.argv[1:]
+iters = 4
+if "--iters" in argv:
+    i = argv.index("--iters"); iters = int(argv[i + 1]); argv = argv[:i] + argv[i + 2:]
+args = [a for a in argv if not a.startswith("--")]
+kind = args[0] if args else "3d"
+dims = [int(a) for a in args[1:]]
+check = "--big" not in argv
+if kind == "2d":
+    P = problems.cantilever2d(*(dims or [120, 60]), filter_kind=problems.FILTER_HEAVISIDE)
+elif kind == "heat":
+    P = problems.heat2d(*(dims or [64, 64]))
+else:
+    P = problems.cantilever3d(*(dims or [24, 12, 8]))
+ctx = capi.Context(local_rank)
+D = capi.Dist(ctx, rank, world)
+S = partition.slab(P, rank, world)
+sim = capi.Simp(ctx, S.local)
+D.set_simp_partition(sim, S, P.nelem)
+hist = []
+ctx.sync(); dist.barrier()
+t0 = time.time()
+for k in range(iters):
+    st = sim.iterate(check_convergence=False)
+    st["phase_ms"] = sim.phase_ms()
+    hist.append(st)
+ctx.sync(); dist.barrier()
+wall = time.time() - t0
+out = sim.get()
+res = {"world": world, "problem": P.name, "iters": iters, "wall_s": wall, "f": [h["f"] for h in hist], "cg_iters": [h["cg_iters"] for h in hist],
+       "opt_steps": [h["opt_steps"] for h in hist], "phase_ms_last": hist[-1]["phase_ms"], "it_per_s": iters / wall}
+if check:
+    gathered = [None] * world
+    lo, hi = S.own_elems
+    plane_e = int(np.prod(P.grid[1:]))
+    dist.all_gather_object(gathered, (S.e0 * plane_e, S.e1 * plane_e, out["s"][lo:hi], out["rho"][lo:hi]))
+    if rank == 0:
+        ref = capi.Simp(ctx, P)
+        fr = [ref.iterate(check_convergence=False) for _ in range(iters)]
+        o = ref.get()
+        s_d, rho_d = np.zeros(P.nelem), np.zeros(P.nelem)
+        for a, b, sv, rv in gathered:
+            s_d[a:b] = sv; rho_d[a:b] = rv
+        res.update(f_single=[h["f"] for h in fr], cg_single=[h["cg_iters"] for h in fr],
+                   max_s_diff=float(np.abs(s_d - o["s"]).max()), max_rho_diff=float(np.abs(rho_d - o["rho"]).max()),
+                   max_f_rel=float(max(abs(a["f"] - b["f"]) / abs(b["f"]) for a, b in zip(hist, fr))))
+        assert res["max_f_rel"] < 1e-8 and res["max_s_diff"] < 1e-6 and res["max_rho_diff"] < 1e-6, res
+if rank == 0:
+    print(json.dumps(res, default=float))
+dist.destroy_process_group()
