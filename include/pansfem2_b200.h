@@ -227,7 +227,7 @@ int pf2_dist_halo(pf2_dist* d, double* vec_dev, const int halo[6]);
 int pf2_csr_set_partition(pf2_csr* A, pf2_dist* d, int own_lo, int own_hi, const int halo[6]);
 /* Make a design loop built on a slab's local mesh one part of a partitioned loop: elements [own_elem_lo, own_elem_hi) are
  * owned, elem_halo = contiguous element ranges exchanged with the neighbours, n_global_elems = elements of the whole mesh
- * (the volume constraint is global).  OC only for now. */
+ * (the volume constraint is global). */
 int pf2_simp_set_partition(pf2_simp* S, pf2_dist* d, int own_elem_lo, int own_elem_hi, const int elem_halo[6], long long n_global_elems);
 
 #ifdef __cplusplus

@@ -155,6 +155,12 @@ int dist_allreduce(pf2_dist* d, double* dev, int count) {
     return PF2_OK;
 }
 
+int dist_allreduce_max(pf2_dist* d, double* dev, int count) {
+    PF2_NCCL(nccl::AllReduce(dev, dev, count, ncclDouble, ncclMax, d->comm, d->ctx->stream));
+    d->ctx->launches++;
+    return PF2_OK;
+}
+
 int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out) {
     pf2_ctx* c = A->ctx;
     pf2_dist* d = A->dist;
@@ -180,7 +186,10 @@ int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, d
     while (!finished) {
         const int todo = std::min(chunk, itrmax - enq);
         for (int k = 0; k < todo; k++) {
+            const bool sample = (k == todo / 2) && enq > 0;      // one SpMV per chunk is bracketed by events (roofline)
+            if (sample) PF2_CUDA(cudaEventRecord(A->pev[slot][0], s));
             PF2_TRY(spmv_dot(A, A->p, A->y, A->st, &A->st->pAp));
+            if (sample) { PF2_CUDA(cudaEventRecord(A->pev[slot][1], s)); A->pev_armed[slot] = true; }
             PF2_TRY(dist_allreduce(d, &A->st->pAp, 1));
             if (solver == PF2_SOLVER_CG) dcg_update_kernel<0><<<ugrid, kThreads, 0, s>>>(lo, hi, A->p, A->y, A->dvec, x, A->r, A->z, A->st, c->red.partials, c->red.ticket);
             else dcg_update_kernel<1><<<ugrid, kThreads, 0, s>>>(lo, hi, A->p, A->y, A->dvec, x, A->r, A->z, A->st, c->red.partials, c->red.ticket);
@@ -197,6 +206,12 @@ int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, d
         if (have_prev) {
             PF2_CUDA(cudaEventSynchronize(A->ev[slot ^ 1]));
             last = A->h_st[slot ^ 1];
+            if (A->pev_armed[slot ^ 1]) {
+                A->pev_armed[slot ^ 1] = false;
+                float ms = 0;
+                if (!last.done && cudaEventElapsedTime(&ms, A->pev[slot ^ 1][0], A->pev[slot ^ 1][1]) == cudaSuccess) { A->prof_ms[0] += ms; A->prof_samples++; }
+                else cudaGetLastError();
+            }
             if (last.done) finished = true;
         }
         if (!finished && (enq >= itrmax || todo == 0)) {
@@ -208,6 +223,7 @@ int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, d
         slot ^= 1;
     }
     PF2_CUDA(cudaStreamSynchronize(s));
+    A->pev_armed[0] = A->pev_armed[1] = false;
     PF2_CUDA(cudaMemcpyAsync(&A->h_st[0], A->st, sizeof(CgState), cudaMemcpyDeviceToHost, s));
     PF2_CUDA(cudaStreamSynchronize(s));
     last = A->h_st[0];

@@ -16,6 +16,9 @@
 
 namespace pf2 {
 
+int dist_allreduce(pf2_dist* d, double* dev, int count);
+int dist_allreduce_max(pf2_dist* d, double* dev, int count);
+
 __device__ __forceinline__ double sq(double x) { return x * x; }
 
 // dense elimination with partial pivoting, as MMA<T>::solvels (MMA.h:465-509); N <= kMaxM+1
@@ -61,7 +64,7 @@ __device__ double kkt_small(const MmaSmall* S, const double* y, const double* la
 // ---- set-up pass: asymptotes, move limits, p0 q0 p q b, starting point (MMA.h:119-197) -----------------------------
 template <int M>
 __global__ void __launch_bounds__(kThreads)
-mma_setup_kernel(int n, int k, MmaParams P, const double* __restrict__ xk, const double* __restrict__ xkm1,
+mma_setup_kernel(int lo, int hi, int n, int k, MmaParams P, const double* __restrict__ xk, const double* __restrict__ xkm1,
                  const double* __restrict__ xkm2, const double* __restrict__ xmin, const double* __restrict__ xmax,
                  const double* __restrict__ dfdx, const double* __restrict__ dgdx, double* __restrict__ L, double* __restrict__ U,
                  double* __restrict__ alpha, double* __restrict__ beta, double* __restrict__ p0, double* __restrict__ q0,
@@ -70,7 +73,7 @@ mma_setup_kernel(int n, int k, MmaParams P, const double* __restrict__ xk, const
     double bs[M];
 #pragma unroll
     for (int i = 0; i < M; i++) bs[i] = 0.0;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    for (int j = lo + blockIdx.x * blockDim.x + threadIdx.x; j < hi; j += gridDim.x * blockDim.x) {
         const double xj = xk[j], w = xmax[j] - xmin[j];
         double Lj, Uj;
         if (k < 2) {
@@ -109,18 +112,23 @@ mma_setup_kernel(int n, int k, MmaParams P, const double* __restrict__ xk, const
     }
     if (grid_sum_last<M>(bs, partials, ticket) && threadIdx.x == 0) {
 #pragma unroll
-        for (int i = 0; i < M; i++) {
-            S->b[i] = -gval[i] + bs[i];
-            S->y[i] = 1.0; S->lam[i] = 1.0; S->s[i] = 1.0; S->mu[i] = fmax(1.0, 0.5 * S->c[i]);
-        }
-        S->z = 1.0; S->zeta = 1.0; S->eps = 1.0; S->newton = 0; S->halvings = 0; S->accept = 0; S->ll = 0;
+        for (int i = 0; i < M; i++) S->red[i] = bs[i];
     }
+}
+// the m-sized tail of the set-up pass; in a partitioned run the sums in S->red have been allreduced in between
+template <int M>
+__global__ void mma_setup_small_kernel(MmaSmall* S, const double* __restrict__ gval) {
+    for (int i = 0; i < M; i++) {
+        S->b[i] = -gval[i] + S->red[i];
+        S->y[i] = 1.0; S->lam[i] = 1.0; S->s[i] = 1.0; S->mu[i] = fmax(1.0, 0.5 * S->c[i]);
+    }
+    S->z = 1.0; S->zeta = 1.0; S->eps = 1.0; S->newton = 0; S->halvings = 0; S->accept = 0; S->ll = 0;
 }
 
 // ---- Newton pass 1 (MMA.h:201-291 + the m-sized updates :332-343,:353-359 + KKTNorm of the current point :361) ------
 template <int M>
 __global__ void __launch_bounds__(kThreads)
-mma_newton1_kernel(int n, const double* __restrict__ x, const double* __restrict__ L, const double* __restrict__ U,
+mma_newton1_kernel(int lo, int hi, int n, const double* __restrict__ x, const double* __restrict__ L, const double* __restrict__ U,
                    const double* __restrict__ alpha, const double* __restrict__ beta, const double* __restrict__ p0,
                    const double* __restrict__ q0, const double* __restrict__ p, const double* __restrict__ q,
                    const double* __restrict__ gsi, const double* __restrict__ ita, double* __restrict__ Dx,
@@ -133,7 +141,7 @@ mma_newton1_kernel(int n, const double* __restrict__ x, const double* __restrict
 #pragma unroll
     for (int i = 0; i < M; i++) lam[i] = S->lam[i];
     const double eps = S->eps;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    for (int j = lo + blockIdx.x * blockDim.x + threadIdx.x; j < hi; j += gridDim.x * blockDim.x) {
         const double xj = x[j], ux = U[j] - xj, xl = xj - L[j], xa = xj - alpha[j], bx = beta[j] - xj;
         double pl = p0[j], ql = q0[j], G[M];
         const double iux2 = 1.0 / sq(ux), ixl2 = 1.0 / sq(xl);
@@ -158,6 +166,18 @@ mma_newton1_kernel(int n, const double* __restrict__ x, const double* __restrict
         v[NT - 1] += sq(grad - gs + it) + sq(gs * xa - eps) + sq(it * bx - eps);
     }
     if (grid_sum_last<NT>(v, partials, ticket) && threadIdx.x == 0) {
+#pragma unroll
+        for (int t = 0; t < NT; t++) S->red[t] = v[t];
+    }
+}
+// reduced (m+1)x(m+1) system and the m-sized Newton updates from the (all)reduced sums in S->red
+template <int M>
+__global__ void mma_newton1_small_kernel(MmaSmall* S) {
+    constexpr int NT = M * M + 2 * M + 1;
+    double v[NT];
+    for (int t = 0; t < NT; t++) v[t] = S->red[t];
+    const double eps = S->eps;
+    {
         double Dy[M], Dlam[M], dty[M], dtlam[M], Dlamy[M], dtlamy[M], gsum[M];
         double la = 0.0;
 #pragma unroll
@@ -208,7 +228,7 @@ mma_newton1_kernel(int n, const double* __restrict__ x, const double* __restrict
 // ---- Newton pass 2: dx, dxi, deta, maximal step (MMA.h:282-287, 338-360) ----------------------------------------------
 template <int M>
 __global__ void __launch_bounds__(kThreads)
-mma_newton2_kernel(int n, const double* __restrict__ x, const double* __restrict__ L, const double* __restrict__ U,
+mma_newton2_kernel(int lo, int hi, int n, const double* __restrict__ x, const double* __restrict__ L, const double* __restrict__ U,
                    const double* __restrict__ alpha, const double* __restrict__ beta, const double* __restrict__ p,
                    const double* __restrict__ q, const double* __restrict__ gsi, const double* __restrict__ ita,
                    const double* __restrict__ Dx, const double* __restrict__ dtx, double* __restrict__ dx,
@@ -218,7 +238,7 @@ mma_newton2_kernel(int n, const double* __restrict__ x, const double* __restrict
     for (int i = 0; i < M; i++) dlam[i] = S->dlam[i];
     const double eps = S->eps;
     double txmax = 0.0;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    for (int j = lo + blockIdx.x * blockDim.x + threadIdx.x; j < hi; j += gridDim.x * blockDim.x) {
         const double xj = x[j], ux = U[j] - xj, xl = xj - L[j], xa = xj - alpha[j], bx = beta[j] - xj, dxx = Dx[j];
         double d = -dtx[j] / dxx;
 #pragma unroll
@@ -233,17 +253,19 @@ mma_newton2_kernel(int n, const double* __restrict__ x, const double* __restrict
         const double t = fmax(fmax(-1.01 * d / xa, 1.01 * d / bx), fmax(-1.01 * dg / gs, -1.01 * di / it));
         if (txmax < t) txmax = t;
     }
-    if (grid_max_last(txmax, partials, ticket) && threadIdx.x == 0) {
-        const double m1 = fmax(fmax(1.0, fmax(txmax, 0.0)), fmax(S->tymax, -1.01 * S->dz / S->z));
-        S->tau = 1.0 / fmax(m1, -1.01 * S->dzeta / S->zeta);
-        S->ll = 0; S->accept = 0;
-    }
+    if (grid_max_last(txmax, partials, ticket) && threadIdx.x == 0) S->red[0] = txmax;
+}
+__global__ void mma_newton2_small_kernel(MmaSmall* S) {
+    const double txmax = S->red[0];
+    const double m1 = fmax(fmax(1.0, fmax(txmax, 0.0)), fmax(S->tymax, -1.01 * S->dz / S->z));
+    S->tau = 1.0 / fmax(m1, -1.01 * S->dzeta / S->zeta);
+    S->ll = 0; S->accept = 0;
 }
 
 // ---- line-search trial (MMA.h:371-410) ---------------------------------------------------------------------------------
 template <int M>
 __global__ void __launch_bounds__(kThreads)
-mma_trial_kernel(int n, const double* __restrict__ x, const double* __restrict__ L, const double* __restrict__ U,
+mma_trial_kernel(int lo, int hi, int n, const double* __restrict__ x, const double* __restrict__ L, const double* __restrict__ U,
                  const double* __restrict__ alpha, const double* __restrict__ beta, const double* __restrict__ p0,
                  const double* __restrict__ q0, const double* __restrict__ p, const double* __restrict__ q,
                  const double* __restrict__ gsi, const double* __restrict__ ita, const double* __restrict__ dx,
@@ -258,7 +280,7 @@ mma_trial_kernel(int n, const double* __restrict__ x, const double* __restrict__
     double lamn[M];
 #pragma unroll
     for (int i = 0; i < M; i++) lamn[i] = S->lam[i] + tau * S->dlam[i];
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    for (int j = lo + blockIdx.x * blockDim.x + threadIdx.x; j < hi; j += gridDim.x * blockDim.x) {
         const double xj = x[j] + tau * dx[j], gs = gsi[j] + tau * dgsi[j], it = ita[j] + tau * dita[j];
         xn[j] = xj; gsin[j] = gs; itan[j] = it;
         const double ux = U[j] - xj, xl = xj - L[j];
@@ -272,6 +294,20 @@ mma_trial_kernel(int n, const double* __restrict__ x, const double* __restrict__
         v[M] += sq(pl / sq(ux) - ql / sq(xl) - gs + it) + sq(gs * (xj - alpha[j]) - eps) + sq(it * (beta[j] - xj) - eps);
     }
     if (grid_sum_last<NT>(v, partials, ticket) && threadIdx.x == 0) {
+#pragma unroll
+        for (int t = 0; t < NT; t++) S->red[t] = v[t];
+    }
+}
+template <int M>
+__global__ void mma_trial_small_kernel(MmaSmall* S) {
+    if (S->accept) return;
+    constexpr int NT = M + 1;
+    double v[NT];
+    for (int t = 0; t < NT; t++) v[t] = S->red[t];
+    const double tau = S->tau, eps = S->eps;
+    double lamn[M];
+    for (int i = 0; i < M; i++) lamn[i] = S->lam[i] + tau * S->dlam[i];
+    {
         double yn[M], sn[M], mun[M], gsum[M];
 #pragma unroll
         for (int i = 0; i < M; i++) {
@@ -468,28 +504,38 @@ template <int M>
 static int mma_update_impl(pf2_mma* mm, double* xk, const double* dfdx, const double* dgdx, int* newton_out) {
     pf2_ctx* c = mm->ctx;
     cudaStream_t s = c->stream;
-    const int n = mm->n;
-    const int grid = c->grid_for(n);
-    mma_setup_kernel<M><<<grid, kThreads, 0, s>>>(n, mm->k, mm->P, xk, mm->xkm1, mm->xkm2, mm->xmin, mm->xmax, dfdx, dgdx, mm->L, mm->U,
+    pf2_dist* d = mm->dist;
+    const int n = mm->n, lo = mm->lo, hi = mm->hi;
+    const int grid = c->grid_for(hi - lo);
+    constexpr int NT1 = M * M + 2 * M + 1;
+    mma_setup_kernel<M><<<grid, kThreads, 0, s>>>(lo, hi, n, mm->k, mm->P, xk, mm->xkm1, mm->xkm2, mm->xmin, mm->xmax, dfdx, dgdx, mm->L, mm->U,
                                                  mm->alpha, mm->beta, mm->p0, mm->q0, mm->p, mm->q, mm->x, mm->gsi, mm->ita, mm->S,
                                                  mm->gval, c->red.partials, c->red.ticket);
+    if (d) PF2_TRY(dist_allreduce(d, mm->S->red, M));
+    mma_setup_small_kernel<M><<<1, 1, 0, s>>>(mm->S, mm->gval);
     PF2_LAUNCH_CHECK();
-    c->launches++;
+    c->launches += 2;
     double eps = 1.0;
     int guard = 0;
     while (eps > 1.0e-7) {      // MMA.h:199
-        mma_newton1_kernel<M><<<grid, kThreads, 0, s>>>(n, mm->x, mm->L, mm->U, mm->alpha, mm->beta, mm->p0, mm->q0, mm->p, mm->q, mm->gsi,
+        mma_newton1_kernel<M><<<grid, kThreads, 0, s>>>(lo, hi, n, mm->x, mm->L, mm->U, mm->alpha, mm->beta, mm->p0, mm->q0, mm->p, mm->q, mm->gsi,
                                                        mm->ita, mm->Dx, mm->dtx, mm->S, c->red.partials, c->red.ticket);
-        mma_newton2_kernel<M><<<grid, kThreads, 0, s>>>(n, mm->x, mm->L, mm->U, mm->alpha, mm->beta, mm->p, mm->q, mm->gsi, mm->ita, mm->Dx,
+        if (d) PF2_TRY(dist_allreduce(d, mm->S->red, NT1));
+        mma_newton1_small_kernel<M><<<1, 1, 0, s>>>(mm->S);
+        mma_newton2_kernel<M><<<grid, kThreads, 0, s>>>(lo, hi, n, mm->x, mm->L, mm->U, mm->alpha, mm->beta, mm->p, mm->q, mm->gsi, mm->ita, mm->Dx,
                                                        mm->dtx, mm->dx, mm->dgsi, mm->dita, mm->S, c->red.partials, c->red.ticket);
-        c->launches += 2;
+        if (d) PF2_TRY(dist_allreduce_max(d, mm->S->red, 1));
+        mma_newton2_small_kernel<<<1, 1, 0, s>>>(mm->S);
+        c->launches += 4;
         bool accepted = false;
         while (!accepted) {
-            mma_trial_kernel<M><<<grid, kThreads, 0, s>>>(n, mm->x, mm->L, mm->U, mm->alpha, mm->beta, mm->p0, mm->q0, mm->p, mm->q, mm->gsi,
+            mma_trial_kernel<M><<<grid, kThreads, 0, s>>>(lo, hi, n, mm->x, mm->L, mm->U, mm->alpha, mm->beta, mm->p0, mm->q0, mm->p, mm->q, mm->gsi,
                                                          mm->ita, mm->dx, mm->dgsi, mm->dita, mm->xn, mm->gsin, mm->itan, mm->S,
                                                          c->red.partials, c->red.ticket);
+            if (d) PF2_TRY(dist_allreduce(d, mm->S->red, M + 1));
+            mma_trial_small_kernel<M><<<1, 1, 0, s>>>(mm->S);
             PF2_LAUNCH_CHECK();
-            c->launches++;
+            c->launches += 2;
             PF2_CUDA(cudaMemcpyAsync(mm->h_S, mm->S, sizeof(MmaSmall), cudaMemcpyDeviceToHost, s));
             PF2_CUDA(cudaStreamSynchronize(s));
             accepted = mm->h_S->accept != 0;
@@ -501,7 +547,7 @@ static int mma_update_impl(pf2_mma* mm, double* xk, const double* dfdx, const do
     // MMA.h:414-418
     PF2_CUDA(cudaMemcpyAsync(mm->xkm2, mm->xkm1, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
     PF2_CUDA(cudaMemcpyAsync(mm->xkm1, xk, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
-    PF2_CUDA(cudaMemcpyAsync(xk, mm->x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    PF2_CUDA(cudaMemcpyAsync(xk + lo, mm->x + lo, sizeof(double) * (size_t)(hi - lo), cudaMemcpyDeviceToDevice, s));
     if (newton_out) *newton_out = mm->h_S->newton;
     return PF2_OK;
 }
@@ -546,6 +592,7 @@ int pf2_mma_create(pf2_ctx* ctx, int n, int m, double a0, const double* a_host, 
     PF2_CUDA(cudaSetDevice(ctx->device));
     pf2_mma* mm = new pf2_mma();
     mm->ctx = ctx; mm->n = n; mm->m = m;
+    mm->lo = 0; mm->hi = n;
     const size_t N = (size_t)n;
     double** vecs[] = { &mm->xmin, &mm->xmax, &mm->xkm1, &mm->xkm2, &mm->L, &mm->U, &mm->alpha, &mm->beta, &mm->p0, &mm->q0, &mm->x,
                         &mm->gsi, &mm->ita, &mm->xn, &mm->gsin, &mm->itan, &mm->dx, &mm->dgsi, &mm->dita, &mm->Dx, &mm->dtx };

@@ -98,10 +98,7 @@ static int simp_iterate(pf2_simp* S, int check_convergence, double stats[8]) {
     int opt_steps = 0;
     if (!(check_convergence && converged)) {
         if (S->oc) PF2_TRY(oc_update(S->oc, S->filter, S->weightlimit, S->scale1, S->s, f, S->dfds, S->dgds, &opt_steps, nullptr));
-        else {
-            if (d) { set_error("MMA on a partitioned design is not built yet: use OC (config 5)"); return PF2_E_UNSUPPORTED; }
-            PF2_TRY(mma_update(S->mma, S->s, f, S->dfds, &g, S->dgds, &opt_steps));
-        }
+        else PF2_TRY(mma_update(S->mma, S->s, f, S->dfds, &g, S->dgds, &opt_steps));
     }
     PF2_CUDA(cudaEventRecord(S->ev[6], s));
     PF2_CUDA(cudaEventSynchronize(S->ev[6]));
@@ -183,6 +180,7 @@ int pf2_simp_set_partition(pf2_simp* S, pf2_dist* d, int own_elem_lo, int own_el
     S->filter->dist = d; S->filter->sum_lo = own_elem_lo; S->filter->sum_hi = own_elem_hi;
     S->mesh->own_elem_lo = own_elem_lo; S->mesh->own_elem_hi = own_elem_hi;
     if (S->oc) S->oc->n_global = n_global_elems;
+    if (S->mma) { S->mma->dist = d; S->mma->lo = own_elem_lo; S->mma->hi = own_elem_hi; }
     return PF2_OK;
 }
 

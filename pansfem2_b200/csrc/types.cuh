@@ -136,6 +136,7 @@ struct MmaSmall {
     double dy[kMaxM], dlam[kMaxM], ds[kMaxM], dmu[kMaxM], dz, dzeta;
     double b[kMaxM];
     double eps, tau, tymax, dwl, dwl1;
+    double red[32];          // sums / max of the current pass (allreduced across ranks in a partitioned run)
     int accept, ll, halvings, newton;
 };
 
@@ -155,6 +156,9 @@ struct pf2_mma {
     double *x = nullptr, *gsi = nullptr, *ita = nullptr, *xn = nullptr, *gsin = nullptr, *itan = nullptr;
     double *dx = nullptr, *dgsi = nullptr, *dita = nullptr, *Dx = nullptr, *dtx = nullptr;
     double* gval = nullptr;
+    // multi-GPU: variables [lo, hi) of the local arrays are owned by this rank
+    pf2_dist* dist = nullptr;
+    int lo = 0, hi = 0;
     pf2::MmaSmall* S = nullptr;
     pf2::MmaSmall* h_S = nullptr;   // pinned
 };

@@ -17,24 +17,27 @@ from __future__ import annotations
 import numpy as np
 
 
-def square_mesh(lx: float, ly: float, nx: int, ny: int):
-    i, j = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), indexing="ij")
-    coords = np.empty(((nx + 1) * (ny + 1), 2), dtype=np.float64)
+def square_mesh(lx: float, ly: float, nx: int, ny: int, xr=None):
+    """xr = (i0, i1): only element columns [i0, i1) (node columns [i0, i1]) with LOCAL ids - one slab of the mesh."""
+    i0, i1 = xr if xr is not None else (0, nx)
+    i, j = np.meshgrid(np.arange(i0, i1 + 1), np.arange(ny + 1), indexing="ij")
+    coords = np.empty(((i1 - i0 + 1) * (ny + 1), 2), dtype=np.float64)
     coords[:, 0] = (lx * (i / float(nx))).ravel()
     coords[:, 1] = (ly * (j / float(ny))).ravel()
-    ei, ej = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    ei, ej = np.meshgrid(np.arange(i1 - i0), np.arange(ny), indexing="ij")
     n0 = ((ny + 1) * ei + ej).ravel()
     conn = np.stack([n0, n0 + (ny + 1), n0 + (ny + 1) + 1, n0 + 1], axis=1).astype(np.int32)
     return coords, conn
 
 
-def box_mesh(lx: float, ly: float, lz: float, nx: int, ny: int, nz: int):
-    i, j, k = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
-    coords = np.empty(((nx + 1) * (ny + 1) * (nz + 1), 3), dtype=np.float64)
+def box_mesh(lx: float, ly: float, lz: float, nx: int, ny: int, nz: int, xr=None):
+    i0, i1 = xr if xr is not None else (0, nx)
+    i, j, k = np.meshgrid(np.arange(i0, i1 + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
+    coords = np.empty(((i1 - i0 + 1) * (ny + 1) * (nz + 1), 3), dtype=np.float64)
     coords[:, 0] = (lx * (i / float(nx))).ravel()
     coords[:, 1] = (ly * (j / float(ny))).ravel()
     coords[:, 2] = (lz * (k / float(nz))).ravel()
-    ei, ej, ek = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    ei, ej, ek = np.meshgrid(np.arange(i1 - i0), np.arange(ny), np.arange(nz), indexing="ij")
     sx, sy = (ny + 1) * (nz + 1), (nz + 1)
     n0 = (ei * sx + ej * sy + ek).ravel().astype(np.int64)
     conn = np.stack([n0, n0 + sx, n0 + sx + sy, n0 + sy,

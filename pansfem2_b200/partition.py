@@ -45,6 +45,51 @@ def _dofmap(nnode, ndof, fixed):
     return n2g.reshape(nnode, ndof)
 
 
+def slab_from_factory(factory, grid, ndof, rank: int, nranks: int) -> Slab:
+    """Build one slab WITHOUT materialising the global mesh: `factory(xr=(i0, i1))` returns the Problem restricted to element
+    planes [i0, i1) with local ids (problems.cantilever2d / heat2d / cantilever3d all take `xr`).  Used for the big configs;
+    `global_rows` is not known locally and is left at (-1, -1)."""
+    nx = grid[0]
+    assert nranks <= nx
+    plane_e = int(np.prod(grid[1:]))
+    plane_n = int(np.prod([g + 1 for g in grid[1:]]))
+    e0, e1 = rank * nx // nranks, (rank + 1) * nx // nranks
+    le0, le1 = max(e0 - 1, 0), min(e1 + 1, nx)
+    L = factory(xr=(le0, le1))
+    on0, on1 = e0, (e1 if rank < nranks - 1 else nx + 1)
+    own_node_lo, own_node_hi = (on0 - le0) * plane_n, (on1 - le0) * plane_n
+    ln = np.asarray(L.loads[0], np.int64)
+    keep = (ln >= own_node_lo) & (ln < own_node_hi)
+    L.loads = (np.asarray(L.loads[0])[keep], np.asarray(L.loads[1])[keep], np.asarray(L.loads[2])[keep])
+    L.name = f"{L.name}_slab{rank}of{nranks}"
+    n2g = _dofmap(L.nnode, ndof, L.fixed)
+    return _finish(L, n2g, rank, nranks, e0, e1, le0, le1, on0, on1, plane_e, plane_n, (-1, -1))
+
+
+def _finish(local, n2g, rank, nranks, e0, e1, le0, le1, on0, on1, plane_e, plane_n, global_rows) -> Slab:
+    def rows_of_planes(p0, p1):
+        a, b = (p0 - le0) * plane_n, (p1 - le0) * plane_n
+        blk = n2g[a:b].ravel()
+        blk = blk[blk >= 0]
+        if blk.size == 0:
+            k = int((n2g[:a].ravel() >= 0).sum())
+            return k, k
+        return int(blk.min()), int(blk.max()) + 1
+
+    own_lo, own_hi = rows_of_planes(on0, on1)
+    sendL = recvL = sendR = recvR = (0, 0)
+    if rank > 0:
+        sendL, recvL = rows_of_planes(e0, e0 + 1), rows_of_planes(e0 - 1, e0)
+    if rank < nranks - 1:
+        sendR, recvR = rows_of_planes(e1 - 1, e1), rows_of_planes(e1, e1 + 1)
+    row_halo = (sendL[0], recvL[0], sendL[1] - sendL[0], sendR[0], recvR[0], sendR[1] - sendR[0])
+    el = lambda p: (p - le0) * plane_e
+    elem_halo = (el(e0), el(e0 - 1) if rank > 0 else 0, plane_e if rank > 0 else 0,
+                 el(e1 - 1), el(e1) if rank < nranks - 1 else 0, plane_e if rank < nranks - 1 else 0)
+    return Slab(rank, nranks, local, e0, e1, le0, le1, (own_lo, own_hi), row_halo, (el(e0), el(e1)), elem_halo,
+                ((on0 - le0) * plane_n, (on1 - le0) * plane_n), global_rows, n2g.astype(np.int32))
+
+
 def slab(P: problems.Problem, rank: int, nranks: int) -> Slab:
     nx = P.grid[0]
     assert nranks <= nx, "more ranks than element planes"

@@ -73,40 +73,44 @@ class Problem:
         return self.nnode * self.ndof - len(self.fixed[0])
 
 
-def cantilever2d(nx=60, ny=40, opt_kind=OPT_OC, filter_kind=FILTER_HEAVISIDE, radius=1.5) -> Problem:
+def cantilever2d(nx=60, ny=40, opt_kind=OPT_OC, filter_kind=FILTER_HEAVISIDE, radius=1.5, xr=None) -> Problem:
+    """xr = (i0, i1): build only element columns [i0, i1) of the nx x ny problem (one slab, local ids)."""
     lx, ly = float(nx), float(ny)
-    coords, conn = mesher.square_mesh(lx, ly, nx, ny)
+    coords, conn = mesher.square_mesh(lx, ly, nx, ny, xr)
     fixed = mesher.fixed_list(coords, [0, 1], lambda x: np.abs(x[:, 0]) < 1.0e-5)
     ln, ld, lv = mesher.fixed_list(coords, [1], lambda x: (np.abs(x[:, 0] - lx) < 1.0e-5) & (np.abs(x[:, 1] - ly / 2) < 1.0e-5), -1.0)
-    nbrs = mesher.filter_neighbors_2d(nx, ny, lx, ly, radius)
-    return Problem(f"cantilever2d_{nx}x{ny}", EQ_PLANESTRAIN, coords, conn, fixed, (ln, ld, lv), nbrs, (nx, ny),
-                   filter_kind=filter_kind, opt_kind=opt_kind)
+    nxl = nx if xr is None else xr[1] - xr[0]
+    nbrs = mesher.filter_neighbors_2d(nxl, ny, float(nxl), ly, radius)
+    return Problem(f"cantilever2d_{nx}x{ny}", EQ_PLANESTRAIN, coords, conn, fixed, (ln, ld, lv), nbrs, (nxl, ny),
+                   filter_kind=filter_kind, opt_kind=opt_kind, extra={"global_grid": (nx, ny)})
 
 
-def heat2d(nx=64, ny=64, opt_kind=OPT_OC, filter_kind=FILTER_DENSITY, radius=1.5) -> Problem:
+def heat2d(nx=64, ny=64, opt_kind=OPT_OC, filter_kind=FILTER_DENSITY, radius=1.5, xr=None) -> Problem:
     """Config 3: Q4 heat conduction, k(rho) = k0 + (k1-k0) rho^p, sink on the middle 10% of the left edge,
     uniform nodal heat load 1/nnode on all free nodes, volume fraction 0.4."""
     lx, ly = float(nx), float(ny)
-    coords, conn = mesher.square_mesh(lx, ly, nx, ny)
+    coords, conn = mesher.square_mesh(lx, ly, nx, ny, xr)
     fixed = mesher.fixed_list(coords, [0], lambda x: (np.abs(x[:, 0]) < 1.0e-5) & (np.abs(x[:, 1] - ly / 2) <= 0.05 * ly + 1.0e-9))
     nnode = coords.shape[0]
     is_fixed = np.zeros(nnode, bool)
     is_fixed[fixed[0]] = True
     ln = np.nonzero(~is_fixed)[0].astype(np.int32)
-    loads = (ln, np.zeros_like(ln), np.full(ln.shape, 1.0 / nnode))
-    nbrs = mesher.filter_neighbors_2d(nx, ny, lx, ly, radius)
-    return Problem(f"heat2d_{nx}x{ny}", EQ_HEAT, coords, conn, fixed, loads, nbrs, (nx, ny),
+    loads = (ln, np.zeros_like(ln), np.full(ln.shape, 1.0 / ((nx + 1) * (ny + 1))))
+    nxl = nx if xr is None else xr[1] - xr[0]
+    nbrs = mesher.filter_neighbors_2d(nxl, ny, float(nxl), ly, radius)
+    return Problem(f"heat2d_{nx}x{ny}", EQ_HEAT, coords, conn, fixed, loads, nbrs, (nxl, ny),
                    filter_kind=filter_kind, opt_kind=opt_kind, E0=1.0e-3, E1=1.0, weightlimit=0.4, scale0=1.0,
-                   beta_period=0)
+                   beta_period=0, extra={"global_grid": (nx, ny)})
 
 
-def cantilever3d(nx=16, ny=8, nz=8, opt_kind=OPT_OC, filter_kind=FILTER_DENSITY, radius=1.5) -> Problem:
+def cantilever3d(nx=16, ny=8, nz=8, opt_kind=OPT_OC, filter_kind=FILTER_DENSITY, radius=1.5, xr=None) -> Problem:
     """Configs 4-5: hex8 cantilever, clamp the x=0 face (3 dofs), unit -y load spread over the line x=lx, y=ly/2."""
     lx, ly, lz = float(nx), float(ny), float(nz)
-    coords, conn = mesher.box_mesh(lx, ly, lz, nx, ny, nz)
+    coords, conn = mesher.box_mesh(lx, ly, lz, nx, ny, nz, xr)
     fixed = mesher.fixed_list(coords, [0, 1, 2], lambda x: np.abs(x[:, 0]) < 1.0e-5)
     sel = lambda x: (np.abs(x[:, 0] - lx) < 1.0e-5) & (np.abs(x[:, 1] - ly / 2) < 1.0e-5)
     ln, ld, lv = mesher.fixed_list(coords, [1], sel, -1.0 / (nz + 1))
-    nbrs = mesher.filter_neighbors_3d(nx, ny, nz, lx, ly, lz, radius)
-    return Problem(f"cantilever3d_{nx}x{ny}x{nz}", EQ_SOLID, coords, conn, fixed, (ln, ld, lv), nbrs, (nx, ny, nz),
-                   filter_kind=filter_kind, opt_kind=opt_kind, beta_period=0)
+    nxl = nx if xr is None else xr[1] - xr[0]
+    nbrs = mesher.filter_neighbors_3d(nxl, ny, nz, float(nxl), ly, lz, radius)
+    return Problem(f"cantilever3d_{nx}x{ny}x{nz}", EQ_SOLID, coords, conn, fixed, (ln, ld, lv), nbrs, (nxl, ny, nz),
+                   filter_kind=filter_kind, opt_kind=opt_kind, beta_period=0, extra={"global_grid": (nx, ny, nz)})

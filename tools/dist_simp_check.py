@@ -24,12 +24,13 @@ args = [a for a in argv if not a.startswith("--")]
 kind = args[0] if args else "3d"
 dims = [int(a) for a in args[1:]]
 check = "--big" not in argv
+opt = problems.OPT_MMA if "--mma" in argv else problems.OPT_OC
 if kind == "2d":
-    P = problems.cantilever2d(*(dims or [120, 60]), filter_kind=problems.FILTER_HEAVISIDE)
+    P = problems.cantilever2d(*(dims or [120, 60]), filter_kind=problems.FILTER_HEAVISIDE, opt_kind=opt)
 elif kind == "heat":
-    P = problems.heat2d(*(dims or [64, 64]))
+    P = problems.heat2d(*(dims or [64, 64]), opt_kind=opt)
 else:
-    P = problems.cantilever3d(*(dims or [24, 12, 8]))
+    P = problems.cantilever3d(*(dims or [24, 12, 8]), opt_kind=opt)
 ctx = capi.Context(local_rank)
 D = capi.Dist(ctx, rank, world)
 S = partition.slab(P, rank, world)
