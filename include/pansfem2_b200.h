@@ -225,6 +225,13 @@ int pf2_dist_halo(pf2_dist* d, double* vec_dev, const int halo[6]);
 /* Mark a LOCAL matrix (local mesh = owned element planes + one ghost plane per side) as one row block of a partitioned
  * system: rows [own_lo, own_hi) are owned; pf2_solve then runs the distributed PCG (halo exchange of p + allreduces). */
 int pf2_csr_set_partition(pf2_csr* A, pf2_dist* d, int own_lo, int own_hi, const int halo[6]);
+/* Peer-memory backend for the partitioned PCG (optional; NCCL otherwise): the halo exchange is fused into the p-update kernel
+ * (boundary planes are stored straight into the neighbours' ghost ranges over NVLink) and the dot-product allreduces run
+ * inside one-warp kernels over IPC-mapped arenas.  export: this rank's IPC handles {arena, Krylov slab} (2 x 64 bytes);
+ * exchange them through any channel; import: all ranks' handles (world x 128 bytes) and all ranks' meta (world x 8 ints =
+ * {row halo descriptor[6], local rows, 0}). */
+int pf2_csr_p2p_export(pf2_csr* A, char handles_out[128]);
+int pf2_csr_p2p_import(pf2_csr* A, const char* all_handles, const int* all_meta);
 /* Make a design loop built on a slab's local mesh one part of a partitioned loop: elements [own_elem_lo, own_elem_hi) are
  * owned, elem_halo = contiguous element ranges exchanged with the neighbours, n_global_elems = elements of the whole mesh
  * (the volume constraint is global). */

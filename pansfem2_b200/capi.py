@@ -465,9 +465,25 @@ class Dist:
         h = (C.c_int * 6)(*[int(v) for v in row_halo])
         _ck(lib().pf2_csr_set_partition(A.h, self.h, int(own_rows[0]), int(own_rows[1]), h))
 
+    def enable_p2p(self, A, row_halo):
+        """Switch the partitioned PCG of matrix A to the peer-memory backend (call after set_partition on every rank)."""
+        import torch.distributed as tdist
+        hb = (C.c_char * 128)()
+        _ck(lib().pf2_csr_p2p_export(A.h, hb))
+        meta = [int(v) for v in row_halo] + [int(A.rows), 0]
+        gathered = [None] * self.world
+        tdist.all_gather_object(gathered, (bytes(hb.raw), meta))
+        allh = (C.c_char * (128 * self.world))()
+        allh.raw = b"".join(g[0] for g in gathered)
+        allm = (C.c_int * (8 * self.world))(*[v for g in gathered for v in g[1]])
+        _ck(lib().pf2_csr_p2p_import(A.h, allh, allm))
+        tdist.barrier()
+
     def set_simp_partition(self, simp, slab, n_global_elems):
         """simp: capi.Simp built on slab.local; also partitions its matrix."""
         self.set_partition(simp.A, slab.own_rows, slab.row_halo)
+        if os.environ.get("PF2_P2P", "1") != "0" and self.world <= 8:
+            self.enable_p2p(simp.A, slab.row_halo)
         h = (C.c_int * 6)(*[int(v) for v in slab.elem_halo])
         _ck(lib().pf2_simp_set_partition(simp.h, self.h, int(slab.own_elems[0]), int(slab.own_elems[1]), h, C.c_longlong(int(n_global_elems))))
 

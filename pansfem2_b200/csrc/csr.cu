@@ -11,6 +11,7 @@
 //   * vector  : TPR lanes per row (2..32) with a shuffle reduction; used when a CTA's rows do not fit in shared memory.
 // Both optionally fuse the dot product x.y (p.Ap of CG, CG.h:433) into the epilogue.
 #include "types.cuh"
+#include "p2p.cuh"
 #include "spmv_tma.cuh"
 #include "spmv_sell.cuh"
 #include <cub/cub.cuh>
@@ -28,7 +29,7 @@ template <int G, bool DOT>
 __global__ void __launch_bounds__(kThreads)
 spmv_stream_kernel(int rows, const long long* __restrict__ indptr, const int* __restrict__ indices,
                    const double* __restrict__ data, const double* __restrict__ x, double* __restrict__ y,
-                   const CgState* __restrict__ st, double* dot_out, double* partials, unsigned int* ticket, int dot_lo, int dot_hi) {
+                   const CgState* __restrict__ st, double* dot_out, double* partials, unsigned int* ticket, int dot_lo, int dot_hi, const P2PView* p2p, unsigned long long* p2p_epoch) {
     if (DOT && st != nullptr && st->done) return;
     __shared__ double prod[kStreamCap];
     __shared__ long long s_range[2];
@@ -68,7 +69,7 @@ spmv_stream_kernel(int rows, const long long* __restrict__ indptr, const int* __
     }
     if (DOT) {
         double v[1] = { dot };
-        if (grid_sum_last<1>(v, partials, ticket) && threadIdx.x == 0) *dot_out = v[0];
+        if (grid_sum_last<1>(v, partials, ticket)) finish_dot(v[0], dot_out, p2p, p2p_epoch);
     }
 }
 
@@ -77,7 +78,7 @@ template <int TPR, bool DOT>
 __global__ void __launch_bounds__(kThreads)
 spmv_vector_kernel(int rows, const long long* __restrict__ indptr, const int* __restrict__ indices,
                    const double* __restrict__ data, const double* __restrict__ x, double* __restrict__ y,
-                   const CgState* __restrict__ st, double* dot_out, double* partials, unsigned int* ticket, int dot_lo, int dot_hi) {
+                   const CgState* __restrict__ st, double* dot_out, double* partials, unsigned int* ticket, int dot_lo, int dot_hi, const P2PView* p2p, unsigned long long* p2p_epoch) {
     if (DOT && st != nullptr && st->done) return;
     constexpr int RPB = kThreads / TPR;
     const int lr = threadIdx.x / TPR, lane = threadIdx.x % TPR;
@@ -101,7 +102,7 @@ spmv_vector_kernel(int rows, const long long* __restrict__ indptr, const int* __
     }
     if (DOT) {
         double v[1] = { dot };
-        if (grid_sum_last<1>(v, partials, ticket) && threadIdx.x == 0) *dot_out = v[0];
+        if (grid_sum_last<1>(v, partials, ticket)) finish_dot(v[0], dot_out, p2p, p2p_epoch);
     }
 }
 
@@ -175,7 +176,7 @@ static int launch_tma(pf2_csr* A, const double* x, double* y, const CgState* st,
     const int ntiles = (A->rows + rpb - 1) / rpb;
     const int grid = std::max(1, std::min(ntiles, c->sm_count * per_sm));
     spmv_tma_kernel<G, DOT><<<grid, kTmaThreads, smem, c->stream>>>(A->rows, A->indptr, A->indices, A->data, x, y, st, dot_out,
-                                                                   c->red.partials, c->red.ticket, cap, stages, A->own_lo, A->own_hi);
+                                                                   c->red.partials, c->red.ticket, cap, stages, A->own_lo, A->own_hi, A->p2p_dev, A->p2p_epoch);
     return PF2_OK;
 }
 
@@ -223,14 +224,14 @@ static int launch_sell(pf2_csr* A, const double* x, double* y, const CgState* st
     const int nb = (nslices + (kThreads / 32) - 1) / (kThreads / 32);
     const int grid = std::max(1, std::min(nb, c->wave_grid((const void*)spmv_sell_kernel<DOT>, kThreads)));
     spmv_sell_kernel<DOT><<<grid, kThreads, 0, c->stream>>>(A->rows, A->sell_ptr, A->sell_idx, A->sell_val, x, y, st, dot_out,
-                                                          c->red.partials, c->red.ticket, A->own_lo, A->own_hi);
+                                                          c->red.partials, c->red.ticket, A->own_lo, A->own_hi, A->p2p_dev, A->p2p_epoch);
     return PF2_OK;
 }
 
 template <bool DOT>
 static int launch_spmv(pf2_csr* A, int variant, const double* x, double* y, const CgState* st, double* dot_out) {
     pf2_ctx* c = A->ctx;
-#define ARGS A->rows, A->indptr, A->indices, A->data, x, y, st, dot_out, c->red.partials, c->red.ticket, A->own_lo, A->own_hi
+#define ARGS A->rows, A->indptr, A->indices, A->data, x, y, st, dot_out, c->red.partials, c->red.ticket, A->own_lo, A->own_hi, A->p2p_dev, A->p2p_epoch
 #define VEC(T)                                                                                               \
     {                                                                                                        \
         long long nb = ((long long)A->rows + (kThreads / T) - 1) / (kThreads / T);                              \
@@ -337,7 +338,7 @@ int pf2_csr_destroy(pf2_csr* A) {
     if (!A) return PF2_OK;
     cudaSetDevice(A->ctx->device);
     cudaStreamSynchronize(A->ctx->stream);
-    void* ptrs[] = { A->indptr, A->indices, A->data, A->F, A->diagpos, A->bmap, A->slab, A->xw, A->bw, A->st, A->sell_ptr, A->sell_idx, A->sell_val,
+    void* ptrs[] = { A->indptr, A->indices, A->data, A->F, A->diagpos, A->bmap, A->slab, A->xw, A->bw, A->st, A->sell_ptr, A->sell_idx, A->sell_val, A->p2p_dev,
                      A->ilu, A->level_rows, A->level_rows_u };
     for (void* p : ptrs) if (p) cudaFree(p);
     if (A->h_st) cudaFreeHost(A->h_st);

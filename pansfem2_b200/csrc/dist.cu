@@ -14,6 +14,7 @@
 #include <nccl.h>
 #include <dlfcn.h>
 #include "types.cuh"
+#include "p2p.cuh"
 
 // NCCL is bound lazily with dlopen so that (a) single-GPU users never load it and (b) inside a Python process the copy
 // torch already loaded (same soname, possibly newer than the system one) is reused instead of a second, older library.
@@ -43,10 +44,23 @@ namespace pf2 { namespace nccl {
     }
 } }
 
+namespace pf2 {
+constexpr int kMaxRanks = kMaxRanksT;
+// Peer-memory view of the box (handed to the kernels by value): see P2PView in types.cuh.
+//   arena (one per rank, cudaMalloc + cudaIpc): slots[2][world][4] fp64 | flags[2][world] u64 | halo_flags[2] u64
+typedef P2PView P2P;
+}  // namespace pf2
+
 struct pf2_dist {
     pf2_ctx* ctx = nullptr;
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
+    // peer-memory backend (optional)
+    bool p2p = false;
+    void* arena = nullptr;
+    pf2::P2P view;
+    unsigned long long* epoch = nullptr;      // device: [0] allreduce epoch, [1] halo epoch
+    std::vector<void*> opened;
 };
 
 namespace pf2 {
@@ -124,11 +138,114 @@ dcg_update_kernel(int lo, int hi, const double* __restrict__ p, const double* __
     if (grid_sum_last<2>(v, partials, ticket) && threadIdx.x == 0) { st->red[0] = v[0]; st->red[1] = v[1]; }
 }
 
+// K2 with the {z.r, r.r} allreduce and the scalar tail fused into the last CTA (peer-memory backend)
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+p2p_update_kernel(int lo, int hi, const double* __restrict__ p, const double* __restrict__ y, const double* __restrict__ dvec,
+                  double* __restrict__ x, double* __restrict__ r, double* __restrict__ z, CgState* st, double* partials,
+                  unsigned int* ticket, const P2PView* p2p, unsigned long long* epoch_ctr) {
+    if (st->done) return;
+    const double alpha = st->rho / st->pAp;
+    double v[2] = { 0.0, 0.0 };
+    for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
+        x[i] = x[i] + alpha * p[i];
+        const double ri = r[i] + (-alpha) * y[i];
+        r[i] = ri;
+        v[1] += ri * ri;
+        if (MODE == 0) { v[0] += ri * ri; }
+        else { const double zi = ri / dvec[i]; z[i] = zi; v[0] += zi * ri; }
+    }
+    if (grid_sum_last<2>(v, partials, ticket)) {
+        __shared__ double sv[4];
+        if (threadIdx.x < 32) {
+            if (threadIdx.x == 0) { sv[0] = v[0]; sv[1] = v[1]; }
+            __syncwarp();
+            p2p_allreduce_warp(*p2p, epoch_ctr, sv, 2);
+            if (threadIdx.x == 0) {
+                const double zr = sv[0], rr = sv[1];
+                st->beta = zr / st->rho;
+                st->rho = zr;
+                st->rr = rr;
+                st->iter = st->iter + 1;
+                if (sqrt(rr) < st->eps * sqrt(st->bb)) st->done = 1;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 dcg_pupdate_kernel(int lo, int hi, const double* __restrict__ z, double* __restrict__ p, const CgState* __restrict__ st) {
     if (st->done) return;
     const double beta = st->beta;
     for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) p[i] = beta * p[i] + z[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Peer-memory collectives (NVLink / NVSwitch, no NCCL on the iteration path).
+//   allreduce of <= 4 fp64: one warp; lane r stores this rank's values into rank r's arena, fences, raises its flag there;
+//   then every lane waits for rank r's flag in the LOCAL arena and lane 0 sums the slots in rank order, so the result is
+//   bitwise identical on every rank.  Slots and flags are double-buffered by epoch parity: a rank cannot run two epochs
+//   ahead of a peer because finishing an epoch needs that peer's flag.
+// ---------------------------------------------------------------------------------------------------------------
+// allreduce of st->pAp after the SpMV (phase 0), of {bb, zr} after init (phase 1), of {zr, rr} + the scalar tail (phase 2)
+__global__ void p2p_cg_scalars_kernel(P2P P, unsigned long long* epoch_ctr, CgState* st, int phase, int maxit, double eps) {
+    if (phase != 1 && st->done) return;
+    __shared__ double v[4];
+    if (threadIdx.x == 0) {
+        if (phase == 0) { v[0] = st->pAp; }
+        else { v[0] = st->red[0]; v[1] = st->red[1]; }
+    }
+    __syncwarp();
+    p2p_allreduce_warp(P, epoch_ctr, v, phase == 0 ? 1 : 2);
+    if (threadIdx.x == 0) {
+        if (phase == 0) st->pAp = v[0];
+        else if (phase == 1) {
+            st->bb = v[0]; st->rr = v[0]; st->rho = v[1]; st->pAp = 0.0; st->beta = 0.0;
+            st->iter = 0; st->done = 0; st->maxit = maxit; st->eps = eps;
+        } else {
+            const double zr = v[0], rr = v[1];
+            st->beta = zr / st->rho;
+            st->rho = zr;
+            st->rr = rr;
+            st->iter = st->iter + 1;
+            if (sqrt(rr) < st->eps * sqrt(st->bb)) st->done = 1;
+        }
+    }
+}
+
+// p = beta p + z on the owned rows, with the halo exchange FUSED: boundary planes are stored straight into the neighbours'
+// ghost ranges over NVLink; the last CTA publishes the halo epoch to both neighbours and waits for theirs, so that the
+// next kernel on this stream (the SpMV) sees complete ghosts.  init = 1: p already holds z (first exchange after set-up).
+__global__ void __launch_bounds__(kThreads)
+p2p_pupdate_halo_kernel(int lo, int hi, const double* __restrict__ z, double* __restrict__ p, const CgState* __restrict__ st, int init,
+                        P2P P, int sendL, int cntL, int sendR, int cntR, unsigned long long* epoch_ctr, unsigned int* ticket) {
+    if (!init && st->done) return;
+    const double beta = init ? 0.0 : st->beta;
+    for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
+        const double v = init ? p[i] : beta * p[i] + z[i];
+        if (!init) p[i] = v;
+        if (P.left_p && i >= sendL && i < sendL + cntL) P.left_p[P.left_recv_off + (i - sendL)] = v;
+        if (P.right_p && i >= sendR && i < sendR + cntR) P.right_p[P.right_recv_off + (i - sendR)] = v;
+    }
+    __shared__ bool last;
+    __threadfence_system();                 // this CTA's remote stores are visible system-wide before the ticket
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned long long epoch = epoch_ctr[1] + 1;
+        // I am the RIGHT neighbour of rank-1 (slot 1 there) and the LEFT neighbour of rank+1 (slot 0 there)
+        if (P.rank > 0) *(volatile unsigned long long*)(P.halo_flags[P.rank - 1] + 1) = epoch;
+        if (P.rank < P.world - 1) *(volatile unsigned long long*)(P.halo_flags[P.rank + 1] + 0) = epoch;
+        volatile unsigned long long* mine = (volatile unsigned long long*)P.halo_flags[P.rank];
+        if (P.rank > 0) while (mine[0] < epoch) {}
+        if (P.rank < P.world - 1) while (mine[1] < epoch) {}
+        __threadfence_system();
+        epoch_ctr[1] = epoch;
+        *ticket = 0u;
+    }
 }
 
 // one node plane per side; ranges are contiguous in the local numbering
@@ -172,9 +289,17 @@ int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, d
     if (solver == PF2_SOLVER_CG) dcg_init_kernel<0><<<grid, kThreads, 0, s>>>(lo, hi, n, b, A->indptr, A->diagpos, A->data, A->dvec, x, A->r, A->z, A->p, A->st, c->red.partials, c->red.ticket);
     else dcg_init_kernel<1><<<grid, kThreads, 0, s>>>(lo, hi, n, b, A->indptr, A->diagpos, A->data, A->dvec, x, A->r, A->z, A->p, A->st, c->red.partials, c->red.ticket);
     PF2_LAUNCH_CHECK();
-    PF2_TRY(dist_allreduce(d, A->st->red, 2));
-    dcg_scalars_kernel<<<1, 1, 0, s>>>(A->st, 0, itrmax, eps);
-    PF2_TRY(dist_halo(d, A->p, A->halo));
+    const bool p2p = d->p2p && A->p2p_ready;
+    const int hgrid = std::min(c->grid_for(hi - lo, 2), c->sm_count * 4);
+    if (p2p) {
+        p2p_cg_scalars_kernel<<<1, 32, 0, s>>>(A->p2p_view, d->epoch, A->st, 1, itrmax, eps);
+        p2p_pupdate_halo_kernel<<<hgrid, kThreads, 0, s>>>(lo, hi, A->z, A->p, A->st, 1, A->p2p_view, A->halo[0], A->halo[2], A->halo[3], A->halo[5],
+                                                           d->epoch, c->red.ticket + 1);
+    } else {
+        PF2_TRY(dist_allreduce(d, A->st->red, 2));
+        dcg_scalars_kernel<<<1, 1, 0, s>>>(A->st, 0, itrmax, eps);
+        PF2_TRY(dist_halo(d, A->p, A->halo));
+    }
     c->launches += 2;
 
     const int chunk = 32;
@@ -190,13 +315,21 @@ int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, d
             if (sample) PF2_CUDA(cudaEventRecord(A->pev[slot][0], s));
             PF2_TRY(spmv_dot(A, A->p, A->y, A->st, &A->st->pAp));
             if (sample) { PF2_CUDA(cudaEventRecord(A->pev[slot][1], s)); A->pev_armed[slot] = true; }
-            PF2_TRY(dist_allreduce(d, &A->st->pAp, 1));
-            if (solver == PF2_SOLVER_CG) dcg_update_kernel<0><<<ugrid, kThreads, 0, s>>>(lo, hi, A->p, A->y, A->dvec, x, A->r, A->z, A->st, c->red.partials, c->red.ticket);
+            if (!p2p) PF2_TRY(dist_allreduce(d, &A->st->pAp, 1));      // peer-memory backend: fused into the SpMV's last CTA
+            if (p2p) {
+                if (solver == PF2_SOLVER_CG) p2p_update_kernel<0><<<ugrid, kThreads, 0, s>>>(lo, hi, A->p, A->y, A->dvec, x, A->r, A->z, A->st, c->red.partials, c->red.ticket, A->p2p_dev, d->epoch);
+                else p2p_update_kernel<1><<<ugrid, kThreads, 0, s>>>(lo, hi, A->p, A->y, A->dvec, x, A->r, A->z, A->st, c->red.partials, c->red.ticket, A->p2p_dev, d->epoch);
+            } else if (solver == PF2_SOLVER_CG) dcg_update_kernel<0><<<ugrid, kThreads, 0, s>>>(lo, hi, A->p, A->y, A->dvec, x, A->r, A->z, A->st, c->red.partials, c->red.ticket);
             else dcg_update_kernel<1><<<ugrid, kThreads, 0, s>>>(lo, hi, A->p, A->y, A->dvec, x, A->r, A->z, A->st, c->red.partials, c->red.ticket);
-            PF2_TRY(dist_allreduce(d, A->st->red, 2));
-            dcg_scalars_kernel<<<1, 1, 0, s>>>(A->st, 1, itrmax, eps);
-            dcg_pupdate_kernel<<<ugrid, kThreads, 0, s>>>(lo, hi, solver == PF2_SOLVER_CG ? A->r : A->z, A->p, A->st);
-            PF2_TRY(dist_halo(d, A->p, A->halo));
+            if (p2p) {
+                p2p_pupdate_halo_kernel<<<hgrid, kThreads, 0, s>>>(lo, hi, solver == PF2_SOLVER_CG ? A->r : A->z, A->p, A->st, 0, A->p2p_view,
+                                                                   A->halo[0], A->halo[2], A->halo[3], A->halo[5], d->epoch, c->red.ticket + 1);
+            } else {
+                PF2_TRY(dist_allreduce(d, A->st->red, 2));
+                dcg_scalars_kernel<<<1, 1, 0, s>>>(A->st, 1, itrmax, eps);
+                dcg_pupdate_kernel<<<ugrid, kThreads, 0, s>>>(lo, hi, solver == PF2_SOLVER_CG ? A->r : A->z, A->p, A->st);
+                PF2_TRY(dist_halo(d, A->p, A->halo));
+            }
             c->launches += 3;
         }
         PF2_LAUNCH_CHECK();
@@ -268,12 +401,91 @@ int pf2_dist_create(pf2_ctx* ctx, int rank, int nranks, const char id_bytes[128]
 int pf2_dist_destroy(pf2_dist* d) {
     if (!d) return PF2_OK;
     cudaStreamSynchronize(d->ctx->stream);
+    for (void* p : d->opened) cudaIpcCloseMemHandle(p);
+    if (d->arena) cudaFree(d->arena);
+    if (d->epoch) cudaFree(d->epoch);
     if (d->comm) nccl::CommDestroy(d->comm);
     delete d;
     return PF2_OK;
 }
 
 int pf2_dist_allreduce_sum(pf2_dist* d, double* dev, int count) { return dist_allreduce(d, dev, count); }
+
+// ---- peer-memory backend ------------------------------------------------------------------------------------------
+// export: this rank's IPC handles {arena (64 B), Krylov slab of A (64 B)} ; import: all ranks' handles + halo descriptors.
+static size_t arena_bytes(int world) { return sizeof(double) * 2 * world * 4 + sizeof(unsigned long long) * (2 * world + 2); }
+
+int pf2_csr_p2p_export(pf2_csr* A, char handles_out[128]) {
+    PF2_CHECK(A && A->dist, "call pf2_csr_set_partition first");
+    pf2_dist* d = A->dist;
+    pf2_ctx* c = A->ctx;
+    PF2_CUDA(cudaSetDevice(c->device));
+    PF2_TRY(ensure_workspace_pub(A));
+    if (!d->arena) {
+        PF2_CUDA(cudaMalloc(&d->arena, arena_bytes(d->nranks)));
+        PF2_CUDA(cudaMemset(d->arena, 0, arena_bytes(d->nranks)));
+        PF2_CUDA(cudaMalloc((void**)&d->epoch, 2 * sizeof(unsigned long long)));
+        PF2_CUDA(cudaMemset(d->epoch, 0, 2 * sizeof(unsigned long long)));
+    }
+    cudaIpcMemHandle_t h0, h1;
+    PF2_CUDA(cudaIpcGetMemHandle(&h0, d->arena));
+    PF2_CUDA(cudaIpcGetMemHandle(&h1, A->slab));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handles_out, &h0, 64);
+    memcpy(handles_out + 64, &h1, 64);
+    return PF2_OK;
+}
+
+// all_handles: world x 128 bytes (as exported); all_meta: world x 8 ints = each rank's {row halo descriptor[6], local rows, 0}
+int pf2_csr_p2p_import(pf2_csr* A, const char* all_handles, const int* all_halo) {
+    PF2_CHECK(A && A->dist && A->dist->arena && all_handles && all_halo, "export first");
+    pf2_dist* d = A->dist;
+    PF2_CHECK(d->nranks <= kMaxRanks, "peer-memory backend supports up to 8 ranks (one box)");
+    PF2_CUDA(cudaSetDevice(A->ctx->device));
+    const int world = d->nranks, me = d->rank;
+    P2P v;
+    memset(&v, 0, sizeof v);
+    v.rank = me; v.world = world;
+    const size_t np = (((size_t)A->rows) + 31) & ~(size_t)31;      // slab layout: r | p | z | y | dvec (solver.cu)
+    for (int r = 0; r < world; r++) {
+        void* base = nullptr;
+        if (r == me) base = d->arena;
+        else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, all_handles + (size_t)r * 128, 64);
+            PF2_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+            d->opened.push_back(base);
+        }
+        v.slots[r] = (double*)base;
+        v.flags[r] = (unsigned long long*)((char*)base + sizeof(double) * 2 * world * 4);
+        v.halo_flags[r] = v.flags[r] + 2 * world;
+    }
+    (void)np;
+    for (int side = 0; side < 2; side++) {
+        const int nb = side == 0 ? me - 1 : me + 1;
+        if (nb < 0 || nb >= world) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, all_handles + (size_t)nb * 128 + 64, 64);
+        void* base = nullptr;
+        PF2_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+        d->opened.push_back(base);
+        // the neighbour's p vector starts one padded vector into its slab; its row count is implied by its own padding,
+        // so the neighbour publishes the p offset through all_halo? -> no: p offset = np_nb doubles; np_nb is sent as halo[6]
+        const int* hn = all_halo + (size_t)nb * 8;
+        const long long np_nb = ((long long)hn[6] + 31) & ~31LL;
+        double* pvec = (double*)base + np_nb;
+        if (side == 0) { v.left_p = pvec; v.left_recv_off = hn[4]; }     // my left plane lands in their RIGHT ghost range (recvR_off)
+        else { v.right_p = pvec; v.right_recv_off = hn[1]; }             // my right plane lands in their LEFT ghost range (recvL_off)
+    }
+    A->p2p_view = v;
+    if (!A->p2p_dev) PF2_CUDA(cudaMalloc((void**)&A->p2p_dev, sizeof(P2PView)));
+    PF2_CUDA(cudaMemcpy(A->p2p_dev, &v, sizeof(P2PView), cudaMemcpyHostToDevice));
+    A->p2p_epoch = d->epoch;
+    A->p2p_ready = true;
+    d->p2p = true;
+    d->view = v;
+    return PF2_OK;
+}
 
 int pf2_dist_halo(pf2_dist* d, double* vec_dev, const int halo[6]) { return dist_halo(d, vec_dev, halo); }
 

@@ -12,6 +12,7 @@
 // sell_entries >= nnz (ratio reported as `sell_fill`).
 #pragma once
 #include "types.cuh"
+#include "p2p.cuh"
 
 namespace pf2 {
 
@@ -69,7 +70,7 @@ template <bool DOT>
 __global__ void __launch_bounds__(kThreads)
 spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* __restrict__ sell_idx, const double* __restrict__ sell_val,
                  const double* __restrict__ x, double* __restrict__ y, const CgState* __restrict__ st, double* dot_out,
-                 double* partials, unsigned int* ticket, int dot_lo, int dot_hi) {
+                 double* partials, unsigned int* ticket, int dot_lo, int dot_hi, const P2PView* p2p, unsigned long long* p2p_epoch) {
     if (DOT && st != nullptr && st->done) return;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -100,7 +101,7 @@ spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* _
     }
     if (DOT) {
         double vsum[1] = { dot };
-        if (grid_sum_last<1>(vsum, partials, ticket) && threadIdx.x == 0) *dot_out = vsum[0];
+        if (grid_sum_last<1>(vsum, partials, ticket)) finish_dot(vsum[0], dot_out, p2p, p2p_epoch);
     }
 }
 

@@ -14,6 +14,7 @@
 // multiple of 4 entries long; the CSR arrays are allocated with 8 spare entries for the over-read.
 #pragma once
 #include "types.cuh"
+#include "p2p.cuh"
 
 namespace pf2 {
 
@@ -74,7 +75,7 @@ template <int G, bool DOT>
 __global__ void __launch_bounds__(kTmaThreads, 4)
 spmv_tma_kernel(int rows, const long long* __restrict__ indptr, const int* __restrict__ indices, const double* __restrict__ data,
                 const double* __restrict__ x, double* __restrict__ y, const CgState* __restrict__ st, double* dot_out,
-                double* partials, unsigned int* ticket, int cap, int stages, int dot_lo, int dot_hi) {
+                double* partials, unsigned int* ticket, int cap, int stages, int dot_lo, int dot_hi, const P2PView* p2p, unsigned long long* p2p_epoch) {
     if (DOT && st != nullptr && st->done) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const size_t stage_bytes = tma_stage_bytes(cap);
@@ -176,9 +177,12 @@ spmv_tma_kernel(int rows, const long long* __restrict__ indptr, const int* __res
             if (tid == 0) {
                 double v = 0.0;
                 for (int w = 0; w < 8; w++) v += sm.red[w];
-                *dot_out = v;
+                sm.red[0] = v;
                 *ticket = 0u;
             }
+            consumer_sync();
+            if (p2p == nullptr) { if (tid == 0) *dot_out = sm.red[0]; }
+            else if (tid < 32) { p2p_allreduce_warp(*p2p, p2p_epoch, sm.red, 1); if (tid == 0) *dot_out = sm.red[0]; }
         }
     }
 }

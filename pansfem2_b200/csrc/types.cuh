@@ -37,6 +37,18 @@ struct CgState {
 }  // namespace pf2
 
 struct pf2_dist;
+namespace pf2 {
+constexpr int kMaxRanksT = 8;
+struct P2PView {          // must match pf2::P2P in dist.cu (kept POD here so that pf2_csr can embed it)
+    int rank, world;
+    double* slots[kMaxRanksT];
+    unsigned long long* flags[kMaxRanksT];
+    unsigned long long* halo_flags[kMaxRanksT];
+    double* left_p;
+    double* right_p;
+    int left_recv_off, right_recv_off;
+};
+}  // namespace pf2
 
 struct pf2_csr {
     pf2_ctx* ctx = nullptr;
@@ -46,6 +58,10 @@ struct pf2_csr {
     int own_lo = 0, own_hi = 0;
     pf2_dist* dist = nullptr;
     int halo[6] = { 0, 0, 0, 0, 0, 0 };   // sendL_off, recvL_off, cntL, sendR_off, recvR_off, cntR (row offsets)
+    bool p2p_ready = false;               // peer-memory backend: neighbours' p vectors and all arenas are mapped
+    pf2::P2PView p2p_view;
+    pf2::P2PView* p2p_dev = nullptr;      // device copy handed to the fused kernels (nullptr: single GPU or NCCL backend)
+    unsigned long long* p2p_epoch = nullptr;
     long long nnz = 0;
     long long* indptr = nullptr;   // rows+1 (int64: config 5 has nnz > 2^31)
     int* indices = nullptr;        // nnz, sorted within a row

@@ -34,6 +34,8 @@ A = capi.Csr.pattern(ctx, mesh, dm)
 rho = ctx.array(rho_g[S.le0 * plane_e:S.le1 * plane_e])
 A.assemble(mesh, dm, L.eq, (L.E0, L.E1, L.poisson, L.penal, L.thickness), L.loads, rho=rho)
 D.set_partition(A, S.own_rows, S.row_halo)
+if os.environ.get('PF2_P2P', '1') != '0':
+    D.enable_p2p(A, S.row_halo)
 x = ctx.empty(A.rows)
 for rep in range(2):
     ctx.sync(); dist.barrier()
