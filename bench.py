@@ -326,7 +326,9 @@ def main():
                                   "update_ms": kstats["update_ms"], "pupdate_ms": kstats["pupdate_ms"]}}
     out = dict(base, value=value, ms_per_step=ms / args.steps,
                config={"workload": desc, "elements": nelem_global, "dof_local": S.A.rows, "nnz_local": S.A.nnz,
-                       "parallelism": "1 GPU" if world == 1 else f"{world} x-slabs (row-block partition, NCCL halo exchange + allreduce)",
+                       "parallelism": "1 GPU" if world == 1 else (f"{world} x-slabs (row-block partition; PCG halo + allreduce fused into the kernels over NVLink peer memory, "
+                                                                    "NCCL for the per-design-iteration exchanges)" if os.environ.get("PF2_P2P", "1") != "0"
+                                                                    else f"{world} x-slabs (row-block partition, NCCL halo exchange + allreduce)"),
                        "l2": "working set (CSR values+indices %.0f MB) exceeds the 126 MB L2; no flush needed" % (12 * S.A.nnz / 1e6),
                        "cg_iters_per_step": cg_iters, "solver": "ScalingCG eps=1e-10 x0=0"},
                e2e={"value": e2e_value, "unit": base["unit"], "h2d_bytes_per_step": int(8 * nelem), "d2h_bytes_per_step": int(16 * nelem),
