@@ -135,8 +135,8 @@ def cpu_reference_sample(P, cg_iters_per_step, opt_steps_hint=25, budget_s=25.0)
     kind = "reference" if use_ref else "port"
     cores = os.cpu_count() or 1
     t_begin = time.time()
-    # strip: same problem family at reduced size (~400 k elements: ~10-20 s of reference CPU work in total)
-    nel_target = 400000
+    # strip: same problem family at reduced size (~1.2 M elements: 10-30 s of reference CPU work in total)
+    nel_target = 1200000
     scale = (P.nelem / nel_target) ** (1.0 / len(P.grid))
     dims = [max(4, int(round(g / scale / 2)) * 2) for g in P.grid]
     if P.eq == problems.EQ_PLANESTRAIN:

@@ -197,9 +197,26 @@ static int sell_build(pf2_csr* A) {
     PF2_CUDA(cudaFree(tmp));
     PF2_TRY(dev_alloc(&A->sell_idx, (size_t)A->sell_entries));
     PF2_TRY(dev_alloc(&A->sell_val, (size_t)A->sell_entries));
-    sell_fill_kernel<<<c->grid_for(A->rows), kThreads, 0, c->stream>>>(A->rows, A->indptr, A->indices, A->sell_ptr, A->sell_idx);
+    int* d_md = nullptr;
+    PF2_TRY(dev_alloc(&d_md, 1));
+    PF2_CUDA(cudaMemsetAsync(d_md, 0, sizeof(int), c->stream));
+    sell_fill_kernel<<<c->grid_for(A->rows), kThreads, 0, c->stream>>>(A->rows, A->indptr, A->indices, A->sell_ptr, A->sell_idx, d_md);
     PF2_LAUNCH_CHECK();
-    c->launches += 4;
+    int md = 0;
+    PF2_CUDA(cudaMemcpyAsync(&md, d_md, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PF2_CUDA(cudaStreamSynchronize(c->stream));
+    PF2_CUDA(cudaFree(d_md));
+    A->sell_max_delta = md;
+    if (md <= 32767) {
+        // banded matrix: keep the 2-byte delta stream and drop the 4-byte one (the absolute columns are recoverable)
+        PF2_TRY(dev_alloc(&A->sell_d16, (size_t)A->sell_entries));
+        sell_delta16_kernel<<<std::min((nslices + 7) / 8, c->sm_count * 16), kThreads, 0, c->stream>>>(A->rows, A->sell_entries, A->sell_ptr, A->sell_idx, A->sell_d16);
+        PF2_LAUNCH_CHECK();
+        PF2_CUDA(cudaStreamSynchronize(c->stream));
+        PF2_CUDA(cudaFree(A->sell_idx));
+        A->sell_idx = nullptr;
+    }
+    c->launches += 5;
     A->sell_values_valid = false;
     return PF2_OK;
 }
@@ -209,7 +226,7 @@ int sell_refresh(pf2_csr* A) {
     pf2_ctx* c = A->ctx;
     const int nslices = (A->rows + kSellC - 1) / kSellC;
     sell_values_kernel<<<std::min((nslices + 7) / 8, c->sm_count * 16), kThreads, 0, c->stream>>>(A->rows, A->indptr, A->data, A->sell_ptr, A->sell_val);
-    sell_pad_tail_kernel<<<1, kThreads, 0, c->stream>>>(A->rows, nslices, A->sell_ptr, A->sell_idx, A->sell_val);
+    sell_pad_tail_kernel<<<1, kThreads, 0, c->stream>>>(A->rows, nslices, A->sell_ptr, A->sell_idx, A->sell_val);   // sell_idx may be null (delta form)
     PF2_LAUNCH_CHECK();
     c->launches += 2;
     A->sell_values_valid = true;
@@ -222,9 +239,15 @@ static int launch_sell(pf2_csr* A, const double* x, double* y, const CgState* st
     if (!A->sell_values_valid) PF2_TRY(sell_refresh(A));
     const int nslices = (A->rows + kSellC - 1) / kSellC;
     const int nb = (nslices + (kThreads / 32) - 1) / (kThreads / 32);
-    const int grid = std::max(1, std::min(nb, c->wave_grid((const void*)spmv_sell_kernel<DOT>, kThreads)));
-    spmv_sell_kernel<DOT><<<grid, kThreads, 0, c->stream>>>(A->rows, A->sell_ptr, A->sell_idx, A->sell_val, x, y, st, dot_out,
-                                                          c->red.partials, c->red.ticket, A->own_lo, A->own_hi, A->p2p_dev, A->p2p_epoch);
+    if (A->sell_d16) {
+        const int grid = std::max(1, std::min(nb, c->wave_grid((const void*)spmv_sell_kernel<DOT, short>, kThreads)));
+        spmv_sell_kernel<DOT, short><<<grid, kThreads, 0, c->stream>>>(A->rows, A->sell_ptr, A->sell_d16, A->sell_val, x, y, st, dot_out,
+                                                                     c->red.partials, c->red.ticket, A->own_lo, A->own_hi, A->p2p_dev, A->p2p_epoch);
+    } else {
+        const int grid = std::max(1, std::min(nb, c->wave_grid((const void*)spmv_sell_kernel<DOT, int>, kThreads)));
+        spmv_sell_kernel<DOT, int><<<grid, kThreads, 0, c->stream>>>(A->rows, A->sell_ptr, A->sell_idx, A->sell_val, x, y, st, dot_out,
+                                                                   c->red.partials, c->red.ticket, A->own_lo, A->own_hi, A->p2p_dev, A->p2p_epoch);
+    }
     return PF2_OK;
 }
 
@@ -338,7 +361,7 @@ int pf2_csr_destroy(pf2_csr* A) {
     if (!A) return PF2_OK;
     cudaSetDevice(A->ctx->device);
     cudaStreamSynchronize(A->ctx->stream);
-    void* ptrs[] = { A->indptr, A->indices, A->data, A->F, A->diagpos, A->bmap, A->slab, A->xw, A->bw, A->st, A->sell_ptr, A->sell_idx, A->sell_val, A->p2p_dev,
+    void* ptrs[] = { A->indptr, A->indices, A->data, A->F, A->diagpos, A->bmap, A->slab, A->xw, A->bw, A->st, A->sell_ptr, A->sell_idx, A->sell_d16, A->sell_val, A->p2p_dev,
                      A->ilu, A->level_rows, A->level_rows_u };
     for (void* p : ptrs) if (p) cudaFree(p);
     if (A->h_st) cudaFreeHost(A->h_st);

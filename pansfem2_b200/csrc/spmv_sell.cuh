@@ -29,14 +29,37 @@ __global__ void sell_slice_len_kernel(int rows, int nslices, const long long* __
 
 // fill indices (pattern) and the CSR->SELL position of every stored entry
 __global__ void sell_fill_kernel(int rows, const long long* __restrict__ indptr, const int* __restrict__ indices,
-                                 const long long* __restrict__ slice_ptr, int* __restrict__ sell_idx) {
+                                 const long long* __restrict__ slice_ptr, int* __restrict__ sell_idx, int* max_delta) {
+    int md = 0;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
         const int s = r / kSellC, l = r % kSellC;
         const long long base = slice_ptr[s];
         const int width = (int)((slice_ptr[s + 1] - base) / kSellC);
         const long long b = indptr[r];
         const int len = (int)(indptr[r + 1] - b);
-        for (int k = 0; k < width; k++) sell_idx[base + (long long)k * kSellC + l] = (k < len) ? indices[b + k] : r;
+        for (int k = 0; k < width; k++) {
+            const int c = (k < len) ? indices[b + k] : r;
+            sell_idx[base + (long long)k * kSellC + l] = c;
+            md = max(md, abs(c - r));
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) md = max(md, __shfl_xor_sync(0xffffffffu, md, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(max_delta, md);
+}
+// 16-bit column deltas (col - row): FEM matrices are banded, so the index stream shrinks from 4 to 2 bytes per nonzero
+__global__ void sell_delta16_kernel(int rows, long long entries, const long long* __restrict__ slice_ptr, const int* __restrict__ sell_idx,
+                                    short* __restrict__ sell_d16) {
+    const int nslices = (rows + kSellC - 1) / kSellC;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int s = warp; s < nslices; s += nwarps) {
+        const long long base = slice_ptr[s];
+        const int width = (int)((slice_ptr[s + 1] - base) / kSellC);
+        const int r = s * kSellC + lane;
+        for (int k = 0; k < width; k++) {
+            const long long pos = base + (long long)k * kSellC + lane;
+            sell_d16[pos] = (r < rows) ? (short)(sell_idx[pos] - r) : (short)0;
+        }
     }
 }
 // padding lanes of the last slice (rows beyond `rows`)
@@ -46,7 +69,7 @@ __global__ void sell_pad_tail_kernel(int rows, int nslices, const long long* __r
     const int width = (int)((slice_ptr[s + 1] - base) / kSellC);
     for (int t = threadIdx.x; t < width * kSellC; t += blockDim.x) {
         const int l = t % kSellC;
-        if (s * kSellC + l >= rows) { sell_idx[base + t] = 0; sell_val[base + t] = 0.0; }
+        if (s * kSellC + l >= rows) { if (sell_idx) sell_idx[base + t] = 0; sell_val[base + t] = 0.0; }
     }
 }
 __global__ void sell_values_kernel(int rows, const long long* __restrict__ indptr, const double* __restrict__ data,
@@ -66,9 +89,10 @@ __global__ void sell_values_kernel(int rows, const long long* __restrict__ indpt
     }
 }
 
-template <bool DOT>
+// IDX = int: absolute columns (4 B/nnz); IDX = short: column - row deltas (2 B/nnz)
+template <bool DOT, class IDX>
 __global__ void __launch_bounds__(kThreads)
-spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* __restrict__ sell_idx, const double* __restrict__ sell_val,
+spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const IDX* __restrict__ sell_idx, const double* __restrict__ sell_val,
                  const double* __restrict__ x, double* __restrict__ y, const CgState* __restrict__ st, double* dot_out,
                  double* partials, unsigned int* ticket, int dot_lo, int dot_hi, const P2PView* p2p, unsigned long long* p2p_epoch) {
     if (DOT && st != nullptr && st->done) return;
@@ -81,19 +105,20 @@ spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* _
         const long long base = slice_ptr[s];
         const int width = (int)((slice_ptr[s + 1] - base) / kSellC);
         const double* v = sell_val + base + lane;
-        const int* c = sell_idx + base + lane;
+        const IDX* c = sell_idx + base + lane;
+        const int r = s * kSellC + lane;
+        const int off = (sizeof(IDX) == 2) ? min(r, rows - 1) : 0;     // deltas are relative to the row (padding lanes: delta 0)
         double acc = 0.0;
         int k = 0;
         for (; k + 6 <= width; k += 6) {
             double vv[6];
             int cc[6];
 #pragma unroll
-            for (int u = 0; u < 6; u++) { vv[u] = __ldcs(v + (k + u) * kSellC); cc[u] = __ldcs(c + (k + u) * kSellC); }
+            for (int u = 0; u < 6; u++) { vv[u] = __ldcs(v + (k + u) * kSellC); cc[u] = off + (int)__ldcs(c + (k + u) * kSellC); }
 #pragma unroll
             for (int u = 0; u < 6; u++) acc += vv[u] * __ldg(x + cc[u]);
         }
-        for (; k < width; k++) acc += __ldcs(v + k * kSellC) * __ldg(x + __ldcs(c + k * kSellC));
-        const int r = s * kSellC + lane;
+        for (; k < width; k++) acc += __ldcs(v + k * kSellC) * __ldg(x + off + (int)__ldcs(c + k * kSellC));
         if (r < rows) {
             y[r] = acc;
             if (DOT && r >= dot_lo && r < dot_hi) dot += acc * x[r];
