@@ -38,10 +38,11 @@ extern "C" {
 enum { PF2_EQ_PLANESTRAIN = 0, PF2_EQ_SOLID = 1, PF2_EQ_HEAT = 2 };
 /* solver selection: CG (CG.h:124), ScalingCG (CG.h:420), ILU0CG (CG.h:320) */
 enum { PF2_SOLVER_CG = 0, PF2_SOLVER_SCALINGCG = 1, PF2_SOLVER_ILU0CG = 2 };
-/* DensityFilter (DensityFilter.h:45-71), HeavisideFilter (HeavisideFilter.h:61-99) */
-enum { PF2_FILTER_DENSITY = 0, PF2_FILTER_HEAVISIDE = 1 };
-/* OC (OC.h:78), MMA (MMA.h:117) */
-enum { PF2_OPT_OC = 0, PF2_OPT_MMA = 1 };
+/* DensityFilter (DensityFilter.h:45-71), HeavisideFilter (HeavisideFilter.h:61-99),
+ * SensitivityFilter / SensitivityFilter2 (SensitivityFilter.h:44-55, 88-99; sensitivities only) */
+enum { PF2_FILTER_DENSITY = 0, PF2_FILTER_HEAVISIDE = 1, PF2_FILTER_SENS_SIGMUND = 2, PF2_FILTER_SENS_BORRVALL = 3 };
+/* OC (OC.h:78), MMA (MMA.h:117), CONLIN (CONLIN.h:89) */
+enum { PF2_OPT_OC = 0, PF2_OPT_MMA = 1, PF2_OPT_CONLIN = 2 };
 
 typedef struct pf2_ctx pf2_ctx;
 typedef struct pf2_mesh pf2_mesh;
@@ -192,9 +193,15 @@ int pf2_mma_is_convergence(pf2_mma* mma, double f, int* converged);
 int pf2_mma_update(pf2_mma* mma, double* x_dev, double f, const double* dfdx_dev, const double* g_host,
                    const double* dgdx_dev, int* newton_steps_out);
 
+/* ---- CONLIN (CONLIN.h:18-26): a pf2_mma handle in CONLIN mode; update / convergence through pf2_mma_update / _is_convergence */
+int pf2_conlin_create(pf2_ctx* ctx, int n, int m, double a0, const double* a_host, const double* c_host,
+                      const double* d_host, const double* xmin_host, const double* xmax_host, pf2_mma** out);
+int pf2_conlin_set_parameters(pf2_mma* conlin, double move, double epsvalue);
+
 /* ---- the device-resident design loop (sample_optimize_density_{oc,mma}.cpp:83-208) ------------------------- */
 /* params[12] = {E0,E1,poisson,p,weightlimit,scale0,scale1,thickness,beta0,beta_period,cg_itrmax,cg_eps}
- * optp: OC {iota,lmin,lmax,leps,move} or MMA {raa0,albefa,move,asyinit,asydecr,asyincr,epsvalue,a0,a,c,d,xmin,xmax} */
+ * optp: OC {iota,lmin,lmax,leps,move} | MMA {raa0,albefa,move,asyinit,asydecr,asyincr,epsvalue,a0,a,c,d,xmin,xmax}
+ *       | CONLIN {move,epsvalue,a0,a,c,d,xmin,xmax} */
 int pf2_simp_create(pf2_ctx* ctx, pf2_mesh* mesh, pf2_dofmap* map, pf2_csr* A, pf2_filter* filter, int eq, int opt_kind,
                     const double* optp, const double params[12], int nload, const int* load_node_host,
                     const int* load_dof_host, const double* load_val_host, pf2_simp** out);

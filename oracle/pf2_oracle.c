@@ -23,7 +23,7 @@
 
 enum { EQ_PLANESTRAIN = 0, EQ_SOLID = 1, EQ_HEAT = 2 };
 enum { FILTER_DENSITY = 0, FILTER_HEAVISIDE = 1 };
-enum { OPT_OC = 0, OPT_MMA = 1 };
+enum { OPT_OC = 0, OPT_MMA = 1, OPT_CONLIN = 2 };
 
 static double now_s(void) {
     struct timespec ts;
@@ -485,6 +485,19 @@ void orc_filter_sens(int kind, int n, const long long* rowptr, const int* nbr, c
     free(dr);
 }
 
+/* SensitivityFilter (Sigmund) src/Optimize/Filter/SensitivityFilter.h:44-55 ; SensitivityFilter2 (Borrvall) :88-99 */
+void orc_sensitivity_filter(int kind, int n, const long long* rowptr, const int* nbr, const double* w, const double* s,
+                            const double* dfds_in, double* out) {
+    for (int i = 0; i < n; i++) {
+        double acc = 0.0, wsum = 0.0;
+        for (long long j = rowptr[i]; j < rowptr[i + 1]; j++) {
+            acc += w[j] * s[nbr[j]] * dfds_in[nbr[j]];
+            wsum += (kind == 2) ? w[j] : w[j] * s[nbr[j]];
+        }
+        out[i] = (kind == 2) ? acc / (wsum * s[i]) : acc / wsum;
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------------------
  * OC::UpdateVariables  src/Optimize/Solver/OC.h:78-107, constraint functor of sample_optimize_density_oc.cpp:198-207
  * (filter + volume).  xk updated in place; returns the number of bisection steps; *lambda_out = last lambda tried.
@@ -528,6 +541,7 @@ typedef struct {
     double a0, *a, *c, *d, *xmin, *xmax, *xkm1, *xkm2, *L, *U;
     double raa0, albefa, move, asyinit, asydecr, asyincr;
     int newton_steps, halvings;
+    int conlin;     /* 1: CONLIN<T> (src/Optimize/Solver/CONLIN.h:89-373): p*x + q/x instead of p/(U-x) + q/(x-L), no asymptotes */
 } orc_mma;
 
 orc_mma* orc_mma_create(int n, int m, double a0, const double* a, const double* c, const double* d, const double* xmin, const double* xmax) {
@@ -548,6 +562,8 @@ void orc_mma_free(orc_mma* M) {
 void orc_mma_setparameters(orc_mma* M, double raa0, double albefa, double move, double asyinit, double asydecr, double asyincr) {
     M->raa0 = raa0; M->albefa = albefa; M->move = move; M->asyinit = asyinit; M->asydecr = asydecr; M->asyincr = asyincr;
 }
+/* CONLIN ctor default move = 0.5 (CONLIN.h:66), SetParameters(move, epsvalue) (:71-74) */
+void orc_mma_set_conlin(orc_mma* M, double move) { M->conlin = 1; M->move = move; }
 void orc_mma_stats(const orc_mma* M, int* newton, int* halvings) { *newton = M->newton_steps; *halvings = M->halvings; }
 
 static void solvels(int N, double* A, double* b, double* x) {    /* MMA.h:465-509, A row-major N x N, destroyed */
@@ -571,6 +587,11 @@ static void solvels(int N, double* A, double* b, double* x) {    /* MMA.h:465-50
     }
 }
 
+/* the separable convex approximation and its derivatives: MMA (MMA.h:211-233) | CONLIN (CONLIN.h:160-172) */
+#define PHI(pv, qv, xv, j)  (M->conlin ? (pv) * (xv) + (qv) / (xv) : (pv) / (M->U[j] - (xv)) + (qv) / ((xv) - M->L[j]))
+#define DPHI(pv, qv, xv, j) (M->conlin ? (pv) - (qv) / pow((xv), 2.0) : (pv) / pow(M->U[j] - (xv), 2.0) - (qv) / pow((xv) - M->L[j], 2.0))
+#define D2PHI(pv, qv, xv, j) (M->conlin ? 2.0 * (qv) / pow((xv), 3.0) : 2.0 * (pv) / pow(M->U[j] - (xv), 3.0) + 2.0 * (qv) / pow((xv) - M->L[j], 3.0))
+
 static double kktnorm(const orc_mma* M, const double* x, const double* y, double z, const double* lam, const double* gsi,
                       const double* ita, const double* mu, double zeta, const double* s, double eps,
                       const double* p, const double* q, const double* p0, const double* q0, const double* alpha,
@@ -584,11 +605,11 @@ static double kktnorm(const orc_mma* M, const double* x, const double* y, double
         for (int i = 0; i < m; i++) {
             pl[j] += lam[i] * p[(size_t)i * n + j];
             ql[j] += lam[i] * q[(size_t)i * n + j];
-            g[i] += p[(size_t)i * n + j] / (M->U[j] - x[j]) + q[(size_t)i * n + j] / (x[j] - M->L[j]);
+            g[i] += PHI(p[(size_t)i * n + j], q[(size_t)i * n + j], x[j], j);
         }
     }
     for (int j = 0; j < n; j++) {
-        norm += pow(pl[j] / pow(M->U[j] - x[j], 2.0) - ql[j] / pow(x[j] - M->L[j], 2.0) - gsi[j] + ita[j], 2.0);
+        norm += pow(DPHI(pl[j], ql[j], x[j], j) - gsi[j] + ita[j], 2.0);
         norm += pow(gsi[j] * (x[j] - alpha[j]) - eps, 2.0);
         norm += pow(ita[j] * (beta[j] - x[j]) - eps, 2.0);
     }
@@ -612,8 +633,10 @@ static double min2(double a, double b) { return b < a ? b : a; }
 void orc_mma_update(orc_mma* M, double* xk, const double* dfdx, const double* gval, const double* dgdx /* m x n */) {
     const int n = M->n, m = M->m;
     double *L = M->L, *U = M->U;
-    /* asymptotes MMA.h:119-142 */
-    if (M->k < 2) {
+    /* asymptotes MMA.h:119-142 (CONLIN has none) */
+    if (M->conlin) {
+        /* nothing */
+    } else if (M->k < 2) {
         for (int j = 0; j < n; j++) {
             double w = M->xmax[j] - M->xmin[j];
             L[j] = xk[j] - M->asyinit * w; U[j] = xk[j] + M->asyinit * w;
@@ -638,9 +661,16 @@ void orc_mma_update(orc_mma* M, double* xk, const double* dfdx, const double* gv
     VEC(alpha, n); VEC(beta, n); VEC(p0, n); VEC(q0, n); VEC(p, (size_t)m * n); VEC(q, (size_t)m * n); VEC(b, m);
     for (int j = 0; j < n; j++) {   /* MMA.h:145-160 */
         double w = M->xmax[j] - M->xmin[j];
+        double dp = max2(dfdx[j], 0.0), dm = max2(-dfdx[j], 0.0);
+        if (M->conlin) {        /* CONLIN.h:92-108 */
+            alpha[j] = max2(M->xmin[j], xk[j] - M->move * w);
+            beta[j] = min2(M->xmax[j], xk[j] + M->move * w);
+            p0[j] = dp;
+            q0[j] = dm * pow(xk[j], 2.0);
+            continue;
+        }
         alpha[j] = max2(max2(M->xmin[j], L[j] + M->albefa * (xk[j] - L[j])), xk[j] - M->move * w);
         beta[j] = min2(min2(M->xmax[j], U[j] - M->albefa * (U[j] - xk[j])), xk[j] + M->move * w);
-        double dp = max2(dfdx[j], 0.0), dm = max2(-dfdx[j], 0.0);
         p0[j] = pow(U[j] - xk[j], 2.0) * (1.001 * dp + 0.001 * dm + M->raa0 / w);
         q0[j] = pow(xk[j] - L[j], 2.0) * (0.001 * dp + 1.001 * dm + M->raa0 / w);
     }
@@ -649,6 +679,12 @@ void orc_mma_update(orc_mma* M, double* xk, const double* dfdx, const double* gv
         for (int j = 0; j < n; j++) {
             double w = M->xmax[j] - M->xmin[j];
             double dp = max2(dgdx[(size_t)i * n + j], 0.0), dm = max2(-dgdx[(size_t)i * n + j], 0.0);
+            if (M->conlin) {    /* CONLIN.h:114-122 */
+                p[(size_t)i * n + j] = dp;
+                q[(size_t)i * n + j] = dm * pow(xk[j], 2.0);
+                b[i] += p[(size_t)i * n + j] * xk[j] + q[(size_t)i * n + j] / xk[j];
+                continue;
+            }
             p[(size_t)i * n + j] = pow(U[j] - xk[j], 2.0) * (1.001 * dp + 0.001 * dm + M->raa0 / w);
             q[(size_t)i * n + j] = pow(xk[j] - L[j], 2.0) * (0.001 * dp + 1.001 * dm + M->raa0 / w);
             b[i] += p[(size_t)i * n + j] / (U[j] - xk[j]) + q[(size_t)i * n + j] / (xk[j] - L[j]);
@@ -676,10 +712,10 @@ void orc_mma_update(orc_mma* M, double* xk, const double* dfdx, const double* gv
             for (int i = 0; i < m; i++) { pl[j] += lam[i] * p[(size_t)i * n + j]; ql[j] += lam[i] * q[(size_t)i * n + j]; }
         }
         for (int i = 0; i < m; i++) for (int j = 0; j < n; j++)
-            G[(size_t)i * n + j] = p[(size_t)i * n + j] / pow(U[j] - x[j], 2.0) - q[(size_t)i * n + j] / pow(x[j] - L[j], 2.0);
+            G[(size_t)i * n + j] = DPHI(p[(size_t)i * n + j], q[(size_t)i * n + j], x[j], j);
         for (int j = 0; j < n; j++) {
-            Dx[j] = 2.0 * pl[j] / pow(U[j] - x[j], 3.0) + 2.0 * ql[j] / pow(x[j] - L[j], 3.0) + gsi[j] / (x[j] - alpha[j]) + ita[j] / (beta[j] - x[j]);
-            dtx[j] = pl[j] / pow(U[j] - x[j], 2.0) - ql[j] / pow(x[j] - L[j], 2.0) - eps / (x[j] - alpha[j]) + eps / (beta[j] - x[j]);
+            Dx[j] = D2PHI(pl[j], ql[j], x[j], j) + gsi[j] / (x[j] - alpha[j]) + ita[j] / (beta[j] - x[j]);
+            dtx[j] = DPHI(pl[j], ql[j], x[j], j) - eps / (x[j] - alpha[j]) + eps / (beta[j] - x[j]);
         }
         double la = 0.0;
         for (int i = 0; i < m; i++) {
@@ -691,7 +727,7 @@ void orc_mma_update(orc_mma* M, double* xk, const double* dfdx, const double* gv
         double dtz = M->a0 - eps / z - la;
         for (int i = 0; i < m; i++) {
             dtlam[i] = -M->a[i] * z - y[i] - b[i] + eps / lam[i];
-            for (int j = 0; j < n; j++) dtlam[i] += p[(size_t)i * n + j] / (U[j] - x[j]) + q[(size_t)i * n + j] / (x[j] - L[j]);
+            for (int j = 0; j < n; j++) dtlam[i] += PHI(p[(size_t)i * n + j], q[(size_t)i * n + j], x[j], j);
             Dlamy[i] = Dlam[i] + 1.0 / Dy[i];
             dtlamy[i] = dtlam[i] + dty[i] / Dy[i];
         }
@@ -866,6 +902,13 @@ int orc_simp_run(int eq, int nnode, const double* coords, int nelem, const int* 
         mma = orc_mma_create(nelem, 1, optp[7], &optp[8], &optp[9], &optp[10], xmin, xmax);
         orc_mma_setparameters(mma, optp[0], optp[1], optp[2], optp[3], optp[4], optp[5]);
         epsvalue = optp[6];
+        free(xmin); free(xmax);
+    } else if (opt_kind == OPT_CONLIN) {      /* sample_optimize_density_CONLIN.cpp:80-85 */
+        double* xmin = (double*)malloc(sizeof(double) * nelem), *xmax = (double*)malloc(sizeof(double) * nelem);
+        for (int i = 0; i < nelem; i++) { xmin[i] = optp[6]; xmax[i] = optp[7]; }
+        mma = orc_mma_create(nelem, 1, optp[2], &optp[3], &optp[4], &optp[5], xmin, xmax);
+        orc_mma_set_conlin(mma, optp[0]);
+        epsvalue = optp[1];
         free(xmin); free(xmax);
     }
     if (phase) memset(phase, 0, sizeof(double) * 8);

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libpf2oracle.so")
 
 EQ_PLANESTRAIN, EQ_SOLID, EQ_HEAT = 0, 1, 2
 FILTER_DENSITY, FILTER_HEAVISIDE = 0, 1
-OPT_OC, OPT_MMA = 0, 1
+OPT_OC, OPT_MMA, OPT_CONLIN = 0, 1, 2
 NDOF = {EQ_PLANESTRAIN: 2, EQ_SOLID: 3, EQ_HEAT: 1}
 NPE = {EQ_PLANESTRAIN: 4, EQ_SOLID: 8, EQ_HEAT: 4}
 
@@ -204,6 +204,9 @@ class MMA:
     def set_parameters(self, raa0, albefa, move, asyinit, asydecr, asyincr, epsvalue=None):
         lib().orc_mma_setparameters(self.h, *[C.c_double(v) for v in (raa0, albefa, move, asyinit, asydecr, asyincr)])
 
+    def set_conlin(self, move):
+        lib().orc_mma_set_conlin(self.h, C.c_double(move))
+
     def update(self, x, dfdx, g, dgdx):
         x = _f64(x).copy()
         dfdx, g, dgdx = _f64(dfdx), _f64(g), _f64(dgdx)
@@ -214,6 +217,15 @@ class MMA:
         a, b = C.c_int(0), C.c_int(0)
         lib().orc_mma_stats(self.h, C.byref(a), C.byref(b))
         return a.value, b.value
+
+
+def sensitivity_filter(kind, nbrs, s, dfds):
+    rowptr, nbr, w = _i64(nbrs[0]), _i32(nbrs[1]), _f64(nbrs[2])
+    s, dfds = _f64(s), _f64(dfds)
+    n = len(rowptr) - 1
+    out = np.zeros(n)
+    lib().orc_sensitivity_filter(kind, n, _p(rowptr, np.int64), _p(nbr, np.int32), _p(w, np.float64), _p(s, np.float64), _p(dfds, np.float64), _p(out, np.float64))
+    return out
 
 
 def compliance_sens(eq, coords, conn, u, rho, E0, E1, V, t, p, scale0):

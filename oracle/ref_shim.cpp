@@ -44,6 +44,8 @@
 #include "FEM/Controller/Assembling.h"
 #include "Optimize/Solver/OC.h"
 #include "Optimize/Solver/MMA.h"
+#include "Optimize/Solver/CONLIN.h"
+#include "Optimize/Filter/SensitivityFilter.h"
 #include "Optimize/Filter/HeavisideFilter.h"
 #include "Optimize/Filter/DensityFilter.h"
 #include "PrePost/Mesher/SquareMesh.h"
@@ -54,7 +56,7 @@ namespace {
 
 enum { EQ_PLANESTRAIN = 0, EQ_SOLID = 1, EQ_HEAT = 2 };
 enum { FILTER_DENSITY = 0, FILTER_HEAVISIDE = 1 };
-enum { OPT_OC = 0, OPT_MMA = 1 };
+enum { OPT_OC = 0, OPT_MMA = 1, OPT_CONLIN = 2 };
 
 double now() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -329,6 +331,33 @@ void ref_mma_update(void* h, int n, int m, double* x, double f, const double* df
     std::copy(xv.begin(), xv.end(), x);
 }
 
+// ---- CONLIN (CONLIN.h:59-373) ----
+void* ref_conlin_create(int n, int m, double a0, const double* a, const double* c, const double* d, const double* xmin, const double* xmax) {
+    return new CONLIN<double>(n, m, a0, std::vector<double>(a, a + m), std::vector<double>(c, c + m), std::vector<double>(d, d + m),
+                              std::vector<double>(xmin, xmin + n), std::vector<double>(xmax, xmax + n));
+}
+void ref_conlin_free(void* h) { delete (CONLIN<double>*)h; }
+void ref_conlin_setparameters(void* h, double move, double epsvalue) { ((CONLIN<double>*)h)->SetParameters(move, epsvalue); }
+int ref_conlin_isconvergence(void* h, double f) { return ((CONLIN<double>*)h)->IsConvergence(f) ? 1 : 0; }
+void ref_conlin_update(void* h, int n, int m, double* x, double f, const double* dfdx, const double* g, const double* dgdx) {
+    std::vector<double> xv(x, x + n);
+    std::vector<std::vector<double> > dg(m);
+    for (int i = 0; i < m; i++) dg[i].assign(dgdx + (size_t)i * n, dgdx + (size_t)(i + 1) * n);
+    ((CONLIN<double>*)h)->UpdateVariables(xv, f, std::vector<double>(dfdx, dfdx + n), std::vector<double>(g, g + m), dg);
+    std::copy(xv.begin(), xv.end(), x);
+}
+
+// ---- SensitivityFilter / SensitivityFilter2 (SensitivityFilter.h:44-55, 88-99); kind 2 = Sigmund, 3 = Borrvall ----
+void ref_sensitivity_filter(int kind, int n, const long long* rowptr, const int* nbr, const double* w, const double* s, const double* dfds, double* out) {
+    std::vector<std::vector<int> > neighbors(n);
+    std::vector<std::vector<double> > ww(n);
+    for (int i = 0; i < n; i++) { neighbors[i].assign(nbr + rowptr[i], nbr + rowptr[i + 1]); ww[i].assign(w + rowptr[i], w + rowptr[i + 1]); }
+    std::vector<double> r;
+    if (kind == 2) r = SensitivityFilter<double>(n, neighbors, ww).GetFilteredSensitivitis(std::vector<double>(s, s + n), std::vector<double>(dfds, dfds + n));
+    else r = SensitivityFilter2<double>(n, neighbors, ww).GetFilteredSensitivitis(std::vector<double>(s, s + n), std::vector<double>(dfds, dfds + n));
+    std::copy(r.begin(), r.end(), out);
+}
+
 // ---- the SIMP design loop of sample/optimize/sample_optimize_density_{oc,mma}.cpp:83-208 on a caller-supplied
 //      mesh (so the same driver serves plane strain Q4, heat Q4 and solid hex8).  The loop body follows the
 //      sample line by line; only VTK output is dropped and timings added.
@@ -360,7 +389,12 @@ int ref_simp_run(int eq, int dim, int nnode, const double* coords, int npe, int 
 
     OC<double>* oc = nullptr;
     MMA<double>* mma = nullptr;
-    if (opt_kind == OPT_OC) {
+    CONLIN<double>* conlin = nullptr;
+    if (opt_kind == OPT_CONLIN) {
+        conlin = new CONLIN<double>(nelem, 1, optp[2], std::vector<double>(1, optp[3]), std::vector<double>(1, optp[4]),
+                                    std::vector<double>(1, optp[5]), std::vector<double>(nelem, optp[6]), std::vector<double>(nelem, optp[7]));
+        conlin->SetParameters(optp[0], optp[1]);
+    } else if (opt_kind == OPT_OC) {
         oc = new OC<double>(nelem, optp[0], optp[1], optp[2], optp[3], optp[4], std::vector<double>(nelem, 0.01), std::vector<double>(nelem, 1.0));
     } else {
         mma = new MMA<double>(nelem, 1, optp[7], std::vector<double>(1, optp[8]), std::vector<double>(1, optp[9]),
@@ -436,7 +470,7 @@ int ref_simp_run(int eq, int dim, int nnode, const double* coords, int npe, int 
         t1 = now(); if (phase) phase[6] += t1 - t0; t0 = t1;
 
         hist[4 * k + 0] = f; hist[4 * k + 1] = g; hist[4 * k + 3] = 0;
-        bool conv = oc ? oc->IsConvergence(f) : mma->IsConvergence(f);
+        bool conv = oc ? oc->IsConvergence(f) : (mma ? mma->IsConvergence(f) : conlin->IsConvergence(f));
         if (check_convergence && conv) {
             hist[4 * k + 2] = now() - tstart; hist[4 * k + 3] = 1;
             k++;
@@ -449,8 +483,10 @@ int ref_simp_run(int eq, int dim, int nnode, const double* coords, int npe, int 
                 for (int i = 0; i < nelem; i++) gg += scale1 * rr[i] / (weightlimit * nelem);
                 return gg - 1.0 * scale1;
             });
-        } else {
+        } else if (mma) {
             mma->UpdateVariables(s, f, dfds, { g }, { dgds });
+        } else {
+            conlin->UpdateVariables(s, f, dfds, { g }, { dgds });
         }
         t1 = now(); if (phase) phase[7] += t1 - t0;
         hist[4 * k + 2] = now() - tstart;
@@ -461,7 +497,7 @@ int ref_simp_run(int eq, int dim, int nnode, const double* coords, int npe, int 
         if (u_out) u_out[(size_t)i * ndof + d] = u[i](d);
         if (r_out) r_out[(size_t)i * ndof + d] = r[i](d);
     }
-    delete filter; delete oc; delete mma;
+    delete filter; delete oc; delete mma; delete conlin;
     return k;
 }
 

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "_ref", "libpf2ref.so")
 
 EQ_PLANESTRAIN, EQ_SOLID, EQ_HEAT = 0, 1, 2
 FILTER_DENSITY, FILTER_HEAVISIDE = 0, 1
-OPT_OC, OPT_MMA = 0, 1
+OPT_OC, OPT_MMA, OPT_CONLIN = 0, 1, 2
 NDOF = {EQ_PLANESTRAIN: 2, EQ_SOLID: 3, EQ_HEAT: 1}
 
 _lib = None
@@ -36,6 +36,7 @@ def lib():
         _lib.ref_filter_create.restype = C.c_void_p
         _lib.ref_oc_create.restype = C.c_void_p
         _lib.ref_mma_create.restype = C.c_void_p
+        _lib.ref_conlin_create.restype = C.c_void_p
         _lib.ref_system_nnz.restype = C.c_longlong
     return _lib
 
@@ -226,6 +227,42 @@ class MMA:
         dfdx, g, dgdx = _f64(dfdx), _f64(g), _f64(dgdx)
         lib().ref_mma_update(self.h, self.n, self.m, _p(x, np.float64), C.c_double(f), _p(dfdx, np.float64), _p(g, np.float64), _p(dgdx, np.float64))
         return x
+
+
+class CONLIN:
+    def __init__(self, n, m, a0, a, c, d, xmin, xmax):
+        self.n, self.m = n, m
+        a, c, d = _f64(a), _f64(c), _f64(d)
+        xmin = _f64(np.broadcast_to(xmin, (n,)))
+        xmax = _f64(np.broadcast_to(xmax, (n,)))
+        self.h = C.c_void_p(lib().ref_conlin_create(n, m, C.c_double(a0), _p(a, np.float64), _p(c, np.float64), _p(d, np.float64),
+                                                    _p(xmin, np.float64), _p(xmax, np.float64)))
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.ref_conlin_free(self.h)
+            self.h = None
+
+    def set_parameters(self, move, epsvalue):
+        lib().ref_conlin_setparameters(self.h, C.c_double(move), C.c_double(epsvalue))
+
+    def is_convergence(self, f):
+        return bool(lib().ref_conlin_isconvergence(self.h, C.c_double(f)))
+
+    def update(self, x, f, dfdx, g, dgdx):
+        x = _f64(x).copy()
+        dfdx, g, dgdx = _f64(dfdx), _f64(g), _f64(dgdx)
+        lib().ref_conlin_update(self.h, self.n, self.m, _p(x, np.float64), C.c_double(f), _p(dfdx, np.float64), _p(g, np.float64), _p(dgdx, np.float64))
+        return x
+
+
+def sensitivity_filter(kind, nbrs, s, dfds):
+    rowptr, nbr, w = _i64(nbrs[0]), _i32(nbrs[1]), _f64(nbrs[2])
+    s, dfds = _f64(s), _f64(dfds)
+    n = len(rowptr) - 1
+    out = np.zeros(n)
+    lib().ref_sensitivity_filter(kind, n, _p(rowptr, np.int64), _p(nbr, np.int32), _p(w, np.float64), _p(s, np.float64), _p(dfds, np.float64), _p(out, np.float64))
+    return out
 
 
 def simp_run(eq, coords, conn, fixed, loads, filter_kind, nbrs, opt_kind, optp, params, niter, s0, check_convergence=True):

@@ -1,7 +1,7 @@
 """Build the C++ side of the drop-in boundary into pansfem2_b200/bin (git-ignored; travels to the GPU box):
 
   * our own drivers under pansfem2_b200/sample (batched, device-resident API);
-  * where /root/reference exists: the UNMODIFIED reference drivers (sample_optimize_density_oc.cpp, ..._mma.cpp,
+  * where /root/reference exists: the UNMODIFIED reference drivers (sample_optimize_density_oc.cpp, ..._mma.cpp, ..._CONLIN.cpp,
     sample/solid/sample_linear.cpp) compiled against the header mirror pansfem2_b200/src instead of the reference's src/ -
     the drop-in check.  The reference sources are only symlinked into a scratch tree, never copied into the repo.
 """
@@ -21,6 +21,7 @@ LINK = ["-L" + HERE, "-lpansfem2_b200", "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGI
 OWN = [("sample/optimize/sample_optimize_density_batched.cpp", "sample_optimize_density_batched")]
 DROPIN = [("sample/optimize/sample_optimize_density_oc.cpp", "dropin_density_oc"),
           ("sample/optimize/sample_optimize_density_mma.cpp", "dropin_density_mma"),
+          ("sample/optimize/sample_optimize_density_CONLIN.cpp", "dropin_density_conlin"),
           ("sample/solid/sample_linear.cpp", "dropin_solid_linear")]
 
 

@@ -16,8 +16,8 @@ LIB_PATH = os.path.join(HERE, "libpansfem2_b200.so")
 
 EQ_PLANESTRAIN, EQ_SOLID, EQ_HEAT = 0, 1, 2
 SOLVER_CG, SOLVER_SCALINGCG, SOLVER_ILU0CG = 0, 1, 2
-FILTER_DENSITY, FILTER_HEAVISIDE = 0, 1
-OPT_OC, OPT_MMA = 0, 1
+FILTER_DENSITY, FILTER_HEAVISIDE, FILTER_SENS_SIGMUND, FILTER_SENS_BORRVALL = 0, 1, 2, 3
+OPT_OC, OPT_MMA, OPT_CONLIN = 0, 1, 2
 E_NOCONV = 4
 NDOF = {EQ_PLANESTRAIN: 2, EQ_SOLID: 3, EQ_HEAT: 1}
 
@@ -337,14 +337,16 @@ class OC:
 
 
 class MMA:
+    CREATE = "pf2_mma_create"
+
     def __init__(self, ctx, n, m, a0, a, c, d, xmin, xmax):
         self.ctx, self.n, self.m = ctx, n, m
         a, c, d = _f64(a), _f64(c), _f64(d)
         xmin = _f64(np.broadcast_to(xmin, (n,)))
         xmax = _f64(np.broadcast_to(xmax, (n,)))
         self.h = C.c_void_p()
-        _ck(lib().pf2_mma_create(ctx.h, n, m, C.c_double(a0), _p(a, np.float64), _p(c, np.float64), _p(d, np.float64),
-                                 _p(xmin, np.float64), _p(xmax, np.float64), C.byref(self.h)))
+        _ck(getattr(lib(), self.CREATE)(ctx.h, n, m, C.c_double(a0), _p(a, np.float64), _p(c, np.float64), _p(d, np.float64),
+                                        _p(xmin, np.float64), _p(xmax, np.float64), C.byref(self.h)))
 
     def set_parameters(self, raa0, albefa, move, asyinit, asydecr, asyincr, epsvalue):
         _ck(lib().pf2_mma_set_parameters(self.h, *[C.c_double(v) for v in (raa0, albefa, move, asyinit, asydecr, asyincr, epsvalue)]))
@@ -365,6 +367,14 @@ class MMA:
         if self.h:
             lib().pf2_mma_destroy(self.h)
             self.h = C.c_void_p()
+
+
+class CONLIN(MMA):
+    """CONLIN<T> (CONLIN.h): the MMA handle in CONLIN mode; update_host / is_convergence are inherited."""
+    CREATE = "pf2_conlin_create"
+
+    def set_parameters(self, move, epsvalue):
+        _ck(lib().pf2_conlin_set_parameters(self.h, C.c_double(move), C.c_double(epsvalue)))
 
 
 def compliance_sens(mesh, eq, u_dev, rho_dev, params6, want_r=False):

@@ -99,6 +99,24 @@ filter_sens_kernel(int n, const long long* __restrict__ rowptr, const int* __res
     }
 }
 
+// SensitivityFilter (Sigmund, SensitivityFilter.h:44-55):   dfds_i = sum_j w_ij s_j dfds_j / (s_i sum_j w_ij)
+// SensitivityFilter2 (Borrvall, SensitivityFilter.h:88-99): dfds_i = sum_j w_ij s_j dfds_j / sum_j w_ij s_j
+template <int KIND>
+__global__ void __launch_bounds__(kThreads)
+sensitivity_filter_kernel(int n, const long long* __restrict__ rowptr, const int* __restrict__ nbr, const double* __restrict__ w,
+                          const double* __restrict__ s, const double* __restrict__ g, double* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double acc = 0.0, wsum = 0.0;
+        for (long long j = rowptr[i], je = rowptr[i + 1]; j < je; j++) {
+            const int nb = nbr[j];
+            const double wj = w[j], sj = s[nb];
+            acc += wj * sj * g[nb];
+            wsum += (KIND == PF2_FILTER_SENS_SIGMUND) ? wj : wj * sj;
+        }
+        out[i] = (KIND == PF2_FILTER_SENS_SIGMUND) ? acc / (wsum * s[i]) : acc / wsum;
+    }
+}
+
 // OC candidate (OC.h:85-92): x+ = clamp((-dfdx/(dgdx*lambda))^iota * x, max(0,(1-move)x), min(1,(1+move)x))
 __global__ void __launch_bounds__(kThreads)
 oc_candidate_kernel(int n, const double* __restrict__ xk, const double* __restrict__ dfdx, const double* __restrict__ dgdx,
@@ -117,6 +135,7 @@ oc_candidate_kernel(int n, const double* __restrict__ xk, const double* __restri
 
 int filter_apply(pf2_filter* f, const double* s, double* rho, double* sum_out, OcState* oc) {
     pf2_ctx* c = f->ctx;
+    if (f->kind >= PF2_FILTER_SENS_SIGMUND) { set_error("SensitivityFilter has no GetFilteredVariables (SensitivityFilter.h:18-23)"); return PF2_E_UNSUPPORTED; }
     const int grid = c->grid_for(f->n);
     const bool sum = sum_out != nullptr || oc != nullptr;
 #define FA(K, S) filter_apply_kernel<K, S><<<grid, kThreads, 0, c->stream>>>(f->n, f->rowptr, f->nbr, f->w, f->beta, s, rho, sum_out, oc, c->red.partials, c->red.ticket, f->sum_lo, f->sum_hi)
@@ -132,6 +151,14 @@ int filter_apply(pf2_filter* f, const double* s, double* rho, double* sum_out, O
 int filter_sens(pf2_filter* f, const double* s, const double* g1, double* out1, const double* g2, double c2, double* out2) {
     pf2_ctx* c = f->ctx;
     const int grid = c->grid_for(f->n);
+    if (f->kind >= PF2_FILTER_SENS_SIGMUND) {
+        if (f->kind == PF2_FILTER_SENS_SIGMUND) sensitivity_filter_kernel<PF2_FILTER_SENS_SIGMUND><<<grid, kThreads, 0, c->stream>>>(f->n, f->rowptr, f->nbr, f->w, s, g1, out1);
+        else sensitivity_filter_kernel<PF2_FILTER_SENS_BORRVALL><<<grid, kThreads, 0, c->stream>>>(f->n, f->rowptr, f->nbr, f->w, s, g1, out1);
+        PF2_LAUNCH_CHECK();
+        c->launches++;
+        PF2_CHECK(out2 == nullptr, "sensitivity filters take one field at a time");
+        return PF2_OK;
+    }
     if (f->kind == PF2_FILTER_HEAVISIDE) {
         if (!f->dr) PF2_TRY(dev_alloc(&f->dr, (size_t)f->n));
         heaviside_slope_kernel<<<grid, kThreads, 0, c->stream>>>(f->n, f->rowptr, f->nbr, f->w, f->beta, s, f->dr);
@@ -216,7 +243,7 @@ extern "C" {
 
 int pf2_filter_create(pf2_ctx* ctx, int kind, int n, const long long* rowptr_host, const int* nbr_host, const double* w_host, pf2_filter** out) {
     PF2_CHECK(ctx && out && rowptr_host && nbr_host && w_host && n > 0, "bad arguments");
-    PF2_CHECK(kind == PF2_FILTER_DENSITY || kind == PF2_FILTER_HEAVISIDE, "unknown filter kind");
+    PF2_CHECK(kind >= PF2_FILTER_DENSITY && kind <= PF2_FILTER_SENS_BORRVALL, "unknown filter kind");
     PF2_CUDA(cudaSetDevice(ctx->device));
     pf2_filter* f = new pf2_filter();
     f->ctx = ctx; f->kind = kind; f->n = n; f->nnb = rowptr_host[n];

@@ -62,7 +62,10 @@ __device__ double kkt_small(const MmaSmall* S, const double* y, const double* la
 }
 
 // ---- set-up pass: asymptotes, move limits, p0 q0 p q b, starting point (MMA.h:119-197) -----------------------------
-template <int M>
+// CONLIN = true turns the same machinery into CONLIN<T> (Optimize/Solver/CONLIN.h:89-373): the convex approximation
+// p*x + q/x replaces p/(U-x) + q/(x-L) (no asymptotes), with p = max(df,0), q = max(-df,0)*xk^2 (:100-122) and the
+// move limits alpha = max(xmin, xk - move*w), beta = min(xmax, xk + move*w) (:92-96).
+template <int M, bool CONLIN>
 __global__ void __launch_bounds__(kThreads)
 mma_setup_kernel(int lo, int hi, int n, int k, MmaParams P, const double* __restrict__ xk, const double* __restrict__ xkm1,
                  const double* __restrict__ xkm2, const double* __restrict__ xmin, const double* __restrict__ xmax,
@@ -75,6 +78,25 @@ mma_setup_kernel(int lo, int hi, int n, int k, MmaParams P, const double* __rest
     for (int i = 0; i < M; i++) bs[i] = 0.0;
     for (int j = lo + blockIdx.x * blockDim.x + threadIdx.x; j < hi; j += gridDim.x * blockDim.x) {
         const double xj = xk[j], w = xmax[j] - xmin[j];
+        if (CONLIN) {
+            const double al = fmax(xmin[j], xj - P.move * w), be = fmin(xmax[j], xj + P.move * w);
+            alpha[j] = al; beta[j] = be;
+            const double df = dfdx[j];
+            p0[j] = fmax(df, 0.0);
+            q0[j] = fmax(-df, 0.0) * sq(xj);
+#pragma unroll
+            for (int i = 0; i < M; i++) {
+                const double dg = dgdx[(size_t)i * n + j];
+                const double pij = fmax(dg, 0.0), qij = fmax(-dg, 0.0) * sq(xj);
+                p[(size_t)i * n + j] = pij; q[(size_t)i * n + j] = qij;
+                bs[i] += pij * xj + qij / xj;
+            }
+            const double x0 = 0.5 * (al + be);
+            x[j] = x0;
+            gsi[j] = fmax(1.0, 1.0 / (x0 - al));
+            ita[j] = fmax(1.0, 1.0 / (be - x0));
+            continue;
+        }
         double Lj, Uj;
         if (k < 2) {
             Lj = xj - P.asyinit * w; Uj = xj + P.asyinit * w;
@@ -126,7 +148,7 @@ __global__ void mma_setup_small_kernel(MmaSmall* S, const double* __restrict__ g
 }
 
 // ---- Newton pass 1 (MMA.h:201-291 + the m-sized updates :332-343,:353-359 + KKTNorm of the current point :361) ------
-template <int M>
+template <int M, bool CONLIN>
 __global__ void __launch_bounds__(kThreads)
 mma_newton1_kernel(int lo, int hi, int n, const double* __restrict__ x, const double* __restrict__ L, const double* __restrict__ U,
                    const double* __restrict__ alpha, const double* __restrict__ beta, const double* __restrict__ p0,
@@ -142,19 +164,19 @@ mma_newton1_kernel(int lo, int hi, int n, const double* __restrict__ x, const do
     for (int i = 0; i < M; i++) lam[i] = S->lam[i];
     const double eps = S->eps;
     for (int j = lo + blockIdx.x * blockDim.x + threadIdx.x; j < hi; j += gridDim.x * blockDim.x) {
-        const double xj = x[j], ux = U[j] - xj, xl = xj - L[j], xa = xj - alpha[j], bx = beta[j] - xj;
+        const double xj = x[j], ux = CONLIN ? 1.0 : U[j] - xj, xl = CONLIN ? xj : xj - L[j], xa = xj - alpha[j], bx = beta[j] - xj;
         double pl = p0[j], ql = q0[j], G[M];
         const double iux2 = 1.0 / sq(ux), ixl2 = 1.0 / sq(xl);
 #pragma unroll
         for (int i = 0; i < M; i++) {
             const double pij = p[(size_t)i * n + j], qij = q[(size_t)i * n + j];
             pl += lam[i] * pij; ql += lam[i] * qij;
-            G[i] = pij / sq(ux) - qij / sq(xl);
-            v[M * M + M + i] += pij / ux + qij / xl;
+            G[i] = CONLIN ? pij - qij / sq(xj) : pij / sq(ux) - qij / sq(xl);
+            v[M * M + M + i] += CONLIN ? pij * xj + qij / xj : pij / ux + qij / xl;
         }
         const double gs = gsi[j], it = ita[j];
-        const double dxj = 2.0 * pl / (sq(ux) * ux) + 2.0 * ql / (sq(xl) * xl) + gs / xa + it / bx;
-        const double grad = pl * iux2 - ql * ixl2;
+        const double dxj = (CONLIN ? 2.0 * ql / (sq(xj) * xj) : 2.0 * pl / (sq(ux) * ux) + 2.0 * ql / (sq(xl) * xl)) + gs / xa + it / bx;
+        const double grad = CONLIN ? pl - ql / sq(xj) : pl * iux2 - ql * ixl2;
         const double dt = grad - eps / xa + eps / bx;
         Dx[j] = dxj; dtx[j] = dt;
 #pragma unroll
@@ -226,7 +248,7 @@ __global__ void mma_newton1_small_kernel(MmaSmall* S) {
 }
 
 // ---- Newton pass 2: dx, dxi, deta, maximal step (MMA.h:282-287, 338-360) ----------------------------------------------
-template <int M>
+template <int M, bool CONLIN>
 __global__ void __launch_bounds__(kThreads)
 mma_newton2_kernel(int lo, int hi, int n, const double* __restrict__ x, const double* __restrict__ L, const double* __restrict__ U,
                    const double* __restrict__ alpha, const double* __restrict__ beta, const double* __restrict__ p,
@@ -239,11 +261,11 @@ mma_newton2_kernel(int lo, int hi, int n, const double* __restrict__ x, const do
     const double eps = S->eps;
     double txmax = 0.0;
     for (int j = lo + blockIdx.x * blockDim.x + threadIdx.x; j < hi; j += gridDim.x * blockDim.x) {
-        const double xj = x[j], ux = U[j] - xj, xl = xj - L[j], xa = xj - alpha[j], bx = beta[j] - xj, dxx = Dx[j];
+        const double xj = x[j], ux = CONLIN ? 1.0 : U[j] - xj, xl = CONLIN ? xj : xj - L[j], xa = xj - alpha[j], bx = beta[j] - xj, dxx = Dx[j];
         double d = -dtx[j] / dxx;
 #pragma unroll
         for (int i = 0; i < M; i++) {
-            const double Gi = p[(size_t)i * n + j] / sq(ux) - q[(size_t)i * n + j] / sq(xl);
+            const double Gi = CONLIN ? p[(size_t)i * n + j] - q[(size_t)i * n + j] / sq(xj) : p[(size_t)i * n + j] / sq(ux) - q[(size_t)i * n + j] / sq(xl);
             d -= Gi * dlam[i] / dxx;
         }
         const double gs = gsi[j], it = ita[j];
@@ -263,7 +285,7 @@ __global__ void mma_newton2_small_kernel(MmaSmall* S) {
 }
 
 // ---- line-search trial (MMA.h:371-410) ---------------------------------------------------------------------------------
-template <int M>
+template <int M, bool CONLIN>
 __global__ void __launch_bounds__(kThreads)
 mma_trial_kernel(int lo, int hi, int n, const double* __restrict__ x, const double* __restrict__ L, const double* __restrict__ U,
                  const double* __restrict__ alpha, const double* __restrict__ beta, const double* __restrict__ p0,
@@ -283,15 +305,15 @@ mma_trial_kernel(int lo, int hi, int n, const double* __restrict__ x, const doub
     for (int j = lo + blockIdx.x * blockDim.x + threadIdx.x; j < hi; j += gridDim.x * blockDim.x) {
         const double xj = x[j] + tau * dx[j], gs = gsi[j] + tau * dgsi[j], it = ita[j] + tau * dita[j];
         xn[j] = xj; gsin[j] = gs; itan[j] = it;
-        const double ux = U[j] - xj, xl = xj - L[j];
+        const double ux = CONLIN ? 1.0 : U[j] - xj, xl = CONLIN ? xj : xj - L[j];
         double pl = p0[j], ql = q0[j];
 #pragma unroll
         for (int i = 0; i < M; i++) {
             const double pij = p[(size_t)i * n + j], qij = q[(size_t)i * n + j];
             pl += lamn[i] * pij; ql += lamn[i] * qij;
-            v[i] += pij / ux + qij / xl;
+            v[i] += CONLIN ? pij * xj + qij / xj : pij / ux + qij / xl;
         }
-        v[M] += sq(pl / sq(ux) - ql / sq(xl) - gs + it) + sq(gs * (xj - alpha[j]) - eps) + sq(it * (beta[j] - xj) - eps);
+        v[M] += sq((CONLIN ? pl - ql / sq(xj) : pl / sq(ux) - ql / sq(xl)) - gs + it) + sq(gs * (xj - alpha[j]) - eps) + sq(it * (beta[j] - xj) - eps);
     }
     if (grid_sum_last<NT>(v, partials, ticket) && threadIdx.x == 0) {
 #pragma unroll
@@ -500,7 +522,7 @@ using namespace pf2;
 
 namespace pf2 {
 
-template <int M>
+template <int M, bool CONLIN>
 static int mma_update_impl(pf2_mma* mm, double* xk, const double* dfdx, const double* dgdx, int* newton_out) {
     pf2_ctx* c = mm->ctx;
     cudaStream_t s = c->stream;
@@ -508,7 +530,7 @@ static int mma_update_impl(pf2_mma* mm, double* xk, const double* dfdx, const do
     const int n = mm->n, lo = mm->lo, hi = mm->hi;
     const int grid = c->grid_for(hi - lo);
     constexpr int NT1 = M * M + 2 * M + 1;
-    mma_setup_kernel<M><<<grid, kThreads, 0, s>>>(lo, hi, n, mm->k, mm->P, xk, mm->xkm1, mm->xkm2, mm->xmin, mm->xmax, dfdx, dgdx, mm->L, mm->U,
+    mma_setup_kernel<M, CONLIN><<<grid, kThreads, 0, s>>>(lo, hi, n, mm->k, mm->P, xk, mm->xkm1, mm->xkm2, mm->xmin, mm->xmax, dfdx, dgdx, mm->L, mm->U,
                                                  mm->alpha, mm->beta, mm->p0, mm->q0, mm->p, mm->q, mm->x, mm->gsi, mm->ita, mm->S,
                                                  mm->gval, c->red.partials, c->red.ticket);
     if (d) PF2_TRY(dist_allreduce(d, mm->S->red, M));
@@ -518,18 +540,18 @@ static int mma_update_impl(pf2_mma* mm, double* xk, const double* dfdx, const do
     double eps = 1.0;
     int guard = 0;
     while (eps > 1.0e-7) {      // MMA.h:199
-        mma_newton1_kernel<M><<<grid, kThreads, 0, s>>>(lo, hi, n, mm->x, mm->L, mm->U, mm->alpha, mm->beta, mm->p0, mm->q0, mm->p, mm->q, mm->gsi,
+        mma_newton1_kernel<M, CONLIN><<<grid, kThreads, 0, s>>>(lo, hi, n, mm->x, mm->L, mm->U, mm->alpha, mm->beta, mm->p0, mm->q0, mm->p, mm->q, mm->gsi,
                                                        mm->ita, mm->Dx, mm->dtx, mm->S, c->red.partials, c->red.ticket);
         if (d) PF2_TRY(dist_allreduce(d, mm->S->red, NT1));
         mma_newton1_small_kernel<M><<<1, 1, 0, s>>>(mm->S);
-        mma_newton2_kernel<M><<<grid, kThreads, 0, s>>>(lo, hi, n, mm->x, mm->L, mm->U, mm->alpha, mm->beta, mm->p, mm->q, mm->gsi, mm->ita, mm->Dx,
+        mma_newton2_kernel<M, CONLIN><<<grid, kThreads, 0, s>>>(lo, hi, n, mm->x, mm->L, mm->U, mm->alpha, mm->beta, mm->p, mm->q, mm->gsi, mm->ita, mm->Dx,
                                                        mm->dtx, mm->dx, mm->dgsi, mm->dita, mm->S, c->red.partials, c->red.ticket);
         if (d) PF2_TRY(dist_allreduce_max(d, mm->S->red, 1));
         mma_newton2_small_kernel<<<1, 1, 0, s>>>(mm->S);
         c->launches += 4;
         bool accepted = false;
         while (!accepted) {
-            mma_trial_kernel<M><<<grid, kThreads, 0, s>>>(lo, hi, n, mm->x, mm->L, mm->U, mm->alpha, mm->beta, mm->p0, mm->q0, mm->p, mm->q, mm->gsi,
+            mma_trial_kernel<M, CONLIN><<<grid, kThreads, 0, s>>>(lo, hi, n, mm->x, mm->L, mm->U, mm->alpha, mm->beta, mm->p0, mm->q0, mm->p, mm->q, mm->gsi,
                                                          mm->ita, mm->dx, mm->dgsi, mm->dita, mm->xn, mm->gsin, mm->itan, mm->S,
                                                          c->red.partials, c->red.ticket);
             if (d) PF2_TRY(dist_allreduce(d, mm->S->red, M + 1));
@@ -560,6 +582,7 @@ int mma_update(pf2_mma* mm, double* xk, double f, const double* dfdx, const doub
     int rc;
     if (mm->n <= mm->m) {
         PF2_CHECK(mm->n <= kTinyN, "n <= m is supported for n <= 4 only");
+        PF2_CHECK(!mm->conlin, "CONLIN with n <= m is not built");
         mma_tiny_kernel<<<1, 32, 0, s>>>(mm->n, mm->m, mm->k, mm->P, xk, mm->xkm1, mm->xkm2, mm->xmin, mm->xmax, dfdx, dgdx, mm->gval, mm->L, mm->U, mm->S);
         PF2_LAUNCH_CHECK();
         c->launches++;
@@ -568,11 +591,20 @@ int mma_update(pf2_mma* mm, double* xk, double f, const double* dfdx, const doub
         if (newton_out) *newton_out = mm->h_S->newton;
         rc = PF2_OK;
     } else {
-        switch (mm->m) {
-            case 1: rc = mma_update_impl<1>(mm, xk, dfdx, dgdx, newton_out); break;
-            case 2: rc = mma_update_impl<2>(mm, xk, dfdx, dgdx, newton_out); break;
-            case 3: rc = mma_update_impl<3>(mm, xk, dfdx, dgdx, newton_out); break;
-            default: rc = mma_update_impl<4>(mm, xk, dfdx, dgdx, newton_out); break;
+        if (mm->conlin) {
+            switch (mm->m) {
+                case 1: rc = mma_update_impl<1, true>(mm, xk, dfdx, dgdx, newton_out); break;
+                case 2: rc = mma_update_impl<2, true>(mm, xk, dfdx, dgdx, newton_out); break;
+                case 3: rc = mma_update_impl<3, true>(mm, xk, dfdx, dgdx, newton_out); break;
+                default: rc = mma_update_impl<4, true>(mm, xk, dfdx, dgdx, newton_out); break;
+            }
+        } else {
+            switch (mm->m) {
+                case 1: rc = mma_update_impl<1, false>(mm, xk, dfdx, dgdx, newton_out); break;
+                case 2: rc = mma_update_impl<2, false>(mm, xk, dfdx, dgdx, newton_out); break;
+                case 3: rc = mma_update_impl<3, false>(mm, xk, dfdx, dgdx, newton_out); break;
+                default: rc = mma_update_impl<4, false>(mm, xk, dfdx, dgdx, newton_out); break;
+            }
         }
     }
     if (rc != PF2_OK) return rc;
@@ -611,6 +643,21 @@ int pf2_mma_create(pf2_ctx* ctx, int n, int m, double a0, const double* a_host, 
     *out = mm;
     return PF2_OK;
 }
+/* CONLIN<T> (Optimize/Solver/CONLIN.h:18-26): same handle type and update / convergence entry points as MMA */
+int pf2_conlin_create(pf2_ctx* ctx, int n, int m, double a0, const double* a_host, const double* c_host, const double* d_host,
+                      const double* xmin_host, const double* xmax_host, pf2_mma** out) {
+    PF2_TRY(pf2_mma_create(ctx, n, m, a0, a_host, c_host, d_host, xmin_host, xmax_host, out));
+    (*out)->conlin = true;
+    (*out)->P.move = 0.5;                 // CONLIN.h:66
+    return PF2_OK;
+}
+int pf2_conlin_set_parameters(pf2_mma* mm, double move, double epsvalue) {     // CONLIN.h:71-74
+    PF2_CHECK(mm && mm->conlin, "not a CONLIN optimiser");
+    mm->P.move = move;
+    mm->epsvalue = epsvalue;
+    return PF2_OK;
+}
+
 int pf2_mma_destroy(pf2_mma* mm) {
     if (!mm) return PF2_OK;
     cudaStreamSynchronize(mm->ctx->stream);

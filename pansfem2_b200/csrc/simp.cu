@@ -122,7 +122,7 @@ int pf2_simp_create(pf2_ctx* ctx, pf2_mesh* mesh, pf2_dofmap* map, pf2_csr* A, p
                     const int* load_dof_host, const double* load_val_host, pf2_simp** out) {
     PF2_CHECK(ctx && mesh && map && A && filter && optp && params && out, "null argument");
     PF2_CHECK(filter->n == mesh->nelem, "filter size must equal the element count");
-    PF2_CHECK(opt_kind == PF2_OPT_OC || opt_kind == PF2_OPT_MMA, "unknown optimiser");
+    PF2_CHECK(opt_kind == PF2_OPT_OC || opt_kind == PF2_OPT_MMA || opt_kind == PF2_OPT_CONLIN, "unknown optimiser");
     PF2_CUDA(cudaSetDevice(ctx->device));
     pf2_simp* S = new pf2_simp();
     S->ctx = ctx; S->mesh = mesh; S->map = map; S->A = A; S->filter = filter; S->eq = eq; S->opt_kind = opt_kind;
@@ -144,10 +144,14 @@ int pf2_simp_create(pf2_ctx* ctx, pf2_mesh* mesh, pf2_dofmap* map, pf2_csr* A, p
     }
     if (opt_kind == PF2_OPT_OC) {
         PF2_TRY(pf2_oc_create(ctx, S->n, optp[0], optp[1], optp[2], optp[3], optp[4], &S->oc));
-    } else {
+    } else if (opt_kind == PF2_OPT_MMA) {
         std::vector<double> xmin(n, optp[11]), xmax(n, optp[12]);
         PF2_TRY(pf2_mma_create(ctx, S->n, 1, optp[7], &optp[8], &optp[9], &optp[10], xmin.data(), xmax.data(), &S->mma));
         PF2_TRY(pf2_mma_set_parameters(S->mma, optp[0], optp[1], optp[2], optp[3], optp[4], optp[5], optp[6]));
+    } else {
+        std::vector<double> xmin(n, optp[6]), xmax(n, optp[7]);
+        PF2_TRY(pf2_conlin_create(ctx, S->n, 1, optp[2], &optp[3], &optp[4], &optp[5], xmin.data(), xmax.data(), &S->mma));
+        PF2_TRY(pf2_conlin_set_parameters(S->mma, optp[0], optp[1]));
     }
     for (int i = 0; i < 7; i++) PF2_CUDA(cudaEventCreate(&S->ev[i]));
     PF2_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -167,6 +167,7 @@ struct MmaParams {
 struct pf2_mma {
     pf2_ctx* ctx = nullptr;
     int n = 0, m = 0, k = 0;
+    bool conlin = false;                                  // CONLIN<T> instead of MMA<T>
     double previousvalue = 0.0, epsvalue = 1.0e-5;       // MMA.h:67-68
     pf2::MmaParams P = { 1.0e-5, 0.1, 0.5, 0.5, 0.7, 1.2 };   // MMA.h:80-85
     double *xmin = nullptr, *xmax = nullptr, *xkm1 = nullptr, *xkm2 = nullptr, *L = nullptr, *U = nullptr;

@@ -14,7 +14,7 @@ from . import mesher
 
 EQ_PLANESTRAIN, EQ_SOLID, EQ_HEAT = 0, 1, 2
 FILTER_DENSITY, FILTER_HEAVISIDE = 0, 1
-OPT_OC, OPT_MMA = 0, 1
+OPT_OC, OPT_MMA, OPT_CONLIN = 0, 1, 2
 NDOF = {EQ_PLANESTRAIN: 2, EQ_SOLID: 3, EQ_HEAT: 1}
 
 
@@ -47,6 +47,8 @@ class Problem:
     oc: tuple = (0.5, 0.0, 1.0e4, 1.0e-3, 0.15)
     # MMA(n,1,a0=1,a={0},c={1e4},d={0},xmin=.01,xmax=1) + SetParameters(1e-5,.1,.2,.5,.7,1.2,1e-6)  ..._mma.cpp:80-85
     mma: tuple = (1.0e-5, 0.1, 0.2, 0.5, 0.7, 1.2, 1.0e-6, 1.0, 0.0, 1.0e4, 0.0, 0.01, 1.0)
+    # CONLIN(n,1,a0=1,a={0},c={1e4},d={0},xmin=.01,xmax=1) + SetParameters(0.2, 1e-6)  sample_optimize_density_CONLIN.cpp:80-85
+    conlin: tuple = (0.2, 1.0e-6, 1.0, 0.0, 1.0e4, 0.0, 0.01, 1.0)
     s0: float = 0.5
     extra: dict = field(default_factory=dict)
 
@@ -67,7 +69,7 @@ class Problem:
                          self.thickness, self.beta0, float(self.beta_period), float(self.cg_itrmax), self.cg_eps])
 
     def optp(self):
-        return np.array(self.oc if self.opt_kind == OPT_OC else self.mma, dtype=np.float64)
+        return np.array({OPT_OC: self.oc, OPT_MMA: self.mma, OPT_CONLIN: self.conlin}[self.opt_kind], dtype=np.float64)
 
     def free_dofs(self):
         return self.nnode * self.ndof - len(self.fixed[0])

@@ -1,7 +1,7 @@
 //  pansfem2_b200/sample/optimize/sample_optimize_density_batched.cpp
-//  The SIMP cantilever of the reference's sample/optimize/sample_optimize_density_{oc,mma}.cpp driven through the batched,
+//  The SIMP cantilever of the reference's sample/optimize/sample_optimize_density_{oc,mma,CONLIN}.cpp driven through the batched,
 //  device-resident API (B200/Batched.h).  Same problem, same parameters, same VTK output; the design never leaves the GPU.
-//      usage: sample_optimize_density_batched [oc|mma] [nx ny] [output.vtk]
+//      usage: sample_optimize_density_batched [oc|mma|conlin] [nx ny] [output.vtk]
 #include <iostream>
 #include <fstream>
 #include <string>
@@ -49,8 +49,10 @@ int main(int argc, char** argv) {
     B200::Model model(x, elements, 2, ufixed);
     B200::SimpParameters prm;
     std::vector<double> optp = optimizer == "oc" ? std::vector<double>{ 0.5, 0.0, 1.0e4, 1.0e-3, 0.15 }
+                             : optimizer == "conlin" ? std::vector<double>{ 0.2, 1.0e-6, 1.0, 0.0, 10000.0, 0.0, 0.01, 1.0 }
                                                  : std::vector<double>{ 1.0e-5, 0.1, 0.2, 0.5, 0.7, 1.2, 1.0e-6, 1.0, 0.0, 10000.0, 0.0, 0.01, 1.0 };
-    B200::DesignLoop<Equation> loop(model, filter, optimizer == "oc" ? PF2_OPT_OC : PF2_OPT_MMA, optp, prm, qfixed, std::vector<double>(elements.size(), 0.5));
+    const int optkind = optimizer == "oc" ? PF2_OPT_OC : (optimizer == "conlin" ? PF2_OPT_CONLIN : PF2_OPT_MMA);
+    B200::DesignLoop<Equation> loop(model, filter, optkind, optp, prm, qfixed, std::vector<double>(elements.size(), 0.5));
 
     int k = 0;
     for (; k < 500; k++) {

@@ -97,6 +97,7 @@ public:
 public:
         //  _filter: a mirrored DensityFilter<double> / HeavisideFilter<double>; _optimizer: PF2_OPT_OC with {iota,lmin,lmax,leps,move}
         //  or PF2_OPT_MMA with {raa0,albefa,move,asyinit,asydecr,asyincr,epsvalue,a0,a,c,d,xmin,xmax}
+        //  or PF2_OPT_CONLIN with {move,epsvalue,a0,a,c,d,xmin,xmax}
         template<class FILTER>
         DesignLoop(Model& _model, const FILTER& _filter, int _optimizer, const std::vector<double>& _optp, const SimpParameters& _prm, const BcList& _qfixed, const std::vector<double>& _s0)
             : model(_model), handle(nullptr) {

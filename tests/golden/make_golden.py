@@ -3,8 +3,8 @@
     python tests/golden/make_golden.py
 
 Sources (all under /root/reference, nothing is copied verbatim - values are parsed into arrays):
-  * sample/optimize/Density_OC.vtk  / Density_MMA.vtk : committed final-iteration outputs of
-    sample_optimize_density_{oc,mma}.cpp (VECTORS u, VECTORS r, SCALARS s = filtered rho), 6 significant digits.
+  * sample/optimize/Density_OC.vtk  / Density_MMA.vtk / Density_CONLIN.vtk : committed final-iteration outputs of
+    sample_optimize_density_{oc,mma,CONLIN}.cpp (VECTORS u, VECTORS r, SCALARS s = filtered rho), 6 significant digits.
   * sample/solid/result_linear.vtk + {Node,Element,Dirichlet,Neumann}.csv : hex8 50x5x5 cantilever solved by
     sample/solid/sample_linear.cpp (SolidLinearIsotropicElastic + ScalingCG).
   * src/Optimize/Solver/test_MMA.cpp, test_MMA_3.cpp, test_MMA_TOY2.cpp : the print-only known-answer mains are
@@ -55,7 +55,7 @@ def csv_rows(path):
 
 
 def golden_simp():
-    for tag in ("OC", "MMA"):
+    for tag in ("OC", "MMA", "CONLIN"):
         f = parse_vtk_fields(f"{REF}/sample/optimize/Density_{tag}.vtk")
         np.savez_compressed(f"{OUT}/density_{tag.lower()}.npz", u=f["u"][:, :2], r=f["r"][:, :2], rho=f["s"])
         print(tag, {k: v.shape for k, v in f.items()})
@@ -154,8 +154,51 @@ def golden_live():
     print("live fixtures:", len(d))
 
 
+def golden_conlin():
+    """CONLIN<T> and SensitivityFilter/SensitivityFilter2 fixtures from the live reference."""
+    reflib.set_num_threads(1)
+    d = {}
+    rng = np.random.default_rng(20200719)
+    P = problems.cantilever2d(12, 8)
+    n = P.nelem
+    s = rng.uniform(0.05, 1.0, n)
+    dfds = -rng.uniform(0.1, 2.0, n)
+    d["s"], d["dfds"] = s, dfds
+    d["sens_sigmund"] = reflib.sensitivity_filter(2, P.nbrs, s, dfds)
+    d["sens_borrvall"] = reflib.sensitivity_filter(3, P.nbrs, s, dfds)
+    # three CONLIN updates with one and with two constraints (mixed-sign gradients exercise both p and q)
+    for m in (1, 2):
+        opt = reflib.CONLIN(n, m, 1.0, np.zeros(m), np.full(m, 1.0e4), np.zeros(m), 0.01, 1.0)
+        opt.set_parameters(0.2, 1.0e-6)
+        x = s.copy()
+        xs = []
+        for it in range(3):
+            df = dfds * (1.0 + 0.1 * it) * np.where(np.arange(n) % 7 == 3, -0.05, 1.0)
+            g = np.array([x.sum() / (0.5 * n) - 1.0, 0.3 - x[: n // 2].sum() / n][:m])
+            dg = np.stack([np.full(n, 1.0 / (0.5 * n)), np.where(np.arange(n) < n // 2, -1.0 / n, 0.0)][:m])
+            x = opt.update(x, 1.0, df, g, dg)
+            xs.append(x.copy())
+        d[f"conlin_m{m}_x"] = np.stack(xs)
+    # C1 with the CONLIN driver: first 12 design iterations
+    P1 = problems.cantilever2d(60, 40, opt_kind=problems.OPT_CONLIN)
+    R = reflib.simp_run(P1.eq, P1.coords, P1.conn, P1.fixed, P1.loads, P1.filter_kind, P1.nbrs, P1.opt_kind,
+                        P1.optp(), P1.params(), 12, np.full(P1.nelem, 0.5), check_convergence=False)
+    d["c1_conlin_hist"] = R["hist"][:, :2]
+    d["c1_conlin_s12"] = R["s"]
+    d["c1_conlin_rho12"] = R["rho"]
+    print("c1 conlin", R["hist"][:3, :2], R["hist"][-1, :2])
+    np.savez_compressed(f"{OUT}/live_conlin.npz", **d)
+    print("conlin fixtures:", len(d))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "conlin":
+        f = parse_vtk_fields(f"{REF}/sample/optimize/Density_CONLIN.vtk")
+        np.savez_compressed(f"{OUT}/density_conlin.npz", u=f["u"][:, :2], r=f["r"][:, :2], rho=f["s"])
+        golden_conlin()
+        sys.exit(0)
     golden_simp()
     golden_solid()
     golden_mma_kat()
     golden_live()
+    golden_conlin()

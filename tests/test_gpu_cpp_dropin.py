@@ -43,7 +43,7 @@ def need(name):
     return exe
 
 
-@pytest.mark.parametrize("opt,tag,iters", [("oc", "oc", 66), ("mma", "mma", 56)])
+@pytest.mark.parametrize("opt,tag,iters", [("oc", "oc", 66), ("mma", "mma", 56), ("conlin", "conlin", 133)])
 def test_batched_driver_reproduces_golden_vtk(tmp_path, golden_dir, opt, tag, iters):
     exe = need("sample_optimize_density_batched")
     out = tmp_path / "result.vtk"
@@ -65,6 +65,20 @@ def test_unmodified_reference_oc_driver_on_the_header_mirror(tmp_path, golden_di
     files = sorted((tmp_path / "sample" / "optimize").glob("result*.vtk"), key=lambda p: int(p.stem[6:]))
     assert len(files) == 66                       # k = 0..65, as the reference run
     got, g = parse_vtk(files[-1]), np.load(os.path.join(golden_dir, "density_oc.npz"))
+    assert np.abs(got["s"] - g["rho"]).max() < 2e-6
+    np.testing.assert_allclose(got["u"][:, :2], g["u"], rtol=1e-5, atol=1e-11)
+    np.testing.assert_allclose(got["r"][:, :2], g["r"], rtol=1e-5, atol=1e-7)
+
+
+def test_unmodified_reference_conlin_driver_on_the_header_mirror(tmp_path, golden_dir):
+    """sample_optimize_density_CONLIN.cpp, unmodified, on CONLIN.h / HeavisideFilter.h of the mirror: 133 iterations."""
+    exe = need("dropin_density_conlin")
+    (tmp_path / "sample" / "optimize").mkdir(parents=True)
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stderr[-2000:]
+    files = sorted((tmp_path / "sample" / "optimize").glob("result*.vtk"), key=lambda p: int(p.stem[6:]))
+    assert len(files) == 133                      # k = 0..132, as the reference run
+    got, g = parse_vtk(files[-1]), np.load(os.path.join(golden_dir, "density_conlin.npz"))
     assert np.abs(got["s"] - g["rho"]).max() < 2e-6
     np.testing.assert_allclose(got["u"][:, :2], g["u"], rtol=1e-5, atol=1e-11)
     np.testing.assert_allclose(got["r"][:, :2], g["r"], rtol=1e-5, atol=1e-7)

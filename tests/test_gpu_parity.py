@@ -340,6 +340,97 @@ def test_mma_two_constraints_vs_oracle(ctx):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# CONLIN and the sensitivity filters (CONLIN.h, SensitivityFilter.h) - the first "next" row of SURVEY.md section 8f
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def live_conlin(golden_dir):
+    return np.load(os.path.join(golden_dir, "live_conlin.npz"))
+
+
+def test_sensitivity_filters_vs_live_reference_fixture(ctx, live_conlin):
+    P = problems.cantilever2d(12, 8)
+    s, dfds = live_conlin["s"], live_conlin["dfds"]
+    for kind, nm in ((capi.FILTER_SENS_SIGMUND, "sigmund"), (capi.FILTER_SENS_BORRVALL, "borrvall")):
+        f = capi.Filter(ctx, kind, *P.nbrs)
+        assert rel(f.sens_host(s, dfds), live_conlin[f"sens_{nm}"]) < 1e-14
+        with pytest.raises(capi.Pf2Error):
+            f.apply_host(s)                       # the reference classes have no GetFilteredVariables
+        f.close()
+    # ragged 3-D lists against the oracle
+    P = problems.cantilever3d(7, 5, 3)
+    rng = np.random.default_rng(12)
+    s, dfds = rng.uniform(0.01, 1, P.nelem), -rng.uniform(0, 3, P.nelem)
+    for kind in (capi.FILTER_SENS_SIGMUND, capi.FILTER_SENS_BORRVALL):
+        f = capi.Filter(ctx, kind, *P.nbrs)
+        assert rel(f.sens_host(s, dfds), orc.sensitivity_filter(kind, P.nbrs, s, dfds)) < 1e-14
+        f.close()
+
+
+@pytest.mark.parametrize("m", [1, 2])
+def test_conlin_updates_vs_live_reference_fixture(ctx, live_conlin, m):
+    """CONLIN<T>::UpdateVariables (CONLIN.h:89-373): three consecutive updates, mixed-sign gradients, m = 1 and 2."""
+    n = 96
+    opt = capi.CONLIN(ctx, n, m, 1.0, np.zeros(m), np.full(m, 1.0e4), np.zeros(m), 0.01, 1.0)
+    opt.set_parameters(0.2, 1.0e-6)
+    x = live_conlin["s"].copy()
+    for it in range(3):
+        df = live_conlin["dfds"] * (1.0 + 0.1 * it) * np.where(np.arange(n) % 7 == 3, -0.05, 1.0)
+        g = np.array([x.sum() / (0.5 * n) - 1.0, 0.3 - x[: n // 2].sum() / n][:m])
+        dg = np.stack([np.full(n, 1.0 / (0.5 * n)), np.where(np.arange(n) < n // 2, -1.0 / n, 0.0)][:m])
+        xd, steps = opt.update_host(x, 1.0, df, g, dg)
+        assert np.abs(xd - live_conlin[f"conlin_m{m}_x"][it]).max() < 1e-7, it
+        x = live_conlin[f"conlin_m{m}_x"][it]
+    opt.close()
+
+
+def test_conlin_large_n_vs_oracle(ctx):
+    rng = np.random.default_rng(14)
+    n = 20000
+    x = rng.uniform(0.2, 0.8, n)
+    md = capi.CONLIN(ctx, n, 1, 1.0, [0.0], [1.0e4], [0.0], 0.01, 1.0)
+    md.set_parameters(0.2, 1.0e-6)
+    mo = orc.MMA(n, 1, 1.0, [0.0], [1.0e4], [0.0], 0.01, 1.0)
+    mo.set_conlin(0.2)
+    for k in range(3):
+        dfdx = -rng.uniform(0.1, 5.0, n)
+        dgdx = np.full(n, 1.0 / (0.5 * n)) * rng.uniform(0.9, 1.1, n)
+        g = np.array([x.sum() / (0.5 * n) - 1.0])
+        xo = mo.update(x, dfdx, g, dgdx[None, :])
+        xd, steps = md.update_host(x, 1.0, dfdx, g, dgdx[None, :])
+        assert np.abs(xd - xo).max() < 1e-7, k
+        x = xo
+    md.close()
+
+
+def test_simp_c1_conlin_vs_live_reference_and_golden_vtk(ctx, live_conlin, golden_dir):
+    """sample_optimize_density_CONLIN.cpp on the device: the first 12 iterations against the live-reference history, then
+    on to convergence (133 design iterations) against the committed Density_CONLIN.vtk."""
+    P = problems.cantilever2d(60, 40, opt_kind=problems.OPT_CONLIN)
+    S = capi.Simp(ctx, P)
+    hist = []
+    k = 0
+    for k in range(500):
+        st = S.iterate(check_convergence=True)
+        assert st["cg_relres"] < 1e-10
+        hist.append((st["f"], st["g"]))
+        if k == 11:
+            out = S.get()
+            assert np.abs(out["s"] - live_conlin["c1_conlin_s12"]).max() < 1e-6
+        if st["converged"]:
+            break
+    hist = np.array(hist)
+    np.testing.assert_allclose(hist[:12, 0], live_conlin["c1_conlin_hist"][:, 0], rtol=1e-8)
+    np.testing.assert_allclose(hist[:12, 1], live_conlin["c1_conlin_hist"][:, 1], rtol=0, atol=1e-9)
+    assert k + 1 == 133
+    g = np.load(os.path.join(golden_dir, "density_conlin.npz"))
+    out = S.get(want_r=True)
+    assert np.abs(out["rho"] - g["rho"]).max() < 2e-6
+    np.testing.assert_allclose(out["u"], g["u"], rtol=1e-5, atol=1e-11)
+    np.testing.assert_allclose(out["r"], g["r"], rtol=1e-5, atol=1e-7)
+    S.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # reaction / compliance / sensitivity passes and the fused design loop
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("make", [lambda: problems.cantilever2d(12, 8), lambda: problems.heat2d(10, 6), lambda: problems.cantilever3d(4, 3, 2)])

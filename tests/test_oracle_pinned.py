@@ -151,6 +151,62 @@ def test_c1_oc_full_run_vs_density_oc_vtk(golden_dir):
     np.testing.assert_allclose(R["r"], g["r"], rtol=6e-6, atol=1e-9)
 
 
+@pytest.fixture(scope="module")
+def live_conlin(golden_dir):
+    return np.load(os.path.join(golden_dir, "live_conlin.npz"))
+
+
+def test_sensitivity_filters_vs_live_fixture(live_conlin):
+    """SensitivityFilter (Sigmund) / SensitivityFilter2 (Borrvall), SensitivityFilter.h:44-55, 88-99: bit-exact."""
+    P = problems.cantilever2d(12, 8)
+    for kind, nm in ((2, "sigmund"), (3, "borrvall")):
+        out = orc.sensitivity_filter(kind, P.nbrs, live_conlin["s"], live_conlin["dfds"])
+        assert np.array_equal(out, live_conlin[f"sens_{nm}"])
+
+
+def _conlin_inputs(n, m, it, x, dfds):
+    df = dfds * (1.0 + 0.1 * it) * np.where(np.arange(n) % 7 == 3, -0.05, 1.0)
+    g = np.array([x.sum() / (0.5 * n) - 1.0, 0.3 - x[: n // 2].sum() / n][:m])
+    dg = np.stack([np.full(n, 1.0 / (0.5 * n)), np.where(np.arange(n) < n // 2, -1.0 / n, 0.0)][:m])
+    return df, g, dg
+
+
+@pytest.mark.parametrize("m", [1, 2])
+def test_conlin_updates_vs_live_fixture(live_conlin, m):
+    """CONLIN<T>::UpdateVariables (CONLIN.h:89-373) with one and two constraints and mixed-sign gradients."""
+    n = 96
+    opt = orc.MMA(n, m, 1.0, np.zeros(m), np.full(m, 1.0e4), np.zeros(m), 0.01, 1.0)
+    opt.set_conlin(0.2)
+    x = live_conlin["s"].copy()
+    for it in range(3):
+        df, g, dg = _conlin_inputs(n, m, it, x, live_conlin["dfds"])
+        x = opt.update(x, df, g, dg)
+        assert np.abs(x - live_conlin[f"conlin_m{m}_x"][it]).max() < 1e-12
+
+
+def test_c1_conlin_history_vs_live_fixture(live_conlin):
+    P = problems.cantilever2d(60, 40, opt_kind=problems.OPT_CONLIN)
+    R = orc.simp_run(P.eq, P.coords, P.conn, P.fixed, P.loads, P.filter_kind, P.nbrs, P.opt_kind, P.optp(), P.params(),
+                     12, np.full(P.nelem, 0.5), check_convergence=False)
+    np.testing.assert_allclose(R["hist"][:, 0], live_conlin["c1_conlin_hist"][:, 0], rtol=1e-8)
+    np.testing.assert_allclose(R["hist"][:, 1], live_conlin["c1_conlin_hist"][:, 1], rtol=0, atol=1e-9)
+    assert np.abs(R["rho"] - live_conlin["c1_conlin_rho12"]).max() < 1e-6
+    assert np.abs(R["s"] - live_conlin["c1_conlin_s12"]).max() < 1e-6
+
+
+def test_c1_conlin_full_run_vs_density_conlin_vtk(golden_dir):
+    """sample_optimize_density_CONLIN.cpp: 133 design iterations, objective 1.42395e-4, == Density_CONLIN.vtk."""
+    g = np.load(os.path.join(golden_dir, "density_conlin.npz"))
+    P = problems.cantilever2d(60, 40, opt_kind=problems.OPT_CONLIN)
+    R = orc.simp_run(P.eq, P.coords, P.conn, P.fixed, P.loads, P.filter_kind, P.nbrs, P.opt_kind, P.optp(), P.params(),
+                     500, np.full(P.nelem, 0.5))
+    assert R["iters"] == 133
+    assert abs(R["hist"][-1, 0] / P.scale0 - 1.42395e-4) < 1e-9
+    assert np.abs(R["rho"] - g["rho"]).max() < 2e-6
+    np.testing.assert_allclose(R["u"], g["u"], rtol=6e-6, atol=1e-12)
+    np.testing.assert_allclose(R["r"], g["r"], rtol=6e-6, atol=1e-9)
+
+
 def test_solid_hex8_vs_result_linear_vtk(golden_dir):
     g = np.load(os.path.join(golden_dir, "solid_linear.npz"))
     fixed = (g["fix_node"], g["fix_dof"], g["fix_val"])
