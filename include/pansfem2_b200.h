@@ -34,8 +34,23 @@ extern "C" {
 /* equation / element selection == the reference's template arguments
  *   PF2_EQ_PLANESTRAIN : PlaneStrainStiffness<double, ShapeFunction4Square, Gauss4Square>        (PlaneStrain.h:21)
  *   PF2_EQ_SOLID       : SolidLinearIsotropicElastic<double, ShapeFunction8Cubic, Gauss8Cubic>   (Solid.h:21)
- *   PF2_EQ_HEAT        : HeatTransfer<double, ShapeFunction4Square, Gauss4Square>                (HeatTransfer.h:20) */
+ *   PF2_EQ_HEAT        : HeatTransfer<double, ShapeFunction4Square, Gauss4Square>                (HeatTransfer.h:20)
+ * These three are the selections of the topology-optimisation drivers and run on specialised kernels. */
 enum { PF2_EQ_PLANESTRAIN = 0, PF2_EQ_SOLID = 1, PF2_EQ_HEAT = 2 };
+/* Any other <Equation, ShapeFunction, Integration> selection of the reference is an `eq` CODE built with PF2_EQ_CODE:
+ *   physics : the three above, PlaneStressStiffness (PlaneStress.h:21), PlaneStrainStiffnessSRI (PlaneStrain.h:63;
+ *             quad = ICD, the deviatoric rule, quad2 = ICV, the volumetric rule)
+ *   shape   : ShapeFunction3Triangle / 6Triangle / 4Square / 8Square / 4Tetrahedron / 8Cubic / 20Cubic (ShapeFunction.h)
+ *   quad    : Gauss1Triangle / 3Triangle / 1Square / 4Square / 9Square / 1Tetrahedron / 8Cubic / 27Cubic (GaussIntegration.h)
+ * 0 in a field means "the default of that physics" (Q4 + Gauss4Square, hex8 + Gauss8Cubic; SRI: Gauss4Square / Gauss1Square),
+ * so the legacy values 0, 1, 2 are themselves valid codes.  The rule must belong to the shape's reference domain
+ * (triangle, square, tetrahedron, cube), otherwise PF2_E_INVALID. */
+enum { PF2_PHYS_PLANESTRAIN = 0, PF2_PHYS_SOLID = 1, PF2_PHYS_HEAT = 2, PF2_PHYS_PLANESTRESS = 3, PF2_PHYS_PLANESTRAIN_SRI = 4 };
+enum { PF2_SHAPE_DEFAULT = 0, PF2_SHAPE_T3 = 1, PF2_SHAPE_T6 = 2, PF2_SHAPE_Q4 = 3, PF2_SHAPE_Q8 = 4, PF2_SHAPE_TET4 = 5,
+       PF2_SHAPE_HEX8 = 6, PF2_SHAPE_HEX20 = 7 };
+enum { PF2_QUAD_DEFAULT = 0, PF2_QUAD_G1TRI = 1, PF2_QUAD_G3TRI = 2, PF2_QUAD_G1SQ = 3, PF2_QUAD_G4SQ = 4, PF2_QUAD_G9SQ = 5,
+       PF2_QUAD_G1TET = 6, PF2_QUAD_G8CUBE = 7, PF2_QUAD_G27CUBE = 8 };
+#define PF2_EQ_CODE(phys, shape, quad, quad2) ((phys) | ((shape) << 8) | ((quad) << 16) | ((quad2) << 24))
 /* solver selection: CG (CG.h:124), ScalingCG (CG.h:420), ILU0CG (CG.h:320) */
 enum { PF2_SOLVER_CG = 0, PF2_SOLVER_SCALINGCG = 1, PF2_SOLVER_ILU0CG = 2 };
 /* DensityFilter (DensityFilter.h:45-71), HeavisideFilter (HeavisideFilter.h:61-99),
@@ -43,6 +58,9 @@ enum { PF2_SOLVER_CG = 0, PF2_SOLVER_SCALINGCG = 1, PF2_SOLVER_ILU0CG = 2 };
 enum { PF2_FILTER_DENSITY = 0, PF2_FILTER_HEAVISIDE = 1, PF2_FILTER_SENS_SIGMUND = 2, PF2_FILTER_SENS_BORRVALL = 3 };
 /* OC (OC.h:78), MMA (MMA.h:117), CONLIN (CONLIN.h:89) */
 enum { PF2_OPT_OC = 0, PF2_OPT_MMA = 1, PF2_OPT_CONLIN = 2 };
+
+/* decode an eq code: spatial dimension, nodes per element, dofs per node (any pointer may be NULL) */
+int pf2_eq_describe(int eq, int* dim, int* npe, int* ndof);
 
 typedef struct pf2_ctx pf2_ctx;
 typedef struct pf2_mesh pf2_mesh;

@@ -46,40 +46,145 @@ void orc_set_num_threads(int n) {
 #endif
 }
 
-static int ndof_of(int eq) { return eq == EQ_PLANESTRAIN ? 2 : (eq == EQ_SOLID ? 3 : 1); }
-static int dim_of(int eq) { return eq == EQ_SOLID ? 3 : 2; }
+/* eq codes of include/pansfem2_b200.h (PF2_EQ_CODE): phys | shape << 8 | quad << 16 | quad2 << 24; a zero field is the
+ * default of the physics, so the legacy values 0, 1, 2 are codes too. */
+enum { PHYS_PLANESTRAIN = 0, PHYS_SOLID = 1, PHYS_HEAT = 2, PHYS_PLANESTRESS = 3, PHYS_PLANESTRAIN_SRI = 4 };
+enum { SHAPE_T3 = 1, SHAPE_T6, SHAPE_Q4, SHAPE_Q8, SHAPE_TET4, SHAPE_HEX8, SHAPE_HEX20 };
+enum { QUAD_G1TRI = 1, QUAD_G3TRI, QUAD_G1SQ, QUAD_G4SQ, QUAD_G9SQ, QUAD_G1TET, QUAD_G8CUBE, QUAD_G27CUBE };
+typedef struct { int phys, shape, quad, quad2; } orc_sel;
+static orc_sel decode_eq(int eq) {
+    orc_sel s = { eq & 0xff, (eq >> 8) & 0xff, (eq >> 16) & 0xff, (eq >> 24) & 0xff };
+    int solid = s.phys == PHYS_SOLID;
+    if (!s.shape) s.shape = solid ? SHAPE_HEX8 : SHAPE_Q4;
+    int tri = s.shape == SHAPE_T3 || s.shape == SHAPE_T6;
+    if (!s.quad) s.quad = tri ? QUAD_G1TRI : (s.shape == SHAPE_TET4 ? QUAD_G1TET : (solid ? QUAD_G8CUBE : QUAD_G4SQ));
+    if (s.phys == PHYS_PLANESTRAIN_SRI && !s.quad2) s.quad2 = tri ? QUAD_G1TRI : QUAD_G1SQ;
+    return s;
+}
+static int ndof_of(int eq) { int phys = eq & 0xff; return phys == PHYS_SOLID ? 3 : (phys == PHYS_HEAT ? 1 : 2); }
+static int dim_of(int eq) { return (eq & 0xff) == PHYS_SOLID ? 3 : 2; }
+static int npe_of(int eq) {
+    static const int n[8] = { 0, 3, 6, 4, 8, 4, 8, 20 };
+    return n[decode_eq(eq).shape];
+}
+int orc_eq_npe(int eq) { return npe_of(eq); }
+#define ORC_MAX_NPE 20
+#define ORC_MAX_M 60        /* hex20 x 3 dofs */
 
 /* ------------------------------------------------------------------------------------------------------------
- * Shape functions and quadrature.
- * ShapeFunction4Square::dNdr  src/FEM/Controller/ShapeFunction.h:186-191
- * ShapeFunction8Cubic::dNdr   src/FEM/Controller/ShapeFunction.h:318-329
- * Gauss4Square points         src/FEM/Controller/GaussIntegration.h:143-148  (order (-,-),(+,-),(-,+),(+,+))
- * Gauss8Cubic points          src/FEM/Controller/GaussIntegration.h:231-240  (bottom CCW, top CCW); all weights 1.
+ * Shape functions (dN/dr, row k = d/dr_k, npe columns) -- src/FEM/Controller/ShapeFunction.h
+ *   ShapeFunction3Triangle :112-117   6Triangle :150-155   4Square :186-191   8Square :226-246
+ *   4Tetrahedron :277-283             8Cubic :318-329      20Cubic :396-461
  * ---------------------------------------------------------------------------------------------------------- */
-static void dndr_q4(const double* r, double* d /* 2x4 */) {
-    d[0] = -0.25 * (1.0 - r[1]); d[1] = 0.25 * (1.0 - r[1]); d[2] = 0.25 * (1.0 + r[1]); d[3] = -0.25 * (1.0 + r[1]);
-    d[4] = -0.25 * (1.0 - r[0]); d[5] = -0.25 * (1.0 + r[0]); d[6] = 0.25 * (1.0 + r[0]); d[7] = 0.25 * (1.0 - r[0]);
-}
-static void dndr_h8(const double* r, double* d /* 3x8 */) {
-    static const double sx[8] = { -1, 1, 1, -1, -1, 1, 1, -1 };
-    static const double sy[8] = { -1, -1, 1, 1, -1, -1, 1, 1 };
-    static const double sz[8] = { -1, -1, -1, -1, 1, 1, 1, 1 };
-    for (int n = 0; n < 8; n++) {
-        /* the reference writes e.g. -0.125*(1-r1)*(1-r2); sign*0.125*(1 + s*r) evaluates to the same doubles */
-        d[n]      = sx[n] * 0.125 * (1.0 + sy[n] * r[1]) * (1.0 + sz[n] * r[2]);
-        d[8 + n]  = sy[n] * 0.125 * (1.0 + sz[n] * r[2]) * (1.0 + sx[n] * r[0]);
-        d[16 + n] = sz[n] * 0.125 * (1.0 + sx[n] * r[0]) * (1.0 + sy[n] * r[1]);
+static const double HX[8] = { -1, 1, 1, -1, -1, 1, 1, -1 }, HY[8] = { -1, -1, 1, 1, -1, -1, 1, 1 }, HZ[8] = { -1, -1, -1, -1, 1, 1, 1, 1 };
+
+static void shape_dndr(int shape, const double* r, double* d) {
+    const double r0 = r[0], r1 = r[1], r2 = r[2];
+    switch (shape) {
+    case SHAPE_T3:
+        d[0] = 1.0; d[1] = 0.0; d[2] = -1.0;
+        d[3] = 0.0; d[4] = 1.0; d[5] = -1.0;
+        break;
+    case SHAPE_T6:
+        d[0] = 4.0 * r0 - 1.0; d[1] = 0.0; d[2] = -3.0 + 4.0 * r0 + 4.0 * r1; d[3] = 4.0 * r1; d[4] = -4.0 * r1; d[5] = 4.0 * (1.0 - 2.0 * r0 - r1);
+        d[6] = 0.0; d[7] = 4.0 * r1 - 1.0; d[8] = -3.0 + 4.0 * r0 + 4.0 * r1; d[9] = 4.0 * r0; d[10] = 4.0 * (1.0 - r0 - 2.0 * r1); d[11] = -4.0 * r0;
+        break;
+    case SHAPE_Q4:
+        d[0] = -0.25 * (1.0 - r1); d[1] = 0.25 * (1.0 - r1); d[2] = 0.25 * (1.0 + r1); d[3] = -0.25 * (1.0 + r1);
+        d[4] = -0.25 * (1.0 - r0); d[5] = -0.25 * (1.0 + r0); d[6] = 0.25 * (1.0 + r0); d[7] = 0.25 * (1.0 - r0);
+        break;
+    case SHAPE_Q8:      /* the reference differentiates each product term by term; kept in that form */
+        d[0] = 0.25 * (-(1.0 - r1) * (-r0 - r1 - 1.0) - (1.0 - r0) * (1.0 - r1));
+        d[1] = 0.25 * ((1.0 - r1) * (r0 - r1 - 1.0) + (1.0 + r0) * (1.0 - r1));
+        d[2] = 0.25 * ((1.0 + r1) * (r0 + r1 - 1.0) + (1.0 + r0) * (1.0 + r1));
+        d[3] = 0.25 * (-(1.0 + r1) * (-r0 + r1 - 1.0) - (1.0 - r0) * (1.0 + r1));
+        d[4] = -r0 * (1.0 - r1);
+        d[5] = 0.5 * (1.0 + r1) * (1.0 - r1);
+        d[6] = -r0 * (1.0 + r1);
+        d[7] = -0.5 * (1.0 + r1) * (1.0 - r1);
+        d[8] = 0.25 * (-(1.0 - r0) * (-r0 - r1 - 1.0) - (1.0 - r0) * (1.0 - r1));
+        d[9] = 0.25 * (-(1.0 + r0) * (r0 - r1 - 1.0) - (1.0 + r0) * (1.0 - r1));
+        d[10] = 0.25 * ((1.0 + r0) * (r0 + r1 - 1.0) + (1.0 + r0) * (1.0 + r1));
+        d[11] = 0.25 * ((1.0 - r0) * (-r0 + r1 - 1.0) + (1.0 - r0) * (1.0 + r1));
+        d[12] = -0.5 * (1.0 + r0) * (1.0 - r0);
+        d[13] = -r1 * (1.0 + r0);
+        d[14] = 0.5 * (1.0 + r0) * (1.0 - r0);
+        d[15] = -r1 * (1.0 - r0);
+        break;
+    case SHAPE_TET4:
+        for (int k = 0; k < 3; k++) for (int n = 0; n < 4; n++) d[k * 4 + n] = (n == 3) ? -1.0 : (n == k ? 1.0 : 0.0);
+        break;
+    case SHAPE_HEX8:
+        for (int n = 0; n < 8; n++) {
+            /* the reference writes e.g. -0.125*(1-r1)*(1-r2); sign*0.125*(1 + s*r) evaluates to the same doubles */
+            d[n]      = HX[n] * 0.125 * (1.0 + HY[n] * r1) * (1.0 + HZ[n] * r2);
+            d[8 + n]  = HY[n] * 0.125 * (1.0 + HZ[n] * r2) * (1.0 + HX[n] * r0);
+            d[16 + n] = HZ[n] * 0.125 * (1.0 + HX[n] * r0) * (1.0 + HY[n] * r1);
+        }
+        break;
+    default: {          /* SHAPE_HEX20 */
+        /* corners: 0.125*sx*(1 + sy r1)(1 + sz r2)(2 sx r0 + sy r1 + sz r2 - 1) is the reference's
+           +-0.125*(1 -+ r1)*(1 -+ r2)*(1 +- 2 r0 +- r1 +- r2) with the signs multiplied out */
+        for (int n = 0; n < 8; n++) {
+            const double a = 1.0 + HX[n] * r0, b = 1.0 + HY[n] * r1, c = 1.0 + HZ[n] * r2;
+            d[n]      = 0.125 * HX[n] * b * c * (2.0 * HX[n] * r0 + HY[n] * r1 + HZ[n] * r2 - 1.0);
+            d[20 + n] = 0.125 * HY[n] * a * c * (HX[n] * r0 + 2.0 * HY[n] * r1 + HZ[n] * r2 - 1.0);
+            d[40 + n] = 0.125 * HZ[n] * a * b * (HX[n] * r0 + HY[n] * r1 + 2.0 * HZ[n] * r2 - 1.0);
+        }
+        /* mid-edge nodes in the reference's order: 8,10,12,14 on r0-edges; 9,11,13,15 on r1-edges; 16..19 on r2-edges */
+        static const double e0y[4] = { -1, 1, -1, 1 }, e0z[4] = { -1, -1, 1, 1 };       /* nodes 8,10,12,14 */
+        static const double e1x[4] = { 1, -1, 1, -1 }, e1z[4] = { -1, -1, 1, 1 };       /* nodes 9,11,13,15 */
+        static const double e2x[4] = { -1, 1, 1, -1 }, e2y[4] = { -1, -1, 1, 1 };       /* nodes 16,17,18,19 */
+        for (int q = 0; q < 4; q++) {
+            int n = 8 + 2 * q;
+            d[n]      = -0.5 * r0 * (1.0 + e0y[q] * r1) * (1.0 + e0z[q] * r2);
+            d[20 + n] = 0.25 * e0y[q] * (1.0 - r0 * r0) * (1.0 + e0z[q] * r2);
+            d[40 + n] = 0.25 * e0z[q] * (1.0 - r0 * r0) * (1.0 + e0y[q] * r1);
+            n = 9 + 2 * q;
+            d[n]      = 0.25 * e1x[q] * (1.0 - r1 * r1) * (1.0 + e1z[q] * r2);
+            d[20 + n] = -0.5 * (1.0 + e1x[q] * r0) * r1 * (1.0 + e1z[q] * r2);
+            d[40 + n] = 0.25 * e1z[q] * (1.0 + e1x[q] * r0) * (1.0 - r1 * r1);
+            n = 16 + q;
+            d[n]      = 0.25 * e2x[q] * (1.0 + e2y[q] * r1) * (1.0 - r2 * r2);
+            d[20 + n] = 0.25 * e2y[q] * (1.0 + e2x[q] * r0) * (1.0 - r2 * r2);
+            d[40 + n] = -0.5 * (1.0 + e2x[q] * r0) * (1.0 + e2y[q] * r1) * r2;
+        }
+        break;
+    }
     }
 }
-static void gauss_point(int dim, int g, double* r) {
-    const double a = 1.0 / sqrt(3.0);
-    if (dim == 2) {
-        static const int s[4][2] = { { -1, -1 }, { 1, -1 }, { -1, 1 }, { 1, 1 } };
-        r[0] = s[g][0] * a; r[1] = s[g][1] * a;
-    } else {
-        static const int s[8][3] = { { -1, -1, -1 }, { 1, -1, -1 }, { 1, 1, -1 }, { -1, 1, -1 },
-                                     { -1, -1, 1 }, { 1, -1, 1 }, { 1, 1, 1 }, { -1, 1, 1 } };
-        r[0] = s[g][0] * a; r[1] = s[g][1] * a; r[2] = s[g][2] * a;
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Integration rules: point g and per-axis weights -- src/FEM/Controller/GaussIntegration.h
+ *   Gauss1Triangle :72-82  Gauss3Triangle :94-107  Gauss1Square :120-130  Gauss4Square :142-157 (order (-,-),(+,-),(-,+),(+,+))
+ *   Gauss9Square :170-195  Gauss1Tetrahedron :208-218  Gauss8Cubic :230-253 (ordered like the hex8 nodes)  Gauss27Cubic :266-327
+ * ---------------------------------------------------------------------------------------------------------- */
+static int quad_count(int quad) {
+    static const int n[9] = { 0, 1, 3, 1, 4, 9, 1, 8, 27 };
+    return n[quad];
+}
+static void quad_point(int quad, int g, double* r, double* w) {
+    const double a3 = 1.0 / sqrt(3.0), s35 = sqrt(3.0 / 5.0);
+    r[0] = r[1] = r[2] = 0.0; w[0] = w[1] = w[2] = 1.0;
+    switch (quad) {
+    case QUAD_G1TRI: r[0] = 1.0 / 3.0; r[1] = 1.0 / 3.0; w[0] = w[1] = 1.0 / sqrt(2.0); break;
+    case QUAD_G3TRI: r[0] = (g == 1) ? 2.0 / 3.0 : 1.0 / 6.0; r[1] = (g == 2) ? 2.0 / 3.0 : 1.0 / 6.0; w[0] = w[1] = 1.0 / sqrt(6.0); break;
+    case QUAD_G1SQ: w[0] = w[1] = 2.0; break;
+    case QUAD_G4SQ: { static const int s[4][2] = { { -1, -1 }, { 1, -1 }, { -1, 1 }, { 1, 1 } }; r[0] = s[g][0] * a3; r[1] = s[g][1] * a3; break; }
+    case QUAD_G9SQ: {
+        int i = g % 3, j = g / 3;
+        r[0] = (i - 1) * s35; r[1] = (j - 1) * s35;
+        w[0] = (i == 1) ? 8.0 / 9.0 : 5.0 / 9.0; w[1] = (j == 1) ? 8.0 / 9.0 : 5.0 / 9.0;
+        break;
+    }
+    case QUAD_G1TET: r[0] = r[1] = r[2] = 1.0 / 4.0; w[0] = w[1] = w[2] = 1.0 / cbrt(6.0); break;
+    case QUAD_G8CUBE: r[0] = HX[g] * a3; r[1] = HY[g] * a3; r[2] = HZ[g] * a3; break;
+    default: {
+        int i = g % 3, j = (g / 3) % 3, k = g / 9;
+        r[0] = (i - 1) * s35; r[1] = (j - 1) * s35; r[2] = (k - 1) * s35;
+        w[0] = (i == 1) ? 8.0 / 9.0 : 5.0 / 9.0; w[1] = (j == 1) ? 8.0 / 9.0 : 5.0 / 9.0; w[2] = (k == 1) ? 8.0 / 9.0 : 5.0 / 9.0;
+        break;
+    }
     }
 }
 
@@ -118,69 +223,89 @@ static void inv_d(int d, const double* v, double* inv) {
 }
 
 /* ------------------------------------------------------------------------------------------------------------
- * Element matrices.
+ * Element matrices for any <Equation, SF, IC> selection.
  * PlaneStrainStiffness           src/FEM/Equation/PlaneStrain.h:21-58
+ * PlaneStrainStiffnessSRI        src/FEM/Equation/PlaneStrain.h:63-125  (volumetric D with ICV, then deviatoric D with ICD)
+ * PlaneStressStiffness           src/FEM/Equation/PlaneStress.h:21-58
  * SolidLinearIsotropicElastic    src/FEM/Equation/Solid.h:21-64
  * HeatTransfer                   src/FEM/Equation/HeatTransfer.h:20-43
  * xe: npe x dim coordinates of the element's nodes.  Ke: (npe*ndof)^2 row-major.
  * Accumulation order kept: Ke += ((((B^T D) B) J) t) w0 w1 [w2]   (PlaneStrain.h:56, Solid.h:62, HeatTransfer.h:41)
  * ---------------------------------------------------------------------------------------------------------- */
-void orc_element_matrix(int eq, const double* xe, double E, double V, double t, double* Ke) {
-    const int dim = dim_of(eq), npe = (eq == EQ_SOLID) ? 8 : 4, ndof = ndof_of(eq), m = npe * ndof;
-    const int ns = (eq == EQ_PLANESTRAIN) ? 3 : (eq == EQ_SOLID ? 6 : dim);
-    double D[36];
-    memset(D, 0, sizeof D);
-    if (eq == EQ_PLANESTRAIN) {
-        D[0] = 1.0 - V; D[1] = V; D[3] = V; D[4] = 1.0 - V; D[8] = 0.5 * (1.0 - 2.0 * V);
-        double f = E / ((1.0 - 2.0 * V) * (1.0 + V));
-        for (int i = 0; i < 9; i++) D[i] *= f;
-    } else if (eq == EQ_SOLID) {
-        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) D[i * 6 + j] = (i == j) ? 1.0 - V : V;
-        for (int i = 3; i < 6; i++) D[i * 6 + i] = 0.5 * (1.0 - 2.0 * V);
-        double f = E / ((1.0 + V) * (1.0 - 2.0 * V));
-        for (int i = 0; i < 36; i++) D[i] *= f;
-    }
-    memset(Ke, 0, sizeof(double) * m * m);
-    const int ng = (dim == 2) ? 4 : 8;
+static void accumulate_rule(int phys, int shape, int quad, int dim, int npe, int ndof, const double* xe, const double* D, int ns,
+                            double alpha, double t, double* Ke) {
+    const int m = npe * ndof, ng = quad_count(quad);
     for (int g = 0; g < ng; g++) {
-        double r[3], dNdr[24], dXdr[9], inv[9], dNdX[24];
-        gauss_point(dim, g, r);
-        if (dim == 2) dndr_q4(r, dNdr); else dndr_h8(r, dNdr);
+        double r[3], w[3], dNdr[3 * ORC_MAX_NPE], dXdr[9], inv[9], dNdX[3 * ORC_MAX_NPE];
+        quad_point(quad, g, r, w);
+        shape_dndr(shape, r, dNdr);
         matmul(dim, npe, dim, dNdr, xe, dXdr);
         double J = det_d(dim, dXdr);
         inv_d(dim, dXdr, inv);
         matmul(dim, dim, npe, inv, dNdr, dNdX);
-        double B[6 * 24], Bt[24 * 6], BtD[24 * 6], BtDB[24 * 24];
-        memset(B, 0, sizeof B);
-        if (eq == EQ_PLANESTRAIN) {
+        double B[6 * ORC_MAX_M], Bt[ORC_MAX_M * 6], BtD[ORC_MAX_M * 6], BtDB[ORC_MAX_M * ORC_MAX_M];
+        memset(B, 0, sizeof(double) * (size_t)ns * m);
+        if (phys == PHYS_SOLID) {
             for (int n = 0; n < npe; n++) {
-                B[0 * m + 2 * n] = dNdX[n];             /* row 0: dN/dx */
-                B[1 * m + 2 * n + 1] = dNdX[npe + n];   /* row 1: dN/dy */
-                B[2 * m + 2 * n] = dNdX[npe + n]; B[2 * m + 2 * n + 1] = dNdX[n];
-            }
-        } else if (eq == EQ_SOLID) {
-            for (int n = 0; n < npe; n++) {
-                double dx = dNdX[n], dy = dNdX[8 + n], dz = dNdX[16 + n];
+                double dx = dNdX[n], dy = dNdX[npe + n], dz = dNdX[2 * npe + n];
                 B[0 * m + 3 * n] = dx; B[1 * m + 3 * n + 1] = dy; B[2 * m + 3 * n + 2] = dz;
                 B[3 * m + 3 * n] = dy; B[3 * m + 3 * n + 1] = dx;            /* gamma_xy */
                 B[4 * m + 3 * n + 1] = dz; B[4 * m + 3 * n + 2] = dy;        /* gamma_yz */
                 B[5 * m + 3 * n] = dz; B[5 * m + 3 * n + 2] = dx;            /* gamma_zx */
             }
-        } else {
+        } else if (phys == PHYS_HEAT) {
             memcpy(B, dNdX, sizeof(double) * dim * npe);
+        } else {
+            for (int n = 0; n < npe; n++) {
+                B[0 * m + 2 * n] = dNdX[n];             /* row 0: dN/dx */
+                B[1 * m + 2 * n + 1] = dNdX[npe + n];   /* row 1: dN/dy */
+                B[2 * m + 2 * n] = dNdX[npe + n]; B[2 * m + 2 * n + 1] = dNdX[n];
+            }
         }
         for (int i = 0; i < ns; i++) for (int j = 0; j < m; j++) Bt[j * ns + i] = B[i * m + j];
-        double w = 1.0; /* IC::Weights are all 1.0 */
-        if (eq == EQ_HEAT) {
+        if (phys == PHYS_HEAT) {
             matmul(m, ns, m, Bt, B, BtDB);
-            for (int i = 0; i < m * m; i++) Ke[i] += BtDB[i] * J * E * t * w * w;    /* E carries alpha */
+            for (int i = 0; i < m * m; i++) Ke[i] += BtDB[i] * J * alpha * t * w[0] * w[1];
         } else {
             matmul(m, ns, ns, Bt, D, BtD);
             matmul(m, ns, m, BtD, B, BtDB);
-            if (eq == EQ_PLANESTRAIN) for (int i = 0; i < m * m; i++) Ke[i] += BtDB[i] * J * t * w * w;
-            else for (int i = 0; i < m * m; i++) Ke[i] += BtDB[i] * J * w * w * w;
+            if (phys == PHYS_SOLID) for (int i = 0; i < m * m; i++) Ke[i] += BtDB[i] * J * w[0] * w[1] * w[2];
+            else for (int i = 0; i < m * m; i++) Ke[i] += BtDB[i] * J * t * w[0] * w[1];
         }
     }
+}
+
+void orc_element_matrix(int eq, const double* xe, double E, double V, double t, double* Ke) {
+    const orc_sel s = decode_eq(eq);
+    const int dim = dim_of(eq), npe = npe_of(eq), ndof = ndof_of(eq), m = npe * ndof;
+    const int ns = (s.phys == PHYS_SOLID) ? 6 : (s.phys == PHYS_HEAT ? dim : 3);
+    double D[36];
+    memset(D, 0, sizeof D);
+    memset(Ke, 0, sizeof(double) * m * m);
+    if (s.phys == PHYS_PLANESTRAIN) {
+        D[0] = 1.0 - V; D[1] = V; D[3] = V; D[4] = 1.0 - V; D[8] = 0.5 * (1.0 - 2.0 * V);
+        double f = E / ((1.0 - 2.0 * V) * (1.0 + V));
+        for (int i = 0; i < 9; i++) D[i] *= f;
+    } else if (s.phys == PHYS_PLANESTRESS) {
+        D[0] = 1.0; D[1] = V; D[3] = V; D[4] = 1.0; D[8] = 0.5 * (1.0 - V);
+        double f = E / ((1.0 - V) * (1.0 + V));
+        for (int i = 0; i < 9; i++) D[i] *= f;
+    } else if (s.phys == PHYS_SOLID) {
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) D[i * 6 + j] = (i == j) ? 1.0 - V : V;
+        for (int i = 3; i < 6; i++) D[i * 6 + i] = 0.5 * (1.0 - 2.0 * V);
+        double f = E / ((1.0 + V) * (1.0 - 2.0 * V));
+        for (int i = 0; i < 36; i++) D[i] *= f;
+    } else if (s.phys == PHYS_PLANESTRAIN_SRI) {
+        D[0] = 1.0; D[1] = 1.0; D[3] = 1.0; D[4] = 1.0;
+        double f = E / (3.0 * (1.0 - 2.0 * V));
+        for (int i = 0; i < 9; i++) D[i] *= f;
+        accumulate_rule(s.phys, s.shape, s.quad2, dim, npe, ndof, xe, D, ns, E, t, Ke);
+        memset(D, 0, sizeof D);
+        D[0] = 4.0; D[1] = -2.0; D[3] = -2.0; D[4] = 4.0; D[8] = 3.0;
+        f = E / (6.0 * (1.0 + V));
+        for (int i = 0; i < 9; i++) D[i] *= f;
+    }
+    accumulate_rule(s.phys, s.shape, s.quad, dim, npe, ndof, xe, D, ns, E, t, Ke);     /* heat: E carries alpha */
 }
 
 /* ------------------------------------------------------------------------------------------------------------
@@ -309,10 +434,10 @@ orc_system* orc_system_from_csr(int n, const int* indptr, const int* indices, co
 void orc_assemble_numeric(orc_system* S, int eq, const double* coords, int nelem, const int* conn,
                           const int* nodetoglobal, const double* ufixed, const double* Emod, double V, double t,
                           int nload, const int* lnode, const int* ldof, const double* lval, double* times) {
-    const int dim = dim_of(eq), npe = (eq == EQ_SOLID) ? 8 : 4, ndof = ndof_of(eq), m = npe * ndof;
+    const int dim = dim_of(eq), npe = npe_of(eq), ndof = ndof_of(eq), m = npe * ndof;
     memset(S->data, 0, sizeof(double) * (size_t)S->indptr[S->n]);
     memset(S->F, 0, sizeof(double) * (size_t)S->n);
-    double Ke[576], xe[24], te = 0, ts = 0;
+    double Ke[ORC_MAX_M * ORC_MAX_M], xe[3 * ORC_MAX_NPE], te = 0, ts = 0;
     for (int e = 0; e < nelem; e++) {
         const int* el = conn + (size_t)e * npe;
         double t0 = now_s();
@@ -840,8 +965,8 @@ void orc_mma_update(orc_mma* M, double* xk, const double* dfdx, const double* gv
 double orc_compliance_sens(int eq, int nnode, const double* coords, int nelem, const int* conn, const double* u /* nnode*ndof */,
                            const double* rho, double E0, double E1, double V, double t, double p, double scale0,
                            double* r_out /* nnode*ndof */, double* dfdrho) {
-    const int dim = dim_of(eq), npe = (eq == EQ_SOLID) ? 8 : 4, ndof = ndof_of(eq), m = npe * ndof;
-    double Ke[576], xe[24], ue[24], Keue[24];
+    const int dim = dim_of(eq), npe = npe_of(eq), ndof = ndof_of(eq), m = npe * ndof;
+    double Ke[ORC_MAX_M * ORC_MAX_M], xe[3 * ORC_MAX_NPE], ue[ORC_MAX_M], Keue[ORC_MAX_M];
     memset(r_out, 0, sizeof(double) * (size_t)nnode * ndof);
     for (int e = 0; e < nelem; e++) {
         const int* el = conn + (size_t)e * npe;
@@ -879,7 +1004,7 @@ int orc_simp_run(int eq, int nnode, const double* coords, int nelem, const int* 
                  int fkind, const long long* rowptr, const int* nbr, const double* w,
                  int opt_kind, const double* optp, const double* params, int niter, int check_convergence,
                  double* s, double* rho, double* u_out, double* r_out, double* hist, double* phase) {
-    const int npe = (eq == EQ_SOLID) ? 8 : 4, ndof = ndof_of(eq);
+    const int npe = npe_of(eq), ndof = ndof_of(eq);
     const double E0 = params[0], E1 = params[1], V = params[2], p = params[3], weightlimit = params[4];
     const double scale0 = params[5], scale1 = params[6], thick = params[7];
     double beta = params[8];

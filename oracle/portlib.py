@@ -15,8 +15,12 @@ LIB_PATH = os.path.join(_HERE, "libpf2oracle.so")
 EQ_PLANESTRAIN, EQ_SOLID, EQ_HEAT = 0, 1, 2
 FILTER_DENSITY, FILTER_HEAVISIDE = 0, 1
 OPT_OC, OPT_MMA, OPT_CONLIN = 0, 1, 2
-NDOF = {EQ_PLANESTRAIN: 2, EQ_SOLID: 3, EQ_HEAT: 1}
-NPE = {EQ_PLANESTRAIN: 4, EQ_SOLID: 8, EQ_HEAT: 4}
+
+
+def ndof_of(eq):
+    """dofs per node of an eq code (include/pansfem2_b200.h PF2_EQ_CODE): the physics is the low byte."""
+    phys = eq & 0xff
+    return 3 if phys == 1 else (1 if phys == 2 else 2)
 
 _lib = None
 
@@ -68,7 +72,7 @@ def num_threads():
 
 def element_matrix(eq, xe, E, V=0.3, t=1.0):
     xe = _f64(xe)
-    m = NPE[eq] * NDOF[eq]
+    m = xe.shape[0] * ndof_of(eq)
     Ke = np.zeros((m, m))
     lib().orc_element_matrix(eq, _p(xe, np.float64), C.c_double(E), C.c_double(V), C.c_double(t), _p(Ke, np.float64))
     return Ke
@@ -140,7 +144,7 @@ def system_from_csr(indptr, indices, data):
 def assemble(eq, coords, conn, fixed, loads, Emod, V=0.3, t=1.0):
     """Returns (System, nodetoglobal, ufixed, times)."""
     coords, conn = _f64(coords), _i32(conn)
-    nnode, ndof = coords.shape[0], NDOF[eq]
+    nnode, ndof = coords.shape[0], ndof_of(eq)
     k, n2g, ufix = dofmap(nnode, ndof, fixed)
     S = System(lib().orc_pattern(nnode, ndof, conn.shape[1], conn.shape[0], _p(conn, np.int32), _p(n2g, np.int32), k))
     ln, ld, lv = _i32(loads[0]), _i32(loads[1]), _f64(loads[2])
@@ -240,7 +244,7 @@ def compliance_sens(eq, coords, conn, u, rho, E0, E1, V, t, p, scale0):
 
 def simp_run(eq, coords, conn, fixed, loads, filter_kind, nbrs, opt_kind, optp, params, niter, s0, check_convergence=True):
     coords, conn = _f64(coords), _i32(conn)
-    nnode, nelem, ndof = coords.shape[0], conn.shape[0], NDOF[eq]
+    nnode, nelem, ndof = coords.shape[0], conn.shape[0], ndof_of(eq)
     fn, fd, fv = _i32(fixed[0]), _i32(fixed[1]), _f64(fixed[2])
     ln, ld, lv = _i32(loads[0]), _i32(loads[1]), _f64(loads[2])
     rowptr, nbr, w = _i64(nbrs[0]), _i32(nbrs[1]), _f64(nbrs[2])

@@ -35,6 +35,7 @@
 #undef private
 #include "LinearAlgebra/Solvers/CG.h"
 #include "FEM/Equation/PlaneStrain.h"
+#include "FEM/Equation/PlaneStress.h"
 #include "FEM/Equation/Solid.h"
 #include "FEM/Equation/HeatTransfer.h"
 #include "FEM/Equation/General.h"
@@ -70,18 +71,68 @@ struct Quiet {
     ~Quiet() { std::cout.rdbuf(old); }
 };
 
-int ndof_of(int eq) { return eq == EQ_PLANESTRAIN ? 2 : (eq == EQ_SOLID ? 3 : 1); }
+// eq codes of include/pansfem2_b200.h (PF2_EQ_CODE): phys | shape << 8 | quad << 16 | quad2 << 24, 0 = the physics' default
+enum { PHYS_PLANESTRAIN = 0, PHYS_SOLID = 1, PHYS_HEAT = 2, PHYS_PLANESTRESS = 3, PHYS_PLANESTRAIN_SRI = 4 };
+enum { SHAPE_T3 = 1, SHAPE_T6, SHAPE_Q4, SHAPE_Q8, SHAPE_TET4, SHAPE_HEX8, SHAPE_HEX20 };
+enum { QUAD_G1TRI = 1, QUAD_G3TRI, QUAD_G1SQ, QUAD_G4SQ, QUAD_G9SQ, QUAD_G1TET, QUAD_G8CUBE, QUAD_G27CUBE };
+struct Sel { int phys, shape, quad, quad2; };
+Sel decode(int eq) {
+    Sel s = { eq & 0xff, (eq >> 8) & 0xff, (eq >> 16) & 0xff, (eq >> 24) & 0xff };
+    bool solid = s.phys == PHYS_SOLID;
+    if (!s.shape) s.shape = solid ? SHAPE_HEX8 : SHAPE_Q4;
+    bool tri = s.shape == SHAPE_T3 || s.shape == SHAPE_T6;
+    if (!s.quad) s.quad = tri ? QUAD_G1TRI : (s.shape == SHAPE_TET4 ? QUAD_G1TET : (solid ? QUAD_G8CUBE : QUAD_G4SQ));
+    if (s.phys == PHYS_PLANESTRAIN_SRI && !s.quad2) s.quad2 = tri ? QUAD_G1TRI : QUAD_G1SQ;
+    return s;
+}
+int ndof_of(int eq) { int phys = eq & 0xff; return phys == PHYS_SOLID ? 3 : (phys == PHYS_HEAT ? 1 : 2); }
 
-// One element matrix through the reference's own template selection
-// (PlaneStrain.h:21, Solid.h:21, HeatTransfer.h:20 with ShapeFunction4Square/8Cubic + Gauss4Square/8Cubic).
-void element_matrix(int eq, Matrix<double>& Ke, std::vector<std::vector<std::pair<int, int> > >& n2e,
-                    const std::vector<int>& element, std::vector<Vector<double> >& x, double E, double V, double t) {
-    if (eq == EQ_PLANESTRAIN) {
-        PlaneStrainStiffness<double, ShapeFunction4Square, Gauss4Square>(Ke, n2e, element, { 0, 1 }, x, E, V, t);
-    } else if (eq == EQ_SOLID) {
-        SolidLinearIsotropicElastic<double, ShapeFunction8Cubic, Gauss8Cubic>(Ke, n2e, element, { 0, 1, 2 }, x, E, V);
-    } else {
-        HeatTransfer<double, ShapeFunction4Square, Gauss4Square>(Ke, n2e, element, { 0 }, x, E, t);
+typedef std::vector<std::vector<std::pair<int, int> > > N2E;
+
+// 2-D selections: the element routine <SF, IC> of the chosen physics, SRI with <SF, ICV, ICD> (PlaneStrain.h:63)
+template<template<class>class SF, template<class>class IC, template<class>class ICV>
+void em2d(const Sel& s, Matrix<double>& Ke, N2E& n2e, const std::vector<int>& element, std::vector<Vector<double> >& x, double E, double V, double t) {
+    switch (s.phys) {
+        case PHYS_PLANESTRAIN: PlaneStrainStiffness<double, SF, IC>(Ke, n2e, element, { 0, 1 }, x, E, V, t); break;
+        case PHYS_PLANESTRESS: PlaneStressStiffness<double, SF, IC>(Ke, n2e, element, { 0, 1 }, x, E, V, t); break;
+        case PHYS_PLANESTRAIN_SRI: PlaneStrainStiffnessSRI<double, SF, ICV, IC>(Ke, n2e, element, { 0, 1 }, x, E, V, t); break;
+        default: HeatTransfer<double, SF, IC>(Ke, n2e, element, { 0 }, x, E, t); break;
+    }
+}
+template<template<class>class SF>
+void em_tri(const Sel& s, Matrix<double>& Ke, N2E& n2e, const std::vector<int>& el, std::vector<Vector<double> >& x, double E, double V, double t) {
+    if (s.quad == QUAD_G1TRI) { if (s.quad2 == QUAD_G3TRI) em2d<SF, Gauss1Triangle, Gauss3Triangle>(s, Ke, n2e, el, x, E, V, t); else em2d<SF, Gauss1Triangle, Gauss1Triangle>(s, Ke, n2e, el, x, E, V, t); }
+    else { if (s.quad2 == QUAD_G3TRI) em2d<SF, Gauss3Triangle, Gauss3Triangle>(s, Ke, n2e, el, x, E, V, t); else em2d<SF, Gauss3Triangle, Gauss1Triangle>(s, Ke, n2e, el, x, E, V, t); }
+}
+template<template<class>class SF, template<class>class IC>
+void em_sq2(const Sel& s, Matrix<double>& Ke, N2E& n2e, const std::vector<int>& el, std::vector<Vector<double> >& x, double E, double V, double t) {
+    if (s.quad2 == QUAD_G4SQ) em2d<SF, IC, Gauss4Square>(s, Ke, n2e, el, x, E, V, t);
+    else if (s.quad2 == QUAD_G9SQ) em2d<SF, IC, Gauss9Square>(s, Ke, n2e, el, x, E, V, t);
+    else em2d<SF, IC, Gauss1Square>(s, Ke, n2e, el, x, E, V, t);
+}
+template<template<class>class SF>
+void em_sq(const Sel& s, Matrix<double>& Ke, N2E& n2e, const std::vector<int>& el, std::vector<Vector<double> >& x, double E, double V, double t) {
+    if (s.quad == QUAD_G1SQ) em_sq2<SF, Gauss1Square>(s, Ke, n2e, el, x, E, V, t);
+    else if (s.quad == QUAD_G9SQ) em_sq2<SF, Gauss9Square>(s, Ke, n2e, el, x, E, V, t);
+    else em_sq2<SF, Gauss4Square>(s, Ke, n2e, el, x, E, V, t);
+}
+template<template<class>class SF>
+void em_cube(const Sel& s, Matrix<double>& Ke, N2E& n2e, const std::vector<int>& el, std::vector<Vector<double> >& x, double E, double V) {
+    if (s.quad == QUAD_G27CUBE) SolidLinearIsotropicElastic<double, SF, Gauss27Cubic>(Ke, n2e, el, { 0, 1, 2 }, x, E, V);
+    else SolidLinearIsotropicElastic<double, SF, Gauss8Cubic>(Ke, n2e, el, { 0, 1, 2 }, x, E, V);
+}
+
+// One element matrix through the reference's own template selection.
+void element_matrix(int eq, Matrix<double>& Ke, N2E& n2e, const std::vector<int>& element, std::vector<Vector<double> >& x, double E, double V, double t) {
+    Sel s = decode(eq);
+    switch (s.shape) {
+        case SHAPE_T3: em_tri<ShapeFunction3Triangle>(s, Ke, n2e, element, x, E, V, t); break;
+        case SHAPE_T6: em_tri<ShapeFunction6Triangle>(s, Ke, n2e, element, x, E, V, t); break;
+        case SHAPE_Q4: em_sq<ShapeFunction4Square>(s, Ke, n2e, element, x, E, V, t); break;
+        case SHAPE_Q8: em_sq<ShapeFunction8Square>(s, Ke, n2e, element, x, E, V, t); break;
+        case SHAPE_TET4: SolidLinearIsotropicElastic<double, ShapeFunction4Tetrahedron, Gauss1Tetrahedron>(Ke, n2e, element, { 0, 1, 2 }, x, E, V); break;
+        case SHAPE_HEX8: em_cube<ShapeFunction8Cubic>(s, Ke, n2e, element, x, E, V); break;
+        default: em_cube<ShapeFunction20Cubic>(s, Ke, n2e, element, x, E, V); break;
     }
 }
 

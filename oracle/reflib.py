@@ -15,7 +15,12 @@ LIB_PATH = os.path.join(_HERE, "_ref", "libpf2ref.so")
 EQ_PLANESTRAIN, EQ_SOLID, EQ_HEAT = 0, 1, 2
 FILTER_DENSITY, FILTER_HEAVISIDE = 0, 1
 OPT_OC, OPT_MMA, OPT_CONLIN = 0, 1, 2
-NDOF = {EQ_PLANESTRAIN: 2, EQ_SOLID: 3, EQ_HEAT: 1}
+
+
+def ndof_of(eq):
+    """dofs per node of an eq code (include/pansfem2_b200.h PF2_EQ_CODE): the physics is the low byte."""
+    phys = eq & 0xff
+    return 3 if phys == 1 else (1 if phys == 2 else 2)
 
 _lib = None
 
@@ -71,7 +76,7 @@ def set_num_threads(n: int):
 def element_matrix(eq, xe, E, V=0.3, t=1.0):
     xe = _f64(xe)
     npe, dim = xe.shape
-    m = npe * NDOF[eq]
+    m = npe * ndof_of(eq)
     Ke = np.zeros((m, m))
     lib().ref_element_matrix(eq, dim, npe, _p(xe, np.float64), C.c_double(E), C.c_double(V), C.c_double(t), _p(Ke, np.float64))
     return Ke
@@ -270,7 +275,7 @@ def simp_run(eq, coords, conn, fixed, loads, filter_kind, nbrs, opt_kind, optp, 
     coords, conn = _f64(coords), _i32(conn)
     nnode, dim = coords.shape
     nelem, npe = conn.shape
-    ndof = NDOF[eq]
+    ndof = ndof_of(eq)
     fn, fd, fv = _i32(fixed[0]), _i32(fixed[1]), _f64(fixed[2])
     ln, ld, lv = _i32(loads[0]), _i32(loads[1]), _f64(loads[2])
     rowptr, nbr, w = _i64(nbrs[0]), _i32(nbrs[1]), _f64(nbrs[2])

@@ -11,6 +11,9 @@ import os
 
 import numpy as np
 
+from . import eqcode
+from .eqcode import eq_code  # noqa: F401
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpansfem2_b200.so")
 
@@ -19,7 +22,6 @@ SOLVER_CG, SOLVER_SCALINGCG, SOLVER_ILU0CG = 0, 1, 2
 FILTER_DENSITY, FILTER_HEAVISIDE, FILTER_SENS_SIGMUND, FILTER_SENS_BORRVALL = 0, 1, 2, 3
 OPT_OC, OPT_MMA, OPT_CONLIN = 0, 1, 2
 E_NOCONV = 4
-NDOF = {EQ_PLANESTRAIN: 2, EQ_SOLID: 3, EQ_HEAT: 1}
 
 _lib = None
 
@@ -141,7 +143,7 @@ class Context:
 
     def element_matrix(self, eq, xe, E, V=0.3, t=1.0):
         xe = _f64(xe)
-        m = xe.shape[0] * NDOF[eq]
+        m = xe.shape[0] * eqcode.ndof(eq)
         Ke = np.zeros((m, m))
         _ck(lib().pf2_element_matrix(self.h, eq, _p(xe, np.float64), C.c_double(E), C.c_double(V), C.c_double(t), _p(Ke, np.float64)))
         return Ke
@@ -381,7 +383,7 @@ def compliance_sens(mesh, eq, u_dev, rho_dev, params6, want_r=False):
     """params6 = (E0, E1, poisson, p, thickness, scale0).  Returns (f, dfdrho, r or None) as host arrays."""
     ctx = mesh.ctx
     dfd = ctx.empty(mesh.nelem)
-    r = ctx.empty(mesh.nnode * NDOF[eq]) if want_r else None
+    r = ctx.empty(mesh.nnode * eqcode.ndof(eq)) if want_r else None
     f = C.c_double(0)
     prm = (C.c_double * 6)(*params6)
     _ck(lib().pf2_compliance_sens(mesh.h, eq, u_dev.ptr, rho_dev.ptr, prm, C.byref(f), dfd.ptr, r.ptr if r is not None else None))

@@ -216,18 +216,21 @@ __global__ void element_matrix_kernel(const double* __restrict__ xe, double E, d
 
 using namespace pf2;
 
-static int eq_ndof(int eq) { return eq == PF2_EQ_PLANESTRAIN ? 2 : (eq == PF2_EQ_SOLID ? 3 : 1); }
-static int eq_npe(int eq) { return eq == PF2_EQ_SOLID ? 8 : 4; }
-static int eq_dim(int eq) { return eq == PF2_EQ_SOLID ? 3 : 2; }
-
 namespace pf2 {
+int assemble_generic_launch(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, const EqInfo& q, const double* modulus_dev, const double* rho_dev,
+                            const double params[5]);
+int sens_generic_launch(pf2_mesh* mesh, const EqInfo& q, const double* u_nodal, const double* rho, const double params[6], double* f_dev,
+                        double* dfdrho, double* r_nodal);
+int element_generic_launch(pf2_ctx* ctx, const EqInfo& q, const double* xe_dev, double E, double t, double* Ke_dev);
+
 // numeric assembly with the nodal loads already on the device (the design loop keeps them resident)
 int assemble_device(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq, const double* modulus_dev, const double* rho_dev,
                     const double params[5], int nload, const int* load_node_dev, const int* load_dof_dev, const double* load_val_dev) {
-    PF2_CHECK(eq >= 0 && eq <= 2, "unknown equation");
+    EqInfo q;
+    PF2_TRY(decode_eq(eq, params[2], &q));
     PF2_CHECK(A->bmap != nullptr, "matrix was not built by pf2_csr_pattern");
-    PF2_CHECK(eq_npe(eq) == mesh->npe && eq_dim(eq) == mesh->dim, "equation does not match the mesh's element type");
-    PF2_CHECK(eq_ndof(eq) == map->ndof, "equation does not match the dof map (the reference asserts doulist.size(), PlaneStrain.h:22)");
+    PF2_CHECK(q.npe == mesh->npe && q.dim == mesh->dim, "equation does not match the mesh's element type");
+    PF2_CHECK(q.ndof == map->ndof, "equation does not match the dof map (the reference asserts doulist.size(), PlaneStrain.h:22)");
     PF2_CHECK(A->map_nelem == mesh->nelem && A->map_npe == mesh->npe && A->map_ndof == map->ndof, "pattern built for another mesh");
     PF2_CHECK(modulus_dev || rho_dev, "need a modulus or a density field");
     pf2_ctx* c = A->ctx;
@@ -239,12 +242,15 @@ int assemble_device(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq, const d
     const int grid = (int)std::min<long long>((work + 127) / 128, (long long)c->sm_count * 32);
 #define LAUNCH(EQ) assemble_kernel<EQ><<<grid, 128, 0, s>>>(mesh->nelem, mesh->coords, mesh->conn, map->n2g, map->ufix, A->bmap, A->indptr, \
                                                           modulus_dev, rho_dev, E0, E1, V, p, t, A->data, A->F)
-    if (eq == PF2_EQ_PLANESTRAIN) LAUNCH(PF2_EQ_PLANESTRAIN);
-    else if (eq == PF2_EQ_SOLID) LAUNCH(PF2_EQ_SOLID);
-    else LAUNCH(PF2_EQ_HEAT);
+    if (!q.fast) PF2_TRY(assemble_generic_launch(A, mesh, map, q, modulus_dev, rho_dev, params));
+    else {
+        if (q.legacy == PF2_EQ_PLANESTRAIN) LAUNCH(PF2_EQ_PLANESTRAIN);
+        else if (q.legacy == PF2_EQ_SOLID) LAUNCH(PF2_EQ_SOLID);
+        else LAUNCH(PF2_EQ_HEAT);
+        PF2_LAUNCH_CHECK();
+        c->launches++;
+    }
 #undef LAUNCH
-    PF2_LAUNCH_CHECK();
-    c->launches++;
     if (nload > 0) {
         loads_kernel<<<c->grid_for(nload), kThreads, 0, s>>>(nload, map->ndof, load_node_dev, load_dof_dev, load_val_dev, map->n2g, A->F);
         PF2_LAUNCH_CHECK();
@@ -260,8 +266,13 @@ int compliance_sens_device(pf2_mesh* mesh, int eq, const double* u_nodal, const 
                            double* dfdrho, double* r_nodal) {
     pf2_ctx* c = mesh->ctx;
     cudaStream_t s = c->stream;
-    const int ndof = eq_ndof(eq);
+    EqInfo q;
+    PF2_TRY(decode_eq(eq, params[2], &q));
+    PF2_CHECK(q.npe == mesh->npe && q.dim == mesh->dim, "equation does not match the mesh");
+    const int ndof = q.ndof;
     if (r_nodal) PF2_CUDA(cudaMemsetAsync(r_nodal, 0, sizeof(double) * (size_t)mesh->nnode * ndof, s));
+    if (!q.fast) return sens_generic_launch(mesh, q, u_nodal, rho, params, f_dev, dfdrho, r_nodal);
+    eq = q.legacy;
     const int grid = c->grid_for(mesh->nelem);
 #define LAUNCH(EQ) sens_kernel<EQ><<<grid, kThreads, 0, s>>>(mesh->nelem, mesh->coords, mesh->conn, u_nodal, rho, params[0], params[1], \
                                                            params[2], params[3], params[4], params[5], dfdrho, r_nodal, f_dev, c->red.partials, c->red.ticket, mesh->own_elem_lo, mesh->own_elem_hi)
@@ -300,16 +311,21 @@ int pf2_assemble(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq, const doub
 }
 
 int pf2_element_matrix(pf2_ctx* ctx, int eq, const double* xe_host, double E, double V, double t, double* Ke_host) {
-    PF2_CHECK(ctx && xe_host && Ke_host && eq >= 0 && eq <= 2, "bad arguments");
-    const int npe = eq_npe(eq), dim = eq_dim(eq), m = npe * eq_ndof(eq);
-    if (!ctx->elem_scratch) PF2_TRY(dev_alloc(&ctx->elem_scratch, (size_t)24 + 576));
-    double *xe = ctx->elem_scratch, *Ke = ctx->elem_scratch + 24;
+    PF2_CHECK(ctx && xe_host && Ke_host, "bad arguments");
+    EqInfo q;
+    PF2_TRY(decode_eq(eq, V, &q));
+    const int npe = q.npe, dim = q.dim, m = npe * q.ndof;
+    if (!ctx->elem_scratch) PF2_TRY(dev_alloc(&ctx->elem_scratch, (size_t)64 + 3600));      // hex20: 60 coordinates, 60 x 60 entries
+    double *xe = ctx->elem_scratch, *Ke = ctx->elem_scratch + 64;
     PF2_CUDA(cudaMemcpyAsync(xe, xe_host, sizeof(double) * npe * dim, cudaMemcpyHostToDevice, ctx->stream));
-    if (eq == PF2_EQ_PLANESTRAIN) element_matrix_kernel<PF2_EQ_PLANESTRAIN><<<1, 32, 0, ctx->stream>>>(xe, E, V, t, Ke);
-    else if (eq == PF2_EQ_SOLID) element_matrix_kernel<PF2_EQ_SOLID><<<1, 32, 0, ctx->stream>>>(xe, E, V, t, Ke);
-    else element_matrix_kernel<PF2_EQ_HEAT><<<1, 32, 0, ctx->stream>>>(xe, E, V, t, Ke);
-    PF2_LAUNCH_CHECK();
-    ctx->launches++;
+    if (!q.fast) PF2_TRY(element_generic_launch(ctx, q, xe, E, t, Ke));
+    else {
+        if (q.legacy == PF2_EQ_PLANESTRAIN) element_matrix_kernel<PF2_EQ_PLANESTRAIN><<<1, 32, 0, ctx->stream>>>(xe, E, V, t, Ke);
+        else if (q.legacy == PF2_EQ_SOLID) element_matrix_kernel<PF2_EQ_SOLID><<<1, 32, 0, ctx->stream>>>(xe, E, V, t, Ke);
+        else element_matrix_kernel<PF2_EQ_HEAT><<<1, 32, 0, ctx->stream>>>(xe, E, V, t, Ke);
+        PF2_LAUNCH_CHECK();
+        ctx->launches++;
+    }
     PF2_CUDA(cudaMemcpyAsync(Ke_host, Ke, sizeof(double) * m * m, cudaMemcpyDeviceToHost, ctx->stream));
     PF2_CUDA(cudaStreamSynchronize(ctx->stream));
     return PF2_OK;
@@ -327,7 +343,6 @@ int pf2_disassemble(pf2_dofmap* map, const double* x_dev, double* u_nodal_dev) {
 int pf2_compliance_sens(pf2_mesh* mesh, int eq, const double* u_nodal_dev, const double* rho_dev, const double params[6],
                         double* f_out, double* dfdrho_dev, double* r_nodal_dev) {
     PF2_CHECK(mesh && u_nodal_dev && rho_dev && params, "null argument");
-    PF2_CHECK(eq >= 0 && eq <= 2 && eq_npe(eq) == mesh->npe && eq_dim(eq) == mesh->dim, "equation does not match the mesh");
     pf2_ctx* c = mesh->ctx;
     PF2_TRY(compliance_sens_device(mesh, eq, u_nodal_dev, rho_dev, params, c->scalars, dfdrho_dev, r_nodal_dev));
     if (f_out) {

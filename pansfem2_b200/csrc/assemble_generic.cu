@@ -1,0 +1,268 @@
+// assemble_generic.cu -- assembly / sensitivity / single-element kernels for the element families beyond the three
+// specialised selections, and the eq-code decoder shared by every entry point.
+//
+//   decode_eq                 : PF2_EQ_CODE(phys, shape, quad, quad2) -> kind, shape, rules, D coefficients
+//   assemble_generic_kernel   : element routine <Equation, SF, IC> + Assembling(K,F,u,Ke,...) (Assembling.h:47-66)
+//   sens_generic_kernel       : reaction / compliance / sensitivity pass of the TO drivers for the same selections
+//   element_generic_kernel    : one element matrix (the reference's per-element call)
+// Same thread mapping as assemble.cu: one thread per (element, local node) holding that node's NDOF rows of Ke.
+#include "types.cuh"
+#include "element_generic.cuh"
+
+namespace pf2 {
+
+static int shape_dim(int shape) { return (shape == PF2_SHAPE_TET4 || shape == PF2_SHAPE_HEX8 || shape == PF2_SHAPE_HEX20) ? 3 : 2; }
+static int shape_npe(int shape) {
+    switch (shape) {
+        case PF2_SHAPE_T3: return 3; case PF2_SHAPE_T6: return 6; case PF2_SHAPE_Q4: return 4; case PF2_SHAPE_Q8: return 8;
+        case PF2_SHAPE_TET4: return 4; case PF2_SHAPE_HEX8: return 8; case PF2_SHAPE_HEX20: return 20;
+    }
+    return 0;
+}
+// reference domain: 0 triangle, 1 square, 2 tetrahedron, 3 cube
+static int shape_domain(int shape) {
+    switch (shape) {
+        case PF2_SHAPE_T3: case PF2_SHAPE_T6: return 0;
+        case PF2_SHAPE_Q4: case PF2_SHAPE_Q8: return 1;
+        case PF2_SHAPE_TET4: return 2;
+        default: return 3;
+    }
+}
+static int quad_domain(int quad) {
+    switch (quad) {
+        case PF2_QUAD_G1TRI: case PF2_QUAD_G3TRI: return 0;
+        case PF2_QUAD_G1SQ: case PF2_QUAD_G4SQ: case PF2_QUAD_G9SQ: return 1;
+        case PF2_QUAD_G1TET: return 2;
+        case PF2_QUAD_G8CUBE: case PF2_QUAD_G27CUBE: return 3;
+    }
+    return -1;
+}
+
+int decode_eq(int eq, double V, EqInfo* out) {
+    EqInfo q;
+    q.phys = eq & 0xff; q.shape = (eq >> 8) & 0xff; q.quad = (eq >> 16) & 0xff; q.quad2 = (eq >> 24) & 0xff;
+    PF2_CHECK(eq >= 0 && q.phys <= PF2_PHYS_PLANESTRAIN_SRI, "unknown equation");
+    PF2_CHECK(q.shape <= PF2_SHAPE_HEX20 && q.quad <= PF2_QUAD_G27CUBE && q.quad2 <= PF2_QUAD_G27CUBE, "unknown shape function / integration rule");
+    const bool solid = q.phys == PF2_PHYS_SOLID;
+    if (q.shape == 0) q.shape = solid ? PF2_SHAPE_HEX8 : PF2_SHAPE_Q4;
+    PF2_CHECK(shape_dim(q.shape) == (solid ? 3 : 2), "shape function does not match the equation's dimension");
+    const int dom = shape_domain(q.shape);
+    static const int dflt[4] = { PF2_QUAD_G1TRI, PF2_QUAD_G4SQ, PF2_QUAD_G1TET, PF2_QUAD_G8CUBE };
+    static const int dflt_reduced[4] = { PF2_QUAD_G1TRI, PF2_QUAD_G1SQ, PF2_QUAD_G1TET, PF2_QUAD_G8CUBE };
+    if (q.quad == 0) q.quad = dflt[dom];
+    PF2_CHECK(quad_domain(q.quad) == dom, "integration rule does not belong to the shape function's reference domain");
+    if (q.phys == PF2_PHYS_PLANESTRAIN_SRI) {
+        if (q.quad2 == 0) q.quad2 = dflt_reduced[dom];
+        PF2_CHECK(quad_domain(q.quad2) == dom, "volumetric integration rule does not belong to the shape function's reference domain");
+    } else {
+        PF2_CHECK(q.quad2 == 0, "a second integration rule is only meaningful for the selective-reduced variant");
+    }
+    q.dim = solid ? 3 : 2;
+    q.npe = shape_npe(q.shape);
+    q.ndof = solid ? 3 : (q.phys == PF2_PHYS_HEAT ? 1 : 2);
+    q.kind = solid ? KIND_SOLID3D : (q.phys == PF2_PHYS_HEAT ? KIND_HEAT2D : KIND_ELAST2D);
+    q.fast = (q.phys == PF2_PHYS_PLANESTRAIN && q.shape == PF2_SHAPE_Q4 && q.quad == PF2_QUAD_G4SQ) ||
+             (q.phys == PF2_PHYS_HEAT && q.shape == PF2_SHAPE_Q4 && q.quad == PF2_QUAD_G4SQ) ||
+             (solid && q.shape == PF2_SHAPE_HEX8 && q.quad == PF2_QUAD_G8CUBE);
+    q.legacy = solid ? PF2_EQ_SOLID : (q.phys == PF2_PHYS_HEAT ? PF2_EQ_HEAT : PF2_EQ_PLANESTRAIN);
+    // D for unit modulus
+    q.npass = 1; q.cn[0] = q.cn[1] = 1.0; q.lam[0] = q.lam[1] = 0.0; q.mu[0] = q.mu[1] = 0.0;
+    if (q.phys == PF2_PHYS_PLANESTRAIN || solid) {          // PlaneStrain.h:37-41, Solid.h:37-44
+        const double c = 1.0 / ((1.0 + V) * (1.0 - 2.0 * V));
+        q.cn[0] = (1.0 - V) * c; q.lam[0] = V * c; q.mu[0] = 0.5 * (1.0 - 2.0 * V) * c;
+    } else if (q.phys == PF2_PHYS_PLANESTRESS) {            // PlaneStress.h:37-41
+        const double c = 1.0 / ((1.0 - V) * (1.0 + V));
+        q.cn[0] = c; q.lam[0] = V * c; q.mu[0] = 0.5 * (1.0 - V) * c;
+    } else if (q.phys == PF2_PHYS_PLANESTRAIN_SRI) {        // PlaneStrain.h:79-83 (volumetric, ICV), :101-105 (deviatoric, ICD)
+        q.npass = 2;
+        const double k = 1.0 / (3.0 * (1.0 - 2.0 * V)), c = 1.0 / (6.0 * (1.0 + V));
+        q.cn[0] = k; q.lam[0] = k; q.mu[0] = 0.0;
+        q.cn[1] = 4.0 * c; q.lam[1] = -2.0 * c; q.mu[1] = 3.0 * c;
+    }
+    *out = q;
+    return PF2_OK;
+}
+
+static ElemSpec make_spec(const EqInfo& q) {
+    ElemSpec sp;
+    sp.npass = q.npass;
+    if (q.npass == 2) { sp.quad[0] = q.quad2; sp.quad[1] = q.quad; }
+    else { sp.quad[0] = q.quad; sp.quad[1] = q.quad; }
+    for (int i = 0; i < 2; i++) { sp.cn[i] = q.cn[i]; sp.lam[i] = q.lam[i]; sp.mu[i] = q.mu[i]; }
+    return sp;
+}
+
+template <int KIND, int SHAPE>
+__global__ void __launch_bounds__(128)
+assemble_generic_kernel(int nelem, ElemSpec sp, const double* __restrict__ coords, const int* __restrict__ conn, const int* __restrict__ n2g,
+                        const double* __restrict__ ufix, const int* __restrict__ bmap, const long long* __restrict__ indptr,
+                        const double* __restrict__ modulus, const double* __restrict__ rho, double E0, double E1, double p,
+                        double t, double* __restrict__ data, double* __restrict__ F) {
+    constexpr int DIM = ShapeTraits<SHAPE>::DIM, NPE = ShapeTraits<SHAPE>::NPE, NDOF = KindTraits<KIND>::NDOF;
+    const long long total = (long long)nelem * NPE;
+    for (long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x; tid < total; tid += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(tid / NPE), a = (int)(tid % NPE);
+        const int* nd = conn + (size_t)e * NPE;
+        const int na = nd[a];
+        int rows[NDOF];
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < NDOF; i++) { rows[i] = n2g[(size_t)na * NDOF + i]; any |= (rows[i] != -1); }
+        if (!any) continue;
+        double X[NPE][DIM];
+#pragma unroll
+        for (int n = 0; n < NPE; n++)
+#pragma unroll
+            for (int k = 0; k < DIM; k++) X[n][k] = coords[(size_t)nd[n] * DIM + k];
+        const double E = modulus ? modulus[e] : simp_modulus(rho[e], E0, E1, p);
+        double acc[NDOF][NPE * NDOF];
+        generic_rows<KIND, SHAPE>(X, a, sp, t, acc);
+        const int* bm = bmap + ((size_t)e * NPE + a) * NPE;
+#pragma unroll (NPE <= 8 ? NPE : 1)
+        for (int b = 0; b < NPE; b++) {
+            const int off = bm[b], nb = nd[b];
+            int cfree[NDOF];
+            int rank = 0;
+#pragma unroll
+            for (int j = 0; j < NDOF; j++) {
+                const int c = n2g[(size_t)nb * NDOF + j];
+                cfree[j] = (c != -1) ? rank++ : -1;
+            }
+#pragma unroll
+            for (int i = 0; i < NDOF; i++) {
+                if (rows[i] == -1) continue;
+                const long long base = indptr[rows[i]] + off;
+#pragma unroll
+                for (int j = 0; j < NDOF; j++) {
+                    const double v = E * acc[i][b * NDOF + j];
+                    if (cfree[j] >= 0) atomicAdd(&data[base + cfree[j]], v);                  // Assembling.h:55
+                    else {
+                        const double uf = ufix[(size_t)nb * NDOF + j];
+                        if (uf != 0.0) atomicAdd(&F[rows[i]], -(v * uf));                       // Assembling.h:59
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int KIND, int SHAPE>
+__global__ void __launch_bounds__(kThreads)
+sens_generic_kernel(int nelem, ElemSpec sp, const double* __restrict__ coords, const int* __restrict__ conn, const double* __restrict__ u,
+                    const double* __restrict__ rho, double E0, double E1, double p, double t, double scale0,
+                    double* __restrict__ dfdrho, double* r_nodal, double* f_out, double* partials, unsigned int* ticket, int sum_lo, int sum_hi) {
+    constexpr int DIM = ShapeTraits<SHAPE>::DIM, NPE = ShapeTraits<SHAPE>::NPE, NDOF = KindTraits<KIND>::NDOF;
+    double fsum = 0.0;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nelem; e += gridDim.x * blockDim.x) {
+        const int* nd = conn + (size_t)e * NPE;
+        double X[NPE][DIM], ue[NPE][NDOF], fe[NPE][NDOF];
+#pragma unroll
+        for (int n = 0; n < NPE; n++) {
+            const int node = nd[n];
+#pragma unroll
+            for (int k = 0; k < DIM; k++) X[n][k] = coords[(size_t)node * DIM + k];
+#pragma unroll
+            for (int k = 0; k < NDOF; k++) { ue[n][k] = u[(size_t)node * NDOF + k]; fe[n][k] = 0.0; }
+        }
+        const double w = r_nodal ? generic_energy<KIND, SHAPE, true>(X, ue, sp, t, fe) : generic_energy<KIND, SHAPE, false>(X, ue, sp, t, fe);
+        const double rh = rho[e];
+        const double E = simp_modulus(rh, E0, E1, p);
+        if (e >= sum_lo && e < sum_hi) fsum += E * w;
+        if (dfdrho) dfdrho[e] = -scale0 * p * (-E0 + E1) * pow(rh, p - 1.0) * w;
+        if (r_nodal) {
+#pragma unroll 1
+            for (int n = 0; n < NPE; n++)
+#pragma unroll
+                for (int k = 0; k < NDOF; k++) atomicAdd(&r_nodal[(size_t)nd[n] * NDOF + k], E * fe[n][k]);
+        }
+    }
+    double v[1] = { fsum };
+    if (grid_sum_last<1>(v, partials, ticket) && threadIdx.x == 0) *f_out = scale0 * v[0];
+}
+
+template <int KIND, int SHAPE>
+__global__ void element_generic_kernel(ElemSpec sp, const double* __restrict__ xe, double E, double t, double* __restrict__ Ke) {
+    constexpr int DIM = ShapeTraits<SHAPE>::DIM, NPE = ShapeTraits<SHAPE>::NPE, NDOF = KindTraits<KIND>::NDOF;
+    const int a = threadIdx.x;
+    if (a >= NPE) return;
+    double X[NPE][DIM];
+    for (int n = 0; n < NPE; n++) for (int k = 0; k < DIM; k++) X[n][k] = xe[n * DIM + k];
+    double acc[NDOF][NPE * NDOF];
+    generic_rows<KIND, SHAPE>(X, a, sp, t, acc);
+    constexpr int M = NPE * NDOF;
+    for (int i = 0; i < NDOF; i++) for (int j = 0; j < M; j++) Ke[(a * NDOF + i) * M + j] = E * acc[i][j];
+}
+
+// (kind, shape) -> instantiation
+#define PF2_DISPATCH_SHAPE(q, CALL)                                                                  \
+    do {                                                                                             \
+        if ((q).kind == KIND_SOLID3D) {                                                              \
+            if ((q).shape == PF2_SHAPE_TET4) { CALL(KIND_SOLID3D, SH_TET4); }                        \
+            else if ((q).shape == PF2_SHAPE_HEX8) { CALL(KIND_SOLID3D, SH_HEX8); }                   \
+            else { CALL(KIND_SOLID3D, SH_HEX20); }                                                   \
+        } else if ((q).kind == KIND_HEAT2D) {                                                        \
+            if ((q).shape == PF2_SHAPE_T3) { CALL(KIND_HEAT2D, SH_T3); }                             \
+            else if ((q).shape == PF2_SHAPE_T6) { CALL(KIND_HEAT2D, SH_T6); }                        \
+            else if ((q).shape == PF2_SHAPE_Q4) { CALL(KIND_HEAT2D, SH_Q4); }                        \
+            else { CALL(KIND_HEAT2D, SH_Q8); }                                                       \
+        } else {                                                                                     \
+            if ((q).shape == PF2_SHAPE_T3) { CALL(KIND_ELAST2D, SH_T3); }                            \
+            else if ((q).shape == PF2_SHAPE_T6) { CALL(KIND_ELAST2D, SH_T6); }                       \
+            else if ((q).shape == PF2_SHAPE_Q4) { CALL(KIND_ELAST2D, SH_Q4); }                       \
+            else { CALL(KIND_ELAST2D, SH_Q8); }                                                      \
+        }                                                                                            \
+    } while (0)
+
+int assemble_generic_launch(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, const EqInfo& q, const double* modulus_dev, const double* rho_dev,
+                            const double params[5]) {
+    pf2_ctx* c = A->ctx;
+    cudaStream_t s = c->stream;
+    const ElemSpec sp = make_spec(q);
+    const double E0 = params[0], E1 = params[1], p = params[3], t = params[4];
+    const long long work = (long long)mesh->nelem * mesh->npe;
+    const int grid = (int)std::min<long long>((work + 127) / 128, (long long)c->sm_count * 32);
+#define CALL(K, S) assemble_generic_kernel<K, S><<<grid, 128, 0, s>>>(mesh->nelem, sp, mesh->coords, mesh->conn, map->n2g, map->ufix, A->bmap, \
+                                                                      A->indptr, modulus_dev, rho_dev, E0, E1, p, t, A->data, A->F)
+    PF2_DISPATCH_SHAPE(q, CALL);
+#undef CALL
+    PF2_LAUNCH_CHECK();
+    c->launches++;
+    return PF2_OK;
+}
+
+int sens_generic_launch(pf2_mesh* mesh, const EqInfo& q, const double* u_nodal, const double* rho, const double params[6], double* f_dev,
+                        double* dfdrho, double* r_nodal) {
+    pf2_ctx* c = mesh->ctx;
+    cudaStream_t s = c->stream;
+    const ElemSpec sp = make_spec(q);
+    const int grid = c->grid_for(mesh->nelem);
+#define CALL(K, S) sens_generic_kernel<K, S><<<grid, kThreads, 0, s>>>(mesh->nelem, sp, mesh->coords, mesh->conn, u_nodal, rho, params[0], params[1], \
+                                                                       params[3], params[4], params[5], dfdrho, r_nodal, f_dev, c->red.partials,     \
+                                                                       c->red.ticket, mesh->own_elem_lo, mesh->own_elem_hi)
+    PF2_DISPATCH_SHAPE(q, CALL);
+#undef CALL
+    PF2_LAUNCH_CHECK();
+    c->launches++;
+    return PF2_OK;
+}
+
+int element_generic_launch(pf2_ctx* ctx, const EqInfo& q, const double* xe_dev, double E, double t, double* Ke_dev) {
+    const ElemSpec sp = make_spec(q);
+#define CALL(K, S) element_generic_kernel<K, S><<<1, 32, 0, ctx->stream>>>(sp, xe_dev, E, t, Ke_dev)
+    PF2_DISPATCH_SHAPE(q, CALL);
+#undef CALL
+    PF2_LAUNCH_CHECK();
+    ctx->launches++;
+    return PF2_OK;
+}
+
+}  // namespace pf2
+
+extern "C" int pf2_eq_describe(int eq, int* dim, int* npe, int* ndof) {
+    pf2::EqInfo q;
+    PF2_TRY(pf2::decode_eq(eq, 0.3, &q));
+    if (dim) *dim = q.dim;
+    if (npe) *npe = q.npe;
+    if (ndof) *ndof = q.ndof;
+    return PF2_OK;
+}

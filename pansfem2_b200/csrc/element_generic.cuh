@@ -1,0 +1,321 @@
+// element_generic.cuh -- the element families beyond Q4/hex8: one device template over
+// <kind, shape> with the quadrature rule and the isotropic coefficients chosen at run time.
+//
+// Restates (paths relative to /root/reference/src/FEM):
+//   Controller/ShapeFunction.h   dNdr of ShapeFunction3Triangle (:112-117), 6Triangle (:150-155), 4Square (:186-191),
+//                                8Square (:226-246), 4Tetrahedron (:277-283), 8Cubic (:318-329), 20Cubic (:396-461)
+//   Controller/GaussIntegration.h points / per-axis weights of Gauss1Triangle (:72-82), Gauss3Triangle (:94-107),
+//                                Gauss1Square (:120-130), Gauss4Square (:142-157), Gauss9Square (:170-195),
+//                                Gauss1Tetrahedron (:208-218), Gauss8Cubic (:230-253), Gauss27Cubic (:266-327)
+//   Equation/PlaneStrain.h:21-58 (PlaneStrainStiffness), :63-125 (PlaneStrainStiffnessSRI), PlaneStress.h:21-58,
+//   HeatTransfer.h:20-43, Solid.h:21-64:  Ke += B^T D B * J * t * w0 * w1 [* w2] over the rule's points.
+//
+// As in element.cuh, B^T D B is never formed: every D above has the shape [[cn, lam, 0], [lam, cn, 0], [0, 0, mu]]
+// (resp. its 3-D analogue), so the (node a, node b) block is closed-form in the gradients.  The selective-reduced
+// variant is two passes over two rules with (cn, lam, mu) = (k, k, 0), k = E/(3(1-2V)), and (4c, -2c, 3c), c = E/(6(1+V)).
+#pragma once
+#include "element.cuh"
+
+namespace pf2 {
+
+enum { SH_T3 = PF2_SHAPE_T3, SH_T6 = PF2_SHAPE_T6, SH_Q4 = PF2_SHAPE_Q4, SH_Q8 = PF2_SHAPE_Q8, SH_TET4 = PF2_SHAPE_TET4,
+       SH_HEX8 = PF2_SHAPE_HEX8, SH_HEX20 = PF2_SHAPE_HEX20 };
+enum { KIND_ELAST2D = 0, KIND_HEAT2D = 1, KIND_SOLID3D = 2 };
+
+// what one launch needs to know about the element routine (filled on the host by decode_eq, passed by value)
+struct ElemSpec {
+    int npass;          // 1, or 2 for the selective-reduced plane-strain variant
+    int quad[2];        // PF2_QUAD_* of each pass
+    double cn[2], lam[2], mu[2];   // D for unit modulus (heat: unused)
+};
+
+template <int SHAPE> struct ShapeTraits;
+template <> struct ShapeTraits<SH_T3> { static constexpr int DIM = 2, NPE = 3; };
+template <> struct ShapeTraits<SH_T6> { static constexpr int DIM = 2, NPE = 6; };
+template <> struct ShapeTraits<SH_Q4> { static constexpr int DIM = 2, NPE = 4; };
+template <> struct ShapeTraits<SH_Q8> { static constexpr int DIM = 2, NPE = 8; };
+template <> struct ShapeTraits<SH_TET4> { static constexpr int DIM = 3, NPE = 4; };
+template <> struct ShapeTraits<SH_HEX8> { static constexpr int DIM = 3, NPE = 8; };
+template <> struct ShapeTraits<SH_HEX20> { static constexpr int DIM = 3, NPE = 20; };
+
+template <int KIND> struct KindTraits;
+template <> struct KindTraits<KIND_ELAST2D> { static constexpr int DIM = 2, NDOF = 2; };
+template <> struct KindTraits<KIND_HEAT2D> { static constexpr int DIM = 2, NDOF = 1; };
+template <> struct KindTraits<KIND_SOLID3D> { static constexpr int DIM = 3, NDOF = 3; };
+
+// ---- quadrature ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int quad_count(int quad) {
+    switch (quad) {
+        case PF2_QUAD_G3TRI: return 3;
+        case PF2_QUAD_G4SQ: return 4;
+        case PF2_QUAD_G9SQ: return 9;
+        case PF2_QUAD_G8CUBE: return 8;
+        case PF2_QUAD_G27CUBE: return 27;
+        default: return 1;      // G1TRI, G1SQ, G1TET
+    }
+}
+// point g of the rule and the PRODUCT of its per-axis weights (the reference multiplies Weights[g][0]*Weights[g][1][*Weights[g][2]])
+__device__ __forceinline__ void quad_point(int quad, int g, double (&r)[3], double& w) {
+    const double s35 = sqrt(3.0 / 5.0);
+    r[2] = 0.0;
+    switch (quad) {
+        case PF2_QUAD_G1TRI: { r[0] = 1.0 / 3.0; r[1] = 1.0 / 3.0; const double a = 1.0 / sqrt(2.0); w = a * a; break; }
+        case PF2_QUAD_G3TRI: {
+            r[0] = (g == 1) ? 2.0 / 3.0 : 1.0 / 6.0; r[1] = (g == 2) ? 2.0 / 3.0 : 1.0 / 6.0;
+            const double a = 1.0 / sqrt(6.0); w = a * a; break;
+        }
+        case PF2_QUAD_G1SQ: { r[0] = 0.0; r[1] = 0.0; w = 2.0 * 2.0; break; }
+        case PF2_QUAD_G4SQ: { q4_gauss(g, r[0], r[1]); w = 1.0; break; }
+        case PF2_QUAD_G9SQ: {
+            const int i = g % 3, j = g / 3;
+            r[0] = (i - 1) * s35; r[1] = (j - 1) * s35;
+            w = ((i == 1) ? 8.0 / 9.0 : 5.0 / 9.0) * ((j == 1) ? 8.0 / 9.0 : 5.0 / 9.0); break;
+        }
+        case PF2_QUAD_G1TET: { r[0] = 0.25; r[1] = 0.25; r[2] = 0.25; const double a = 1.0 / cbrt(6.0); w = a * a * a; break; }
+        case PF2_QUAD_G8CUBE: { h8_gauss(g, r[0], r[1], r[2]); w = 1.0; break; }
+        default: {  // G27CUBE
+            const int i = g % 3, j = (g / 3) % 3, k = g / 9;
+            r[0] = (i - 1) * s35; r[1] = (j - 1) * s35; r[2] = (k - 1) * s35;
+            w = ((i == 1) ? 8.0 / 9.0 : 5.0 / 9.0) * ((j == 1) ? 8.0 / 9.0 : 5.0 / 9.0) * ((k == 1) ? 8.0 / 9.0 : 5.0 / 9.0); break;
+        }
+    }
+}
+
+// ---- dN/dr, d[k][n] ----------------------------------------------------------------------------------------------
+template <int SHAPE>
+__device__ __forceinline__ void shape_dndr(const double (&r)[3], double (&d)[ShapeTraits<SHAPE>::DIM][ShapeTraits<SHAPE>::NPE]) {
+    const double r0 = r[0], r1 = r[1], r2 = r[2];
+    if constexpr (SHAPE == SH_T3) {
+        d[0][0] = 1.0; d[0][1] = 0.0; d[0][2] = -1.0;
+        d[1][0] = 0.0; d[1][1] = 1.0; d[1][2] = -1.0;
+    } else if constexpr (SHAPE == SH_T6) {
+        d[0][0] = 4.0 * r0 - 1.0; d[0][1] = 0.0; d[0][2] = -3.0 + 4.0 * r0 + 4.0 * r1; d[0][3] = 4.0 * r1; d[0][4] = -4.0 * r1;
+        d[0][5] = 4.0 * (1.0 - 2.0 * r0 - r1);
+        d[1][0] = 0.0; d[1][1] = 4.0 * r1 - 1.0; d[1][2] = -3.0 + 4.0 * r0 + 4.0 * r1; d[1][3] = 4.0 * r0;
+        d[1][4] = 4.0 * (1.0 - r0 - 2.0 * r1); d[1][5] = -4.0 * r0;
+    } else if constexpr (SHAPE == SH_Q4) {
+        d[0][0] = -0.25 * (1.0 - r1); d[0][1] = 0.25 * (1.0 - r1); d[0][2] = 0.25 * (1.0 + r1); d[0][3] = -0.25 * (1.0 + r1);
+        d[1][0] = -0.25 * (1.0 - r0); d[1][1] = -0.25 * (1.0 + r0); d[1][2] = 0.25 * (1.0 + r0); d[1][3] = 0.25 * (1.0 - r0);
+    } else if constexpr (SHAPE == SH_Q8) {
+        // corners n = 0..3 with signs (sx, sy): N = (1 + sx r0)(1 + sy r1)(sx r0 + sy r1 - 1)/4
+#pragma unroll
+        for (int n = 0; n < 4; n++) {
+            const double sx = ((n + 1) & 2) ? 1.0 : -1.0, sy = (n & 2) ? 1.0 : -1.0;
+            d[0][n] = 0.25 * sx * (1.0 + sy * r1) * (2.0 * sx * r0 + sy * r1);
+            d[1][n] = 0.25 * sy * (1.0 + sx * r0) * (sx * r0 + 2.0 * sy * r1);
+        }
+        // mid-side nodes 4:(0,-1) 5:(1,0) 6:(0,1) 7:(-1,0)
+        d[0][4] = -r0 * (1.0 - r1);               d[1][4] = -0.5 * (1.0 + r0) * (1.0 - r0);
+        d[0][5] = 0.5 * (1.0 + r1) * (1.0 - r1);  d[1][5] = -r1 * (1.0 + r0);
+        d[0][6] = -r0 * (1.0 + r1);               d[1][6] = 0.5 * (1.0 + r0) * (1.0 - r0);
+        d[0][7] = -0.5 * (1.0 + r1) * (1.0 - r1); d[1][7] = -r1 * (1.0 - r0);
+    } else if constexpr (SHAPE == SH_TET4) {
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+            for (int n = 0; n < 4; n++) d[k][n] = (n == 3) ? -1.0 : ((n == k) ? 1.0 : 0.0);
+    } else if constexpr (SHAPE == SH_HEX8) {
+#pragma unroll
+        for (int n = 0; n < 8; n++) {
+            const double sx = h8_sx(n), sy = h8_sy(n), sz = h8_sz(n);
+            d[0][n] = sx * 0.125 * (1.0 + sy * r1) * (1.0 + sz * r2);
+            d[1][n] = sy * 0.125 * (1.0 + sz * r2) * (1.0 + sx * r0);
+            d[2][n] = sz * 0.125 * (1.0 + sx * r0) * (1.0 + sy * r1);
+        }
+    } else {    // SH_HEX20
+        // corners: N = (1 + sx r0)(1 + sy r1)(1 + sz r2)(sx r0 + sy r1 + sz r2 - 2)/8
+#pragma unroll
+        for (int n = 0; n < 8; n++) {
+            const double sx = h8_sx(n), sy = h8_sy(n), sz = h8_sz(n);
+            const double a = 1.0 + sx * r0, b = 1.0 + sy * r1, c = 1.0 + sz * r2;
+            d[0][n] = 0.125 * sx * b * c * (2.0 * sx * r0 + sy * r1 + sz * r2 - 1.0);
+            d[1][n] = 0.125 * sy * a * c * (sx * r0 + 2.0 * sy * r1 + sz * r2 - 1.0);
+            d[2][n] = 0.125 * sz * a * b * (sx * r0 + sy * r1 + 2.0 * sz * r2 - 1.0);
+        }
+        // edge mid-points in the reference's own order (ShapeFunction.h:354-365):
+        //   8,10,12,14 on r0-edges (sy,sz) = (-,-),(+,-),(-,+),(+,+) ; 9,11,13,15 on r1-edges (sx,sz) = (+,-),(-,-),(+,+),(-,+)
+        //   16..19 on r2-edges (sx,sy) = (-,-),(+,-),(+,+),(-,+)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            {   // r0-edge node 8 + 2q
+                const double sy = (q & 1) ? 1.0 : -1.0, sz = (q & 2) ? 1.0 : -1.0;
+                const int n = 8 + 2 * q;
+                d[0][n] = -0.5 * r0 * (1.0 + sy * r1) * (1.0 + sz * r2);
+                d[1][n] = 0.25 * sy * (1.0 - r0 * r0) * (1.0 + sz * r2);
+                d[2][n] = 0.25 * sz * (1.0 - r0 * r0) * (1.0 + sy * r1);
+            }
+            {   // r1-edge node 9 + 2q
+                const double sx = (q & 1) ? -1.0 : 1.0, sz = (q & 2) ? 1.0 : -1.0;
+                const int n = 9 + 2 * q;
+                d[0][n] = 0.25 * sx * (1.0 - r1 * r1) * (1.0 + sz * r2);
+                d[1][n] = -0.5 * r1 * (1.0 + sx * r0) * (1.0 + sz * r2);
+                d[2][n] = 0.25 * sz * (1.0 + sx * r0) * (1.0 - r1 * r1);
+            }
+            {   // r2-edge node 16 + q
+                const double sx = ((q + 1) & 2) ? 1.0 : -1.0, sy = (q & 2) ? 1.0 : -1.0;
+                const int n = 16 + q;
+                d[0][n] = 0.25 * sx * (1.0 + sy * r1) * (1.0 - r2 * r2);
+                d[1][n] = 0.25 * sy * (1.0 + sx * r0) * (1.0 - r2 * r2);
+                d[2][n] = -0.5 * r2 * (1.0 + sx * r0) * (1.0 + sy * r1);
+            }
+        }
+    }
+}
+
+// dXdr = dNdr * X, J = det, dNdX = dXdr^-1 * dNdr   (g overwrites d in place)
+template <int SHAPE>
+__device__ __forceinline__ void shape_grad(const double (&X)[ShapeTraits<SHAPE>::NPE][ShapeTraits<SHAPE>::DIM], const double (&r)[3],
+                                           double (&g)[ShapeTraits<SHAPE>::DIM][ShapeTraits<SHAPE>::NPE], double& det) {
+    constexpr int DIM = ShapeTraits<SHAPE>::DIM, NPE = ShapeTraits<SHAPE>::NPE;
+    shape_dndr<SHAPE>(r, g);
+    double J[DIM][DIM];
+#pragma unroll
+    for (int i = 0; i < DIM; i++)
+#pragma unroll
+        for (int k = 0; k < DIM; k++) {
+            double v = 0.0;
+#pragma unroll
+            for (int n = 0; n < NPE; n++) v += g[i][n] * X[n][k];
+            J[i][k] = v;
+        }
+    if constexpr (DIM == 2) {
+        det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+        const double i00 = J[1][1] / det, i01 = -J[0][1] / det, i10 = -J[1][0] / det, i11 = J[0][0] / det;
+#pragma unroll
+        for (int n = 0; n < NPE; n++) {
+            const double d0 = g[0][n], d1 = g[1][n];
+            g[0][n] = i00 * d0 + i01 * d1;
+            g[1][n] = i10 * d0 + i11 * d1;
+        }
+    } else {
+        det = -J[2][2] * J[0][1] * J[1][0] - J[2][1] * J[1][2] * J[0][0] - J[0][2] * J[1][1] * J[2][0]
+              + J[2][0] * J[0][1] * J[1][2] + J[2][1] * J[1][0] * J[0][2] + J[0][0] * J[1][1] * J[2][2];
+        const double i00 = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / det, i01 = -(J[0][1] * J[2][2] - J[0][2] * J[2][1]) / det;
+        const double i02 = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det, i10 = -(J[1][0] * J[2][2] - J[1][2] * J[2][0]) / det;
+        const double i11 = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det, i12 = -(J[0][0] * J[1][2] - J[0][2] * J[1][0]) / det;
+        const double i20 = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det, i21 = -(J[0][0] * J[2][1] - J[0][1] * J[2][0]) / det;
+        const double i22 = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+#pragma unroll
+        for (int n = 0; n < NPE; n++) {
+            const double d0 = g[0][n], d1 = g[1][n], d2 = g[2][n];
+            g[0][n] = i00 * d0 + i01 * d1 + i02 * d2;
+            g[1][n] = i10 * d0 + i11 * d1 + i12 * d2;
+            g[2][n] = i20 * d0 + i21 * d1 + i22 * d2;
+        }
+    }
+}
+
+// Rows of local node `a` of the element matrix for unit modulus: acc[i][b*NDOF + j], i = dof of node a.
+template <int KIND, int SHAPE>
+__device__ __forceinline__ void generic_rows(const double (&X)[ShapeTraits<SHAPE>::NPE][ShapeTraits<SHAPE>::DIM], int a, const ElemSpec& sp,
+                                             double t, double (&acc)[KindTraits<KIND>::NDOF][ShapeTraits<SHAPE>::NPE * KindTraits<KIND>::NDOF]) {
+    constexpr int DIM = ShapeTraits<SHAPE>::DIM, NPE = ShapeTraits<SHAPE>::NPE, NDOF = KindTraits<KIND>::NDOF;
+    static_assert(DIM == KindTraits<KIND>::DIM, "shape / equation dimension mismatch");
+#pragma unroll
+    for (int i = 0; i < NDOF; i++)
+#pragma unroll
+        for (int j = 0; j < NPE * NDOF; j++) acc[i][j] = 0.0;
+    for (int pass = 0; pass < sp.npass; pass++) {
+        const double cn = sp.cn[pass], lam = sp.lam[pass], mu = sp.mu[pass];
+        const int ng = quad_count(sp.quad[pass]);
+#pragma unroll 1
+        for (int q = 0; q < ng; q++) {
+            double r[3], wq, det, g[DIM][NPE];
+            quad_point(sp.quad[pass], q, r, wq);
+            shape_grad<SHAPE>(X, r, g, det);
+            const double w = (KIND == KIND_SOLID3D) ? det * wq : det * t * wq;
+            double ga[DIM];
+#pragma unroll
+            for (int k = 0; k < DIM; k++) {
+                ga[k] = g[k][0];
+#pragma unroll
+                for (int n = 1; n < NPE; n++) if (n == a) ga[k] = g[k][n];
+            }
+#pragma unroll
+            for (int b = 0; b < NPE; b++) {
+                if constexpr (KIND == KIND_HEAT2D) {
+                    acc[0][b] += (ga[0] * g[0][b] + ga[1] * g[1][b]) * w;
+                } else {
+                    double dotab = 0.0;
+#pragma unroll
+                    for (int k = 0; k < DIM; k++) dotab += ga[k] * g[k][b];
+#pragma unroll
+                    for (int i = 0; i < NDOF; i++)
+#pragma unroll
+                        for (int j = 0; j < NDOF; j++) {
+                            const double v = (i == j) ? (cn * ga[i] * g[i][b] + mu * (dotab - ga[i] * g[i][b]))
+                                                      : (lam * ga[i] * g[j][b] + mu * ga[j] * g[i][b]);
+                            acc[i][b * NDOF + j] += v * w;
+                        }
+                }
+            }
+        }
+    }
+}
+
+// strain energy ue^T Ke(E=1) ue of one element and, optionally, fe = Ke(E=1) ue
+template <int KIND, int SHAPE, bool WANT_F>
+__device__ __forceinline__ double generic_energy(const double (&X)[ShapeTraits<SHAPE>::NPE][ShapeTraits<SHAPE>::DIM],
+                                                 const double (&ue)[ShapeTraits<SHAPE>::NPE][KindTraits<KIND>::NDOF], const ElemSpec& sp, double t,
+                                                 double (&fe)[ShapeTraits<SHAPE>::NPE][KindTraits<KIND>::NDOF]) {
+    constexpr int DIM = ShapeTraits<SHAPE>::DIM, NPE = ShapeTraits<SHAPE>::NPE;
+    double wsum = 0.0;
+    for (int pass = 0; pass < sp.npass; pass++) {
+        const double cn = sp.cn[pass], lam = sp.lam[pass], mu = sp.mu[pass];
+        const int ng = quad_count(sp.quad[pass]);
+#pragma unroll 1
+        for (int q = 0; q < ng; q++) {
+            double r[3], wq, det, g[DIM][NPE];
+            quad_point(sp.quad[pass], q, r, wq);
+            shape_grad<SHAPE>(X, r, g, det);
+            const double w = (KIND == KIND_SOLID3D) ? det * wq : det * t * wq;
+            if constexpr (KIND == KIND_HEAT2D) {
+                double qx = 0.0, qy = 0.0;
+#pragma unroll
+                for (int n = 0; n < NPE; n++) { qx += g[0][n] * ue[n][0]; qy += g[1][n] * ue[n][0]; }
+                wsum += (qx * qx + qy * qy) * w;
+                if constexpr (WANT_F) {
+#pragma unroll
+                    for (int n = 0; n < NPE; n++) fe[n][0] += (g[0][n] * qx + g[1][n] * qy) * w;
+                }
+            } else if constexpr (KIND == KIND_ELAST2D) {
+                double exx = 0, eyy = 0, gxy = 0;
+#pragma unroll
+                for (int n = 0; n < NPE; n++) {
+                    exx += g[0][n] * ue[n][0]; eyy += g[1][n] * ue[n][1]; gxy += g[1][n] * ue[n][0] + g[0][n] * ue[n][1];
+                }
+                const double sxx = cn * exx + lam * eyy, syy = cn * eyy + lam * exx, sxy = mu * gxy;
+                wsum += (sxx * exx + syy * eyy + sxy * gxy) * w;
+                if constexpr (WANT_F) {
+#pragma unroll
+                    for (int n = 0; n < NPE; n++) {
+                        fe[n][0] += (g[0][n] * sxx + g[1][n] * sxy) * w;
+                        fe[n][1] += (g[1][n] * syy + g[0][n] * sxy) * w;
+                    }
+                }
+            } else {
+                double exx = 0, eyy = 0, ezz = 0, gxy = 0, gyz = 0, gzx = 0;
+#pragma unroll
+                for (int n = 0; n < NPE; n++) {
+                    const double ux = ue[n][0], uy = ue[n][1], uz = ue[n][2];
+                    exx += g[0][n] * ux; eyy += g[1][n] * uy; ezz += g[2][n] * uz;
+                    gxy += g[1][n] * ux + g[0][n] * uy; gyz += g[2][n] * uy + g[1][n] * uz; gzx += g[2][n] * ux + g[0][n] * uz;
+                }
+                const double sxx = cn * exx + lam * (eyy + ezz), syy = cn * eyy + lam * (exx + ezz), szz = cn * ezz + lam * (exx + eyy);
+                const double sxy = mu * gxy, syz = mu * gyz, szx = mu * gzx;
+                wsum += (sxx * exx + syy * eyy + szz * ezz + sxy * gxy + syz * gyz + szx * gzx) * w;
+                if constexpr (WANT_F) {
+#pragma unroll
+                    for (int n = 0; n < NPE; n++) {
+                        fe[n][0] += (g[0][n] * sxx + g[1][n] * sxy + g[2][n] * szx) * w;
+                        fe[n][1] += (g[1][n] * syy + g[0][n] * sxy + g[2][n] * syz) * w;
+                        fe[n][2] += (g[2][n] * szz + g[1][n] * syz + g[0][n] * szx) * w;
+                    }
+                }
+            }
+        }
+    }
+    return wsum;
+}
+
+}  // namespace pf2

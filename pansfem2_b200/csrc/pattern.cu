@@ -163,7 +163,8 @@ extern "C" {
 
 int pf2_mesh_create(pf2_ctx* ctx, int dim, int nnode, const double* coords_host, int npe, int nelem, const int* conn_host, pf2_mesh** out) {
     PF2_CHECK(ctx && out && coords_host && conn_host, "null argument");
-    PF2_CHECK((dim == 2 && npe == 4) || (dim == 3 && npe == 8), "supported elements: Q4 (dim 2, 4 nodes), hex8 (dim 3, 8 nodes)");
+    PF2_CHECK((dim == 2 && (npe == 3 || npe == 4 || npe == 6 || npe == 8)) || (dim == 3 && (npe == 4 || npe == 8 || npe == 20)),
+              "supported elements: T3 / Q4 / T6 / Q8 (dim 2; 3, 4, 6, 8 nodes), tet4 / hex8 / hex20 (dim 3; 4, 8, 20 nodes)");
     PF2_CHECK(nnode > 0 && nelem > 0, "empty mesh");
     PF2_CUDA(cudaSetDevice(ctx->device));
     pf2_mesh* m = new pf2_mesh();

@@ -2,6 +2,20 @@
 #pragma once
 #include "common.cuh"
 
+namespace pf2 {
+// decoded PF2_EQ_CODE (assemble_generic.cu)
+struct EqInfo {
+    int phys, shape, quad, quad2;   // fields of the code with the defaults filled in
+    int kind;                       // KIND_ELAST2D / KIND_HEAT2D / KIND_SOLID3D
+    int dim, npe, ndof;
+    bool fast;                      // one of the three specialised selections (element.cuh)
+    int legacy;                     // PF2_EQ_PLANESTRAIN / _SOLID / _HEAT of the specialised kernel when fast
+    int npass;
+    double cn[2], lam[2], mu[2];
+};
+int decode_eq(int eq, double V, EqInfo* out);
+}  // namespace pf2
+
 struct pf2_mesh {
     pf2_ctx* ctx = nullptr;
     int dim = 0, nnode = 0, npe = 0, nelem = 0;

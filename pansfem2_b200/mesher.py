@@ -104,3 +104,86 @@ def filter_neighbors_allpairs(centroids: np.ndarray, radius: float):
         w.append((radius - d[js]) / radius)
         rowptr[i + 1] = rowptr[i] + len(js)
     return rowptr, np.concatenate(nbr).astype(np.int32), np.concatenate(w).astype(np.float64)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Element families beyond Q4 / hex8.  Node order inside an element follows the reference's
+# ShapeFunction*::Points (ShapeFunction.h:98, 133, 171, 207, 262, 299, 345-365).
+# ------------------------------------------------------------------------------------------------------------------
+NATURAL_NODES = {
+    "T3": np.array([[1, 0], [0, 1], [0, 0]], float),
+    "T6": np.array([[1, 0], [0, 1], [0, 0], [0.5, 0.5], [0, 0.5], [0.5, 0]], float),
+    "Q4": np.array([[-1, -1], [1, -1], [1, 1], [-1, 1]], float),
+    "Q8": np.array([[-1, -1], [1, -1], [1, 1], [-1, 1], [0, -1], [1, 0], [0, 1], [-1, 0]], float),
+    "Tet4": np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [0, 0, 0]], float),
+    "Hex8": np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], float),
+    # the 20 nodes ShapeFunction20Cubic::dNdr differentiates (ShapeFunction.h:396-461): corners, then mid-edges
+    # 8..11 bottom face, 12..15 top face, 16..19 vertical edges
+    "Hex20": np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1],
+                       [0, -1, -1], [1, 0, -1], [0, 1, -1], [-1, 0, -1], [0, -1, 1], [1, 0, 1], [0, 1, 1], [-1, 0, 1],
+                       [-1, -1, 0], [1, -1, 0], [1, 1, 0], [-1, 1, 0]], float),
+}
+
+
+def _weld(points: np.ndarray, cells: int, npe: int):
+    """Merge coincident element nodes (coordinates are multiples of 1/2 cell): returns (coords, conn)."""
+    key = np.round(points * 4.0).astype(np.int64)
+    uniq, inv = np.unique(key, axis=0, return_inverse=True)
+    return uniq.astype(np.float64) / 4.0, inv.reshape(cells, npe).astype(np.int32)
+
+
+def family_mesh(family: str, n, lengths=None):
+    """Structured mesh of an n[0] x n[1] (x n[2]) block of unit-aspect cells made of `family` elements:
+    T3 / T6 = each cell cut in two along its diagonal, Q8, Tet4 = each cell cut in six (Kuhn), Hex20.
+    Returns (coords, conn); lengths default to the cell counts (unit cells)."""
+    n = tuple(int(v) for v in n)
+    dim = len(n)
+    lengths = tuple(float(v) for v in (lengths or n))
+    nat = NATURAL_NODES[family]
+    cells = np.stack(np.meshgrid(*[np.arange(v) for v in n], indexing="ij"), axis=-1).reshape(-1, dim).astype(float)
+    if family in ("Q4", "Q8", "Hex8", "Hex20"):
+        local = [(nat + 1.0) / 2.0]                                    # one element per cell on [0,1]^dim
+    elif family in ("T3", "T6"):
+        # two counter-clockwise triangles; vertex i of the triangle sits at natural point i (r0, r1, 1-r0-r1)
+        tris = [np.array([[1, 0], [1, 1], [0, 0]], float), np.array([[1, 1], [0, 1], [0, 0]], float)]
+        local = [np.array([p[0] * v[0] + p[1] * v[1] + (1 - p[0] - p[1]) * v[2] for p in nat]) for v in tris]
+    elif family == "Tet4":
+        import itertools
+        local = []
+        for perm in itertools.permutations(range(3)):                  # Kuhn subdivision: 6 tetrahedra per cube
+            v = [np.zeros(3)]
+            for ax in perm:
+                w = v[-1].copy(); w[ax] = 1.0; v.append(w)
+            t = np.array([v[1], v[2], v[3], v[0]])
+            if np.linalg.det(t[:3] - t[3]) < 0:
+                t = t[[1, 0, 2, 3]]
+            local.append(t)
+    else:
+        raise ValueError(family)
+    pts = np.concatenate([(cells[:, None, :] + l[None, :, :]) for l in local], axis=1)     # cells x (k*npe) x dim
+    npe = nat.shape[0]
+    coords, conn = _weld(pts.reshape(-1, dim), cells.shape[0] * len(local), npe)
+    coords = coords * (np.array(lengths) / np.array(n, float))
+    return coords, conn
+
+
+def element_centroids(coords: np.ndarray, conn: np.ndarray):
+    """CenterOfGravity (General.h): mean of the element's node coordinates."""
+    return coords[conn].mean(axis=1)
+
+
+def filter_neighbors_centroid(centroids: np.ndarray, radius: float):
+    """Same lists as the all-pairs search of the samples (ascending element id, weight (R-d)/R) through a k-d tree."""
+    from scipy.spatial import cKDTree
+    tree = cKDTree(centroids)
+    lists = tree.query_ball_point(centroids, radius * (1.0 + 1e-12))
+    rowptr = np.zeros(len(centroids) + 1, dtype=np.int64)
+    nbr, w = [], []
+    for i, js in enumerate(lists):
+        js = np.array(sorted(js), dtype=np.int64)
+        d = np.sqrt(((centroids[js] - centroids[i]) ** 2).sum(axis=1))
+        keep = d <= radius
+        js, d = js[keep], d[keep]
+        nbr.append(js); w.append((radius - d) / radius)
+        rowptr[i + 1] = rowptr[i] + len(js)
+    return rowptr, np.concatenate(nbr).astype(np.int32), np.concatenate(w).astype(np.float64)

@@ -10,12 +10,11 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from . import mesher
+from . import eqcode, mesher
 
 EQ_PLANESTRAIN, EQ_SOLID, EQ_HEAT = 0, 1, 2
 FILTER_DENSITY, FILTER_HEAVISIDE = 0, 1
 OPT_OC, OPT_MMA, OPT_CONLIN = 0, 1, 2
-NDOF = {EQ_PLANESTRAIN: 2, EQ_SOLID: 3, EQ_HEAT: 1}
 
 
 @dataclass
@@ -54,7 +53,7 @@ class Problem:
 
     @property
     def ndof(self):
-        return NDOF[self.eq]
+        return eqcode.ndof(self.eq)
 
     @property
     def nnode(self):
@@ -116,3 +115,30 @@ def cantilever3d(nx=16, ny=8, nz=8, opt_kind=OPT_OC, filter_kind=FILTER_DENSITY,
     nbrs = mesher.filter_neighbors_3d(nxl, ny, nz, float(nxl), ly, lz, radius)
     return Problem(f"cantilever3d_{nx}x{ny}x{nz}", EQ_SOLID, coords, conn, fixed, (ln, ld, lv), nbrs, (nxl, ny, nz),
                    filter_kind=filter_kind, opt_kind=opt_kind, beta_period=0, extra={"global_grid": (nx, ny, nz)})
+
+
+def family_problem(eq, n, opt_kind=OPT_OC, filter_kind=FILTER_DENSITY, radius=1.5) -> Problem:
+    """A cantilever (elastic physics) or heat sink (HeatTransfer) on a structured block of ANY element family: `eq` is a
+    PF2_EQ_CODE (pansfem2_b200/eqcode.py), n the cell counts.  Clamp / sink on x = 0; unit load on the nodes of the
+    x = lx face closest to mid-height (elastic) or a uniform nodal source (heat)."""
+    phys, shape, _, _ = eqcode.fields(eq)
+    fam = eqcode.SHAPE_NAME[shape]
+    coords, conn = mesher.family_mesh(fam, n)
+    ndof = eqcode.ndof(eq)
+    lx, ly = float(n[0]), float(n[1])
+    fixed = mesher.fixed_list(coords, list(range(ndof)), lambda x: np.abs(x[:, 0]) < 1.0e-9)
+    if phys == eqcode.PHYS_HEAT:
+        is_fixed = np.zeros(coords.shape[0], bool)
+        is_fixed[fixed[0]] = True
+        ln = np.nonzero(~is_fixed)[0].astype(np.int32)
+        loads = (ln, np.zeros_like(ln), np.full(ln.shape, 1.0 / coords.shape[0]))
+        kw = dict(E0=1.0e-3, E1=1.0, weightlimit=0.4, scale0=1.0)
+    else:
+        face = np.abs(coords[:, 0] - lx) < 1.0e-9
+        dist = np.where(face, np.abs(coords[:, 1] - ly / 2), np.inf)
+        sel = np.nonzero(face & (dist <= dist.min() + 1.0e-9))[0].astype(np.int32)
+        loads = (sel, np.ones_like(sel), np.full(sel.shape, -1.0 / len(sel)))
+        kw = {}
+    nbrs = mesher.filter_neighbors_centroid(mesher.element_centroids(coords, conn), radius)
+    return Problem(f"{eqcode.describe(eq)}_{'x'.join(str(v) for v in n)}", eq, coords, conn, fixed, loads, nbrs, tuple(n),
+                   filter_kind=filter_kind, opt_kind=opt_kind, beta_period=0, **kw)

@@ -191,7 +191,82 @@ def golden_conlin():
     print("conlin fixtures:", len(d))
 
 
+def parse_vtk_mesh(path):
+    lines = open(path).read().split("\n")
+    i = next(k for k, ln in enumerate(lines) if ln.startswith("POINTS"))
+    npts = int(lines[i].split()[1])
+    pts = np.array([[float(v) for v in lines[i + 1 + k].split()] for k in range(npts)])
+    j = next(k for k, ln in enumerate(lines) if ln.startswith("CELLS"))
+    ncell = int(lines[j].split()[1])
+    cells = [[int(v) for v in lines[j + 1 + k].split()][1:] for k in range(ncell)]
+    return pts, np.array(cells, dtype=np.int32)
+
+
+def all_selections():
+    from pansfem2_b200 import eqcode as ec
+    out = []
+    for phys in (ec.PHYS_PLANESTRAIN, ec.PHYS_PLANESTRESS, ec.PHYS_HEAT, ec.PHYS_PLANESTRAIN_SRI, ec.PHYS_SOLID):
+        shapes = (ec.SHAPE_TET4, ec.SHAPE_HEX8, ec.SHAPE_HEX20) if phys == ec.PHYS_SOLID else (ec.SHAPE_T3, ec.SHAPE_T6, ec.SHAPE_Q4, ec.SHAPE_Q8)
+        for shape in shapes:
+            for quad in ec.SHAPE_RULES[shape]:
+                for q2 in (ec.SHAPE_RULES[shape] if phys == ec.PHYS_PLANESTRAIN_SRI else (0,)):
+                    out.append(ec.eq_code(phys, shape, quad, q2))
+    return out
+
+
+def golden_families():
+    """Element families beyond Q4 / hex8: every <Equation, SF, IC> selection of the reference on a
+    distorted element, assembled systems + solves + short SIMP runs on family meshes (live reference), and the reference's
+    committed T3 outputs sample/heattransfer/static.vtk and sample/planestrain/result.vtk."""
+    from pansfem2_b200 import eqcode as ec, mesher
+    reflib.set_num_threads(1)
+    rng = np.random.default_rng(20210301)
+    d = {}
+    sel = all_selections()
+    d["selections"] = np.array(sel, np.int64)
+    for eq in sel:
+        shape = ec.fields(eq)[1]
+        nat = mesher.NATURAL_NODES[ec.SHAPE_NAME[shape]]
+        xe = nat * (np.array([1.3, 0.9]) if nat.shape[1] == 2 else np.array([1.3, 0.8, 1.1])) + 0.08 * rng.uniform(-1, 1, nat.shape)
+        d[f"xe_{eq}"] = xe
+        d[f"ke_{eq}"] = reflib.element_matrix(eq, xe, 2.5, 0.3, 0.7)
+    # assembled systems (non-zero Dirichlet values) and ScalingCG solutions on small family meshes
+    cases = {"t3_heat": (ec.eq_code(ec.PHYS_HEAT, ec.SHAPE_T3), (6, 4)),
+             "t6_pstress": (ec.eq_code(ec.PHYS_PLANESTRESS, ec.SHAPE_T6, ec.QUAD_G3TRI), (5, 3)),
+             "q8_sri": (ec.eq_code(ec.PHYS_PLANESTRAIN_SRI, ec.SHAPE_Q8, ec.QUAD_G9SQ, ec.QUAD_G4SQ), (5, 3)),
+             "q8_pstrain": (ec.eq_code(ec.PHYS_PLANESTRAIN, ec.SHAPE_Q8, ec.QUAD_G9SQ), (4, 3)),
+             "tet4": (ec.eq_code(ec.PHYS_SOLID, ec.SHAPE_TET4), (3, 2, 2)),
+             "hex20": (ec.eq_code(ec.PHYS_SOLID, ec.SHAPE_HEX20, ec.QUAD_G27CUBE), (3, 2, 2))}
+    for nm, (eq, n) in cases.items():
+        P = problems.family_problem(eq, n)
+        fixed = (P.fixed[0], P.fixed[1], np.where(P.fixed[1] == 0, 0.01, -0.02))
+        Emod = rng.uniform(0.5, 2.0, P.nelem)
+        S = reflib.assemble(P.eq, P.coords, P.conn, fixed, P.loads, Emod, 0.3, 0.8)
+        indptr, indices, data, F = S.arrays()
+        d[f"{nm}_eq"], d[f"{nm}_n"] = np.int64(eq), np.array(n)
+        d.update({f"{nm}_Emod": Emod, f"{nm}_indptr": indptr, f"{nm}_indices": indices, f"{nm}_data": data, f"{nm}_F": F,
+                  f"{nm}_x": S.solve(1, F)[0]})
+        # 4 SIMP iterations (OC + density filter), history and final design
+        R = reflib.simp_run(P.eq, P.coords, P.conn, P.fixed, P.loads, P.filter_kind, P.nbrs, P.opt_kind, P.optp(), P.params(), 4,
+                            np.full(P.nelem, 0.5), check_convergence=False)
+        d[f"{nm}_hist"], d[f"{nm}_s4"] = R["hist"][:, :2], R["s"]
+        print(nm, ec.describe(eq), P.nelem, "rows", S.rows, "f", R["hist"][:, 0])
+    np.savez_compressed(f"{OUT}/live_families.npz", **d)
+    # committed T3 outputs of the reference
+    pts, cells = parse_vtk_mesh(f"{REF}/sample/heattransfer/static.vtk")
+    f = parse_vtk_fields(f"{REF}/sample/heattransfer/static.vtk")
+    T = f["T"] if f["T"].ndim == 1 else f["T"][:, 0]
+    pts2, cells2 = parse_vtk_mesh(f"{REF}/sample/planestrain/result.vtk")
+    f2 = parse_vtk_fields(f"{REF}/sample/planestrain/result.vtk")
+    np.savez_compressed(f"{OUT}/t3_samples.npz", heat_coords=pts[:, :2], heat_conn=cells, heat_T=T,
+                        ps_coords=pts2[:, :2], ps_conn=cells2, ps_u=f2["u"][:, :2], ps_r=f2["r"][:, :2])
+    print("t3 goldens", pts.shape, cells.shape, T.min(), T.max(), f2["u"])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "families":
+        golden_families()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "conlin":
         f = parse_vtk_fields(f"{REF}/sample/optimize/Density_CONLIN.vtk")
         np.savez_compressed(f"{OUT}/density_conlin.npz", u=f["u"][:, :2], r=f["r"][:, :2], rho=f["s"])
@@ -202,3 +277,4 @@ if __name__ == "__main__":
     golden_mma_kat()
     golden_live()
     golden_conlin()
+    golden_families()
