@@ -12,11 +12,15 @@
 namespace PANSFEM2 { namespace B200 {
     //  equation tags == the reference's element routines with their template arguments
     template<template<class>class SF, template<class>class IC>
-    struct PlaneStrainStiffnessTag { static_assert(IsQ4Gauss4<SF, IC>::value, "Q4 + Gauss4Square"); static const int eq = PF2_EQ_PLANESTRAIN; static const int ndof = 2; };
+    struct PlaneStrainStiffnessTag { static const int eq = EqCode<PF2_PHYS_PLANESTRAIN, SF, IC>::value; static const int ndof = 2; };
     template<template<class>class SF, template<class>class IC>
-    struct SolidLinearIsotropicElasticTag { static_assert(IsH8Gauss8<SF, IC>::value, "Hex8 + Gauss8Cubic"); static const int eq = PF2_EQ_SOLID; static const int ndof = 3; };
+    struct PlaneStressStiffnessTag { static const int eq = EqCode<PF2_PHYS_PLANESTRESS, SF, IC>::value; static const int ndof = 2; };
+    template<template<class>class SF, template<class>class ICV, template<class>class ICD>
+    struct PlaneStrainStiffnessSRITag { static const int eq = EqCodeSRI<SF, ICV, ICD>::value; static const int ndof = 2; };
     template<template<class>class SF, template<class>class IC>
-    struct HeatTransferTag { static_assert(IsQ4Gauss4<SF, IC>::value, "Q4 + Gauss4Square"); static const int eq = PF2_EQ_HEAT; static const int ndof = 1; };
+    struct SolidLinearIsotropicElasticTag { static const int eq = EqCode<PF2_PHYS_SOLID, SF, IC>::value; static const int ndof = 3; };
+    template<template<class>class SF, template<class>class IC>
+    struct HeatTransferTag { static const int eq = EqCode<PF2_PHYS_HEAT, SF, IC>::value; static const int ndof = 1; };
 
     typedef std::vector<std::pair<std::pair<int, int>, double> > BcList;
     inline void SplitBc(const BcList& _bc, std::vector<int>& _node, std::vector<int>& _dof, std::vector<double>& _val) {

@@ -258,6 +258,11 @@ def golden_families():
     T = f["T"] if f["T"].ndim == 1 else f["T"][:, 0]
     pts2, cells2 = parse_vtk_mesh(f"{REF}/sample/planestrain/result.vtk")
     f2 = parse_vtk_fields(f"{REF}/sample/planestrain/result.vtk")
+    # N / dNdr / Points / Weights of every policy class, printed by the reference's own headers
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "shape_tables")
+        subprocess.run(["g++", "-O1", "-std=c++17", f"-I{REF}/src", f"{ROOT}/tests/cpp/shape_tables.cpp", "-o", exe], check=True)
+        open(f"{OUT}/shape_tables.txt", "w").write(subprocess.run([exe], check=True, capture_output=True, text=True).stdout)
     np.savez_compressed(f"{OUT}/t3_samples.npz", heat_coords=pts[:, :2], heat_conn=cells, heat_T=T,
                         ps_coords=pts2[:, :2], ps_conn=cells2, ps_u=f2["u"][:, :2], ps_r=f2["r"][:, :2])
     print("t3 goldens", pts.shape, cells.shape, T.min(), T.max(), f2["u"])

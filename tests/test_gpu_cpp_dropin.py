@@ -111,3 +111,54 @@ def test_unmodified_reference_solid_driver_on_the_header_mirror(tmp_path, golden
     got = parse_vtk(d / "result_linear.vtk")
     assert abs(np.abs(got["u"]).max() - 1.48963) < 1e-5
     np.testing.assert_allclose(got["u"], g["u"], rtol=6e-6, atol=1e-9)
+
+
+def test_unmodified_reference_planestrain_t3_driver_on_the_header_mirror(tmp_path, golden_dir):
+    """sample/planestrain/sample_planestrain.cpp, unmodified: PlaneStrainStiffness<ShapeFunction3Triangle, Gauss1Triangle> on the
+    device, body / surface force vectors through the mirror's host routines, CG; output against the committed result.vtk."""
+    exe = need("dropin_planestrain_t3")
+    (tmp_path / "sample" / "planestrain").mkdir(parents=True)
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got, g = parse_vtk(tmp_path / "sample" / "planestrain" / "result.vtk"), np.load(os.path.join(golden_dir, "t3_samples.npz"))
+    np.testing.assert_allclose(got["u"][:, :2], g["ps_u"], rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(got["r"][:, :2], g["ps_r"], rtol=1e-5, atol=2e-3)
+
+
+@pytest.mark.parametrize("family,nx,ny", [("t3", 12, 8), ("q8sri", 10, 6)])
+def test_batched_driver_on_other_element_families(family, nx, ny):
+    """sample_optimize_density_families: the batched C++ API with PlaneStressStiffnessTag<3Triangle, Gauss1Triangle> and
+    PlaneStrainStiffnessSRITag<8Square, Gauss4Square, Gauss9Square>; the run is replayed in the oracle on the same mesh."""
+    from oracle import portlib as orc
+    from pansfem2_b200 import eqcode as ec, mesher, problems
+    exe = need("sample_optimize_density_families")
+    r = subprocess.run([exe, family, str(nx), str(ny), "4"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    hist = np.array([[float(t) for t in (ln.split("\t")[2], ln.split("\t")[4])] for ln in r.stdout.strip().split("\n") if ln.startswith("k =")])
+    assert hist.shape == (4, 2)
+    coords, quads = mesher.square_mesh(float(nx), float(ny), nx, ny)
+    if family == "t3":
+        conn = np.stack([quads[:, [1, 2, 0]], quads[:, [2, 3, 0]]], axis=1).reshape(-1, 3)
+        eq = ec.eq_code(ec.PHYS_PLANESTRESS, ec.SHAPE_T3, ec.QUAD_G1TRI)
+    else:
+        mid, extra, conn = {}, [], []
+        for q in quads:
+            e = list(q)
+            for a in range(4):
+                key = (min(q[a], q[(a + 1) % 4]), max(q[a], q[(a + 1) % 4]))
+                if key not in mid:
+                    mid[key] = len(coords) + len(extra)
+                    extra.append((coords[key[0]] + coords[key[1]]) / 2.0)
+                e.append(mid[key])
+            conn.append(e)
+        coords, conn = np.vstack([coords, np.array(extra)]), np.array(conn, np.int32)
+        eq = ec.eq_code(ec.PHYS_PLANESTRAIN_SRI, ec.SHAPE_Q8, ec.QUAD_G9SQ, ec.QUAD_G4SQ)
+    conn = np.ascontiguousarray(conn, dtype=np.int32)
+    fixed = mesher.fixed_list(coords, [0, 1], lambda x: np.abs(x[:, 0]) < 1e-9)
+    loads = mesher.fixed_list(coords, [1], lambda x: (np.abs(x[:, 0] - nx) < 1e-9) & (np.abs(x[:, 1] - ny / 2) < 1e-9), -1.0)
+    nbrs = mesher.filter_neighbors_allpairs(mesher.element_centroids(coords, conn), 1.5)
+    P = problems.Problem("replay", eq, coords, conn, fixed, loads, nbrs, (nx, ny), filter_kind=problems.FILTER_DENSITY, beta_period=0)
+    R = orc.simp_run(eq, P.coords, P.conn, P.fixed, P.loads, P.filter_kind, P.nbrs, P.opt_kind, P.optp(), P.params(), 4,
+                     np.full(P.nelem, 0.5), check_convergence=False)
+    np.testing.assert_allclose(hist[:, 0], R["hist"][:, 0], rtol=1e-8)
+    np.testing.assert_allclose(hist[:, 1], R["hist"][:, 1], rtol=0, atol=1e-9)
