@@ -390,6 +390,12 @@ def compliance_sens(mesh, eq, u_dev, rho_dev, params6, want_r=False):
     return f.value, dfd.download(), (r.download().reshape(mesh.nnode, -1) if r is not None else None)
 
 
+def compliance_sens_device(mesh, eq, u_dev, rho_dev, params6, dfdrho_dev, r_dev=None):
+    """Same pass with caller-owned device outputs and no host read-back (the compliance stays in the context's scalar slot)."""
+    prm = (C.c_double * 6)(*params6)
+    _ck(lib().pf2_compliance_sens(mesh.h, eq, u_dev.ptr, rho_dev.ptr, prm, None, dfdrho_dev.ptr, r_dev.ptr if r_dev is not None else None))
+
+
 class Simp:
     """The device-resident design loop for a pansfem2_b200.problems.Problem."""
 
