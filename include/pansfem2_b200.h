@@ -70,6 +70,7 @@ typedef struct pf2_filter pf2_filter;
 typedef struct pf2_oc pf2_oc;
 typedef struct pf2_mma pf2_mma;
 typedef struct pf2_simp pf2_simp;
+typedef struct pf2_levelset pf2_levelset;
 
 const char* pf2_last_error(void);
 const char* pf2_version(void);
@@ -236,6 +237,25 @@ int pf2_simp_get(pf2_simp* S, double* s_host, double* rho_host, double* u_nodal_
 /* per-phase device time of the last iteration, ms: {filter, assemble, solve, compliance+sens, filter-sens, update} */
 int pf2_simp_phase_ms(pf2_simp* S, double ms[6]);
 int pf2_simp_cg_stats(pf2_simp* S, double* spmv_ms_avg, long long* spmv_calls);
+
+/* ---- the level-set design loop (sample_optimize_levelset.cpp:75-192; PlaneStress.h:21, ReactionDiffusion.h:21-145,
+ *      General.h:193-235) ---------------------------------------------------------------------------------------- */
+/* mesh: Q4; map_u / K: the 2-dof displacement numbering and its pattern (pf2_dofmap_create, pf2_csr_pattern);
+ * phi_fixed_nodes: nodes where the level-set function is held at 0 (driver :63-68);
+ * prm = { Vmax, tau, E0, Emin, nu, nvol, dt, d, p } (driver :25-34); tmax bounds the objective history.
+ * The reaction-diffusion matrix T = Me/dt + tau*nelem*Ke is assembled once here (it does not depend on the design).
+ * Initial state phi = 1, str = 1 (driver :70-71); pf2_levelset_set_state overrides it. */
+int pf2_levelset_create(pf2_ctx* ctx, pf2_mesh* mesh, pf2_dofmap* map_u, pf2_csr* K, int nphi, const int* phi_fixed_nodes_host,
+                        const double prm[9], int tmax, int nload, const int* load_node_host, const int* load_dof_host,
+                        const double* load_val_host, pf2_levelset** out);
+int pf2_levelset_destroy(pf2_levelset* ls);
+int pf2_levelset_set_state(pf2_levelset* ls, const double* phi_host, const double* str_host);
+/* one pass of the loop body; stats[8] = { objective (the driver prints objective/nelem), volume, lambda, converged,
+ * CG iterations of the displacement solve, its relative residual, CG iterations of the phi solve, t }.
+ * When the driver's convergence test fires (:128-137) the level-set update is skipped, as there. */
+int pf2_levelset_iterate(pf2_levelset* ls, int check_convergence, double stats[8]);
+/* phi (nnode), str (nelem), u (nnode*2) of the last iteration; any pointer may be NULL */
+int pf2_levelset_get(pf2_levelset* ls, double* phi_host, double* str_host, double* u_host);
 
 /* ---- multi-GPU: row-block (x-slab) partition over the GPUs of one box (no counterpart in the reference, whose only
  *      parallelism is the OpenMP loop of CSR.h:114) ----------------------------------------------------------------- */

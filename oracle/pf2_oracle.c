@@ -1078,3 +1078,154 @@ int orc_simp_run(int eq, int nnode, const double* coords, int nelem, const int* 
     free(n2g); free(ufix); free(Emod); free(sol); free(dfdrho); free(dgdrho); free(dfds); free(dgds); free(u);
     return k;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Level-set topology optimisation  sample/optimize/sample_optimize_levelset.cpp:75-192   
+ *   PlaneStressStiffness<Q4, Gauss4Square>                     src/FEM/Equation/PlaneStress.h:21-58
+ *   ReactionDiffusionConsistentMass / Stiffness / Reaction     src/FEM/Equation/ReactionDiffusion.h:21-48, 82-107, 111-145
+ *   InterpolateNodalFromElemental / ElementalFromNodal         src/FEM/Equation/General.h:193-207, 225-235
+ * prm = { Vmax, tau, E0, Emin, nu, nvol, dt, d, p };  hist[3*t] = { objective[t], vol, lambda };  same contract as
+ * ref_levelset_run (oracle/ref_shim.cpp).
+ * ---------------------------------------------------------------------------------------------------------- */
+static void shape_n_q4(const double* r, double* N) {          /* ShapeFunction4Square::N  ShapeFunction.h:175-182 */
+    N[0] = 0.25 * (1.0 - r[0]) * (1.0 - r[1]); N[1] = 0.25 * (1.0 + r[0]) * (1.0 - r[1]);
+    N[2] = 0.25 * (1.0 + r[0]) * (1.0 + r[1]); N[3] = 0.25 * (1.0 - r[0]) * (1.0 + r[1]);
+}
+
+/* Me (4x4), Ke = D dNdX^T dNdX (4x4), Fe = int N C (u - lambda) with u interpolated from the nodal field un */
+static void rd_element_q4(const double* xe, double Dcoef, const double* un, double Ccoef, double lambda, double* Me, double* Ke, double* Fe) {
+    memset(Me, 0, sizeof(double) * 16); memset(Ke, 0, sizeof(double) * 16); memset(Fe, 0, sizeof(double) * 4);
+    for (int g = 0; g < 4; g++) {
+        double r[3], w[3], N[4], dNdr[8], dXdr[4], inv[4], dNdX[8];
+        quad_point(QUAD_G4SQ, g, r, w);
+        shape_n_q4(r, N);
+        shape_dndr(SHAPE_Q4, r, dNdr);
+        matmul(2, 4, 2, dNdr, xe, dXdr);
+        double J = det_d(2, dXdr);
+        inv_d(2, dXdr, inv);
+        matmul(2, 2, 4, inv, dNdr, dNdX);
+        for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) Me[i * 4 + j] += N[i] * N[j] * J * w[0] * w[1];
+        double DBt[8], BtB[16];                                  /* (_D*dNdX.Transpose())*dNdX*J*w0*w1 */
+        for (int i = 0; i < 4; i++) for (int k = 0; k < 2; k++) DBt[i * 2 + k] = dNdX[k * 4 + i] * Dcoef;
+        matmul(4, 2, 4, DBt, dNdX, BtB);
+        for (int i = 0; i < 16; i++) Ke[i] += BtB[i] * J * w[0] * w[1];
+        double u = 0.0;
+        for (int i = 0; i < 4; i++) u += N[i] * un[i];
+        double f = Ccoef * (u - lambda);
+        for (int i = 0; i < 4; i++) Fe[i] += N[i] * f * J * w[0] * w[1];
+    }
+}
+
+int orc_levelset_run(int nnode, const double* coords, int nelem, const int* conn,
+                     int nfixed, const int* fnode, const int* fdof, const double* fval,
+                     int nload, const int* lnode, const int* ldof, const double* lval,
+                     int nphi, const int* pnode, const double* prm, int tmax,
+                     double* phi, double* str, double* u_out, double* hist, int* converged) {
+    const double Vmax = prm[0], tau = prm[1], E0 = prm[2], Emin = prm[3], nu = prm[4], nvol = prm[5], dt = prm[6], d = prm[7], p = prm[8];
+    const int eq = PHYS_PLANESTRESS | (SHAPE_Q4 << 8) | (QUAD_G4SQ << 16);
+    const double A1 = -1.5 * (1.0 - nu) * (1.0 - 14.0 * nu + 15.0 * pow(nu, 2.0)) * E0 / ((1.0 + nu) * (7.0 - 5.0 * nu) * pow(1.0 - 2.0 * nu, 2.0));
+    const double A2 = 7.5 * (1.0 - nu) * E0 / ((1.0 + nu) * (7.0 - 5.0 * nu));
+    const double c = A1 / (A1 + 2.0 * A2);
+    /* displacement system */
+    int* n2g = (int*)malloc(sizeof(int) * (size_t)nnode * 2);
+    double* ufix = (double*)malloc(sizeof(double) * (size_t)nnode * 2);
+    int kdeg = orc_dofmap(nnode, 2, nfixed, fnode, fdof, fval, n2g, ufix);
+    orc_system* K = orc_pattern(nnode, 2, 4, nelem, conn, n2g, kdeg);
+    /* level-set system: phi = 0 on the listed nodes */
+    int* n2g2 = (int*)malloc(sizeof(int) * (size_t)nnode);
+    int* pdof = (int*)calloc((size_t)nphi, sizeof(int));
+    double* pval = (double*)calloc((size_t)nphi, sizeof(double));
+    int tdeg = orc_dofmap(nnode, 1, nphi, pnode, pdof, pval, n2g2, NULL);
+    orc_system* T = orc_pattern(nnode, 1, 4, nelem, conn, n2g2, tdeg);
+    double* Emod = (double*)malloc(sizeof(double) * (size_t)nelem), *x = (double*)malloc(sizeof(double) * (size_t)kdeg);
+    double* u = (double*)malloc(sizeof(double) * (size_t)nnode * 2), *TD = (double*)malloc(sizeof(double) * (size_t)nelem);
+    double* TDN = (double*)malloc(sizeof(double) * (size_t)nnode), *objective = (double*)calloc((size_t)tmax, sizeof(double));
+    int* count = (int*)malloc(sizeof(int) * (size_t)nnode);
+    double* y = (double*)malloc(sizeof(double) * (size_t)tdeg);
+    double volInit = 0.0;
+    for (int i = 0; i < nelem; i++) volInit += str[i];
+    volInit /= (double)nelem;
+    *converged = 0;
+    int t = 0;
+    for (; t < tmax; t++) {
+        for (int i = 0; i < nelem; i++) Emod[i] = Emin + str[i] * (E0 - Emin);
+        orc_assemble_numeric(K, eq, coords, nelem, conn, n2g, ufix, Emod, nu, 1.0, nload, lnode, ldof, lval, NULL);
+        double relres;
+        orc_solve(K, NULL, 1, K->F, 100000, 1.0e-10, x, &relres);
+        for (size_t i = 0; i < (size_t)nnode * 2; i++) u[i] = (n2g[i] != -1) ? x[n2g[i]] : ufix[i];
+        memcpy(u_out, u, sizeof(double) * (size_t)nnode * 2);
+        /* objective and topological derivative (driver :112-122) */
+        for (int e = 0; e < nelem; e++) {
+            const int* el = conn + (size_t)e * 4;
+            double xe[8], ue[8], Ke[64], Keue[8];
+            for (int a = 0; a < 4; a++) for (int k = 0; k < 2; k++) { xe[a * 2 + k] = coords[(size_t)el[a] * 2 + k]; ue[a * 2 + k] = u[(size_t)el[a] * 2 + k]; }
+            orc_element_matrix(eq, xe, Emod[e], nu, 1.0, Ke);
+            for (int i = 0; i < 8; i++) { double v = 0.0; for (int j = 0; j < 8; j++) v += Ke[i * 8 + j] * ue[j]; Keue[i] = v; }
+            double w = 0.0;
+            for (int i = 0; i < 8; i++) w += ue[i] * Keue[i];
+            objective[t] += w;
+            orc_element_matrix(eq, xe, (A1 + 2.0 * A2) * (1.0 - pow(c, 2.0)), c, 1.0, Ke);
+            for (int i = 0; i < 8; i++) { double v = 0.0; for (int j = 0; j < 8; j++) v += Ke[i * 8 + j] * ue[j]; Keue[i] = v; }
+            const double a = 1.0e-4 + str[e] * (1.0 - 1.0e-4);
+            w = 0.0;
+            for (int i = 0; i < 8; i++) w += (ue[i] * a) * Keue[i];          /* (a*ue)*(Ke*ue): scalar*Vector, then the dot */
+            TD[e] = w;
+        }
+        for (int i = 0; i < nnode; i++) { TDN[i] = 0.0; count[i] = 0; }
+        for (int e = 0; e < nelem; e++) for (int a = 0; a < 4; a++) { TDN[conn[(size_t)e * 4 + a]] += TD[e]; count[conn[(size_t)e * 4 + a]]++; }
+        for (int i = 0; i < nnode; i++) TDN[i] /= (double)count[i];
+        double vol = 0.0;
+        for (int i = 0; i < nelem; i++) vol += str[i];
+        vol /= (double)nelem;
+        const double frac = 1.0 - (t + 1) / (double)nvol;
+        const double ex = Vmax + (volInit - Vmax) * (frac > 0.0 ? frac : 0.0);
+        double tsum = 0.0;
+        for (int i = 0; i < nnode; i++) tsum += TDN[i];
+        const double lambda = tsum / (double)nnode * exp(p * ((vol - ex) / ex + d));
+        hist[3 * t] = objective[t]; hist[3 * t + 1] = vol; hist[3 * t + 2] = lambda;
+        if (t > nvol && fabs(vol - Vmax) < 0.005) {
+            int ok = 1;
+            for (int k = 1; k <= 5; k++) ok = ok && (fabs(objective[t] - objective[t - k]) < 0.01 * fabs(objective[t]));
+            if (ok) { *converged = 1; t++; break; }
+        }
+        double Cc = 0.0;
+        for (int i = 0; i < nnode; i++) Cc += fabs(TDN[i]);
+        Cc = nelem / Cc;
+        /* reaction-diffusion step (driver :147-176); phi is held at 0 on the listed nodes (SetDirichlet) */
+        for (int i = 0; i < nphi; i++) phi[pnode[i]] = 0.0;
+        memset(T->data, 0, sizeof(double) * (size_t)T->indptr[T->n]);
+        memset(T->F, 0, sizeof(double) * (size_t)T->n);
+        for (int e = 0; e < nelem; e++) {
+            const int* el = conn + (size_t)e * 4;
+            double xe[8], un[4], phie[4], Me[16], Ke[16], Fe[4], Te[16], Ye[4];
+            for (int a = 0; a < 4; a++) { xe[a * 2] = coords[(size_t)el[a] * 2]; xe[a * 2 + 1] = coords[(size_t)el[a] * 2 + 1]; un[a] = TDN[el[a]]; phie[a] = phi[el[a]]; }
+            rd_element_q4(xe, tau * nelem, un, Cc, lambda, Me, Ke, Fe);
+            for (int i = 0; i < 16; i++) Te[i] = Me[i] / dt + Ke[i];
+            for (int i = 0; i < 4; i++) { double v = 0.0; for (int j = 0; j < 4; j++) v += (Me[i * 4 + j] / dt) * phie[j]; Ye[i] = v + Fe[i]; }
+            for (int i = 0; i < 4; i++) {
+                int r = n2g2[el[i]];
+                if (r == -1) continue;
+                for (int j = 0; j < 4; j++) {
+                    int cc = n2g2[el[j]];
+                    if (cc != -1) T->data[find_col(T, r, cc)] += Te[i * 4 + j];
+                    else T->F[r] -= Te[i * 4 + j] * phi[el[j]];
+                }
+            }
+            for (int i = 0; i < 4; i++) { int r = n2g2[el[i]]; if (r != -1) T->F[r] += Ye[i]; }
+        }
+        orc_solve(T, NULL, 1, T->F, 100000, 1.0e-10, y, &relres);
+        for (int i = 0; i < nnode; i++) {
+            if (n2g2[i] != -1) phi[i] = y[n2g2[i]];
+            phi[i] = fmax(fmin(1.0, phi[i]), -1.0);
+        }
+        for (int e = 0; e < nelem; e++) {
+            double v = 0.0;
+            for (int a = 0; a < 4; a++) v += phi[conn[(size_t)e * 4 + a]];
+            v /= 4.0;
+            str[e] = (v < 0.0) ? 0.0 : 1.0;
+        }
+    }
+    free(n2g); free(ufix); free(n2g2); free(pdof); free(pval); free(Emod); free(x); free(u); free(TD); free(TDN); free(objective); free(count); free(y);
+    orc_system_free(K); orc_system_free(T);
+    return t;
+}

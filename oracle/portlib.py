@@ -260,3 +260,22 @@ def simp_run(eq, coords, conn, fixed, loads, filter_kind, nbrs, opt_kind, optp, 
                             _p(s, np.float64), _p(rho, np.float64), _p(u, np.float64), _p(r, np.float64),
                             _p(hist, np.float64), _p(phase, np.float64))
     return dict(s=s, rho=rho, u=u, r=r, hist=hist[:it], phase=phase, iters=it)
+
+
+def levelset_run(coords, conn, fixed, loads, phifixed_nodes, prm, tmax, phi0, str0):
+    """The level-set loop of sample/optimize/sample_optimize_levelset.cpp (orc_levelset_run); same contract as reflib.levelset_run."""
+    coords, conn = _f64(coords), _i32(conn)
+    fn, fd, fv = _i32(fixed[0]), _i32(fixed[1]), _f64(fixed[2])
+    ln, ld, lv = _i32(loads[0]), _i32(loads[1]), _f64(loads[2])
+    pn = _i32(phifixed_nodes)
+    prm = _f64(prm)
+    nnode, nelem = coords.shape[0], conn.shape[0]
+    phi, st = _f64(phi0).copy(), _f64(str0).copy()
+    u, hist = np.zeros((nnode, 2)), np.zeros((tmax, 3))
+    conv = C.c_int(0)
+    it = lib().orc_levelset_run(nnode, _p(coords, np.float64), nelem, _p(conn, np.int32),
+                                len(fn), _p(fn, np.int32), _p(fd, np.int32), _p(fv, np.float64),
+                                len(ln), _p(ln, np.int32), _p(ld, np.int32), _p(lv, np.float64),
+                                len(pn), _p(pn, np.int32), _p(prm, np.float64), int(tmax),
+                                _p(phi, np.float64), _p(st, np.float64), _p(u, np.float64), _p(hist, np.float64), C.byref(conv))
+    return dict(hist=hist[:it], phi=phi, str=st, u=u, iters=it, converged=bool(conv.value))

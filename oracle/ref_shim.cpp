@@ -38,6 +38,7 @@
 #include "FEM/Equation/PlaneStress.h"
 #include "FEM/Equation/Solid.h"
 #include "FEM/Equation/HeatTransfer.h"
+#include "FEM/Equation/ReactionDiffusion.h"
 #include "FEM/Equation/General.h"
 #include "FEM/Controller/ShapeFunction.h"
 #include "FEM/Controller/GaussIntegration.h"
@@ -407,6 +408,119 @@ void ref_sensitivity_filter(int kind, int n, const long long* rowptr, const int*
     if (kind == 2) r = SensitivityFilter<double>(n, neighbors, ww).GetFilteredSensitivitis(std::vector<double>(s, s + n), std::vector<double>(dfds, dfds + n));
     else r = SensitivityFilter2<double>(n, neighbors, ww).GetFilteredSensitivitis(std::vector<double>(s, s + n), std::vector<double>(dfds, dfds + n));
     std::copy(r.begin(), r.end(), out);
+}
+
+// ---- the level-set design loop of sample/optimize/sample_optimize_levelset.cpp:75-192, element routines and helpers
+//      called exactly as there (PlaneStressStiffness, ReactionDiffusion{ConsistentMass,Stiffness,Reaction},
+//      InterpolateNodalFromElemental / InterpolateElementalFromNodal, ScalingCG) ----
+// prm = { Vmax, tau, E0, Emin, nu, nvol, dt, d, p };  phi_io (nnode), str_io (nelem) in/out;  u_out (nnode*2);
+// hist[3*t] = { objective[t] (the sample prints objective/nelem), vol, lambda };  *converged = 1 when the sample's test fired.
+// Returns the number of iterations whose history was recorded.
+int ref_levelset_run(int nnode, const double* coords, int nelem, const int* conn,
+                     int nfixed, const int* fnode, const int* fdof, const double* fval,
+                     int nload, const int* lnode, const int* ldof, const double* lval,
+                     int nphi, const int* pnode, const double* prm, int tmax,
+                     double* phi_io, double* str_io, double* u_out, double* hist, int* converged) {
+    Quiet q;
+    const double Vmax = prm[0], tau = prm[1], E0 = prm[2], Emin = prm[3], nu = prm[4], nvol = prm[5], dt = prm[6], d = prm[7], p = prm[8];
+    std::vector<Vector<double> > x = make_nodes(2, nnode, coords);
+    std::vector<std::vector<int> > elements = make_elements(4, nelem, conn);
+    BCList ufixed = make_bc(nfixed, fnode, fdof, fval), qfixed = make_bc(nload, lnode, ldof, lval);
+    BCList phifixed(nphi);
+    for (int i = 0; i < nphi; i++) phifixed[i] = { { pnode[i], 0 }, 0.0 };
+
+    double A1 = -1.5*(1.0 - nu)*(1.0 - 14.0*nu + 15.0*pow(nu, 2.0))*E0/((1.0 + nu)*(7.0 - 5.0*nu)*pow(1.0 - 2.0*nu, 2.0));
+    double A2 = 7.5*(1.0 - nu)*E0/((1.0 + nu)*(7.0 - 5.0*nu));
+    double c = A1/(A1 + 2.0*A2);
+
+    std::vector<Vector<double> > phi(nnode, Vector<double>(1));
+    for (int i = 0; i < nnode; i++) phi[i](0) = phi_io[i];
+    std::vector<double> str(str_io, str_io + nelem);
+    double volInit = std::accumulate(str.begin(), str.end(), 0.0)/(double)elements.size();
+    std::vector<double> objective(tmax);
+    *converged = 0;
+    int t = 0;
+    for (; t < tmax; t++) {
+        std::vector<Vector<double> > u(x.size(), Vector<double>(2));
+        std::vector<std::vector<int> > nodetoglobal(x.size(), std::vector<int>(2, 0));
+        SetDirichlet(u, nodetoglobal, ufixed);
+        int KDEGREE = Renumbering(nodetoglobal);
+        LILCSR<double> K(KDEGREE, KDEGREE);
+        std::vector<double> F(KDEGREE, 0.0);
+        for (size_t i = 0; i < elements.size(); i++) {
+            N2E nodetoelement;
+            Matrix<double> Ke;
+            PlaneStressStiffness<double, ShapeFunction4Square, Gauss4Square>(Ke, nodetoelement, elements[i], { 0, 1 }, x, Emin + str[i]*(E0 - Emin), nu, 1.0);
+            Assembling(K, F, u, Ke, nodetoglobal, nodetoelement, elements[i]);
+        }
+        Assembling(F, qfixed, nodetoglobal);
+        CSR<double> Kmod(K);
+        std::vector<double> result = ScalingCG(Kmod, F, 100000, 1.0e-10);
+        Disassembling(u, result, nodetoglobal);
+        for (int i = 0; i < nnode; i++) { u_out[2*i] = u[i](0); u_out[2*i + 1] = u[i](1); }
+
+        std::vector<Vector<double> > TD(elements.size(), Vector<double>(1));
+        for (size_t i = 0; i < elements.size(); i++) {
+            N2E nodetoelement;
+            Matrix<double> Ke;
+            PlaneStressStiffness<double, ShapeFunction4Square, Gauss4Square>(Ke, nodetoelement, elements[i], { 0, 1 }, x, Emin + str[i]*(E0 - Emin), nu, 1.0);
+            Vector<double> ue = ElementVector(u, nodetoelement, elements[i]);
+            objective[t] += ue*(Ke*ue);
+            PlaneStressStiffness<double, ShapeFunction4Square, Gauss4Square>(Ke, nodetoelement, elements[i], { 0, 1 }, x, (A1 + 2.0*A2)*(1.0 - pow(c, 2.0)), c, 1.0);
+            TD[i](0) = (1.0e-4 + str[i]*(1.0 - 1.0e-4))*ue*(Ke*ue);
+        }
+        std::vector<Vector<double> > TDN = InterpolateNodalFromElemental<double, Vector>(x.size(), Vector<double>(1), TD, elements);
+
+        double vol = std::accumulate(str.begin(), str.end(), 0.0)/(double)elements.size();
+        double ex = Vmax + (volInit - Vmax)*std::max(0.0, 1.0 - (t + 1)/(double)nvol);
+        double lambda = std::accumulate(TDN.begin(), TDN.end(), Vector<double>(1))(0)/(double)x.size()*exp(p*((vol - ex)/ex + d));
+        hist[3*t] = objective[t]; hist[3*t + 1] = vol; hist[3*t + 2] = lambda;
+
+        if (t > nvol && fabs(vol - Vmax) < 0.005 &&
+            fabs(objective[t] - objective[t - 5]) < 0.01*fabs(objective[t]) &&
+            fabs(objective[t] - objective[t - 4]) < 0.01*fabs(objective[t]) &&
+            fabs(objective[t] - objective[t - 3]) < 0.01*fabs(objective[t]) &&
+            fabs(objective[t] - objective[t - 2]) < 0.01*fabs(objective[t]) &&
+            fabs(objective[t] - objective[t - 1]) < 0.01*fabs(objective[t])) {
+            *converged = 1;
+            t++;
+            break;
+        }
+
+        double C = 0.0;
+        for (size_t i = 0; i < x.size(); i++) C += fabs(TDN[i](0));
+        C = elements.size()/C;
+
+        std::vector<std::vector<int> > nodetoglobal2(x.size(), std::vector<int>(1, 0));
+        SetDirichlet(phi, nodetoglobal2, phifixed);
+        int TDEGREE = Renumbering(nodetoglobal2);
+        LILCSR<double> T(TDEGREE, TDEGREE);
+        std::vector<double> Y(TDEGREE, 0.0);
+        for (size_t i = 0; i < elements.size(); i++) {
+            N2E nodetoelement;
+            Matrix<double> Me, Ke;
+            Vector<double> Fe;
+            ReactionDiffusionConsistentMass<double, ShapeFunction4Square, Gauss4Square>(Me, nodetoelement, elements[i], { 0 }, x);
+            ReactionDiffusionStiffness<double, ShapeFunction4Square, Gauss4Square>(Ke, nodetoelement, elements[i], { 0 }, x, tau*elements.size());
+            ReactionDiffusionReaction<double, ShapeFunction4Square, Gauss4Square>(Fe, nodetoelement, elements[i], { 0 }, x, TDN, [&](double _u, Vector<double> _dudX) {
+                return C*(_u - lambda);
+            });
+            Vector<double> phie = ElementVector(phi, nodetoelement, elements[i]);
+            Matrix<double> Te = Me/dt + Ke;
+            Vector<double> Ye = Me/dt*phie + Fe;
+            Assembling(T, Y, phi, Te, nodetoglobal2, nodetoelement, elements[i]);
+            Assembling(Y, Ye, nodetoglobal2, nodetoelement, elements[i]);
+        }
+        CSR<double> Tmod(T);
+        std::vector<double> result2 = ScalingCG(Tmod, Y, 100000, 1.0e-10);
+        Disassembling(phi, result2, nodetoglobal2);
+        for (size_t i = 0; i < x.size(); i++) phi[i](0) = std::max(std::min(1.0, phi[i](0)), -1.0);
+        std::vector<Vector<double> > phie = InterpolateElementalFromNodal<double, Vector>(Vector<double>(1), phi, elements);
+        for (size_t i = 0; i < elements.size(); i++) str[i] = (phie[i](0) < 0.0) ? 0.0 : 1.0;
+    }
+    for (int i = 0; i < nnode; i++) phi_io[i] = phi[i](0);
+    std::copy(str.begin(), str.end(), str_io);
+    return t;
 }
 
 // ---- the SIMP design loop of sample/optimize/sample_optimize_density_{oc,mma}.cpp:83-208 on a caller-supplied

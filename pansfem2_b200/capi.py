@@ -455,6 +455,43 @@ class Simp:
             o.close()
 
 
+class LevelSet:
+    """The device-resident level-set loop for a pansfem2_b200.problems.LevelSetProblem (sample_optimize_levelset.cpp)."""
+
+    def __init__(self, ctx, P):
+        self.ctx, self.P = ctx, P
+        self.mesh = Mesh(ctx, P.coords, P.conn)
+        self.dofmap = DofMap(ctx, P.nnode, 2, P.fixed)
+        self.K = Csr.pattern(ctx, self.mesh, self.dofmap)
+        pn = _i32(P.phifixed)
+        ln, ld, lv = _i32(P.loads[0]), _i32(P.loads[1]), _f64(P.loads[2])
+        prm = _f64(P.prm())
+        self.h = C.c_void_p()
+        _ck(lib().pf2_levelset_create(ctx.h, self.mesh.h, self.dofmap.h, self.K.h, len(pn), _p(pn, np.int32), _p(prm, np.float64), int(P.tmax),
+                                      len(ln), _p(ln, np.int32), _p(ld, np.int32), _p(lv, np.float64), C.byref(self.h)))
+
+    def set_state(self, phi, st):
+        phi, st = _f64(phi), _f64(st)
+        _ck(lib().pf2_levelset_set_state(self.h, _p(phi, np.float64), _p(st, np.float64)))
+
+    def iterate(self, check_convergence=True):
+        st = (C.c_double * 8)()
+        _ck(lib().pf2_levelset_iterate(self.h, int(check_convergence), st))
+        return dict(objective=st[0], vol=st[1], lam=st[2], converged=bool(st[3]), cg_iters=int(st[4]), cg_relres=st[5], cg_iters_phi=int(st[6]), t=int(st[7]))
+
+    def get(self):
+        phi, st, u = np.zeros(self.P.nnode), np.zeros(self.P.nelem), np.zeros((self.P.nnode, 2))
+        _ck(lib().pf2_levelset_get(self.h, _p(phi, np.float64), _p(st, np.float64), _p(u, np.float64)))
+        return dict(phi=phi, str=st, u=u)
+
+    def close(self):
+        if self.h:
+            lib().pf2_levelset_destroy(self.h)
+            self.h = None
+        for o in (self.K, self.dofmap, self.mesh):
+            o.close()
+
+
 class Dist:
     """Row-block partition over the GPUs of one box.  `group` is an initialised torch.distributed process group (any
     backend): it is only used to hand rank 0's NCCL id to the other ranks."""

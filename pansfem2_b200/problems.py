@@ -142,3 +142,44 @@ def family_problem(eq, n, opt_kind=OPT_OC, filter_kind=FILTER_DENSITY, radius=1.
     nbrs = mesher.filter_neighbors_centroid(mesher.element_centroids(coords, conn), radius)
     return Problem(f"{eqcode.describe(eq)}_{'x'.join(str(v) for v in n)}", eq, coords, conn, fixed, loads, nbrs, tuple(n),
                    filter_kind=filter_kind, opt_kind=opt_kind, beta_period=0, **kw)
+
+
+@dataclass
+class LevelSetProblem:
+    """sample/optimize/sample_optimize_levelset.cpp:24-72: Q4 plane-stress cantilever, reaction-diffusion level-set update."""
+    coords: np.ndarray
+    conn: np.ndarray
+    fixed: tuple                # (node, dof, value) of the displacement field
+    loads: tuple
+    phifixed: np.ndarray        # nodes where phi is held at 0 (the outer boundary)
+    grid: tuple
+    Vmax: float = 0.5
+    tau: float = 2.0e-4
+    E0: float = 1.0
+    Emin: float = 1.0e-4
+    nu: float = 0.3
+    nvol: float = 100.0
+    dt: float = 0.1
+    d: float = -0.02
+    p: float = 4.0
+    tmax: int = 200
+
+    def prm(self):
+        return np.array([self.Vmax, self.tau, self.E0, self.Emin, self.nu, self.nvol, self.dt, self.d, self.p])
+
+    @property
+    def nnode(self):
+        return self.coords.shape[0]
+
+    @property
+    def nelem(self):
+        return self.conn.shape[0]
+
+
+def levelset2d(nx=60, ny=40, **kw) -> LevelSetProblem:
+    lx, ly = float(nx), float(ny)
+    coords, conn = mesher.square_mesh(lx, ly, nx, ny)
+    fixed = mesher.fixed_list(coords, [0, 1], lambda x: np.abs(x[:, 0]) < 1.0e-5)
+    loads = mesher.fixed_list(coords, [1], lambda x: (np.abs(x[:, 0] - lx) < 1.0e-5) & (np.abs(x[:, 1] - ly / 2) < 1.0 + 1.0e-5), -1.0)
+    edge = (np.abs(coords[:, 0]) < 1.0e-5) | (np.abs(coords[:, 0] - lx) < 1.0e-5) | (np.abs(coords[:, 1]) < 1.0e-5) | (np.abs(coords[:, 1] - ly) < 1.0e-5)
+    return LevelSetProblem(coords, conn, fixed, loads, np.nonzero(edge)[0].astype(np.int32), (nx, ny), **kw)

@@ -268,7 +268,45 @@ def golden_families():
     print("t3 goldens", pts.shape, cells.shape, T.min(), T.max(), f2["u"])
 
 
+def golden_levelset():
+    """Level-set loop: the UNMODIFIED sample/optimize/sample_optimize_levelset.cpp is compiled and run
+    (stdout history at 6 digits + its last result*.vtk), and the same loop is run through the reference's routines by
+    oracle/ref_shim.cpp ref_levelset_run for a full-precision history."""
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(f"{tmp}/sample/optimize")
+        exe = os.path.join(tmp, "levelset")
+        subprocess.run(["g++", "-O3", "-fopenmp", "-std=c++17", f"-I{REF}", f"{REF}/sample/optimize/sample_optimize_levelset.cpp", "-o", exe], check=True)
+        txt = subprocess.run([exe], check=True, capture_output=True, text=True, cwd=tmp).stdout
+        rows = [[float(v) for v in re.findall(r"= ([-+0-9.e]+)", ln)] for ln in txt.split("\n") if ln.startswith("t =")]
+        out["stdout_hist"] = np.array(rows)                      # t, compliance (= objective/nelem), volume, lambda
+        out["stdout_converged"] = np.int64("Convergence" in txt)
+        files = sorted([f for f in os.listdir(f"{tmp}/sample/optimize") if f.startswith("result")], key=lambda f: int(f[6:-4]))
+        f = parse_vtk_fields(f"{tmp}/sample/optimize/{files[-1]}")
+        out["vtk_count"] = np.int64(len(files))
+        out["vtk_u"], out["vtk_phi"], out["vtk_str"] = f["u"][:, :2], f["phi"], f["str"]
+    reflib.set_num_threads(8)
+    P = problems.levelset2d()
+    R = reflib.levelset_run(P.coords, P.conn, P.fixed, P.loads, P.phifixed, P.prm(), P.tmax, np.ones(P.nnode), np.ones(P.nelem))
+    out["hist"], out["phi"], out["str"], out["u"] = R["hist"], R["phi"], R["str"], R["u"]
+    out["iters"], out["converged"] = np.int64(R["iters"]), np.int64(R["converged"])
+    R40 = reflib.levelset_run(P.coords, P.conn, P.fixed, P.loads, P.phifixed, P.prm(), 40, np.ones(P.nnode), np.ones(P.nelem))
+    out["phi40"], out["str40"] = R40["phi"], R40["str"]
+    # a second, smaller case started from a perturbed state (holes), 25 iterations
+    P2 = problems.levelset2d(24, 16, nvol=10.0)
+    rng = np.random.default_rng(3)
+    phi0 = np.clip(rng.uniform(-0.3, 1.0, P2.nnode), -1, 1)
+    str0 = (phi0[P2.conn].mean(axis=1) >= 0).astype(float)
+    R2 = reflib.levelset_run(P2.coords, P2.conn, P2.fixed, P2.loads, P2.phifixed, P2.prm(), 25, phi0, str0)
+    out.update(small_phi0=phi0, small_str0=str0, small_hist=R2["hist"], small_phi=R2["phi"], small_str=R2["str"], small_iters=np.int64(R2["iters"]))
+    np.savez_compressed(f"{OUT}/levelset.npz", **out)
+    print("levelset", out["stdout_hist"].shape, int(out["vtk_count"]), int(out["iters"]), bool(out["converged"]), R2["hist"][-1])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "levelset":
+        golden_levelset()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "families":
         golden_families()
         sys.exit(0)
@@ -283,3 +321,4 @@ if __name__ == "__main__":
     golden_live()
     golden_conlin()
     golden_families()
+    golden_levelset()
