@@ -48,7 +48,7 @@ void orc_set_num_threads(int n) {
 
 /* eq codes of include/pansfem2_b200.h (PF2_EQ_CODE): phys | shape << 8 | quad << 16 | quad2 << 24; a zero field is the
  * default of the physics, so the legacy values 0, 1, 2 are codes too. */
-enum { PHYS_PLANESTRAIN = 0, PHYS_SOLID = 1, PHYS_HEAT = 2, PHYS_PLANESTRESS = 3, PHYS_PLANESTRAIN_SRI = 4 };
+enum { PHYS_PLANESTRAIN = 0, PHYS_SOLID = 1, PHYS_HEAT = 2, PHYS_PLANESTRESS = 3, PHYS_PLANESTRAIN_SRI = 4, PHYS_MASS = 5 };
 enum { SHAPE_T3 = 1, SHAPE_T6, SHAPE_Q4, SHAPE_Q8, SHAPE_TET4, SHAPE_HEX8, SHAPE_HEX20 };
 enum { QUAD_G1TRI = 1, QUAD_G3TRI, QUAD_G1SQ, QUAD_G4SQ, QUAD_G9SQ, QUAD_G1TET, QUAD_G8CUBE, QUAD_G27CUBE };
 typedef struct { int phys, shape, quad, quad2; } orc_sel;
@@ -61,7 +61,7 @@ static orc_sel decode_eq(int eq) {
     if (s.phys == PHYS_PLANESTRAIN_SRI && !s.quad2) s.quad2 = tri ? QUAD_G1TRI : QUAD_G1SQ;
     return s;
 }
-static int ndof_of(int eq) { int phys = eq & 0xff; return phys == PHYS_SOLID ? 3 : (phys == PHYS_HEAT ? 1 : 2); }
+static int ndof_of(int eq) { int phys = eq & 0xff; return phys == PHYS_SOLID ? 3 : ((phys == PHYS_HEAT || phys == PHYS_MASS) ? 1 : 2); }
 static int dim_of(int eq) { return (eq & 0xff) == PHYS_SOLID ? 3 : 2; }
 static int npe_of(int eq) {
     static const int n[8] = { 0, 3, 6, 4, 8, 4, 8, 20 };
@@ -154,6 +154,28 @@ static void shape_dndr(int shape, const double* r, double* d) {
     }
 }
 
+/* N(r) of the 2-D shapes: ShapeFunction.h:102-108 (3Triangle), :137-146 (6Triangle), :175-182 (4Square), :211-222 (8Square) */
+static void shape_n2d(int shape, const double* r, double* N) {
+    const double r0 = r[0], r1 = r[1];
+    switch (shape) {
+    case SHAPE_T3: N[0] = r0; N[1] = r1; N[2] = 1.0 - r0 - r1; break;
+    case SHAPE_T6:
+        N[0] = r0 * (2.0 * r0 - 1.0); N[1] = r1 * (2.0 * r1 - 1.0); N[2] = (1.0 - r0 - r1) * (1.0 - 2.0 * r0 - 2.0 * r1);
+        N[3] = 4.0 * r0 * r1; N[4] = 4.0 * r1 * (1.0 - r0 - r1); N[5] = 4.0 * (1.0 - r0 - r1) * r0;
+        break;
+    case SHAPE_Q4:
+        N[0] = 0.25 * (1.0 - r0) * (1.0 - r1); N[1] = 0.25 * (1.0 + r0) * (1.0 - r1);
+        N[2] = 0.25 * (1.0 + r0) * (1.0 + r1); N[3] = 0.25 * (1.0 - r0) * (1.0 + r1);
+        break;
+    default:    /* SHAPE_Q8 */
+        N[0] = 0.25 * (1.0 - r0) * (1.0 - r1) * (-r0 - r1 - 1.0); N[1] = 0.25 * (1.0 + r0) * (1.0 - r1) * (r0 - r1 - 1.0);
+        N[2] = 0.25 * (1.0 + r0) * (1.0 + r1) * (r0 + r1 - 1.0);  N[3] = 0.25 * (1.0 - r0) * (1.0 + r1) * (-r0 + r1 - 1.0);
+        N[4] = 0.5 * (1.0 - r0) * (1.0 + r0) * (1.0 - r1); N[5] = 0.5 * (1.0 + r0) * (1.0 + r1) * (1.0 - r1);
+        N[6] = 0.5 * (1.0 + r0) * (1.0 - r0) * (1.0 + r1); N[7] = 0.5 * (1.0 - r0) * (1.0 + r1) * (1.0 - r1);
+        break;
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------------------
  * Integration rules: point g and per-axis weights -- src/FEM/Controller/GaussIntegration.h
  *   Gauss1Triangle :72-82  Gauss3Triangle :94-107  Gauss1Square :120-130  Gauss4Square :142-157 (order (-,-),(+,-),(-,+),(+,+))
@@ -241,6 +263,12 @@ static void accumulate_rule(int phys, int shape, int quad, int dim, int npe, int
         shape_dndr(shape, r, dNdr);
         matmul(dim, npe, dim, dNdr, xe, dXdr);
         double J = det_d(dim, dXdr);
+        if (phys == PHYS_MASS) {            /* ReactionDiffusionConsistentMass  ReactionDiffusion.h:40-47: N N^T J w0 w1 */
+            double N[ORC_MAX_NPE];
+            shape_n2d(shape, r, N);
+            for (int i = 0; i < npe; i++) for (int j = 0; j < npe; j++) Ke[i * npe + j] += N[i] * N[j] * J * w[0] * w[1];
+            continue;
+        }
         inv_d(dim, dXdr, inv);
         matmul(dim, dim, npe, inv, dNdr, dNdX);
         double B[6 * ORC_MAX_M], Bt[ORC_MAX_M * 6], BtD[ORC_MAX_M * 6], BtDB[ORC_MAX_M * ORC_MAX_M];
@@ -306,6 +334,7 @@ void orc_element_matrix(int eq, const double* xe, double E, double V, double t, 
         for (int i = 0; i < 9; i++) D[i] *= f;
     }
     accumulate_rule(s.phys, s.shape, s.quad, dim, npe, ndof, xe, D, ns, E, t, Ke);     /* heat: E carries alpha */
+    if (s.phys == PHYS_MASS) for (int i = 0; i < m * m; i++) Ke[i] *= E * t;            /* the reference's mass has no coefficient */
 }
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -20,7 +20,7 @@ OPT_OC, OPT_MMA, OPT_CONLIN = 0, 1, 2
 def ndof_of(eq):
     """dofs per node of an eq code (include/pansfem2_b200.h PF2_EQ_CODE): the physics is the low byte."""
     phys = eq & 0xff
-    return 3 if phys == 1 else (1 if phys == 2 else 2)
+    return 3 if phys == 1 else (1 if phys in (2, 5) else 2)
 
 _lib = None
 

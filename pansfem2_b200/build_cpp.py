@@ -19,12 +19,14 @@ FLAGS = ["-O2", "-std=c++17", "-fopenmp"]
 LINK = ["-L" + HERE, "-lpansfem2_b200", "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/.."]
 
 OWN = [("sample/optimize/sample_optimize_density_batched.cpp", "sample_optimize_density_batched"),
-       ("sample/optimize/sample_optimize_density_families.cpp", "sample_optimize_density_families")]
+       ("sample/optimize/sample_optimize_density_families.cpp", "sample_optimize_density_families"),
+       ("sample/optimize/sample_optimize_levelset_batched.cpp", "sample_optimize_levelset_batched")]
 DROPIN = [("sample/optimize/sample_optimize_density_oc.cpp", "dropin_density_oc"),
           ("sample/optimize/sample_optimize_density_mma.cpp", "dropin_density_mma"),
           ("sample/optimize/sample_optimize_density_CONLIN.cpp", "dropin_density_conlin"),
           ("sample/solid/sample_linear.cpp", "dropin_solid_linear"),
-          ("sample/planestrain/sample_planestrain.cpp", "dropin_planestrain_t3")]
+          ("sample/planestrain/sample_planestrain.cpp", "dropin_planestrain_t3"),
+          ("sample/optimize/sample_optimize_levelset.cpp", "dropin_levelset")]
 
 
 def _compile(src, exe):

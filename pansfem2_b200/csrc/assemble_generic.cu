@@ -41,7 +41,7 @@ static int quad_domain(int quad) {
 int decode_eq(int eq, double V, EqInfo* out) {
     EqInfo q;
     q.phys = eq & 0xff; q.shape = (eq >> 8) & 0xff; q.quad = (eq >> 16) & 0xff; q.quad2 = (eq >> 24) & 0xff;
-    PF2_CHECK(eq >= 0 && q.phys <= PF2_PHYS_PLANESTRAIN_SRI, "unknown equation");
+    PF2_CHECK(eq >= 0 && q.phys <= PF2_PHYS_MASS, "unknown equation");
     PF2_CHECK(q.shape <= PF2_SHAPE_HEX20 && q.quad <= PF2_QUAD_G27CUBE && q.quad2 <= PF2_QUAD_G27CUBE, "unknown shape function / integration rule");
     const bool solid = q.phys == PF2_PHYS_SOLID;
     if (q.shape == 0) q.shape = solid ? PF2_SHAPE_HEX8 : PF2_SHAPE_Q4;
@@ -59,8 +59,8 @@ int decode_eq(int eq, double V, EqInfo* out) {
     }
     q.dim = solid ? 3 : 2;
     q.npe = shape_npe(q.shape);
-    q.ndof = solid ? 3 : (q.phys == PF2_PHYS_HEAT ? 1 : 2);
-    q.kind = solid ? KIND_SOLID3D : (q.phys == PF2_PHYS_HEAT ? KIND_HEAT2D : KIND_ELAST2D);
+    q.ndof = solid ? 3 : ((q.phys == PF2_PHYS_HEAT || q.phys == PF2_PHYS_MASS) ? 1 : 2);
+    q.kind = solid ? KIND_SOLID3D : (q.phys == PF2_PHYS_HEAT ? KIND_HEAT2D : (q.phys == PF2_PHYS_MASS ? KIND_MASS2D : KIND_ELAST2D));
     q.fast = (q.phys == PF2_PHYS_PLANESTRAIN && q.shape == PF2_SHAPE_Q4 && q.quad == PF2_QUAD_G4SQ) ||
              (q.phys == PF2_PHYS_HEAT && q.shape == PF2_SHAPE_Q4 && q.quad == PF2_QUAD_G4SQ) ||
              (solid && q.shape == PF2_SHAPE_HEX8 && q.quad == PF2_QUAD_G8CUBE);
@@ -205,6 +205,11 @@ __global__ void element_generic_kernel(ElemSpec sp, const double* __restrict__ x
             else if ((q).shape == PF2_SHAPE_T6) { CALL(KIND_HEAT2D, SH_T6); }                        \
             else if ((q).shape == PF2_SHAPE_Q4) { CALL(KIND_HEAT2D, SH_Q4); }                        \
             else { CALL(KIND_HEAT2D, SH_Q8); }                                                       \
+        } else if ((q).kind == KIND_MASS2D) {                                                        \
+            if ((q).shape == PF2_SHAPE_T3) { CALL(KIND_MASS2D, SH_T3); }                             \
+            else if ((q).shape == PF2_SHAPE_T6) { CALL(KIND_MASS2D, SH_T6); }                        \
+            else if ((q).shape == PF2_SHAPE_Q4) { CALL(KIND_MASS2D, SH_Q4); }                        \
+            else { CALL(KIND_MASS2D, SH_Q8); }                                                       \
         } else {                                                                                     \
             if ((q).shape == PF2_SHAPE_T3) { CALL(KIND_ELAST2D, SH_T3); }                            \
             else if ((q).shape == PF2_SHAPE_T6) { CALL(KIND_ELAST2D, SH_T6); }                       \

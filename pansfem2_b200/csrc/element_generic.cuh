@@ -20,7 +20,7 @@ namespace pf2 {
 
 enum { SH_T3 = PF2_SHAPE_T3, SH_T6 = PF2_SHAPE_T6, SH_Q4 = PF2_SHAPE_Q4, SH_Q8 = PF2_SHAPE_Q8, SH_TET4 = PF2_SHAPE_TET4,
        SH_HEX8 = PF2_SHAPE_HEX8, SH_HEX20 = PF2_SHAPE_HEX20 };
-enum { KIND_ELAST2D = 0, KIND_HEAT2D = 1, KIND_SOLID3D = 2 };
+enum { KIND_ELAST2D = 0, KIND_HEAT2D = 1, KIND_SOLID3D = 2, KIND_MASS2D = 3 };
 
 // what one launch needs to know about the element routine (filled on the host by decode_eq, passed by value)
 struct ElemSpec {
@@ -42,6 +42,7 @@ template <int KIND> struct KindTraits;
 template <> struct KindTraits<KIND_ELAST2D> { static constexpr int DIM = 2, NDOF = 2; };
 template <> struct KindTraits<KIND_HEAT2D> { static constexpr int DIM = 2, NDOF = 1; };
 template <> struct KindTraits<KIND_SOLID3D> { static constexpr int DIM = 3, NDOF = 3; };
+template <> struct KindTraits<KIND_MASS2D> { static constexpr int DIM = 2, NDOF = 1; };     // scalar consistent mass N N^T
 
 // ---- quadrature ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int quad_count(int quad) {
@@ -162,6 +163,33 @@ __device__ __forceinline__ void shape_dndr(const double (&r)[3], double (&d)[Sha
     }
 }
 
+// N(r) of the 2-D shapes (ShapeFunction.h:102-108, 137-146, 175-182, 211-222): needed by the consistent mass matrices
+template <int SHAPE>
+__device__ __forceinline__ void shape_n(const double (&r)[3], double (&N)[ShapeTraits<SHAPE>::NPE]) {
+    const double r0 = r[0], r1 = r[1];
+    if constexpr (SHAPE == SH_T3) {
+        N[0] = r0; N[1] = r1; N[2] = 1.0 - r0 - r1;
+    } else if constexpr (SHAPE == SH_T6) {
+        const double c = 1.0 - r0 - r1;
+        N[0] = r0 * (2.0 * r0 - 1.0); N[1] = r1 * (2.0 * r1 - 1.0); N[2] = c * (1.0 - 2.0 * r0 - 2.0 * r1);
+        N[3] = 4.0 * r0 * r1; N[4] = 4.0 * r1 * c; N[5] = 4.0 * c * r0;
+    } else if constexpr (SHAPE == SH_Q4) {
+        N[0] = 0.25 * (1.0 - r0) * (1.0 - r1); N[1] = 0.25 * (1.0 + r0) * (1.0 - r1);
+        N[2] = 0.25 * (1.0 + r0) * (1.0 + r1); N[3] = 0.25 * (1.0 - r0) * (1.0 + r1);
+    } else if constexpr (SHAPE == SH_Q8) {
+#pragma unroll
+        for (int n = 0; n < 4; n++) {
+            const double sx = ((n + 1) & 2) ? 1.0 : -1.0, sy = (n & 2) ? 1.0 : -1.0;
+            N[n] = 0.25 * (1.0 + sx * r0) * (1.0 + sy * r1) * (sx * r0 + sy * r1 - 1.0);
+        }
+        N[4] = 0.5 * (1.0 - r0) * (1.0 + r0) * (1.0 - r1); N[5] = 0.5 * (1.0 + r0) * (1.0 + r1) * (1.0 - r1);
+        N[6] = 0.5 * (1.0 + r0) * (1.0 - r0) * (1.0 + r1); N[7] = 0.5 * (1.0 - r0) * (1.0 + r1) * (1.0 - r1);
+    } else {
+#pragma unroll
+        for (int n = 0; n < ShapeTraits<SHAPE>::NPE; n++) N[n] = 0.0;      // 3-D shapes: no mass kind instantiated
+    }
+}
+
 // dXdr = dNdr * X, J = det, dNdX = dXdr^-1 * dNdr   (g overwrites d in place)
 template <int SHAPE>
 __device__ __forceinline__ void shape_grad(const double (&X)[ShapeTraits<SHAPE>::NPE][ShapeTraits<SHAPE>::DIM], const double (&r)[3],
@@ -231,6 +259,16 @@ __device__ __forceinline__ void generic_rows(const double (&X)[ShapeTraits<SHAPE
 #pragma unroll
                 for (int n = 1; n < NPE; n++) if (n == a) ga[k] = g[k][n];
             }
+            if constexpr (KIND == KIND_MASS2D) {
+                double N[NPE];
+                shape_n<SHAPE>(r, N);
+                double Na = N[0];
+#pragma unroll
+                for (int n = 1; n < NPE; n++) if (n == a) Na = N[n];
+#pragma unroll
+                for (int b = 0; b < NPE; b++) acc[0][b] += Na * N[b] * w;
+                continue;
+            }
 #pragma unroll
             for (int b = 0; b < NPE; b++) {
                 if constexpr (KIND == KIND_HEAT2D) {
@@ -269,7 +307,18 @@ __device__ __forceinline__ double generic_energy(const double (&X)[ShapeTraits<S
             quad_point(sp.quad[pass], q, r, wq);
             shape_grad<SHAPE>(X, r, g, det);
             const double w = (KIND == KIND_SOLID3D) ? det * wq : det * t * wq;
-            if constexpr (KIND == KIND_HEAT2D) {
+            if constexpr (KIND == KIND_MASS2D) {
+                double N[NPE];
+                shape_n<SHAPE>(r, N);
+                double ug = 0.0;
+#pragma unroll
+                for (int n = 0; n < NPE; n++) ug += N[n] * ue[n][0];
+                wsum += ug * ug * w;
+                if constexpr (WANT_F) {
+#pragma unroll
+                    for (int n = 0; n < NPE; n++) fe[n][0] += N[n] * ug * w;
+                }
+            } else if constexpr (KIND == KIND_HEAT2D) {
                 double qx = 0.0, qy = 0.0;
 #pragma unroll
                 for (int n = 0; n < NPE; n++) { qx += g[0][n] * ue[n][0]; qy += g[1][n] * ue[n][0]; }

@@ -133,4 +133,42 @@ private:
         Model& model;
         pf2_simp* handle;
     };
+
+    //  the level-set design loop of sample/optimize/sample_optimize_levelset.cpp with every field resident on the device
+    struct LevelSetParameters {
+        double Vmax = 0.5, tau = 2.0e-4, E0 = 1.0, Emin = 1.0e-4, nu = 0.3, nvol = 100, dt = 0.1, d = -0.02, p = 4.0;
+        int tmax = 200;
+    };
+    struct LevelSetReport { double objective, volume, lambda; bool converged; int cg_iterations; double cg_relres; int cg_iterations_phi; int t; };
+
+    class LevelSetLoop {
+public:
+        //  _model: Q4 mesh with the 2-dof displacement numbering; _phifixed: nodes where phi is held at 0 (GenerateFixedlist({ 0 }, ...))
+        LevelSetLoop(Model& _model, const BcList& _qfixed, const BcList& _phifixed, const LevelSetParameters& _prm) : model(_model), handle(nullptr) {
+            std::vector<int> ln, ld, pn, pd; std::vector<double> lv, pv;
+            SplitBc(_qfixed, ln, ld, lv);
+            SplitBc(_phifixed, pn, pd, pv);
+            const double prm[9] = { _prm.Vmax, _prm.tau, _prm.E0, _prm.Emin, _prm.nu, _prm.nvol, _prm.dt, _prm.d, _prm.p };
+            Check(pf2_levelset_create(Device::Context(), model.mesh, model.dofmap, model.pattern, (int)pn.size(), pn.data(), prm, _prm.tmax,
+                                      (int)ln.size(), ln.data(), ld.data(), lv.data(), &handle), "pf2_levelset_create");
+        }
+        ~LevelSetLoop() { pf2_levelset_destroy(handle); }
+        LevelSetLoop(const LevelSetLoop&) = delete;
+
+        LevelSetReport Iterate(bool _checkconvergence = true) {
+            double st[8];
+            Check(pf2_levelset_iterate(handle, _checkconvergence ? 1 : 0, st), "pf2_levelset_iterate");
+            return LevelSetReport{ st[0], st[1], st[2], st[3] != 0.0, (int)st[4], st[5], (int)st[6], (int)st[7] };
+        }
+        void Get(std::vector<Vector<double> >& _phi, std::vector<double>& _str, std::vector<Vector<double> >& _u) {
+            std::vector<double> phi(model.nnode), u((size_t)model.nnode*2);
+            _str.resize(model.nelem);
+            Check(pf2_levelset_get(handle, phi.data(), _str.data(), u.data()), "pf2_levelset_get");
+            _phi.assign(model.nnode, Vector<double>(1)); _u.assign(model.nnode, Vector<double>(2));
+            for (int i = 0; i < model.nnode; i++) { _phi[i](0) = phi[i]; _u[i](0) = u[2*(size_t)i]; _u[i](1) = u[2*(size_t)i + 1]; }
+        }
+private:
+        Model& model;
+        pf2_levelset* handle;
+    };
 } }

@@ -39,6 +39,13 @@ namespace PANSFEM2 {
         _fout << "SCALARS " << _symbol << " float\nLOOKUP_TABLE default\n";
         for (const auto& v : _values) _fout << v << std::endl;
     }
+    //  one-component nodal fields held as Vector<T> (the level-set driver's phi): Vector's operator<< ends each component with a newline
+    template<class T>
+    void AddPointScalers(std::vector<Vector<T> > _values, std::string _symbol, std::ofstream& _fout, bool _isheader) {
+        B200::SectionHeader("POINT_DATA", _values.size(), _isheader, _fout);
+        _fout << "SCALARS " << _symbol << " float\nLOOKUP_TABLE default\n";
+        for (const auto& v : _values) _fout << v;
+    }
     template<class T>
     void AddPointVectors(std::vector<Vector<T> > _values, std::string _symbol, std::ofstream& _fout, bool _isheader) {
         B200::SectionHeader("POINT_DATA", _values.size(), _isheader, _fout);

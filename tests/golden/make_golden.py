@@ -205,7 +205,7 @@ def parse_vtk_mesh(path):
 def all_selections():
     from pansfem2_b200 import eqcode as ec
     out = []
-    for phys in (ec.PHYS_PLANESTRAIN, ec.PHYS_PLANESTRESS, ec.PHYS_HEAT, ec.PHYS_PLANESTRAIN_SRI, ec.PHYS_SOLID):
+    for phys in (ec.PHYS_PLANESTRAIN, ec.PHYS_PLANESTRESS, ec.PHYS_HEAT, ec.PHYS_PLANESTRAIN_SRI, ec.PHYS_SOLID, ec.PHYS_MASS):
         shapes = (ec.SHAPE_TET4, ec.SHAPE_HEX8, ec.SHAPE_HEX20) if phys == ec.PHYS_SOLID else (ec.SHAPE_T3, ec.SHAPE_T6, ec.SHAPE_Q4, ec.SHAPE_Q8)
         for shape in shapes:
             for quad in ec.SHAPE_RULES[shape]:

@@ -26,7 +26,7 @@ def t3(golden_dir):
 
 def test_every_selection_element_matrix(fam):
     sel = [int(v) for v in fam["selections"]]
-    assert len(sel) == 61
+    assert len(sel) == 71
     for eq in sel:
         ke = orc.element_matrix(eq, fam[f"xe_{eq}"], 2.5, 0.3, 0.7)
         ref = fam[f"ke_{eq}"]

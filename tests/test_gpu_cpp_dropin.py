@@ -162,3 +162,43 @@ def test_batched_driver_on_other_element_families(family, nx, ny):
                      np.full(P.nelem, 0.5), check_convergence=False)
     np.testing.assert_allclose(hist[:, 0], R["hist"][:, 0], rtol=1e-8)
     np.testing.assert_allclose(hist[:, 1], R["hist"][:, 1], rtol=0, atol=1e-9)
+
+
+def _levelset_stdout(txt):
+    import re
+    return np.array([[float(v) for v in re.findall(r"= ([-+0-9.e]+)", ln)] for ln in txt.split("\n") if ln.startswith("t =")])
+
+
+def test_batched_levelset_driver_reproduces_the_reference_run(tmp_path, golden_dir):
+    """sample_optimize_levelset_batched (B200::LevelSetLoop): the console history and the final fields of the reference's
+    sample_optimize_levelset.cpp run (tests/golden/levelset.npz: stdout of the unmodified sample + its last VTK)."""
+    exe = need("sample_optimize_levelset_batched")
+    out = tmp_path / "result.vtk"
+    r = subprocess.run([exe, "60", "40", str(out)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    g = np.load(os.path.join(golden_dir, "levelset.npz"))
+    hist = _levelset_stdout(r.stdout)
+    assert "Convergence" in r.stdout and hist.shape == g["stdout_hist"].shape == (115, 4)
+    np.testing.assert_allclose(hist, g["stdout_hist"], rtol=2e-5)             # both sides print 6 digits
+    got = parse_vtk(out)
+    assert np.array_equal(got["str"], g["vtk_str"])
+    np.testing.assert_allclose(got["phi"], g["vtk_phi"], rtol=2e-5, atol=1e-9)
+    np.testing.assert_allclose(got["u"][:, :2], g["vtk_u"], rtol=2e-5, atol=1e-9)
+
+
+def test_unmodified_reference_levelset_driver_on_the_header_mirror(tmp_path, golden_dir):
+    """sample/optimize/sample_optimize_levelset.cpp, unmodified, on the mirror's PlaneStress.h / ReactionDiffusion.h / General.h
+    (per-element device calls + host containers): same history, same convergence iteration, same final structure."""
+    exe = need("dropin_levelset")
+    (tmp_path / "sample" / "optimize").mkdir(parents=True)
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stderr[-2000:]
+    g = np.load(os.path.join(golden_dir, "levelset.npz"))
+    hist = _levelset_stdout(r.stdout)
+    assert "Convergence" in r.stdout and hist.shape == (115, 4)
+    np.testing.assert_allclose(hist, g["stdout_hist"], rtol=2e-5)
+    files = sorted((tmp_path / "sample" / "optimize").glob("result*.vtk"), key=lambda p: int(p.stem[6:]))
+    assert len(files) == int(g["vtk_count"]) == 116
+    got = parse_vtk(files[-1])
+    assert np.array_equal(got["str"], g["vtk_str"])
+    np.testing.assert_allclose(got["phi"], g["vtk_phi"], rtol=2e-5, atol=1e-9)

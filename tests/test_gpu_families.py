@@ -40,7 +40,7 @@ def rel(a, b):
 
 def test_every_selection_element_matrix(ctx, fam):
     sel = [int(v) for v in fam["selections"]]
-    assert len(sel) == 61
+    assert len(sel) == 71
     for eq in sel:
         ke = ctx.element_matrix(eq, fam[f"xe_{eq}"], 2.5, 0.3, 0.7)
         assert rel(ke, fam[f"ke_{eq}"]) < 1e-13, ec.describe(eq)
