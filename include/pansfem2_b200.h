@@ -53,8 +53,10 @@ enum { PF2_SHAPE_DEFAULT = 0, PF2_SHAPE_T3 = 1, PF2_SHAPE_T6 = 2, PF2_SHAPE_Q4 =
 enum { PF2_QUAD_DEFAULT = 0, PF2_QUAD_G1TRI = 1, PF2_QUAD_G3TRI = 2, PF2_QUAD_G1SQ = 3, PF2_QUAD_G4SQ = 4, PF2_QUAD_G9SQ = 5,
        PF2_QUAD_G1TET = 6, PF2_QUAD_G8CUBE = 7, PF2_QUAD_G27CUBE = 8 };
 #define PF2_EQ_CODE(phys, shape, quad, quad2) ((phys) | ((shape) << 8) | ((quad) << 16) | ((quad2) << 24))
-/* solver selection: CG (CG.h:124), ScalingCG (CG.h:420), ILU0CG (CG.h:320) */
-enum { PF2_SOLVER_CG = 0, PF2_SOLVER_SCALINGCG = 1, PF2_SOLVER_ILU0CG = 2 };
+/* solver selection: CG (CG.h:124), ScalingCG (CG.h:420), ILU0CG (CG.h:320); for non-symmetric systems BiCGSTAB (CG.h:159),
+ * BiCGSTAB2 (CG.h:199), ScalingBiCGSTAB (CG.h:458), ILU0BiCGSTAB (CG.h:357) */
+enum { PF2_SOLVER_CG = 0, PF2_SOLVER_SCALINGCG = 1, PF2_SOLVER_ILU0CG = 2, PF2_SOLVER_BICGSTAB = 3, PF2_SOLVER_BICGSTAB2 = 4,
+       PF2_SOLVER_SCALINGBICGSTAB = 5, PF2_SOLVER_ILU0BICGSTAB = 6 };
 /* DensityFilter (DensityFilter.h:45-71), HeavisideFilter (HeavisideFilter.h:61-99),
  * SensitivityFilter / SensitivityFilter2 (SensitivityFilter.h:44-55, 88-99; sensitivities only) */
 enum { PF2_FILTER_DENSITY = 0, PF2_FILTER_HEAVISIDE = 1, PF2_FILTER_SENS_SIGMUND = 2, PF2_FILTER_SENS_BORRVALL = 3 };

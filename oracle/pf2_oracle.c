@@ -602,6 +602,86 @@ int orc_solve(const orc_system* A, const orc_system* M, int kind, const double* 
 }
 
 /* ------------------------------------------------------------------------------------------------------------
+ * The non-symmetric Krylov family
+ * BiCGSTAB         src/LinearAlgebra/Solvers/CG.h:159-194      kind 3
+ * BiCGSTAB2        src/LinearAlgebra/Solvers/CG.h:199-253      kind 4
+ * ScalingBiCGSTAB  src/LinearAlgebra/Solvers/CG.h:458-495      kind 5   (note p0 = D^-1 r0, :465)
+ * ILU0BiCGSTAB     src/LinearAlgebra/Solvers/CG.h:357-393      kind 6   (M = ILU0 factors)
+ * Vector updates keep the operand order of xeaxpbypcz / zeaxpby / zeawpbxmypcz / zeawpbxpcy / zeavpbwpcxpdy (CG.h:56-120).
+ * Returns the number of iterations performed; *relres = final ||r||/||b|| of the recursive residual.
+ * ---------------------------------------------------------------------------------------------------------- */
+int orc_solve_bicgstab(const orc_system* A, const orc_system* M, int kind, const double* b, int itrmax, double eps, double* x, double* relres) {
+    const int n = A->n;
+    const size_t bytes = sizeof(double) * (size_t)n;
+    double *r = (double*)malloc(bytes), *rdash = (double*)malloc(bytes), *p = (double*)malloc(bytes), *Ap = (double*)malloc(bytes);
+    double *s = (double*)malloc(bytes), *As = (double*)malloc(bytes), *Mp = (double*)malloc(bytes), *Ms = (double*)malloc(bytes);
+    double *D = (double*)malloc(bytes), *u = (double*)calloc((size_t)n, sizeof(double)), *w = (double*)calloc((size_t)n, sizeof(double));
+    double *z = (double*)calloc((size_t)n, sizeof(double)), *tkm1 = (double*)calloc((size_t)n, sizeof(double)), *y = (double*)malloc(bytes);
+    for (int i = 0; i < n; i++) { x[i] = 0.0; D[i] = (kind == 5) ? diag_of(A, i) : 1.0; }
+    orc_spmv(A, x, Ap);
+    for (int i = 0; i < n; i++) { r[i] = b[i] - Ap[i]; rdash[i] = r[i]; }
+    if (kind == 4) memset(p, 0, bytes);
+    else if (kind == 5) for (int i = 0; i < n; i++) p[i] = r[i] / D[i];
+    else memcpy(p, r, bytes);
+    double beta = 0.0;
+    double rdashr = dot(n, rdash, r);
+    const double bnorm = sqrt(dot(n, b, b));
+    int it = itrmax;
+    double rnorm = sqrt(dot(n, r, r));
+    for (int k = 0; k < itrmax; ++k) {
+        if (kind != 4) {
+            const double* mp = p;
+            if (kind == 5) { for (int i = 0; i < n; i++) Mp[i] = p[i] / D[i]; mp = Mp; }
+            else if (kind == 6) { orc_preilu0(M, p, Mp); mp = Mp; }
+            orc_spmv(A, mp, Ap);
+            const double alpha = rdashr / dot(n, rdash, Ap);
+            for (int i = 0; i < n; i++) s[i] = 1.0 * r[i] + (-alpha) * Ap[i];
+            const double* ms = s;
+            if (kind == 5) { for (int i = 0; i < n; i++) Ms[i] = s[i] / D[i]; ms = Ms; }
+            else if (kind == 6) { orc_preilu0(M, s, Ms); ms = Ms; }
+            orc_spmv(A, ms, As);
+            const double omega = dot(n, As, s) / dot(n, As, As);
+            for (int i = 0; i < n; i++) x[i] = 1.0 * x[i] + alpha * mp[i] + omega * ms[i];
+            for (int i = 0; i < n; i++) r[i] = 1.0 * s[i] + (-omega) * As[i];
+            const double rdashr1 = dot(n, rdash, r);
+            beta = alpha / omega * rdashr1 / rdashr;
+            for (int i = 0; i < n; i++) p[i] = beta * p[i] + 1.0 * r[i] + (-beta * omega) * Ap[i];
+            rdashr = rdashr1;
+        } else {
+            double* t = s; double* At = As;
+            for (int i = 0; i < n; i++) p[i] = beta * p[i] + 1.0 * r[i] + (-beta) * u[i];
+            orc_spmv(A, p, Ap);
+            const double alpha = rdashr / dot(n, rdash, Ap);
+            for (int i = 0; i < n; i++) y[i] = 1.0 * tkm1[i] + (-1.0) * r[i] + (-alpha) * w[i] + alpha * Ap[i];
+            for (int i = 0; i < n; i++) t[i] = 1.0 * r[i] + (-alpha) * Ap[i];
+            orc_spmv(A, t, At);
+            const double Att = dot(n, At, t), AtAt = dot(n, At, At);
+            double zeta, ita;
+            if (k % 2 == 0) { zeta = Att / AtAt; ita = 0.0; }
+            else {
+                const double yy = dot(n, y, y), yt = dot(n, y, t), Aty = dot(n, At, y);
+                zeta = (yy * Att - yt * Aty) / (AtAt * yy - Aty * Aty);
+                ita = (AtAt * yt - Aty * Att) / (AtAt * yy - Aty * Aty);
+            }
+            for (int i = 0; i < n; i++) u[i] = zeta * Ap[i] + ita * (tkm1[i] - r[i] + beta * u[i]);
+            for (int i = 0; i < n; i++) z[i] = ita * z[i] + zeta * r[i] + (-alpha) * u[i];
+            for (int i = 0; i < n; i++) x[i] = 1.0 * x[i] + alpha * p[i] + 1.0 * z[i];
+            for (int i = 0; i < n; i++) r[i] = 1.0 * t[i] + (-ita) * y[i] + (-zeta) * At[i];
+            const double rdashr1 = dot(n, rdash, r);
+            beta = alpha * rdashr1 / (zeta * rdashr);
+            for (int i = 0; i < n; i++) w[i] = 1.0 * At[i] + beta * Ap[i];
+            rdashr = rdashr1;
+            memcpy(tkm1, t, bytes);
+        }
+        rnorm = sqrt(dot(n, r, r));
+        if (rnorm < eps * bnorm) { it = k + 1; break; }
+    }
+    if (relres) *relres = rnorm / bnorm;
+    free(r); free(rdash); free(p); free(Ap); free(s); free(As); free(Mp); free(Ms); free(D); free(u); free(w); free(z); free(tkm1); free(y);
+    return it;
+}
+
+/* ------------------------------------------------------------------------------------------------------------
  * Filters.
  * HeavisideFilter::GetFilteredVariables     src/Optimize/Filter/HeavisideFilter.h:61-73
  * HeavisideFilter::GetFilteredSensitivitis  src/Optimize/Filter/HeavisideFilter.h:77-99

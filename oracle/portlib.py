@@ -116,10 +116,16 @@ class System:
         return y
 
     def solve(self, kind, b, itrmax=100000, eps=1e-10, M=None):
-        """kind 0 CG, 1 ScalingCG, 2 ILU0CG.  Returns (x, iterations, relres)."""
+        """kind 0 CG, 1 ScalingCG, 2 ILU0CG, 3 BiCGSTAB, 4 BiCGSTAB2, 5 ScalingBiCGSTAB, 6 ILU0BiCGSTAB.  Returns (x, iterations, relres)."""
         b = _f64(b)
         x = np.zeros(self.rows)
         relres = C.c_double(0)
+        if kind >= 3:
+            if kind == 6 and M is None:
+                M = self.ilu0()
+            it = lib().orc_solve_bicgstab(self.h, M.h if M is not None else None, kind, _p(b, np.float64), int(itrmax), C.c_double(eps),
+                                          _p(x, np.float64), C.byref(relres))
+            return x, it, relres.value
         if kind == 2 and M is None:
             M = self.ilu0()
         it = lib().orc_solve(self.h, M.h if M is not None else None, kind, _p(b, np.float64), int(itrmax), C.c_double(eps),

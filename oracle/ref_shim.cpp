@@ -38,6 +38,7 @@
 #include "FEM/Equation/PlaneStress.h"
 #include "FEM/Equation/Solid.h"
 #include "FEM/Equation/HeatTransfer.h"
+#include "FEM/Equation/Advection.h"
 #include "FEM/Equation/ReactionDiffusion.h"
 #include "FEM/Equation/General.h"
 #include "FEM/Controller/ShapeFunction.h"
@@ -301,7 +302,15 @@ void ref_solve(void* h, int kind, const double* b, int itrmax, double eps, doubl
     double t0 = now(), tf = 0;
     if (kind == 0) xv = CG(*s->K, bv, itrmax, eps);
     else if (kind == 1) xv = ScalingCG(*s->K, bv, itrmax, eps);
-    else {
+    else if (kind == 3) xv = BiCGSTAB(*s->K, bv, itrmax, eps);               // CG.h:159
+    else if (kind == 4) xv = BiCGSTAB2(*s->K, bv, itrmax, eps);              // CG.h:199
+    else if (kind == 5) xv = ScalingBiCGSTAB(*s->K, bv, itrmax, eps);        // CG.h:458
+    else if (kind == 6) {                                                    // CG.h:357
+        CSR<double> M = ILU0(*s->K);
+        tf = now() - t0;
+        t0 = now();
+        xv = ILU0BiCGSTAB(*s->K, M, bv, itrmax, eps);
+    } else {
         CSR<double> M = ILU0(*s->K);
         tf = now() - t0;
         t0 = now();
@@ -409,6 +418,36 @@ void ref_sensitivity_filter(int kind, int n, const long long* rowptr, const int*
     if (kind == 2) r = SensitivityFilter<double>(n, neighbors, ww).GetFilteredSensitivitis(std::vector<double>(s, s + n), std::vector<double>(dfds, dfds + n));
     else r = SensitivityFilter2<double>(n, neighbors, ww).GetFilteredSensitivitis(std::vector<double>(s, s + n), std::vector<double>(dfds, dfds + n));
     std::copy(r.begin(), r.end(), out);
+}
+
+// ---- the non-symmetric system of sample/advection/sample_advectiondiffusion_static.cpp:37-58: T3 elements,
+//      Ke = Advection + Diffusion + AdvectionSUPG (Advection.h), assembled with the sample's calls.  Used as a fixture for
+//      the BiCGSTAB family (the sample solves it with BiCGSTAB and its output is the committed AdvectionSUPG.vtk). ----
+void* ref_advection_system(int nnode, const double* coords, int nelem, const int* conn, int nfixed, const int* fnode, const double* fval,
+                           double a, double theta_deg, double k) {
+    std::vector<Vector<double> > x = make_nodes(2, nnode, coords);
+    std::vector<std::vector<int> > elements = make_elements(3, nelem, conn);
+    BCList ufixed(nfixed);
+    for (int i = 0; i < nfixed; i++) ufixed[i] = { { fnode[i], 0 }, fval[i] };
+    RefSystem* sys = new RefSystem();
+    std::vector<Vector<double> > T(x.size(), Vector<double>(1));
+    sys->nodetoglobal = std::vector<std::vector<int> >(x.size(), std::vector<int>(1, 0));
+    SetDirichlet(T, sys->nodetoglobal, ufixed);
+    int KDEGREE = Renumbering(sys->nodetoglobal);
+    LILCSR<double> K(KDEGREE, KDEGREE);
+    sys->F.assign(KDEGREE, 0.0);
+    const double ax = a*cos(theta_deg*M_PI/180.0), ay = a*sin(theta_deg*M_PI/180.0);
+    for (auto element : elements) {
+        N2E nodetoelement;
+        Matrix<double> A, B, C;
+        Advection<double, ShapeFunction3Triangle, Gauss1Triangle>(A, nodetoelement, element, { 0 }, x, ax, ay);
+        Diffusion<double, ShapeFunction3Triangle, Gauss1Triangle>(B, nodetoelement, element, { 0 }, x, k);
+        AdvectionSUPG<double, ShapeFunction3Triangle, Gauss1Triangle>(C, nodetoelement, element, { 0 }, x, ax, ay, k);
+        Matrix<double> Ke = A + B + C;
+        Assembling(K, sys->F, T, Ke, sys->nodetoglobal, nodetoelement, element);
+    }
+    sys->K = new CSR<double>(K);
+    return sys;
 }
 
 // ---- the level-set design loop of sample/optimize/sample_optimize_levelset.cpp:75-192, element routines and helpers

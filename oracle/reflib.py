@@ -42,6 +42,7 @@ def lib():
         _lib.ref_oc_create.restype = C.c_void_p
         _lib.ref_mma_create.restype = C.c_void_p
         _lib.ref_conlin_create.restype = C.c_void_p
+        _lib.ref_advection_system.restype = C.c_void_p
         _lib.ref_system_nnz.restype = C.c_longlong
     return _lib
 
@@ -124,7 +125,7 @@ class System:
         return y, sec.value
 
     def solve(self, kind, b, itrmax=100000, eps=1e-10):
-        """kind: 0 CG, 1 ScalingCG, 2 ILU0CG.  Returns (x, seconds_solve, seconds_factor)."""
+        """kind: 0 CG, 1 ScalingCG, 2 ILU0CG, 3 BiCGSTAB, 4 BiCGSTAB2, 5 ScalingBiCGSTAB, 6 ILU0BiCGSTAB.  Returns (x, seconds_solve, seconds_factor)."""
         b = _f64(b)
         x = np.zeros(self.rows)
         sec = (C.c_double * 2)()
@@ -321,3 +322,11 @@ def levelset_run(coords, conn, fixed, loads, phifixed_nodes, prm, tmax, phi0, st
                                 len(pn), _p(pn, np.int32), _p(prm, np.float64), int(tmax),
                                 _p(phi, np.float64), _p(st, np.float64), _p(u, np.float64), _p(hist, np.float64), C.byref(conv))
     return dict(hist=hist[:it], phi=phi, str=st, u=u, iters=it, converged=bool(conv.value))
+
+
+def advection_system(coords, conn, fixed_nodes, fixed_vals, a=1.0, theta_deg=60.0, k=1.0e-6):
+    """K, F of sample/advection/sample_advectiondiffusion_static.cpp (T3; Advection + Diffusion + AdvectionSUPG)."""
+    coords, conn = _f64(coords), _i32(conn)
+    fn, fv = _i32(fixed_nodes), _f64(fixed_vals)
+    return System(lib().ref_advection_system(coords.shape[0], _p(coords, np.float64), conn.shape[0], _p(conn, np.int32), len(fn),
+                                             _p(fn, np.int32), _p(fv, np.float64), C.c_double(a), C.c_double(theta_deg), C.c_double(k)))

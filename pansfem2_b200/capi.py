@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(HERE, "libpansfem2_b200.so")
 
 EQ_PLANESTRAIN, EQ_SOLID, EQ_HEAT = 0, 1, 2
 SOLVER_CG, SOLVER_SCALINGCG, SOLVER_ILU0CG = 0, 1, 2
+SOLVER_BICGSTAB, SOLVER_BICGSTAB2, SOLVER_SCALINGBICGSTAB, SOLVER_ILU0BICGSTAB = 3, 4, 5, 6
 FILTER_DENSITY, FILTER_HEAVISIDE, FILTER_SENS_SIGMUND, FILTER_SENS_BORRVALL = 0, 1, 2, 3
 OPT_OC, OPT_MMA, OPT_CONLIN = 0, 1, 2
 E_NOCONV = 4

@@ -365,6 +365,10 @@ int pf2_csr_destroy(pf2_csr* A) {
                      A->ilu, A->level_rows, A->level_rows_u };
     for (void* p : ptrs) if (p) cudaFree(p);
     if (A->h_st) cudaFreeHost(A->h_st);
+    if (A->bi_slab) cudaFree(A->bi_slab);
+    if (A->bi_st) cudaFree(A->bi_st);
+    if (A->bi_hst) cudaFreeHost(A->bi_hst);
+    for (int i = 0; i < 2; i++) if (A->bi_ev[i]) cudaEventDestroy(A->bi_ev[i]);
     for (int i = 0; i < 2; i++) if (A->ev[i]) cudaEventDestroy(A->ev[i]);
     for (int i = 0; i < 2; i++) for (int j = 0; j < 4; j++) if (A->pev[i][j]) cudaEventDestroy(A->pev[i][j]);
     delete A;

@@ -284,7 +284,7 @@ int ilu0_apply(pf2_csr* A, double* v, const CgState* st, const double* factors =
     for (int l = 0; l < Lu; l++) {
         const int cnt = A->h_level_ptr_u[l + 1] - A->h_level_ptr_u[l];
         ilu0_sweep_level_kernel<false><<<(cnt + 127) / 128, 128, 0, c->stream>>>(cnt, A->level_rows_u + A->h_level_ptr_u[l], A->indptr,
-                                                                                 A->indices, A->diagpos, A->ilu, v, st);
+                                                                                 A->indices, A->diagpos, q, v, st);
         c->launches++;
     }
     PF2_LAUNCH_CHECK();
@@ -354,10 +354,12 @@ static void harvest_profile(pf2_csr* A, int slot) {
 
 int ensure_workspace_pub(pf2_csr* A) { return ensure_workspace(A); }
 int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out);
+int solve_bicgstab(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out);
 
 int solve(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out) {
     pf2_ctx* c = A->ctx;
-    PF2_CHECK(solver >= 0 && solver <= 2, "unknown solver");
+    PF2_CHECK(solver >= 0 && solver <= PF2_SOLVER_ILU0BICGSTAB, "unknown solver");
+    if (solver >= PF2_SOLVER_BICGSTAB) return solve_bicgstab(A, solver, b, x, itrmax, eps, iters_out, relres_out);
     if (A->dist) { PF2_CUDA(cudaSetDevice(c->device)); return solve_dist(A, solver, b, x, itrmax, eps, iters_out, relres_out); }
     PF2_CHECK(itrmax >= 0, "itrmax");
     PF2_CUDA(cudaSetDevice(c->device));

@@ -112,6 +112,11 @@ struct pf2_csr {
     // instrumentation: every chunk one iteration is bracketed by events (sampled per-kernel device time)
     cudaEvent_t pev[2][4] = { { nullptr, nullptr, nullptr, nullptr }, { nullptr, nullptr, nullptr, nullptr } };
     bool pev_armed[2] = { false, false };
+    // BiCGSTAB family workspace (bicgstab.cu): 12 vectors, device state, pinned mirror (2 slots), poll events
+    double* bi_slab = nullptr;
+    void* bi_st = nullptr;
+    void* bi_hst = nullptr;
+    cudaEvent_t bi_ev[2] = { nullptr, nullptr };
     double prof_ms[3] = { 0, 0, 0 };   // spmv+dot, update, p-update
     long long prof_samples = 0;
     long long total_iters = 0;

@@ -1,6 +1,7 @@
 //  pansfem2_b200/src/LinearAlgebra/Solvers/CG.h
-//  Mirror of the SPD solver family of the reference (src/LinearAlgebra/Solvers/CG.h, global namespace):
-//      CG :124-154, ILU0 :258-284, PreILU0 :289-315, ILU0CG :320-352, GetDiagonal :398, Scaling :409, ScalingCG :420-453
+//  Mirror of the Krylov solver family of the reference (src/LinearAlgebra/Solvers/CG.h, global namespace):
+//      CG :124-154, ILU0 :258-284, PreILU0 :289-315, ILU0CG :320-352, GetDiagonal :398, Scaling :409, ScalingCG :420-453,
+//      BiCGSTAB :159-194, BiCGSTAB2 :199-253, ILU0BiCGSTAB :357-393, ScalingBiCGSTAB :458-495
 //  Same signatures and the same observable behaviour (x0 = 0, stop on ||r|| < eps*||b|| of the recursive residual,
 //  "Convergence:faild" on stdout at itrmax, last iterate returned); for T = double the iterations run on the B200.
 #pragma once
@@ -90,4 +91,29 @@ std::vector<T> Scaling(std::vector<T>& _D, std::vector<T>& _b) {
 template<class T>
 std::vector<T> ScalingCG(CSR<T>& _A, const std::vector<T>& _b, int _itrmax, T _eps) {
     return PANSFEM2::B200::Solve(_A, PF2_SOLVER_SCALINGCG, _b, _itrmax, _eps, false);
+}
+
+//********************BiCGSTAB method********************
+template<class T>
+std::vector<T> BiCGSTAB(CSR<T>& _A, std::vector<T>& _b, int _itrmax, T _eps) {
+    return PANSFEM2::B200::Solve(_A, PF2_SOLVER_BICGSTAB, _b, _itrmax, _eps, false);
+}
+
+//********************BiCGSTAB2 method********************
+template<class T>
+std::vector<T> BiCGSTAB2(CSR<T>& _A, std::vector<T>& _b, int _itrmax, T _eps) {
+    return PANSFEM2::B200::Solve(_A, PF2_SOLVER_BICGSTAB2, _b, _itrmax, _eps, false);
+}
+
+//*******************ILU(0) preconditioning BiCGSTAB method*******************
+template<class T>
+std::vector<T> ILU0BiCGSTAB(CSR<T>& _A, CSR<T>& _M, std::vector<T>& _b, int _itrmax, T _eps) {
+    (void)_M;                           //  the factors are recomputed (and cached) next to _A on the device
+    return PANSFEM2::B200::Solve(_A, PF2_SOLVER_ILU0BICGSTAB, _b, _itrmax, _eps, true);
+}
+
+//********************Scaling preconditioning BiCGSTAB method********************
+template<class T>
+std::vector<T> ScalingBiCGSTAB(CSR<T>& _A, std::vector<T>& _b, int _itrmax, T _eps) {
+    return PANSFEM2::B200::Solve(_A, PF2_SOLVER_SCALINGBICGSTAB, _b, _itrmax, _eps, false);
 }

@@ -303,7 +303,59 @@ def golden_levelset():
     print("levelset", out["stdout_hist"].shape, int(out["vtk_count"]), int(out["iters"]), bool(out["converged"]), R2["hist"][-1])
 
 
+def krylov_case():
+    """A non-symmetric test system: the Q4 conduction matrix of heat2d(14, 10) plus a skew, convection-like perturbation on the
+    same pattern (deterministic)."""
+    from oracle import portlib as orc
+    P = problems.heat2d(14, 10)
+    S = orc.assemble(P.eq, P.coords, P.conn, P.fixed, P.loads, np.ones(P.nelem))[0]
+    indptr, indices, data, F = S.arrays()
+    rng = np.random.default_rng(5)
+    rows = np.repeat(np.arange(len(indptr) - 1), np.diff(indptr))
+    data2 = data + 0.3 * np.sign(indices - rows) * rng.uniform(0.5, 1.0, len(data)) * np.abs(data)
+    b = rng.uniform(-1, 1, len(F))
+    return indptr, indices, data2, b
+
+
+def golden_krylov():
+    """BiCGSTAB / BiCGSTAB2 / ScalingBiCGSTAB / ILU0BiCGSTAB (CG.h:159-253, 357-393, 458-495) of the live reference."""
+    reflib.set_num_threads(1)
+    indptr, indices, data, b = krylov_case()
+    A = reflib.system_from_csr(indptr, indices, data)
+    d = dict(indptr=indptr, indices=indices, data=data, b=b)
+    for kind, nm in ((3, "bicgstab"), (4, "bicgstab2"), (5, "scalingbicgstab"), (6, "ilu0bicgstab")):
+        d[f"x_{nm}"] = A.solve(kind, b)[0]
+    d["x_exact"] = np.linalg.solve(_dense(indptr, indices, data), b)
+    # the reference's own non-symmetric sample: sample/advection/sample_advectiondiffusion_static.cpp (T3, SUPG), solved there with
+    # BiCGSTAB; its committed output is AdvectionSUPG.vtk.  K and F are assembled by the reference's routines (ref_advection_system).
+    adv = f"{REF}/sample/advection"
+    nodes = np.array([[float(v) for v in r[1:3]] for r in csv_rows(f"{adv}/Node.csv")])
+    elems = np.array([[int(v) for v in r[1:4]] for r in csv_rows(f"{adv}/Element.csv")], dtype=np.int32)
+    fix = [(int(r[0]), float(r[1])) for r in csv_rows(f"{adv}/Dirichlet.csv") if r[1] != "free"]
+    fn, fv = np.array([f[0] for f in fix], np.int32), np.array([f[1] for f in fix])
+    S = reflib.advection_system(nodes, elems, fn, fv)
+    ai, aj, ad, aF = S.arrays()
+    L = open(f"{adv}/AdvectionSUPG.vtk").read().split("\n")
+    i0 = next(k for k, ln in enumerate(L) if ln.startswith("SCALARS T"))
+    T = np.array([float(v) for v in L[i0 + 2:i0 + 2 + len(nodes)]])
+    d.update(adv_coords=nodes, adv_conn=elems, adv_fix_node=fn, adv_fix_val=fv, adv_indptr=ai, adv_indices=aj, adv_data=ad, adv_F=aF,
+             adv_n2g=S.nodetoglobal(len(nodes), 1), adv_T=T, adv_x_bicgstab=S.solve(3, aF)[0])
+    np.savez_compressed(f"{OUT}/live_krylov.npz", **d)
+    print("krylov", len(b), [float(np.abs(d[k] - d["x_exact"]).max()) for k in d if k.startswith("x_") and k != "x_exact"])
+
+
+def _dense(indptr, indices, data):
+    n = len(indptr) - 1
+    M = np.zeros((n, n))
+    for i in range(n):
+        M[i, indices[indptr[i]:indptr[i + 1]]] = data[indptr[i]:indptr[i + 1]]
+    return M
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "krylov":
+        golden_krylov()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "levelset":
         golden_levelset()
         sys.exit(0)
@@ -322,3 +374,4 @@ if __name__ == "__main__":
     golden_conlin()
     golden_families()
     golden_levelset()
+    golden_krylov()
