@@ -151,6 +151,13 @@ int pf2_spmv_set_tma_tuning(pf2_csr* A, int stages, int ctas_per_sm);
 /* micro-benchmark hook: run SpMV `reps` times with kernel variant `variant` (0 = auto), device-timed */
 int pf2_spmv_bench(pf2_csr* A, int variant, int reps, int flush_l2, double* ms_per_spmv);
 
+/* Opt-in matrix-free application of K on a UNIFORM structured mesh (SquareMesh.h numbering / x-major hex lattice, all elements
+ * congruent; Q4 or hex8 stiffness selections): y = sum_e E_e Ke0 p_e with one shared unit-modulus element matrix, instead of
+ * streaming the CSR.  Same product up to summation order; assembly, preconditioner and the Krylov recurrences are unchanged.
+ * Call after pf2_csr_pattern; takes effect from the next pf2_assemble (SpMV variant 41).  PF2_E_UNSUPPORTED when the mesh does
+ * not qualify (the matrix keeps its CSR kernels).  pf2_spmv_set_variant(A, 0) returns to the CSR kernels. */
+int pf2_csr_matrix_free(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq);
+
 /* ---- CG / ScalingCG / ILU0CG (CG.h:124-154, 420-453, 320-352); ILU0 / PreILU0 (CG.h:258-315) ---------------- */
 /* x0 = 0; stop when ||r||_2 < eps*||b||_2 on the recursive residual.  Returns PF2_E_NOCONV at itrmax (x holds
  * the last iterate, as the reference returns it). */

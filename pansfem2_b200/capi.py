@@ -225,6 +225,10 @@ class Csr:
         _ck(lib().pf2_assemble(self.h, mesh.h, dofmap.h, eq, modulus.ptr if modulus is not None else None,
                                rho.ptr if rho is not None else None, prm, len(ln), _p(ln, np.int32), _p(ld, np.int32), _p(lv, np.float64)))
 
+    def matrix_free(self, mesh, dofmap, eq):
+        """Opt into the matrix-free operator (uniform structured Q4 / hex8 meshes); takes effect from the next assemble."""
+        _ck(lib().pf2_csr_matrix_free(self.h, mesh.h, dofmap.h, eq))
+
     def spmv_host(self, x):
         x = _f64(x)
         y = np.zeros(self.rows)
@@ -400,12 +404,14 @@ def compliance_sens_device(mesh, eq, u_dev, rho_dev, params6, dfdrho_dev, r_dev=
 class Simp:
     """The device-resident design loop for a pansfem2_b200.problems.Problem."""
 
-    def __init__(self, ctx, problem, solver=SOLVER_SCALINGCG):
+    def __init__(self, ctx, problem, solver=SOLVER_SCALINGCG, matrix_free=False):
         P = problem
         self.ctx, self.P = ctx, P
         self.mesh = Mesh(ctx, P.coords, P.conn)
         self.dofmap = DofMap(ctx, P.nnode, P.ndof, P.fixed)
         self.A = Csr.pattern(ctx, self.mesh, self.dofmap)
+        if matrix_free:
+            self.A.matrix_free(self.mesh, self.dofmap, P.eq)
         self.filter = Filter(ctx, P.filter_kind, *P.nbrs)
         ln, ld, lv = _i32(P.loads[0]), _i32(P.loads[1]), _f64(P.loads[2])
         optp, params = _f64(P.optp()), _f64(P.params())

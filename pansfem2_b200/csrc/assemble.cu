@@ -222,6 +222,7 @@ int assemble_generic_launch(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, const E
 int sens_generic_launch(pf2_mesh* mesh, const EqInfo& q, const double* u_nodal, const double* rho, const double params[6], double* f_dev,
                         double* dfdrho, double* r_nodal);
 int element_generic_launch(pf2_ctx* ctx, const EqInfo& q, const double* xe_dev, double E, double t, double* Ke_dev);
+int mf_update(pf2_csr* A, pf2_mesh* mesh, const double* modulus_dev, const double* rho_dev, const double params[5]);
 
 // numeric assembly with the nodal loads already on the device (the design loop keeps them resident)
 int assemble_device(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq, const double* modulus_dev, const double* rho_dev,
@@ -258,6 +259,7 @@ int assemble_device(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq, const d
     }
     A->ilu_valid = false;
     A->sell_values_valid = false;
+    if (A->mf_ready) PF2_TRY(mf_update(A, mesh, modulus_dev, rho_dev, params));
     return PF2_OK;
 }
 

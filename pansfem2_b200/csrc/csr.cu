@@ -14,6 +14,7 @@
 #include "p2p.cuh"
 #include "spmv_tma.cuh"
 #include "spmv_sell.cuh"
+#include "spmv_mf.cuh"
 #include <cub/cub.cuh>
 
 namespace pf2 {
@@ -251,6 +252,58 @@ static int launch_sell(pf2_csr* A, const double* x, double* y, const CgState* st
     return PF2_OK;
 }
 
+// matrix-free operator: Ke0 travels through constant memory, re-uploaded only when another matrix (or new parameters) used it last
+static const pf2_csr* g_mf_owner = nullptr;
+static unsigned long long g_mf_owner_version = 0;
+
+template <bool DOT>
+static int launch_mf(pf2_csr* A, const double* x, double* y, const CgState* st, double* dot_out) {
+    pf2_ctx* c = A->ctx;
+    PF2_CHECK(A->mf_ready && A->mf_version > 0, "matrix-free operator: assemble once after pf2_csr_matrix_free");
+    if (g_mf_owner != A || g_mf_owner_version != A->mf_version) {
+        const int m = (1 << A->mf_dim) * A->mf_ndof;
+        PF2_CUDA(cudaMemcpyToSymbolAsync(c_mf_ke0, A->mf_ke0, sizeof(double) * (size_t)m * m, 0, cudaMemcpyHostToDevice, c->stream));
+        g_mf_owner = A; g_mf_owner_version = A->mf_version;
+    }
+    MfGrid G;
+    G.n[0] = A->mf_n[0]; G.n[1] = A->mf_n[1]; G.n[2] = A->mf_n[2];
+    G.nnode = A->mf_n[0] * A->mf_n[1] * A->mf_n[2];
+    const int nb = (G.nnode + kThreads - 1) / kThreads;
+#define MF(D, N)                                                                                                                     \
+    {                                                                                                                                \
+        const int grid = std::max(1, std::min(nb, DOT ? c->wave_grid((const void*)spmv_mf_kernel<D, N, DOT>, kThreads) : c->sm_count * 16)); \
+        spmv_mf_kernel<D, N, DOT><<<grid, kThreads, 0, c->stream>>>(G, A->mf_n2g, A->mf_E, x, y, st, dot_out, c->red.partials, c->red.ticket, \
+                                                               A->own_lo, A->own_hi, A->p2p_dev, A->p2p_epoch);                      \
+    }
+    if (A->mf_dim == 3) MF(3, 3)
+    else if (A->mf_ndof == 2) MF(2, 2)
+    else MF(2, 1)
+#undef MF
+    return PF2_OK;
+}
+
+// called by assemble_device after every numeric assembly when the operator is enabled: per-element moduli and (when V / t changed) Ke0
+int mf_update(pf2_csr* A, pf2_mesh* mesh, const double* modulus_dev, const double* rho_dev, const double params[5]) {
+    pf2_ctx* c = A->ctx;
+    const double E0 = params[0], E1 = params[1], V = params[2], p = params[3], t = params[4];
+    mf_modulus_kernel<<<c->grid_for(A->mf_nelem), kThreads, 0, c->stream>>>(A->mf_nelem, modulus_dev, rho_dev, E0, E1, p, A->mf_E);
+    PF2_LAUNCH_CHECK();
+    c->launches++;
+    if (A->mf_version == 0 || V != A->mf_V || t != A->mf_t) {
+        const int npe = 1 << A->mf_dim, dim = A->mf_dim;
+        int nd[8];
+        double xe[24];
+        PF2_CUDA(cudaMemcpyAsync(nd, mesh->conn, sizeof(int) * npe, cudaMemcpyDeviceToHost, c->stream));
+        PF2_CUDA(cudaStreamSynchronize(c->stream));
+        for (int a = 0; a < npe; a++) PF2_CUDA(cudaMemcpyAsync(xe + a * dim, mesh->coords + (size_t)nd[a] * dim, sizeof(double) * dim, cudaMemcpyDeviceToHost, c->stream));
+        PF2_CUDA(cudaStreamSynchronize(c->stream));
+        PF2_TRY(pf2_element_matrix(c, A->mf_eq, xe, 1.0, V, t, A->mf_ke0));
+        A->mf_V = V; A->mf_t = t;
+        A->mf_version++;
+    }
+    return PF2_OK;
+}
+
 template <bool DOT>
 static int launch_spmv(pf2_csr* A, int variant, const double* x, double* y, const CgState* st, double* dot_out) {
     pf2_ctx* c = A->ctx;
@@ -279,6 +332,7 @@ static int launch_spmv(pf2_csr* A, int variant, const double* x, double* y, cons
         case 14: STR(8) break;
         case 15: STR(16) break;
         case 31: PF2_TRY((launch_sell<DOT>(A, x, y, st, dot_out))); break;
+        case 41: PF2_TRY((launch_mf<DOT>(A, x, y, st, dot_out))); break;
         case 21: PF2_TRY((launch_tma<1, DOT>(A, x, y, st, dot_out))); break;
         case 22: PF2_TRY((launch_tma<2, DOT>(A, x, y, st, dot_out))); break;
         case 23: PF2_TRY((launch_tma<4, DOT>(A, x, y, st, dot_out))); break;
@@ -302,6 +356,7 @@ static bool variant_ok(const pf2_csr* A, int variant) {
         return (long long)(kThreads / G) * A->max_row <= kStreamCap;
     }
     if (variant == 31) return true;
+    if (variant == 41) return A->mf_ready;
     if (variant >= 21 && variant <= 26) {
         int G = 1 << (variant - 21);
         return (long long)(kConsumers / G) * A->max_row <= kTileNnz;
@@ -365,6 +420,8 @@ int pf2_csr_destroy(pf2_csr* A) {
                      A->ilu, A->level_rows, A->level_rows_u };
     for (void* p : ptrs) if (p) cudaFree(p);
     if (A->h_st) cudaFreeHost(A->h_st);
+    if (A->mf_E) cudaFree(A->mf_E);
+    if (g_mf_owner == A) g_mf_owner = nullptr;
     if (A->bi_slab) cudaFree(A->bi_slab);
     if (A->bi_st) cudaFree(A->bi_st);
     if (A->bi_hst) cudaFreeHost(A->bi_hst);
@@ -420,6 +477,47 @@ int pf2_spmv_host(pf2_csr* A, const double* x_host, double* y_host) {
 
 int pf2_spmv_set_tma_tuning(pf2_csr* A, int stages, int ctas_per_sm) {
     A->tma_stages = stages; A->tma_ctas_per_sm = ctas_per_sm;
+    return PF2_OK;
+}
+
+int pf2_csr_matrix_free(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq) {
+    PF2_CHECK(A && mesh && map, "null argument");
+    pf2_ctx* c = A->ctx;
+    int dim = 0, npe = 0, ndof = 0;
+    PF2_TRY(pf2_eq_describe(eq, &dim, &npe, &ndof));
+    const int phys = eq & 0xff, shape = (eq >> 8) & 0xff;
+    const bool q4 = dim == 2 && npe == 4 && (shape == 0 || shape == PF2_SHAPE_Q4), h8 = dim == 3 && npe == 8 && (shape == 0 || shape == PF2_SHAPE_HEX8);
+    if (!(q4 || h8) || phys == PF2_PHYS_MASS) { set_error("matrix-free operator: Q4 / hex8 stiffness selections only"); return PF2_E_UNSUPPORTED; }
+    PF2_CHECK(mesh->dim == dim && mesh->npe == npe && map->ndof == ndof && A->rows == map->kdegree, "mesh / dof map / matrix do not belong together");
+    // lattice dimensions from element 0 (x-major numbering: the second local node is one x-stride away)
+    int nd[8];
+    PF2_CUDA(cudaMemcpyAsync(nd, mesh->conn, sizeof(int) * npe, cudaMemcpyDeviceToHost, c->stream));
+    PF2_CUDA(cudaStreamSynchronize(c->stream));
+    int n0 = 0, n1 = 0, n2 = 1;
+    if (dim == 2) { n1 = nd[1] - nd[0]; }
+    else { n2 = nd[3] - nd[0]; const int s0 = nd[1] - nd[0]; n1 = (n2 > 0) ? s0 / n2 : 0; if (n2 <= 1 || n1 * n2 != s0) n1 = 0; }
+    if (n1 <= 1) { set_error("matrix-free operator: mesh is not an x-major structured lattice"); return PF2_E_UNSUPPORTED; }
+    n0 = mesh->nnode / (n1 * n2);
+    const long long ne = (long long)(n0 - 1) * (n1 - 1) * (dim == 3 ? n2 - 1 : 1);
+    if (n0 <= 1 || (long long)n0 * n1 * n2 != mesh->nnode || ne != mesh->nelem) { set_error("matrix-free operator: mesh is not an x-major structured lattice"); return PF2_E_UNSUPPORTED; }
+    MfGrid G;
+    G.n[0] = n0; G.n[1] = n1; G.n[2] = n2; G.nnode = mesh->nnode;
+    int* bad = nullptr;
+    PF2_TRY(dev_alloc(&bad, 1));
+    PF2_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), c->stream));
+    mf_verify_kernel<<<c->grid_for(mesh->nelem), kThreads, 0, c->stream>>>(dim, G, mesh->nelem, mesh->conn, mesh->coords, bad);
+    int hbad = 0;
+    PF2_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PF2_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(bad);
+    c->launches++;
+    if (hbad) { set_error("matrix-free operator: elements are not congruent translates on an x-major lattice"); return PF2_E_UNSUPPORTED; }
+    if (!A->mf_E) PF2_TRY(dev_alloc(&A->mf_E, (size_t)mesh->nelem));
+    A->mf_dim = dim; A->mf_ndof = ndof; A->mf_eq = eq; A->mf_n[0] = n0; A->mf_n[1] = n1; A->mf_n[2] = n2; A->mf_nelem = mesh->nelem;
+    A->mf_n2g = map->n2g;
+    A->mf_version = 0;
+    A->mf_ready = true;
+    A->spmv_variant = 41;
     return PF2_OK;
 }
 

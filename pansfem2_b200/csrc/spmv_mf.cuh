@@ -1,0 +1,142 @@
+// spmv_mf.cuh -- matrix-free application of the assembled operator on a UNIFORM structured mesh (opt-in SpMV variant 41).
+//
+// On the structured benchmark meshes (SquareMesh.h:62-107 numbering, our x-major hex mesher) every element is congruent, so
+// Ke = E_e * Ke0 with one shared unit-modulus matrix Ke0 and    y = K p = sum_e E_e * scatter(Ke0 * gather(p, e)).
+// One thread owns one node: it gathers p on the 3^dim neighbouring nodes (through nodetoglobal, fixed dofs read as 0 -- which is
+// exactly Dirichlet by elimination), walks the 2^dim adjacent elements with Ke0 in constant memory (immediate operands of the
+// DFMA) and writes its NDOF rows.  Traffic per dof: p 8 B + y 8 B + nodetoglobal 4 B + E 8/ndof B  (~24 B) instead of the CSR
+// stream's 10..12 B per NONZERO (~384 B/dof in 2-D elasticity, ~834 B/dof for hex8), so the operator is bound by the DFMA pipe,
+// not by HBM.  The product equals the CSR product up to the order of the floating-point sums (K_ij p_j is sum_e (E_e Ke0_ij) p_j
+// there, sum_e E_e (Ke0_ij p_j) here); the Krylov recurrences, preconditioner (the assembled diagonal) and stopping test are
+// untouched.  CSR assembly still runs (the matrix stays available for download, ILU(0) and the default CSR kernels).
+#pragma once
+#include "types.cuh"
+#include "p2p.cuh"
+
+namespace pf2 {
+
+__constant__ double c_mf_ke0[576];      // (npe*ndof)^2 <= 24^2, row-major, unit modulus
+
+struct MfGrid {
+    int n[3];       // nodes per axis (x-major: node id = (i*n[1] + j)*n[2] + k ; 2-D: n[2] = 1)
+    int nnode;
+};
+
+// corner offsets of local node a: Q4 (0,0)(1,0)(1,1)(0,1) ; hex8 bottom face then top face (ShapeFunction.h:171, 299)
+__device__ __forceinline__ void mf_corner(int dim, int a, int& ox, int& oy, int& oz) {
+    ox = ((a + 1) & 2) ? 1 : 0;
+    oy = (a & 2) ? 1 : 0;
+    oz = (dim == 3 && (a & 4)) ? 1 : 0;
+}
+
+template <int DIM, int NDOF, bool DOT>
+__global__ void __launch_bounds__(kThreads)      // grid_sum_last folds kThreads / 32 warp sums
+spmv_mf_kernel(MfGrid G, const int* __restrict__ n2g, const double* __restrict__ E, const double* __restrict__ x, double* __restrict__ y,
+               const CgState* __restrict__ st, double* dot_out, double* partials, unsigned int* ticket, int dot_lo, int dot_hi,
+               const P2PView* p2p, unsigned long long* p2p_epoch) {
+    if (DOT && st != nullptr && st->done) return;
+    constexpr int NC = 1 << DIM, M = NC * NDOF, NN = (DIM == 2) ? 9 : 27;
+    const int n1 = G.n[1], n2 = G.n[2];
+    const int s0 = n1 * n2, s1 = n2;                       // node strides along x, y (z stride 1; in 2-D y stride 1 because n2 = 1)
+    const int e1 = n1 - 1, e2 = (DIM == 3) ? n2 - 1 : 1;   // elements per axis y, z
+    double dot = 0.0;
+    for (int nid = blockIdx.x * blockDim.x + threadIdx.x; nid < G.nnode; nid += gridDim.x * blockDim.x) {
+        int rows[NDOF];
+        bool any = false;
+#pragma unroll
+        for (int d = 0; d < NDOF; d++) { rows[d] = n2g[(size_t)nid * NDOF + d]; any |= (rows[d] != -1); }
+        if (!any) continue;
+        const int k = (DIM == 3) ? nid % n2 : 0;
+        const int j = (nid / n2) % n1;
+        const int i = nid / s0;
+        // p on the 3^DIM neighbouring nodes (0 outside the mesh and on fixed dofs)
+        double pn[NN][NDOF];
+#pragma unroll
+        for (int q = 0; q < NN; q++) {
+            const int di = q % 3 - 1, dj = (q / 3) % 3 - 1, dk = (DIM == 3) ? q / 9 - 1 : 0;
+            const bool in = (unsigned)(i + di) < (unsigned)G.n[0] && (unsigned)(j + dj) < (unsigned)n1 && (DIM == 2 || (unsigned)(k + dk) < (unsigned)n2);
+            const long long nb = (long long)nid + di * s0 + dj * s1 + dk;
+#pragma unroll
+            for (int d = 0; d < NDOF; d++) {
+                const int r = in ? n2g[(size_t)nb * NDOF + d] : -1;
+                pn[q][d] = (r != -1) ? __ldg(x + r) : 0.0;
+            }
+        }
+        double acc[NDOF];
+#pragma unroll
+        for (int d = 0; d < NDOF; d++) acc[d] = 0.0;
+        // this node is local node a of the element whose origin is (i - ox, j - oy, k - oz)
+#pragma unroll
+        for (int a = 0; a < NC; a++) {
+            int ox, oy, oz;
+            mf_corner(DIM, a, ox, oy, oz);
+            const int ei = i - ox, ej = j - oy, ek = k - oz;
+            const bool in = (unsigned)ei < (unsigned)(G.n[0] - 1) && (unsigned)ej < (unsigned)e1 && (DIM == 2 || (unsigned)ek < (unsigned)e2);
+            if (!in) continue;
+            const double Ee = E[((size_t)ei * e1 + ej) * e2 + ek];
+            double t[NDOF];
+#pragma unroll
+            for (int d = 0; d < NDOF; d++) t[d] = 0.0;
+#pragma unroll
+            for (int b = 0; b < NC; b++) {
+                int bx, by, bz;
+                mf_corner(DIM, b, bx, by, bz);
+                const int q = (bx - ox + 1) + 3 * (by - oy + 1) + ((DIM == 3) ? 9 * (bz - oz + 1) : 0);
+#pragma unroll
+                for (int di = 0; di < NDOF; di++)
+#pragma unroll
+                    for (int dj = 0; dj < NDOF; dj++) t[di] += c_mf_ke0[(a * NDOF + di) * M + b * NDOF + dj] * pn[q][dj];
+            }
+#pragma unroll
+            for (int d = 0; d < NDOF; d++) acc[d] += Ee * t[d];
+        }
+#pragma unroll
+        for (int d = 0; d < NDOF; d++) {
+            const int r = rows[d];
+            if (r == -1) continue;
+            y[r] = acc[d];
+            if (DOT && r >= dot_lo && r < dot_hi) dot += acc[d] * pn[(NN - 1) / 2][d];      // centre entry = x[r]
+        }
+    }
+    if (DOT) {
+        double vsum[1] = { dot };
+        if (grid_sum_last<1>(vsum, partials, ticket)) finish_dot(vsum[0], dot_out, p2p, p2p_epoch);
+    }
+}
+
+// lattice check: connectivity follows the x-major numbering and every element is a translate of element 0
+__global__ void mf_verify_kernel(int dim, MfGrid G, int nelem, const int* __restrict__ conn, const double* __restrict__ coords, int* bad) {
+    const int npe = 1 << dim;
+    const int n1 = G.n[1], n2 = G.n[2], s0 = n1 * n2, s1 = n2;
+    const int e1 = n1 - 1, e2 = (dim == 3) ? n2 - 1 : 1;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nelem; e += gridDim.x * blockDim.x) {
+        const int ek = e % e2, ej = (e / e2) % e1, ei = e / (e1 * e2);
+        const int origin = ei * s0 + ej * s1 + ek;
+        bool ok = true;
+        for (int a = 0; a < npe; a++) {
+            int ox, oy, oz;
+            mf_corner(dim, a, ox, oy, oz);
+            const int node = origin + ox * s0 + oy * s1 + oz;
+            ok = ok && (conn[(size_t)e * npe + a] == node);
+            if (!ok) break;
+            for (int c = 0; c < dim; c++) {
+                // edge vectors relative to the element's first node must equal those of element 0
+                const double d0 = coords[(size_t)conn[a] * dim + c] - coords[(size_t)conn[0] * dim + c];
+                const double de = coords[(size_t)node * dim + c] - coords[(size_t)origin * dim + c];
+                const double scale = fabs(coords[(size_t)conn[npe == 4 ? 2 : 6] * dim + c] - coords[(size_t)conn[0] * dim + c]) + 1.0e-300;
+                ok = ok && (fabs(d0 - de) <= 1.0e-9 * scale);
+            }
+        }
+        if (!ok) atomicExch(bad, 1);
+    }
+}
+
+__global__ void mf_modulus_kernel(int nelem, const double* __restrict__ modulus, const double* __restrict__ rho, double E0, double E1, double p,
+                                  double* __restrict__ E) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nelem; e += gridDim.x * blockDim.x) {
+        if (modulus) E[e] = modulus[e];
+        else { const double rp = pow(rho[e], p); E[e] = E1 * rp + E0 * (1.0 - rp); }
+    }
+}
+
+}  // namespace pf2

@@ -112,6 +112,14 @@ struct pf2_csr {
     // instrumentation: every chunk one iteration is bracketed by events (sampled per-kernel device time)
     cudaEvent_t pev[2][4] = { { nullptr, nullptr, nullptr, nullptr }, { nullptr, nullptr, nullptr, nullptr } };
     bool pev_armed[2] = { false, false };
+    // matrix-free operator on a uniform structured mesh (spmv_mf.cuh, SpMV variant 41; opt-in)
+    bool mf_ready = false;
+    int mf_dim = 0, mf_ndof = 0, mf_eq = 0, mf_n[3] = { 0, 0, 0 }, mf_nelem = 0;
+    double* mf_E = nullptr;           // per-element modulus of the last assembly
+    const int* mf_n2g = nullptr;      // borrowed from the dof map
+    double mf_ke0[576];               // unit-modulus element matrix (host copy, uploaded to constant memory)
+    double mf_V = -1.0, mf_t = -1.0;  // parameters mf_ke0 was built with
+    unsigned long long mf_version = 0;
     // BiCGSTAB family workspace (bicgstab.cu): 12 vectors, device state, pinned mirror (2 slots), poll events
     double* bi_slab = nullptr;
     void* bi_st = nullptr;
