@@ -205,6 +205,10 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-matrix-free-leg", action="store_true", help="skip the extra timed leg with the matrix-free operator")
+    ap.add_argument("--operator", default=os.environ.get("PF2_OPERATOR", "csr"), choices=["csr", "matrix-free"],
+                    help="how K is applied inside the PCG: the assembled CSR (default; the path the roofline is quoted on) or the opt-in "
+                         "matrix-free operator for uniform structured meshes (pf2_csr_matrix_free)")
     ap.add_argument("--cg-iters-hint", type=float, default=0.0, help="CG iterations per design iteration for --impl reference scaling")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -251,11 +255,11 @@ def main():
         D = capi.Dist(ctx, rank, world)
         slab = partition.slab_from_factory(lambda xr: make_problem(args.workload, xr=xr), dims, ndof, rank, world)
         P = slab.local
-        S = capi.Simp(ctx, P)
+        S = capi.Simp(ctx, P, matrix_free=(args.operator == "matrix-free"))
         D.set_simp_partition(S, slab, nelem_global)
     else:
         P = make_problem(args.workload)
-        S = capi.Simp(ctx, P)
+        S = capi.Simp(ctx, P, matrix_free=(args.operator == "matrix-free"))
     P.extra["nnz"] = S.A.nnz
     nelem = P.nelem
     s_in, s_out, rho_out = capi.pinned_empty(nelem), capi.pinned_empty(nelem), capi.pinned_empty(nelem)
@@ -300,6 +304,30 @@ def main():
     ms_e2e = ctx.timer_stop()
     barrier()
     clocks = sampler.stop()
+    # ---- extra leg (reported beside the headline, never instead of it): the same loop with K applied matrix-free ----
+    mf = None
+    if args.operator == "csr" and not args.no_matrix_free_leg:
+        try:
+            S.A.matrix_free(S.mesh, S.dofmap, P.eq)
+            S.iterate(check_convergence=False)                       # first assembly with the operator (Ke0 upload), untimed
+            S.A.solver_stats(reset=True)
+            barrier()
+            ctx.timer_start()
+            mf_steps = [S.iterate(check_convergence=False) for _ in range(args.steps)]
+            ms_mf = ctx.timer_stop()
+            barrier()
+            ks = S.A.solver_stats(reset=True)
+            if world > 1:
+                t = torch.tensor([ms_mf], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_mf = t.item()
+            mf = {"value": args.steps / (ms_mf * 1e-3), "unit": base["unit"], "ms_per_step": ms_mf / args.steps,
+                  "cg_iters_per_step": float(np.mean([s["cg_iters"] for s in mf_steps])), "cg_relres_max": max(s["cg_relres"] for s in mf_steps),
+                  "operator_ms": ks["spmv_ms"], "update_ms": ks["update_ms"], "pupdate_ms": ks["pupdate_ms"],
+                  "note": "opt-in pf2_csr_matrix_free (uniform structured mesh): y = sum_e E_e Ke0 p_e instead of the CSR stream; same assembly, "
+                          "preconditioner, recurrences and stopping test; parity in tests/test_gpu_matrix_free.py"}
+        except capi.Pf2Error as e:
+            mf = {"unavailable": str(e)[:160]}
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -318,6 +346,26 @@ def main():
         achieved = spmv_bytes / (kstats["spmv_ms"] * 1e-3) / 1e9
         v = kstats["variant"]
         kname = "spmv_sell_kernel<DOT> (SELL-32, thread per row)" if v == 31 else ("spmv_tma_kernel" if v >= 21 else "spmv_stream_kernel" if v >= 11 else "spmv_vector_kernel")
+        if v == 41:
+            # matrix-free operator: the matrix stream is gone, the dominant HBM kernel of a PCG iteration is the fused vector update
+            upd_bytes = 64 * S.A.rows
+            achieved = upd_bytes / (kstats["update_ms"] * 1e-3) / 1e9
+            mf_bytes = (8 + 8 + 4) * S.A.rows + 8 * nelem
+            roof = {"bound": "hbm", "kernel": "cg_update_kernel<Jacobi>: x += a p, r -= a Kp, z = r/D, z.r, r.r (the largest HBM kernel once K is applied matrix-free)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                    "algorithmic_bytes_per_launch": upd_bytes, "avg_launch_ms": kstats["update_ms"], "samples": kstats["samples"],
+                    "matrix_free_operator": {"kernel": "spmv_mf_kernel (variant 41): y = sum_e E_e Ke0 p_e fused with p.Kp, DFMA-bound",
+                                             "avg_launch_ms": kstats["spmv_ms"], "compulsory_bytes_per_launch": mf_bytes,
+                                             "dfma_gflops": 2.0 * S.A.nnz / (kstats["spmv_ms"] * 1e-3) / 1e9,
+                                             "csr_equivalent_GBps": spmv_bytes / (kstats["spmv_ms"] * 1e-3) / 1e9},
+                    "pcg_iteration": {"ms": kstats["spmv_ms"] + kstats["update_ms"] + kstats["pupdate_ms"], "update_ms": kstats["update_ms"],
+                                      "pupdate_ms": kstats["pupdate_ms"]}}
+        else:
+            roof = None
+    if roof is None and kstats["samples"] > 0 and kstats["spmv_ms"] > 0:
+        achieved = spmv_bytes / (kstats["spmv_ms"] * 1e-3) / 1e9
+        v = kstats["variant"]
+        kname = "spmv_sell_kernel<DOT> (SELL-32, thread per row)" if v == 31 else ("spmv_tma_kernel" if v >= 21 else "spmv_stream_kernel" if v >= 11 else "spmv_vector_kernel")
         roof = {"bound": "hbm", "kernel": f"{kname}: y = K p fused with p.Kp (variant {v})", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic(args.workload),
                 "algorithmic_bytes_per_launch": spmv_bytes, "avg_launch_ms": kstats["spmv_ms"], "samples": kstats["samples"],
@@ -330,11 +378,14 @@ def main():
                                                                     "NCCL for the per-design-iteration exchanges)" if os.environ.get("PF2_P2P", "1") != "0"
                                                                     else f"{world} x-slabs (row-block partition, NCCL halo exchange + allreduce)"),
                        "l2": "working set (CSR values+indices %.0f MB) exceeds the 126 MB L2; no flush needed" % (12 * S.A.nnz / 1e6),
-                       "cg_iters_per_step": cg_iters, "solver": "ScalingCG eps=1e-10 x0=0"},
+                       "cg_iters_per_step": cg_iters, "solver": "ScalingCG eps=1e-10 x0=0",
+                       "operator": "assembled CSR (SELL-32 mirror)" if args.operator == "csr" else "matrix-free on the uniform mesh (pf2_csr_matrix_free); CSR still assembled every iteration"},
                e2e={"value": e2e_value, "unit": base["unit"], "h2d_bytes_per_step": int(8 * nelem), "d2h_bytes_per_step": int(16 * nelem),
                     "ms_per_step": ms_e2e / args.steps},
                gpu_launches=int(launches), clocks=clocks, roofline=roof, wall_s=wall,
                phases_ms=steps[-1]["phase_ms"], objective=[s["f"] for s in steps], cg_relres_max=max(s["cg_relres"] for s in steps))
+    if mf is not None:
+        out["matrix_free"] = mf
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             try:

@@ -268,9 +268,10 @@ static int launch_mf(pf2_csr* A, const double* x, double* y, const CgState* st, 
     MfGrid G;
     G.n[0] = A->mf_n[0]; G.n[1] = A->mf_n[1]; G.n[2] = A->mf_n[2];
     G.nnode = A->mf_n[0] * A->mf_n[1] * A->mf_n[2];
-    const int nb = (G.nnode + kThreads - 1) / kThreads;
 #define MF(D, N)                                                                                                                     \
     {                                                                                                                                \
+        const int nb = ((G.n[0] + MfTile<D>::TI - 1) / MfTile<D>::TI) * ((G.n[1] + MfTile<D>::TJ - 1) / MfTile<D>::TJ) *             \
+                       ((D) == 3 ? (G.n[2] + MfTile<D>::TK - 1) / MfTile<D>::TK : 1);                                                \
         const int grid = std::max(1, std::min(nb, DOT ? c->wave_grid((const void*)spmv_mf_kernel<D, N, DOT>, kThreads) : c->sm_count * 16)); \
         spmv_mf_kernel<D, N, DOT><<<grid, kThreads, 0, c->stream>>>(G, A->mf_n2g, A->mf_E, x, y, st, dot_out, c->red.partials, c->red.ticket, \
                                                                A->own_lo, A->own_hi, A->p2p_dev, A->p2p_epoch);                      \

@@ -29,74 +29,91 @@ __device__ __forceinline__ void mf_corner(int dim, int a, int& ox, int& oy, int&
     oz = (dim == 3 && (a & 4)) ? 1 : 0;
 }
 
+// Tile of nodes one CTA owns per step (k fastest, like the numbering) and its one-node halo.
+template <int DIM> struct MfTile;
+template <> struct MfTile<2> { static constexpr int TI = 4, TJ = 64, TK = 1; };
+template <> struct MfTile<3> { static constexpr int TI = 4, TJ = 8, TK = 8; };
+
+// One CTA = one tile of kThreads nodes.  Phase 1 stages p of the tile + halo in shared memory (ONE nodetoglobal lookup and one
+// gather per staged node instead of 3^dim per node); phase 2: one thread per node walks its 2^dim elements out of shared memory.
 template <int DIM, int NDOF, bool DOT>
 __global__ void __launch_bounds__(kThreads)      // grid_sum_last folds kThreads / 32 warp sums
 spmv_mf_kernel(MfGrid G, const int* __restrict__ n2g, const double* __restrict__ E, const double* __restrict__ x, double* __restrict__ y,
                const CgState* __restrict__ st, double* dot_out, double* partials, unsigned int* ticket, int dot_lo, int dot_hi,
                const P2PView* p2p, unsigned long long* p2p_epoch) {
     if (DOT && st != nullptr && st->done) return;
-    constexpr int NC = 1 << DIM, M = NC * NDOF, NN = (DIM == 2) ? 9 : 27;
-    const int n1 = G.n[1], n2 = G.n[2];
-    const int s0 = n1 * n2, s1 = n2;                       // node strides along x, y (z stride 1; in 2-D y stride 1 because n2 = 1)
-    const int e1 = n1 - 1, e2 = (DIM == 3) ? n2 - 1 : 1;   // elements per axis y, z
+    constexpr int NC = 1 << DIM, M = NC * NDOF;
+    constexpr int TI = MfTile<DIM>::TI, TJ = MfTile<DIM>::TJ, TK = MfTile<DIM>::TK;
+    constexpr int HJ = TJ + 2, HK = (DIM == 3) ? TK + 2 : 1, HI = TI + 2, HALO = HI * HJ * HK;
+    static_assert(TI * TJ * TK == kThreads, "one thread per tile node");
+    __shared__ double sp[HALO * NDOF];
+    __shared__ int srow[HALO * NDOF];
+    const int n0 = G.n[0], n1 = G.n[1], n2 = G.n[2];
+    const int e1 = n1 - 1, e2 = (DIM == 3) ? n2 - 1 : 1;
+    const int tiles_i = (n0 + TI - 1) / TI, tiles_j = (n1 + TJ - 1) / TJ, tiles_k = (DIM == 3) ? (n2 + TK - 1) / TK : 1;
+    const int ntiles = tiles_i * tiles_j * tiles_k;
+    // this thread's node inside the tile and its centre slot in the halo box
+    const int tk = threadIdx.x % TK, tj = (threadIdx.x / TK) % TJ, ti = threadIdx.x / (TK * TJ);
+    const int hc = ((ti + 1) * HJ + (tj + 1)) * HK + ((DIM == 3) ? tk + 1 : 0);
     double dot = 0.0;
-    for (int nid = blockIdx.x * blockDim.x + threadIdx.x; nid < G.nnode; nid += gridDim.x * blockDim.x) {
-        int rows[NDOF];
-        bool any = false;
-#pragma unroll
-        for (int d = 0; d < NDOF; d++) { rows[d] = n2g[(size_t)nid * NDOF + d]; any |= (rows[d] != -1); }
-        if (!any) continue;
-        const int k = (DIM == 3) ? nid % n2 : 0;
-        const int j = (nid / n2) % n1;
-        const int i = nid / s0;
-        // p on the 3^DIM neighbouring nodes (0 outside the mesh and on fixed dofs)
-        double pn[NN][NDOF];
-#pragma unroll
-        for (int q = 0; q < NN; q++) {
-            const int di = q % 3 - 1, dj = (q / 3) % 3 - 1, dk = (DIM == 3) ? q / 9 - 1 : 0;
-            const bool in = (unsigned)(i + di) < (unsigned)G.n[0] && (unsigned)(j + dj) < (unsigned)n1 && (DIM == 2 || (unsigned)(k + dk) < (unsigned)n2);
-            const long long nb = (long long)nid + di * s0 + dj * s1 + dk;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int bk = tile % tiles_k, bj = (tile / tiles_k) % tiles_j, bi = tile / (tiles_k * tiles_j);
+        const int i0 = bi * TI, j0 = bj * TJ, k0 = bk * TK;
+        // phase 1: stage p (and the row numbers) of the tile + halo
+        for (int h = threadIdx.x; h < HALO; h += kThreads) {
+            const int hk = h % HK, hj = (h / HK) % HJ, hi = h / (HK * HJ);
+            const int gi = i0 - 1 + hi, gj = j0 - 1 + hj, gk = (DIM == 3) ? k0 - 1 + hk : 0;
+            const bool in = (unsigned)gi < (unsigned)n0 && (unsigned)gj < (unsigned)n1 && (unsigned)gk < (unsigned)n2;
+            const size_t nid = ((size_t)gi * n1 + gj) * n2 + gk;
 #pragma unroll
             for (int d = 0; d < NDOF; d++) {
-                const int r = in ? n2g[(size_t)nb * NDOF + d] : -1;
-                pn[q][d] = (r != -1) ? __ldg(x + r) : 0.0;
+                const int r = in ? n2g[nid * NDOF + d] : -1;
+                srow[h * NDOF + d] = r;
+                sp[h * NDOF + d] = (r != -1) ? x[r] : 0.0;
             }
         }
-        double acc[NDOF];
+        __syncthreads();
+        // phase 2
+        const int i = i0 + ti, j = j0 + tj, k = k0 + tk;
+        if (i < n0 && j < n1 && k < n2) {
+            double acc[NDOF];
 #pragma unroll
-        for (int d = 0; d < NDOF; d++) acc[d] = 0.0;
-        // this node is local node a of the element whose origin is (i - ox, j - oy, k - oz)
+            for (int d = 0; d < NDOF; d++) acc[d] = 0.0;
 #pragma unroll
-        for (int a = 0; a < NC; a++) {
-            int ox, oy, oz;
-            mf_corner(DIM, a, ox, oy, oz);
-            const int ei = i - ox, ej = j - oy, ek = k - oz;
-            const bool in = (unsigned)ei < (unsigned)(G.n[0] - 1) && (unsigned)ej < (unsigned)e1 && (DIM == 2 || (unsigned)ek < (unsigned)e2);
-            if (!in) continue;
-            const double Ee = E[((size_t)ei * e1 + ej) * e2 + ek];
-            double t[NDOF];
+            for (int a = 0; a < NC; a++) {
+                int ox, oy, oz;
+                mf_corner(DIM, a, ox, oy, oz);
+                const int ei = i - ox, ej = j - oy, ek = k - oz;
+                const bool in = (unsigned)ei < (unsigned)(n0 - 1) && (unsigned)ej < (unsigned)e1 && (DIM == 2 || (unsigned)ek < (unsigned)e2);
+                if (!in) continue;
+                const double Ee = __ldg(E + ((size_t)ei * e1 + ej) * e2 + ek);
+                double t[NDOF];
 #pragma unroll
-            for (int d = 0; d < NDOF; d++) t[d] = 0.0;
+                for (int d = 0; d < NDOF; d++) t[d] = 0.0;
 #pragma unroll
-            for (int b = 0; b < NC; b++) {
-                int bx, by, bz;
-                mf_corner(DIM, b, bx, by, bz);
-                const int q = (bx - ox + 1) + 3 * (by - oy + 1) + ((DIM == 3) ? 9 * (bz - oz + 1) : 0);
+                for (int b = 0; b < NC; b++) {
+                    int bx, by, bz;
+                    mf_corner(DIM, b, bx, by, bz);
+                    const int q = hc + ((bx - ox) * HJ + (by - oy)) * HK + ((DIM == 3) ? (bz - oz) : 0);
 #pragma unroll
-                for (int di = 0; di < NDOF; di++)
+                    for (int dj = 0; dj < NDOF; dj++) {
+                        const double pv = sp[q * NDOF + dj];
 #pragma unroll
-                    for (int dj = 0; dj < NDOF; dj++) t[di] += c_mf_ke0[(a * NDOF + di) * M + b * NDOF + dj] * pn[q][dj];
+                        for (int di = 0; di < NDOF; di++) t[di] += c_mf_ke0[(a * NDOF + di) * M + b * NDOF + dj] * pv;
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < NDOF; d++) acc[d] += Ee * t[d];
             }
 #pragma unroll
-            for (int d = 0; d < NDOF; d++) acc[d] += Ee * t[d];
+            for (int d = 0; d < NDOF; d++) {
+                const int r = srow[hc * NDOF + d];
+                if (r == -1) continue;
+                y[r] = acc[d];
+                if (DOT && r >= dot_lo && r < dot_hi) dot += acc[d] * sp[hc * NDOF + d];
+            }
         }
-#pragma unroll
-        for (int d = 0; d < NDOF; d++) {
-            const int r = rows[d];
-            if (r == -1) continue;
-            y[r] = acc[d];
-            if (DOT && r >= dot_lo && r < dot_hi) dot += acc[d] * pn[(NN - 1) / 2][d];      // centre entry = x[r]
-        }
+        __syncthreads();
     }
     if (DOT) {
         double vsum[1] = { dot };

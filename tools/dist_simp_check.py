@@ -34,7 +34,7 @@ else:
 ctx = capi.Context(local_rank)
 D = capi.Dist(ctx, rank, world)
 S = partition.slab(P, rank, world)
-sim = capi.Simp(ctx, S.local)
+sim = capi.Simp(ctx, S.local, matrix_free=("--matrix-free" in argv))
 D.set_simp_partition(sim, S, P.nelem)
 hist = []
 ctx.sync(); dist.barrier()
