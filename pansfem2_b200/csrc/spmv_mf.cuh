@@ -32,7 +32,7 @@ __device__ __forceinline__ void mf_corner(int dim, int a, int& ox, int& oy, int&
 // Tile of nodes one CTA owns per step (k fastest, like the numbering) and its one-node halo.
 template <int DIM> struct MfTile;
 template <> struct MfTile<2> { static constexpr int TI = 4, TJ = 64, TK = 1; };
-template <> struct MfTile<3> { static constexpr int TI = 4, TJ = 8, TK = 8; };
+template <> struct MfTile<3> { static constexpr int TI = 4, TJ = 4, TK = 16; };     // 16 consecutive k per half-warp: conflict-free LDS.64
 
 // One CTA = one tile of kThreads nodes.  Phase 1 stages p of the tile + halo in shared memory (ONE nodetoglobal lookup and one
 // gather per staged node instead of 3^dim per node); phase 2: one thread per node walks its 2^dim elements out of shared memory.
@@ -46,8 +46,8 @@ spmv_mf_kernel(MfGrid G, const int* __restrict__ n2g, const double* __restrict__
     constexpr int TI = MfTile<DIM>::TI, TJ = MfTile<DIM>::TJ, TK = MfTile<DIM>::TK;
     constexpr int HJ = TJ + 2, HK = (DIM == 3) ? TK + 2 : 1, HI = TI + 2, HALO = HI * HJ * HK;
     static_assert(TI * TJ * TK == kThreads, "one thread per tile node");
-    __shared__ double sp[HALO * NDOF];
-    __shared__ int srow[HALO * NDOF];
+    __shared__ double sp[NDOF][HALO];      // one plane per dof: a half-warp reads 16 consecutive doubles
+    __shared__ int srow[NDOF][HALO];
     const int n0 = G.n[0], n1 = G.n[1], n2 = G.n[2];
     const int e1 = n1 - 1, e2 = (DIM == 3) ? n2 - 1 : 1;
     const int tiles_i = (n0 + TI - 1) / TI, tiles_j = (n1 + TJ - 1) / TJ, tiles_k = (DIM == 3) ? (n2 + TK - 1) / TK : 1;
@@ -68,8 +68,8 @@ spmv_mf_kernel(MfGrid G, const int* __restrict__ n2g, const double* __restrict__
 #pragma unroll
             for (int d = 0; d < NDOF; d++) {
                 const int r = in ? n2g[nid * NDOF + d] : -1;
-                srow[h * NDOF + d] = r;
-                sp[h * NDOF + d] = (r != -1) ? x[r] : 0.0;
+                srow[d][h] = r;
+                sp[d][h] = (r != -1) ? x[r] : 0.0;
             }
         }
         __syncthreads();
@@ -97,7 +97,7 @@ spmv_mf_kernel(MfGrid G, const int* __restrict__ n2g, const double* __restrict__
                     const int q = hc + ((bx - ox) * HJ + (by - oy)) * HK + ((DIM == 3) ? (bz - oz) : 0);
 #pragma unroll
                     for (int dj = 0; dj < NDOF; dj++) {
-                        const double pv = sp[q * NDOF + dj];
+                        const double pv = sp[dj][q];
 #pragma unroll
                         for (int di = 0; di < NDOF; di++) t[di] += c_mf_ke0[(a * NDOF + di) * M + b * NDOF + dj] * pv;
                     }
@@ -107,10 +107,10 @@ spmv_mf_kernel(MfGrid G, const int* __restrict__ n2g, const double* __restrict__
             }
 #pragma unroll
             for (int d = 0; d < NDOF; d++) {
-                const int r = srow[hc * NDOF + d];
+                const int r = srow[d][hc];
                 if (r == -1) continue;
                 y[r] = acc[d];
-                if (DOT && r >= dot_lo && r < dot_hi) dot += acc[d] * sp[hc * NDOF + d];
+                if (DOT && r >= dot_lo && r < dot_hi) dot += acc[d] * sp[d][hc];
             }
         }
         __syncthreads();
