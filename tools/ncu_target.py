@@ -15,6 +15,8 @@ if "--itr" in args:
     i = args.index("--itr")
     itr = int(args[i + 1])
     args = args[:i] + args[i + 2:]
+mf = "--matrix-free" in args
+args = [a for a in args if a != "--matrix-free"]
 kind = args[0] if args else "2d"
 dims = [int(a) for a in args[1:]]
 if kind == "2d":
@@ -24,7 +26,7 @@ elif kind == "heat":
 else:
     P = problems.cantilever3d(*(dims or [96, 48, 48]))
 ctx = capi.Context(0)
-S = capi.Simp(ctx, P)
+S = capi.Simp(ctx, P, matrix_free=mf)
 rho = ctx.array(np.full(P.nelem, 0.5))
 S.A.assemble(S.mesh, S.dofmap, P.eq, (P.E0, P.E1, P.poisson, P.penal, P.thickness), P.loads, rho=rho)
 x = ctx.empty(S.A.rows)
