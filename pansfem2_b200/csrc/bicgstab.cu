@@ -188,6 +188,7 @@ static int ensure_bi_workspace(pf2_csr* A) {
     const size_t np = (((size_t)A->rows) + 31) & ~(size_t)31;
     PF2_TRY(dev_alloc(&A->bi_slab, 12 * np));
     PF2_TRY(dev_alloc((BiState**)&A->bi_st, 1));
+    PF2_CUDA(cudaMemset(A->bi_st, 0, sizeof(BiState)));
     PF2_CUDA(cudaHostAlloc((void**)&A->bi_hst, 2 * sizeof(BiState), cudaHostAllocDefault));
     if (!A->bi_ev[0]) {
         PF2_CUDA(cudaEventCreateWithFlags(&A->bi_ev[0], cudaEventDisableTiming));

@@ -201,6 +201,7 @@ static int ensure_workspace(pf2_csr* A) {
     PF2_TRY(dev_alloc(&A->slab, 5 * np));
     A->r = A->slab; A->p = A->slab + np; A->z = A->slab + 2 * np; A->y = A->slab + 3 * np; A->dvec = A->slab + 4 * np;
     PF2_TRY(dev_alloc(&A->st, 1));
+    PF2_CUDA(cudaMemset(A->st, 0, sizeof(CgState)));      // red[] / pad are only written by the partitioned path; keep the D2H poll copies clean
     for (int i = 0; i < 2; i++) for (int j = 0; j < 4; j++) PF2_CUDA(cudaEventCreate(&A->pev[i][j]));
     PF2_CUDA(cudaHostAlloc((void**)&A->h_st, 2 * sizeof(CgState), cudaHostAllocDefault));
     PF2_CUDA(cudaEventCreateWithFlags(&A->ev[0], cudaEventDisableTiming));

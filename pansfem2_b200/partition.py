@@ -68,6 +68,7 @@ def slab_from_factory(factory, grid, ndof, rank: int, nranks: int) -> Slab:
 
 def _finish(local, n2g, rank, nranks, e0, e1, le0, le1, on0, on1, plane_e, plane_n, global_rows) -> Slab:
     def rows_of_planes(p0, p1):
+        """local row range [lo, hi) of node planes [p0, p1) (global plane indices); an empty range sits where it would start"""
         a, b = (p0 - le0) * plane_n, (p1 - le0) * plane_n
         blk = n2g[a:b].ravel()
         blk = blk[blk >= 0]
@@ -107,7 +108,6 @@ def slab(P: problems.Problem, rank: int, nranks: int) -> Slab:
     fixed = ((fn[keep] - node_lo).astype(np.int32), np.asarray(P.fixed[1])[keep].astype(np.int32), np.asarray(P.fixed[2])[keep])
     # owned node planes
     on0, on1 = e0, (e1 if rank < nranks - 1 else nx + 1)
-    own_node_lo, own_node_hi = (on0 - le0) * plane_n, (on1 - le0) * plane_n
     # loads only on owned nodes (each load is applied exactly once)
     ln = np.asarray(P.loads[0], np.int64)
     keep = (ln >= on0 * plane_n) & (ln < on1 * plane_n)
@@ -122,39 +122,14 @@ def slab(P: problems.Problem, rank: int, nranks: int) -> Slab:
     local = problems.Problem(f"{P.name}_slab{rank}of{nranks}", P.eq, coords, conn, fixed, loads, nbrs, lgrid,
                              filter_kind=P.filter_kind, opt_kind=P.opt_kind, E0=P.E0, E1=P.E1, poisson=P.poisson, penal=P.penal,
                              weightlimit=P.weightlimit, scale0=P.scale0, scale1=P.scale1, thickness=P.thickness, beta0=P.beta0,
-                             beta_period=P.beta_period, cg_itrmax=P.cg_itrmax, cg_eps=P.cg_eps, oc=P.oc, mma=P.mma, s0=P.s0)
+                             beta_period=P.beta_period, cg_itrmax=P.cg_itrmax, cg_eps=P.cg_eps, oc=P.oc, mma=P.mma, conlin=P.conlin, s0=P.s0)
     n2g = _dofmap(coords.shape[0], ndof, fixed)
-
-    def rows_of_planes(p0, p1):
-        """local row range [lo, hi) of node planes [p0, p1) (global plane indices)."""
-        a, b = (p0 - le0) * plane_n, (p1 - le0) * plane_n
-        blk = n2g[a:b].ravel()
-        blk = blk[blk >= 0]
-        if blk.size == 0:
-            # no free dof on these planes: empty range placed where it would start
-            before = n2g[:a].ravel()
-            k = int((before >= 0).sum())
-            return k, k
-        return int(blk.min()), int(blk.max()) + 1
-
-    own_lo, own_hi = rows_of_planes(on0, on1)
-    sendL = recvL = sendR = recvR = (0, 0)
-    if rank > 0:
-        sendL, recvL = rows_of_planes(e0, e0 + 1), rows_of_planes(e0 - 1, e0)
-    if rank < nranks - 1:
-        sendR, recvR = rows_of_planes(e1 - 1, e1), rows_of_planes(e1, e1 + 1)
-    row_halo = (sendL[0], recvL[0], sendL[1] - sendL[0], sendR[0], recvR[0], sendR[1] - sendR[0])
-    # element halos: my first / last owned element plane <-> the neighbour's ghost plane
-    el = lambda p: (p - le0) * plane_e
-    elem_halo = (el(e0), el(e0 - 1) if rank > 0 else 0, plane_e if rank > 0 else 0,
-                 el(e1 - 1), el(e1) if rank < nranks - 1 else 0, plane_e if rank < nranks - 1 else 0)
     # global position of the owned rows
     gn2g = _dofmap(P.nnode, ndof, P.fixed)
     gblk = gn2g[on0 * plane_n:on1 * plane_n].ravel()
     gblk = gblk[gblk >= 0]
     global_rows = (int(gblk.min()), int(gblk.max()) + 1) if gblk.size else (0, 0)
-    return Slab(rank, nranks, local, e0, e1, le0, le1, (own_lo, own_hi), row_halo, (el(e0), el(e1)), elem_halo,
-                (own_node_lo, own_node_hi), global_rows, n2g.astype(np.int32))
+    return _finish(local, n2g, rank, nranks, e0, e1, le0, le1, on0, on1, plane_e, plane_n, global_rows)
 
 
 # ------------------------------------------------------------------------------------------------------------------
