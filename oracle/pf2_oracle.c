@@ -891,7 +891,7 @@ void orc_mma_update(orc_mma* M, double* xk, const double* dfdx, const double* gv
             U[j] = min2(max2(xk[j] + 0.01 * w, U[j]), xk[j] + 10.0 * w);
         }
     }
-#define VEC(name, cnt) double* name = (double*)calloc((size_t)(cnt), sizeof(double))
+#define VEC(name, cnt) double* name = (double*)calloc((cnt) > 0 ? (size_t)(cnt) : 1, sizeof(double))
     VEC(alpha, n); VEC(beta, n); VEC(p0, n); VEC(q0, n); VEC(p, (size_t)m * n); VEC(q, (size_t)m * n); VEC(b, m);
     for (int j = 0; j < n; j++) {   /* MMA.h:145-160 */
         double w = M->xmax[j] - M->xmin[j];
