@@ -157,7 +157,8 @@ static void plan_spmv(pf2_csr* A) {
     // Measured inside the PCG loop on B200 (tools/cg_sweep.py, profiles/r01_cg_sweep_*.json): the SELL-32 thread-per-row
     // kernel wins whenever padding is small (FEM rows are near-uniform); otherwise the sub-warp CSR kernel with 2-3
     // nonzeros per lane.  The shared-memory stream and TMA-pipeline kernels stay selectable (11-15, 21-26).
-    if (A->rows >= 64 && sell_build(A) == PF2_OK && (double)A->sell_entries <= 1.15 * (double)A->nnz) { A->spmv_variant = 31; return; }
+    // (thread-per-row slices stop paying once rows are long: hex20 rows average 166 nonzeros and the warp-per-row CSR kernel wins)
+    if (A->rows >= 64 && mean <= 96.0 && sell_build(A) == PF2_OK && (double)A->sell_entries <= 1.15 * (double)A->nnz) { A->spmv_variant = 31; return; }
     A->spmv_variant = mean <= 4 ? 1 : mean <= 10 ? 2 : mean <= 24 ? 3 : mean <= 48 ? 4 : 5;
 }
 
@@ -181,27 +182,57 @@ static int launch_tma(pf2_csr* A, const double* x, double* y, const CgState* st,
     return PF2_OK;
 }
 
-static int sell_build(pf2_csr* A) {
-    if (A->sell_ptr) return PF2_OK;
+// slice pointers for the current slot->row map; returns the number of stored entries
+static int sell_slices(pf2_csr* A, int nslices, long long* entries) {
     pf2_ctx* c = A->ctx;
-    const int nslices = (A->rows + kSellC - 1) / kSellC;
-    PF2_TRY(dev_alloc(&A->sell_ptr, (size_t)nslices + 1));
-    sell_slice_len_kernel<<<c->grid_for(nslices), kThreads, 0, c->stream>>>(A->rows, nslices, A->indptr, A->sell_ptr);
+    sell_slice_len_kernel<<<c->grid_for(nslices), kThreads, 0, c->stream>>>(A->rows, nslices, A->indptr, A->sell_perm, A->sell_ptr);
     PF2_LAUNCH_CHECK();
     void* tmp = nullptr;
     size_t bytes = 0;
     PF2_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, A->sell_ptr, A->sell_ptr, nslices + 1, c->stream));
     PF2_CUDA(cudaMalloc(&tmp, bytes ? bytes : 8));
     PF2_CUDA(cub::DeviceScan::InclusiveSum(tmp, bytes, A->sell_ptr, A->sell_ptr, nslices + 1, c->stream));
-    PF2_CUDA(cudaMemcpyAsync(&A->sell_entries, A->sell_ptr + nslices, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    PF2_CUDA(cudaMemcpyAsync(entries, A->sell_ptr + nslices, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     PF2_CUDA(cudaStreamSynchronize(c->stream));
     PF2_CUDA(cudaFree(tmp));
+    c->launches += 2;
+    return PF2_OK;
+}
+
+static int sell_build(pf2_csr* A) {
+    if (A->sell_ptr) return PF2_OK;
+    pf2_ctx* c = A->ctx;
+    const int nslices = (A->rows + kSellC - 1) / kSellC;
+    const int slots = nslices * kSellC;
+    PF2_TRY(dev_alloc(&A->sell_ptr, (size_t)nslices + 1));
+    PF2_TRY(sell_slices(A, nslices, &A->sell_entries));
+    if ((double)A->sell_entries > 1.03 * (double)A->nnz) {
+        // ragged rows: sort by length inside windows of kSellSigma rows (SELL-C-sigma) and cut the slices from the sorted order
+        unsigned long long *k0 = nullptr, *k1 = nullptr;
+        int *v0 = nullptr;
+        PF2_TRY(dev_alloc(&k0, (size_t)A->rows)); PF2_TRY(dev_alloc(&k1, (size_t)A->rows)); PF2_TRY(dev_alloc(&v0, (size_t)A->rows));
+        PF2_TRY(dev_alloc(&A->sell_perm, (size_t)slots));
+        sell_sort_keys_kernel<<<c->grid_for(A->rows), kThreads, 0, c->stream>>>(A->rows, A->indptr, k0, v0);
+        void* tmp = nullptr;
+        size_t bytes = 0;
+        PF2_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k0, k1, v0, A->sell_perm, A->rows, 0, 64, c->stream));
+        PF2_CUDA(cudaMalloc(&tmp, bytes ? bytes : 8));
+        PF2_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, k0, k1, v0, A->sell_perm, A->rows, 0, 64, c->stream));
+        sell_perm_tail_kernel<<<1, kThreads, 0, c->stream>>>(A->rows, slots, A->sell_perm);
+        PF2_LAUNCH_CHECK();
+        PF2_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(tmp); cudaFree(k0); cudaFree(k1); cudaFree(v0);
+        c->launches += 3;
+        long long sorted_entries = 0;
+        PF2_TRY(sell_slices(A, nslices, &sorted_entries));
+        A->sell_entries = sorted_entries;
+    }
     PF2_TRY(dev_alloc(&A->sell_idx, (size_t)A->sell_entries));
     PF2_TRY(dev_alloc(&A->sell_val, (size_t)A->sell_entries));
     int* d_md = nullptr;
     PF2_TRY(dev_alloc(&d_md, 1));
     PF2_CUDA(cudaMemsetAsync(d_md, 0, sizeof(int), c->stream));
-    sell_fill_kernel<<<c->grid_for(A->rows), kThreads, 0, c->stream>>>(A->rows, A->indptr, A->indices, A->sell_ptr, A->sell_idx, d_md);
+    sell_fill_kernel<<<c->grid_for(slots), kThreads, 0, c->stream>>>(A->rows, slots, A->indptr, A->indices, A->sell_perm, A->sell_ptr, A->sell_idx, d_md);
     PF2_LAUNCH_CHECK();
     int md = 0;
     PF2_CUDA(cudaMemcpyAsync(&md, d_md, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -211,13 +242,13 @@ static int sell_build(pf2_csr* A) {
     if (md <= 32767) {
         // banded matrix: keep the 2-byte delta stream and drop the 4-byte one (the absolute columns are recoverable)
         PF2_TRY(dev_alloc(&A->sell_d16, (size_t)A->sell_entries));
-        sell_delta16_kernel<<<std::min((nslices + 7) / 8, c->sm_count * 16), kThreads, 0, c->stream>>>(A->rows, A->sell_entries, A->sell_ptr, A->sell_idx, A->sell_d16);
+        sell_delta16_kernel<<<std::min((nslices + 7) / 8, c->sm_count * 16), kThreads, 0, c->stream>>>(A->rows, A->sell_entries, A->sell_ptr, A->sell_perm, A->sell_idx, A->sell_d16);
         PF2_LAUNCH_CHECK();
         PF2_CUDA(cudaStreamSynchronize(c->stream));
         PF2_CUDA(cudaFree(A->sell_idx));
         A->sell_idx = nullptr;
     }
-    c->launches += 5;
+    c->launches += 2;
     A->sell_values_valid = false;
     return PF2_OK;
 }
@@ -226,7 +257,7 @@ int sell_refresh(pf2_csr* A) {
     PF2_TRY(sell_build(A));
     pf2_ctx* c = A->ctx;
     const int nslices = (A->rows + kSellC - 1) / kSellC;
-    sell_values_kernel<<<std::min((nslices + 7) / 8, c->sm_count * 16), kThreads, 0, c->stream>>>(A->rows, A->indptr, A->data, A->sell_ptr, A->sell_val);
+    sell_values_kernel<<<std::min((nslices + 7) / 8, c->sm_count * 16), kThreads, 0, c->stream>>>(A->rows, A->indptr, A->data, A->sell_perm, A->sell_ptr, A->sell_val);
     sell_pad_tail_kernel<<<1, kThreads, 0, c->stream>>>(A->rows, nslices, A->sell_ptr, A->sell_idx, A->sell_val);   // sell_idx may be null (delta form)
     PF2_LAUNCH_CHECK();
     c->launches += 2;
@@ -240,15 +271,16 @@ static int launch_sell(pf2_csr* A, const double* x, double* y, const CgState* st
     if (!A->sell_values_valid) PF2_TRY(sell_refresh(A));
     const int nslices = (A->rows + kSellC - 1) / kSellC;
     const int nb = (nslices + (kThreads / 32) - 1) / (kThreads / 32);
-    if (A->sell_d16) {
-        const int grid = std::max(1, std::min(nb, c->wave_grid((const void*)spmv_sell_kernel<DOT, short>, kThreads)));
-        spmv_sell_kernel<DOT, short><<<grid, kThreads, 0, c->stream>>>(A->rows, A->sell_ptr, A->sell_d16, A->sell_val, x, y, st, dot_out,
-                                                                     c->red.partials, c->red.ticket, A->own_lo, A->own_hi, A->p2p_dev, A->p2p_epoch);
-    } else {
-        const int grid = std::max(1, std::min(nb, c->wave_grid((const void*)spmv_sell_kernel<DOT, int>, kThreads)));
-        spmv_sell_kernel<DOT, int><<<grid, kThreads, 0, c->stream>>>(A->rows, A->sell_ptr, A->sell_idx, A->sell_val, x, y, st, dot_out,
-                                                                   c->red.partials, c->red.ticket, A->own_lo, A->own_hi, A->p2p_dev, A->p2p_epoch);
+#define SELL(IDXT, PERMV, IDXPTR)                                                                                                          \
+    {                                                                                                                                      \
+        const int grid = std::max(1, std::min(nb, c->wave_grid((const void*)spmv_sell_kernel<DOT, IDXT, PERMV>, kThreads)));                  \
+        spmv_sell_kernel<DOT, IDXT, PERMV><<<grid, kThreads, 0, c->stream>>>(A->rows, A->sell_ptr, A->sell_perm, IDXPTR, A->sell_val, x, y, st, \
+                                                                             dot_out, c->red.partials, c->red.ticket, A->own_lo, A->own_hi,   \
+                                                                             A->p2p_dev, A->p2p_epoch);                                       \
     }
+    if (A->sell_d16) { if (A->sell_perm) SELL(short, true, A->sell_d16) else SELL(short, false, A->sell_d16) }
+    else { if (A->sell_perm) SELL(int, true, A->sell_idx) else SELL(int, false, A->sell_idx) }
+#undef SELL
     return PF2_OK;
 }
 
@@ -417,7 +449,7 @@ int pf2_csr_destroy(pf2_csr* A) {
     if (!A) return PF2_OK;
     cudaSetDevice(A->ctx->device);
     cudaStreamSynchronize(A->ctx->stream);
-    void* ptrs[] = { A->indptr, A->indices, A->data, A->F, A->diagpos, A->bmap, A->slab, A->xw, A->bw, A->st, A->sell_ptr, A->sell_idx, A->sell_d16, A->sell_val, A->p2p_dev,
+    void* ptrs[] = { A->indptr, A->indices, A->data, A->F, A->diagpos, A->bmap, A->slab, A->xw, A->bw, A->st, A->sell_ptr, A->sell_perm, A->sell_idx, A->sell_d16, A->sell_val, A->p2p_dev,
                      A->ilu, A->level_rows, A->level_rows_u };
     for (void* p : ptrs) if (p) cudaFree(p);
     if (A->h_st) cudaFreeHost(A->h_st);

@@ -10,6 +10,9 @@
 // CSR stays the canonical storage (assembly, download, ILU0): sell_val is refreshed from CSR data before a solve
 // (one 16 B/nnz pass, < 0.1 % of a solve).  Algorithmic bytes stay 12*nnz + 24*rows; the stored entries are
 // sell_entries >= nnz (ratio reported as `sell_fill`).
+// Ragged matrices (T6 / Q8 / hex20 meshes: corner and mid-side nodes have different row lengths) use SELL-C-sigma: inside
+// windows of kSellSigma rows the rows are sorted by length before being cut into slices, `sell_perm[slot]` names the row a lane
+// owns (-1 = padding lane).  Column deltas stay relative to the lane's own row, so the 2-byte index stream survives.
 #pragma once
 #include "types.cuh"
 #include "p2p.cuh"
@@ -17,22 +20,42 @@
 namespace pf2 {
 
 constexpr int kSellC = 32;
+constexpr int kSellSigma = 1024;     // sorting window (rows): small enough that a slice's rows stay neighbours in the mesh
 
-__global__ void sell_slice_len_kernel(int rows, int nslices, const long long* __restrict__ indptr, long long* __restrict__ slice_ptr) {
+// row owned by slot `slot` (slice * 32 + lane): natural order, or the length-sorted permutation; -1 = padding lane
+__device__ __forceinline__ int sell_row(const int* __restrict__ perm, int rows, int slot) {
+    if (perm) return perm[slot];
+    return slot < rows ? slot : -1;
+}
+// sort key of row r: window | (65535 - length) | position in window  -> descending length inside each window, stable
+__global__ void sell_sort_keys_kernel(int rows, const long long* __restrict__ indptr, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+        const unsigned long long len = (unsigned long long)min((long long)65535, indptr[r + 1] - indptr[r]);
+        keys[r] = ((unsigned long long)(r / kSellSigma) << 32) | ((65535ull - len) << 12) | (unsigned long long)(r % kSellSigma);
+        vals[r] = r;
+    }
+}
+__global__ void sell_perm_tail_kernel(int rows, int slots, int* __restrict__ perm) {
+    for (int i = rows + blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += gridDim.x * blockDim.x) perm[i] = -1;
+}
+
+__global__ void sell_slice_len_kernel(int rows, int nslices, const long long* __restrict__ indptr, const int* __restrict__ perm, long long* __restrict__ slice_ptr) {
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nslices; s += gridDim.x * blockDim.x) {
         int m = 0;
-        for (int r = s * kSellC; r < min(rows, (s + 1) * kSellC); r++) m = max(m, (int)(indptr[r + 1] - indptr[r]));
+        for (int l = 0; l < kSellC; l++) { const int r = sell_row(perm, rows, s * kSellC + l); if (r >= 0) m = max(m, (int)(indptr[r + 1] - indptr[r])); }
         slice_ptr[s + 1] = (long long)m * kSellC;
         if (s == 0) slice_ptr[0] = 0;
     }
 }
 
 // fill indices (pattern) and the CSR->SELL position of every stored entry
-__global__ void sell_fill_kernel(int rows, const long long* __restrict__ indptr, const int* __restrict__ indices,
+__global__ void sell_fill_kernel(int rows, int slots, const long long* __restrict__ indptr, const int* __restrict__ indices, const int* __restrict__ perm,
                                  const long long* __restrict__ slice_ptr, int* __restrict__ sell_idx, int* max_delta) {
     int md = 0;
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
-        const int s = r / kSellC, l = r % kSellC;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < slots; slot += gridDim.x * blockDim.x) {
+        const int r = sell_row(perm, rows, slot);
+        if (r < 0) continue;
+        const int s = slot / kSellC, l = slot % kSellC;
         const long long base = slice_ptr[s];
         const int width = (int)((slice_ptr[s + 1] - base) / kSellC);
         const long long b = indptr[r];
@@ -47,22 +70,22 @@ __global__ void sell_fill_kernel(int rows, const long long* __restrict__ indptr,
     if ((threadIdx.x & 31) == 0) atomicMax(max_delta, md);
 }
 // 16-bit column deltas (col - row): FEM matrices are banded, so the index stream shrinks from 4 to 2 bytes per nonzero
-__global__ void sell_delta16_kernel(int rows, long long entries, const long long* __restrict__ slice_ptr, const int* __restrict__ sell_idx,
-                                    short* __restrict__ sell_d16) {
+__global__ void sell_delta16_kernel(int rows, long long entries, const long long* __restrict__ slice_ptr, const int* __restrict__ perm,
+                                    const int* __restrict__ sell_idx, short* __restrict__ sell_d16) {
     const int nslices = (rows + kSellC - 1) / kSellC;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int s = warp; s < nslices; s += nwarps) {
         const long long base = slice_ptr[s];
         const int width = (int)((slice_ptr[s + 1] - base) / kSellC);
-        const int r = s * kSellC + lane;
+        const int r = sell_row(perm, rows, s * kSellC + lane);
         for (int k = 0; k < width; k++) {
             const long long pos = base + (long long)k * kSellC + lane;
-            sell_d16[pos] = (r < rows) ? (short)(sell_idx[pos] - r) : (short)0;
+            sell_d16[pos] = (r >= 0) ? (short)(sell_idx[pos] - r) : (short)0;
         }
     }
 }
-// padding lanes of the last slice (rows beyond `rows`)
+// padding lanes of the last slice (slots beyond `rows`; with a permutation they are the last slots too)
 __global__ void sell_pad_tail_kernel(int rows, int nslices, const long long* __restrict__ slice_ptr, int* __restrict__ sell_idx, double* __restrict__ sell_val) {
     const int s = nslices - 1;
     const long long base = slice_ptr[s];
@@ -72,27 +95,27 @@ __global__ void sell_pad_tail_kernel(int rows, int nslices, const long long* __r
         if (s * kSellC + l >= rows) { if (sell_idx) sell_idx[base + t] = 0; sell_val[base + t] = 0.0; }
     }
 }
-__global__ void sell_values_kernel(int rows, const long long* __restrict__ indptr, const double* __restrict__ data,
+__global__ void sell_values_kernel(int rows, const long long* __restrict__ indptr, const double* __restrict__ data, const int* __restrict__ perm,
                                    const long long* __restrict__ slice_ptr, double* __restrict__ sell_val) {
     // one warp per slice: lane l copies row l; reads are strided (row-contiguous), writes coalesced
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int nslices = (rows + kSellC - 1) / kSellC;
     for (int s = warp; s < nslices; s += nwarps) {
-        const int r = s * kSellC + lane;
+        const int r = sell_row(perm, rows, s * kSellC + lane);
         const long long base = slice_ptr[s];
         const int width = (int)((slice_ptr[s + 1] - base) / kSellC);
         long long b = 0;
         int len = 0;
-        if (r < rows) { b = indptr[r]; len = (int)(indptr[r + 1] - b); }
+        if (r >= 0) { b = indptr[r]; len = (int)(indptr[r + 1] - b); }
         for (int k = 0; k < width; k++) sell_val[base + (long long)k * kSellC + lane] = (k < len) ? data[b + k] : 0.0;
     }
 }
 
 // IDX = int: absolute columns (4 B/nnz); IDX = short: column - row deltas (2 B/nnz)
-template <bool DOT, class IDX>
+template <bool DOT, class IDX, bool PERM = false>
 __global__ void __launch_bounds__(kThreads)
-spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const IDX* __restrict__ sell_idx, const double* __restrict__ sell_val,
+spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* __restrict__ perm, const IDX* __restrict__ sell_idx, const double* __restrict__ sell_val,
                  const double* __restrict__ x, double* __restrict__ y, const CgState* __restrict__ st, double* dot_out,
                  double* partials, unsigned int* ticket, int dot_lo, int dot_hi, const P2PView* p2p, unsigned long long* p2p_epoch) {
     if (DOT && st != nullptr && st->done) return;
@@ -106,8 +129,8 @@ spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const IDX* _
         const int width = (int)((slice_ptr[s + 1] - base) / kSellC);
         const double* v = sell_val + base + lane;
         const IDX* c = sell_idx + base + lane;
-        const int r = s * kSellC + lane;
-        const int off = (sizeof(IDX) == 2) ? min(r, rows - 1) : 0;     // deltas are relative to the row (padding lanes: delta 0)
+        const int r = PERM ? perm[s * kSellC + lane] : ((s * kSellC + lane < rows) ? s * kSellC + lane : -1);
+        const int off = (sizeof(IDX) == 2) ? max(r, 0) : 0;            // deltas are relative to the lane's row (padding lanes: delta 0, value 0)
         double acc = 0.0;
         int k = 0;
         for (; k + 6 <= width; k += 6) {
@@ -119,7 +142,7 @@ spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const IDX* _
             for (int u = 0; u < 6; u++) acc += vv[u] * __ldg(x + cc[u]);
         }
         for (; k < width; k++) acc += __ldcs(v + k * kSellC) * __ldg(x + off + (int)__ldcs(c + k * kSellC));
-        if (r < rows) {
+        if (r >= 0) {
             y[r] = acc;
             if (DOT && r >= dot_lo && r < dot_hi) dot += acc * x[r];
         }

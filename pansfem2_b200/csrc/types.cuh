@@ -91,6 +91,7 @@ struct pf2_csr {
     int tma_stages = 3, tma_ctas_per_sm = 4;   // TMA pipeline depth and residency target
     // SELL-32 mirror (variant 31): slice pointers, column-major indices / values, stored entries
     long long* sell_ptr = nullptr;
+    int* sell_perm = nullptr;      // SELL-C-sigma: row of every slot (slice*32 + lane), -1 = padding; null = natural order
     int* sell_idx = nullptr;       // absolute columns (dropped when the 16-bit delta form is usable)
     short* sell_d16 = nullptr;     // column - row, 2 bytes per stored entry (|delta| <= 32767)
     int sell_max_delta = 0;
