@@ -42,12 +42,16 @@ enum { PF2_EQ_PLANESTRAIN = 0, PF2_EQ_SOLID = 1, PF2_EQ_HEAT = 2 };
  *             quad = ICD, the deviatoric rule, quad2 = ICV, the volumetric rule), and the scalar consistent mass matrix
  *             E * N N^T * t of ReactionDiffusionConsistentMass (ReactionDiffusion.h:21; E = 1, t = 1) and HeatCapacity
  *             (HeatTransfer.h:48; E = rho*c).  ReactionDiffusionStiffness (ReactionDiffusion.h:82) is PF2_PHYS_HEAT with E = D, t = 1.
+ *             PlaneStrainStiffnessBbar (PlaneStrain.h:129; quad = ICD, quad2 = ICV like SRI) and the 2-dof consistent mass
+ *             E * N^T N * t of PlaneStrainMass / PlaneStressMass (PlaneStrain.h:386, PlaneStress.h:63; E = rho), and
+ *             PlaneStrainStiffnessWilsonTaylor (PlaneStrain.h:189; quadrilaterals, Gauss4Square or Gauss9Square).
  *   shape   : ShapeFunction3Triangle / 6Triangle / 4Square / 8Square / 4Tetrahedron / 8Cubic / 20Cubic (ShapeFunction.h)
  *   quad    : Gauss1Triangle / 3Triangle / 1Square / 4Square / 9Square / 1Tetrahedron / 8Cubic / 27Cubic (GaussIntegration.h)
  * 0 in a field means "the default of that physics" (Q4 + Gauss4Square, hex8 + Gauss8Cubic; SRI: Gauss4Square / Gauss1Square),
  * so the legacy values 0, 1, 2 are themselves valid codes.  The rule must belong to the shape's reference domain
  * (triangle, square, tetrahedron, cube), otherwise PF2_E_INVALID. */
-enum { PF2_PHYS_PLANESTRAIN = 0, PF2_PHYS_SOLID = 1, PF2_PHYS_HEAT = 2, PF2_PHYS_PLANESTRESS = 3, PF2_PHYS_PLANESTRAIN_SRI = 4, PF2_PHYS_MASS = 5 };
+enum { PF2_PHYS_PLANESTRAIN = 0, PF2_PHYS_SOLID = 1, PF2_PHYS_HEAT = 2, PF2_PHYS_PLANESTRESS = 3, PF2_PHYS_PLANESTRAIN_SRI = 4, PF2_PHYS_MASS = 5,
+       PF2_PHYS_PLANESTRAIN_BBAR = 6, PF2_PHYS_MASS2 = 7, PF2_PHYS_PLANESTRAIN_WT = 8 };
 enum { PF2_SHAPE_DEFAULT = 0, PF2_SHAPE_T3 = 1, PF2_SHAPE_T6 = 2, PF2_SHAPE_Q4 = 3, PF2_SHAPE_Q8 = 4, PF2_SHAPE_TET4 = 5,
        PF2_SHAPE_HEX8 = 6, PF2_SHAPE_HEX20 = 7 };
 enum { PF2_QUAD_DEFAULT = 0, PF2_QUAD_G1TRI = 1, PF2_QUAD_G3TRI = 2, PF2_QUAD_G1SQ = 3, PF2_QUAD_G4SQ = 4, PF2_QUAD_G9SQ = 5,

@@ -48,7 +48,7 @@ void orc_set_num_threads(int n) {
 
 /* eq codes of include/pansfem2_b200.h (PF2_EQ_CODE): phys | shape << 8 | quad << 16 | quad2 << 24; a zero field is the
  * default of the physics, so the legacy values 0, 1, 2 are codes too. */
-enum { PHYS_PLANESTRAIN = 0, PHYS_SOLID = 1, PHYS_HEAT = 2, PHYS_PLANESTRESS = 3, PHYS_PLANESTRAIN_SRI = 4, PHYS_MASS = 5 };
+enum { PHYS_PLANESTRAIN = 0, PHYS_SOLID = 1, PHYS_HEAT = 2, PHYS_PLANESTRESS = 3, PHYS_PLANESTRAIN_SRI = 4, PHYS_MASS = 5, PHYS_PLANESTRAIN_BBAR = 6, PHYS_MASS2 = 7, PHYS_PLANESTRAIN_WT = 8 };
 enum { SHAPE_T3 = 1, SHAPE_T6, SHAPE_Q4, SHAPE_Q8, SHAPE_TET4, SHAPE_HEX8, SHAPE_HEX20 };
 enum { QUAD_G1TRI = 1, QUAD_G3TRI, QUAD_G1SQ, QUAD_G4SQ, QUAD_G9SQ, QUAD_G1TET, QUAD_G8CUBE, QUAD_G27CUBE };
 typedef struct { int phys, shape, quad, quad2; } orc_sel;
@@ -58,7 +58,7 @@ static orc_sel decode_eq(int eq) {
     if (!s.shape) s.shape = solid ? SHAPE_HEX8 : SHAPE_Q4;
     int tri = s.shape == SHAPE_T3 || s.shape == SHAPE_T6;
     if (!s.quad) s.quad = tri ? QUAD_G1TRI : (s.shape == SHAPE_TET4 ? QUAD_G1TET : (solid ? QUAD_G8CUBE : QUAD_G4SQ));
-    if (s.phys == PHYS_PLANESTRAIN_SRI && !s.quad2) s.quad2 = tri ? QUAD_G1TRI : QUAD_G1SQ;
+    if ((s.phys == PHYS_PLANESTRAIN_SRI || s.phys == PHYS_PLANESTRAIN_BBAR) && !s.quad2) s.quad2 = tri ? QUAD_G1TRI : QUAD_G1SQ;
     return s;
 }
 static int ndof_of(int eq) { int phys = eq & 0xff; return phys == PHYS_SOLID ? 3 : ((phys == PHYS_HEAT || phys == PHYS_MASS) ? 1 : 2); }
@@ -244,6 +244,74 @@ static void inv_d(int d, const double* v, double* inv) {
     for (int i = 0; i < d * d; i++) inv[i] /= det;
 }
 
+/* Matrix<T>::Determinant for n > 3 (Laplace expansion along column 0, Matrix.h:336-341) and Inverse = adjugate / det (:346-360) */
+static double det_n(int n, const double* v) {
+    if (n <= 3) return (n == 1) ? v[0] : det_d(n, v);
+    double value = 0.0, minor[9];
+    for (int i = 0; i < n; i++) {
+        int c = 0;
+        for (int a = 0; a < n; a++) { if (a == i) continue; for (int b = 1; b < n; b++) minor[c++] = v[a * n + b]; }
+        value += (((i & 1) ? -1.0 : 1.0)) * v[i * n] * det_n(n - 1, minor);
+    }
+    return value;
+}
+static void inv4(const double* v, double* inv) {
+    double minor[9];
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) {
+            int c = 0;      /* Cofactor(j, i): drop row j, column i */
+            for (int a = 0; a < 4; a++) { if (a == j) continue; for (int b = 0; b < 4; b++) { if (b == i) continue; minor[c++] = v[a * 4 + b]; } }
+            inv[i * 4 + j] = ((((i + j) & 1) ? -1.0 : 1.0)) * det_d(3, minor);
+        }
+    const double det = det_n(4, v);
+    for (int i = 0; i < 16; i++) inv[i] /= det;
+}
+
+/* PlaneStrainStiffnessWilsonTaylor  src/FEM/Equation/PlaneStrain.h:189-243: incompatible modes P = (1 - r0^2, 1 - r1^2), statically condensed */
+static void wilson_taylor(int shape, int quad, int npe, const double* xe, double E, double V, double t, double* Ke) {
+    const int m = 2 * npe, ng = quad_count(quad);
+    double D[9] = { 1.0 - V, V, 0, V, 1.0 - V, 0, 0, 0, 0.5 * (1.0 - 2.0 * V) };
+    const double f = E / ((1.0 - 2.0 * V) * (1.0 + V));
+    for (int i = 0; i < 9; i++) D[i] *= f;
+    double Keaa[16], Kead[4 * ORC_MAX_M];
+    memset(Keaa, 0, sizeof Keaa); memset(Kead, 0, sizeof(double) * 4 * m); memset(Ke, 0, sizeof(double) * m * m);
+    for (int g = 0; g < ng; g++) {
+        double r[3], w[3], dNdr[2 * ORC_MAX_NPE], dXdr[4], inv[4], dNdX[2 * ORC_MAX_NPE];
+        quad_point(quad, g, r, w);
+        shape_dndr(shape, r, dNdr);
+        matmul(2, npe, 2, dNdr, xe, dXdr);
+        const double J = det_d(2, dXdr);
+        inv_d(2, dXdr, inv);
+        matmul(2, 2, npe, inv, dNdr, dNdX);
+        double B[3 * ORC_MAX_M], Bt[ORC_MAX_M * 3], BtD[ORC_MAX_M * 3], BtDB[ORC_MAX_M * ORC_MAX_M];
+        memset(B, 0, sizeof(double) * 3 * m);
+        for (int n = 0; n < npe; n++) {
+            B[0 * m + 2 * n] = dNdX[n]; B[1 * m + 2 * n + 1] = dNdX[npe + n];
+            B[2 * m + 2 * n] = dNdX[npe + n]; B[2 * m + 2 * n + 1] = dNdX[n];
+        }
+        const double dPdr[4] = { -2.0 * r[0], 0.0, 0.0, -2.0 * r[1] };
+        double dPdX[4];
+        matmul(2, 2, 2, inv, dPdr, dPdX);
+        const double G[12] = { dPdX[0], 0.0, dPdX[1], 0.0,
+                               0.0, dPdX[2], 0.0, dPdX[3],
+                               dPdX[2], dPdX[0], dPdX[3], dPdX[1] };
+        double Gt[12], GtD[12], GtDG[16], GtDB[4 * ORC_MAX_M];
+        for (int i = 0; i < 3; i++) for (int j = 0; j < m; j++) Bt[j * 3 + i] = B[i * m + j];
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 4; j++) Gt[j * 3 + i] = G[i * 4 + j];
+        matmul(m, 3, 3, Bt, D, BtD); matmul(m, 3, m, BtD, B, BtDB);
+        matmul(4, 3, 3, Gt, D, GtD); matmul(4, 3, 4, GtD, G, GtDG); matmul(4, 3, m, GtD, B, GtDB);
+        for (int i = 0; i < m * m; i++) Ke[i] += BtDB[i] * J * t * w[0] * w[1];
+        for (int i = 0; i < 16; i++) Keaa[i] += GtDG[i] * J * t * w[0] * w[1];
+        for (int i = 0; i < 4 * m; i++) Kead[i] += GtDB[i] * J * t * w[0] * w[1];
+    }
+    double Kinv[16], KdaT[ORC_MAX_M * 4], T1[ORC_MAX_M * 4], T2[ORC_MAX_M * ORC_MAX_M];
+    inv4(Keaa, Kinv);
+    for (int i = 0; i < 4; i++) for (int j = 0; j < m; j++) KdaT[j * 4 + i] = Kead[i * m + j];
+    matmul(m, 4, 4, KdaT, Kinv, T1);            /* (Kead^T Keaa^-1) Kead, left to right */
+    matmul(m, 4, m, T1, Kead, T2);
+    for (int i = 0; i < m * m; i++) Ke[i] -= T2[i];
+}
+
 /* ------------------------------------------------------------------------------------------------------------
  * Element matrices for any <Equation, SF, IC> selection.
  * PlaneStrainStiffness           src/FEM/Equation/PlaneStrain.h:21-58
@@ -254,8 +322,9 @@ static void inv_d(int d, const double* v, double* inv) {
  * xe: npe x dim coordinates of the element's nodes.  Ke: (npe*ndof)^2 row-major.
  * Accumulation order kept: Ke += ((((B^T D) B) J) t) w0 w1 [w2]   (PlaneStrain.h:56, Solid.h:62, HeatTransfer.h:41)
  * ---------------------------------------------------------------------------------------------------------- */
+/* bmode: 0 = the standard B; 1 / 2 = Bvol / Bdev of PlaneStrainStiffnessBbar (PlaneStrain.h:150-156, 166-172) */
 static void accumulate_rule(int phys, int shape, int quad, int dim, int npe, int ndof, const double* xe, const double* D, int ns,
-                            double alpha, double t, double* Ke) {
+                            double alpha, double t, double* Ke, int bmode) {
     const int m = npe * ndof, ng = quad_count(quad);
     for (int g = 0; g < ng; g++) {
         double r[3], w[3], dNdr[3 * ORC_MAX_NPE], dXdr[9], inv[9], dNdX[3 * ORC_MAX_NPE];
@@ -267,6 +336,16 @@ static void accumulate_rule(int phys, int shape, int quad, int dim, int npe, int
             double N[ORC_MAX_NPE];
             shape_n2d(shape, r, N);
             for (int i = 0; i < npe; i++) for (int j = 0; j < npe; j++) Ke[i * npe + j] += N[i] * N[j] * J * w[0] * w[1];
+            continue;
+        }
+        if (phys == PHYS_MASS2) {           /* PlaneStrainMass  PlaneStrain.h:397-407: B = [N 0; 0 N], Me += B^T B J rho t w0 w1 */
+            double N[ORC_MAX_NPE], Bm[2 * ORC_MAX_M], Bmt[ORC_MAX_M * 2], BtB[ORC_MAX_M * ORC_MAX_M];
+            shape_n2d(shape, r, N);
+            memset(Bm, 0, sizeof(double) * 2 * m);
+            for (int n = 0; n < npe; n++) { Bm[0 * m + 2 * n] = N[n]; Bm[1 * m + 2 * n + 1] = N[n]; }
+            for (int i = 0; i < 2; i++) for (int j = 0; j < m; j++) Bmt[j * 2 + i] = Bm[i * m + j];
+            matmul(m, 2, m, Bmt, Bm, BtB);
+            for (int i = 0; i < m * m; i++) Ke[i] += BtB[i] * J * alpha * t * w[0] * w[1];
             continue;
         }
         inv_d(dim, dXdr, inv);
@@ -283,6 +362,17 @@ static void accumulate_rule(int phys, int shape, int quad, int dim, int npe, int
             }
         } else if (phys == PHYS_HEAT) {
             memcpy(B, dNdX, sizeof(double) * dim * npe);
+        } else if (bmode == 1) {
+            for (int n = 0; n < npe; n++) {
+                B[0 * m + 2 * n] = 0.5 * dNdX[n]; B[0 * m + 2 * n + 1] = 0.5 * dNdX[npe + n];
+                B[1 * m + 2 * n] = 0.5 * dNdX[n]; B[1 * m + 2 * n + 1] = 0.5 * dNdX[npe + n];
+            }
+        } else if (bmode == 2) {
+            for (int n = 0; n < npe; n++) {
+                B[0 * m + 2 * n] = 0.5 * dNdX[n];  B[0 * m + 2 * n + 1] = -0.5 * dNdX[npe + n];
+                B[1 * m + 2 * n] = -0.5 * dNdX[n]; B[1 * m + 2 * n + 1] = 0.5 * dNdX[npe + n];
+                B[2 * m + 2 * n] = dNdX[npe + n];  B[2 * m + 2 * n + 1] = dNdX[n];
+            }
         } else {
             for (int n = 0; n < npe; n++) {
                 B[0 * m + 2 * n] = dNdX[n];             /* row 0: dN/dx */
@@ -306,7 +396,7 @@ static void accumulate_rule(int phys, int shape, int quad, int dim, int npe, int
 void orc_element_matrix(int eq, const double* xe, double E, double V, double t, double* Ke) {
     const orc_sel s = decode_eq(eq);
     const int dim = dim_of(eq), npe = npe_of(eq), ndof = ndof_of(eq), m = npe * ndof;
-    const int ns = (s.phys == PHYS_SOLID) ? 6 : (s.phys == PHYS_HEAT ? dim : 3);
+    const int ns = (s.phys == PHYS_SOLID) ? 6 : ((s.phys == PHYS_HEAT || s.phys == PHYS_MASS) ? dim : 3);
     double D[36];
     memset(D, 0, sizeof D);
     memset(Ke, 0, sizeof(double) * m * m);
@@ -327,13 +417,22 @@ void orc_element_matrix(int eq, const double* xe, double E, double V, double t, 
         D[0] = 1.0; D[1] = 1.0; D[3] = 1.0; D[4] = 1.0;
         double f = E / (3.0 * (1.0 - 2.0 * V));
         for (int i = 0; i < 9; i++) D[i] *= f;
-        accumulate_rule(s.phys, s.shape, s.quad2, dim, npe, ndof, xe, D, ns, E, t, Ke);
+        accumulate_rule(s.phys, s.shape, s.quad2, dim, npe, ndof, xe, D, ns, E, t, Ke, 0);
         memset(D, 0, sizeof D);
         D[0] = 4.0; D[1] = -2.0; D[3] = -2.0; D[4] = 4.0; D[8] = 3.0;
         f = E / (6.0 * (1.0 + V));
         for (int i = 0; i < 9; i++) D[i] *= f;
     }
-    accumulate_rule(s.phys, s.shape, s.quad, dim, npe, ndof, xe, D, ns, E, t, Ke);     /* heat: E carries alpha */
+    if (s.phys == PHYS_PLANESTRAIN_WT) { wilson_taylor(s.shape, s.quad, npe, xe, E, V, t, Ke); return; }
+    if (s.phys == PHYS_PLANESTRAIN_BBAR) {
+        D[0] = 1.0 - V; D[1] = V; D[3] = V; D[4] = 1.0 - V; D[8] = 0.5 * (1.0 - 2.0 * V);
+        double f = E / ((1.0 - 2.0 * V) * (1.0 + V));
+        for (int i = 0; i < 9; i++) D[i] *= f;
+        accumulate_rule(s.phys, s.shape, s.quad2, dim, npe, ndof, xe, D, ns, E, t, Ke, 1);
+        accumulate_rule(s.phys, s.shape, s.quad, dim, npe, ndof, xe, D, ns, E, t, Ke, 2);
+        return;
+    }
+    accumulate_rule(s.phys, s.shape, s.quad, dim, npe, ndof, xe, D, ns, E, t, Ke, 0);     /* heat / mass: E carries the coefficient */
     if (s.phys == PHYS_MASS) for (int i = 0; i < m * m; i++) Ke[i] *= E * t;            /* the reference's mass has no coefficient */
 }
 

@@ -74,7 +74,7 @@ struct Quiet {
 };
 
 // eq codes of include/pansfem2_b200.h (PF2_EQ_CODE): phys | shape << 8 | quad << 16 | quad2 << 24, 0 = the physics' default
-enum { PHYS_PLANESTRAIN = 0, PHYS_SOLID = 1, PHYS_HEAT = 2, PHYS_PLANESTRESS = 3, PHYS_PLANESTRAIN_SRI = 4, PHYS_MASS = 5 };
+enum { PHYS_PLANESTRAIN = 0, PHYS_SOLID = 1, PHYS_HEAT = 2, PHYS_PLANESTRESS = 3, PHYS_PLANESTRAIN_SRI = 4, PHYS_MASS = 5, PHYS_PLANESTRAIN_BBAR = 6, PHYS_MASS2 = 7, PHYS_PLANESTRAIN_WT = 8 };
 enum { SHAPE_T3 = 1, SHAPE_T6, SHAPE_Q4, SHAPE_Q8, SHAPE_TET4, SHAPE_HEX8, SHAPE_HEX20 };
 enum { QUAD_G1TRI = 1, QUAD_G3TRI, QUAD_G1SQ, QUAD_G4SQ, QUAD_G9SQ, QUAD_G1TET, QUAD_G8CUBE, QUAD_G27CUBE };
 struct Sel { int phys, shape, quad, quad2; };
@@ -84,7 +84,7 @@ Sel decode(int eq) {
     if (!s.shape) s.shape = solid ? SHAPE_HEX8 : SHAPE_Q4;
     bool tri = s.shape == SHAPE_T3 || s.shape == SHAPE_T6;
     if (!s.quad) s.quad = tri ? QUAD_G1TRI : (s.shape == SHAPE_TET4 ? QUAD_G1TET : (solid ? QUAD_G8CUBE : QUAD_G4SQ));
-    if (s.phys == PHYS_PLANESTRAIN_SRI && !s.quad2) s.quad2 = tri ? QUAD_G1TRI : QUAD_G1SQ;
+    if ((s.phys == PHYS_PLANESTRAIN_SRI || s.phys == PHYS_PLANESTRAIN_BBAR) && !s.quad2) s.quad2 = tri ? QUAD_G1TRI : QUAD_G1SQ;
     return s;
 }
 int ndof_of(int eq) { int phys = eq & 0xff; return phys == PHYS_SOLID ? 3 : ((phys == PHYS_HEAT || phys == PHYS_MASS) ? 1 : 2); }
@@ -99,6 +99,9 @@ void em2d(const Sel& s, Matrix<double>& Ke, N2E& n2e, const std::vector<int>& el
         case PHYS_PLANESTRESS: PlaneStressStiffness<double, SF, IC>(Ke, n2e, element, { 0, 1 }, x, E, V, t); break;
         case PHYS_PLANESTRAIN_SRI: PlaneStrainStiffnessSRI<double, SF, ICV, IC>(Ke, n2e, element, { 0, 1 }, x, E, V, t); break;
         case PHYS_MASS: ReactionDiffusionConsistentMass<double, SF, IC>(Ke, n2e, element, { 0 }, x); Ke *= E*t; break;    // ReactionDiffusion.h:21 (E = t = 1)
+        case PHYS_PLANESTRAIN_BBAR: PlaneStrainStiffnessBbar<double, SF, ICV, IC>(Ke, n2e, element, { 0, 1 }, x, E, V, t); break;   // PlaneStrain.h:129
+        case PHYS_PLANESTRAIN_WT: PlaneStrainStiffnessWilsonTaylor<double, SF, IC>(Ke, n2e, element, { 0, 1 }, x, E, V, t); break;          // PlaneStrain.h:189
+        case PHYS_MASS2: PlaneStrainMass<double, SF, IC>(Ke, n2e, element, { 0, 1 }, x, E, t); break;                                // PlaneStrain.h:386 (E = rho)
         default: HeatTransfer<double, SF, IC>(Ke, n2e, element, { 0 }, x, E, t); break;
     }
 }

@@ -41,7 +41,7 @@ static int quad_domain(int quad) {
 int decode_eq(int eq, double V, EqInfo* out) {
     EqInfo q;
     q.phys = eq & 0xff; q.shape = (eq >> 8) & 0xff; q.quad = (eq >> 16) & 0xff; q.quad2 = (eq >> 24) & 0xff;
-    PF2_CHECK(eq >= 0 && q.phys <= PF2_PHYS_MASS, "unknown equation");
+    PF2_CHECK(eq >= 0 && q.phys <= PF2_PHYS_PLANESTRAIN_WT, "unknown equation");
     PF2_CHECK(q.shape <= PF2_SHAPE_HEX20 && q.quad <= PF2_QUAD_G27CUBE && q.quad2 <= PF2_QUAD_G27CUBE, "unknown shape function / integration rule");
     const bool solid = q.phys == PF2_PHYS_SOLID;
     if (q.shape == 0) q.shape = solid ? PF2_SHAPE_HEX8 : PF2_SHAPE_Q4;
@@ -51,7 +51,7 @@ int decode_eq(int eq, double V, EqInfo* out) {
     static const int dflt_reduced[4] = { PF2_QUAD_G1TRI, PF2_QUAD_G1SQ, PF2_QUAD_G1TET, PF2_QUAD_G8CUBE };
     if (q.quad == 0) q.quad = dflt[dom];
     PF2_CHECK(quad_domain(q.quad) == dom, "integration rule does not belong to the shape function's reference domain");
-    if (q.phys == PF2_PHYS_PLANESTRAIN_SRI) {
+    if (q.phys == PF2_PHYS_PLANESTRAIN_SRI || q.phys == PF2_PHYS_PLANESTRAIN_BBAR) {
         if (q.quad2 == 0) q.quad2 = dflt_reduced[dom];
         PF2_CHECK(quad_domain(q.quad2) == dom, "volumetric integration rule does not belong to the shape function's reference domain");
     } else {
@@ -60,14 +60,16 @@ int decode_eq(int eq, double V, EqInfo* out) {
     q.dim = solid ? 3 : 2;
     q.npe = shape_npe(q.shape);
     q.ndof = solid ? 3 : ((q.phys == PF2_PHYS_HEAT || q.phys == PF2_PHYS_MASS) ? 1 : 2);
-    q.kind = solid ? KIND_SOLID3D : (q.phys == PF2_PHYS_HEAT ? KIND_HEAT2D : (q.phys == PF2_PHYS_MASS ? KIND_MASS2D : KIND_ELAST2D));
+    q.kind = solid ? KIND_SOLID3D : (q.phys == PF2_PHYS_HEAT ? KIND_HEAT2D : (q.phys == PF2_PHYS_MASS ? KIND_MASS2D : (q.phys == PF2_PHYS_MASS2 ? KIND_MASS2D_V : KIND_ELAST2D)));
     q.fast = (q.phys == PF2_PHYS_PLANESTRAIN && q.shape == PF2_SHAPE_Q4 && q.quad == PF2_QUAD_G4SQ) ||
              (q.phys == PF2_PHYS_HEAT && q.shape == PF2_SHAPE_Q4 && q.quad == PF2_QUAD_G4SQ) ||
              (solid && q.shape == PF2_SHAPE_HEX8 && q.quad == PF2_QUAD_G8CUBE);
     q.legacy = solid ? PF2_EQ_SOLID : (q.phys == PF2_PHYS_HEAT ? PF2_EQ_HEAT : PF2_EQ_PLANESTRAIN);
     // D for unit modulus
     q.npass = 1; q.cn[0] = q.cn[1] = 1.0; q.lam[0] = q.lam[1] = 0.0; q.mu[0] = q.mu[1] = 0.0;
-    if (q.phys == PF2_PHYS_PLANESTRAIN || solid) {          // PlaneStrain.h:37-41, Solid.h:37-44
+    if (q.phys == PF2_PHYS_PLANESTRAIN_WT)
+        PF2_CHECK(dom == 1 && q.quad != PF2_QUAD_G1SQ, "Wilson-Taylor: quadrilateral shapes with at least Gauss4Square (the modes vanish at the centre point)");
+    if (q.phys == PF2_PHYS_PLANESTRAIN || q.phys == PF2_PHYS_PLANESTRAIN_WT || solid) {          // PlaneStrain.h:37-41, Solid.h:37-44
         const double c = 1.0 / ((1.0 + V) * (1.0 - 2.0 * V));
         q.cn[0] = (1.0 - V) * c; q.lam[0] = V * c; q.mu[0] = 0.5 * (1.0 - 2.0 * V) * c;
     } else if (q.phys == PF2_PHYS_PLANESTRESS) {            // PlaneStress.h:37-41
@@ -78,6 +80,13 @@ int decode_eq(int eq, double V, EqInfo* out) {
         const double k = 1.0 / (3.0 * (1.0 - 2.0 * V)), c = 1.0 / (6.0 * (1.0 + V));
         q.cn[0] = k; q.lam[0] = k; q.mu[0] = 0.0;
         q.cn[1] = 4.0 * c; q.lam[1] = -2.0 * c; q.mu[1] = 3.0 * c;
+    } else if (q.phys == PF2_PHYS_PLANESTRAIN_BBAR) {       // PlaneStrain.h:143-175: B = Bvol (ICV) + Bdev (ICD), plane-strain D on both
+        // Bvol^T D Bvol = (D00 + 2 D01 + D11)/4 (g_a g_b^T) ; Bdev^T D Bdev = (D00 - 2 D01 + D11)/4 [gx gx, -gx gy; -gy gx, gy gy] + D22 shear
+        q.npass = 2;
+        const double c = 1.0 / ((1.0 + V) * (1.0 - 2.0 * V));
+        const double m = 0.5 * (1.0 - 2.0 * V) * c;
+        q.cn[0] = 0.5 * c; q.lam[0] = 0.5 * c; q.mu[0] = 0.0;
+        q.cn[1] = m; q.lam[1] = -m; q.mu[1] = m;
     }
     *out = q;
     return PF2_OK;
@@ -86,6 +95,7 @@ int decode_eq(int eq, double V, EqInfo* out) {
 static ElemSpec make_spec(const EqInfo& q) {
     ElemSpec sp;
     sp.npass = q.npass;
+    sp.wilson_taylor = (q.phys == PF2_PHYS_PLANESTRAIN_WT) ? 1 : 0;
     if (q.npass == 2) { sp.quad[0] = q.quad2; sp.quad[1] = q.quad; }
     else { sp.quad[0] = q.quad; sp.quad[1] = q.quad; }
     for (int i = 0; i < 2; i++) { sp.cn[i] = q.cn[i]; sp.lam[i] = q.lam[i]; sp.mu[i] = q.mu[i]; }
@@ -205,6 +215,11 @@ __global__ void element_generic_kernel(ElemSpec sp, const double* __restrict__ x
             else if ((q).shape == PF2_SHAPE_T6) { CALL(KIND_HEAT2D, SH_T6); }                        \
             else if ((q).shape == PF2_SHAPE_Q4) { CALL(KIND_HEAT2D, SH_Q4); }                        \
             else { CALL(KIND_HEAT2D, SH_Q8); }                                                       \
+        } else if ((q).kind == KIND_MASS2D_V) {                                                      \
+            if ((q).shape == PF2_SHAPE_T3) { CALL(KIND_MASS2D_V, SH_T3); }                           \
+            else if ((q).shape == PF2_SHAPE_T6) { CALL(KIND_MASS2D_V, SH_T6); }                      \
+            else if ((q).shape == PF2_SHAPE_Q4) { CALL(KIND_MASS2D_V, SH_Q4); }                      \
+            else { CALL(KIND_MASS2D_V, SH_Q8); }                                                     \
         } else if ((q).kind == KIND_MASS2D) {                                                        \
             if ((q).shape == PF2_SHAPE_T3) { CALL(KIND_MASS2D, SH_T3); }                             \
             else if ((q).shape == PF2_SHAPE_T6) { CALL(KIND_MASS2D, SH_T6); }                        \

@@ -20,13 +20,14 @@ namespace pf2 {
 
 enum { SH_T3 = PF2_SHAPE_T3, SH_T6 = PF2_SHAPE_T6, SH_Q4 = PF2_SHAPE_Q4, SH_Q8 = PF2_SHAPE_Q8, SH_TET4 = PF2_SHAPE_TET4,
        SH_HEX8 = PF2_SHAPE_HEX8, SH_HEX20 = PF2_SHAPE_HEX20 };
-enum { KIND_ELAST2D = 0, KIND_HEAT2D = 1, KIND_SOLID3D = 2, KIND_MASS2D = 3 };
+enum { KIND_ELAST2D = 0, KIND_HEAT2D = 1, KIND_SOLID3D = 2, KIND_MASS2D = 3, KIND_MASS2D_V = 4 };
 
 // what one launch needs to know about the element routine (filled on the host by decode_eq, passed by value)
 struct ElemSpec {
     int npass;          // 1, or 2 for the selective-reduced plane-strain variant
     int quad[2];        // PF2_QUAD_* of each pass
     double cn[2], lam[2], mu[2];   // D for unit modulus (heat: unused)
+    int wilson_taylor;             // 1: incompatible modes condensed out (PlaneStrainStiffnessWilsonTaylor), quads only
 };
 
 template <int SHAPE> struct ShapeTraits;
@@ -43,6 +44,7 @@ template <> struct KindTraits<KIND_ELAST2D> { static constexpr int DIM = 2, NDOF
 template <> struct KindTraits<KIND_HEAT2D> { static constexpr int DIM = 2, NDOF = 1; };
 template <> struct KindTraits<KIND_SOLID3D> { static constexpr int DIM = 3, NDOF = 3; };
 template <> struct KindTraits<KIND_MASS2D> { static constexpr int DIM = 2, NDOF = 1; };     // scalar consistent mass N N^T
+template <> struct KindTraits<KIND_MASS2D_V> { static constexpr int DIM = 2, NDOF = 2; };   // 2-dof consistent mass (N_a N_b) I_2
 
 // ---- quadrature ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int quad_count(int quad) {
@@ -233,12 +235,202 @@ __device__ __forceinline__ void shape_grad(const double (&X)[ShapeTraits<SHAPE>:
     }
 }
 
+// ---- Wilson-Taylor incompatible modes (PlaneStrain.h:189-243) --------------------------------------------------------
+// The two modes P = (1 - r0^2, 1 - r1^2) act like two extra nodes whose "gradients" are h_m = -2 r_m * column m of dXdr^-1, so the
+// blocks Keaa (modes x modes), Kead (modes x nodes) come from the same closed form as the nodal blocks; then
+// Ke -= Kead^T Keaa^-1 Kead.  Gradients + the two mode gradients at one integration point:
+template <int SHAPE>
+__device__ __forceinline__ void wt_grad(const double (&X)[ShapeTraits<SHAPE>::NPE][2], const double (&r)[3], double (&g)[2][ShapeTraits<SHAPE>::NPE],
+                                        double (&h)[2][2], double& det) {
+    constexpr int NPE = ShapeTraits<SHAPE>::NPE;
+    shape_dndr<SHAPE>(r, g);
+    double J00 = 0, J01 = 0, J10 = 0, J11 = 0;
+#pragma unroll
+    for (int n = 0; n < NPE; n++) { J00 += g[0][n] * X[n][0]; J01 += g[0][n] * X[n][1]; J10 += g[1][n] * X[n][0]; J11 += g[1][n] * X[n][1]; }
+    det = J00 * J11 - J01 * J10;
+    const double i00 = J11 / det, i01 = -J01 / det, i10 = -J10 / det, i11 = J00 / det;
+#pragma unroll
+    for (int n = 0; n < NPE; n++) {
+        const double d0 = g[0][n], d1 = g[1][n];
+        g[0][n] = i00 * d0 + i01 * d1;
+        g[1][n] = i10 * d0 + i11 * d1;
+    }
+    // dPdX = dXdr^-1 * diag(-2 r0, -2 r1): mode m has gradient (dPdX(0,m), dPdX(1,m))
+    h[0][0] = i00 * (-2.0 * r[0]); h[1][0] = i10 * (-2.0 * r[0]);
+    h[0][1] = i01 * (-2.0 * r[1]); h[1][1] = i11 * (-2.0 * r[1]);
+}
+// isotropic block K_ab[i][j] for gradients ga, gb (2-D)
+__device__ __forceinline__ double iso_block2(double cn, double lam, double mu, const double (&ga)[2], const double (&gb)[2], int i, int j) {
+    return (i == j) ? (cn * ga[i] * gb[i] + mu * ga[1 - i] * gb[1 - i]) : (lam * ga[i] * gb[j] + mu * ga[j] * gb[i]);
+}
+// solve the 4x4 SPD system Kaa z = v (Gaussian elimination, no pivoting needed)
+__device__ __forceinline__ void solve4(double (&A)[4][4], double (&v)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const double piv = 1.0 / A[k][k];
+#pragma unroll
+        for (int i = k + 1; i < 4; i++) {
+            const double f = A[i][k] * piv;
+#pragma unroll
+            for (int j = k + 1; j < 4; j++) A[i][j] -= f * A[k][j];
+            v[i] -= f * v[k];
+        }
+    }
+#pragma unroll
+    for (int k = 3; k >= 0; k--) {
+        double s = v[k];
+#pragma unroll
+        for (int j = k + 1; j < 4; j++) s -= A[k][j] * v[j];
+        v[k] = s / A[k][k];
+    }
+}
+
+// rows of node a of the condensed matrix (unit modulus)
+template <int SHAPE>
+__device__ __forceinline__ void wt_rows(const double (&X)[ShapeTraits<SHAPE>::NPE][2], int a, const ElemSpec& sp, double t,
+                                        double (&acc)[2][ShapeTraits<SHAPE>::NPE * 2]) {
+    constexpr int NPE = ShapeTraits<SHAPE>::NPE, M = NPE * 2;
+    const double cn = sp.cn[0], lam = sp.lam[0], mu = sp.mu[0];
+    double Kaa[4][4], Kad[4][M];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) Kaa[i][j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < M; j++) Kad[i][j] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < M; j++) acc[i][j] = 0.0;
+    const int ng = quad_count(sp.quad[0]);
+#pragma unroll 1
+    for (int q = 0; q < ng; q++) {
+        double r[3], wq, det, g[2][NPE], h[2][2];
+        quad_point(sp.quad[0], q, r, wq);
+        wt_grad<SHAPE>(X, r, g, h, det);
+        const double w = det * t * wq;
+        double ga[2] = { g[0][0], g[1][0] };
+#pragma unroll
+        for (int n = 1; n < NPE; n++) if (n == a) { ga[0] = g[0][n]; ga[1] = g[1][n]; }
+#pragma unroll
+        for (int b = 0; b < NPE; b++) {
+            const double gb[2] = { g[0][b], g[1][b] };
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    acc[i][b * 2 + j] += iso_block2(cn, lam, mu, ga, gb, i, j) * w;
+#pragma unroll
+                    for (int mm = 0; mm < 2; mm++) {
+                        const double hm[2] = { h[0][mm], h[1][mm] };
+                        Kad[mm * 2 + i][b * 2 + j] += iso_block2(cn, lam, mu, hm, gb, i, j) * w;
+                    }
+                }
+        }
+#pragma unroll
+        for (int m1 = 0; m1 < 2; m1++)
+#pragma unroll
+            for (int m2 = 0; m2 < 2; m2++) {
+                const double h1[2] = { h[0][m1], h[1][m1] }, h2[2] = { h[0][m2], h[1][m2] };
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < 2; j++) Kaa[m1 * 2 + i][m2 * 2 + j] += iso_block2(cn, lam, mu, h1, h2, i, j) * w;
+            }
+    }
+    // acc_i -= Kad[:, a*2+i]^T Kaa^-1 Kad
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        double z[4], A[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            double v = Kad[k][0];
+#pragma unroll
+            for (int c = 1; c < M; c++) if (c == a * 2 + i) v = Kad[k][c];
+            z[k] = v;
+#pragma unroll
+            for (int j = 0; j < 4; j++) A[k][j] = Kaa[k][j];
+        }
+        solve4(A, z);
+#pragma unroll
+        for (int c = 0; c < M; c++) acc[i][c] -= z[0] * Kad[0][c] + z[1] * Kad[1][c] + z[2] * Kad[2][c] + z[3] * Kad[3][c];
+    }
+}
+
+// ue^T Ke ue and optionally Ke ue for the condensed element
+template <int SHAPE, bool WANT_F>
+__device__ __forceinline__ double wt_energy(const double (&X)[ShapeTraits<SHAPE>::NPE][2], const double (&ue)[ShapeTraits<SHAPE>::NPE][2], const ElemSpec& sp,
+                                            double t, double (&fe)[ShapeTraits<SHAPE>::NPE][2]) {
+    constexpr int NPE = ShapeTraits<SHAPE>::NPE;
+    const double cn = sp.cn[0], lam = sp.lam[0], mu = sp.mu[0];
+    double Kaa[4][4], v[4] = { 0.0, 0.0, 0.0, 0.0 }, wsum = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) Kaa[i][j] = 0.0;
+    const int ng = quad_count(sp.quad[0]);
+#pragma unroll 1
+    for (int q = 0; q < ng; q++) {
+        double r[3], wq, det, g[2][NPE], h[2][2];
+        quad_point(sp.quad[0], q, r, wq);
+        wt_grad<SHAPE>(X, r, g, h, det);
+        const double w = det * t * wq;
+        double exx = 0, eyy = 0, gxy = 0;
+#pragma unroll
+        for (int n = 0; n < NPE; n++) { exx += g[0][n] * ue[n][0]; eyy += g[1][n] * ue[n][1]; gxy += g[1][n] * ue[n][0] + g[0][n] * ue[n][1]; }
+        const double sxx = cn * exx + lam * eyy, syy = cn * eyy + lam * exx, sxy = mu * gxy;
+        wsum += (sxx * exx + syy * eyy + sxy * gxy) * w;
+        if constexpr (WANT_F) {
+#pragma unroll
+            for (int n = 0; n < NPE; n++) { fe[n][0] += (g[0][n] * sxx + g[1][n] * sxy) * w; fe[n][1] += (g[1][n] * syy + g[0][n] * sxy) * w; }
+        }
+#pragma unroll
+        for (int mm = 0; mm < 2; mm++) {        // v = Kad ue = sum_g G^T sigma(ue)
+            v[mm * 2 + 0] += (h[0][mm] * sxx + h[1][mm] * sxy) * w;
+            v[mm * 2 + 1] += (h[1][mm] * syy + h[0][mm] * sxy) * w;
+        }
+#pragma unroll
+        for (int m1 = 0; m1 < 2; m1++)
+#pragma unroll
+            for (int m2 = 0; m2 < 2; m2++) {
+                const double h1[2] = { h[0][m1], h[1][m1] }, h2[2] = { h[0][m2], h[1][m2] };
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < 2; j++) Kaa[m1 * 2 + i][m2 * 2 + j] += iso_block2(cn, lam, mu, h1, h2, i, j) * w;
+            }
+    }
+    double z[4] = { v[0], v[1], v[2], v[3] };
+    solve4(Kaa, z);                             // z = Kaa^-1 Kad ue  (the condensed mode amplitudes, sign flipped)
+    wsum -= v[0] * z[0] + v[1] * z[1] + v[2] * z[2] + v[3] * z[3];
+    if constexpr (WANT_F) {
+        // fe -= Kad^T z = sum_g B^T sigma(G z)
+#pragma unroll 1
+        for (int q = 0; q < ng; q++) {
+            double r[3], wq, det, g[2][NPE], h[2][2];
+            quad_point(sp.quad[0], q, r, wq);
+            wt_grad<SHAPE>(X, r, g, h, det);
+            const double w = det * t * wq;
+            const double exx = h[0][0] * z[0] + h[0][1] * z[2], eyy = h[1][0] * z[1] + h[1][1] * z[3];
+            const double gxy = h[1][0] * z[0] + h[0][0] * z[1] + h[1][1] * z[2] + h[0][1] * z[3];
+            const double sxx = cn * exx + lam * eyy, syy = cn * eyy + lam * exx, sxy = mu * gxy;
+#pragma unroll
+            for (int n = 0; n < NPE; n++) { fe[n][0] -= (g[0][n] * sxx + g[1][n] * sxy) * w; fe[n][1] -= (g[1][n] * syy + g[0][n] * sxy) * w; }
+        }
+    }
+    return wsum;
+}
+
 // Rows of local node `a` of the element matrix for unit modulus: acc[i][b*NDOF + j], i = dof of node a.
 template <int KIND, int SHAPE>
 __device__ __forceinline__ void generic_rows(const double (&X)[ShapeTraits<SHAPE>::NPE][ShapeTraits<SHAPE>::DIM], int a, const ElemSpec& sp,
                                              double t, double (&acc)[KindTraits<KIND>::NDOF][ShapeTraits<SHAPE>::NPE * KindTraits<KIND>::NDOF]) {
     constexpr int DIM = ShapeTraits<SHAPE>::DIM, NPE = ShapeTraits<SHAPE>::NPE, NDOF = KindTraits<KIND>::NDOF;
     static_assert(DIM == KindTraits<KIND>::DIM, "shape / equation dimension mismatch");
+    if constexpr (KIND == KIND_ELAST2D && (SHAPE == SH_Q4 || SHAPE == SH_Q8)) {
+        if (sp.wilson_taylor) { wt_rows<SHAPE>(X, a, sp, t, acc); return; }
+    }
 #pragma unroll
     for (int i = 0; i < NDOF; i++)
 #pragma unroll
@@ -259,14 +451,17 @@ __device__ __forceinline__ void generic_rows(const double (&X)[ShapeTraits<SHAPE
 #pragma unroll
                 for (int n = 1; n < NPE; n++) if (n == a) ga[k] = g[k][n];
             }
-            if constexpr (KIND == KIND_MASS2D) {
+            if constexpr (KIND == KIND_MASS2D || KIND == KIND_MASS2D_V) {
                 double N[NPE];
                 shape_n<SHAPE>(r, N);
                 double Na = N[0];
 #pragma unroll
                 for (int n = 1; n < NPE; n++) if (n == a) Na = N[n];
 #pragma unroll
-                for (int b = 0; b < NPE; b++) acc[0][b] += Na * N[b] * w;
+                for (int b = 0; b < NPE; b++) {
+#pragma unroll
+                    for (int i = 0; i < NDOF; i++) acc[i][b * NDOF + i] += Na * N[b] * w;
+                }
                 continue;
             }
 #pragma unroll
@@ -297,6 +492,9 @@ __device__ __forceinline__ double generic_energy(const double (&X)[ShapeTraits<S
                                                  const double (&ue)[ShapeTraits<SHAPE>::NPE][KindTraits<KIND>::NDOF], const ElemSpec& sp, double t,
                                                  double (&fe)[ShapeTraits<SHAPE>::NPE][KindTraits<KIND>::NDOF]) {
     constexpr int DIM = ShapeTraits<SHAPE>::DIM, NPE = ShapeTraits<SHAPE>::NPE;
+    if constexpr (KIND == KIND_ELAST2D && (SHAPE == SH_Q4 || SHAPE == SH_Q8)) {
+        if (sp.wilson_taylor) return wt_energy<SHAPE, WANT_F>(X, ue, sp, t, fe);
+    }
     double wsum = 0.0;
     for (int pass = 0; pass < sp.npass; pass++) {
         const double cn = sp.cn[pass], lam = sp.lam[pass], mu = sp.mu[pass];
@@ -307,16 +505,20 @@ __device__ __forceinline__ double generic_energy(const double (&X)[ShapeTraits<S
             quad_point(sp.quad[pass], q, r, wq);
             shape_grad<SHAPE>(X, r, g, det);
             const double w = (KIND == KIND_SOLID3D) ? det * wq : det * t * wq;
-            if constexpr (KIND == KIND_MASS2D) {
+            if constexpr (KIND == KIND_MASS2D || KIND == KIND_MASS2D_V) {
+                constexpr int ND = KindTraits<KIND>::NDOF;
                 double N[NPE];
                 shape_n<SHAPE>(r, N);
-                double ug = 0.0;
 #pragma unroll
-                for (int n = 0; n < NPE; n++) ug += N[n] * ue[n][0];
-                wsum += ug * ug * w;
-                if constexpr (WANT_F) {
+                for (int d = 0; d < ND; d++) {
+                    double ug = 0.0;
 #pragma unroll
-                    for (int n = 0; n < NPE; n++) fe[n][0] += N[n] * ug * w;
+                    for (int n = 0; n < NPE; n++) ug += N[n] * ue[n][d];
+                    wsum += ug * ug * w;
+                    if constexpr (WANT_F) {
+#pragma unroll
+                        for (int n = 0; n < NPE; n++) fe[n][d] += N[n] * ug * w;
+                    }
                 }
             } else if constexpr (KIND == KIND_HEAT2D) {
                 double qx = 0.0, qy = 0.0;

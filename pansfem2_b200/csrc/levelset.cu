@@ -219,7 +219,7 @@ struct pf2_levelset {
 
 static ElemSpec planestress_spec(double V) {
     ElemSpec sp;
-    sp.npass = 1; sp.quad[0] = sp.quad[1] = PF2_QUAD_G4SQ;
+    sp.npass = 1; sp.quad[0] = sp.quad[1] = PF2_QUAD_G4SQ; sp.wilson_taylor = 0;
     const double c = 1.0 / ((1.0 - V) * (1.0 + V));
     sp.cn[0] = sp.cn[1] = c; sp.lam[0] = sp.lam[1] = V * c; sp.mu[0] = sp.mu[1] = 0.5 * (1.0 - V) * c;
     return sp;

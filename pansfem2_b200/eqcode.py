@@ -2,7 +2,7 @@
 <Equation, ShapeFunction, Integration> (host-side bookkeeping only)."""
 from __future__ import annotations
 
-PHYS_PLANESTRAIN, PHYS_SOLID, PHYS_HEAT, PHYS_PLANESTRESS, PHYS_PLANESTRAIN_SRI, PHYS_MASS = 0, 1, 2, 3, 4, 5
+PHYS_PLANESTRAIN, PHYS_SOLID, PHYS_HEAT, PHYS_PLANESTRESS, PHYS_PLANESTRAIN_SRI, PHYS_MASS, PHYS_PLANESTRAIN_BBAR, PHYS_MASS2, PHYS_PLANESTRAIN_WT = range(9)
 SHAPE_DEFAULT, SHAPE_T3, SHAPE_T6, SHAPE_Q4, SHAPE_Q8, SHAPE_TET4, SHAPE_HEX8, SHAPE_HEX20 = range(8)
 QUAD_DEFAULT, QUAD_G1TRI, QUAD_G3TRI, QUAD_G1SQ, QUAD_G4SQ, QUAD_G9SQ, QUAD_G1TET, QUAD_G8CUBE, QUAD_G27CUBE = range(9)
 
@@ -11,7 +11,7 @@ SHAPE_NAME = {SHAPE_T3: "T3", SHAPE_T6: "T6", SHAPE_Q4: "Q4", SHAPE_Q8: "Q8", SH
 QUAD_NAME = {QUAD_G1TRI: "Gauss1Triangle", QUAD_G3TRI: "Gauss3Triangle", QUAD_G1SQ: "Gauss1Square", QUAD_G4SQ: "Gauss4Square",
              QUAD_G9SQ: "Gauss9Square", QUAD_G1TET: "Gauss1Tetrahedron", QUAD_G8CUBE: "Gauss8Cubic", QUAD_G27CUBE: "Gauss27Cubic"}
 PHYS_NAME = {PHYS_PLANESTRAIN: "PlaneStrain", PHYS_SOLID: "Solid", PHYS_HEAT: "HeatTransfer", PHYS_PLANESTRESS: "PlaneStress",
-             PHYS_PLANESTRAIN_SRI: "PlaneStrainSRI", PHYS_MASS: "ConsistentMass"}
+             PHYS_PLANESTRAIN_SRI: "PlaneStrainSRI", PHYS_MASS: "ConsistentMass", PHYS_PLANESTRAIN_BBAR: "PlaneStrainBbar", PHYS_MASS2: "ConsistentMass2dof", PHYS_PLANESTRAIN_WT: "PlaneStrainWilsonTaylor"}
 # rules of each reference domain (triangle, square, tetrahedron, cube)
 SHAPE_RULES = {SHAPE_T3: (QUAD_G1TRI, QUAD_G3TRI), SHAPE_T6: (QUAD_G1TRI, QUAD_G3TRI),
                SHAPE_Q4: (QUAD_G1SQ, QUAD_G4SQ, QUAD_G9SQ), SHAPE_Q8: (QUAD_G1SQ, QUAD_G4SQ, QUAD_G9SQ),
@@ -32,7 +32,7 @@ def fields(eq):
         shape = SHAPE_HEX8 if solid else SHAPE_Q4
     if quad == 0:
         quad = DEFAULT_RULE[shape]
-    if phys == PHYS_PLANESTRAIN_SRI and quad2 == 0:
+    if phys in (PHYS_PLANESTRAIN_SRI, PHYS_PLANESTRAIN_BBAR) and quad2 == 0:
         quad2 = QUAD_G1TRI if shape in (SHAPE_T3, SHAPE_T6) else QUAD_G1SQ
     return phys, shape, quad, quad2
 

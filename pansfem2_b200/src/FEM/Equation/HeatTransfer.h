@@ -13,4 +13,12 @@ namespace PANSFEM2 {
         assert((int)_element.size() == SF<T>::n);
         B200::ElementMatrix<T>(B200::EqCode<PF2_PHYS_HEAT, SF, IC>::value, 1, _Ke, _nodetoelement, _element, _doulist, _x, _alpha, T(0), _t);
     }
+
+    //  HeatCapacity (HeatTransfer.h:47-71): rho * c * N N^T * t, the scalar consistent mass on the device
+    template<class T, template<class>class SF, template<class>class IC>
+    void HeatCapacity(Matrix<T>& _Ce, std::vector<std::vector<std::pair<int, int> > >& _nodetoelement, const std::vector<int>& _element, const std::vector<int>& _doulist, std::vector<Vector<T> >& _x, T _rho, T _c, T _t) {
+        assert(_doulist.size() == 1);
+        assert((int)_element.size() == SF<T>::n);
+        B200::ElementMatrix<T>(B200::EqCode<PF2_PHYS_MASS, SF, IC>::value, 1, _Ce, _nodetoelement, _element, _doulist, _x, _rho*_c, T(0), _t);
+    }
 }

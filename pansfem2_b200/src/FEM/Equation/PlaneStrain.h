@@ -1,6 +1,7 @@
 //  pansfem2_b200/src/FEM/Equation/PlaneStrain.h
 //  PlaneStrainStiffness<T, SF, IC> (src/FEM/Equation/PlaneStrain.h:20-21), PlaneStrainStiffnessSRI<T, SF, ICV, ICD> (:62-63),
-//  PlaneStrainSurfaceForce (:420-421) and PlaneStrainBodyForce (:502-503) with the reference's signatures.
+//  PlaneStrainStiffnessBbar (:128-129), PlaneStrainStiffnessWilsonTaylor (:188-189), PlaneStrainMass (:385-386), PlaneStrainSurfaceForce (:420-421) and PlaneStrainBodyForce
+//  (:502-503) with the reference's signatures.
 //  Stiffness: any of T3 / T6 / Q4 / Q8 with a rule of its reference domain, computed on the B200.  The two load vectors take a
 //  C++ functor and stay on the host (a few flops per edge / element).
 #pragma once
@@ -22,6 +23,31 @@ namespace PANSFEM2 {
         assert(_doulist.size() == 2);
         assert((int)_element.size() == SF<T>::n);
         B200::ElementMatrix<T>(B200::EqCodeSRI<SF, ICV, ICD>::value, 2, _Ke, _nodetoelement, _element, _doulist, _x, _E, _V, _t);
+    }
+
+    //  B-bar as the reference implements it (PlaneStrain.h:128-185): volumetric part of B integrated with ICV, deviatoric part with ICD
+    template<class T, template<class>class SF, template<class>class ICV, template<class>class ICD>
+    void PlaneStrainStiffnessBbar(Matrix<T>& _Ke, std::vector<std::vector<std::pair<int, int> > >& _nodetoelement, const std::vector<int>& _element, const std::vector<int>& _doulist, std::vector<Vector<T> >& _x, T _E, T _V, T _t) {
+        assert(_doulist.size() == 2);
+        assert((int)_element.size() == SF<T>::n);
+        const int eq = (B200::EqCodeSRI<SF, ICV, ICD>::value & ~0xff) | PF2_PHYS_PLANESTRAIN_BBAR;
+        B200::ElementMatrix<T>(eq, 2, _Ke, _nodetoelement, _element, _doulist, _x, _E, _V, _t);
+    }
+
+    //  Wilson-Taylor incompatible modes, statically condensed (PlaneStrain.h:188-243); quadrilaterals with Gauss4Square / Gauss9Square
+    template<class T, template<class>class SF, template<class>class IC>
+    void PlaneStrainStiffnessWilsonTaylor(Matrix<T>& _Ke, std::vector<std::vector<std::pair<int, int> > >& _nodetoelement, const std::vector<int>& _element, const std::vector<int>& _doulist, std::vector<Vector<T> >& _x, T _E, T _V, T _t) {
+        assert(_doulist.size() == 2);
+        assert((int)_element.size() == SF<T>::n);
+        B200::ElementMatrix<T>(B200::EqCode<PF2_PHYS_PLANESTRAIN_WT, SF, IC>::value, 2, _Ke, _nodetoelement, _element, _doulist, _x, _E, _V, _t);
+    }
+
+    //  consistent mass rho * N^T N * t (PlaneStrain.h:385-408)
+    template<class T, template<class>class SF, template<class>class IC>
+    void PlaneStrainMass(Matrix<T>& _Me, std::vector<std::vector<std::pair<int, int> > >& _nodetoelement, const std::vector<int>& _element, const std::vector<int>& _doulist, std::vector<Vector<T> >& _x, T _rho, T _t) {
+        assert(_doulist.size() == 2);
+        assert((int)_element.size() == SF<T>::n);
+        B200::ElementMatrix<T>(B200::EqCode<PF2_PHYS_MASS2, SF, IC>::value, 2, _Me, _nodetoelement, _element, _doulist, _x, _rho, T(0), _t);
     }
 
     namespace B200 {

@@ -13,6 +13,12 @@ namespace PANSFEM2 {
         B200::ElementMatrix<T>(B200::EqCode<PF2_PHYS_PLANESTRESS, SF, IC>::value, 2, _Ke, _nodetoelement, _element, _doulist, _x, _E, _V, _t);
     }
 
+    //  PlaneStressMass (PlaneStress.h:62-63): the same rho * N^T N * t
+    template<class T, template<class>class SF, template<class>class IC>
+    void PlaneStressMass(Matrix<T>& _Me, std::vector<std::vector<std::pair<int, int> > >& _nodetoelement, const std::vector<int>& _element, const std::vector<int>& _doulist, std::vector<Vector<T> >& _x, T _rho, T _t) {
+        PlaneStrainMass<T, SF, IC>(_Me, _nodetoelement, _element, _doulist, _x, _rho, _t);
+    }
+
     template<class T, template<class>class SF, template<class>class IC, class F>
     void PlaneStressSurfaceForce(Vector<T>& _Fe, std::vector<std::vector<std::pair<int, int> > >& _nodetoelement, const std::vector<int>& _element, const std::vector<int>& _doulist, std::vector<Vector<T> >& _x, F _f, T _t) {
         assert(_doulist.size() == 2);

@@ -205,12 +205,17 @@ def parse_vtk_mesh(path):
 def all_selections():
     from pansfem2_b200 import eqcode as ec
     out = []
-    for phys in (ec.PHYS_PLANESTRAIN, ec.PHYS_PLANESTRESS, ec.PHYS_HEAT, ec.PHYS_PLANESTRAIN_SRI, ec.PHYS_SOLID, ec.PHYS_MASS):
+    for phys in (ec.PHYS_PLANESTRAIN, ec.PHYS_PLANESTRESS, ec.PHYS_HEAT, ec.PHYS_PLANESTRAIN_SRI, ec.PHYS_SOLID, ec.PHYS_MASS,
+                 ec.PHYS_PLANESTRAIN_BBAR, ec.PHYS_MASS2):
         shapes = (ec.SHAPE_TET4, ec.SHAPE_HEX8, ec.SHAPE_HEX20) if phys == ec.PHYS_SOLID else (ec.SHAPE_T3, ec.SHAPE_T6, ec.SHAPE_Q4, ec.SHAPE_Q8)
         for shape in shapes:
             for quad in ec.SHAPE_RULES[shape]:
-                for q2 in (ec.SHAPE_RULES[shape] if phys == ec.PHYS_PLANESTRAIN_SRI else (0,)):
+                for q2 in (ec.SHAPE_RULES[shape] if phys in (ec.PHYS_PLANESTRAIN_SRI, ec.PHYS_PLANESTRAIN_BBAR) else (0,)):
                     out.append(ec.eq_code(phys, shape, quad, q2))
+    # Wilson-Taylor incompatible modes: quadrilaterals, rules with off-centre points (the modes vanish at the centre)
+    for shape in (ec.SHAPE_Q4, ec.SHAPE_Q8):
+        for quad in (ec.QUAD_G4SQ, ec.QUAD_G9SQ):
+            out.append(ec.eq_code(ec.PHYS_PLANESTRAIN_WT, shape, quad))
     return out
 
 
@@ -235,6 +240,8 @@ def golden_families():
              "t6_pstress": (ec.eq_code(ec.PHYS_PLANESTRESS, ec.SHAPE_T6, ec.QUAD_G3TRI), (5, 3)),
              "q8_sri": (ec.eq_code(ec.PHYS_PLANESTRAIN_SRI, ec.SHAPE_Q8, ec.QUAD_G9SQ, ec.QUAD_G4SQ), (5, 3)),
              "q8_pstrain": (ec.eq_code(ec.PHYS_PLANESTRAIN, ec.SHAPE_Q8, ec.QUAD_G9SQ), (4, 3)),
+             "q4_wt": (ec.eq_code(ec.PHYS_PLANESTRAIN_WT, ec.SHAPE_Q4, ec.QUAD_G4SQ), (6, 4)),
+             "q4_bbar": (ec.eq_code(ec.PHYS_PLANESTRAIN_BBAR, ec.SHAPE_Q4, ec.QUAD_G4SQ, ec.QUAD_G1SQ), (6, 4)),
              "tet4": (ec.eq_code(ec.PHYS_SOLID, ec.SHAPE_TET4), (3, 2, 2)),
              "hex20": (ec.eq_code(ec.PHYS_SOLID, ec.SHAPE_HEX20, ec.QUAD_G27CUBE), (3, 2, 2))}
     for nm, (eq, n) in cases.items():

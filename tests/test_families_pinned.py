@@ -11,7 +11,7 @@ from oracle import reflib
 from pansfem2_b200 import eqcode as ec
 from pansfem2_b200 import problems
 
-CASES = ["t3_heat", "t6_pstress", "q8_sri", "q8_pstrain", "tet4", "hex20"]
+CASES = ["t3_heat", "t6_pstress", "q8_sri", "q8_pstrain", "q4_wt", "q4_bbar", "tet4", "hex20"]
 
 
 @pytest.fixture(scope="module")
@@ -26,7 +26,7 @@ def t3(golden_dir):
 
 def test_every_selection_element_matrix(fam):
     sel = [int(v) for v in fam["selections"]]
-    assert len(sel) == 71
+    assert len(sel) == 111
     for eq in sel:
         ke = orc.element_matrix(eq, fam[f"xe_{eq}"], 2.5, 0.3, 0.7)
         ref = fam[f"ke_{eq}"]

@@ -40,7 +40,7 @@ def rel(a, b):
 
 def test_every_selection_element_matrix(ctx, fam):
     sel = [int(v) for v in fam["selections"]]
-    assert len(sel) == 71
+    assert len(sel) == 111
     for eq in sel:
         ke = ctx.element_matrix(eq, fam[f"xe_{eq}"], 2.5, 0.3, 0.7)
         assert rel(ke, fam[f"ke_{eq}"]) < 1e-13, ec.describe(eq)
@@ -51,7 +51,9 @@ def test_invalid_selections_are_rejected(ctx):
     for eq in (ec.eq_code(ec.PHYS_PLANESTRAIN, ec.SHAPE_T3, ec.QUAD_G4SQ),        # square rule on a triangle
                ec.eq_code(ec.PHYS_SOLID, ec.SHAPE_Q4),                             # 2-D shape in a 3-D equation
                ec.eq_code(ec.PHYS_PLANESTRESS, ec.SHAPE_Q4, ec.QUAD_G4SQ, ec.QUAD_G1SQ),  # second rule without SRI
-               ec.eq_code(7)):
+               ec.eq_code(ec.PHYS_PLANESTRAIN_WT, ec.SHAPE_Q4, ec.QUAD_G1SQ),              # Wilson-Taylor needs off-centre points
+               ec.eq_code(ec.PHYS_PLANESTRAIN_WT, ec.SHAPE_T3),                            # ... and a quadrilateral
+               ec.eq_code(31)):
         with pytest.raises(capi.Pf2Error):
             ctx.element_matrix(eq, xe, 1.0)
 
