@@ -288,8 +288,7 @@ static int launch_sell(pf2_csr* A, const double* x, double* y, const CgState* st
 static const pf2_csr* g_mf_owner = nullptr;
 static unsigned long long g_mf_owner_version = 0;
 
-template <bool DOT>
-static int launch_mf(pf2_csr* A, const double* x, double* y, const CgState* st, double* dot_out) {
+static int mf_constant(pf2_csr* A) {
     pf2_ctx* c = A->ctx;
     PF2_CHECK(A->mf_ready && A->mf_version > 0, "matrix-free operator: assemble once after pf2_csr_matrix_free");
     if (g_mf_owner != A || g_mf_owner_version != A->mf_version) {
@@ -297,6 +296,54 @@ static int launch_mf(pf2_csr* A, const double* x, double* y, const CgState* st, 
         PF2_CUDA(cudaMemcpyToSymbolAsync(c_mf_ke0, A->mf_ke0, sizeof(double) * (size_t)m * m, 0, cudaMemcpyHostToDevice, c->stream));
         g_mf_owner = A; g_mf_owner_version = A->mf_version;
     }
+    return PF2_OK;
+}
+
+// ---- nodal-space PCG pieces (called by solve_mf_nodal, solver.cu) ----
+int mf_nodal_begin(pf2_csr* A, int jacobi, const double* b, double* bn, double* dn, double* xn, double* r, double* z, double* p0, double* p1, int itrmax, double eps) {
+    pf2_ctx* c = A->ctx;
+    PF2_TRY(mf_constant(A));
+    const size_t nfull = (size_t)A->mf_n[0] * A->mf_n[1] * A->mf_n[2] * A->mf_ndof;
+    const int g = c->grid_for((long long)nfull, 2);
+    mf_expand_kernel<<<g, kThreads, 0, c->stream>>>(nfull, A->mf_n2g, b, A->indptr, A->diagpos, A->data, jacobi, bn, dn);
+    mf_init_kernel<<<std::min(g, c->sm_count * 4), kThreads, 0, c->stream>>>(nfull, bn, dn, xn, r, z, p0, p1, A->st, itrmax, eps, c->red.partials, c->red.ticket);
+    PF2_LAUNCH_CHECK();
+    c->launches += 2;
+    return PF2_OK;
+}
+int mf_nodal_apply(pf2_csr* A, const double* p_old, const double* z, double* p_new, double* y) {
+    pf2_ctx* c = A->ctx;
+    MfGrid G;
+    G.n[0] = A->mf_n[0]; G.n[1] = A->mf_n[1]; G.n[2] = A->mf_n[2];
+    G.nnode = A->mf_n[0] * A->mf_n[1] * A->mf_n[2];
+#define MFN(D, N)                                                                                                                      \
+    {                                                                                                                                  \
+        const int nb = ((G.n[0] + MfTile<D>::TI - 1) / MfTile<D>::TI) * ((G.n[1] + MfTile<D>::TJ - 1) / MfTile<D>::TJ) *               \
+                       ((D) == 3 ? (G.n[2] + MfTile<D>::TK - 1) / MfTile<D>::TK : 1);                                                  \
+        const int grid = std::max(1, std::min(nb, c->wave_grid((const void*)spmv_mf_nodal_kernel<D, N>, kThreads)));                   \
+        spmv_mf_nodal_kernel<D, N><<<grid, kThreads, 0, c->stream>>>(G, A->mf_n2g, A->mf_E, p_old, z, p_new, y, A->st, c->red.partials, c->red.ticket); \
+    }
+    if (A->mf_dim == 3) MFN(3, 3)
+    else if (A->mf_ndof == 2) MFN(2, 2)
+    else MFN(2, 1)
+#undef MFN
+    PF2_LAUNCH_CHECK();
+    c->launches++;
+    return PF2_OK;
+}
+int mf_nodal_end(pf2_csr* A, const double* xn, double* x) {
+    pf2_ctx* c = A->ctx;
+    const size_t nfull = (size_t)A->mf_n[0] * A->mf_n[1] * A->mf_n[2] * A->mf_ndof;
+    mf_gather_kernel<<<c->grid_for((long long)nfull, 2), kThreads, 0, c->stream>>>(nfull, A->mf_n2g, xn, x);
+    PF2_LAUNCH_CHECK();
+    c->launches++;
+    return PF2_OK;
+}
+
+template <bool DOT>
+static int launch_mf(pf2_csr* A, const double* x, double* y, const CgState* st, double* dot_out) {
+    pf2_ctx* c = A->ctx;
+    PF2_TRY(mf_constant(A));
     MfGrid G;
     G.n[0] = A->mf_n[0]; G.n[1] = A->mf_n[1]; G.n[2] = A->mf_n[2];
     G.nnode = A->mf_n[0] * A->mf_n[1] * A->mf_n[2];
@@ -454,6 +501,7 @@ int pf2_csr_destroy(pf2_csr* A) {
     for (void* p : ptrs) if (p) cudaFree(p);
     if (A->h_st) cudaFreeHost(A->h_st);
     if (A->mf_E) cudaFree(A->mf_E);
+    if (A->mf_slab) cudaFree(A->mf_slab);
     if (g_mf_owner == A) g_mf_owner = nullptr;
     if (A->bi_slab) cudaFree(A->bi_slab);
     if (A->bi_st) cudaFree(A->bi_st);
@@ -550,6 +598,7 @@ int pf2_csr_matrix_free(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq) {
     A->mf_n2g = map->n2g;
     A->mf_version = 0;
     A->mf_ready = true;
+    A->mf_nodal = (getenv("PF2_MF_NODAL") == nullptr) || atoi(getenv("PF2_MF_NODAL")) != 0;     // PF2_MF_NODAL=0 keeps the reduced-numbering PCG
     A->spmv_variant = 41;
     return PF2_OK;
 }

@@ -357,12 +357,78 @@ int ensure_workspace_pub(pf2_csr* A) { return ensure_workspace(A); }
 int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out);
 int solve_bicgstab(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out);
 
+// ---- PCG in nodal numbering with the matrix-free operator (single GPU; csr.cu / spmv_mf.cuh) -----------------------------
+int mf_nodal_begin(pf2_csr* A, int jacobi, const double* b, double* bn, double* dn, double* xn, double* r, double* z, double* p0, double* p1, int itrmax, double eps);
+int mf_nodal_apply(pf2_csr* A, const double* p_old, const double* z, double* p_new, double* y);
+int mf_nodal_end(pf2_csr* A, const double* xn, double* x);
+
+static int solve_mf_nodal(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out) {
+    pf2_ctx* c = A->ctx;
+    PF2_CUDA(cudaSetDevice(c->device));
+    PF2_TRY(ensure_workspace(A));          // device state, events, pinned mirror
+    const size_t nfull = (size_t)A->mf_n[0] * A->mf_n[1] * A->mf_n[2] * A->mf_ndof;
+    const size_t np = (nfull + 31) & ~(size_t)31;
+    if (!A->mf_slab) PF2_TRY(dev_alloc(&A->mf_slab, 8 * np));
+    double *bn = A->mf_slab, *dn = bn + np, *xn = bn + 2 * np, *r = bn + 3 * np, *z = bn + 4 * np, *y = bn + 5 * np;
+    double* P[2] = { bn + 6 * np, bn + 7 * np };
+    const int n = (int)nfull;
+    PF2_TRY(mf_nodal_begin(A, solver == PF2_SOLVER_SCALINGCG ? 1 : 0, b, bn, dn, xn, r, z, P[0], P[1], itrmax, eps));
+    const int gu = std::min(c->grid_for(n, 4), c->wave_grid((const void*)cg_update_kernel<1>, kThreads));
+    const int chunk = 32;
+    int enq = 0, slot = 0;
+    bool have_prev = false, finished = false;
+    CgState last;
+    memset(&last, 0, sizeof last);
+    while (!finished) {
+        const int todo = std::min(chunk, itrmax - enq);
+        for (int k = 0; k < todo; k++) {
+            const bool sample = (k == todo / 2) && enq > 0;
+            cudaEvent_t* pev = sample ? A->pev[slot] : nullptr;
+            const int it = enq + k;
+            if (pev) PF2_CUDA(cudaEventRecord(pev[0], c->stream));
+            PF2_TRY(mf_nodal_apply(A, P[it & 1], z, P[(it + 1) & 1], y));                       // p = beta p + z ; y = K p ; p.y
+            if (pev) PF2_CUDA(cudaEventRecord(pev[1], c->stream));
+            cg_update_kernel<1><<<gu, kThreads, 0, c->stream>>>(n, P[(it + 1) & 1], y, dn, xn, r, z, A->st, c->red.partials, c->red.ticket);
+            c->launches++;
+            if (pev) { PF2_CUDA(cudaEventRecord(pev[2], c->stream)); PF2_CUDA(cudaEventRecord(pev[3], c->stream)); A->pev_armed[slot] = true; }
+        }
+        PF2_LAUNCH_CHECK();
+        enq += todo;
+        PF2_CUDA(cudaMemcpyAsync(&A->h_st[slot], A->st, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+        PF2_CUDA(cudaEventRecord(A->ev[slot], c->stream));
+        if (have_prev) {
+            PF2_CUDA(cudaEventSynchronize(A->ev[slot ^ 1]));
+            last = A->h_st[slot ^ 1];
+            if (!last.done) harvest_profile(A, slot ^ 1); else A->pev_armed[slot ^ 1] = false;
+            if (last.done) finished = true;
+        }
+        if (!finished && (enq >= itrmax || todo == 0)) finished = true;
+        have_prev = true;
+        slot ^= 1;
+    }
+    PF2_TRY(mf_nodal_end(A, xn, x));
+    PF2_CUDA(cudaMemcpyAsync(&A->h_st[0], A->st, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+    PF2_CUDA(cudaStreamSynchronize(c->stream));
+    A->pev_armed[0] = A->pev_armed[1] = false;
+    last = A->h_st[0];
+    A->total_iters += last.iter;
+    if (iters_out) *iters_out = last.iter;
+    if (relres_out) *relres_out = sqrt(last.rr) / sqrt(last.bb);
+    if (!last.done) {
+        set_error("Convergence:faild after %d iterations (relres %.3e)", last.iter, sqrt(last.rr) / sqrt(last.bb));
+        return PF2_E_NOCONV;
+    }
+    return PF2_OK;
+}
+
 int solve(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out) {
     pf2_ctx* c = A->ctx;
     PF2_CHECK(solver >= 0 && solver <= PF2_SOLVER_ILU0BICGSTAB, "unknown solver");
     if (solver >= PF2_SOLVER_BICGSTAB) return solve_bicgstab(A, solver, b, x, itrmax, eps, iters_out, relres_out);
     if (A->dist) { PF2_CUDA(cudaSetDevice(c->device)); return solve_dist(A, solver, b, x, itrmax, eps, iters_out, relres_out); }
     PF2_CHECK(itrmax >= 0, "itrmax");
+    if (A->spmv_variant == 41 && A->mf_nodal && A->mf_version > 0 && solver != PF2_SOLVER_ILU0CG)
+        return solve_mf_nodal(A, solver, b, x, itrmax, eps, iters_out, relres_out);
     PF2_CUDA(cudaSetDevice(c->device));
     PF2_TRY(ensure_workspace(A));
     const int n = A->rows;

@@ -121,6 +121,128 @@ spmv_mf_kernel(MfGrid G, const int* __restrict__ n2g, const double* __restrict__
     }
 }
 
+// ---- nodal-space variant, fused with the direction update ---------------------------------------------------------------
+// The single-GPU PCG can run in NODAL numbering (vectors of nnode*NDOF entries, fixed dofs carried as identity rows with zero
+// right-hand side -- they stay 0 through every recurrence), which removes the nodetoglobal indirection from the gathers, and
+// the direction update p = beta p + z (CG.h:439) can then be folded into the staging phase: the tile + halo entries of p are
+// rebuilt from p_old and z while they are loaded, the tile's own entries are written to the OTHER p buffer (ping-pong, so halo
+// readers of neighbouring tiles still see p_old), and the separate p-update kernel disappears.
+template <int DIM, int NDOF>
+__global__ void __launch_bounds__(kThreads)
+spmv_mf_nodal_kernel(MfGrid G, const int* __restrict__ n2g, const double* __restrict__ E, const double* __restrict__ p_old, const double* __restrict__ z,
+                     double* __restrict__ p_new, double* __restrict__ y, CgState* __restrict__ st, double* partials, unsigned int* ticket) {
+    if (st->done) return;
+    constexpr int NC = 1 << DIM, M = NC * NDOF;
+    constexpr int TI = MfTile<DIM>::TI, TJ = MfTile<DIM>::TJ, TK = MfTile<DIM>::TK;
+    constexpr int HJ = TJ + 2, HK = (DIM == 3) ? TK + 2 : 1, HI = TI + 2, HALO = HI * HJ * HK;
+    __shared__ double sp[NDOF][HALO];
+    const double beta = st->beta;
+    const int n0 = G.n[0], n1 = G.n[1], n2 = G.n[2];
+    const int e1 = n1 - 1, e2 = (DIM == 3) ? n2 - 1 : 1;
+    const int tiles_i = (n0 + TI - 1) / TI, tiles_j = (n1 + TJ - 1) / TJ, tiles_k = (DIM == 3) ? (n2 + TK - 1) / TK : 1;
+    const int ntiles = tiles_i * tiles_j * tiles_k;
+    const int tk = threadIdx.x % TK, tj = (threadIdx.x / TK) % TJ, ti = threadIdx.x / (TK * TJ);
+    const int hc = ((ti + 1) * HJ + (tj + 1)) * HK + ((DIM == 3) ? tk + 1 : 0);
+    double dot = 0.0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int bk = tile % tiles_k, bj = (tile / tiles_k) % tiles_j, bi = tile / (tiles_k * tiles_j);
+        const int i0 = bi * TI, j0 = bj * TJ, k0 = bk * TK;
+        for (int h = threadIdx.x; h < HALO; h += kThreads) {
+            const int hk = h % HK, hj = (h / HK) % HJ, hi = h / (HK * HJ);
+            const int gi = i0 - 1 + hi, gj = j0 - 1 + hj, gk = (DIM == 3) ? k0 - 1 + hk : 0;
+            const bool in = (unsigned)gi < (unsigned)n0 && (unsigned)gj < (unsigned)n1 && (unsigned)gk < (unsigned)n2;
+            const size_t nid = ((size_t)gi * n1 + gj) * n2 + gk;
+            const bool own = hi >= 1 && hi <= TI && hj >= 1 && hj <= TJ && (DIM == 2 || (hk >= 1 && hk <= TK));
+#pragma unroll
+            for (int d = 0; d < NDOF; d++) {
+                double v = 0.0;
+                if (in) {
+                    v = beta * p_old[nid * NDOF + d] + z[nid * NDOF + d];          // xeaxpy (CG.h:41-49)
+                    if (own) p_new[nid * NDOF + d] = v;
+                }
+                sp[d][h] = v;
+            }
+        }
+        __syncthreads();
+        const int i = i0 + ti, j = j0 + tj, k = k0 + tk;
+        if (i < n0 && j < n1 && k < n2) {
+            const size_t nid = ((size_t)i * n1 + j) * n2 + k;
+            double acc[NDOF];
+#pragma unroll
+            for (int d = 0; d < NDOF; d++) acc[d] = 0.0;
+#pragma unroll
+            for (int a = 0; a < NC; a++) {
+                int ox, oy, oz;
+                mf_corner(DIM, a, ox, oy, oz);
+                const int ei = i - ox, ej = j - oy, ek = k - oz;
+                const bool in = (unsigned)ei < (unsigned)(n0 - 1) && (unsigned)ej < (unsigned)e1 && (DIM == 2 || (unsigned)ek < (unsigned)e2);
+                if (!in) continue;
+                const double Ee = __ldg(E + ((size_t)ei * e1 + ej) * e2 + ek);
+                double t[NDOF];
+#pragma unroll
+                for (int d = 0; d < NDOF; d++) t[d] = 0.0;
+#pragma unroll
+                for (int b = 0; b < NC; b++) {
+                    int bx, by, bz;
+                    mf_corner(DIM, b, bx, by, bz);
+                    const int q = hc + ((bx - ox) * HJ + (by - oy)) * HK + ((DIM == 3) ? (bz - oz) : 0);
+#pragma unroll
+                    for (int dj = 0; dj < NDOF; dj++) {
+                        const double pv = sp[dj][q];
+#pragma unroll
+                        for (int di = 0; di < NDOF; di++) t[di] += c_mf_ke0[(a * NDOF + di) * M + b * NDOF + dj] * pv;
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < NDOF; d++) acc[d] += Ee * t[d];
+            }
+#pragma unroll
+            for (int d = 0; d < NDOF; d++) {
+                const bool fixed = n2g[nid * NDOF + d] == -1;              // identity row: y = p = 0
+                const double yv = fixed ? 0.0 : acc[d];
+                y[nid * NDOF + d] = yv;
+                dot += yv * sp[d][hc];
+            }
+        }
+        __syncthreads();
+    }
+    double vsum[1] = { dot };
+    if (grid_sum_last<1>(vsum, partials, ticket) && threadIdx.x == 0) st->pAp = vsum[0];
+}
+
+// reduced <-> nodal numbering
+__global__ void mf_expand_kernel(size_t nfull, const int* __restrict__ n2g, const double* __restrict__ b, const long long* __restrict__ indptr,
+                                 const int* __restrict__ diagpos, const double* __restrict__ data, int jacobi, double* __restrict__ bn, double* __restrict__ dn) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nfull; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = n2g[i];
+        bn[i] = (r != -1) ? b[r] : 0.0;
+        double d = 1.0;
+        if (jacobi && r != -1) { const int dp = diagpos[r]; d = dp >= 0 ? data[indptr[r] + dp] : 0.0; }      // GetDiagonal (CG.h:398-404)
+        dn[i] = d;
+    }
+}
+__global__ void mf_gather_kernel(size_t nfull, const int* __restrict__ n2g, const double* __restrict__ xn, double* __restrict__ x) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nfull; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = n2g[i];
+        if (r != -1) x[r] = xn[i];
+    }
+}
+// x = 0 ; r = b ; z = r / D ; p = z ; bb ; rho = z.r      (CG.h:422-428 in nodal numbering; both p buffers start as z)
+__global__ void __launch_bounds__(kThreads)
+mf_init_kernel(size_t nfull, const double* __restrict__ bn, const double* __restrict__ dn, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
+               double* __restrict__ p0, double* __restrict__ p1, CgState* st, int maxit, double eps, double* partials, unsigned int* ticket) {
+    double v[2] = { 0.0, 0.0 };
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nfull; i += (size_t)gridDim.x * blockDim.x) {
+        const double bi = bn[i], zi = bi / dn[i];
+        x[i] = 0.0; r[i] = bi; z[i] = zi; p0[i] = zi; p1[i] = zi;
+        v[0] += bi * bi; v[1] += zi * bi;
+    }
+    if (grid_sum_last<2>(v, partials, ticket) && threadIdx.x == 0) {
+        st->bb = v[0]; st->rr = v[0]; st->rho = v[1]; st->pAp = 0.0; st->beta = 0.0; st->zr_new = 0.0;
+        st->iter = 0; st->done = 0; st->maxit = maxit; st->eps = eps;
+    }
+}
+
 // lattice check: connectivity follows the x-major numbering and every element is a translate of element 0
 __global__ void mf_verify_kernel(int dim, MfGrid G, int nelem, const int* __restrict__ conn, const double* __restrict__ coords, int* bad) {
     const int npe = 1 << dim;

@@ -121,6 +121,8 @@ struct pf2_csr {
     double mf_ke0[576];               // unit-modulus element matrix (host copy, uploaded to constant memory)
     double mf_V = -1.0, mf_t = -1.0;  // parameters mf_ke0 was built with
     unsigned long long mf_version = 0;
+    bool mf_nodal = false;            // single GPU: run the PCG in nodal numbering with the p-update fused into the operator
+    double* mf_slab = nullptr;        // nodal-space vectors: b | D | x | r | z | y | p0 | p1
     // BiCGSTAB family workspace (bicgstab.cu): 12 vectors, device state, pinned mirror (2 slots), poll events
     double* bi_slab = nullptr;
     void* bi_st = nullptr;
