@@ -465,11 +465,13 @@ class Simp:
 class LevelSet:
     """The device-resident level-set loop for a pansfem2_b200.problems.LevelSetProblem (sample_optimize_levelset.cpp)."""
 
-    def __init__(self, ctx, P):
+    def __init__(self, ctx, P, matrix_free=False):
         self.ctx, self.P = ctx, P
         self.mesh = Mesh(ctx, P.coords, P.conn)
         self.dofmap = DofMap(ctx, P.nnode, 2, P.fixed)
         self.K = Csr.pattern(ctx, self.mesh, self.dofmap)
+        if matrix_free:     # the displacement solve applies K matrix-free (plane-stress Q4 on the uniform SquareMesh)
+            self.K.matrix_free(self.mesh, self.dofmap, eq_code(eqcode.PHYS_PLANESTRESS, eqcode.SHAPE_Q4, eqcode.QUAD_G4SQ))
         pn = _i32(P.phifixed)
         ln, ld, lv = _i32(P.loads[0]), _i32(P.loads[1]), _f64(P.loads[2])
         prm = _f64(P.prm())

@@ -38,11 +38,12 @@ def test_small_case_from_perturbed_state(ctx, gold):
     L.close()
 
 
-def test_sample_run_to_convergence(ctx, gold):
+@pytest.mark.parametrize("matrix_free", [False, True])
+def test_sample_run_to_convergence(ctx, gold, matrix_free):
     """sample_optimize_levelset.cpp on the device: 60 x 40, converges at t = 115 like the reference; history against the
-    full-precision reference run, final fields against the sample's last VTK."""
+    full-precision reference run, final fields against the sample's last VTK.  Also with K applied matrix-free."""
     P = problems.levelset2d()
-    L = capi.LevelSet(ctx, P)
+    L = capi.LevelSet(ctx, P, matrix_free=matrix_free)
     hist = []
     t = 0
     for t in range(P.tmax):

@@ -14,7 +14,7 @@ nx, ny, iters = (int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])) if len(sy
 P = problems.levelset2d(nx, ny, tmax=iters + 2)
 ctx = capi.Context(0)
 t0 = time.time()
-L = capi.LevelSet(ctx, P)
+L = capi.LevelSet(ctx, P, matrix_free=(os.environ.get("PF2_OPERATOR") == "matrix-free"))
 ctx.sync()
 setup = time.time() - t0
 rows = []
