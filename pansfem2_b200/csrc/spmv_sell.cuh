@@ -85,6 +85,39 @@ __global__ void sell_delta16_kernel(int rows, long long entries, const long long
         }
     }
 }
+// ---- block deltas: rows of an NB-dof-per-node FEM matrix hold their columns in runs of NB consecutive indices (the dofs of one
+// neighbouring node), so ONE 16-bit delta per run is enough: the index stream shrinks from 2 to 2/NB bytes per nonzero.
+// Requires every row to consist of complete runs (true unless Dirichlet conditions fix only some dofs of a node).
+__global__ void sell_block_check_kernel(int rows, int nb, const long long* __restrict__ indptr, const int* __restrict__ indices, int* bad) {
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+        const long long b = indptr[r];
+        const int len = (int)(indptr[r + 1] - b);
+        bool ok = (len % nb) == 0;
+        for (int k = 0; ok && k < len; k += nb)
+            for (int j = 1; j < nb; j++) ok = ok && (indices[b + k + j] == indices[b + k] + j);
+        if (!ok) atomicExch(bad, 1);
+    }
+}
+// b16[(slice_base / nb) + kb * 32 + lane] = first column of run kb - row ; padding runs point at a valid in-range run with zero values
+__global__ void sell_block16_kernel(int rows, int nb, const long long* __restrict__ slice_ptr, const int* __restrict__ perm,
+                                    const int* __restrict__ sell_idx, short* __restrict__ b16) {
+    const int nslices = (rows + kSellC - 1) / kSellC;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int s = warp; s < nslices; s += nwarps) {
+        const long long base = slice_ptr[s];
+        const int width = (int)((slice_ptr[s + 1] - base) / kSellC);
+        const int r = sell_row(perm, rows, s * kSellC + lane);
+        for (int kb = 0; kb < width / nb; kb++) {
+            int d = 0;
+            if (r >= 0) {
+                d = sell_idx[base + (long long)(kb * nb) * kSellC + lane] - r;          // padding entries carry column r: delta 0 ...
+                if (r + d + nb > rows) d = rows - nb - r;                              // ... moved left if the run would leave the matrix
+            }
+            b16[base / nb + (long long)kb * kSellC + lane] = (short)d;
+        }
+    }
+}
 // padding lanes of the last slice (slots beyond `rows`; with a permutation they are the last slots too)
 __global__ void sell_pad_tail_kernel(int rows, int nslices, const long long* __restrict__ slice_ptr, int* __restrict__ sell_idx, double* __restrict__ sell_val) {
     const int s = nslices - 1;
@@ -113,7 +146,7 @@ __global__ void sell_values_kernel(int rows, const long long* __restrict__ indpt
 }
 
 // IDX = int: absolute columns (4 B/nnz); IDX = short: column - row deltas (2 B/nnz)
-template <bool DOT, class IDX, bool PERM = false>
+template <bool DOT, class IDX, bool PERM = false, int NB = 1>
 __global__ void __launch_bounds__(kThreads)
 spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* __restrict__ perm, const IDX* __restrict__ sell_idx, const double* __restrict__ sell_val,
                  const double* __restrict__ x, double* __restrict__ y, const CgState* __restrict__ st, double* dot_out,
@@ -132,6 +165,32 @@ spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* _
         const int r = PERM ? perm[s * kSellC + lane] : ((s * kSellC + lane < rows) ? s * kSellC + lane : -1);
         const int off = (sizeof(IDX) == 2) ? max(r, 0) : 0;            // deltas are relative to the lane's row (padding lanes: delta 0, value 0)
         double acc = 0.0;
+        if constexpr (NB > 1) {
+            // block deltas: one index per run of NB consecutive columns; the index stream of this slice starts at base / NB
+            const IDX* cb = sell_idx + base / NB + lane;
+            const int nblk = width / NB;
+            constexpr int UB = (NB == 2) ? 3 : 2;              // 6 values in flight per step, like the scalar path
+            int kb = 0;
+            for (; kb + UB <= nblk; kb += UB) {
+                double vv[UB * NB];
+                int cc[UB];
+#pragma unroll
+                for (int u = 0; u < UB; u++) {
+                    cc[u] = off + (int)__ldcs(cb + (kb + u) * kSellC);
+#pragma unroll
+                    for (int j = 0; j < NB; j++) vv[u * NB + j] = __ldcs(v + ((kb + u) * NB + j) * kSellC);
+                }
+#pragma unroll
+                for (int u = 0; u < UB; u++)
+#pragma unroll
+                    for (int j = 0; j < NB; j++) acc += vv[u * NB + j] * __ldg(x + cc[u] + j);
+            }
+            for (; kb < nblk; kb++) {
+                const int c0 = off + (int)__ldcs(cb + kb * kSellC);
+#pragma unroll
+                for (int j = 0; j < NB; j++) acc += __ldcs(v + (kb * NB + j) * kSellC) * __ldg(x + c0 + j);
+            }
+        } else {
         int k = 0;
         for (; k + 6 <= width; k += 6) {
             double vv[6];
@@ -142,6 +201,7 @@ spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* _
             for (int u = 0; u < 6; u++) acc += vv[u] * __ldg(x + cc[u]);
         }
         for (; k < width; k++) acc += __ldcs(v + k * kSellC) * __ldg(x + off + (int)__ldcs(c + k * kSellC));
+        }
         if (r >= 0) {
             y[r] = acc;
             if (DOT && r >= dot_lo && r < dot_hi) dot += acc * x[r];
