@@ -146,7 +146,7 @@ __global__ void sell_values_kernel(int rows, const long long* __restrict__ indpt
 }
 
 // IDX = int: absolute columns (4 B/nnz); IDX = short: column - row deltas (2 B/nnz)
-template <bool DOT, class IDX, bool PERM = false, int NB = 1>
+template <bool DOT, class IDX, bool PERM = false, int NB = 1, int U = 6>
 __global__ void __launch_bounds__(kThreads)
 spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* __restrict__ perm, const IDX* __restrict__ sell_idx, const double* __restrict__ sell_val,
                  const double* __restrict__ x, double* __restrict__ y, const CgState* __restrict__ st, double* dot_out,
@@ -192,13 +192,13 @@ spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* _
             }
         } else {
         int k = 0;
-        for (; k + 6 <= width; k += 6) {
-            double vv[6];
-            int cc[6];
+        for (; k + U <= width; k += U) {
+            double vv[U];
+            int cc[U];
 #pragma unroll
-            for (int u = 0; u < 6; u++) { vv[u] = __ldcs(v + (k + u) * kSellC); cc[u] = off + (int)__ldcs(c + (k + u) * kSellC); }
+            for (int u = 0; u < U; u++) { vv[u] = __ldcs(v + (k + u) * kSellC); cc[u] = off + (int)__ldcs(c + (k + u) * kSellC); }
 #pragma unroll
-            for (int u = 0; u < 6; u++) acc += vv[u] * __ldg(x + cc[u]);
+            for (int u = 0; u < U; u++) acc += vv[u] * __ldg(x + cc[u]);
         }
         for (; k < width; k++) acc += __ldcs(v + k * kSellC) * __ldg(x + off + (int)__ldcs(c + k * kSellC));
         }
