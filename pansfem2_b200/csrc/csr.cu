@@ -239,34 +239,42 @@ static int sell_build(pf2_csr* A) {
     PF2_CUDA(cudaStreamSynchronize(c->stream));
     PF2_CUDA(cudaFree(d_md));
     A->sell_max_delta = md;
-    if (md <= 32767) {
-        // banded matrix: keep the 2-byte delta stream and drop the 4-byte one (the absolute columns are recoverable)
-        // node-block structure (pattern-built matrices know their dofs per node): one delta per run of NB columns
-        // Measured on B200: hex8 (runs of 3) SpMV 0.245 -> 0.203 ms at 0.69 M dof; 2-D elasticity (runs of 2) loses 5 % (the kernel is
-        // bound by load latency x rounds there, and the rounds do not get shorter), so runs of 2 stay off unless PF2_SELL_BLOCK=1.
-        int nb = 1;
-        const char* blk = getenv("PF2_SELL_BLOCK");
-        const bool want = blk ? (atoi(blk) != 0) : (A->map_ndof == 3);
-        if (want && (A->map_ndof == 2 || A->map_ndof == 3) && A->rows > A->map_ndof) {
-            int* d_bad = nullptr;
-            PF2_TRY(dev_alloc(&d_bad, 1));
-            PF2_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), c->stream));
-            sell_block_check_kernel<<<c->grid_for(A->rows), kThreads, 0, c->stream>>>(A->rows, A->map_ndof, A->indptr, A->indices, d_bad);
-            int bad = 1;
-            PF2_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-            PF2_CUDA(cudaStreamSynchronize(c->stream));
-            cudaFree(d_bad);
-            c->launches++;
-            if (!bad) nb = A->map_ndof;
-        }
-        A->sell_nb = nb;
-        if (nb > 1) {
+    // node-block structure (pattern-built matrices know their dofs per node): one delta per run of NB consecutive columns.
+    // Measured on B200: hex8 (runs of 3) SpMV 0.245 -> 0.203 ms at 0.69 M dof; 2-D elasticity (runs of 2) loses 5 % (the kernel is
+    // bound by load latency x rounds there, and the rounds do not get shorter), so runs of 2 stay off unless PF2_SELL_BLOCK=1.
+    int nb = 1;
+    const char* blk = getenv("PF2_SELL_BLOCK");
+    const bool want = blk ? (atoi(blk) != 0) : (A->map_ndof == 3);
+    if (want && (A->map_ndof == 2 || A->map_ndof == 3) && A->rows > A->map_ndof && A->rows % A->map_ndof == 0) {
+        int* d_bad = nullptr;
+        PF2_TRY(dev_alloc(&d_bad, 1));
+        PF2_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), c->stream));
+        sell_block_check_kernel<<<c->grid_for(A->rows), kThreads, 0, c->stream>>>(A->rows, A->map_ndof, A->indptr, A->indices, d_bad);
+        int bad = 1;
+        PF2_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        PF2_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(d_bad);
+        c->launches++;
+        if (!bad) nb = A->map_ndof;
+    }
+    A->sell_nb = nb;
+    const int gblk = std::min((nslices + 7) / 8, c->sm_count * 16);
+    if (nb > 1) {
+        if (md / nb + 1 <= 32767 && getenv("PF2_SELL_BLOCK32") == nullptr) {      // PF2_SELL_BLOCK32: force the wide form (tests)
             PF2_TRY(dev_alloc(&A->sell_d16, (size_t)(A->sell_entries / nb)));
-            sell_block16_kernel<<<std::min((nslices + 7) / 8, c->sm_count * 16), kThreads, 0, c->stream>>>(A->rows, nb, A->sell_ptr, A->sell_perm, A->sell_idx, A->sell_d16);
+            sell_block_index_kernel<short><<<gblk, kThreads, 0, c->stream>>>(A->rows, nb, A->sell_ptr, A->sell_perm, A->sell_idx, A->sell_d16);
         } else {
-            PF2_TRY(dev_alloc(&A->sell_d16, (size_t)A->sell_entries));
-            sell_delta16_kernel<<<std::min((nslices + 7) / 8, c->sm_count * 16), kThreads, 0, c->stream>>>(A->rows, A->sell_entries, A->sell_ptr, A->sell_perm, A->sell_idx, A->sell_d16);
+            PF2_TRY(dev_alloc(&A->sell_b32, (size_t)(A->sell_entries / nb)));
+            sell_block_index_kernel<int><<<gblk, kThreads, 0, c->stream>>>(A->rows, nb, A->sell_ptr, A->sell_perm, A->sell_idx, A->sell_b32);
         }
+        PF2_LAUNCH_CHECK();
+        PF2_CUDA(cudaStreamSynchronize(c->stream));
+        PF2_CUDA(cudaFree(A->sell_idx));
+        A->sell_idx = nullptr;
+    } else if (md <= 32767) {
+        // banded matrix: keep the 2-byte delta stream and drop the 4-byte one (the absolute columns are recoverable)
+        PF2_TRY(dev_alloc(&A->sell_d16, (size_t)A->sell_entries));
+        sell_delta16_kernel<<<gblk, kThreads, 0, c->stream>>>(A->rows, A->sell_entries, A->sell_ptr, A->sell_perm, A->sell_idx, A->sell_d16);
         PF2_LAUNCH_CHECK();
         PF2_CUDA(cudaStreamSynchronize(c->stream));
         PF2_CUDA(cudaFree(A->sell_idx));
@@ -302,7 +310,10 @@ static int launch_sell(pf2_csr* A, const double* x, double* y, const CgState* st
                                                                                   st, dot_out, c->red.partials, c->red.ticket, A->own_lo,      \
                                                                                   A->own_hi, A->p2p_dev, A->p2p_epoch);                        \
     }
-    if (A->sell_d16) {
+    if (A->sell_b32) {         // block deltas too wide for 16 bits
+        if (A->sell_nb == 3) { if (A->sell_perm) SELL(int, true, 3, A->sell_b32) else SELL(int, false, 3, A->sell_b32) }
+        else { if (A->sell_perm) SELL(int, true, 2, A->sell_b32) else SELL(int, false, 2, A->sell_b32) }
+    } else if (A->sell_d16) {
         if (A->sell_nb == 2) { if (A->sell_perm) SELL(short, true, 2, A->sell_d16) else SELL(short, false, 2, A->sell_d16) }
         else if (A->sell_nb == 3) { if (A->sell_perm) SELL(short, true, 3, A->sell_d16) else SELL(short, false, 3, A->sell_d16) }
         else if (A->sell_perm) SELL(short, true, 1, A->sell_d16)
@@ -536,7 +547,7 @@ int pf2_csr_destroy(pf2_csr* A) {
     if (!A) return PF2_OK;
     cudaSetDevice(A->ctx->device);
     cudaStreamSynchronize(A->ctx->stream);
-    void* ptrs[] = { A->indptr, A->indices, A->data, A->F, A->diagpos, A->bmap, A->slab, A->xw, A->bw, A->st, A->sell_ptr, A->sell_perm, A->sell_idx, A->sell_d16, A->sell_val, A->p2p_dev,
+    void* ptrs[] = { A->indptr, A->indices, A->data, A->F, A->diagpos, A->bmap, A->slab, A->xw, A->bw, A->st, A->sell_ptr, A->sell_perm, A->sell_idx, A->sell_d16, A->sell_b32, A->sell_val, A->p2p_dev,
                      A->ilu, A->level_rows, A->level_rows_u };
     for (void* p : ptrs) if (p) cudaFree(p);
     if (A->h_st) cudaFreeHost(A->h_st);

@@ -93,14 +93,18 @@ __global__ void sell_block_check_kernel(int rows, int nb, const long long* __res
         const long long b = indptr[r];
         const int len = (int)(indptr[r + 1] - b);
         bool ok = (len % nb) == 0;
-        for (int k = 0; ok && k < len; k += nb)
+        for (int k = 0; ok && k < len; k += nb) {
+            ok = (indices[b + k] % nb) == 0;                     // runs start on a node boundary: deltas are exact in node units
             for (int j = 1; j < nb; j++) ok = ok && (indices[b + k + j] == indices[b + k] + j);
+        }
         if (!ok) atomicExch(bad, 1);
     }
 }
-// b16[(slice_base / nb) + kb * 32 + lane] = first column of run kb - row ; padding runs point at a valid in-range run with zero values
-__global__ void sell_block16_kernel(int rows, int nb, const long long* __restrict__ slice_ptr, const int* __restrict__ perm,
-                                    const int* __restrict__ sell_idx, short* __restrict__ b16) {
+// bidx[(slice_base / nb) + kb * 32 + lane] = (first column of run kb - first row of the lane's node) / nb : deltas in NODE units, so
+// they fit 16 bits up to 32 767 nodes of bandwidth (hex8 meshes with planes of up to ~10 900 nodes); wider meshes store them as int32
+template <class OUT>
+__global__ void sell_block_index_kernel(int rows, int nb, const long long* __restrict__ slice_ptr, const int* __restrict__ perm,
+                                        const int* __restrict__ sell_idx, OUT* __restrict__ bidx) {
     const int nslices = (rows + kSellC - 1) / kSellC;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -108,13 +112,11 @@ __global__ void sell_block16_kernel(int rows, int nb, const long long* __restric
         const long long base = slice_ptr[s];
         const int width = (int)((slice_ptr[s + 1] - base) / kSellC);
         const int r = sell_row(perm, rows, s * kSellC + lane);
+        const int rbase = (r >= 0) ? r - r % nb : 0;
         for (int kb = 0; kb < width / nb; kb++) {
-            int d = 0;
-            if (r >= 0) {
-                d = sell_idx[base + (long long)(kb * nb) * kSellC + lane] - r;          // padding entries carry column r: delta 0 ...
-                if (r + d + nb > rows) d = rows - nb - r;                              // ... moved left if the run would leave the matrix
-            }
-            b16[base / nb + (long long)kb * kSellC + lane] = (short)d;
+            // padding entries carry column r, i.e. node delta 0: a run inside the matrix with zero values
+            const int d = (r >= 0) ? (sell_idx[base + (long long)(kb * nb) * kSellC + lane] - rbase) / nb : 0;
+            bidx[base / nb + (long long)kb * kSellC + lane] = (OUT)d;
         }
     }
 }
@@ -163,7 +165,8 @@ spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* _
         const double* v = sell_val + base + lane;
         const IDX* c = sell_idx + base + lane;
         const int r = PERM ? perm[s * kSellC + lane] : ((s * kSellC + lane < rows) ? s * kSellC + lane : -1);
-        const int off = (sizeof(IDX) == 2) ? max(r, 0) : 0;            // deltas are relative to the lane's row (padding lanes: delta 0, value 0)
+        const int off = (NB > 1) ? max(r, 0) - max(r, 0) % NB                // block deltas: node units relative to the first row of the lane's node
+                                 : ((sizeof(IDX) == 2) ? max(r, 0) : 0);     // per-entry deltas are relative to the lane's row (padding lanes: delta 0, value 0)
         double acc = 0.0;
         if constexpr (NB > 1) {
             // block deltas: one index per run of NB consecutive columns; the index stream of this slice starts at base / NB
@@ -176,7 +179,7 @@ spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* _
                 int cc[UB];
 #pragma unroll
                 for (int u = 0; u < UB; u++) {
-                    cc[u] = off + (int)__ldcs(cb + (kb + u) * kSellC);
+                    cc[u] = off + NB * (int)__ldcs(cb + (kb + u) * kSellC);
 #pragma unroll
                     for (int j = 0; j < NB; j++) vv[u * NB + j] = __ldcs(v + ((kb + u) * NB + j) * kSellC);
                 }
@@ -186,7 +189,7 @@ spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* _
                     for (int j = 0; j < NB; j++) acc += vv[u * NB + j] * __ldg(x + cc[u] + j);
             }
             for (; kb < nblk; kb++) {
-                const int c0 = off + (int)__ldcs(cb + kb * kSellC);
+                const int c0 = off + NB * (int)__ldcs(cb + kb * kSellC);
 #pragma unroll
                 for (int j = 0; j < NB; j++) acc += __ldcs(v + (kb * NB + j) * kSellC) * __ldg(x + c0 + j);
             }

@@ -94,7 +94,8 @@ struct pf2_csr {
     int* sell_perm = nullptr;      // SELL-C-sigma: row of every slot (slice*32 + lane), -1 = padding; null = natural order
     int* sell_idx = nullptr;       // absolute columns (dropped when the 16-bit delta form is usable)
     short* sell_d16 = nullptr;     // column - row, 2 bytes per stored entry (|delta| <= 32767)
-    int sell_nb = 1;               // > 1: sell_d16 holds ONE delta per run of sell_nb consecutive columns (block deltas)
+    int sell_nb = 1;               // > 1: ONE node-unit delta per run of sell_nb consecutive columns, in sell_d16 or (wide meshes) sell_b32
+    int* sell_b32 = nullptr;
     int sell_max_delta = 0;
     double* sell_val = nullptr;
     long long sell_entries = 0;

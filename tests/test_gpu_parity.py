@@ -134,6 +134,38 @@ def test_spmv_all_kernel_variants(ctx):
         A.close()
 
 
+@pytest.mark.parametrize("env", [{}, {"PF2_SELL_BLOCK32": "1"}, {"PF2_SELL_BLOCK": "1"}, {"PF2_SELL_BLOCK": "0"}])
+def test_spmv_sell_index_forms(ctx, env):
+    """The SELL mirror's index streams: per-entry 16-bit deltas, one node-unit delta per run of NDOF columns (int16, and int32 for
+    meshes wider than 32 767 nodes - forced here), with and without the run form in 2-D.  Same product, same solve."""
+    old = {k: os.environ.get(k) for k in ("PF2_SELL_BLOCK32", "PF2_SELL_BLOCK")}
+    try:
+        for k in old:
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        for P in (problems.cantilever3d(10, 6, 5), problems.cantilever2d(40, 24)):
+            rng = np.random.default_rng(17)
+            rho = rng.uniform(0.05, 1.0, P.nelem)
+            mesh = capi.Mesh(ctx, P.coords, P.conn)
+            dm = capi.DofMap(ctx, P.nnode, P.ndof, P.fixed)
+            A = capi.Csr.pattern(ctx, mesh, dm)
+            A.assemble(mesh, dm, P.eq, (P.E0, P.E1, P.poisson, P.penal, P.thickness), P.loads, rho=ctx.array(rho))
+            indptr, indices, data, F = A.download()
+            x = rng.uniform(-1, 1, A.rows)
+            y = A.spmv_host(x)
+            yo = orc.system_from_csr(indptr.astype(np.int32), indices, data).spmv(x)
+            assert rel(y, yo) < 1e-13
+            xs, it, rr = A.solve_host(capi.SOLVER_SCALINGCG, F)
+            assert rr < 1e-10
+            for o in (A, dm, mesh):
+                o.close()
+    finally:
+        for k, v in old.items():
+            os.environ.pop(k, None)
+            if v is not None:
+                os.environ[k] = v
+
+
 def test_spmv_ragged_and_empty_rows(ctx):
     rng = np.random.default_rng(9)
     n = 1000
