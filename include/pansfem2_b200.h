@@ -51,7 +51,11 @@ enum { PF2_EQ_PLANESTRAIN = 0, PF2_EQ_SOLID = 1, PF2_EQ_HEAT = 2 };
  * so the legacy values 0, 1, 2 are themselves valid codes.  The rule must belong to the shape's reference domain
  * (triangle, square, tetrahedron, cube), otherwise PF2_E_INVALID. */
 enum { PF2_PHYS_PLANESTRAIN = 0, PF2_PHYS_SOLID = 1, PF2_PHYS_HEAT = 2, PF2_PHYS_PLANESTRESS = 3, PF2_PHYS_PLANESTRAIN_SRI = 4, PF2_PHYS_MASS = 5,
-       PF2_PHYS_PLANESTRAIN_BBAR = 6, PF2_PHYS_MASS2 = 7, PF2_PHYS_PLANESTRAIN_WT = 8 };
+       PF2_PHYS_PLANESTRAIN_BBAR = 6, PF2_PHYS_MASS2 = 7, PF2_PHYS_PLANESTRAIN_WT = 8, PF2_PHYS_ADVDIFF = 9 };
+/* PF2_PHYS_ADVDIFF: the scalar advection-diffusion routines of Advection.h on any 2-D shape / rule; the quad2 field of the code is
+ * the MASK of the routines to sum: Advection (Advection.h:19), Diffusion (:135), AdvectionSUPG (:47), AdvectionShockCapturing (:91),
+ * Mass (:161), MassSUPG (:188).  pf2_element_matrix takes (E, V, t) = (ax, ay, k); systems are assembled by pf2_advdiff_assemble. */
+enum { PF2_ADV_ADVECTION = 1, PF2_ADV_DIFFUSION = 2, PF2_ADV_SUPG = 4, PF2_ADV_SHOCK = 8, PF2_ADV_MASS = 16, PF2_ADV_MASS_SUPG = 32 };
 enum { PF2_SHAPE_DEFAULT = 0, PF2_SHAPE_T3 = 1, PF2_SHAPE_T6 = 2, PF2_SHAPE_Q4 = 3, PF2_SHAPE_Q8 = 4, PF2_SHAPE_TET4 = 5,
        PF2_SHAPE_HEX8 = 6, PF2_SHAPE_HEX20 = 7 };
 enum { PF2_QUAD_DEFAULT = 0, PF2_QUAD_G1TRI = 1, PF2_QUAD_G3TRI = 2, PF2_QUAD_G1SQ = 3, PF2_QUAD_G4SQ = 4, PF2_QUAD_G9SQ = 5,
@@ -142,6 +146,15 @@ int pf2_csr_device_data(pf2_csr* A, double** data_dev);
 int pf2_assemble(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq, const double* modulus_dev, const double* rho_dev,
                  const double params[5], int nload, const int* load_node_host, const int* load_dof_host,
                  const double* load_val_host);
+/* The element loops of sample/advection/sample_advectiondiffusion_static.cpp:42-55 and ..._dynamic.cpp:51-70 as one launch:
+ *   K  = cm*(M + MS) + ck*(A + D + AS + SC)                         over the routines selected in eq (PF2_PHYS_ADVDIFF),
+ *   F  = (cm*(M + MS) - cf*(A + D + AS + SC)) * T_e - K * T_fixed    (Assembling.h:22-43; the first part only when T_nodal_dev is given)
+ * static sample: cm = 0, ck = 1, cf = 0, T_nodal_dev = NULL; dynamic sample: cm = 1/dt, ck = theta, cf = 1 - theta.
+ * prm = {ax, ay, k, cm, ck, cf}; vel_dev: per-element velocity (nelem*2, the dynamic sample's rotating field) or NULL for the uniform
+ * (ax, ay).  T_nodal_dev: the nodal field (nnode); fixed nodes are read from the dof map's Dirichlet values.  One dof per node;
+ * the matrix is non-symmetric: solve with PF2_SOLVER_BICGSTAB and friends, then pf2_disassemble. */
+int pf2_advdiff_assemble(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq, const double* vel_dev, const double prm[6],
+                         const double* T_nodal_dev);
 /* one element matrix, host in / host out: the reference's per-element call kept for parity
  * (PlaneStrain.h:21-58, Solid.h:21-64, HeatTransfer.h:20-43).  xe: npe*dim, Ke_out: (npe*ndof)^2 row-major. */
 int pf2_element_matrix(pf2_ctx* ctx, int eq, const double* xe_host, double E, double V, double t, double* Ke_host);

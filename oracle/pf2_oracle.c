@@ -593,6 +593,125 @@ void orc_assemble_numeric(orc_system* S, int eq, const double* coords, int nelem
 }
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Advection-diffusion element family   src/FEM/Equation/Advection.h
+ *   Advection :19-43   AdvectionSUPG :47-87   AdvectionShockCapturing :91-131   Diffusion :135-157   Mass :161-184   MassSUPG :188-228
+ * one dof per node, 2-D shapes; every product below is evaluated in the order the reference's Matrix / Vector operators evaluate
+ * the expression written there (left to right), so the result is bit-identical to the compiled reference.
+ * terms: 1 Advection, 2 Diffusion, 4 AdvectionSUPG, 8 AdvectionShockCapturing, 16 Mass, 32 MassSUPG.
+ * ---------------------------------------------------------------------------------------------------------- */
+enum { ADV_A = 1, ADV_D = 2, ADV_S = 4, ADV_SC = 8, ADV_M = 16, ADV_MS = 32 };
+static int npe_of_shape(int shape) { static const int n[8] = { 0, 3, 6, 4, 8, 4, 8, 20 }; return n[shape]; }
+
+static void adv_one_term(int shape, int quad, int term, const double* xe, double ax, double ay, double k, double* Ke) {
+    const int npe = npe_of_shape(shape), ng = quad_count(quad);
+    const double a[2] = { ax, ay };
+    memset(Ke, 0, sizeof(double) * npe * npe);
+    for (int g = 0; g < ng; g++) {
+        double r[3], w[3], N[ORC_MAX_NPE], dNdr[3 * ORC_MAX_NPE], dXdr[9], inv[9], dNdX[3 * ORC_MAX_NPE];
+        quad_point(quad, g, r, w);
+        shape_n2d(shape, r, N);
+        shape_dndr(shape, r, dNdr);
+        matmul(2, npe, 2, dNdr, xe, dXdr);
+        double J = det_d(2, dXdr);
+        inv_d(2, dXdr, inv);
+        matmul(2, 2, npe, inv, dNdr, dNdX);
+        double tau = 0.0;
+        if (term == ADV_S || term == ADV_SC || term == ADV_MS) {        /* Advection.h:69-82, 113-126, 210-223 */
+            double norm = 0.0;
+            norm += pow(a[0], 2.0); norm += pow(a[1], 2.0);             /* Vector<T>::Norm  Vector.h:297-303 */
+            norm = sqrt(norm);
+            double sum = 0.0;
+            for (int i = 0; i < npe; i++) {
+                double v = 0.0;                                         /* dNdX.Transpose()*a */
+                for (int l = 0; l < 2; l++) v += dNdX[l * npe + i] * a[l];
+                sum += fabs(v) / norm;
+            }
+            double he = 2.0 / sum;
+            double alpha = 0.5 * norm * he / k;
+            tau = (term == ADV_SC) ? 0.5 * norm * he : 0.5 * he / norm;
+            if (alpha <= 3.0) tau *= alpha / 3.0; else tau *= 1.0;
+        }
+        for (int i = 0; i < npe; i++) {
+            /* the row-i factors that precede the last product */
+            double m2[2] = { 0.0, 0.0 }, v1 = 0.0;
+            if (term == ADV_A) { m2[0] = N[i] * a[0]; m2[1] = N[i] * a[1]; }                            /* N*c.Transpose() */
+            else if (term == ADV_D) { m2[0] = dNdX[i] * k; m2[1] = dNdX[npe + i] * k; }                 /* _k*dNdX.Transpose() */
+            else if (term == ADV_SC) { m2[0] = dNdX[i] * tau; m2[1] = dNdX[npe + i] * tau; }            /* tau*dNdX.Transpose() */
+            else if (term == ADV_S || term == ADV_MS) {
+                for (int l = 0; l < 2; l++) v1 += (dNdX[l * npe + i] * tau) * a[l];                     /* (tau*dNdX.Transpose())*a */
+                m2[0] = v1 * a[0]; m2[1] = v1 * a[1];                                                   /* ...*a.Transpose() */
+            }
+            for (int j = 0; j < npe; j++) {
+                double v;
+                if (term == ADV_M) v = N[i] * N[j];                                                     /* N*N.Transpose() */
+                else if (term == ADV_MS) v = v1 * N[j];                                                 /* ...*N.Transpose() */
+                else { v = 0.0; for (int l = 0; l < 2; l++) v += m2[l] * dNdX[l * npe + j]; }           /* ...*dNdX */
+                Ke[i * npe + j] += v * J * w[0] * w[1];
+            }
+        }
+    }
+}
+
+/* sum of the selected terms of `group` in the samples' order; returns 0 when none is selected (Ke zeroed) */
+static int adv_sum(int shape, int quad, int terms, int group, const double* xe, double ax, double ay, double k, double* Ke) {
+    static const int order[6] = { ADV_A, ADV_D, ADV_S, ADV_SC, ADV_M, ADV_MS };
+    const int npe = npe_of_shape(shape);
+    double P[ORC_MAX_NPE * ORC_MAX_NPE];
+    int any = 0;
+    memset(Ke, 0, sizeof(double) * npe * npe);
+    for (int q = 0; q < 6; q++) {
+        if (!(terms & group & order[q])) continue;
+        adv_one_term(shape, quad, order[q], xe, ax, ay, k, P);
+        if (!any) memcpy(Ke, P, sizeof(double) * npe * npe);
+        else for (int i = 0; i < npe * npe; i++) Ke[i] = Ke[i] + P[i];
+        any = 1;
+    }
+    return any;
+}
+
+void orc_advdiff_element(int shape, int quad, int terms, const double* xe, double ax, double ay, double k, double* Ke) {
+    adv_sum(shape, quad, terms, 63, xe, ax, ay, k, Ke);
+}
+
+/* dt == 0: sample_advectiondiffusion_static.cpp:42-55 (Ke = A + B + C [+ D]); dt > 0: one step of
+ * sample_advectiondiffusion_dynamic.cpp:51-70 (Ke = (M + MS)/dt + theta*(A + D + AS), Fe = ((M + MS)/dt - (1 - theta)*(A + D + AS))*Te).
+ * Tn (nnode): nodal field with the Dirichlet values already written on the fixed nodes; vel: nelem*2. */
+void orc_advdiff_assemble(orc_system* S, int shape, int quad, int terms, const double* coords, int nelem, const int* conn,
+                          const int* nodetoglobal, const double* vel, double k, double dt, double theta, const double* Tn) {
+    const int npe = npe_of_shape(shape);
+    memset(S->data, 0, sizeof(double) * (size_t)S->indptr[S->n]);
+    memset(S->F, 0, sizeof(double) * (size_t)S->n);
+    double KK[ORC_MAX_NPE * ORC_MAX_NPE], MM[ORC_MAX_NPE * ORC_MAX_NPE], Ke[ORC_MAX_NPE * ORC_MAX_NPE], Fe[ORC_MAX_NPE], xe[2 * ORC_MAX_NPE];
+    for (int e = 0; e < nelem; e++) {
+        const int* el = conn + (size_t)e * npe;
+        for (int a = 0; a < npe; a++) for (int d = 0; d < 2; d++) xe[a * 2 + d] = coords[(size_t)el[a] * 2 + d];
+        adv_sum(shape, quad, terms, ADV_A | ADV_D | ADV_S | ADV_SC, xe, vel[2 * e], vel[2 * e + 1], k, KK);
+        if (dt == 0.0) {
+            memcpy(Ke, KK, sizeof(double) * npe * npe);
+            for (int i = 0; i < npe; i++) Fe[i] = 0.0;
+        } else {
+            adv_sum(shape, quad, terms, ADV_M | ADV_MS, xe, vel[2 * e], vel[2 * e + 1], k, MM);
+            for (int i = 0; i < npe * npe; i++) Ke[i] = MM[i] / dt + KK[i] * theta;
+            for (int i = 0; i < npe; i++) {
+                double v = 0.0;
+                for (int j = 0; j < npe; j++) v += (MM[i * npe + j] / dt - KK[i * npe + j] * (1.0 - theta)) * Tn[el[j]];
+                Fe[i] = v;
+            }
+        }
+        for (int i = 0; i < npe; i++) {
+            int r = nodetoglobal[el[i]];
+            if (r == -1) continue;
+            for (int j = 0; j < npe; j++) {
+                int c = nodetoglobal[el[j]];
+                if (c != -1) S->data[find_col(S, r, c)] += Ke[i * npe + j];         /* Assembling.h:30 / :55 */
+                else S->F[r] -= Ke[i * npe + j] * Tn[el[j]];                        /* Assembling.h:34 / :59 */
+            }
+            if (dt != 0.0) S->F[r] += Fe[i];                                        /* Assembling.h:38 */
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------------
  * CSR<T>::operator*   src/LinearAlgebra/Models/CSR.h:109-122 (the reference's only OpenMP loop)
  * ---------------------------------------------------------------------------------------------------------- */
 void orc_spmv(const orc_system* S, const double* x, double* y) {

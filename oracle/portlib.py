@@ -285,3 +285,31 @@ def levelset_run(coords, conn, fixed, loads, phifixed_nodes, prm, tmax, phi0, st
                                 len(pn), _p(pn, np.int32), _p(prm, np.float64), int(tmax),
                                 _p(phi, np.float64), _p(st, np.float64), _p(u, np.float64), _p(hist, np.float64), C.byref(conv))
     return dict(hist=hist[:it], phi=phi, str=st, u=u, iters=it, converged=bool(conv.value))
+
+
+ADV_TERMS = dict(advection=1, diffusion=2, supg=4, shock=8, mass=16, mass_supg=32)
+_NPE = {1: 3, 2: 6, 3: 4, 4: 8}
+
+
+def advdiff_element(shape, quad, terms, xe, ax, ay, k):
+    """Sum of the selected Advection.h routines (Advection.h:19-229) on one element <SF, IC>."""
+    xe = _f64(xe)
+    npe = _NPE[shape]
+    Ke = np.zeros((npe, npe))
+    lib().orc_advdiff_element(shape, quad, terms, _p(xe, np.float64), C.c_double(ax), C.c_double(ay), C.c_double(k), _p(Ke, np.float64))
+    return Ke
+
+
+def advdiff_system(shape, quad, terms, coords, conn, fixed_nodes, fixed_vals, vel, k, dt=0.0, theta=0.5, Tn=None):
+    """dt = 0: K, F of sample_advectiondiffusion_static.cpp; dt > 0: one step of sample_advectiondiffusion_dynamic.cpp.
+    Returns (System, nodetoglobal, Tn with the Dirichlet values written)."""
+    coords, conn, vel = _f64(coords), _i32(conn), _f64(vel)
+    nnode = coords.shape[0]
+    fn = _i32(fixed_nodes)
+    kdeg, n2g, ufix = dofmap(nnode, 1, (fn, np.zeros_like(fn), _f64(fixed_vals)))
+    T = np.zeros(nnode) if Tn is None else _f64(Tn).copy()
+    T[fn] = _f64(fixed_vals)                       # SetDirichlet (BoundaryCondition.h:20-25)
+    S = System(lib().orc_pattern(nnode, 1, conn.shape[1], conn.shape[0], _p(conn, np.int32), _p(n2g, np.int32), kdeg))
+    lib().orc_advdiff_assemble(S.h, shape, quad, terms, _p(coords, np.float64), conn.shape[0], _p(conn, np.int32), _p(n2g, np.int32),
+                               _p(vel, np.float64), C.c_double(k), C.c_double(dt), C.c_double(theta), _p(T, np.float64))
+    return S, n2g, T

@@ -453,6 +453,107 @@ void* ref_advection_system(int nnode, const double* coords, int nelem, const int
     return sys;
 }
 
+// ---- the advection-diffusion element family (Advection.h:19-229) for any 2-D <SF, IC>, and the systems the two advection samples
+//      build from it.  terms: 1 Advection, 2 Diffusion, 4 AdvectionSUPG, 8 AdvectionShockCapturing, 16 Mass, 32 MassSUPG. ----
+}   // extern "C"
+namespace {
+enum { ADV_A = 1, ADV_D = 2, ADV_S = 4, ADV_SC = 8, ADV_M = 16, ADV_MS = 32 };
+template<template<class>class SF, template<class>class IC>
+void adv_term(int term, Matrix<double>& Ke, N2E& n2e, const std::vector<int>& el, std::vector<Vector<double> >& x, double ax, double ay, double k) {
+    switch (term) {
+        case ADV_A: Advection<double, SF, IC>(Ke, n2e, el, { 0 }, x, ax, ay); break;
+        case ADV_D: Diffusion<double, SF, IC>(Ke, n2e, el, { 0 }, x, k); break;
+        case ADV_S: AdvectionSUPG<double, SF, IC>(Ke, n2e, el, { 0 }, x, ax, ay, k); break;
+        case ADV_SC: AdvectionShockCapturing<double, SF, IC>(Ke, n2e, el, { 0 }, x, ax, ay, k); break;
+        case ADV_M: Mass<double, SF, IC>(Ke, n2e, el, { 0 }, x); break;
+        default: MassSUPG<double, SF, IC>(Ke, n2e, el, { 0 }, x, ax, ay, k); break;
+    }
+}
+void adv_term_sel(int shape, int quad, int term, Matrix<double>& Ke, N2E& n2e, const std::vector<int>& el, std::vector<Vector<double> >& x, double ax, double ay, double k) {
+#define ADV_TRI(SF) do { if (quad == QUAD_G3TRI) adv_term<SF, Gauss3Triangle>(term, Ke, n2e, el, x, ax, ay, k); else adv_term<SF, Gauss1Triangle>(term, Ke, n2e, el, x, ax, ay, k); } while (0)
+#define ADV_SQ(SF) do { if (quad == QUAD_G1SQ) adv_term<SF, Gauss1Square>(term, Ke, n2e, el, x, ax, ay, k); else if (quad == QUAD_G9SQ) adv_term<SF, Gauss9Square>(term, Ke, n2e, el, x, ax, ay, k); \
+                        else adv_term<SF, Gauss4Square>(term, Ke, n2e, el, x, ax, ay, k); } while (0)
+    switch (shape) {
+        case SHAPE_T3: ADV_TRI(ShapeFunction3Triangle); break;
+        case SHAPE_T6: ADV_TRI(ShapeFunction6Triangle); break;
+        case SHAPE_Q8: ADV_SQ(ShapeFunction8Square); break;
+        default: ADV_SQ(ShapeFunction4Square); break;
+    }
+#undef ADV_TRI
+#undef ADV_SQ
+}
+// sum of the selected terms among `group`, in the samples' order (A + D + AS [+ SC]; M + MS)
+bool adv_sum(int shape, int quad, int terms, int group, Matrix<double>& S, N2E& n2e, const std::vector<int>& el, std::vector<Vector<double> >& x, double ax, double ay, double k) {
+    bool any = false;
+    static const int order[6] = { ADV_A, ADV_D, ADV_S, ADV_SC, ADV_M, ADV_MS };
+    for (int t : order) {
+        if (!(terms & group & t)) continue;
+        Matrix<double> P;
+        adv_term_sel(shape, quad, t, P, n2e, el, x, ax, ay, k);
+        if (!any) S = P; else S = S + P;
+        any = true;
+    }
+    if (!any) {
+        S = Matrix<double>(el.size(), el.size());
+        n2e = N2E(el.size(), std::vector<std::pair<int, int> >(1));
+        for (size_t i = 0; i < el.size(); i++) n2e[i][0] = std::make_pair(0, (int)i);
+    }
+    return any;
+}
+}   // namespace
+extern "C" {
+
+// one term (or the sum of several) on one element
+int ref_advdiff_element(int shape, int quad, int terms, int npe, const double* xe, double ax, double ay, double k, double* Ke_out) {
+    std::vector<Vector<double> > x = make_nodes(2, npe, xe);
+    std::vector<int> element(npe);
+    std::iota(element.begin(), element.end(), 0);
+    Matrix<double> Ke;
+    N2E n2e;
+    adv_sum(shape, quad, terms, 63, Ke, n2e, element, x, ax, ay, k);
+    for (int i = 0; i < npe; i++) for (int j = 0; j < npe; j++) Ke_out[i * npe + j] = Ke(i, j);
+    return npe;
+}
+
+// dt == 0: the static sample's system (sample_advectiondiffusion_static.cpp:42-55), Ke = A + B + C [+ D];
+// dt > 0: one step of the dynamic sample (sample_advectiondiffusion_dynamic.cpp:51-70), Ke = (M + MS)/dt + theta*(A + D + AS),
+// Fe = ((M + MS)/dt - (1 - theta)*(A + D + AS))*Te.  vel: per-element velocity (nelem*2); Tn: nodal field (fixed nodes are overwritten
+// with their Dirichlet values, as SetDirichlet does).
+void* ref_advdiff_system(int shape, int quad, int terms, int nnode, const double* coords, int npe, int nelem, const int* conn, int nfixed,
+                         const int* fnode, const double* fval, const double* vel, double k, double dt, double theta, const double* Tn) {
+    std::vector<Vector<double> > x = make_nodes(2, nnode, coords);
+    std::vector<std::vector<int> > elements = make_elements(npe, nelem, conn);
+    BCList ufixed(nfixed);
+    for (int i = 0; i < nfixed; i++) ufixed[i] = { { fnode[i], 0 }, fval[i] };
+    RefSystem* sys = new RefSystem();
+    std::vector<Vector<double> > T(x.size(), Vector<double>(1));
+    if (Tn) for (int i = 0; i < nnode; i++) T[i](0) = Tn[i];
+    sys->nodetoglobal = std::vector<std::vector<int> >(x.size(), std::vector<int>(1, 0));
+    SetDirichlet(T, sys->nodetoglobal, ufixed);
+    int KDEGREE = Renumbering(sys->nodetoglobal);
+    LILCSR<double> K(KDEGREE, KDEGREE);
+    sys->F.assign(KDEGREE, 0.0);
+    for (int e = 0; e < nelem; e++) {
+        std::vector<int> element = elements[e];
+        const double ax = vel[2 * e], ay = vel[2 * e + 1];
+        N2E nodetoelement;
+        Matrix<double> KK;     // (a default-constructed Matrix must be assigned before it dies: Matrix.h:91-99 leaves `values` dangling)
+        adv_sum(shape, quad, terms, ADV_A | ADV_D | ADV_S | ADV_SC, KK, nodetoelement, element, x, ax, ay, k);
+        if (dt == 0.0) {
+            Assembling(K, sys->F, T, KK, sys->nodetoglobal, nodetoelement, element);
+        } else {
+            Matrix<double> MM;
+            adv_sum(shape, quad, terms, ADV_M | ADV_MS, MM, nodetoelement, element, x, ax, ay, k);
+            Vector<double> Te = ElementVector(T, nodetoelement, element);
+            Matrix<double> Ke = MM/dt + theta*KK;
+            Vector<double> Fe = (MM/dt - (1.0 - theta)*KK)*Te;
+            Assembling(K, sys->F, T, Ke, Fe, sys->nodetoglobal, nodetoelement, element);
+        }
+    }
+    sys->K = new CSR<double>(K);
+    return sys;
+}
+
 // ---- the level-set design loop of sample/optimize/sample_optimize_levelset.cpp:75-192, element routines and helpers
 //      called exactly as there (PlaneStressStiffness, ReactionDiffusion{ConsistentMass,Stiffness,Reaction},
 //      InterpolateNodalFromElemental / InterpolateElementalFromNodal, ScalingCG) ----

@@ -43,6 +43,7 @@ def lib():
         _lib.ref_mma_create.restype = C.c_void_p
         _lib.ref_conlin_create.restype = C.c_void_p
         _lib.ref_advection_system.restype = C.c_void_p
+        _lib.ref_advdiff_system.restype = C.c_void_p
         _lib.ref_system_nnz.restype = C.c_longlong
     return _lib
 
@@ -330,3 +331,26 @@ def advection_system(coords, conn, fixed_nodes, fixed_vals, a=1.0, theta_deg=60.
     fn, fv = _i32(fixed_nodes), _f64(fixed_vals)
     return System(lib().ref_advection_system(coords.shape[0], _p(coords, np.float64), conn.shape[0], _p(conn, np.int32), len(fn),
                                              _p(fn, np.int32), _p(fv, np.float64), C.c_double(a), C.c_double(theta_deg), C.c_double(k)))
+
+
+ADV_TERMS = dict(advection=1, diffusion=2, supg=4, shock=8, mass=16, mass_supg=32)
+_NPE = {1: 3, 2: 6, 3: 4, 4: 8}
+
+
+def advdiff_element(shape, quad, terms, xe, ax, ay, k):
+    """Sum of the selected Advection.h routines (Advection.h:19-229) on one element <SF, IC>."""
+    xe = _f64(xe)
+    npe = _NPE[shape]
+    Ke = np.zeros((npe, npe))
+    lib().ref_advdiff_element(shape, quad, terms, npe, _p(xe, np.float64), C.c_double(ax), C.c_double(ay), C.c_double(k), _p(Ke, np.float64))
+    return Ke
+
+
+def advdiff_system(shape, quad, terms, coords, conn, fixed_nodes, fixed_vals, vel, k, dt=0.0, theta=0.5, Tn=None):
+    """dt = 0: K, F of sample_advectiondiffusion_static.cpp; dt > 0: one step of sample_advectiondiffusion_dynamic.cpp."""
+    coords, conn, vel = _f64(coords), _i32(conn), _f64(vel)
+    fn, fv = _i32(fixed_nodes), _f64(fixed_vals)
+    Tn = None if Tn is None else _f64(Tn)
+    return System(lib().ref_advdiff_system(shape, quad, terms, coords.shape[0], _p(coords, np.float64), conn.shape[1], conn.shape[0],
+                                           _p(conn, np.int32), len(fn), _p(fn, np.int32), _p(fv, np.float64), _p(vel, np.float64),
+                                           C.c_double(k), C.c_double(dt), C.c_double(theta), _p(Tn, np.float64)))

@@ -223,6 +223,7 @@ int sens_generic_launch(pf2_mesh* mesh, const EqInfo& q, const double* u_nodal, 
                         double* dfdrho, double* r_nodal);
 int element_generic_launch(pf2_ctx* ctx, const EqInfo& q, const double* xe_dev, double E, double t, double* Ke_dev);
 int mf_update(pf2_csr* A, pf2_mesh* mesh, const double* modulus_dev, const double* rho_dev, const double params[5]);
+int advdiff_element_launch(pf2_ctx* ctx, const EqInfo& q, const double* xe_dev, double ax, double ay, double k, double* Ke_dev);
 
 // numeric assembly with the nodal loads already on the device (the design loop keeps them resident)
 int assemble_device(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq, const double* modulus_dev, const double* rho_dev,
@@ -230,6 +231,7 @@ int assemble_device(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq, const d
     EqInfo q;
     PF2_TRY(decode_eq(eq, params[2], &q));
     PF2_CHECK(A->bmap != nullptr, "matrix was not built by pf2_csr_pattern");
+    PF2_CHECK(q.phys != PF2_PHYS_ADVDIFF, "advection-diffusion selections are assembled by pf2_advdiff_assemble");
     PF2_CHECK(q.npe == mesh->npe && q.dim == mesh->dim, "equation does not match the mesh's element type");
     PF2_CHECK(q.ndof == map->ndof, "equation does not match the dof map (the reference asserts doulist.size(), PlaneStrain.h:22)");
     PF2_CHECK(A->map_nelem == mesh->nelem && A->map_npe == mesh->npe && A->map_ndof == map->ndof, "pattern built for another mesh");
@@ -271,6 +273,7 @@ int compliance_sens_device(pf2_mesh* mesh, int eq, const double* u_nodal, const 
     EqInfo q;
     PF2_TRY(decode_eq(eq, params[2], &q));
     PF2_CHECK(q.npe == mesh->npe && q.dim == mesh->dim, "equation does not match the mesh");
+    PF2_CHECK(q.phys != PF2_PHYS_ADVDIFF, "no compliance / sensitivity pass for the (non-symmetric) advection-diffusion operator");
     const int ndof = q.ndof;
     if (r_nodal) PF2_CUDA(cudaMemsetAsync(r_nodal, 0, sizeof(double) * (size_t)mesh->nnode * ndof, s));
     if (!q.fast) return sens_generic_launch(mesh, q, u_nodal, rho, params, f_dev, dfdrho, r_nodal);
@@ -320,7 +323,8 @@ int pf2_element_matrix(pf2_ctx* ctx, int eq, const double* xe_host, double E, do
     if (!ctx->elem_scratch) PF2_TRY(dev_alloc(&ctx->elem_scratch, (size_t)64 + 3600));      // hex20: 60 coordinates, 60 x 60 entries
     double *xe = ctx->elem_scratch, *Ke = ctx->elem_scratch + 64;
     PF2_CUDA(cudaMemcpyAsync(xe, xe_host, sizeof(double) * npe * dim, cudaMemcpyHostToDevice, ctx->stream));
-    if (!q.fast) PF2_TRY(element_generic_launch(ctx, q, xe, E, t, Ke));
+    if (q.phys == PF2_PHYS_ADVDIFF) PF2_TRY(advdiff_element_launch(ctx, q, xe, E, V, t, Ke));      // (E, V, t) = (ax, ay, k)
+    else if (!q.fast) PF2_TRY(element_generic_launch(ctx, q, xe, E, t, Ke));
     else {
         if (q.legacy == PF2_EQ_PLANESTRAIN) element_matrix_kernel<PF2_EQ_PLANESTRAIN><<<1, 32, 0, ctx->stream>>>(xe, E, V, t, Ke);
         else if (q.legacy == PF2_EQ_SOLID) element_matrix_kernel<PF2_EQ_SOLID><<<1, 32, 0, ctx->stream>>>(xe, E, V, t, Ke);

@@ -41,8 +41,10 @@ static int quad_domain(int quad) {
 int decode_eq(int eq, double V, EqInfo* out) {
     EqInfo q;
     q.phys = eq & 0xff; q.shape = (eq >> 8) & 0xff; q.quad = (eq >> 16) & 0xff; q.quad2 = (eq >> 24) & 0xff;
-    PF2_CHECK(eq >= 0 && q.phys <= PF2_PHYS_PLANESTRAIN_WT, "unknown equation");
-    PF2_CHECK(q.shape <= PF2_SHAPE_HEX20 && q.quad <= PF2_QUAD_G27CUBE && q.quad2 <= PF2_QUAD_G27CUBE, "unknown shape function / integration rule");
+    PF2_CHECK(eq >= 0 && q.phys <= PF2_PHYS_ADVDIFF, "unknown equation");
+    const bool adv = q.phys == PF2_PHYS_ADVDIFF;     // quad2 carries the PF2_ADV_* mask
+    PF2_CHECK(q.shape <= PF2_SHAPE_HEX20 && q.quad <= PF2_QUAD_G27CUBE && (adv || q.quad2 <= PF2_QUAD_G27CUBE), "unknown shape function / integration rule");
+    PF2_CHECK(!adv || (q.quad2 >= 1 && q.quad2 <= 63), "advection-diffusion: the quad2 field must select at least one routine (PF2_ADV_*)");
     const bool solid = q.phys == PF2_PHYS_SOLID;
     if (q.shape == 0) q.shape = solid ? PF2_SHAPE_HEX8 : PF2_SHAPE_Q4;
     PF2_CHECK(shape_dim(q.shape) == (solid ? 3 : 2), "shape function does not match the equation's dimension");
@@ -54,13 +56,13 @@ int decode_eq(int eq, double V, EqInfo* out) {
     if (q.phys == PF2_PHYS_PLANESTRAIN_SRI || q.phys == PF2_PHYS_PLANESTRAIN_BBAR) {
         if (q.quad2 == 0) q.quad2 = dflt_reduced[dom];
         PF2_CHECK(quad_domain(q.quad2) == dom, "volumetric integration rule does not belong to the shape function's reference domain");
-    } else {
+    } else if (!adv) {
         PF2_CHECK(q.quad2 == 0, "a second integration rule is only meaningful for the selective-reduced variant");
     }
     q.dim = solid ? 3 : 2;
     q.npe = shape_npe(q.shape);
-    q.ndof = solid ? 3 : ((q.phys == PF2_PHYS_HEAT || q.phys == PF2_PHYS_MASS) ? 1 : 2);
-    q.kind = solid ? KIND_SOLID3D : (q.phys == PF2_PHYS_HEAT ? KIND_HEAT2D : (q.phys == PF2_PHYS_MASS ? KIND_MASS2D : (q.phys == PF2_PHYS_MASS2 ? KIND_MASS2D_V : KIND_ELAST2D)));
+    q.ndof = solid ? 3 : ((q.phys == PF2_PHYS_HEAT || q.phys == PF2_PHYS_MASS || adv) ? 1 : 2);
+    q.kind = adv ? KIND_ADVDIFF2D : solid ? KIND_SOLID3D : (q.phys == PF2_PHYS_HEAT ? KIND_HEAT2D : (q.phys == PF2_PHYS_MASS ? KIND_MASS2D : (q.phys == PF2_PHYS_MASS2 ? KIND_MASS2D_V : KIND_ELAST2D)));
     q.fast = (q.phys == PF2_PHYS_PLANESTRAIN && q.shape == PF2_SHAPE_Q4 && q.quad == PF2_QUAD_G4SQ) ||
              (q.phys == PF2_PHYS_HEAT && q.shape == PF2_SHAPE_Q4 && q.quad == PF2_QUAD_G4SQ) ||
              (solid && q.shape == PF2_SHAPE_HEX8 && q.quad == PF2_QUAD_G8CUBE);
@@ -92,7 +94,7 @@ int decode_eq(int eq, double V, EqInfo* out) {
     return PF2_OK;
 }
 
-static ElemSpec make_spec(const EqInfo& q) {
+ElemSpec make_spec(const EqInfo& q) {
     ElemSpec sp;
     sp.npass = q.npass;
     sp.wilson_taylor = (q.phys == PF2_PHYS_PLANESTRAIN_WT) ? 1 : 0;

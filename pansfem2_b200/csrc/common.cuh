@@ -43,6 +43,10 @@ void set_error(const char* fmt, ...);
 
 constexpr int kThreads = 256;
 
+// element routines (element.cuh, element_generic.cuh) also compile for the host so that tests/cpp/host_elements.cu can check the
+// SAME source against the oracle on a machine without a GPU; the library itself only ever calls them from kernels
+#define PF2_HD __host__ __device__ __forceinline__
+
 // reduction scratch: per-block partials + a ticket counter; the last block to arrive folds the partials in a fixed
 // order, so every reduction is deterministic for a given grid size.
 struct ReduceScratch {

@@ -19,12 +19,12 @@ namespace pf2 {
 
 // ---- Q4 -------------------------------------------------------------------------------------------------------
 // Gauss point g of Gauss4Square: (-,-),(+,-),(-,+),(+,+)
-__device__ __forceinline__ void q4_gauss(int g, double& r0, double& r1) {
+PF2_HD void q4_gauss(int g, double& r0, double& r1) {
     r0 = (g & 1) ? PF2_INV_SQRT3 : -PF2_INV_SQRT3;
     r1 = (g & 2) ? PF2_INV_SQRT3 : -PF2_INV_SQRT3;
 }
 // X: 4 nodes x 2.  Outputs dN/dX (gx[n], gy[n]) and det J.
-__device__ __forceinline__ void q4_grad(const double (&X)[4][2], double r0, double r1, double (&gx)[4], double (&gy)[4], double& det) {
+PF2_HD void q4_grad(const double (&X)[4][2], double r0, double r1, double (&gx)[4], double (&gy)[4], double& det) {
     const double d0[4] = { -0.25 * (1.0 - r1), 0.25 * (1.0 - r1), 0.25 * (1.0 + r1), -0.25 * (1.0 + r1) };
     const double d1[4] = { -0.25 * (1.0 - r0), -0.25 * (1.0 + r0), 0.25 * (1.0 + r0), 0.25 * (1.0 - r0) };
     double J00 = 0.0, J01 = 0.0, J10 = 0.0, J11 = 0.0;
@@ -43,14 +43,14 @@ __device__ __forceinline__ void q4_grad(const double (&X)[4][2], double r0, doub
 }
 
 // ---- hex8 ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double h8_sx(int n) { return ((n + 1) & 2) ? 1.0 : -1.0; }   // -,+,+,-,-,+,+,-
-__device__ __forceinline__ double h8_sy(int n) { return (n & 2) ? 1.0 : -1.0; }         // -,-,+,+,-,-,+,+
-__device__ __forceinline__ double h8_sz(int n) { return (n & 4) ? 1.0 : -1.0; }         // -,-,-,-,+,+,+,+
+PF2_HD double h8_sx(int n) { return ((n + 1) & 2) ? 1.0 : -1.0; }   // -,+,+,-,-,+,+,-
+PF2_HD double h8_sy(int n) { return (n & 2) ? 1.0 : -1.0; }         // -,-,+,+,-,-,+,+
+PF2_HD double h8_sz(int n) { return (n & 4) ? 1.0 : -1.0; }         // -,-,-,-,+,+,+,+
 // Gauss8Cubic orders its points like the nodes (bottom CCW, top CCW)
-__device__ __forceinline__ void h8_gauss(int g, double& r0, double& r1, double& r2) {
+PF2_HD void h8_gauss(int g, double& r0, double& r1, double& r2) {
     r0 = h8_sx(g) * PF2_INV_SQRT3; r1 = h8_sy(g) * PF2_INV_SQRT3; r2 = h8_sz(g) * PF2_INV_SQRT3;
 }
-__device__ __forceinline__ void h8_grad(const double (&X)[8][3], double r0, double r1, double r2,
+PF2_HD void h8_grad(const double (&X)[8][3], double r0, double r1, double r2,
                                         double (&gx)[8], double (&gy)[8], double (&gz)[8], double& det) {
     double d0[8], d1[8], d2[8];
     double J[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } };
@@ -86,14 +86,14 @@ __device__ __forceinline__ void h8_grad(const double (&X)[8][3], double r0, doub
 // isotropic coefficients for unit modulus
 struct Iso {
     double cn, lam, mu;
-    __device__ __forceinline__ Iso(double V) {
+    PF2_HD Iso(double V) {
         const double c = 1.0 / ((1.0 + V) * (1.0 - 2.0 * V));
         cn = (1.0 - V) * c; lam = V * c; mu = 0.5 * (1.0 - 2.0 * V) * c;
     }
 };
 
 // SIMP interpolation of the drivers (sample_optimize_density_oc.cpp:123)
-__device__ __forceinline__ double simp_modulus(double rho, double E0, double E1, double p) {
+PF2_HD double simp_modulus(double rho, double E0, double E1, double p) {
     const double rp = pow(rho, p);
     return E1 * rp + E0 * (1.0 - rp);
 }
@@ -105,7 +105,7 @@ template <> struct ElemTraits<PF2_EQ_PLANESTRAIN> { static constexpr int DIM = 2
 template <> struct ElemTraits<PF2_EQ_HEAT> { static constexpr int DIM = 2, NPE = 4, NDOF = 1; };
 template <> struct ElemTraits<PF2_EQ_SOLID> { static constexpr int DIM = 3, NPE = 8, NDOF = 3; };
 
-__device__ __forceinline__ void planestrain_rows(const double (&X)[4][2], int a, double V, double t, double (&acc)[2][8]) {
+PF2_HD void planestrain_rows(const double (&X)[4][2], int a, double V, double t, double (&acc)[2][8]) {
     const Iso c(V);
 #pragma unroll
     for (int i = 0; i < 2; i++)
@@ -130,7 +130,7 @@ __device__ __forceinline__ void planestrain_rows(const double (&X)[4][2], int a,
     }
 }
 
-__device__ __forceinline__ void heat_rows(const double (&X)[4][2], int a, double t, double (&acc)[1][4]) {
+PF2_HD void heat_rows(const double (&X)[4][2], int a, double t, double (&acc)[1][4]) {
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[0][j] = 0.0;
 #pragma unroll
@@ -147,7 +147,7 @@ __device__ __forceinline__ void heat_rows(const double (&X)[4][2], int a, double
     }
 }
 
-__device__ __forceinline__ void solid_rows(const double (&X)[8][3], int a, double V, double (&acc)[3][24]) {
+PF2_HD void solid_rows(const double (&X)[8][3], int a, double V, double (&acc)[3][24]) {
     const Iso c(V);
 #pragma unroll
     for (int i = 0; i < 3; i++)

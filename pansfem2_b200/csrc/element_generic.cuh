@@ -20,7 +20,8 @@ namespace pf2 {
 
 enum { SH_T3 = PF2_SHAPE_T3, SH_T6 = PF2_SHAPE_T6, SH_Q4 = PF2_SHAPE_Q4, SH_Q8 = PF2_SHAPE_Q8, SH_TET4 = PF2_SHAPE_TET4,
        SH_HEX8 = PF2_SHAPE_HEX8, SH_HEX20 = PF2_SHAPE_HEX20 };
-enum { KIND_ELAST2D = 0, KIND_HEAT2D = 1, KIND_SOLID3D = 2, KIND_MASS2D = 3, KIND_MASS2D_V = 4 };
+enum { KIND_ELAST2D = 0, KIND_HEAT2D = 1, KIND_SOLID3D = 2, KIND_MASS2D = 3, KIND_MASS2D_V = 4,
+       KIND_ADVDIFF2D = 5 };   // the last one lives in element_advdiff.cuh / advdiff.cu, not in the generic template
 
 // what one launch needs to know about the element routine (filled on the host by decode_eq, passed by value)
 struct ElemSpec {
@@ -47,7 +48,7 @@ template <> struct KindTraits<KIND_MASS2D> { static constexpr int DIM = 2, NDOF 
 template <> struct KindTraits<KIND_MASS2D_V> { static constexpr int DIM = 2, NDOF = 2; };   // 2-dof consistent mass (N_a N_b) I_2
 
 // ---- quadrature ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int quad_count(int quad) {
+PF2_HD int quad_count(int quad) {
     switch (quad) {
         case PF2_QUAD_G3TRI: return 3;
         case PF2_QUAD_G4SQ: return 4;
@@ -58,7 +59,7 @@ __device__ __forceinline__ int quad_count(int quad) {
     }
 }
 // point g of the rule and the PRODUCT of its per-axis weights (the reference multiplies Weights[g][0]*Weights[g][1][*Weights[g][2]])
-__device__ __forceinline__ void quad_point(int quad, int g, double (&r)[3], double& w) {
+PF2_HD void quad_point(int quad, int g, double (&r)[3], double& w) {
     const double s35 = sqrt(3.0 / 5.0);
     r[2] = 0.0;
     switch (quad) {
@@ -86,7 +87,7 @@ __device__ __forceinline__ void quad_point(int quad, int g, double (&r)[3], doub
 
 // ---- dN/dr, d[k][n] ----------------------------------------------------------------------------------------------
 template <int SHAPE>
-__device__ __forceinline__ void shape_dndr(const double (&r)[3], double (&d)[ShapeTraits<SHAPE>::DIM][ShapeTraits<SHAPE>::NPE]) {
+PF2_HD void shape_dndr(const double (&r)[3], double (&d)[ShapeTraits<SHAPE>::DIM][ShapeTraits<SHAPE>::NPE]) {
     const double r0 = r[0], r1 = r[1], r2 = r[2];
     if constexpr (SHAPE == SH_T3) {
         d[0][0] = 1.0; d[0][1] = 0.0; d[0][2] = -1.0;
@@ -167,7 +168,7 @@ __device__ __forceinline__ void shape_dndr(const double (&r)[3], double (&d)[Sha
 
 // N(r) of the 2-D shapes (ShapeFunction.h:102-108, 137-146, 175-182, 211-222): needed by the consistent mass matrices
 template <int SHAPE>
-__device__ __forceinline__ void shape_n(const double (&r)[3], double (&N)[ShapeTraits<SHAPE>::NPE]) {
+PF2_HD void shape_n(const double (&r)[3], double (&N)[ShapeTraits<SHAPE>::NPE]) {
     const double r0 = r[0], r1 = r[1];
     if constexpr (SHAPE == SH_T3) {
         N[0] = r0; N[1] = r1; N[2] = 1.0 - r0 - r1;
@@ -194,7 +195,7 @@ __device__ __forceinline__ void shape_n(const double (&r)[3], double (&N)[ShapeT
 
 // dXdr = dNdr * X, J = det, dNdX = dXdr^-1 * dNdr   (g overwrites d in place)
 template <int SHAPE>
-__device__ __forceinline__ void shape_grad(const double (&X)[ShapeTraits<SHAPE>::NPE][ShapeTraits<SHAPE>::DIM], const double (&r)[3],
+PF2_HD void shape_grad(const double (&X)[ShapeTraits<SHAPE>::NPE][ShapeTraits<SHAPE>::DIM], const double (&r)[3],
                                            double (&g)[ShapeTraits<SHAPE>::DIM][ShapeTraits<SHAPE>::NPE], double& det) {
     constexpr int DIM = ShapeTraits<SHAPE>::DIM, NPE = ShapeTraits<SHAPE>::NPE;
     shape_dndr<SHAPE>(r, g);
@@ -240,7 +241,7 @@ __device__ __forceinline__ void shape_grad(const double (&X)[ShapeTraits<SHAPE>:
 // blocks Keaa (modes x modes), Kead (modes x nodes) come from the same closed form as the nodal blocks; then
 // Ke -= Kead^T Keaa^-1 Kead.  Gradients + the two mode gradients at one integration point:
 template <int SHAPE>
-__device__ __forceinline__ void wt_grad(const double (&X)[ShapeTraits<SHAPE>::NPE][2], const double (&r)[3], double (&g)[2][ShapeTraits<SHAPE>::NPE],
+PF2_HD void wt_grad(const double (&X)[ShapeTraits<SHAPE>::NPE][2], const double (&r)[3], double (&g)[2][ShapeTraits<SHAPE>::NPE],
                                         double (&h)[2][2], double& det) {
     constexpr int NPE = ShapeTraits<SHAPE>::NPE;
     shape_dndr<SHAPE>(r, g);
@@ -260,11 +261,11 @@ __device__ __forceinline__ void wt_grad(const double (&X)[ShapeTraits<SHAPE>::NP
     h[0][1] = i01 * (-2.0 * r[1]); h[1][1] = i11 * (-2.0 * r[1]);
 }
 // isotropic block K_ab[i][j] for gradients ga, gb (2-D)
-__device__ __forceinline__ double iso_block2(double cn, double lam, double mu, const double (&ga)[2], const double (&gb)[2], int i, int j) {
+PF2_HD double iso_block2(double cn, double lam, double mu, const double (&ga)[2], const double (&gb)[2], int i, int j) {
     return (i == j) ? (cn * ga[i] * gb[i] + mu * ga[1 - i] * gb[1 - i]) : (lam * ga[i] * gb[j] + mu * ga[j] * gb[i]);
 }
 // solve the 4x4 SPD system Kaa z = v (Gaussian elimination, no pivoting needed)
-__device__ __forceinline__ void solve4(double (&A)[4][4], double (&v)[4]) {
+PF2_HD void solve4(double (&A)[4][4], double (&v)[4]) {
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const double piv = 1.0 / A[k][k];
@@ -287,7 +288,7 @@ __device__ __forceinline__ void solve4(double (&A)[4][4], double (&v)[4]) {
 
 // rows of node a of the condensed matrix (unit modulus)
 template <int SHAPE>
-__device__ __forceinline__ void wt_rows(const double (&X)[ShapeTraits<SHAPE>::NPE][2], int a, const ElemSpec& sp, double t,
+PF2_HD void wt_rows(const double (&X)[ShapeTraits<SHAPE>::NPE][2], int a, const ElemSpec& sp, double t,
                                         double (&acc)[2][ShapeTraits<SHAPE>::NPE * 2]) {
     constexpr int NPE = ShapeTraits<SHAPE>::NPE, M = NPE * 2;
     const double cn = sp.cn[0], lam = sp.lam[0], mu = sp.mu[0];
@@ -360,7 +361,7 @@ __device__ __forceinline__ void wt_rows(const double (&X)[ShapeTraits<SHAPE>::NP
 
 // ue^T Ke ue and optionally Ke ue for the condensed element
 template <int SHAPE, bool WANT_F>
-__device__ __forceinline__ double wt_energy(const double (&X)[ShapeTraits<SHAPE>::NPE][2], const double (&ue)[ShapeTraits<SHAPE>::NPE][2], const ElemSpec& sp,
+PF2_HD double wt_energy(const double (&X)[ShapeTraits<SHAPE>::NPE][2], const double (&ue)[ShapeTraits<SHAPE>::NPE][2], const ElemSpec& sp,
                                             double t, double (&fe)[ShapeTraits<SHAPE>::NPE][2]) {
     constexpr int NPE = ShapeTraits<SHAPE>::NPE;
     const double cn = sp.cn[0], lam = sp.lam[0], mu = sp.mu[0];
@@ -424,7 +425,7 @@ __device__ __forceinline__ double wt_energy(const double (&X)[ShapeTraits<SHAPE>
 
 // Rows of local node `a` of the element matrix for unit modulus: acc[i][b*NDOF + j], i = dof of node a.
 template <int KIND, int SHAPE>
-__device__ __forceinline__ void generic_rows(const double (&X)[ShapeTraits<SHAPE>::NPE][ShapeTraits<SHAPE>::DIM], int a, const ElemSpec& sp,
+PF2_HD void generic_rows(const double (&X)[ShapeTraits<SHAPE>::NPE][ShapeTraits<SHAPE>::DIM], int a, const ElemSpec& sp,
                                              double t, double (&acc)[KindTraits<KIND>::NDOF][ShapeTraits<SHAPE>::NPE * KindTraits<KIND>::NDOF]) {
     constexpr int DIM = ShapeTraits<SHAPE>::DIM, NPE = ShapeTraits<SHAPE>::NPE, NDOF = KindTraits<KIND>::NDOF;
     static_assert(DIM == KindTraits<KIND>::DIM, "shape / equation dimension mismatch");
@@ -488,7 +489,7 @@ __device__ __forceinline__ void generic_rows(const double (&X)[ShapeTraits<SHAPE
 
 // strain energy ue^T Ke(E=1) ue of one element and, optionally, fe = Ke(E=1) ue
 template <int KIND, int SHAPE, bool WANT_F>
-__device__ __forceinline__ double generic_energy(const double (&X)[ShapeTraits<SHAPE>::NPE][ShapeTraits<SHAPE>::DIM],
+PF2_HD double generic_energy(const double (&X)[ShapeTraits<SHAPE>::NPE][ShapeTraits<SHAPE>::DIM],
                                                  const double (&ue)[ShapeTraits<SHAPE>::NPE][KindTraits<KIND>::NDOF], const ElemSpec& sp, double t,
                                                  double (&fe)[ShapeTraits<SHAPE>::NPE][KindTraits<KIND>::NDOF]) {
     constexpr int DIM = ShapeTraits<SHAPE>::DIM, NPE = ShapeTraits<SHAPE>::NPE;

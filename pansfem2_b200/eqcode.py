@@ -2,7 +2,10 @@
 <Equation, ShapeFunction, Integration> (host-side bookkeeping only)."""
 from __future__ import annotations
 
-PHYS_PLANESTRAIN, PHYS_SOLID, PHYS_HEAT, PHYS_PLANESTRESS, PHYS_PLANESTRAIN_SRI, PHYS_MASS, PHYS_PLANESTRAIN_BBAR, PHYS_MASS2, PHYS_PLANESTRAIN_WT = range(9)
+PHYS_PLANESTRAIN, PHYS_SOLID, PHYS_HEAT, PHYS_PLANESTRESS, PHYS_PLANESTRAIN_SRI, PHYS_MASS, PHYS_PLANESTRAIN_BBAR, PHYS_MASS2, PHYS_PLANESTRAIN_WT, PHYS_ADVDIFF = range(10)
+# PF2_ADV_* routine mask of PHYS_ADVDIFF (carried in the quad2 field): Advection.h:19, :135, :47, :91, :161, :188
+ADV_ADVECTION, ADV_DIFFUSION, ADV_SUPG, ADV_SHOCK, ADV_MASS, ADV_MASS_SUPG = 1, 2, 4, 8, 16, 32
+ADV_NAME = {1: "Advection", 2: "Diffusion", 4: "AdvectionSUPG", 8: "AdvectionShockCapturing", 16: "Mass", 32: "MassSUPG"}
 SHAPE_DEFAULT, SHAPE_T3, SHAPE_T6, SHAPE_Q4, SHAPE_Q8, SHAPE_TET4, SHAPE_HEX8, SHAPE_HEX20 = range(8)
 QUAD_DEFAULT, QUAD_G1TRI, QUAD_G3TRI, QUAD_G1SQ, QUAD_G4SQ, QUAD_G9SQ, QUAD_G1TET, QUAD_G8CUBE, QUAD_G27CUBE = range(9)
 
@@ -11,7 +14,8 @@ SHAPE_NAME = {SHAPE_T3: "T3", SHAPE_T6: "T6", SHAPE_Q4: "Q4", SHAPE_Q8: "Q8", SH
 QUAD_NAME = {QUAD_G1TRI: "Gauss1Triangle", QUAD_G3TRI: "Gauss3Triangle", QUAD_G1SQ: "Gauss1Square", QUAD_G4SQ: "Gauss4Square",
              QUAD_G9SQ: "Gauss9Square", QUAD_G1TET: "Gauss1Tetrahedron", QUAD_G8CUBE: "Gauss8Cubic", QUAD_G27CUBE: "Gauss27Cubic"}
 PHYS_NAME = {PHYS_PLANESTRAIN: "PlaneStrain", PHYS_SOLID: "Solid", PHYS_HEAT: "HeatTransfer", PHYS_PLANESTRESS: "PlaneStress",
-             PHYS_PLANESTRAIN_SRI: "PlaneStrainSRI", PHYS_MASS: "ConsistentMass", PHYS_PLANESTRAIN_BBAR: "PlaneStrainBbar", PHYS_MASS2: "ConsistentMass2dof", PHYS_PLANESTRAIN_WT: "PlaneStrainWilsonTaylor"}
+             PHYS_PLANESTRAIN_SRI: "PlaneStrainSRI", PHYS_MASS: "ConsistentMass", PHYS_PLANESTRAIN_BBAR: "PlaneStrainBbar", PHYS_MASS2: "ConsistentMass2dof", PHYS_PLANESTRAIN_WT: "PlaneStrainWilsonTaylor",
+             PHYS_ADVDIFF: "AdvectionDiffusion"}
 # rules of each reference domain (triangle, square, tetrahedron, cube)
 SHAPE_RULES = {SHAPE_T3: (QUAD_G1TRI, QUAD_G3TRI), SHAPE_T6: (QUAD_G1TRI, QUAD_G3TRI),
                SHAPE_Q4: (QUAD_G1SQ, QUAD_G4SQ, QUAD_G9SQ), SHAPE_Q8: (QUAD_G1SQ, QUAD_G4SQ, QUAD_G9SQ),
@@ -39,7 +43,7 @@ def fields(eq):
 
 def ndof(eq) -> int:
     phys = eq & 0xff
-    return 3 if phys == PHYS_SOLID else (1 if phys in (PHYS_HEAT, PHYS_MASS) else 2)
+    return 3 if phys == PHYS_SOLID else (1 if phys in (PHYS_HEAT, PHYS_MASS, PHYS_ADVDIFF) else 2)
 
 
 def dim(eq) -> int:
@@ -52,5 +56,7 @@ def npe(eq) -> int:
 
 def describe(eq) -> str:
     phys, shape, quad, quad2 = fields(eq)
+    if phys == PHYS_ADVDIFF:
+        return "+".join(n for b, n in ADV_NAME.items() if quad2 & b) + f"<{SHAPE_NAME[shape]},{QUAD_NAME[quad]}>"
     s = f"{PHYS_NAME[phys]}<{SHAPE_NAME[shape]},{QUAD_NAME[quad]}"
     return s + (f",{QUAD_NAME[quad2]}>" if quad2 else ">")

@@ -351,6 +351,91 @@ def golden_krylov():
     print("krylov", len(b), [float(np.abs(d[k] - d["x_exact"]).max()) for k in d if k.startswith("x_") and k != "x_exact"])
 
 
+def advection_sample_inputs():
+    """Node.csv / Element.csv / Dirichlet.csv / DirichletD.csv of sample/advection, the dynamic sample's initial cone
+    (sample_advectiondiffusion_dynamic.cpp:27-34) and its per-element rotating velocity (:48-50, CenterOfGravity General.h:71-78)."""
+    adv = f"{REF}/sample/advection"
+    nodes = np.array([[float(v) for v in r[1:3]] for r in csv_rows(f"{adv}/Node.csv")])
+    elems = np.array([[int(v) for v in r[1:4]] for r in csv_rows(f"{adv}/Element.csv")], dtype=np.int32)
+    fix = [(int(r[0]), float(r[1])) for r in csv_rows(f"{adv}/Dirichlet.csv") if r[1] != "free"]
+    fixd = [(int(r[0]), float(r[1])) for r in csv_rows(f"{adv}/DirichletD.csv") if r[1] != "free"]
+    T0 = np.zeros(len(nodes))
+    r = np.sqrt((nodes[:, 0] - 0.5) ** 2 + (nodes[:, 1] - 0.75) ** 2)
+    T0[r <= 0.25] = 0.5 * (np.cos(4.0 * np.pi * r[r <= 0.25]) + 1.0)
+    cg = (nodes[elems[:, 0]] + nodes[elems[:, 1]] + nodes[elems[:, 2]]) / 3.0
+    vel = np.stack([-(cg[:, 1] - 0.5), cg[:, 0] - 0.5], axis=1)
+    return dict(coords=nodes, conn=elems, fix_node=np.array([f[0] for f in fix], np.int32), fix_val=np.array([f[1] for f in fix]),
+                fixd_node=np.array([f[0] for f in fixd], np.int32), fixd_val=np.array([f[1] for f in fixd]), T0=T0, vel=vel)
+
+
+def vtk_scalar(path, name, n):
+    L = open(path).read().split("\n")
+    i0 = next(k for k, ln in enumerate(L) if ln.startswith(f"SCALARS {name}"))
+    return np.array([float(v) for v in L[i0 + 2:i0 + 2 + n]])
+
+
+def golden_advection():
+    """Advection-diffusion element family (Advection.h:19-229) of the live reference: every routine on
+    every 2-D <SF, IC> on a distorted element, the systems of the two advection samples, a Q4 / T6 / Q8 time step with all six routines,
+    and the committed outputs AdvectionSUPG.vtk, AdvectionSUPGdynamic0.vtk, AdvectionSUPGdynamic99.vtk."""
+    from pansfem2_b200 import eqcode as ec, mesher
+    reflib.set_num_threads(1)
+    rng = np.random.default_rng(20211003)
+    d = {}
+    cases = []
+    for shape in (ec.SHAPE_T3, ec.SHAPE_T6, ec.SHAPE_Q4, ec.SHAPE_Q8):
+        nat = mesher.NATURAL_NODES[ec.SHAPE_NAME[shape]]
+        for quad in ec.SHAPE_RULES[shape]:
+            xe = nat * np.array([1.3, 0.9]) + 0.08 * rng.uniform(-1, 1, nat.shape)
+            for terms in (1, 2, 4, 8, 16, 32, 7, 55, 63):
+                for k in (1.0e-6, 0.4):           # alpha > 3 and alpha <= 3 (Advection.h:78-82)
+                    ax, ay = rng.uniform(-1.5, 1.5, 2)
+                    cases.append((shape, quad, terms, ax, ay, k))
+                    d[f"xe_{len(cases) - 1}"] = xe
+                    d[f"ke_{len(cases) - 1}"] = reflib.advdiff_element(shape, quad, terms, xe, ax, ay, k)
+    d["cases"] = np.array(cases)
+    # the dynamic sample: first step's system, the field after steps 1, 2, 3 and 100 (live reference, BiCGSTAB as there), committed VTKs
+    I = advection_sample_inputs()
+    d.update({f"smp_{k}": v for k, v in I.items()})
+    adv = f"{REF}/sample/advection"
+    n = len(I["coords"])
+    d["smp_T_static_vtk"] = vtk_scalar(f"{adv}/AdvectionSUPG.vtk", "T", n)
+    d["smp_T_dyn0_vtk"] = vtk_scalar(f"{adv}/AdvectionSUPGdynamic0.vtk", "T", n)
+    d["smp_T_dyn99_vtk"] = vtk_scalar(f"{adv}/AdvectionSUPGdynamic99.vtk", "T", n)
+    terms, dt, theta = 1 | 2 | 4 | 16 | 32, np.pi / 50.0, 0.5
+    T = I["T0"].copy()
+    T[I["fixd_node"]] = I["fixd_val"]
+    free = None
+    for step in range(100):
+        S = reflib.advdiff_system(ec.SHAPE_T3, ec.QUAD_G1TRI, terms, I["coords"], I["conn"], I["fixd_node"], I["fixd_val"], I["vel"], 0.0, dt, theta, T)
+        ai, aj, ad, aF = S.arrays()
+        if step == 0:
+            d.update(dyn_indptr=ai, dyn_indices=aj, dyn_data=ad, dyn_F=aF, dyn_n2g=S.nodetoglobal(n, 1))
+            free = np.nonzero(d["dyn_n2g"][:, 0] >= 0)[0]
+        x = S.solve(3, aF)[0]
+        T[free] = x[d["dyn_n2g"][free, 0]]
+        if step in (0, 1, 2, 99):
+            d[f"dyn_T{step}"] = T.copy()
+    print("dynamic sample vs committed VTKs:", np.abs(d["dyn_T0"] - d["smp_T_dyn0_vtk"]).max(), np.abs(d["dyn_T99"] - d["smp_T_dyn99_vtk"]).max())
+    # one time step with all six routines on Q4 / T6 / Q8 family meshes, non-zero Dirichlet values, non-uniform velocity
+    for nm, shape, quad, nn in (("q4", ec.SHAPE_Q4, ec.QUAD_G4SQ, (7, 5)), ("t6", ec.SHAPE_T6, ec.QUAD_G3TRI, (5, 4)), ("q8", ec.SHAPE_Q8, ec.QUAD_G9SQ, (4, 3))):
+        coords, conn = mesher.family_mesh(ec.SHAPE_NAME[shape], nn)
+        coords = coords + 0.07 * np.sin(1.7 * coords[:, ::-1] + 0.3)          # smooth distortion, keeps mid-side nodes consistent enough
+        fn = np.nonzero(np.abs(coords[:, 0] - coords[:, 0].min()) < 0.2)[0].astype(np.int32)
+        fv = 0.5 + 0.1 * np.arange(len(fn))
+        cg = coords[conn].mean(axis=1)
+        vel = np.stack([1.0 + 0.2 * cg[:, 1], -0.4 + 0.1 * cg[:, 0]], axis=1)
+        Tn = np.cos(0.9 * coords[:, 0]) * np.sin(0.7 * coords[:, 1] + 0.2)
+        S = reflib.advdiff_system(shape, quad, 63, coords, conn, fn, fv, vel, 0.02, 0.05, 0.6, Tn)
+        ai, aj, ad, aF = S.arrays()
+        d.update({f"{nm}_shape": np.int64(shape), f"{nm}_quad": np.int64(quad), f"{nm}_coords": coords, f"{nm}_conn": conn, f"{nm}_fix_node": fn,
+                  f"{nm}_fix_val": fv, f"{nm}_vel": vel, f"{nm}_Tn": Tn, f"{nm}_indptr": ai, f"{nm}_indices": aj, f"{nm}_data": ad, f"{nm}_F": aF,
+                  f"{nm}_x": S.solve(3, aF)[0]})
+        print(nm, len(coords), "nodes", S.rows, "rows")
+    np.savez_compressed(f"{OUT}/live_advection.npz", **d)
+    print("advection:", len(cases), "element cases")
+
+
 def _dense(indptr, indices, data):
     n = len(indptr) - 1
     M = np.zeros((n, n))
@@ -362,6 +447,9 @@ def _dense(indptr, indices, data):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "krylov":
         golden_krylov()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "advection":
+        golden_advection()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "levelset":
         golden_levelset()
