@@ -20,13 +20,16 @@ LINK = ["-L" + HERE, "-lpansfem2_b200", "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGI
 
 OWN = [("sample/optimize/sample_optimize_density_batched.cpp", "sample_optimize_density_batched"),
        ("sample/optimize/sample_optimize_density_families.cpp", "sample_optimize_density_families"),
-       ("sample/optimize/sample_optimize_levelset_batched.cpp", "sample_optimize_levelset_batched")]
+       ("sample/optimize/sample_optimize_levelset_batched.cpp", "sample_optimize_levelset_batched"),
+       ("sample/advection/sample_advectiondiffusion_batched.cpp", "sample_advectiondiffusion_batched")]
 DROPIN = [("sample/optimize/sample_optimize_density_oc.cpp", "dropin_density_oc"),
           ("sample/optimize/sample_optimize_density_mma.cpp", "dropin_density_mma"),
           ("sample/optimize/sample_optimize_density_CONLIN.cpp", "dropin_density_conlin"),
           ("sample/solid/sample_linear.cpp", "dropin_solid_linear"),
           ("sample/planestrain/sample_planestrain.cpp", "dropin_planestrain_t3"),
-          ("sample/optimize/sample_optimize_levelset.cpp", "dropin_levelset")]
+          ("sample/optimize/sample_optimize_levelset.cpp", "dropin_levelset"),
+          ("sample/advection/sample_advectiondiffusion_static.cpp", "dropin_advection_static"),
+          ("sample/advection/sample_advectiondiffusion_dynamic.cpp", "dropin_advection_dynamic")]
 
 
 def _compile(src, exe):

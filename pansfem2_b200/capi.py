@@ -225,6 +225,11 @@ class Csr:
         _ck(lib().pf2_assemble(self.h, mesh.h, dofmap.h, eq, modulus.ptr if modulus is not None else None,
                                rho.ptr if rho is not None else None, prm, len(ln), _p(ln, np.int32), _p(ld, np.int32), _p(lv, np.float64)))
 
+    def advdiff_assemble(self, mesh, dofmap, eq, prm, vel=None, T=None):
+        """pf2_advdiff_assemble: prm = (ax, ay, k, cm, ck, cf); vel (nelem*2) / T (nnode) are DeviceArrays or None."""
+        p6 = (C.c_double * 6)(*prm)
+        _ck(lib().pf2_advdiff_assemble(self.h, mesh.h, dofmap.h, eq, vel.ptr if vel is not None else None, p6, T.ptr if T is not None else None))
+
     def matrix_free(self, mesh, dofmap, eq):
         """Opt into the matrix-free operator (uniform structured Q4 / hex8 meshes); takes effect from the next assemble."""
         _ck(lib().pf2_csr_matrix_free(self.h, mesh.h, dofmap.h, eq))

@@ -4,6 +4,8 @@
 //  a driver that used to run the whole design iteration on the host (sample_optimize_density_oc.cpp:83-208) steps a DesignLoop.
 #pragma once
 #include <vector>
+#include <cassert>
+#include <iostream>
 #include <utility>
 #include <memory>
 #include "ElementSelect.h"
@@ -21,6 +23,9 @@ namespace PANSFEM2 { namespace B200 {
     struct SolidLinearIsotropicElasticTag { static const int eq = EqCode<PF2_PHYS_SOLID, SF, IC>::value; static const int ndof = 3; };
     template<template<class>class SF, template<class>class IC>
     struct HeatTransferTag { static const int eq = EqCode<PF2_PHYS_HEAT, SF, IC>::value; static const int ndof = 1; };
+    //  the Advection.h routines a driver sums per element (TERMS = PF2_ADV_ADVECTION | PF2_ADV_DIFFUSION | ...)
+    template<template<class>class SF, template<class>class IC, int TERMS>
+    struct AdvectionDiffusionTag { static const int eq = EqCode<PF2_PHYS_ADVDIFF, SF, IC>::value | (TERMS << 24); static const int ndof = 1; };
 
     typedef std::vector<std::pair<std::pair<int, int>, double> > BcList;
     inline void SplitBc(const BcList& _bc, std::vector<int>& _node, std::vector<int>& _dof, std::vector<double>& _val) {
@@ -170,5 +175,65 @@ public:
 private:
         Model& model;
         pf2_levelset* handle;
+    };
+
+    //  The scalar advection-diffusion problem of sample/advection with the field resident on the device.
+    //      steady (sample_advectiondiffusion_static.cpp:42-58):   Solve() assembles K = A + D + AS [+ SC], F = -K T_fixed and solves
+    //      transient (sample_advectiondiffusion_dynamic.cpp:44-75): Step(dt, theta) assembles K = (M + MS)/dt + theta (A + D + AS),
+    //          F = ((M + MS)/dt - (1 - theta)(A + D + AS)) T - K T_fixed, solves and writes the new field back (Disassembling)
+    //  one assembly launch + one BiCGSTAB solve per call; nothing returns to the host until Get().
+    template<class EQTAG>
+    class AdvectionDiffusion {
+public:
+        //  _model: 1-dof numbering; _velocity: one Vector per element, or a single Vector for a uniform field; _T0: initial nodal field
+        AdvectionDiffusion(Model& _model, const std::vector<Vector<double> >& _velocity, double _k, std::vector<Vector<double> >& _T0)
+            : model(_model), k(_k), ax(0.0), ay(0.0), uniform(_velocity.size() == 1), T((size_t)_model.nnode), x((size_t)_model.KDEGREE) {
+            static_assert(EQTAG::ndof == 1, "advection-diffusion is a scalar problem");
+            assert(model.ndof == 1);
+            assert(uniform || (int)_velocity.size() == model.nelem);
+            std::vector<Vector<double> >& vel = const_cast<std::vector<Vector<double> >&>(_velocity);     //  Vector<T>::operator() is non-const in the reference
+            if (uniform) { ax = vel[0](0); ay = vel[0](1); }
+            else {
+                std::vector<double> v((size_t)model.nelem*2);
+                for (int e = 0; e < model.nelem; e++) { v[2*(size_t)e] = vel[e](0); v[2*(size_t)e + 1] = vel[e](1); }
+                velocity.Upload(v);
+            }
+            std::vector<double> t0((size_t)model.nnode);
+            for (int i = 0; i < model.nnode; i++) t0[i] = _T0[i](0);
+            T.Upload(t0);
+        }
+        AdvectionDiffusion(const AdvectionDiffusion&) = delete;
+
+        //  returns the Krylov iteration count; _solver = PF2_SOLVER_BICGSTAB / _BICGSTAB2 / _SCALINGBICGSTAB / _ILU0BICGSTAB
+        int Step(double _dt, double _theta, int _solver = PF2_SOLVER_BICGSTAB, int _itrmax = 100000, double _eps = 1.0e-10) {
+            const double prm[6] = { ax, ay, k, 1.0/_dt, _theta, 1.0 - _theta };
+            return Advance(prm, true, _solver, _itrmax, _eps);
+        }
+        int Solve(int _solver = PF2_SOLVER_BICGSTAB, int _itrmax = 100000, double _eps = 1.0e-10) {
+            const double prm[6] = { ax, ay, k, 0.0, 1.0, 0.0 };
+            return Advance(prm, false, _solver, _itrmax, _eps);
+        }
+        void Get(std::vector<Vector<double> >& _T) {
+            std::vector<double> t = T.Download();
+            _T.assign(model.nnode, Vector<double>(1));
+            for (int i = 0; i < model.nnode; i++) _T[i](0) = t[i];
+        }
+private:
+        int Advance(const double _prm[6], bool _transient, int _solver, int _itrmax, double _eps) {
+            Check(pf2_advdiff_assemble(model.pattern, model.mesh, model.dofmap, EQTAG::eq, uniform ? nullptr : velocity.Get(), _prm, _transient ? T.Get() : nullptr), "pf2_advdiff_assemble");
+            double* F = nullptr;
+            Check(pf2_csr_device_F(model.pattern, &F), "pf2_csr_device_F");
+            int iters = 0;
+            double relres = 0.0;
+            const int rc = pf2_solve(model.pattern, _solver, F, x.Get(), _itrmax, _eps, &iters, &relres);
+            Check(rc, "pf2_solve");
+            if (rc == PF2_E_NOCONV) std::cout << "\nConvergence:faild" << std::endl;
+            Check(pf2_disassemble(model.dofmap, x.Get(), T.Get()), "pf2_disassemble");
+            return iters;
+        }
+        Model& model;
+        double k, ax, ay;
+        bool uniform;
+        Buffer velocity, T, x;
     };
 } }
