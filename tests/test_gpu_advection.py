@@ -140,7 +140,7 @@ def write_model(d, adv):
     with open(d / "Node.csv", "w") as f:
         f.write("ID,x0,x1\n")
         for i, c in enumerate(adv["smp_coords"]):
-            f.write(f"{i},{c[0]!r},{c[1]!r}\n")
+            f.write(f"{i},{float(c[0])!r},{float(c[1])!r}\n")
     with open(d / "Element.csv", "w") as f:
         f.write("Cell ID,Point Index 0,Point Index 1,Point Index 2\n")
         for i, e in enumerate(adv["smp_conn"]):
