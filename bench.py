@@ -384,6 +384,15 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
                gpu_launches=int(launches), clocks=clocks, roofline=roof, wall_s=wall,
                phases_ms=steps[-1]["phase_ms"], objective=[s["f"] for s in steps], cg_relres_max=max(s["cg_relres"] for s in steps))
+    # third figure of BASELINE.json's metric: assembly elements/s (numeric phase: element routine + scatter / gather into the CSR),
+    # from the per-phase device time of the timed steps (this rank's elements; slabs assemble concurrently)
+    asm_ms = float(np.mean([st["phase_ms"]["assemble"] for st in steps]))
+    if asm_ms > 0:
+        bytes_per_elem = {2: 590.0, 1: 175.0, 3: 4300.0}.get(P.ndof, 0.0)     # Q4 plane strain / heat / hex8, map included
+        out["assembly"] = {"elements_per_s": nelem / (asm_ms * 1e-3), "ms": asm_ms, "elements_local": int(nelem),
+                           "algorithmic_bytes_per_element": bytes_per_elem, "algorithmic_GBps": bytes_per_elem * nelem / (asm_ms * 1e-3) / 1e9,
+                           "kernel": "assemble_gather_kernel (row gather, every entry written once, bitwise reproducible)" if P.ndof < 3
+                                     else "assemble_kernel<SOLID> (scatter, fp64 RED)"}
     if mf is not None:
         out["matrix_free"] = mf
     if rank == 0:

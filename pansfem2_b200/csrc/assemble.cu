@@ -14,6 +14,7 @@
 // + density 8 + map 4*npe^2 + values 8*(npe*ndof)^2 atomically added.
 #include "types.cuh"
 #include "element.cuh"
+#include "assemble_gather.cuh"
 
 namespace pf2 {
 
@@ -77,6 +78,18 @@ assemble_kernel(int nelem, const double* __restrict__ coords, const int* __restr
         }
     }
 }
+
+// the specialised 2-D element routines as row providers of the gather kernel (assemble_gather.cuh)
+struct ElemPlaneStrainQ4 {
+    static constexpr int DIM = 2, NPE = 4, NDOF = 2;
+    double V, t;
+    __device__ __forceinline__ void rows(const double (&X)[4][2], int a, double (&acc)[2][8]) const { planestrain_rows(X, a, V, t, acc); }
+};
+struct ElemHeatQ4 {
+    static constexpr int DIM = 2, NPE = 4, NDOF = 1;
+    double t;
+    __device__ __forceinline__ void rows(const double (&X)[4][2], int a, double (&acc)[1][4]) const { heat_rows(X, a, t, acc); }
+};
 
 // Assembling(F, q, nodetoglobal) (Assembling.h:152-158)
 __global__ void loads_kernel(int nload, int ndof, const int* __restrict__ node, const int* __restrict__ dof,
@@ -238,14 +251,20 @@ int assemble_device(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq, const d
     PF2_CHECK(modulus_dev || rho_dev, "need a modulus or a density field");
     pf2_ctx* c = A->ctx;
     cudaStream_t s = c->stream;
-    PF2_CUDA(cudaMemsetAsync(A->data, 0, sizeof(double) * (size_t)A->nnz, s));
-    PF2_CUDA(cudaMemsetAsync(A->F, 0, sizeof(double) * (size_t)A->rows, s));
     const double E0 = params[0], E1 = params[1], V = params[2], p = params[3], t = params[4];
+    // 2-D selections: row-gather kernel (every entry written once, no memset, bitwise reproducible) when the plan fits
+    const bool gather = q.dim == 2 && gather_usable(A, mesh);
+    if (!gather) {
+        PF2_CUDA(cudaMemsetAsync(A->data, 0, sizeof(double) * (size_t)A->nnz, s));
+        PF2_CUDA(cudaMemsetAsync(A->F, 0, sizeof(double) * (size_t)A->rows, s));
+    }
     const long long work = (long long)mesh->nelem * mesh->npe;
     const int grid = (int)std::min<long long>((work + 127) / 128, (long long)c->sm_count * 32);
 #define LAUNCH(EQ) assemble_kernel<EQ><<<grid, 128, 0, s>>>(mesh->nelem, mesh->coords, mesh->conn, map->n2g, map->ufix, A->bmap, A->indptr, \
                                                           modulus_dev, rho_dev, E0, E1, V, p, t, A->data, A->F)
     if (!q.fast) PF2_TRY(assemble_generic_launch(A, mesh, map, q, modulus_dev, rho_dev, params));
+    else if (gather && q.legacy == PF2_EQ_PLANESTRAIN) PF2_TRY(assemble_gather_launch(A, mesh, map, ElemPlaneStrainQ4{ V, t }, modulus_dev, rho_dev, E0, E1, p));
+    else if (gather && q.legacy == PF2_EQ_HEAT) PF2_TRY(assemble_gather_launch(A, mesh, map, ElemHeatQ4{ t }, modulus_dev, rho_dev, E0, E1, p));
     else {
         if (q.legacy == PF2_EQ_PLANESTRAIN) LAUNCH(PF2_EQ_PLANESTRAIN);
         else if (q.legacy == PF2_EQ_SOLID) LAUNCH(PF2_EQ_SOLID);

@@ -8,6 +8,7 @@
 // Same thread mapping as assemble.cu: one thread per (element, local node) holding that node's NDOF rows of Ke.
 #include "types.cuh"
 #include "element_generic.cuh"
+#include "assemble_gather.cuh"
 
 namespace pf2 {
 
@@ -205,6 +206,15 @@ __global__ void element_generic_kernel(ElemSpec sp, const double* __restrict__ x
     for (int i = 0; i < NDOF; i++) for (int j = 0; j < M; j++) Ke[(a * NDOF + i) * M + j] = E * acc[i][j];
 }
 
+// the generic template as a row provider of the gather kernel (assemble_gather.cuh)
+template <int KIND, int SHAPE>
+struct ElemGeneric {
+    static constexpr int DIM = ShapeTraits<SHAPE>::DIM, NPE = ShapeTraits<SHAPE>::NPE, NDOF = KindTraits<KIND>::NDOF;
+    ElemSpec sp;
+    double t;
+    __device__ __forceinline__ void rows(const double (&X)[NPE][DIM], int a, double (&acc)[NDOF][NPE * NDOF]) const { generic_rows<KIND, SHAPE>(X, a, sp, t, acc); }
+};
+
 // (kind, shape) -> instantiation
 #define PF2_DISPATCH_SHAPE(q, CALL)                                                                  \
     do {                                                                                             \
@@ -241,6 +251,24 @@ int assemble_generic_launch(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, const E
     cudaStream_t s = c->stream;
     const ElemSpec sp = make_spec(q);
     const double E0 = params[0], E1 = params[1], p = params[3], t = params[4];
+    if (q.dim == 2 && gather_usable(A, mesh)) {         // the caller skipped the memsets on the same condition
+#define CALL(K, S) PF2_TRY((assemble_gather_launch(A, mesh, map, ElemGeneric<K, S>{ sp, t }, modulus_dev, rho_dev, E0, E1, p)))
+        if (q.kind == KIND_HEAT2D) {
+            if (q.shape == PF2_SHAPE_T3) { CALL(KIND_HEAT2D, SH_T3); } else if (q.shape == PF2_SHAPE_T6) { CALL(KIND_HEAT2D, SH_T6); }
+            else if (q.shape == PF2_SHAPE_Q4) { CALL(KIND_HEAT2D, SH_Q4); } else { CALL(KIND_HEAT2D, SH_Q8); }
+        } else if (q.kind == KIND_MASS2D_V) {
+            if (q.shape == PF2_SHAPE_T3) { CALL(KIND_MASS2D_V, SH_T3); } else if (q.shape == PF2_SHAPE_T6) { CALL(KIND_MASS2D_V, SH_T6); }
+            else if (q.shape == PF2_SHAPE_Q4) { CALL(KIND_MASS2D_V, SH_Q4); } else { CALL(KIND_MASS2D_V, SH_Q8); }
+        } else if (q.kind == KIND_MASS2D) {
+            if (q.shape == PF2_SHAPE_T3) { CALL(KIND_MASS2D, SH_T3); } else if (q.shape == PF2_SHAPE_T6) { CALL(KIND_MASS2D, SH_T6); }
+            else if (q.shape == PF2_SHAPE_Q4) { CALL(KIND_MASS2D, SH_Q4); } else { CALL(KIND_MASS2D, SH_Q8); }
+        } else {
+            if (q.shape == PF2_SHAPE_T3) { CALL(KIND_ELAST2D, SH_T3); } else if (q.shape == PF2_SHAPE_T6) { CALL(KIND_ELAST2D, SH_T6); }
+            else if (q.shape == PF2_SHAPE_Q4) { CALL(KIND_ELAST2D, SH_Q4); } else { CALL(KIND_ELAST2D, SH_Q8); }
+        }
+#undef CALL
+        return PF2_OK;
+    }
     const long long work = (long long)mesh->nelem * mesh->npe;
     const int grid = (int)std::min<long long>((work + 127) / 128, (long long)c->sm_count * 32);
 #define CALL(K, S) assemble_generic_kernel<K, S><<<grid, 128, 0, s>>>(mesh->nelem, sp, mesh->coords, mesh->conn, map->n2g, map->ufix, A->bmap, \

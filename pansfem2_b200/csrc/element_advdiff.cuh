@@ -48,8 +48,8 @@ PF2_HD void advdiff_rows(const double (&X)[ShapeTraits<SHAPE>::NPE][2], int a, c
             const double norm = sqrt(ax * ax + ay * ay);
             double sum = 0.0;
 #pragma unroll
-            for (int n = 0; n < NPE; n++) sum += fabs(ax * g[0][n] + ay * g[1][n]) / norm;
-            const double he = 2.0 / sum, alpha = 0.5 * norm * he / k;
+            for (int n = 0; n < NPE; n++) sum += fabs(ax * g[0][n] + ay * g[1][n]);
+            const double he = 2.0 * norm / sum, alpha = 0.5 * norm * he / k;       // he = 2 / sum_i (|a . grad N_i| / |a|)
             const double f = (alpha <= 3.0) ? alpha / 3.0 : 1.0;
             tau = 0.5 * he / norm * f;
             tausc = 0.5 * norm * he * f;

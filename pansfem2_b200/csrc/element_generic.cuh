@@ -211,7 +211,8 @@ PF2_HD void shape_grad(const double (&X)[ShapeTraits<SHAPE>::NPE][ShapeTraits<SH
         }
     if constexpr (DIM == 2) {
         det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
-        const double i00 = J[1][1] / det, i01 = -J[0][1] / det, i10 = -J[1][0] / det, i11 = J[0][0] / det;
+        const double idet = 1.0 / det;      // one reciprocal, then products: the divisions were ~40 % of a Q4 row's fp64 work
+        const double i00 = J[1][1] * idet, i01 = -J[0][1] * idet, i10 = -J[1][0] * idet, i11 = J[0][0] * idet;
 #pragma unroll
         for (int n = 0; n < NPE; n++) {
             const double d0 = g[0][n], d1 = g[1][n];
@@ -221,11 +222,12 @@ PF2_HD void shape_grad(const double (&X)[ShapeTraits<SHAPE>::NPE][ShapeTraits<SH
     } else {
         det = -J[2][2] * J[0][1] * J[1][0] - J[2][1] * J[1][2] * J[0][0] - J[0][2] * J[1][1] * J[2][0]
               + J[2][0] * J[0][1] * J[1][2] + J[2][1] * J[1][0] * J[0][2] + J[0][0] * J[1][1] * J[2][2];
-        const double i00 = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / det, i01 = -(J[0][1] * J[2][2] - J[0][2] * J[2][1]) / det;
-        const double i02 = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det, i10 = -(J[1][0] * J[2][2] - J[1][2] * J[2][0]) / det;
-        const double i11 = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det, i12 = -(J[0][0] * J[1][2] - J[0][2] * J[1][0]) / det;
-        const double i20 = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det, i21 = -(J[0][0] * J[2][1] - J[0][1] * J[2][0]) / det;
-        const double i22 = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+        const double idet = 1.0 / det;      // one reciprocal, then products: the divisions were ~40 % of a Q4 row's fp64 work
+        const double i00 = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * idet, i01 = -(J[0][1] * J[2][2] - J[0][2] * J[2][1]) * idet;
+        const double i02 = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * idet, i10 = -(J[1][0] * J[2][2] - J[1][2] * J[2][0]) * idet;
+        const double i11 = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * idet, i12 = -(J[0][0] * J[1][2] - J[0][2] * J[1][0]) * idet;
+        const double i20 = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) * idet, i21 = -(J[0][0] * J[2][1] - J[0][1] * J[2][0]) * idet;
+        const double i22 = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * idet;
 #pragma unroll
         for (int n = 0; n < NPE; n++) {
             const double d0 = g[0][n], d1 = g[1][n], d2 = g[2][n];
@@ -249,7 +251,8 @@ PF2_HD void wt_grad(const double (&X)[ShapeTraits<SHAPE>::NPE][2], const double 
 #pragma unroll
     for (int n = 0; n < NPE; n++) { J00 += g[0][n] * X[n][0]; J01 += g[0][n] * X[n][1]; J10 += g[1][n] * X[n][0]; J11 += g[1][n] * X[n][1]; }
     det = J00 * J11 - J01 * J10;
-    const double i00 = J11 / det, i01 = -J01 / det, i10 = -J10 / det, i11 = J00 / det;
+    const double idet = 1.0 / det;      // one reciprocal, then products: the divisions were ~40 % of a Q4 row's fp64 work
+    const double i00 = J11 * idet, i01 = -J01 * idet, i10 = -J10 * idet, i11 = J00 * idet;
 #pragma unroll
     for (int n = 0; n < NPE; n++) {
         const double d0 = g[0][n], d1 = g[1][n];
@@ -465,21 +468,25 @@ PF2_HD void generic_rows(const double (&X)[ShapeTraits<SHAPE>::NPE][ShapeTraits<
                 }
                 continue;
             }
+            // node a's gradient folded with D and the weight once per point (DIM FMAs per diagonal entry, 2 per off-diagonal one)
+            double cg[DIM], lg[DIM], mg[DIM];
+#pragma unroll
+            for (int k = 0; k < DIM; k++) { cg[k] = cn * ga[k] * w; lg[k] = lam * ga[k] * w; mg[k] = mu * ga[k] * w; }
 #pragma unroll
             for (int b = 0; b < NPE; b++) {
                 if constexpr (KIND == KIND_HEAT2D) {
-                    acc[0][b] += (ga[0] * g[0][b] + ga[1] * g[1][b]) * w;
+                    acc[0][b] += (ga[0] * w) * g[0][b] + (ga[1] * w) * g[1][b];
                 } else {
-                    double dotab = 0.0;
-#pragma unroll
-                    for (int k = 0; k < DIM; k++) dotab += ga[k] * g[k][b];
 #pragma unroll
                     for (int i = 0; i < NDOF; i++)
 #pragma unroll
                         for (int j = 0; j < NDOF; j++) {
-                            const double v = (i == j) ? (cn * ga[i] * g[i][b] + mu * (dotab - ga[i] * g[i][b]))
-                                                      : (lam * ga[i] * g[j][b] + mu * ga[j] * g[i][b]);
-                            acc[i][b * NDOF + j] += v * w;
+                            if (i == j) {
+                                double v = cg[i] * g[i][b];
+#pragma unroll
+                                for (int k = 0; k < DIM; k++) if (k != i) v += mg[k] * g[k][b];
+                                acc[i][b * NDOF + j] += v;
+                            } else acc[i][b * NDOF + j] += lg[i] * g[j][b] + mg[j] * g[i][b];
                         }
                 }
             }

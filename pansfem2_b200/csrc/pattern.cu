@@ -45,6 +45,35 @@ __global__ void fill_n2e_kernel(int nelem, int npe, const int* __restrict__ conn
     }
 }
 
+// gather plan: each node's element list in ascending order (the slots above were handed out by atomics), so that the numeric phase
+// adds the element contributions of a row in the reference's own order (element loop ascending) and is bitwise reproducible
+__global__ void sort_n2e_kernel(int nnode, const int* __restrict__ ptr, int* __restrict__ n2e) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nnode; i += gridDim.x * blockDim.x) {
+        const int b = ptr[i], e = ptr[i + 1];
+        for (int a = b + 1; a < e; a++) {
+            const int v = n2e[a];
+            int j = a - 1;
+            while (j >= b && n2e[j] > v) { n2e[j + 1] = n2e[j]; j--; }
+            n2e[j + 1] = v;
+        }
+    }
+}
+__global__ void node_free_count_kernel(int nnode, int ndof, const int* __restrict__ n2g, int* __restrict__ cnt) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= nnode; i += gridDim.x * blockDim.x) {
+        int c = 0;
+        if (i < nnode) for (int d = 0; d < ndof; d++) c += (n2g[(size_t)i * ndof + d] != -1);
+        cnt[i] = c;
+    }
+}
+// largest number of stored entries owned by one tile of `tile` consecutive nodes
+__global__ void tile_nnz_max_kernel(int nnode, int tile, const int* __restrict__ node_row0, const long long* __restrict__ indptr, unsigned long long* out) {
+    const int ntiles = (nnode + tile - 1) / tile;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += gridDim.x * blockDim.x) {
+        const int n0 = t * tile, n1 = min(n0 + tile, nnode);
+        atomicMax(out, (unsigned long long)(indptr[node_row0[n1]] - indptr[node_row0[n0]]));
+    }
+}
+
 // per node: sorted unique neighbour nodes.  PASS 0 counts, PASS 1 writes the list and the exclusive prefix of free dofs.
 template <int PASS>
 __global__ void node_adjacency_kernel(int nnode, int npe, int ndof, const int* __restrict__ conn, const int* __restrict__ n2e_ptr,
@@ -305,6 +334,28 @@ int pf2_csr_pattern(pf2_ctx* ctx, pf2_mesh* mesh, pf2_dofmap* map, pf2_csr** out
     bmap_kernel<<<ctx->grid_for((long long)nelem * npe * npe), kThreads, 0, s>>>(nelem, npe, mesh->conn, adj_ptr, adj, adjfree, A->bmap);
     PF2_LAUNCH_CHECK();
     ctx->launches += 7;
+    // gather plan for the numeric phase (assemble_gather.cuh)
+    {
+        sort_n2e_kernel<<<gnode, kThreads, 0, s>>>(nnode, n2e_ptr, n2e);
+        PF2_LAUNCH_CHECK();
+        int* nfree = nullptr;
+        unsigned long long* d_max = nullptr;
+        PF2_TRY(dev_alloc(&nfree, (size_t)nnode + 1)); PF2_TRY(dev_alloc(&A->node_row0, (size_t)nnode + 1)); PF2_TRY(dev_alloc(&d_max, 1));
+        node_free_count_kernel<<<gnode, kThreads, 0, s>>>(nnode, ndof, map->n2g, nfree);
+        PF2_LAUNCH_CHECK();
+        PF2_TRY(exclusive_scan(ctx, nfree, A->node_row0, (size_t)nnode + 1));
+        PF2_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned long long), s));
+        tile_nnz_max_kernel<<<gnode, kThreads, 0, s>>>(nnode, kGatherTile, A->node_row0, A->indptr, d_max);
+        PF2_LAUNCH_CHECK();
+        unsigned long long h_max = 0;
+        PF2_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, s));
+        PF2_CUDA(cudaStreamSynchronize(s));
+        cudaFree(nfree); cudaFree(d_max);
+        A->n2e_ptr = n2e_ptr; A->n2e = n2e; A->gather_nnode = nnode;
+        A->gather_smem = (size_t)h_max * sizeof(double);
+        ctx->launches += 3;
+        n2e_ptr = nullptr; n2e = nullptr;       // owned by the matrix from here on
+    }
     PF2_CUDA(cudaStreamSynchronize(s));
     cudaFree(cnt); cudaFree(n2e_ptr); cudaFree(cursor); cudaFree(n2e);
     cudaFree(adj_cnt); cudaFree(adj_ptr); cudaFree(adj); cudaFree(adjfree); cudaFree(rowlen); cudaFree(overflow);

@@ -32,6 +32,7 @@ struct pf2_dofmap {
 };
 
 namespace pf2 {
+constexpr int kGatherTile = 128;   // nodes (= threads) per CTA of the gather assembly (assemble_gather.cuh)
 constexpr int kCsrPad = 8;   // spare entries behind indptr / indices / data (see spmv_tma.cuh)
 // device-resident state of one Krylov solve (CG.h:124-154 / 420-453 / 320-352)
 struct CgState {
@@ -86,6 +87,13 @@ struct pf2_csr {
     // scatter map of the symbolic phase (pattern-built matrices only)
     int* bmap = nullptr;           // [(e*npe+a)*npe + b] : column offset of node b's first free dof in node a's rows
     int map_npe = 0, map_ndof = 0, map_nelem = 0;
+    // gather plan of the numeric phase (assemble_gather.cuh): node -> adjacent elements in ascending order, rows before each node,
+    // and the shared-memory bytes the largest node tile needs (0: plan not usable, the scatter kernels run)
+    int* n2e_ptr = nullptr;        // nnode + 1
+    int* n2e = nullptr;            // nelem * npe
+    int* node_row0 = nullptr;      // nnode + 1 : free dofs in the nodes before this one (= first row of the node)
+    int gather_nnode = 0;
+    size_t gather_smem = 0;
     // SpMV plan
     int spmv_variant = 0;          // 0 = not planned
     int tma_stages = 3, tma_ctas_per_sm = 4;   // TMA pipeline depth and residency target
