@@ -34,7 +34,7 @@ PF2_HD void q4_grad(const double (&X)[4][2], double r0, double r1, double (&gx)[
         J10 += d1[n] * X[n][0]; J11 += d1[n] * X[n][1];
     }
     det = J00 * J11 - J01 * J10;
-    const double idet = 1.0 / det;      // one reciprocal, then products: the divisions were ~40 % of a Q4 row's fp64 work
+    const double idet = 1.0 / det;      // one reciprocal, then products (a DP division is ~10 dependent FMAs)
     const double i00 = J11 * idet, i01 = -J01 * idet, i10 = -J10 * idet, i11 = J00 * idet;
 #pragma unroll
     for (int n = 0; n < 4; n++) {
@@ -67,7 +67,7 @@ PF2_HD void h8_grad(const double (&X)[8][3], double r0, double r1, double r2,
     det = -J[2][2] * J[0][1] * J[1][0] - J[2][1] * J[1][2] * J[0][0] - J[0][2] * J[1][1] * J[2][0]
           + J[2][0] * J[0][1] * J[1][2] + J[2][1] * J[1][0] * J[0][2] + J[0][0] * J[1][1] * J[2][2];
     // adjugate / det
-    const double idet = 1.0 / det;      // one reciprocal, then products: the divisions were ~40 % of a Q4 row's fp64 work
+    const double idet = 1.0 / det;      // one reciprocal, then products (a DP division is ~10 dependent FMAs)
     const double i00 = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * idet;
     const double i01 = -(J[0][1] * J[2][2] - J[0][2] * J[2][1]) * idet;
     const double i02 = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * idet;
@@ -126,10 +126,11 @@ PF2_HD void planestrain_rows(const double (&X)[4][2], int a, double V, double t,
         const double cnx = c.cn * ax * w, cny = c.cn * ay * w, lmx = c.lam * ax * w, lmy = c.lam * ay * w, mux = c.mu * ax * w, muy = c.mu * ay * w;
 #pragma unroll
         for (int b = 0; b < 4; b++) {
-            acc[0][2 * b]     += cnx * gx[b] + muy * gy[b];
-            acc[0][2 * b + 1] += lmx * gy[b] + muy * gx[b];
-            acc[1][2 * b]     += lmy * gx[b] + mux * gy[b];
-            acc[1][2 * b + 1] += cny * gy[b] + mux * gx[b];
+            // two chained FMAs per entry (a sum of two products added to acc would cost a multiply, an FMA and an add)
+            acc[0][2 * b]     += cnx * gx[b]; acc[0][2 * b]     += muy * gy[b];
+            acc[0][2 * b + 1] += lmx * gy[b]; acc[0][2 * b + 1] += muy * gx[b];
+            acc[1][2 * b]     += lmy * gx[b]; acc[1][2 * b]     += mux * gy[b];
+            acc[1][2 * b + 1] += cny * gy[b]; acc[1][2 * b + 1] += mux * gx[b];
         }
     }
 }
@@ -148,7 +149,7 @@ PF2_HD void heat_rows(const double (&X)[4][2], int a, double t, double (&acc)[1]
         for (int n = 1; n < 4; n++) if (n == a) { ax = gx[n]; ay = gy[n]; }
         const double axw = ax * w, ayw = ay * w;
 #pragma unroll
-        for (int b = 0; b < 4; b++) acc[0][b] += axw * gx[b] + ayw * gy[b];
+        for (int b = 0; b < 4; b++) { acc[0][b] += axw * gx[b]; acc[0][b] += ayw * gy[b]; }
     }
 }
 
@@ -177,8 +178,8 @@ PF2_HD void solid_rows(const double (&X)[8][3], int a, double V, double (&acc)[3
             for (int i = 0; i < 3; i++)
 #pragma unroll
                 for (int j = 0; j < 3; j++) {
-                    if (i == j) acc[i][3 * b + j] += cg[i] * gb[i] + mg[(i + 1) % 3] * gb[(i + 1) % 3] + mg[(i + 2) % 3] * gb[(i + 2) % 3];
-                    else acc[i][3 * b + j] += lg[i] * gb[j] + mg[j] * gb[i];
+                    if (i == j) { acc[i][3 * b + j] += cg[i] * gb[i]; acc[i][3 * b + j] += mg[(i + 1) % 3] * gb[(i + 1) % 3]; acc[i][3 * b + j] += mg[(i + 2) % 3] * gb[(i + 2) % 3]; }
+                    else { acc[i][3 * b + j] += lg[i] * gb[j]; acc[i][3 * b + j] += mg[j] * gb[i]; }
                 }
         }
     }

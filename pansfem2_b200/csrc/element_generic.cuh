@@ -211,7 +211,7 @@ PF2_HD void shape_grad(const double (&X)[ShapeTraits<SHAPE>::NPE][ShapeTraits<SH
         }
     if constexpr (DIM == 2) {
         det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
-        const double idet = 1.0 / det;      // one reciprocal, then products: the divisions were ~40 % of a Q4 row's fp64 work
+        const double idet = 1.0 / det;      // one reciprocal, then products (a DP division is ~10 dependent FMAs)
         const double i00 = J[1][1] * idet, i01 = -J[0][1] * idet, i10 = -J[1][0] * idet, i11 = J[0][0] * idet;
 #pragma unroll
         for (int n = 0; n < NPE; n++) {
@@ -222,7 +222,7 @@ PF2_HD void shape_grad(const double (&X)[ShapeTraits<SHAPE>::NPE][ShapeTraits<SH
     } else {
         det = -J[2][2] * J[0][1] * J[1][0] - J[2][1] * J[1][2] * J[0][0] - J[0][2] * J[1][1] * J[2][0]
               + J[2][0] * J[0][1] * J[1][2] + J[2][1] * J[1][0] * J[0][2] + J[0][0] * J[1][1] * J[2][2];
-        const double idet = 1.0 / det;      // one reciprocal, then products: the divisions were ~40 % of a Q4 row's fp64 work
+        const double idet = 1.0 / det;      // one reciprocal, then products (a DP division is ~10 dependent FMAs)
         const double i00 = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * idet, i01 = -(J[0][1] * J[2][2] - J[0][2] * J[2][1]) * idet;
         const double i02 = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * idet, i10 = -(J[1][0] * J[2][2] - J[1][2] * J[2][0]) * idet;
         const double i11 = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * idet, i12 = -(J[0][0] * J[1][2] - J[0][2] * J[1][0]) * idet;
@@ -251,7 +251,7 @@ PF2_HD void wt_grad(const double (&X)[ShapeTraits<SHAPE>::NPE][2], const double 
 #pragma unroll
     for (int n = 0; n < NPE; n++) { J00 += g[0][n] * X[n][0]; J01 += g[0][n] * X[n][1]; J10 += g[1][n] * X[n][0]; J11 += g[1][n] * X[n][1]; }
     det = J00 * J11 - J01 * J10;
-    const double idet = 1.0 / det;      // one reciprocal, then products: the divisions were ~40 % of a Q4 row's fp64 work
+    const double idet = 1.0 / det;      // one reciprocal, then products (a DP division is ~10 dependent FMAs)
     const double i00 = J11 * idet, i01 = -J01 * idet, i10 = -J10 * idet, i11 = J00 * idet;
 #pragma unroll
     for (int n = 0; n < NPE; n++) {
@@ -475,18 +475,18 @@ PF2_HD void generic_rows(const double (&X)[ShapeTraits<SHAPE>::NPE][ShapeTraits<
 #pragma unroll
             for (int b = 0; b < NPE; b++) {
                 if constexpr (KIND == KIND_HEAT2D) {
-                    acc[0][b] += (ga[0] * w) * g[0][b] + (ga[1] * w) * g[1][b];
+                    acc[0][b] += (ga[0] * w) * g[0][b]; acc[0][b] += (ga[1] * w) * g[1][b];
                 } else {
 #pragma unroll
                     for (int i = 0; i < NDOF; i++)
 #pragma unroll
                         for (int j = 0; j < NDOF; j++) {
+                            // chained FMAs into the accumulator
                             if (i == j) {
-                                double v = cg[i] * g[i][b];
+                                acc[i][b * NDOF + j] += cg[i] * g[i][b];
 #pragma unroll
-                                for (int k = 0; k < DIM; k++) if (k != i) v += mg[k] * g[k][b];
-                                acc[i][b * NDOF + j] += v;
-                            } else acc[i][b * NDOF + j] += lg[i] * g[j][b] + mg[j] * g[i][b];
+                                for (int k = 0; k < DIM; k++) if (k != i) acc[i][b * NDOF + j] += mg[k] * g[k][b];
+                            } else { acc[i][b * NDOF + j] += lg[i] * g[j][b]; acc[i][b * NDOF + j] += mg[j] * g[i][b]; }
                         }
                 }
             }
