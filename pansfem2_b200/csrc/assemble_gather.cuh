@@ -118,11 +118,8 @@ template <class ELEM>
 int assemble_gather_launch(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, const ELEM& elem, const double* modulus_dev, const double* rho_dev,
                            double E0, double E1, double p) {
     pf2_ctx* c = A->ctx;
-    static bool attr_set = false;       // per instantiation
-    if (!attr_set) {
-        PF2_CUDA(cudaFuncSetAttribute(assemble_gather_kernel<ELEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmemLimit));
-        attr_set = true;
-    }
+    // per function AND per device, so it is (re)stated on every launch: a host-side call of about a microsecond
+    PF2_CUDA(cudaFuncSetAttribute(assemble_gather_kernel<ELEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmemLimit));
     const GatherArgs g = { mesh->nnode, mesh->coords, mesh->conn, map->n2g, map->ufix, A->n2e_ptr, A->n2e, A->node_row0, A->bmap, A->indptr,
                            modulus_dev, rho_dev, E0, E1, p, A->data, A->F };
     const int ntiles = (mesh->nnode + kGatherTile - 1) / kGatherTile;
