@@ -59,4 +59,17 @@ namespace PANSFEM2 {
             for (size_t i = 0; i < t.size(); i++) if (t[i] != "free") _qfixed.push_back(std::make_pair(std::make_pair(id, (int)i), (T)std::stod(t[i])));
         });
     }
+    //  initial values: row "id,v0,v1,..." overwrites the components of _u[id] that are not "free" (ImportFromCSV.h:181-217)
+    template<class T>
+    bool ImportInitialFromCSV(std::vector<Vector<T> >& _u, std::string _fname) {
+        return B200::ReadCsvRows(_fname, "Initial Condition", [&](int id, const std::vector<std::string>& t) {
+            for (int i = 0; i < _u[id].SIZE() && i < (int)t.size(); i++) if (t[i] != "free") _u[id](i) = (T)std::stod(t[i]);
+        });
+    }
+    //  periodic pairs: rows "master,slave" (ImportFromCSV.h:221-250)
+    inline bool ImportPeriodicFromCSV(std::vector<std::pair<int, int> >& _ufixed, std::string _fname) {
+        return B200::ReadCsvRows(_fname, "Periodic Boundary Condition", [&](int master, const std::vector<std::string>& t) {
+            _ufixed.push_back(std::make_pair(master, std::stoi(t.at(0))));
+        });
+    }
 }

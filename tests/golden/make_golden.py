@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import os
 import re
+import shutil
 import subprocess
 import sys
 import tempfile
@@ -436,6 +437,20 @@ def golden_advection():
     print("advection:", len(cases), "element cases")
 
 
+def golden_io():
+    """The data formats either side of the path: tests/cpp/io_formats.cpp built against the REFERENCE's PrePost headers (ExportToVTK.h,
+    ImportFromCSV.h, ImportFromVTK.h / ImportFromVTK2.h); its VTK bytes and parsed values are the golden the mirror build must equal."""
+    with tempfile.TemporaryDirectory() as tmp:
+        for tag, flags in (("", []), ("_vtk2", ["-DIO_VTK2"])):
+            exe = os.path.join(tmp, "io" + tag)
+            subprocess.run(["g++", "-O1", "-std=c++17", "-w", *flags, f"-I{REF}/src", f"{ROOT}/tests/cpp/io_formats.cpp", "-o", exe], check=True)
+            os.makedirs(os.path.join(tmp, "work"), exist_ok=True)
+            out = subprocess.run([exe, "work"], cwd=tmp, check=True, capture_output=True, text=True).stdout
+            open(f"{OUT}/io_formats{tag}.txt", "w").write(out)
+        shutil.copyfile(os.path.join(tmp, "work", "out.vtk"), f"{OUT}/io_formats_out.vtk")
+    print("io goldens written")
+
+
 def _dense(indptr, indices, data):
     n = len(indptr) - 1
     M = np.zeros((n, n))
@@ -447,6 +462,9 @@ def _dense(indptr, indices, data):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "krylov":
         golden_krylov()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "io":
+        golden_io()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "advection":
         golden_advection()
