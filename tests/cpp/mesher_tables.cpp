@@ -1,0 +1,63 @@
+// tests/cpp/mesher_tables.cpp -- every query of SquareMesh<T> and SquareMesh2<T> (PrePost/Mesher/SquareMesh.h) on a few grids, printed
+// with full precision.  Built against the reference's headers for the golden (tests/golden/make_golden.py meshers ->
+// tests/golden/mesher_tables.txt) and against the header mirror in tests/test_mesher_tables.py: same numbers, same order.
+#include <cstdio>
+#include <cmath>
+#include <vector>
+#include "LinearAlgebra/Models/Vector.h"
+#include "PrePost/Mesher/SquareMesh.h"
+
+using namespace PANSFEM2;
+
+static void nodes(const char* name, std::vector<Vector<double> > v) {
+    std::printf("%s %zu\n", name, v.size());
+    for (auto& p : v) std::printf(" %.17g %.17g\n", p(0), p(1));
+}
+static void lists(const char* name, const std::vector<std::vector<int> >& v) {
+    std::printf("%s %zu\n", name, v.size());
+    for (const auto& e : v) { for (int n : e) std::printf(" %d", n); std::printf("\n"); }
+}
+static void ids(const char* name, const std::vector<int>& v) {
+    std::printf("%s %zu:", name, v.size());
+    for (int n : v) std::printf(" %d", n);
+    std::printf("\n");
+}
+static void fixed(const char* name, const std::vector<std::pair<std::pair<int, int>, double> >& v) {
+    std::printf("%s %zu:", name, v.size());
+    for (const auto& b : v) std::printf(" (%d,%d,%g)", b.first.first, b.first.second, b.second);
+    std::printf("\n");
+}
+
+int main() {
+    const int grids[3][2] = { { 4, 3 }, { 1, 1 }, { 5, 2 } };
+    for (const auto& g : grids) {
+        const int nx = g[0], ny = g[1];
+        const double lx = 2.5*nx, ly = 0.7*ny;
+        std::printf("== SquareMesh %d x %d\n", nx, ny);
+        SquareMesh<double> mesh(lx, ly, nx, ny);
+        nodes("nodes", mesh.GenerateNodes());
+        nodes("nodes2", mesh.GenerateNodes2());
+        lists("elements", mesh.GenerateElements());
+        lists("elements2", mesh.GenerateElements2());
+        lists("edges", mesh.GenerateEdges());
+        lists("edges2", mesh.GenerateEdges2());
+        ids("elements right half", mesh.GenerateElementIdsSelected([&](Vector<double> p) { return p(0) > 0.5*lx - 1.0e-9; }));
+        ids("edges on top", mesh.GenerateEdgeIdsSelected([&](Vector<double> p) { return std::fabs(p(1) - ly) < 1.0e-9; }));
+        ids("edges on the left or bottom", mesh.GenerateEdgeIdsSelected([&](Vector<double> p) { return p(0) < 1.0e-9 || p(1) < 1.0e-9; }));
+        fixed("clamp x = 0", mesh.GenerateFixedlist({ 0, 1 }, [](Vector<double> p) { return std::fabs(p(0)) < 1.0e-9; }));
+        fixed("clamp2 x = 0", mesh.GenerateFixedlist2({ 0, 1 }, [](Vector<double> p) { return std::fabs(p(0)) < 1.0e-9; }));
+        fixed("roller2 upper half", mesh.GenerateFixedlist2({ 1 }, [&](Vector<double> p) { return p(1) > 0.5*ly; }));
+    }
+    const double ratios[2][2] = { { 1.3, 1.1 }, { 0.8, 2.0 } };
+    const int grids2[3][2] = { { 6, 4 }, { 5, 3 }, { 2, 2 } };
+    for (const auto& r : ratios) for (const auto& g : grids2) {
+        std::printf("== SquareMesh2 %d x %d ratios %g %g\n", g[0], g[1], r[0], r[1]);
+        SquareMesh2<double> mesh(3.0, 2.0, g[0], g[1], r[0], r[1]);
+        nodes("nodes", mesh.GenerateNodes());
+        lists("elements", mesh.GenerateElements());
+        lists("edges", mesh.GenerateEdges());
+        fixed("right side", mesh.GenerateFixedlist({ 1 }, [](Vector<double> p) { return std::fabs(p(0) - 3.0) < 1.0e-9; }));
+        fixed("centre lines", mesh.GenerateFixedlist({ 0 }, [](Vector<double> p) { return std::fabs(p(0) - 1.5) < 1.0e-12 || std::fabs(p(1) - 1.0) < 1.0e-12; }));
+    }
+    return 0;
+}

@@ -437,6 +437,16 @@ def golden_advection():
     print("advection:", len(cases), "element cases")
 
 
+def golden_meshers():
+    """SquareMesh<T> / SquareMesh2<T> of the reference (PrePost/Mesher/SquareMesh.h): tests/cpp/mesher_tables.cpp built against the
+    reference's headers; the mirror build must print the same table."""
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "mesher_tables")
+        subprocess.run(["g++", "-O1", "-std=c++17", "-w", f"-I{REF}/src", f"{ROOT}/tests/cpp/mesher_tables.cpp", "-o", exe], check=True)
+        open(f"{OUT}/mesher_tables.txt", "w").write(subprocess.run([exe], check=True, capture_output=True, text=True).stdout)
+    print("mesher golden written")
+
+
 def golden_io():
     """The data formats either side of the path: tests/cpp/io_formats.cpp built against the REFERENCE's PrePost headers (ExportToVTK.h,
     ImportFromCSV.h, ImportFromVTK.h / ImportFromVTK2.h); its VTK bytes and parsed values are the golden the mirror build must equal."""
@@ -462,6 +472,9 @@ def _dense(indptr, indices, data):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "krylov":
         golden_krylov()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "meshers":
+        golden_meshers()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "io":
         golden_io()
