@@ -1,6 +1,6 @@
 //  pansfem2_b200/src/FEM/Controller/ShapeFunction.h
 //  Shape-function policy classes used as template arguments of the element routines, mirroring
-//  src/FEM/Controller/ShapeFunction.h: ShapeFunction2Line (:20-48), 3Triangle (:87-118), 6Triangle (:122-156),
+//  src/FEM/Controller/ShapeFunction.h: ShapeFunction2Line (:20-48), 3Line (:52-82), 3Triangle (:87-118), 6Triangle (:122-156),
 //  4Square (:160-191), 8Square (:196-247), 4Tetrahedron (:251-284), 8Cubic (:288-329), 20Cubic (:334-461):
 //  static d, n, Points, N(r), dNdr(r).  On the hot path they are compile-time TAGS that select a CUDA kernel
 //  instantiation (B200/ElementSelect.h); N / dNdr stay callable for user code and the host-side load vectors.
@@ -46,6 +46,19 @@ public:
     };
     template<class T>
     const std::vector<Vector<T> > ShapeFunction2Line<T>::Points = { { -1.0 }, { 1.0 } };
+
+    //********************3NodesLine: end nodes first, then the mid node********************
+    template<class T>
+    class ShapeFunction3Line {
+public:
+        static const int d = 1;
+        static const int n = 3;
+        static const std::vector<Vector<T> > Points;
+        static Vector<T> N(Vector<T> _r) { const T r = _r(0); Vector<T> v(n); v(0) = -0.5*(1.0 - r)*r; v(1) = 0.5*r*(1.0 + r); v(2) = (1.0 - r)*(1.0 + r); return v; }
+        static Matrix<T> dNdr(Vector<T> _r) { const T r = _r(0); Matrix<T> m(d, n); m(0, 0) = -0.5*(1.0 - 2.0*r); m(0, 1) = 0.5*(1.0 + 2.0*r); m(0, 2) = -2.0*r; return m; }
+    };
+    template<class T>
+    const std::vector<Vector<T> > ShapeFunction3Line<T>::Points = { { -1.0 }, { 1.0 }, { T() } };
 
     //********************3NodesTriangle: area coordinates (r0, r1, 1 - r0 - r1)********************
     template<class T>

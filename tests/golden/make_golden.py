@@ -437,6 +437,16 @@ def golden_advection():
     print("advection:", len(cases), "element cases")
 
 
+def golden_routines():
+    """Host-side helpers without a device path (General.h, HeatTransferSurfaceFlux, ShapeFunction3Line, SetPeriodic ...):
+    tests/cpp/host_routines.cpp built against the reference's headers."""
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "host_routines")
+        subprocess.run(["g++", "-O1", "-std=c++17", "-w", f"-I{REF}/src", f"{ROOT}/tests/cpp/host_routines.cpp", "-o", exe], check=True)
+        open(f"{OUT}/host_routines.txt", "w").write(subprocess.run([exe], check=True, capture_output=True, text=True).stdout)
+    print("host routines golden written")
+
+
 def golden_meshers():
     """SquareMesh<T> / SquareMesh2<T> of the reference (PrePost/Mesher/SquareMesh.h): tests/cpp/mesher_tables.cpp built against the
     reference's headers; the mirror build must print the same table."""
@@ -472,6 +482,9 @@ def _dense(indptr, indices, data):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "krylov":
         golden_krylov()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "routines":
+        golden_routines()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "meshers":
         golden_meshers()
