@@ -437,6 +437,15 @@ def golden_advection():
     print("advection:", len(cases), "element cases")
 
 
+def golden_linalg():
+    """Boundary types (Vector, Matrix, LILCSR, CSR host behaviour): tests/cpp/linalg_tables.cpp built against the reference's headers."""
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "linalg_tables")
+        subprocess.run(["g++", "-O1", "-std=c++17", "-w", f"-I{REF}/src", f"{ROOT}/tests/cpp/linalg_tables.cpp", "-o", exe], check=True)
+        open(f"{OUT}/linalg_tables.txt", "w").write(subprocess.run([exe], check=True, capture_output=True, text=True).stdout)
+    print("linalg golden written")
+
+
 def golden_routines():
     """Host-side helpers without a device path (General.h, HeatTransferSurfaceFlux, ShapeFunction3Line, SetPeriodic ...):
     tests/cpp/host_routines.cpp built against the reference's headers."""
@@ -482,6 +491,9 @@ def _dense(indptr, indices, data):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "krylov":
         golden_krylov()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "linalg":
+        golden_linalg()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "routines":
         golden_routines()
