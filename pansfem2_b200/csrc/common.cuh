@@ -44,7 +44,7 @@ void set_error(const char* fmt, ...);
 constexpr int kThreads = 256;
 
 // element routines (element.cuh, element_generic.cuh) also compile for the host so that tests/cpp/host_elements.cu can check the
-// SAME source against the oracle on a machine without a GPU; the library itself only ever calls them from kernels
+// SAME source against the reference fixtures on a machine without a GPU; the library itself only ever calls them from kernels
 #define PF2_HD __host__ __device__ __forceinline__
 
 // reduction scratch: per-block partials + a ticket counter; the last block to arrive folds the partials in a fixed
