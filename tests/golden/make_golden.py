@@ -433,6 +433,12 @@ def golden_advection():
                   f"{nm}_fix_val": fv, f"{nm}_vel": vel, f"{nm}_Tn": Tn, f"{nm}_indptr": ai, f"{nm}_indices": aj, f"{nm}_data": ad, f"{nm}_F": aF,
                   f"{nm}_x": S.solve(3, aF)[0]})
         print(nm, len(coords), "nodes", S.rows, "rows")
+    # the theta-scheme heat conduction of sample/heattransfer/sample_heattransfer_dynamic.cpp (HeatTransfer + HeatCapacity, 500 steps) is the
+    # Diffusion + Mass pair of the same family; its committed dynamic.vtk (the last step, on the mesh static.vtk also uses) is a golden too
+    hv = f"{REF}/sample/heattransfer/dynamic.vtk"
+    pts, cells = parse_vtk_mesh(hv)
+    d["heatdyn_coords"], d["heatdyn_conn"] = pts[:, :2], cells
+    d["heatdyn_T_vtk"] = vtk_scalar(hv, "T", len(pts))
     np.savez_compressed(f"{OUT}/live_advection.npz", **d)
     print("advection:", len(cases), "element cases")
 

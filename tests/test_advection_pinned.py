@@ -67,6 +67,36 @@ def test_dynamic_sample_100_steps_and_vtks(adv):
     assert np.abs(adv["dyn_T0"] - adv["smp_T_dyn0_vtk"]).max() < 1e-6
 
 
+def heat_dynamic_problem(adv):
+    """sample/heattransfer/sample_heattransfer_dynamic.cpp:19-45: unit square (T3), T = 300 on x = 0, T = 0 on x = 1, conductivity = capacity = 1,
+    dt = 0.001, theta = 0.5, 500 steps from T = 0.  HeatTransfer + HeatCapacity are the Diffusion + Mass pair of the advection family."""
+    coords, conn = adv["heatdyn_coords"], adv["heatdyn_conn"]
+    left = np.nonzero(np.abs(coords[:, 0]) < 1e-5)[0]
+    right = np.nonzero(np.abs(coords[:, 0] - 1.0) < 1e-5)[0]
+    fn = np.concatenate([left, right]).astype(np.int32)
+    fv = np.concatenate([np.full(len(left), 300.0), np.zeros(len(right))])
+    return coords, conn, fn, fv
+
+
+def heat_dynamic_run(adv, steps=500):
+    coords, conn, fn, fv = heat_dynamic_problem(adv)
+    vel, T = np.zeros((len(conn), 2)), np.zeros(len(coords))
+    for step in range(steps):
+        S, n2g, T = orc.advdiff_system(T3, G1TRI, 2 | 16, coords, conn, fn, fv, vel, 1.0, 0.001, 0.5, T)
+        x, it, relres = S.solve(1, S.arrays()[3])            # ScalingCG, as the sample
+        assert relres < 1e-10
+        free = n2g[:, 0] >= 0
+        T[free] = x[n2g[free, 0]]
+    return T
+
+
+def test_heat_conduction_theta_scheme_reproduces_dynamic_vtk(adv):
+    T = heat_dynamic_run(adv)
+    # 6 printed digits of values up to 300, on coordinates that were themselves printed with 6 digits
+    assert np.abs(T - adv["heatdyn_T_vtk"]).max() < 2e-3
+    assert T.min() > -1e-9 and abs(T.max() - 300.0) < 1e-12
+
+
 @pytest.mark.parametrize("nm", ["q4", "t6", "q8"])
 def test_all_six_routines_time_step_on_family_meshes(adv, nm):
     S, n2g, T = orc.advdiff_system(int(adv[f"{nm}_shape"]), int(adv[f"{nm}_quad"]), 63, adv[f"{nm}_coords"], adv[f"{nm}_conn"], adv[f"{nm}_fix_node"],

@@ -108,6 +108,27 @@ def test_dynamic_sample_time_loop_on_the_device(ctx, adv):
     P.close()
 
 
+def test_heat_conduction_theta_scheme_on_the_device(ctx, adv):
+    """sample/heattransfer/sample_heattransfer_dynamic.cpp (HeatTransfer + HeatCapacity, Crank-Nicolson, ScalingCG, 500 steps) through the
+    Diffusion + Mass pair of pf2_advdiff_assemble with the field resident on the device -> the committed dynamic.vtk and the oracle's run."""
+    from test_advection_pinned import heat_dynamic_problem, heat_dynamic_run
+    coords, conn, fn, fv = heat_dynamic_problem(adv)
+    P = Problem(ctx, coords, conn, fn, fv)
+    eq = ec.eq_code(ec.PHYS_ADVDIFF, ec.SHAPE_T3, ec.QUAD_G1TRI, ec.ADV_DIFFUSION | ec.ADV_MASS)
+    dt, theta = 0.001, 0.5
+    prm = (0.0, 0.0, 1.0, 1.0 / dt, theta, 1.0 - theta)
+    T, x = ctx.array(np.zeros(len(coords))), ctx.empty(P.K.rows)
+    for step in range(500):
+        P.K.advdiff_assemble(P.mesh, P.map, eq, prm, T=T)
+        it, relres = P.K.solve(capi.SOLVER_SCALINGCG, P.K.device_F(), x)
+        assert relres < 1e-10
+        P.map.disassemble(x, T)
+    Tn = T.download()
+    assert np.abs(Tn - adv["heatdyn_T_vtk"]).max() < 2e-3
+    assert np.abs(Tn - heat_dynamic_run(adv)).max() < 1e-4
+    P.close()
+
+
 @pytest.mark.parametrize("nm", ["q4", "t6", "q8"])
 def test_all_six_routines_time_step_on_family_meshes(ctx, adv, nm):
     P = Problem(ctx, adv[f"{nm}_coords"], adv[f"{nm}_conn"], adv[f"{nm}_fix_node"], adv[f"{nm}_fix_val"])
