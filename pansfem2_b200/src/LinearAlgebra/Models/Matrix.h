@@ -103,7 +103,13 @@ protected:
 
     template<class T> inline Vector<T>::Vector(const Matrix<T>& _mat) : values(_mat.values) { assert(_mat.col == 1); }
     template<class T> inline Matrix<T> Vector<T>::Transpose() const { Matrix<T> r(1, SIZE()); r.values = values; return r; }
-    template<class T> inline Matrix<T> Vector<T>::operator*(const Matrix<T>& _mat) const { return Matrix<T>(*this)*_mat; }
+    //  column vector times a 1 x n matrix: the outer product, each entry ONE product (no accumulation from zero: 0 * -1 stays -0, Vector.h:253-263)
+    template<class T> inline Matrix<T> Vector<T>::operator*(const Matrix<T>& _mat) const {
+        assert(_mat.row == 1);
+        Matrix<T> r(SIZE(), _mat.col);
+        for (int i = 0; i < SIZE(); i++) for (int j = 0; j < _mat.col; j++) r.values[(size_t)i*_mat.col + j] = values[i]*_mat.values[j];
+        return r;
+    }
 
     template<class U>
     inline std::ostream& operator<<(std::ostream& _out, const Matrix<U>& _mat) {

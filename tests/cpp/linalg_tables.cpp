@@ -28,7 +28,8 @@ int main() {
     vec("a normal", a.Normal()); vec("a x b", VectorProduct(a, b)); vec("a vstack b", a.Vstack(b)); vec("segment", a.Vstack(b).Segment(1, 4));
     Vector<double> c = a; c += b; vec("+=", c); c -= a; vec("-=", c); c *= 3.0; vec("*=", c); c /= -0.7; vec("/=", c);
     vec("from std::vector", Vector<double>(std::vector<double>({ 9.5, -1.25 })));
-    mat("a transpose", a.Transpose()); mat("a * b^T", a*b.Transpose()); mat("diagonal(a)", Diagonal(a)); mat("identity", Identity<double>(3));
+    mat("a transpose", a.Transpose()); mat("a * b^T", a*b.Transpose());
+    mat("signed zeros of an outer product", Vector<double>({ 0.0, 2.0, -0.0 })*Vector<double>({ -1.0, 0.0, 3.0 }).Transpose()); mat("diagonal(a)", Diagonal(a)); mat("identity", Identity<double>(3));
     std::ostringstream os; os << a; std::printf("vector stream [%s]\n", os.str().c_str());
 
     Matrix<double> M(3, 3), N(3, 2);

@@ -18,5 +18,5 @@ def test_vector_matrix_and_sparse_containers_match_the_reference(tmp_path, golde
                     "-o", str(exe), f"-L{os.path.dirname(lib)}", "-lpansfem2_b200", f"-Wl,-rpath,{os.path.dirname(lib)}"], check=True)
     got = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     want = open(os.path.join(golden_dir, "linalg_tables.txt")).read()
-    assert got.count("\n") == want.count("\n") == 137
+    assert got.count("\n") == want.count("\n") == 141
     assert got == want
