@@ -334,8 +334,9 @@ int pf2_csr_pattern(pf2_ctx* ctx, pf2_mesh* mesh, pf2_dofmap* map, pf2_csr** out
     bmap_kernel<<<ctx->grid_for((long long)nelem * npe * npe), kThreads, 0, s>>>(nelem, npe, mesh->conn, adj_ptr, adj, adjfree, A->bmap);
     PF2_LAUNCH_CHECK();
     ctx->launches += 7;
-    // gather plan for the numeric phase (assemble_gather.cuh)
-    {
+    // gather plan for the numeric phase (assemble_gather.cuh): kept for 2-D meshes only, where the kernel is used (a hex8 mesh would
+    // carry 8 element ids per element for nothing: 0.45 GB on configs[4])
+    if (mesh->dim == 2) {
         sort_n2e_kernel<<<gnode, kThreads, 0, s>>>(nnode, n2e_ptr, n2e);
         PF2_LAUNCH_CHECK();
         int* nfree = nullptr;
