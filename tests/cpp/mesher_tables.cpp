@@ -6,6 +6,9 @@
 #include <vector>
 #include "LinearAlgebra/Models/Vector.h"
 #include "PrePost/Mesher/SquareMesh.h"
+#include "PrePost/Mesher/AnnulusMesh.h"
+#include "PrePost/Mesher/SquareAnnulusMesh.h"
+#include "PrePost/Mesher/SquareCircleAnnulusMesh.h"
 
 using namespace PANSFEM2;
 
@@ -58,6 +61,31 @@ int main() {
         lists("edges", mesh.GenerateEdges());
         fixed("right side", mesh.GenerateFixedlist({ 1 }, [](Vector<double> p) { return std::fabs(p(0) - 3.0) < 1.0e-9; }));
         fixed("centre lines", mesh.GenerateFixedlist({ 0 }, [](Vector<double> p) { return std::fabs(p(0) - 1.5) < 1.0e-12 || std::fabs(p(1) - 1.0) < 1.0e-12; }));
+    }
+    //----------ring-shaped meshers----------
+    {
+        std::printf("== AnnulusMesh\n");
+        AnnulusMesh<double> mesh(0.4, 1.7, 3, 7);
+        nodes("nodes", mesh.GenerateNodes()); lists("elements", mesh.GenerateElements()); lists("edges", mesh.GenerateEdges());
+        fixed("outer circle", mesh.GenerateFixedlist({ 0, 1 }, [](Vector<double> p) { return std::fabs(p.Norm() - 1.7) < 1.0e-9; }));
+        fixed("upper half", mesh.GenerateFixedlist({ 1 }, [](Vector<double> p) { return p(1) > 1.0e-9; }));
+    }
+    {
+        std::printf("== SquareAnnulusMesh\n");
+        SquareAnnulusMesh<double> mesh(1.0, 1.4, 0.35, 0.6, 4, 3, 2);
+        nodes("nodes", mesh.GenerateNodes()); lists("elements", mesh.GenerateElements()); lists("edges", mesh.GenerateEdges());
+        fixed("outer frame by the fixed-list coordinates", mesh.GenerateFixedlist({ 0, 1 }, [](Vector<double> p) { return std::fabs(std::fabs(p(0)) - 0.5) < 1.0e-9 || std::fabs(std::fabs(p(1)) - 0.7) < 1.0e-9; }));
+        fixed("right of centre", mesh.GenerateFixedlist({ 0 }, [](Vector<double> p) { return p(0) > 0.2; }));
+        SquareAnnulusMesh<double> same(1.0, 1.0, 1.0 - 0.2, 1.0 - 0.6, 10, 10, 10);       // sample_optimize_homogenization.cpp:48 with a = 0.2, b = 0.6
+        std::vector<Vector<double> > all = same.GenerateNodes();
+        std::printf("homogenization cell %zu nodes, node 217: %.17g %.17g\n", all.size(), all[217](0), all[217](1));
+    }
+    {
+        std::printf("== SquareCircleAnnulusMesh\n");
+        SquareCircleAnnulusMesh<double> mesh(2.0, 1.0, 0.3, 1.5, 3, 2, 3);
+        nodes("nodes", mesh.GenerateNodes()); lists("elements", mesh.GenerateElements()); lists("edges", mesh.GenerateEdges());
+        fixed("hole", mesh.GenerateFixedlist({ 0, 1 }, [](Vector<double> p) { return std::fabs(p.Norm() - 0.3) < 1.0e-9; }));
+        fixed("left side", mesh.GenerateFixedlist({ 0 }, [](Vector<double> p) { return std::fabs(p(0) + 1.0) < 1.0e-9; }));
     }
     return 0;
 }

@@ -1,6 +1,7 @@
 """Host side of the header mirror: SquareMesh<T> (Q4 and the 8-node "2" variants, boundary edges, element / edge selection, fixed lists)
-and SquareMesh2<T> (graded) must generate exactly what the reference's PrePost/Mesher/SquareMesh.h generates - same coordinates to the
-last bit, same numbering, same order.  tests/cpp/mesher_tables.cpp is compiled against the mirror here and compared with its output when
+SquareMesh2<T> (graded) and the ring-shaped AnnulusMesh<T>, SquareAnnulusMesh<T> (with the reference's swapped-rectangle quirk in
+GenerateFixedlist), SquareCircleAnnulusMesh<T> must generate exactly what the reference's PrePost/Mesher headers generate - same
+coordinates to the last bit, same numbering, same order.  tests/cpp/mesher_tables.cpp is compiled against the mirror here and compared with its output when
 built against the reference's headers (tests/golden/mesher_tables.txt; tests/golden/make_golden.py meshers).  CPU only."""
 import os
 import subprocess
@@ -14,5 +15,5 @@ def test_square_meshers_match_the_reference(tmp_path, golden_dir):
                     f"{ROOT}/tests/cpp/mesher_tables.cpp", "-o", str(exe)], check=True)
     got = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     want = open(os.path.join(golden_dir, "mesher_tables.txt")).read()
-    assert got.count("\n") == want.count("\n") == 641
+    assert got.count("\n") == want.count("\n") == 911
     assert got == want
