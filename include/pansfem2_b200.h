@@ -51,10 +51,13 @@ enum { PF2_EQ_PLANESTRAIN = 0, PF2_EQ_SOLID = 1, PF2_EQ_HEAT = 2 };
  * so the legacy values 0, 1, 2 are themselves valid codes.  The rule must belong to the shape's reference domain
  * (triangle, square, tetrahedron, cube), otherwise PF2_E_INVALID. */
 enum { PF2_PHYS_PLANESTRAIN = 0, PF2_PHYS_SOLID = 1, PF2_PHYS_HEAT = 2, PF2_PHYS_PLANESTRESS = 3, PF2_PHYS_PLANESTRAIN_SRI = 4, PF2_PHYS_MASS = 5,
-       PF2_PHYS_PLANESTRAIN_BBAR = 6, PF2_PHYS_MASS2 = 7, PF2_PHYS_PLANESTRAIN_WT = 8, PF2_PHYS_ADVDIFF = 9 };
+       PF2_PHYS_PLANESTRAIN_BBAR = 6, PF2_PHYS_MASS2 = 7, PF2_PHYS_PLANESTRAIN_WT = 8, PF2_PHYS_ADVDIFF = 9,
+       PF2_PHYS_PLANE_D = 10, PF2_PHYS_PLANE_D_BBAR = 11, PF2_PHYS_PLANE_D_WT = 12 };
 /* PF2_PHYS_ADVDIFF: the scalar advection-diffusion routines of Advection.h on any 2-D shape / rule; the quad2 field of the code is
  * the MASK of the routines to sum: Advection (Advection.h:19), Diffusion (:135), AdvectionSUPG (:47), AdvectionShockCapturing (:91),
  * Mass (:161), MassSUPG (:188).  pf2_element_matrix takes (E, V, t) = (ax, ay, k); systems are assembled by pf2_advdiff_assemble. */
+/* PF2_PHYS_PLANE_D / _D_BBAR / _D_WT: PlaneStiffness, PlaneStiffnessBbar (quad = ICD, quad2 = ICV) and PlaneStiffnessWilsonTaylor of
+ * Homogenization.h:141-280 - plane elements with a caller-supplied 3 x 3 constitutive matrix; one element through pf2_element_matrix_d. */
 enum { PF2_ADV_ADVECTION = 1, PF2_ADV_DIFFUSION = 2, PF2_ADV_SUPG = 4, PF2_ADV_SHOCK = 8, PF2_ADV_MASS = 16, PF2_ADV_MASS_SUPG = 32 };
 enum { PF2_SHAPE_DEFAULT = 0, PF2_SHAPE_T3 = 1, PF2_SHAPE_T6 = 2, PF2_SHAPE_Q4 = 3, PF2_SHAPE_Q8 = 4, PF2_SHAPE_TET4 = 5,
        PF2_SHAPE_HEX8 = 6, PF2_SHAPE_HEX20 = 7 };
@@ -158,6 +161,8 @@ int pf2_advdiff_assemble(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq, co
 /* one element matrix, host in / host out: the reference's per-element call kept for parity
  * (PlaneStrain.h:21-58, Solid.h:21-64, HeatTransfer.h:20-43).  xe: npe*dim, Ke_out: (npe*ndof)^2 row-major. */
 int pf2_element_matrix(pf2_ctx* ctx, int eq, const double* xe_host, double E, double V, double t, double* Ke_host);
+/* the same for the PF2_PHYS_PLANE_D* selections (Homogenization.h:141-280): D_host = the 3 x 3 constitutive matrix, row-major */
+int pf2_element_matrix_d(pf2_ctx* ctx, int eq, const double* xe_host, const double D_host[9], double t, double* Ke_host);
 
 /* ---- CSR<T>::operator* (CSR.h:109-122) ------------------------------------------------------------------------ */
 int pf2_spmv(pf2_csr* A, const double* x_dev, double* y_dev);

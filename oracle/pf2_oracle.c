@@ -268,11 +268,17 @@ static void inv4(const double* v, double* inv) {
 }
 
 /* PlaneStrainStiffnessWilsonTaylor  src/FEM/Equation/PlaneStrain.h:189-243: incompatible modes P = (1 - r0^2, 1 - r1^2), statically condensed */
+static void wilson_taylor_d(int shape, int quad, int npe, const double* xe, const double* D, double t, double* Ke);
 static void wilson_taylor(int shape, int quad, int npe, const double* xe, double E, double V, double t, double* Ke) {
-    const int m = 2 * npe, ng = quad_count(quad);
     double D[9] = { 1.0 - V, V, 0, V, 1.0 - V, 0, 0, 0, 0.5 * (1.0 - 2.0 * V) };
     const double f = E / ((1.0 - 2.0 * V) * (1.0 + V));
     for (int i = 0; i < 9; i++) D[i] *= f;
+    wilson_taylor_d(shape, quad, npe, xe, D, t, Ke);
+}
+/* PlaneStrainStiffnessWilsonTaylor (PlaneStrain.h:189-243) and PlaneStiffnessWilsonTaylor (Homogenization.h:230-280) are the same
+ * statements around a different D */
+static void wilson_taylor_d(int shape, int quad, int npe, const double* xe, const double* D, double t, double* Ke) {
+    const int m = 2 * npe, ng = quad_count(quad);
     double Keaa[16], Kead[4 * ORC_MAX_M];
     memset(Keaa, 0, sizeof Keaa); memset(Kead, 0, sizeof(double) * 4 * m); memset(Ke, 0, sizeof(double) * m * m);
     for (int g = 0; g < ng; g++) {
@@ -434,6 +440,24 @@ void orc_element_matrix(int eq, const double* xe, double E, double V, double t, 
     }
     accumulate_rule(s.phys, s.shape, s.quad, dim, npe, ndof, xe, D, ns, E, t, Ke, 0);     /* heat / mass: E carries the coefficient */
     if (s.phys == PHYS_MASS) for (int i = 0; i < m * m; i++) Ke[i] *= E * t;            /* the reference's mass has no coefficient */
+}
+
+/* PlaneStiffness / PlaneStiffnessBbar / PlaneStiffnessWilsonTaylor   src/FEM/Equation/Homogenization.h:141-166, 170-226, 230-280:
+ * the plane routines with a caller-supplied 3 x 3 constitutive matrix D (row-major).  eq: phys 10 / 11 / 12 of include/pansfem2_b200.h. */
+void orc_element_matrix_d(int eq, const double* xe, const double* D, double t, double* Ke) {
+    const orc_sel s0 = decode_eq(eq);
+    orc_sel s = s0;
+    const int npe = npe_of(eq), m = 2 * npe;
+    const int tri = s.shape == SHAPE_T3 || s.shape == SHAPE_T6;
+    if (s.phys == 11 && !s.quad2) s.quad2 = tri ? QUAD_G1TRI : QUAD_G1SQ;
+    memset(Ke, 0, sizeof(double) * m * m);
+    if (s.phys == 12) { wilson_taylor_d(s.shape, s.quad, npe, xe, D, t, Ke); return; }
+    if (s.phys == 11) {
+        accumulate_rule(PHYS_PLANESTRAIN_BBAR, s.shape, s.quad2, 2, npe, 2, xe, D, 3, 1.0, t, Ke, 1);
+        accumulate_rule(PHYS_PLANESTRAIN_BBAR, s.shape, s.quad, 2, npe, 2, xe, D, 3, 1.0, t, Ke, 2);
+        return;
+    }
+    accumulate_rule(PHYS_PLANESTRAIN, s.shape, s.quad, 2, npe, 2, xe, D, 3, 1.0, t, Ke, 0);
 }
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -313,3 +313,12 @@ def advdiff_system(shape, quad, terms, coords, conn, fixed_nodes, fixed_vals, ve
     lib().orc_advdiff_assemble(S.h, shape, quad, terms, _p(coords, np.float64), conn.shape[0], _p(conn, np.int32), _p(n2g, np.int32),
                                _p(vel, np.float64), C.c_double(k), C.c_double(dt), C.c_double(theta), _p(T, np.float64))
     return S, n2g, T
+
+
+def element_matrix_d(eq, xe, D, t=1.0):
+    """PlaneStiffness / PlaneStiffnessBbar / PlaneStiffnessWilsonTaylor (Homogenization.h:141-280): eq with phys 10 / 11 / 12, D 3 x 3."""
+    xe, D = _f64(xe), _f64(D).reshape(9)
+    m = 2 * xe.shape[0]
+    Ke = np.zeros((m, m))
+    lib().orc_element_matrix_d(int(eq), _p(xe, np.float64), _p(D, np.float64), C.c_double(t), _p(Ke, np.float64))
+    return Ke

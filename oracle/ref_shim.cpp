@@ -39,6 +39,7 @@
 #include "FEM/Equation/Solid.h"
 #include "FEM/Equation/HeatTransfer.h"
 #include "FEM/Equation/Advection.h"
+#include "FEM/Equation/Homogenization.h"
 #include "FEM/Equation/ReactionDiffusion.h"
 #include "FEM/Equation/General.h"
 #include "FEM/Controller/ShapeFunction.h"
@@ -451,6 +452,53 @@ void* ref_advection_system(int nnode, const double* coords, int nelem, const int
     }
     sys->K = new CSR<double>(K);
     return sys;
+}
+
+// ---- PlaneStiffness / PlaneStiffnessBbar / PlaneStiffnessWilsonTaylor (Homogenization.h:141-280) for any 2-D <SF, IC[, ICV]>;
+//      mode 0 / 1 / 2; quad2 = ICV of the B-bar variant ----
+}   // extern "C"
+namespace {
+template<template<class>class SF, template<class>class IC, template<class>class ICV>
+void plane_d(int mode, Matrix<double>& Ke, N2E& n2e, const std::vector<int>& el, std::vector<Vector<double> >& x, Matrix<double> D, double t) {
+    if (mode == 1) PlaneStiffnessBbar<double, SF, ICV, IC>(Ke, n2e, el, { 0, 1 }, x, D, t);
+    else if (mode == 2) PlaneStiffnessWilsonTaylor<double, SF, IC>(Ke, n2e, el, { 0, 1 }, x, D, t);
+    else PlaneStiffness<double, SF, IC>(Ke, n2e, el, { 0, 1 }, x, D, t);
+}
+template<template<class>class SF>
+void plane_d_tri(int mode, int quad, int quad2, Matrix<double>& Ke, N2E& n2e, const std::vector<int>& el, std::vector<Vector<double> >& x, Matrix<double> D, double t) {
+    if (quad == QUAD_G3TRI) { if (quad2 == QUAD_G3TRI) plane_d<SF, Gauss3Triangle, Gauss3Triangle>(mode, Ke, n2e, el, x, D, t); else plane_d<SF, Gauss3Triangle, Gauss1Triangle>(mode, Ke, n2e, el, x, D, t); }
+    else { if (quad2 == QUAD_G3TRI) plane_d<SF, Gauss1Triangle, Gauss3Triangle>(mode, Ke, n2e, el, x, D, t); else plane_d<SF, Gauss1Triangle, Gauss1Triangle>(mode, Ke, n2e, el, x, D, t); }
+}
+template<template<class>class SF, template<class>class IC>
+void plane_d_sq2(int mode, int quad2, Matrix<double>& Ke, N2E& n2e, const std::vector<int>& el, std::vector<Vector<double> >& x, Matrix<double> D, double t) {
+    if (quad2 == QUAD_G4SQ) plane_d<SF, IC, Gauss4Square>(mode, Ke, n2e, el, x, D, t);
+    else if (quad2 == QUAD_G9SQ) plane_d<SF, IC, Gauss9Square>(mode, Ke, n2e, el, x, D, t);
+    else plane_d<SF, IC, Gauss1Square>(mode, Ke, n2e, el, x, D, t);
+}
+template<template<class>class SF>
+void plane_d_sq(int mode, int quad, int quad2, Matrix<double>& Ke, N2E& n2e, const std::vector<int>& el, std::vector<Vector<double> >& x, Matrix<double> D, double t) {
+    if (quad == QUAD_G1SQ) plane_d_sq2<SF, Gauss1Square>(mode, quad2, Ke, n2e, el, x, D, t);
+    else if (quad == QUAD_G9SQ) plane_d_sq2<SF, Gauss9Square>(mode, quad2, Ke, n2e, el, x, D, t);
+    else plane_d_sq2<SF, Gauss4Square>(mode, quad2, Ke, n2e, el, x, D, t);
+}
+}   // namespace
+extern "C" {
+int ref_plane_d_element(int shape, int quad, int quad2, int mode, int npe, const double* xe, const double* D9, double t, double* Ke_out) {
+    std::vector<Vector<double> > x = make_nodes(2, npe, xe);
+    std::vector<int> element(npe);
+    std::iota(element.begin(), element.end(), 0);
+    Matrix<double> D(3, 3), Ke;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) D(i, j) = D9[3 * i + j];
+    N2E n2e;
+    switch (shape) {
+        case SHAPE_T3: plane_d_tri<ShapeFunction3Triangle>(mode, quad, quad2, Ke, n2e, element, x, D, t); break;
+        case SHAPE_T6: plane_d_tri<ShapeFunction6Triangle>(mode, quad, quad2, Ke, n2e, element, x, D, t); break;
+        case SHAPE_Q8: plane_d_sq<ShapeFunction8Square>(mode, quad, quad2, Ke, n2e, element, x, D, t); break;
+        default: plane_d_sq<ShapeFunction4Square>(mode, quad, quad2, Ke, n2e, element, x, D, t); break;
+    }
+    const int m = 2 * npe;
+    for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) Ke_out[i * m + j] = Ke(i, j);
+    return m;
 }
 
 // ---- the advection-diffusion element family (Advection.h:19-229) for any 2-D <SF, IC>, and the systems the two advection samples

@@ -354,3 +354,12 @@ def advdiff_system(shape, quad, terms, coords, conn, fixed_nodes, fixed_vals, ve
     return System(lib().ref_advdiff_system(shape, quad, terms, coords.shape[0], _p(coords, np.float64), conn.shape[1], conn.shape[0],
                                            _p(conn, np.int32), len(fn), _p(fn, np.int32), _p(fv, np.float64), _p(vel, np.float64),
                                            C.c_double(k), C.c_double(dt), C.c_double(theta), _p(Tn, np.float64)))
+
+
+def plane_d_element(shape, quad, quad2, mode, xe, D, t=1.0):
+    """PlaneStiffness (mode 0) / PlaneStiffnessBbar (1; quad = ICD, quad2 = ICV) / PlaneStiffnessWilsonTaylor (2) of Homogenization.h."""
+    xe, D = _f64(xe), _f64(D).reshape(9)
+    m = 2 * xe.shape[0]
+    Ke = np.zeros((m, m))
+    lib().ref_plane_d_element(shape, quad, quad2, mode, xe.shape[0], _p(xe, np.float64), _p(D, np.float64), C.c_double(t), _p(Ke, np.float64))
+    return Ke

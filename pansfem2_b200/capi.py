@@ -149,6 +149,14 @@ class Context:
         _ck(lib().pf2_element_matrix(self.h, eq, _p(xe, np.float64), C.c_double(E), C.c_double(V), C.c_double(t), _p(Ke, np.float64)))
         return Ke
 
+    def element_matrix_d(self, eq, xe, D, t=1.0):
+        """PF2_PHYS_PLANE_D* selections (PlaneStiffness*, Homogenization.h:141-280): D is the 3 x 3 constitutive matrix."""
+        xe, D = _f64(xe), _f64(D).reshape(9)
+        m = xe.shape[0] * 2
+        Ke = np.zeros((m, m))
+        _ck(lib().pf2_element_matrix_d(self.h, eq, _p(xe, np.float64), _p(D, np.float64), C.c_double(t), _p(Ke, np.float64)))
+        return Ke
+
     def close(self):
         if self.h:
             lib().pf2_ctx_destroy(self.h)

@@ -237,6 +237,7 @@ int sens_generic_launch(pf2_mesh* mesh, const EqInfo& q, const double* u_nodal, 
 int element_generic_launch(pf2_ctx* ctx, const EqInfo& q, const double* xe_dev, double E, double t, double* Ke_dev);
 int mf_update(pf2_csr* A, pf2_mesh* mesh, const double* modulus_dev, const double* rho_dev, const double params[5]);
 int advdiff_element_launch(pf2_ctx* ctx, const EqInfo& q, const double* xe_dev, double ax, double ay, double k, double* Ke_dev);
+int element_general_launch(pf2_ctx* ctx, const EqInfo& q, const double* xe_dev, const double D[9], double t, double* Ke_dev);
 
 // numeric assembly with the nodal loads already on the device (the design loop keeps them resident)
 int assemble_device(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq, const double* modulus_dev, const double* rho_dev,
@@ -245,6 +246,7 @@ int assemble_device(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq, const d
     PF2_TRY(decode_eq(eq, params[2], &q));
     PF2_CHECK(A->bmap != nullptr, "matrix was not built by pf2_csr_pattern");
     PF2_CHECK(q.phys != PF2_PHYS_ADVDIFF, "advection-diffusion selections are assembled by pf2_advdiff_assemble");
+    PF2_CHECK(q.phys < PF2_PHYS_PLANE_D, "selections with a caller-supplied constitutive matrix have the per-element entry point only (pf2_element_matrix_d)");
     PF2_CHECK(q.npe == mesh->npe && q.dim == mesh->dim, "equation does not match the mesh's element type");
     PF2_CHECK(q.ndof == map->ndof, "equation does not match the dof map (the reference asserts doulist.size(), PlaneStrain.h:22)");
     PF2_CHECK(A->map_nelem == mesh->nelem && A->map_npe == mesh->npe && A->map_ndof == map->ndof, "pattern built for another mesh");
@@ -293,6 +295,7 @@ int compliance_sens_device(pf2_mesh* mesh, int eq, const double* u_nodal, const 
     PF2_TRY(decode_eq(eq, params[2], &q));
     PF2_CHECK(q.npe == mesh->npe && q.dim == mesh->dim, "equation does not match the mesh");
     PF2_CHECK(q.phys != PF2_PHYS_ADVDIFF, "no compliance / sensitivity pass for the (non-symmetric) advection-diffusion operator");
+    PF2_CHECK(q.phys < PF2_PHYS_PLANE_D, "selections with a caller-supplied constitutive matrix have the per-element entry point only (pf2_element_matrix_d)");
     const int ndof = q.ndof;
     if (r_nodal) PF2_CUDA(cudaMemsetAsync(r_nodal, 0, sizeof(double) * (size_t)mesh->nnode * ndof, s));
     if (!q.fast) return sens_generic_launch(mesh, q, u_nodal, rho, params, f_dev, dfdrho, r_nodal);
@@ -338,6 +341,7 @@ int pf2_element_matrix(pf2_ctx* ctx, int eq, const double* xe_host, double E, do
     PF2_CHECK(ctx && xe_host && Ke_host, "bad arguments");
     EqInfo q;
     PF2_TRY(decode_eq(eq, V, &q));
+    PF2_CHECK(q.phys < PF2_PHYS_PLANE_D, "this selection takes a constitutive matrix: pf2_element_matrix_d");
     const int npe = q.npe, dim = q.dim, m = npe * q.ndof;
     if (!ctx->elem_scratch) PF2_TRY(dev_alloc(&ctx->elem_scratch, (size_t)64 + 3600));      // hex20: 60 coordinates, 60 x 60 entries
     double *xe = ctx->elem_scratch, *Ke = ctx->elem_scratch + 64;
@@ -351,6 +355,21 @@ int pf2_element_matrix(pf2_ctx* ctx, int eq, const double* xe_host, double E, do
         PF2_LAUNCH_CHECK();
         ctx->launches++;
     }
+    PF2_CUDA(cudaMemcpyAsync(Ke_host, Ke, sizeof(double) * m * m, cudaMemcpyDeviceToHost, ctx->stream));
+    PF2_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PF2_OK;
+}
+
+int pf2_element_matrix_d(pf2_ctx* ctx, int eq, const double* xe_host, const double D_host[9], double t, double* Ke_host) {
+    PF2_CHECK(ctx && xe_host && D_host && Ke_host, "bad arguments");
+    EqInfo q;
+    PF2_TRY(decode_eq(eq, 0.0, &q));
+    PF2_CHECK(q.phys >= PF2_PHYS_PLANE_D, "not a PF2_PHYS_PLANE_D* selection");
+    const int npe = q.npe, m = npe * 2;
+    if (!ctx->elem_scratch) PF2_TRY(dev_alloc(&ctx->elem_scratch, (size_t)64 + 3600));
+    double *xe = ctx->elem_scratch, *Ke = ctx->elem_scratch + 64;
+    PF2_CUDA(cudaMemcpyAsync(xe, xe_host, sizeof(double) * npe * 2, cudaMemcpyHostToDevice, ctx->stream));
+    PF2_TRY(element_general_launch(ctx, q, xe, D_host, t, Ke));
     PF2_CUDA(cudaMemcpyAsync(Ke_host, Ke, sizeof(double) * m * m, cudaMemcpyDeviceToHost, ctx->stream));
     PF2_CUDA(cudaStreamSynchronize(ctx->stream));
     return PF2_OK;

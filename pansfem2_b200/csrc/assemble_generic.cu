@@ -42,7 +42,8 @@ static int quad_domain(int quad) {
 int decode_eq(int eq, double V, EqInfo* out) {
     EqInfo q;
     q.phys = eq & 0xff; q.shape = (eq >> 8) & 0xff; q.quad = (eq >> 16) & 0xff; q.quad2 = (eq >> 24) & 0xff;
-    PF2_CHECK(eq >= 0 && q.phys <= PF2_PHYS_ADVDIFF, "unknown equation");
+    PF2_CHECK(eq >= 0 && q.phys <= PF2_PHYS_PLANE_D_WT, "unknown equation");
+    const bool gend = q.phys >= PF2_PHYS_PLANE_D;     // caller-supplied constitutive matrix
     const bool adv = q.phys == PF2_PHYS_ADVDIFF;     // quad2 carries the PF2_ADV_* mask
     PF2_CHECK(q.shape <= PF2_SHAPE_HEX20 && q.quad <= PF2_QUAD_G27CUBE && (adv || q.quad2 <= PF2_QUAD_G27CUBE), "unknown shape function / integration rule");
     PF2_CHECK(!adv || (q.quad2 >= 1 && q.quad2 <= 63), "advection-diffusion: the quad2 field must select at least one routine (PF2_ADV_*)");
@@ -54,7 +55,7 @@ int decode_eq(int eq, double V, EqInfo* out) {
     static const int dflt_reduced[4] = { PF2_QUAD_G1TRI, PF2_QUAD_G1SQ, PF2_QUAD_G1TET, PF2_QUAD_G8CUBE };
     if (q.quad == 0) q.quad = dflt[dom];
     PF2_CHECK(quad_domain(q.quad) == dom, "integration rule does not belong to the shape function's reference domain");
-    if (q.phys == PF2_PHYS_PLANESTRAIN_SRI || q.phys == PF2_PHYS_PLANESTRAIN_BBAR) {
+    if (q.phys == PF2_PHYS_PLANESTRAIN_SRI || q.phys == PF2_PHYS_PLANESTRAIN_BBAR || q.phys == PF2_PHYS_PLANE_D_BBAR) {
         if (q.quad2 == 0) q.quad2 = dflt_reduced[dom];
         PF2_CHECK(quad_domain(q.quad2) == dom, "volumetric integration rule does not belong to the shape function's reference domain");
     } else if (!adv) {
@@ -63,14 +64,14 @@ int decode_eq(int eq, double V, EqInfo* out) {
     q.dim = solid ? 3 : 2;
     q.npe = shape_npe(q.shape);
     q.ndof = solid ? 3 : ((q.phys == PF2_PHYS_HEAT || q.phys == PF2_PHYS_MASS || adv) ? 1 : 2);
-    q.kind = adv ? KIND_ADVDIFF2D : solid ? KIND_SOLID3D : (q.phys == PF2_PHYS_HEAT ? KIND_HEAT2D : (q.phys == PF2_PHYS_MASS ? KIND_MASS2D : (q.phys == PF2_PHYS_MASS2 ? KIND_MASS2D_V : KIND_ELAST2D)));
+    q.kind = gend ? KIND_ELAST2D_D : adv ? KIND_ADVDIFF2D : solid ? KIND_SOLID3D : (q.phys == PF2_PHYS_HEAT ? KIND_HEAT2D : (q.phys == PF2_PHYS_MASS ? KIND_MASS2D : (q.phys == PF2_PHYS_MASS2 ? KIND_MASS2D_V : KIND_ELAST2D)));
     q.fast = (q.phys == PF2_PHYS_PLANESTRAIN && q.shape == PF2_SHAPE_Q4 && q.quad == PF2_QUAD_G4SQ) ||
              (q.phys == PF2_PHYS_HEAT && q.shape == PF2_SHAPE_Q4 && q.quad == PF2_QUAD_G4SQ) ||
              (solid && q.shape == PF2_SHAPE_HEX8 && q.quad == PF2_QUAD_G8CUBE);
     q.legacy = solid ? PF2_EQ_SOLID : (q.phys == PF2_PHYS_HEAT ? PF2_EQ_HEAT : PF2_EQ_PLANESTRAIN);
     // D for unit modulus
     q.npass = 1; q.cn[0] = q.cn[1] = 1.0; q.lam[0] = q.lam[1] = 0.0; q.mu[0] = q.mu[1] = 0.0;
-    if (q.phys == PF2_PHYS_PLANESTRAIN_WT)
+    if (q.phys == PF2_PHYS_PLANESTRAIN_WT || q.phys == PF2_PHYS_PLANE_D_WT)
         PF2_CHECK(dom == 1 && q.quad != PF2_QUAD_G1SQ, "Wilson-Taylor: quadrilateral shapes with at least Gauss4Square (the modes vanish at the centre point)");
     if (q.phys == PF2_PHYS_PLANESTRAIN || q.phys == PF2_PHYS_PLANESTRAIN_WT || solid) {          // PlaneStrain.h:37-41, Solid.h:37-44
         const double c = 1.0 / ((1.0 + V) * (1.0 - 2.0 * V));
@@ -214,6 +215,39 @@ struct ElemGeneric {
     double t;
     __device__ __forceinline__ void rows(const double (&X)[NPE][DIM], int a, double (&acc)[NDOF][NPE * NDOF]) const { generic_rows<KIND, SHAPE>(X, a, sp, t, acc); }
 };
+
+// one element with a caller-supplied constitutive matrix (PlaneStiffness*, Homogenization.h:141-280)
+template <int SHAPE>
+__global__ void element_general_kernel(ElemSpecD sp, const double* __restrict__ xe, double t, double* __restrict__ Ke) {
+    constexpr int NPE = ShapeTraits<SHAPE>::NPE, M = NPE * 2;
+    const int a = threadIdx.x;
+    if (a >= NPE) return;
+    double X[NPE][2];
+    for (int n = 0; n < NPE; n++) { X[n][0] = xe[n * 2]; X[n][1] = xe[n * 2 + 1]; }
+    double acc[2][M];
+    general_rows<SHAPE>(X, a, sp, t, acc);
+    for (int i = 0; i < 2; i++) for (int j = 0; j < M; j++) Ke[(a * 2 + i) * M + j] = acc[i][j];
+}
+
+ElemSpecD make_spec_d(const EqInfo& q, const double D[9]) {
+    ElemSpecD sp;
+    sp.mode = (q.phys == PF2_PHYS_PLANE_D_BBAR) ? 1 : ((q.phys == PF2_PHYS_PLANE_D_WT) ? 2 : 0);
+    if (sp.mode == 1) { sp.quad[0] = q.quad2; sp.quad[1] = q.quad; }       // volumetric rule first, as PlaneStiffnessBbar integrates
+    else { sp.quad[0] = q.quad; sp.quad[1] = q.quad; }
+    for (int i = 0; i < 9; i++) sp.D[i] = D[i];
+    return sp;
+}
+
+int element_general_launch(pf2_ctx* ctx, const EqInfo& q, const double* xe_dev, const double D[9], double t, double* Ke_dev) {
+    const ElemSpecD sp = make_spec_d(q, D);
+    if (q.shape == PF2_SHAPE_T3) element_general_kernel<SH_T3><<<1, 32, 0, ctx->stream>>>(sp, xe_dev, t, Ke_dev);
+    else if (q.shape == PF2_SHAPE_T6) element_general_kernel<SH_T6><<<1, 32, 0, ctx->stream>>>(sp, xe_dev, t, Ke_dev);
+    else if (q.shape == PF2_SHAPE_Q4) element_general_kernel<SH_Q4><<<1, 32, 0, ctx->stream>>>(sp, xe_dev, t, Ke_dev);
+    else element_general_kernel<SH_Q8><<<1, 32, 0, ctx->stream>>>(sp, xe_dev, t, Ke_dev);
+    PF2_LAUNCH_CHECK();
+    ctx->launches++;
+    return PF2_OK;
+}
 
 // (kind, shape) -> instantiation
 #define PF2_DISPATCH_SHAPE(q, CALL)                                                                  \

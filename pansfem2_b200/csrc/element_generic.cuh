@@ -21,7 +21,8 @@ namespace pf2 {
 enum { SH_T3 = PF2_SHAPE_T3, SH_T6 = PF2_SHAPE_T6, SH_Q4 = PF2_SHAPE_Q4, SH_Q8 = PF2_SHAPE_Q8, SH_TET4 = PF2_SHAPE_TET4,
        SH_HEX8 = PF2_SHAPE_HEX8, SH_HEX20 = PF2_SHAPE_HEX20 };
 enum { KIND_ELAST2D = 0, KIND_HEAT2D = 1, KIND_SOLID3D = 2, KIND_MASS2D = 3, KIND_MASS2D_V = 4,
-       KIND_ADVDIFF2D = 5 };   // the last one lives in element_advdiff.cuh / advdiff.cu, not in the generic template
+       KIND_ADVDIFF2D = 5,     // lives in element_advdiff.cuh / advdiff.cu, not in the generic template
+       KIND_ELAST2D_D = 6 };   // caller-supplied constitutive matrix: general_rows below, per-element entry point only
 
 // what one launch needs to know about the element routine (filled on the host by decode_eq, passed by value)
 struct ElemSpec {
@@ -575,6 +576,146 @@ PF2_HD double generic_energy(const double (&X)[ShapeTraits<SHAPE>::NPE][ShapeTra
         }
     }
     return wsum;
+}
+
+// ---- arbitrary constitutive matrix (FEM/Equation/Homogenization.h:141-280) -----------------------------------------------------
+// PlaneStiffness, PlaneStiffnessBbar and PlaneStiffnessWilsonTaylor take a caller-supplied 3 x 3 D (a homogenised, rotated material),
+// so the isotropic closed form above does not apply: the (a, b) block is Ba^T D Bb with the 3 x 2 strain-displacement columns of the two
+// nodes.  mode 0: B = [gx 0; 0 gy; gy gx];  mode 1 (B-bar): Bvol = [gx gy; gx gy; 0 0]/2 on rule quad[0] plus
+// Bdev = [gx -gy; -gx gy; 2gy 2gx]/2 on rule quad[1];  mode 2: Wilson-Taylor modes condensed out as in wt_rows, Ke -= Kead^T Keaa^-1 Kead.
+struct ElemSpecD {
+    int mode;           // 0 plain, 1 B-bar, 2 Wilson-Taylor
+    int quad[2];
+    double D[9];        // row-major
+};
+
+PF2_HD void strain_columns(int part, double gx, double gy, double (&B)[3][2]) {
+    if (part == 1) { B[0][0] = 0.5 * gx; B[0][1] = 0.5 * gy; B[1][0] = 0.5 * gx; B[1][1] = 0.5 * gy; B[2][0] = 0.0; B[2][1] = 0.0; }
+    else if (part == 2) { B[0][0] = 0.5 * gx; B[0][1] = -0.5 * gy; B[1][0] = -0.5 * gx; B[1][1] = 0.5 * gy; B[2][0] = gy; B[2][1] = gx; }
+    else { B[0][0] = gx; B[0][1] = 0.0; B[1][0] = 0.0; B[1][1] = gy; B[2][0] = gy; B[2][1] = gx; }
+}
+// K += (Ba^T D Bb) * w
+PF2_HD void general_block(const double (&Ba)[3][2], const double (&Bb)[3][2], const double (&D)[9], double w, double (&K)[2][2]) {
+    double DB[3][2];
+#pragma unroll
+    for (int p = 0; p < 3; p++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) DB[p][j] = D[p * 3] * Bb[0][j] + D[p * 3 + 1] * Bb[1][j] + D[p * 3 + 2] * Bb[2][j];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) K[i][j] += (Ba[0][i] * DB[0][j] + Ba[1][i] * DB[1][j] + Ba[2][i] * DB[2][j]) * w;
+}
+
+// rows of local node a: acc[i][b*2 + j]
+template <int SHAPE>
+PF2_HD void general_rows(const double (&X)[ShapeTraits<SHAPE>::NPE][2], int a, const ElemSpecD& sp, double t, double (&acc)[2][ShapeTraits<SHAPE>::NPE * 2]) {
+    constexpr int NPE = ShapeTraits<SHAPE>::NPE, M = NPE * 2;
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < M; j++) acc[i][j] = 0.0;
+    if (sp.mode != 2) {
+        const int npass = (sp.mode == 1) ? 2 : 1;
+        for (int pass = 0; pass < npass; pass++) {
+            const int part = (sp.mode == 1) ? pass + 1 : 0, quad = sp.quad[pass];
+            const int ng = quad_count(quad);
+#pragma unroll 1
+            for (int q = 0; q < ng; q++) {
+                double r[3], wq, det, g[2][NPE];
+                quad_point(quad, q, r, wq);
+                shape_grad<SHAPE>(X, r, g, det);
+                const double w = det * t * wq;
+                double gax = g[0][0], gay = g[1][0];
+#pragma unroll
+                for (int n = 1; n < NPE; n++) if (n == a) { gax = g[0][n]; gay = g[1][n]; }
+                double Ba[3][2];
+                strain_columns(part, gax, gay, Ba);
+#pragma unroll
+                for (int b = 0; b < NPE; b++) {
+                    double Bb[3][2], K[2][2] = { { 0.0, 0.0 }, { 0.0, 0.0 } };
+                    strain_columns(part, g[0][b], g[1][b], Bb);
+                    general_block(Ba, Bb, sp.D, w, K);
+#pragma unroll
+                    for (int i = 0; i < 2; i++)
+#pragma unroll
+                        for (int j = 0; j < 2; j++) acc[i][b * 2 + j] += K[i][j];
+                }
+            }
+        }
+        return;
+    }
+    // Wilson-Taylor: the two incompatible modes act as extra "nodes" with gradients h_m (wt_grad)
+    double Kaa[4][4], Kad[4][M];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) Kaa[i][j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < M; j++) Kad[i][j] = 0.0;
+    }
+    const int ng = quad_count(sp.quad[0]);
+#pragma unroll 1
+    for (int q = 0; q < ng; q++) {
+        double r[3], wq, det, g[2][NPE], h[2][2];
+        quad_point(sp.quad[0], q, r, wq);
+        wt_grad<SHAPE>(X, r, g, h, det);
+        const double w = det * t * wq;
+        double gax = g[0][0], gay = g[1][0];
+#pragma unroll
+        for (int n = 1; n < NPE; n++) if (n == a) { gax = g[0][n]; gay = g[1][n]; }
+        double Ba[3][2], G[2][3][2];
+        strain_columns(0, gax, gay, Ba);
+#pragma unroll
+        for (int m = 0; m < 2; m++) strain_columns(0, h[0][m], h[1][m], G[m]);
+#pragma unroll
+        for (int b = 0; b < NPE; b++) {
+            double Bb[3][2], K[2][2] = { { 0.0, 0.0 }, { 0.0, 0.0 } };
+            strain_columns(0, g[0][b], g[1][b], Bb);
+            general_block(Ba, Bb, sp.D, w, K);
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) acc[i][b * 2 + j] += K[i][j];
+#pragma unroll
+            for (int m = 0; m < 2; m++) {               // Kead += G^T D B
+                double Kg[2][2] = { { 0.0, 0.0 }, { 0.0, 0.0 } };
+                general_block(G[m], Bb, sp.D, w, Kg);
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < 2; j++) Kad[m * 2 + i][b * 2 + j] += Kg[i][j];
+            }
+        }
+#pragma unroll
+        for (int m1 = 0; m1 < 2; m1++)
+#pragma unroll
+            for (int m2 = 0; m2 < 2; m2++) {            // Keaa += G^T D G
+                double Kg[2][2] = { { 0.0, 0.0 }, { 0.0, 0.0 } };
+                general_block(G[m1], G[m2], sp.D, w, Kg);
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < 2; j++) Kaa[m1 * 2 + i][m2 * 2 + j] += Kg[i][j];
+            }
+    }
+    // row (a, i) of Kead^T Keaa^-1 Kead = (Keaa^-T v)^T Kead with v = column a*2+i of Kead: solve Keaa^T z = v
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        double z[4], A[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            double v = Kad[k][0];
+#pragma unroll
+            for (int c = 1; c < M; c++) if (c == a * 2 + i) v = Kad[k][c];
+            z[k] = v;
+#pragma unroll
+            for (int j = 0; j < 4; j++) A[k][j] = Kaa[j][k];
+        }
+        solve4(A, z);
+#pragma unroll
+        for (int c = 0; c < M; c++) acc[i][c] -= z[0] * Kad[0][c] + z[1] * Kad[1][c] + z[2] * Kad[2][c] + z[3] * Kad[3][c];
+    }
 }
 
 }  // namespace pf2

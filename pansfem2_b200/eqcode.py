@@ -2,7 +2,7 @@
 <Equation, ShapeFunction, Integration> (host-side bookkeeping only)."""
 from __future__ import annotations
 
-PHYS_PLANESTRAIN, PHYS_SOLID, PHYS_HEAT, PHYS_PLANESTRESS, PHYS_PLANESTRAIN_SRI, PHYS_MASS, PHYS_PLANESTRAIN_BBAR, PHYS_MASS2, PHYS_PLANESTRAIN_WT, PHYS_ADVDIFF = range(10)
+PHYS_PLANESTRAIN, PHYS_SOLID, PHYS_HEAT, PHYS_PLANESTRESS, PHYS_PLANESTRAIN_SRI, PHYS_MASS, PHYS_PLANESTRAIN_BBAR, PHYS_MASS2, PHYS_PLANESTRAIN_WT, PHYS_ADVDIFF, PHYS_PLANE_D, PHYS_PLANE_D_BBAR, PHYS_PLANE_D_WT = range(13)
 # PF2_ADV_* routine mask of PHYS_ADVDIFF (carried in the quad2 field): Advection.h:19, :135, :47, :91, :161, :188
 ADV_ADVECTION, ADV_DIFFUSION, ADV_SUPG, ADV_SHOCK, ADV_MASS, ADV_MASS_SUPG = 1, 2, 4, 8, 16, 32
 ADV_NAME = {1: "Advection", 2: "Diffusion", 4: "AdvectionSUPG", 8: "AdvectionShockCapturing", 16: "Mass", 32: "MassSUPG"}
@@ -15,7 +15,8 @@ QUAD_NAME = {QUAD_G1TRI: "Gauss1Triangle", QUAD_G3TRI: "Gauss3Triangle", QUAD_G1
              QUAD_G9SQ: "Gauss9Square", QUAD_G1TET: "Gauss1Tetrahedron", QUAD_G8CUBE: "Gauss8Cubic", QUAD_G27CUBE: "Gauss27Cubic"}
 PHYS_NAME = {PHYS_PLANESTRAIN: "PlaneStrain", PHYS_SOLID: "Solid", PHYS_HEAT: "HeatTransfer", PHYS_PLANESTRESS: "PlaneStress",
              PHYS_PLANESTRAIN_SRI: "PlaneStrainSRI", PHYS_MASS: "ConsistentMass", PHYS_PLANESTRAIN_BBAR: "PlaneStrainBbar", PHYS_MASS2: "ConsistentMass2dof", PHYS_PLANESTRAIN_WT: "PlaneStrainWilsonTaylor",
-             PHYS_ADVDIFF: "AdvectionDiffusion"}
+             PHYS_ADVDIFF: "AdvectionDiffusion", PHYS_PLANE_D: "PlaneStiffness", PHYS_PLANE_D_BBAR: "PlaneStiffnessBbar",
+             PHYS_PLANE_D_WT: "PlaneStiffnessWilsonTaylor"}
 # rules of each reference domain (triangle, square, tetrahedron, cube)
 SHAPE_RULES = {SHAPE_T3: (QUAD_G1TRI, QUAD_G3TRI), SHAPE_T6: (QUAD_G1TRI, QUAD_G3TRI),
                SHAPE_Q4: (QUAD_G1SQ, QUAD_G4SQ, QUAD_G9SQ), SHAPE_Q8: (QUAD_G1SQ, QUAD_G4SQ, QUAD_G9SQ),
@@ -36,7 +37,7 @@ def fields(eq):
         shape = SHAPE_HEX8 if solid else SHAPE_Q4
     if quad == 0:
         quad = DEFAULT_RULE[shape]
-    if phys in (PHYS_PLANESTRAIN_SRI, PHYS_PLANESTRAIN_BBAR) and quad2 == 0:
+    if phys in (PHYS_PLANESTRAIN_SRI, PHYS_PLANESTRAIN_BBAR, PHYS_PLANE_D_BBAR) and quad2 == 0:
         quad2 = QUAD_G1TRI if shape in (SHAPE_T3, SHAPE_T6) else QUAD_G1SQ
     return phys, shape, quad, quad2
 

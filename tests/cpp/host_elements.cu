@@ -6,7 +6,7 @@
 #include "types.cuh"
 #include "element_advdiff.cuh"
 
-namespace pf2 { ElemSpec make_spec(const EqInfo& q); }
+namespace pf2 { ElemSpec make_spec(const EqInfo& q); ElemSpecD make_spec_d(const EqInfo& q, const double D[9]); }
 using namespace pf2;
 
 template <int KIND, int SHAPE>
@@ -43,6 +43,19 @@ static void rows_advdiff(const AdvSpec& sp, const double* xe, double* KK, double
         double accK[NPE], accM[NPE];
         advdiff_rows<SHAPE>(X, a, sp, accK, accM);
         for (int b = 0; b < NPE; b++) { KK[a * NPE + b] = accK[b]; MM[a * NPE + b] = accM[b]; }
+    }
+}
+
+// Ke as pf2_element_matrix_d returns it (general_rows: PlaneStiffness / Bbar / WilsonTaylor with a caller-supplied D)
+template <int SHAPE>
+static void rows_general(const ElemSpecD& sp, const double* xe, double t, double* Ke) {
+    constexpr int NPE = ShapeTraits<SHAPE>::NPE, M = NPE * 2;
+    double X[NPE][2];
+    for (int n = 0; n < NPE; n++) { X[n][0] = xe[n * 2]; X[n][1] = xe[n * 2 + 1]; }
+    for (int a = 0; a < NPE; a++) {
+        double acc[2][M];
+        general_rows<SHAPE>(X, a, sp, t, acc);
+        for (int i = 0; i < 2; i++) for (int j = 0; j < M; j++) Ke[(a * 2 + i) * M + j] = acc[i][j];
     }
 }
 
@@ -116,6 +129,18 @@ int pf2host_element_energy(int eq, const double* xe, const double* ue, double V,
 #define CALL(K, S) *w_out = energy_generic<K, S>(sp, xe, ue, t, fe)
     DISPATCH(q, CALL);
 #undef CALL
+    return PF2_OK;
+}
+
+int pf2host_element_matrix_d(int eq, const double* xe, const double* D, double t, double* Ke) {
+    EqInfo q;
+    PF2_TRY(decode_eq(eq, 0.0, &q));
+    PF2_CHECK(q.kind == KIND_ELAST2D_D, "not a PF2_PHYS_PLANE_D* selection");
+    const ElemSpecD sp = make_spec_d(q, D);
+    if (q.shape == PF2_SHAPE_T3) rows_general<SH_T3>(sp, xe, t, Ke);
+    else if (q.shape == PF2_SHAPE_T6) rows_general<SH_T6>(sp, xe, t, Ke);
+    else if (q.shape == PF2_SHAPE_Q4) rows_general<SH_Q4>(sp, xe, t, Ke);
+    else rows_general<SH_Q8>(sp, xe, t, Ke);
     return PF2_OK;
 }
 

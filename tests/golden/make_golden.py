@@ -443,6 +443,32 @@ def golden_advection():
     print("advection:", len(cases), "element cases")
 
 
+def golden_plane_d():
+    """PlaneStiffness / PlaneStiffnessBbar / PlaneStiffnessWilsonTaylor (Homogenization.h:141-280) of the live reference on distorted
+    elements with symmetric and non-symmetric constitutive matrices."""
+    from pansfem2_b200 import eqcode as ec, mesher
+    rng = np.random.default_rng(20210120)
+    d, cases = {}, []
+    for shape in (ec.SHAPE_T3, ec.SHAPE_T6, ec.SHAPE_Q4, ec.SHAPE_Q8):
+        nat = mesher.NATURAL_NODES[ec.SHAPE_NAME[shape]]
+        for quad in ec.SHAPE_RULES[shape]:
+            xe = nat * np.array([1.3, 0.9]) + 0.08 * rng.uniform(-1, 1, nat.shape)
+            A = rng.uniform(-1, 1, (3, 3))
+            Dsym = A @ A.T + 0.5 * np.eye(3)
+            for mode, phys in ((0, ec.PHYS_PLANE_D), (1, ec.PHYS_PLANE_D_BBAR), (2, ec.PHYS_PLANE_D_WT)):
+                if mode == 2 and (shape in (ec.SHAPE_T3, ec.SHAPE_T6) or quad == ec.QUAD_G1SQ):
+                    continue
+                for quad2 in (ec.SHAPE_RULES[shape] if mode == 1 else (0,)):
+                    for D in (Dsym, Dsym + 0.1 * rng.uniform(-1, 1, (3, 3))):
+                        k = len(cases)
+                        cases.append(ec.eq_code(phys, shape, quad, quad2))
+                        d[f"xe_{k}"], d[f"D_{k}"] = xe, D
+                        d[f"ke_{k}"] = reflib.plane_d_element(shape, quad, quad2, mode, xe, D, 0.7)
+    d["cases"] = np.array(cases, np.int64)
+    np.savez_compressed(f"{OUT}/live_plane_d.npz", **d)
+    print("plane_d:", len(cases), "cases")
+
+
 def golden_linalg():
     """Boundary types (Vector, Matrix, LILCSR, CSR host behaviour): tests/cpp/linalg_tables.cpp built against the reference's headers."""
     with tempfile.TemporaryDirectory() as tmp:
@@ -497,6 +523,9 @@ def _dense(indptr, indices, data):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "krylov":
         golden_krylov()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "plane_d":
+        golden_plane_d()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "linalg":
         golden_linalg()

@@ -110,6 +110,20 @@ def test_advection_diffusion_groups_split(host, golden_dir):
         assert rel(MM, orc.advdiff_element(int(shape), int(quad), 48, xe, ax, ay, k)) < 1e-13
 
 
+def test_general_constitutive_matrix_selections_match_the_live_reference(host, golden_dir):
+    """PlaneStiffness / PlaneStiffnessBbar / PlaneStiffnessWilsonTaylor (Homogenization.h:141-280): general_rows on the host."""
+    pd = np.load(os.path.join(golden_dir, "live_plane_d.npz"))
+    cases = [int(v) for v in pd["cases"]]
+    assert len(cases) == 80
+    for k, eq in enumerate(cases):
+        xe, D = np.ascontiguousarray(pd[f"xe_{k}"]), np.ascontiguousarray(pd[f"D_{k}"]).reshape(9)
+        m = 2 * xe.shape[0]
+        Ke = np.zeros((m, m))
+        assert host.pf2host_element_matrix_d(eq, _ptr(xe), _ptr(D), C.c_double(0.7), _ptr(Ke)) == 0
+        assert rel(Ke, pd[f"ke_{k}"]) < 1e-12, ec.describe(eq)
+        assert rel(orc.element_matrix_d(eq, xe, D, 0.7), pd[f"ke_{k}"]) == 0.0           # the restatement is bit-identical
+
+
 def test_invalid_codes_are_rejected_by_the_decoder(host):
     xe, Ke = np.zeros((8, 2)), np.zeros((8, 8))
     for eq in (ec.eq_code(ec.PHYS_ADVDIFF, ec.SHAPE_T3, ec.QUAD_G1TRI, 0),       # no routine selected
