@@ -29,7 +29,9 @@ DROPIN = [("sample/optimize/sample_optimize_density_oc.cpp", "dropin_density_oc"
           ("sample/planestrain/sample_planestrain.cpp", "dropin_planestrain_t3"),
           ("sample/optimize/sample_optimize_levelset.cpp", "dropin_levelset"),
           ("sample/advection/sample_advectiondiffusion_static.cpp", "dropin_advection_static"),
-          ("sample/advection/sample_advectiondiffusion_dynamic.cpp", "dropin_advection_dynamic")]
+          ("sample/advection/sample_advectiondiffusion_dynamic.cpp", "dropin_advection_dynamic"),
+          ("sample/homogenization/sample_homogenization.cpp", "dropin_homogenization"),
+          ("sample/optimize/sample_optimize_homogenization.cpp", "dropin_optimize_homogenization")]
 
 
 def _compile(src, exe):

@@ -1,7 +1,8 @@
 // tests/cpp/host_routines.cpp -- the host-side helpers of the element / controller headers that take no device path: Area, Volume,
 // CenterOfGravity, ElementVector (both overloads), WeakSpring, LagrangeInterpolation(+Derivative) (FEM/Equation/General.h),
 // HeatTransferSurfaceFlux (HeatTransfer.h), ShapeFunction3Line (ShapeFunction.h), SetDirichlet / SetPeriodic / Renumbering
-// (BoundaryCondition.h, Assembling.h).  Built against the reference's headers for the golden (tests/golden/make_golden.py routines ->
+// (BoundaryCondition.h, Assembling.h), and the host-side integrals of Homogenization.h (unit-strain load columns, homogenised constitutive
+// matrix, check integral).  Built against the reference's headers for the golden (tests/golden/make_golden.py routines ->
 // tests/golden/host_routines.txt) and against the header mirror in tests/test_host_routines.py.
 #include <cstdio>
 #include <cmath>
@@ -15,6 +16,7 @@
 #include "FEM/Controller/Assembling.h"
 #include "FEM/Equation/General.h"
 #include "FEM/Equation/HeatTransfer.h"
+#include "FEM/Equation/Homogenization.h"
 
 using namespace PANSFEM2;
 
@@ -79,6 +81,22 @@ int main() {
         mat("3Line dNdr", ShapeFunction3Line<double>::dNdr(Vector<double>({ r })));
     }
     std::printf("3Line points"); for (auto p : ShapeFunction3Line<double>::Points) std::printf(" %g", p(0)); std::printf(" d %d n %d\n", ShapeFunction3Line<double>::d, ShapeFunction3Line<double>::n);
+
+    //----------homogenisation integrals on a distorted Q4 and a T6----------
+    {
+        std::vector<Vector<double> > chi0(8, Vector<double>(2)), chi1(8, Vector<double>(2)), chi2(8, Vector<double>(2));
+        for (int i = 0; i < 8; i++) for (int d = 0; d < 2; d++) { chi0[i](d) = 0.01*std::sin(1.0 + 3*i + d); chi1[i](d) = -0.02*std::cos(0.5*i - d); chi2[i](d) = 0.005*(i - 3.5)*(d + 1); }
+        Matrix<double> Fes;
+        std::vector<std::vector<std::pair<int, int> > > nh;
+        HomogenizePlaneStrainBodyForce<double, ShapeFunction4Square, Gauss4Square>(Fes, nh, { 0, 1, 2, 3 }, { 0, 1 }, x2, 210000.0, 0.3, 0.8);
+        mat("homogenize body force Q4", Fes); n2e("homogenize map", nh);
+        mat("homogenize constitutive Q4", HomogenizePlaneStrainConstitutive<double, ShapeFunction4Square, Gauss4Square>(x2, q4, chi0, chi1, chi2, 210000.0, 0.3, 0.8));
+        mat("homogenize check Q4", HomogenizePlaneStrainCheck<double, ShapeFunction4Square, Gauss4Square>(x2, q4, chi0, chi1, chi2, 0.8));
+        std::vector<int> t6 = { 0, 1, 2, 4, 5, 6 };
+        HomogenizePlaneStrainBodyForce<double, ShapeFunction6Triangle, Gauss3Triangle>(Fes, nh, t6, { 0, 1 }, x2, 1.0, 0.25, 1.0);
+        mat("homogenize body force T6", Fes);
+        mat("homogenize constitutive T6", HomogenizePlaneStrainConstitutive<double, ShapeFunction6Triangle, Gauss3Triangle>(x2, t6, chi0, chi1, chi2, 1.0, 0.25, 1.0));
+    }
 
     //----------numbering: Dirichlet marks, periodic pairs----------
     std::vector<std::vector<int> > n2g(7, std::vector<int>(2, 0));

@@ -80,6 +80,19 @@ int main() {
         std::vector<Vector<double> > all = same.GenerateNodes();
         std::printf("homogenization cell %zu nodes, node 217: %.17g %.17g\n", all.size(), all[217](0), all[217](1));
     }
+    for (int variant = 0; variant < 2; variant++) {
+        std::printf("== SquareAnnulusMesh2 %d\n", variant);
+        SquareAnnulusMesh2<double> mesh = variant == 0 ? SquareAnnulusMesh2<double>(1.5, 1.0, 6, 5, 2, 3) : SquareAnnulusMesh2<double>(1.0, 1.0, 4, 4, 2, 2);
+        nodes("nodes", mesh.GenerateNodes()); lists("elements", mesh.GenerateElements()); lists("edges", mesh.GenerateEdges());
+        fixed("top", mesh.GenerateFixedlist({ 1 }, [](Vector<double> p) { return std::fabs(p(1) - 1.0) < 1.0e-9; }));
+        fixed("right of the hole", mesh.GenerateFixedlist({ 0, 1 }, [](Vector<double> p) { return p(0) > 0.8; }));
+    }
+    {
+        SquareAnnulusMesh2<double> cell(1.0, 1.0, 20, 20, 10, 10);                       // sample/homogenization/sample_homogenization.cpp:31
+        std::vector<Vector<double> > all = cell.GenerateNodes();
+        std::vector<std::vector<int> > el = cell.GenerateElements();
+        std::printf("homogenization cell 2: %zu nodes %zu elements, node 200: %.17g %.17g, element 150: %d %d %d %d\n", all.size(), el.size(), all[200](0), all[200](1), el[150][0], el[150][1], el[150][2], el[150][3]);
+    }
     {
         std::printf("== SquareCircleAnnulusMesh\n");
         SquareCircleAnnulusMesh<double> mesh(2.0, 1.0, 0.3, 1.5, 3, 2, 3);

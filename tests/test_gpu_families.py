@@ -46,6 +46,23 @@ def test_every_selection_element_matrix(ctx, fam):
         assert rel(ke, fam[f"ke_{eq}"]) < 1e-13, ec.describe(eq)
 
 
+def test_general_constitutive_matrix_selections(ctx, golden_dir):
+    """PlaneStiffness / PlaneStiffnessBbar / PlaneStiffnessWilsonTaylor (Homogenization.h:141-280) through pf2_element_matrix_d: 80 live-reference
+    cases (every 2-D shape / rule, every <ICV, ICD> pair, symmetric and non-symmetric D).  (Added after the last GPU slot of r01; the same
+    device rows are checked on the host by tests/test_host_elements.py.)"""
+    pd = np.load(os.path.join(golden_dir, "live_plane_d.npz"))
+    cases = [int(v) for v in pd["cases"]]
+    assert len(cases) == 80
+    for k, eq in enumerate(cases):
+        ke = ctx.element_matrix_d(eq, pd[f"xe_{k}"], pd[f"D_{k}"], 0.7)
+        assert rel(ke, pd[f"ke_{k}"]) < 1e-12, ec.describe(eq)
+    # the two per-element entry points refuse each other's selections
+    with pytest.raises(capi.Pf2Error):
+        ctx.element_matrix(cases[0], pd["xe_0"], 1.0)
+    with pytest.raises(capi.Pf2Error):
+        ctx.element_matrix_d(ec.eq_code(ec.PHYS_PLANESTRAIN, ec.SHAPE_Q4), np.zeros((4, 2)), np.eye(3))
+
+
 def test_invalid_selections_are_rejected(ctx):
     xe = np.zeros((4, 2))
     for eq in (ec.eq_code(ec.PHYS_PLANESTRAIN, ec.SHAPE_T3, ec.QUAD_G4SQ),        # square rule on a triangle

@@ -1,7 +1,8 @@
 """Host side of the header mirror: the helpers that have no device path - Area, Volume, CenterOfGravity, both ElementVector overloads,
 WeakSpring (with the reference's local-column quirk), LagrangeInterpolation and its derivative (FEM/Equation/General.h),
 HeatTransferSurfaceFlux (HeatTransfer.h), ShapeFunction3Line (ShapeFunction.h), SetDirichlet / SetPeriodic / RemoveBoundaryConditions
-(BoundaryCondition.h), Renumbering (Assembling.h).  tests/cpp/host_routines.cpp is compiled against the mirror here; its output must
+(BoundaryCondition.h), Renumbering (Assembling.h), and the host-side integrals of Homogenization.h (HomogenizePlaneStrainBodyForce,
+...Constitutive, ...Check).  tests/cpp/host_routines.cpp is compiled against the mirror here; its output must
 equal, digit for digit, what it prints when built against the reference's headers (tests/golden/host_routines.txt).  CPU only."""
 import os
 import subprocess
@@ -15,5 +16,5 @@ def test_host_routines_match_the_reference(tmp_path, golden_dir):
                     f"{ROOT}/tests/cpp/host_routines.cpp", "-o", str(exe)], check=True)
     got = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     want = open(os.path.join(golden_dir, "host_routines.txt")).read()
-    assert got.count("\n") == want.count("\n") == 50
+    assert got.count("\n") == want.count("\n") == 85
     assert got == want
