@@ -443,6 +443,25 @@ def golden_advection():
     print("advection:", len(cases), "element cases")
 
 
+def golden_homogenization():
+    """sample/homogenization: the periodic node pairs of its Periodic.csv, the committed result_microscopic.vtk (characteristic displacements
+    chi0..2 of the 20 x 20 cell with a 10 x 10 hole) and the two matrices the UNMODIFIED sample prints (check integral, homogenised C)."""
+    hom = f"{REF}/sample/homogenization"
+    pairs = np.array([[int(v) for v in r[:2]] for r in csv_rows(f"{hom}/Periodic.csv")], np.int32)
+    pts, cells = parse_vtk_mesh(f"{hom}/result_microscopic.vtk")
+    f = parse_vtk_fields(f"{hom}/result_microscopic.vtk")
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(f"{tmp}/sample/homogenization")
+        shutil.copyfile(f"{hom}/Periodic.csv", f"{tmp}/sample/homogenization/Periodic.csv")
+        exe = os.path.join(tmp, "homog")
+        subprocess.run(["g++", "-O2", "-fopenmp", "-w", f"{hom}/sample_homogenization.cpp", "-o", exe], check=True)
+        out = subprocess.run([exe], cwd=tmp, check=True, capture_output=True, text=True).stdout
+    vals = np.array([float(v) for v in out.split()]).reshape(2, 3, 3)
+    np.savez_compressed(f"{OUT}/homogenization.npz", pairs=pairs, coords=pts[:, :2], conn=cells, chi0=f["chi0"][:, :2], chi1=f["chi1"][:, :2],
+                        chi2=f["chi2"][:, :2], check=vals[0], CH=vals[1])
+    print("homogenization:", pairs.shape, pts.shape, cells.shape, vals[1])
+
+
 def golden_plane_d():
     """PlaneStiffness / PlaneStiffnessBbar / PlaneStiffnessWilsonTaylor (Homogenization.h:141-280) of the live reference on distorted
     elements with symmetric and non-symmetric constitutive matrices."""
@@ -523,6 +542,9 @@ def _dense(indptr, indices, data):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "krylov":
         golden_krylov()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "homogenization":
+        golden_homogenization()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "plane_d":
         golden_plane_d()

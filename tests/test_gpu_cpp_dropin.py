@@ -125,6 +125,29 @@ def test_unmodified_reference_planestrain_t3_driver_on_the_header_mirror(tmp_pat
     np.testing.assert_allclose(got["r"][:, :2], g["ps_r"], rtol=1e-5, atol=2e-3)
 
 
+def test_unmodified_reference_homogenization_driver_on_the_header_mirror(tmp_path, golden_dir):
+    """sample/homogenization/sample_homogenization.cpp, unmodified: SquareAnnulusMesh2, ImportPeriodicFromCSV + SetPeriodic, per-element
+    PlaneStrainStiffness on the device, HomogenizePlaneStrainBodyForce / WeakSpring / ...Constitutive on the host, three ScalingCG solves on
+    the device -> the committed result_microscopic.vtk and the matrices the reference run prints.  (Added after the last GPU slot of r01;
+    tests/test_homogenization_pinned.py is the CPU replay that set the tolerances.)"""
+    exe = need("dropin_homogenization")
+    g = np.load(os.path.join(golden_dir, "homogenization.npz"))
+    d = tmp_path / "sample" / "homogenization"
+    d.mkdir(parents=True)
+    with open(d / "Periodic.csv", "w") as f:
+        f.write("masterid,slaveid\n")
+        for m, s_ in g["pairs"]:
+            f.write(f"{int(m)},{int(s_)}\n")
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = parse_vtk(d / "result_microscopic.vtk")
+    for c in range(3):
+        assert np.abs(got[f"chi{c}"][:, :2] - g[f"chi{c}"]).max() < 2e-6
+    vals = np.array([float(v) for v in r.stdout.split() if v[0] in "-0123456789."])[-18:].reshape(2, 3, 3)
+    np.testing.assert_allclose(vals[0], g["check"], rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(vals[1], g["CH"], rtol=2e-5, atol=1e-6)
+
+
 @pytest.mark.parametrize("family,nx,ny", [("t3", 12, 8), ("q8sri", 10, 6)])
 def test_batched_driver_on_other_element_families(family, nx, ny):
     """sample_optimize_density_families: the batched C++ API with PlaneStressStiffnessTag<3Triangle, Gauss1Triangle> and
