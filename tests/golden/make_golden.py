@@ -11,6 +11,12 @@ Sources (all under /root/reference, nothing is copied verbatim - values are pars
     compiled UNMODIFIED and their stdout parsed (iterates per outer iteration).
   * live reference (oracle/_ref/libpf2ref.so): unit-element matrices, C1 iteration history, a 12x8 system's CSR,
     ILU0 factors and solver outputs - the fixtures the GPU box checks the C restatement against.
+
+Sub-commands (python tests/golden/make_golden.py <name>) regenerate one family of fixtures:
+    conlin | families | levelset | krylov     the widened rows 1-4 (live_conlin, live_families + t3_samples + shape_tables, levelset, live_krylov)
+    advection                                  Advection.h family: 180 element cases, both advection samples, sample/heattransfer/dynamic.vtk
+    plane_d | homogenization                   PlaneStiffness* with a caller-supplied D; sample/homogenization (pairs, result_microscopic.vtk, stdout)
+    io | meshers | routines | linalg           host-side mirror: small C++ programs under tests/cpp built against the REFERENCE's headers, stdout kept
 """
 from __future__ import annotations
 
