@@ -391,8 +391,8 @@ def main():
         bytes_per_elem = {2: 590.0, 1: 175.0, 3: 4300.0}.get(P.ndof, 0.0)     # Q4 plane strain / heat / hex8, map included
         out["assembly"] = {"elements_per_s": nelem / (asm_ms * 1e-3), "ms": asm_ms, "elements_local": int(nelem),
                            "algorithmic_bytes_per_element": bytes_per_elem, "algorithmic_GBps": bytes_per_elem * nelem / (asm_ms * 1e-3) / 1e9,
-                           "kernel": "assemble_gather_kernel (row gather, every entry written once, bitwise reproducible)" if P.ndof < 3
-                                     else "assemble_kernel<SOLID> (scatter, fp64 RED)"}
+                           "kernel": "assemble_gather_kernel (row gather, every entry written once, bitwise reproducible)"
+                                     if (P.ndof < 3 and not os.environ.get("PF2_ASSEMBLE_SCATTER")) else "assemble_kernel (scatter, fp64 RED)"}
     if mf is not None:
         out["matrix_free"] = mf
     if rank == 0:
