@@ -1,6 +1,7 @@
 //  pansfem2_b200/src/FEM/Controller/Assembling.h
 //  The per-element (legacy) assembly interface of src/FEM/Controller/Assembling.h on host containers:
-//      K+F+Fe :22, K+F (Dirichlet lift) :47, K only :99, F += Fe :119, lift only :132, nodal Neumann :152,
+//      K+F+Fe :22, K+F (Dirichlet lift) :47, K+F over several node groups (mixed interpolations) :71, K only :99, F += Fe :119,
+//      lift only :132, nodal Neumann :152,
 //      Disassembling :163, Renumbering :175
 //  Semantics kept: Dirichlet rows skipped, fixed columns lifted into F (F -= Ke*u_fixed), every Ke entry inserted
 //  (explicit zeros included).  These overloads only move numbers between host containers; the hot path is the batched
@@ -38,6 +39,21 @@ namespace PANSFEM2 {
     void Assembling(LILCSR<T>& _K, std::vector<T>& _F, std::vector<Vector<T> >& _u, Matrix<T>& _Ke, Vector<T>& _Fe, const std::vector<std::vector<int> >& _nodetoglobal, const std::vector<std::vector<std::pair<int, int> > >& _nodetoelement, const std::vector<int>& _element) {
         Assembling(_K, _F, _u, _Ke, _nodetoglobal, _nodetoelement, _element);
         Assembling(_F, _Fe, _nodetoglobal, _nodetoelement, _element);
+    }
+    //  one element matrix over several node groups (e.g. velocity nodes + pressure nodes): rows and columns run over every dof of every group
+    template<class T>
+    void Assembling(LILCSR<T>& _K, std::vector<T>& _F, std::vector<Vector<T> >& _u, Matrix<T>& _Ke, const std::vector<std::vector<int> >& _nodetoglobal, const std::vector<std::vector<std::vector<std::pair<int, int> > > >& _nodetoelements, const std::vector<std::vector<int> >& _elements) {
+        struct Dof { int global, local, node, dof; };
+        std::vector<Dof> dofs;
+        for (size_t g = 0; g < _elements.size(); g++) for (size_t i = 0; i < _elements[g].size(); i++) for (const auto& d : _nodetoelements[g][i])
+            dofs.push_back(Dof{ _nodetoglobal[_elements[g][i]][d.first], d.second, _elements[g][i], d.first });
+        for (const Dof& r : dofs) {
+            if (r.global == -1) continue;
+            for (const Dof& c : dofs) {
+                if (c.global != -1) _K.set(r.global, c.global, _K.get(r.global, c.global) + _Ke(r.local, c.local));
+                else _F[r.global] -= _Ke(r.local, c.local)*_u[c.node](c.dof);
+            }
+        }
     }
     template<class T>
     void Assembling(LILCSR<T>& _K, Matrix<T>& _Ke, const std::vector<std::vector<int> >& _nodetoglobal, const std::vector<std::vector<std::pair<int, int> > >& _nodetoelement, const std::vector<int>& _element) {

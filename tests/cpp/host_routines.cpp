@@ -10,6 +10,7 @@
 #include "LinearAlgebra/Models/Vector.h"
 #include "LinearAlgebra/Models/Matrix.h"
 #include "LinearAlgebra/Models/LILCSR.h"
+#include "LinearAlgebra/Models/CSR.h"
 #include "FEM/Controller/ShapeFunction.h"
 #include "FEM/Controller/GaussIntegration.h"
 #include "FEM/Controller/BoundaryCondition.h"
@@ -96,6 +97,47 @@ int main() {
         HomogenizePlaneStrainBodyForce<double, ShapeFunction6Triangle, Gauss3Triangle>(Fes, nh, t6, { 0, 1 }, x2, 1.0, 0.25, 1.0);
         mat("homogenize body force T6", Fes);
         mat("homogenize constitutive T6", HomogenizePlaneStrainConstitutive<double, ShapeFunction6Triangle, Gauss3Triangle>(x2, t6, chi0, chi1, chi2, 1.0, 0.25, 1.0));
+    }
+
+    //----------every Assembling overload, Disassembling: a 2-element patch with a fixed node and prescribed values----------
+    {
+        std::vector<std::vector<int> > n2g = { { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } };
+        std::vector<Vector<double> > uu(5, Vector<double>(2));
+        std::vector<std::pair<std::pair<int, int>, double> > fix = { { { 1, 0 }, 0.25 }, { { 1, 1 }, -0.5 }, { { 4, 1 }, 2.0 } };
+        SetDirichlet(uu, n2g, fix);
+        const int KD = Renumbering(n2g);
+        LILCSR<double> K(KD, KD);
+        std::vector<double> F(KD, 0.0);
+        const std::vector<std::vector<int> > patch = { { 0, 1, 2 }, { 2, 1, 4, 3 } };
+        for (const auto& el : patch) {
+            const int m = 2*(int)el.size();
+            Matrix<double> Ke(m, m);
+            Vector<double> Fe(m);
+            std::vector<std::vector<std::pair<int, int> > > map(el.size(), std::vector<std::pair<int, int> >(2));
+            for (int i = 0; i < (int)el.size(); i++) { map[i][0] = std::make_pair(0, 2*i); map[i][1] = std::make_pair(1, 2*i + 1); }
+            for (int i = 0; i < m; i++) { Fe(i) = 0.1*(i + 1) - 0.3; for (int j = 0; j < m; j++) Ke(i, j) = 1.0/(1.0 + i + 2.0*j) + (i == j ? 3.0 : 0.0) + 0.01*el[0]; }
+            Assembling(K, F, uu, Ke, Fe, n2g, map, el);          // K + F + Fe
+            Assembling(K, F, uu, Ke, n2g, map, el);              // K + Dirichlet lift
+            Assembling(K, Ke, n2g, map, el);                     // K only
+            Assembling(F, Fe, n2g, map, el);                     // F += Fe
+            Assembling(F, uu, Ke, n2g, map, el);                 // lift only
+        }
+        {   // one matrix over two node groups: 2-dof nodes {0, 2} and a 1-dof group {3} (dof 1 of node 3)
+            Matrix<double> Ke(5, 5);
+            for (int i = 0; i < 5; i++) for (int j = 0; j < 5; j++) Ke(i, j) = 0.5*i - 0.25*j + (i == j ? 2.0 : 0.0);
+            std::vector<std::vector<std::vector<std::pair<int, int> > > > maps = { { { { 0, 0 }, { 1, 1 } }, { { 0, 2 }, { 1, 3 } } }, { { { 1, 4 } } } };
+            Assembling(K, F, uu, Ke, n2g, maps, { { 0, 1 }, { 3 } });
+        }
+        Assembling(F, std::vector<std::pair<std::pair<int, int>, double> >({ { { 0, 1 }, -100.0 }, { { 1, 0 }, 7.0 }, { { 3, 0 }, 1.5 } }), n2g);
+        numbering("patch numbering", n2g);
+        std::printf("KDEGREE %d\n", KD);
+        CSR<double> A(K);
+        for (int i = 0; i < KD; i++) { std::printf("row %d:", i); for (int j = 0; j < KD; j++) std::printf(" %.17g", A.get(i, j)); std::printf("\n"); }
+        stdvec("patch F", F);
+        std::vector<double> sol(KD);
+        for (int i = 0; i < KD; i++) sol[i] = 10.0 + i;
+        Disassembling(uu, sol, n2g);
+        for (auto& v : uu) vec("u", v);
     }
 
     //----------numbering: Dirichlet marks, periodic pairs----------
