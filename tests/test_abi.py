@@ -29,6 +29,14 @@ def test_header_symbols_exported(libpath):
     assert not missing, missing
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/pansfem2_b200.h must compile as C99 on its own (what a cgo / JNI / ctypes-style binding would see)."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "pansfem2_b200.h"\nint main(void) { return PF2_EQ_CODE(PF2_PHYS_ADVDIFF, PF2_SHAPE_T3, PF2_QUAD_G1TRI, PF2_ADV_SUPG) == 0; }\n')
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", f"-I{ROOT}/include", str(src)], check=True)
+
+
 def test_no_cpu_fallback(libpath):
     import torch
     if torch.cuda.is_available():
