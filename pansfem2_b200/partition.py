@@ -83,6 +83,13 @@ def _finish(local, n2g, rank, nranks, e0, e1, le0, le1, on0, on1, plane_e, plane
         sendL, recvL = rows_of_planes(e0, e0 + 1), rows_of_planes(e0 - 1, e0)
     if rank < nranks - 1:
         sendR, recvR = rows_of_planes(e1 - 1, e1), rows_of_planes(e1, e1 + 1)
+    # one count per side serves both directions of the exchange, so the plane sent and the plane received must carry the same number
+    # of rows.  That only fails when an exchanged plane holds Dirichlet dofs - a rank whose single element plane touches the clamped
+    # face - which would leave the neighbours waiting for different amounts of data: refuse it here.
+    for side, (snd, rcv) in (("left", (sendL, recvL)), ("right", (sendR, recvR))):
+        if snd[1] - snd[0] != rcv[1] - rcv[0]:
+            raise ValueError(f"rank {rank} of {nranks}: the {side} halo would send {snd[1] - snd[0]} rows and receive {rcv[1] - rcv[0]} "
+                             "(a boundary-condition plane is being exchanged): use fewer ranks, at least two element planes per rank")
     row_halo = (sendL[0], recvL[0], sendL[1] - sendL[0], sendR[0], recvR[0], sendR[1] - sendR[0])
     el = lambda p: (p - le0) * plane_e
     elem_halo = (el(e0), el(e0 - 1) if rank > 0 else 0, plane_e if rank > 0 else 0,

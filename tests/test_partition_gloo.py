@@ -1,4 +1,4 @@
-"""Multi-process (gloo, world_size 2 and 3) tests of the row-block partition logic on CPU: local meshes with ghost planes,
+"""Multi-process (gloo, world_size 2, 3 and 4: interior ranks with two neighbours) tests of the row-block partition logic on CPU: local meshes with ghost planes,
 owned row ranges, contiguous halo ranges, loads applied once.  Each rank assembles ITS slab with the oracle, the ranks run
 the partitioned Jacobi-PCG (numpy emulation of csrc/dist.cu: halo exchange of p + allreduces) over torch.distributed/gloo,
 and the gathered solution must equal the single-domain oracle solve."""
@@ -79,7 +79,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("kind,world", [("2d", 2), ("3d", 2), ("heat", 3)])
+@pytest.mark.parametrize("kind,world", [("2d", 2), ("3d", 2), ("heat", 3), ("2d", 4)])
 def test_partitioned_pcg_matches_single_domain(tmp_path, kind, world):
     mp.spawn(_worker, args=(world, _free_port(), kind, str(tmp_path)), nprocs=world, join=True)
     P = _make(kind)
@@ -101,9 +101,17 @@ def test_partitioned_pcg_matches_single_domain(tmp_path, kind, world):
     assert np.abs(x - xref).max() < 1e-9 * np.abs(xref).max()
 
 
-def test_slab_ranges_cover_elements_and_rows():
+def test_too_many_ranks_is_refused():
+    """9 element planes on 8 ranks leave rank 0 with the clamped plane only: its neighbour would send a full plane and receive none."""
     P = problems.cantilever3d(9, 4, 2)
-    for world in (1, 2, 4):
+    with pytest.raises(ValueError, match="fewer ranks"):
+        for r in range(8):
+            partition.slab(P, r, 8)
+
+
+def test_slab_ranges_cover_elements_and_rows():
+    P = problems.cantilever3d(18, 4, 2)
+    for world in (1, 2, 4, 8):
         rows, elems = [], []
         for r in range(world):
             S = partition.slab(P, r, world)
