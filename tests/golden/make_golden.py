@@ -463,8 +463,19 @@ def golden_homogenization():
         subprocess.run(["g++", "-O2", "-fopenmp", "-w", f"{hom}/sample_homogenization.cpp", "-o", exe], check=True)
         out = subprocess.run([exe], cwd=tmp, check=True, capture_output=True, text=True).stdout
     vals = np.array([float(v) for v in out.split()]).reshape(2, 3, 3)
+    # sample/optimize/sample_optimize_homogenization.cpp: its Periodic.csv and the objective / weight history the UNMODIFIED driver prints
+    # (157 iterations, about 6 minutes on 8 cores; the committed Homogenization_*.vtk are not reproduced by the current driver)
+    opt = f"{REF}/sample/optimize"
+    pairs_opt = np.array([[int(v) for v in r[:2]] for r in csv_rows(f"{opt}/Periodic.csv")], np.int32)
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(f"{tmp}/sample/optimize")
+        shutil.copyfile(f"{opt}/Periodic.csv", f"{tmp}/sample/optimize/Periodic.csv")
+        exe = os.path.join(tmp, "homopt")
+        subprocess.run(["g++", "-O3", "-fopenmp", "-w", f"{opt}/sample_optimize_homogenization.cpp", "-o", exe], check=True)
+        log = subprocess.run([exe], cwd=tmp, check=True, capture_output=True, text=True).stdout
+    hist = np.array([[float(a), float(b)] for a, b in re.findall(r"Objective:\s*([-0-9.e+]+)\s*Weight:\s*([-0-9.e+]+)", log)])
     np.savez_compressed(f"{OUT}/homogenization.npz", pairs=pairs, coords=pts[:, :2], conn=cells, chi0=f["chi0"][:, :2], chi1=f["chi1"][:, :2],
-                        chi2=f["chi2"][:, :2], check=vals[0], CH=vals[1])
+                        chi2=f["chi2"][:, :2], check=vals[0], CH=vals[1], pairs_opt=pairs_opt, opt_history=hist)
     print("homogenization:", pairs.shape, pts.shape, cells.shape, vals[1])
 
 
