@@ -7,8 +7,12 @@
  * identical inputs it agrees with the reference to the last bit or two (pinned in tests/test_oracle_pinned.py
  * against the reference's golden VTKs, its MMA known-answer tests and the live reference).
  *
- * Pinning status: PINNED (golden vectors tests/golden/*.npz generated from the reference's committed outputs
- * sample/optimize/Density_{OC,MMA}.vtk, sample/solid/result_linear.vtk; KATs from src/Optimize/Solver/test_MMA*.cpp).
+ * Pinning status: PINNED (golden vectors tests/golden/ *.npz generated from the reference's committed outputs
+ * sample/optimize/Density_{OC,MMA,CONLIN}.vtk, sample/solid/result_linear.vtk, sample/heattransfer/{static,dynamic}.vtk,
+ * sample/planestrain/result.vtk, sample/advection/AdvectionSUPG{,dynamic0,dynamic99}.vtk, sample/homogenization/result_microscopic.vtk;
+ * KATs from src/Optimize/Solver/test_MMA*.cpp; live-reference dumps and the stdout of the unmodified level-set and homogenisation
+ * drivers).  Per row: tests/test_oracle_pinned.py, test_families_pinned.py, test_levelset_pinned.py, test_krylov_pinned.py,
+ * test_advection_pinned.py, test_homogenization_pinned.py, test_homogenization_opt_pinned.py.
  *
  * Data model: flat arrays.  coords[nnode*dim], conn[nelem*npe], nodetoglobal[nnode*ndof] (-1 = Dirichlet).
  */
