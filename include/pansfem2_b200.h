@@ -187,10 +187,22 @@ int pf2_solve(pf2_csr* A, int solver, const double* b_dev, double* x_dev, int it
               double* relres_out);
 int pf2_solve_host(pf2_csr* A, int solver, const double* b_host, double* x_host, int itrmax, double eps,
                    int* iters_out, double* relres_out);
-/* sampled per-kernel device times of the Krylov loop (CUDA events around one iteration per chunk):
+/* The same solve from the initial guess held in x_dev (overload sanctioned by SURVEY.md section 7: the reference always starts
+ * from x0 = 0, CG.h:423).  Recurrences and stopping rule ||r|| < eps*||b|| are unchanged; r0 = b - A*x0 costs one extra product.
+ * On a partitioned matrix the ghost entries of x0 must be valid.  ILU0CG and the BiCGSTAB family ignore the guess. */
+int pf2_solve_x0(pf2_csr* A, int solver, const double* b_dev, double* x_dev, int itrmax, double eps, int* iters_out,
+                 double* relres_out);
+/* How CG / ScalingCG iterate (CG.h:430-449): 1 = one persistent cooperative kernel per solve (grid barriers carry the dot
+ * products; default where the SELL-32 mirror applies), 0 = three kernels per iteration, -1 = environment (PF2_PCG, default 1). */
+int pf2_csr_set_pcg_mode(pf2_csr* A, int mode);
+/* per-kernel device times of the Krylov loop.  Three-kernel loop: CUDA events around one iteration per chunk; persistent kernel:
+ * its in-kernel %globaltimer stamps per phase (barriers included), samples = iterations.
  * out = {spmv+dot ms, update ms, p-update ms, samples, total iterations, SpMV variant, rows, nnz} */
 int pf2_csr_solver_stats(pf2_csr* A, double out[8]);
 int pf2_csr_solver_stats_reset(pf2_csr* A);
+/* persistent PCG kernel since the last reset: out = {CUDA-event ms of the kernel launches (whole solves), iterations, solves,
+ * CTAs of the last launch, product / update / p-update phase ms per iteration, stored SELL entries} */
+int pf2_csr_pcg_stats(pf2_csr* A, double out[8]);
 /* ILU(0) factors of A (unit-L strictly lower + U with diagonal in A's pattern), cached on A until values change */
 int pf2_ilu0_factor(pf2_csr* A);
 int pf2_ilu0_download(pf2_csr* A, double* data_host);
@@ -260,6 +272,13 @@ int pf2_simp_create(pf2_ctx* ctx, pf2_mesh* mesh, pf2_dofmap* map, pf2_csr* A, p
 int pf2_simp_destroy(pf2_simp* S);
 int pf2_simp_set_design(pf2_simp* S, const double* s_host);
 int pf2_simp_set_solver(pf2_simp* S, int solver);
+/* Restart the loop at iteration 0 (driver :78-83) with the design s_host: Heaviside beta, the optimiser's previousvalue and
+ * iteration count (MMA / CONLIN rebuild their asymptotes for k < 2, MMA.h:133-141) and the warm-start state are reset. */
+int pf2_simp_reset(pf2_simp* S, const double* s_host);
+/* Opt-in: the PCG of design iteration k starts from the displacements of iteration k-1 instead of 0 (pf2_solve_x0; the
+ * reference's drivers always start from 0, CG.h:423).  Same stopping rule; compliance and densities agree within the solver
+ * tolerance (tests/test_gpu_parity.py). */
+int pf2_simp_set_warm_start(pf2_simp* S, int on);
 /* One design iteration; the design never leaves the device.  stats[8] = {f, g, converged, cg_iters, cg_relres,
  * optimizer_steps, beta, k}.  When `converged` is set the design was NOT updated (the driver breaks, :192-195). */
 int pf2_simp_iterate(pf2_simp* S, int check_convergence, double stats[8]);
@@ -310,6 +329,8 @@ int pf2_csr_set_partition(pf2_csr* A, pf2_dist* d, int own_lo, int own_hi, const
  * {row halo descriptor[6], local rows, 0}). */
 int pf2_csr_p2p_export(pf2_csr* A, char handles_out[128]);
 int pf2_csr_p2p_import(pf2_csr* A, const char* all_handles, const int* all_meta);
+/* Unmap the neighbours' Krylov slabs again.  All ranks call it and synchronise before any of them destroys its matrix. */
+int pf2_csr_p2p_release(pf2_csr* A);
 /* Make a design loop built on a slab's local mesh one part of a partitioned loop: elements [own_elem_lo, own_elem_hi) are
  * owned, elem_halo = contiguous element ranges exchanged with the neighbours, n_global_elems = elements of the whole mesh
  * (the volume constraint is global). */

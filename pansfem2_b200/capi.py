@@ -267,11 +267,23 @@ class Csr:
                  allow=() if raise_noconv else (E_NOCONV,))
         return x, it.value, rr.value
 
-    def solve(self, solver, b_dev, x_dev, itrmax=100000, eps=1e-10):
+    def solve(self, solver, b_dev, x_dev, itrmax=100000, eps=1e-10, warm=False):
+        """warm=True: x_dev holds the initial guess (pf2_solve_x0); otherwise the reference's x0 = 0."""
         it, rr = C.c_int(0), C.c_double(0)
-        _ck(lib().pf2_solve(self.h, solver, b_dev.ptr if isinstance(b_dev, DeviceArray) else b_dev, x_dev.ptr, int(itrmax), C.c_double(eps),
-                            C.byref(it), C.byref(rr)))
+        fn = lib().pf2_solve_x0 if warm else lib().pf2_solve
+        _ck(fn(self.h, solver, b_dev.ptr if isinstance(b_dev, DeviceArray) else b_dev, x_dev.ptr, int(itrmax), C.c_double(eps),
+               C.byref(it), C.byref(rr)))
         return it.value, rr.value
+
+    def set_pcg_mode(self, mode):
+        """1: persistent cooperative PCG kernel, 0: three kernels per iteration, -1: environment default (PF2_PCG)."""
+        _ck(lib().pf2_csr_set_pcg_mode(self.h, int(mode)))
+
+    def pcg_stats(self):
+        st = (C.c_double * 8)()
+        _ck(lib().pf2_csr_pcg_stats(self.h, st))
+        return dict(kernel_ms=st[0], iters=int(st[1]), solves=int(st[2]), grid=int(st[3]), product_ms=st[4], update_ms=st[5],
+                    pupdate_ms=st[6], sell_entries=int(st[7]))
 
     def solver_stats(self, reset=False):
         st = (C.c_double * 8)()
@@ -438,6 +450,14 @@ class Simp:
         s = _f64(s)
         _ck(lib().pf2_simp_set_design(self.h, _p(s, np.float64)))
 
+    def reset(self, s=None):
+        """Back to design iteration 0 with design s (default: the uniform initial design)."""
+        s = _f64(np.full(self.P.nelem, self.P.s0) if s is None else s)
+        _ck(lib().pf2_simp_reset(self.h, _p(s, np.float64)))
+
+    def set_warm_start(self, on=True):
+        _ck(lib().pf2_simp_set_warm_start(self.h, int(bool(on))))
+
     @staticmethod
     def _stats(st):
         return dict(f=st[0], g=st[1], converged=bool(st[2]), cg_iters=int(st[3]), cg_relres=st[4], opt_steps=int(st[5]), beta=st[6], k=int(st[7]))
@@ -554,6 +574,12 @@ class Dist:
         allh.raw = b"".join(g[0] for g in gathered)
         allm = (C.c_int * (8 * self.world))(*[v for g in gathered for v in g[1]])
         _ck(lib().pf2_csr_p2p_import(A.h, allh, allm))
+        tdist.barrier()
+
+    def release_p2p(self, A):
+        """Collective: unmap the neighbours' slabs of matrix A on every rank, then synchronise, so that A can be destroyed."""
+        import torch.distributed as tdist
+        _ck(lib().pf2_csr_p2p_release(A.h))
         tdist.barrier()
 
     def set_simp_partition(self, simp, slab, n_global_elems):

@@ -335,6 +335,8 @@ static int launch_sell(pf2_csr* A, const double* x, double* y, const CgState* st
     return PF2_OK;
 }
 
+int plan_spmv_pub(pf2_csr* A) { plan_spmv(A); return PF2_OK; }
+
 // matrix-free operator: Ke0 travels through constant memory, re-uploaded only when another matrix (or new parameters) used it last
 static const pf2_csr* g_mf_owner = nullptr;
 static unsigned long long g_mf_owner_version = 0;
@@ -551,6 +553,8 @@ int pf2_csr_destroy(pf2_csr* A) {
                      A->ilu, A->level_rows, A->level_rows_u, A->n2e_ptr, A->n2e, A->node_row0 };
     for (void* p : ptrs) if (p) cudaFree(p);
     if (A->h_st) cudaFreeHost(A->h_st);
+    if (A->pcg_sync) cudaFree(A->pcg_sync);
+    if (A->h_pcg_sync) cudaFreeHost(A->h_pcg_sync);
     if (A->mf_E) cudaFree(A->mf_E);
     if (A->mf_slab) cudaFree(A->mf_slab);
     if (g_mf_owner == A) g_mf_owner = nullptr;

@@ -60,7 +60,8 @@ struct pf2_dist {
     void* arena = nullptr;
     pf2::P2P view;
     unsigned long long* epoch = nullptr;      // device: [0] allreduce epoch, [1] halo epoch
-    std::vector<void*> opened;
+    std::vector<void*> opened;                // peers' arenas, mapped once per partition object
+    void* peer_arena[pf2::kMaxRanksT] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 };
 
 namespace pf2 {
@@ -450,11 +451,13 @@ int pf2_csr_p2p_import(pf2_csr* A, const char* all_handles, const int* all_halo)
     for (int r = 0; r < world; r++) {
         void* base = nullptr;
         if (r == me) base = d->arena;
+        else if (d->peer_arena[r]) base = d->peer_arena[r];       // a second matrix of the same partition: the arenas are already mapped
         else {
             cudaIpcMemHandle_t h;
             memcpy(&h, all_handles + (size_t)r * 128, 64);
             PF2_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
             d->opened.push_back(base);
+            d->peer_arena[r] = base;
         }
         v.slots[r] = (double*)base;
         v.flags[r] = (unsigned long long*)((char*)base + sizeof(double) * 2 * world * 4);
@@ -468,7 +471,7 @@ int pf2_csr_p2p_import(pf2_csr* A, const char* all_handles, const int* all_halo)
         memcpy(&h, all_handles + (size_t)nb * 128 + 64, 64);
         void* base = nullptr;
         PF2_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
-        d->opened.push_back(base);
+        A->p2p_opened[side] = base;
         // the neighbour's p vector starts one padded vector into its slab; its row count is implied by its own padding,
         // so the neighbour publishes the p offset through all_halo? -> no: p offset = np_nb doubles; np_nb is sent as halo[6]
         const int* hn = all_halo + (size_t)nb * 8;
@@ -484,6 +487,19 @@ int pf2_csr_p2p_import(pf2_csr* A, const char* all_handles, const int* all_halo)
     A->p2p_ready = true;
     d->p2p = true;
     d->view = v;
+    return PF2_OK;
+}
+
+// Unmap the neighbours' Krylov slabs of this matrix.  Every rank calls it (and the ranks synchronise) BEFORE any of them destroys
+// its matrix: freeing memory a peer still has mapped is undefined.
+int pf2_csr_p2p_release(pf2_csr* A) {
+    if (!A) return PF2_OK;
+    PF2_CUDA(cudaSetDevice(A->ctx->device));
+    PF2_CUDA(cudaStreamSynchronize(A->ctx->stream));
+    for (int side = 0; side < 2; side++) {
+        if (A->p2p_opened[side]) { PF2_CUDA(cudaIpcCloseMemHandle(A->p2p_opened[side])); A->p2p_opened[side] = nullptr; }
+    }
+    A->p2p_ready = false;
     return PF2_OK;
 }
 

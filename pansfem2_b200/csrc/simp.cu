@@ -19,7 +19,7 @@ int assemble_device(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq, const d
                     const double params[5], int nload, const int* load_node_dev, const int* load_dof_dev, const double* load_val_dev);
 int compliance_sens_device(pf2_mesh* mesh, int eq, const double* u_nodal, const double* rho, const double params[6], double* f_dev,
                            double* dfdrho, double* r_nodal);
-int solve(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out);
+int solve_x0(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int warm, int* iters_out, double* relres_out);
 int filter_apply(pf2_filter* f, const double* s, double* rho, double* sum_out, OcState* oc);
 int filter_sens(pf2_filter* f, const double* s, const double* g1, double* out1, const double* g2, double c2, double* out2);
 int oc_update(pf2_oc* oc, pf2_filter* filter, double weightlimit, double scale1, double* x, double f, const double* dfdx,
@@ -45,6 +45,9 @@ struct pf2_simp {
     int beta_period = 0, itrmax = 100000;
     double cgeps = 1.0e-10;
     int k = 0;
+    double beta0 = 0.0;          // Heaviside beta of pf2_simp_create (restored by pf2_simp_reset)
+    int warm_start = 0;          // opt-in: PCG starts from the previous design iteration's displacements (pf2_simp_set_warm_start)
+    bool have_solution = false;  // xsol holds a converged solution of this run
     int nload = 0;
     int *ld_node = nullptr, *ld_dof = nullptr;
     double* ld_val = nullptr;
@@ -75,8 +78,9 @@ static int simp_iterate(pf2_simp* S, int check_convergence, double stats[8]) {
     PF2_CUDA(cudaEventRecord(S->ev[2], s));
     int iters = 0;
     double relres = 0.0;
-    int rc = solve(S->A, S->solver, S->A->F, S->xsol, S->itrmax, S->cgeps, &iters, &relres);
+    int rc = solve_x0(S->A, S->solver, S->A->F, S->xsol, S->itrmax, S->cgeps, (S->warm_start && S->have_solution) ? 1 : 0, &iters, &relres);
     if (rc != PF2_OK && rc != PF2_E_NOCONV) return rc;      // non-convergence: the reference prints and carries on
+    S->have_solution = true;
     if (d) PF2_TRY(dist_halo(d, S->xsol, S->A->halo));                         // displacements of the ghost node planes
     PF2_TRY(pf2_disassemble(S->map, S->xsol, S->u));
     PF2_CUDA(cudaEventRecord(S->ev[3], s));
@@ -130,6 +134,7 @@ int pf2_simp_create(pf2_ctx* ctx, pf2_mesh* mesh, pf2_dofmap* map, pf2_csr* A, p
     S->E0 = params[0]; S->E1 = params[1]; S->V = params[2]; S->p = params[3]; S->weightlimit = params[4];
     S->scale0 = params[5]; S->scale1 = params[6]; S->thick = params[7]; S->beta = params[8];
     S->beta_period = (int)params[9]; S->itrmax = (int)params[10]; S->cgeps = params[11];
+    S->beta0 = S->beta;
     const size_t n = (size_t)S->n, nd = (size_t)mesh->nnode * map->ndof;
     PF2_TRY(dev_alloc(&S->s, n)); PF2_TRY(dev_alloc(&S->rho, n)); PF2_TRY(dev_alloc(&S->dfdrho, n));
     PF2_TRY(dev_alloc(&S->dfds, n)); PF2_TRY(dev_alloc(&S->dgds, n));
@@ -174,6 +179,22 @@ int pf2_simp_destroy(pf2_simp* S) {
 int pf2_simp_set_design(pf2_simp* S, const double* s_host) {
     PF2_CUDA(cudaMemcpyAsync(S->s, s_host, sizeof(double) * (size_t)S->n, cudaMemcpyHostToDevice, S->ctx->stream));
     PF2_CUDA(cudaStreamSynchronize(S->ctx->stream));
+    return PF2_OK;
+}
+// Back to iteration 0 of the driver (sample_optimize_density_oc.cpp:78-83): design, Heaviside beta, the optimiser's history
+// (previousvalue, iteration count: MMA re-initialises its asymptotes for k < 2, MMA.h:133-141) and the warm-start state.
+int pf2_simp_reset(pf2_simp* S, const double* s_host) {
+    PF2_CHECK(S && s_host, "null argument");
+    PF2_TRY(pf2_simp_set_design(S, s_host));
+    S->k = 0; S->beta = S->beta0; S->have_solution = false;
+    if (S->oc) { S->oc->k = 0; S->oc->previousvalue = 0.0; }
+    if (S->mma) { S->mma->k = 0; S->mma->previousvalue = 0.0; }
+    return PF2_OK;
+}
+int pf2_simp_set_warm_start(pf2_simp* S, int on) {
+    PF2_CHECK(S, "null argument");
+    S->warm_start = on ? 1 : 0;
+    if (!on) S->have_solution = false;
     return PF2_OK;
 }
 int pf2_simp_set_partition(pf2_simp* S, pf2_dist* d, int own_elem_lo, int own_elem_hi, const int elem_halo[6], long long n_global_elems) {

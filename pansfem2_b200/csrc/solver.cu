@@ -23,25 +23,29 @@ __global__ void __launch_bounds__(kThreads)
 cg_init_kernel(int n, const double* __restrict__ b, const long long* __restrict__ indptr, const int* __restrict__ diagpos,
                const double* __restrict__ data, double* __restrict__ dvec, double* __restrict__ x, double* __restrict__ r,
                double* __restrict__ z, double* __restrict__ p, CgState* st, int maxit, double eps, double* partials,
-               unsigned int* ticket) {
-    double v[2] = { 0.0, 0.0 };
+               unsigned int* ticket, const double* __restrict__ y0) {
+    // y0 = A x0 of a warm start (x keeps x0, r = b - y0); nullptr: the reference's x0 = 0
+    double v[3] = { 0.0, 0.0, 0.0 };
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double bi = b[i];
-        x[i] = 0.0;
-        r[i] = bi;
-        double zi = bi;
+        double ri = bi;
+        if (y0) ri = bi - y0[i]; else x[i] = 0.0;
+        r[i] = ri;
+        double zi = ri;
         if (MODE == 1) {
             const int dp = diagpos[i];
             const double d = dp >= 0 ? data[indptr[i] + dp] : 0.0;      // GetDiagonal (CG.h:398-404), gathered once per solve
             dvec[i] = d;
-            zi = bi / d;
+            zi = ri / d;
         }
-        if (MODE != 2) { z[i] = zi; p[i] = zi; v[1] += zi * bi; }
+        if (MODE != 2) { z[i] = zi; p[i] = zi; v[1] += zi * ri; }
         v[0] += bi * bi;
+        v[2] += ri * ri;
     }
-    if (grid_sum_last<2>(v, partials, ticket) && threadIdx.x == 0) {
-        st->bb = v[0]; st->rr = v[0]; st->rho = v[1]; st->pAp = 0.0; st->beta = 0.0; st->zr_new = 0.0;
-        st->iter = 0; st->done = 0; st->maxit = maxit; st->eps = eps;
+    if (grid_sum_last<3>(v, partials, ticket) && threadIdx.x == 0) {
+        st->bb = v[0]; st->rr = v[2]; st->rho = v[1]; st->pAp = 0.0; st->beta = 0.0; st->zr_new = 0.0;
+        st->iter = 0; st->maxit = maxit; st->eps = eps;
+        st->done = (y0 != nullptr && sqrt(v[2]) < eps * sqrt(v[0])) ? 1 : 0;      // only a warm start can begin converged
     }
 }
 
@@ -421,22 +425,32 @@ static int solve_mf_nodal(pf2_csr* A, int solver, const double* b, double* x, in
     return PF2_OK;
 }
 
-int solve(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out) {
+int pcg_persistent_solve(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int warm, int* iters_out, double* relres_out);
+
+// warm = 1: x holds the initial guess x0 (the reference always starts from 0, CG.h:423; SURVEY.md section 7 hard part 1 sanctions the
+// overload: same recurrences and stopping rule ||r|| < eps ||b||, parity is on the converged solution)
+int solve_x0(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int warm, int* iters_out, double* relres_out) {
     pf2_ctx* c = A->ctx;
     PF2_CHECK(solver >= 0 && solver <= PF2_SOLVER_ILU0BICGSTAB, "unknown solver");
-    if (solver >= PF2_SOLVER_BICGSTAB) return solve_bicgstab(A, solver, b, x, itrmax, eps, iters_out, relres_out);
-    if (A->dist) { PF2_CUDA(cudaSetDevice(c->device)); return solve_dist(A, solver, b, x, itrmax, eps, iters_out, relres_out); }
     PF2_CHECK(itrmax >= 0, "itrmax");
+    if (solver >= PF2_SOLVER_BICGSTAB) return solve_bicgstab(A, solver, b, x, itrmax, eps, iters_out, relres_out);
+    PF2_CUDA(cudaSetDevice(c->device));
+    if (solver != PF2_SOLVER_ILU0CG && !(A->spmv_variant == 41)) {
+        const int rc = pcg_persistent_solve(A, solver, b, x, itrmax, eps, warm, iters_out, relres_out);
+        if (rc != PF2_E_UNSUPPORTED) return rc;
+    }
+    if (A->dist) return solve_dist(A, solver, b, x, itrmax, eps, iters_out, relres_out);      // host-ordered loop: always from x0 = 0
     if (A->spmv_variant == 41 && A->mf_nodal && A->mf_version > 0 && solver != PF2_SOLVER_ILU0CG)
         return solve_mf_nodal(A, solver, b, x, itrmax, eps, iters_out, relres_out);
-    PF2_CUDA(cudaSetDevice(c->device));
     PF2_TRY(ensure_workspace(A));
     const int n = A->rows;
+    if (solver == PF2_SOLVER_ILU0CG) warm = 0;
+    if (warm) PF2_TRY(spmv(A, x, A->y));
     PF2_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 7) == 0, "x must be 16-byte aligned (pf2_malloc gives 256)");
     const int grid = std::min(c->grid_for(n, 2), c->sm_count * 4);
     if (solver == PF2_SOLVER_ILU0CG) PF2_TRY(ilu0_factor(A));
     l2_window(A, true);
-#define INIT(M) cg_init_kernel<M><<<grid, kThreads, 0, c->stream>>>(n, b, A->indptr, A->diagpos, A->data, A->dvec, x, A->r, A->z, A->p, A->st, itrmax, eps, c->red.partials, c->red.ticket)
+#define INIT(M) cg_init_kernel<M><<<grid, kThreads, 0, c->stream>>>(n, b, A->indptr, A->diagpos, A->data, A->dvec, x, A->r, A->z, A->p, A->st, itrmax, eps, c->red.partials, c->red.ticket, warm ? A->y : nullptr)
     if (solver == PF2_SOLVER_CG) { INIT(0); }
     else if (solver == PF2_SOLVER_SCALINGCG) { INIT(1); }
     else {
@@ -498,6 +512,10 @@ int solve(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double
     return PF2_OK;
 }
 
+int solve(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out) {
+    return solve_x0(A, solver, b, x, itrmax, eps, 0, iters_out, relres_out);
+}
+
 }  // namespace pf2
 
 using namespace pf2;
@@ -506,6 +524,16 @@ extern "C" {
 
 int pf2_solve(pf2_csr* A, int solver, const double* b_dev, double* x_dev, int itrmax, double eps, int* iters_out, double* relres_out) {
     return solve(A, solver, b_dev, x_dev, itrmax, eps, iters_out, relres_out);
+}
+
+int pf2_solve_x0(pf2_csr* A, int solver, const double* b_dev, double* x_dev, int itrmax, double eps, int* iters_out, double* relres_out) {
+    return solve_x0(A, solver, b_dev, x_dev, itrmax, eps, 1, iters_out, relres_out);
+}
+
+int pf2_csr_set_pcg_mode(pf2_csr* A, int mode) {
+    PF2_CHECK(A && mode >= -1 && mode <= 1, "mode: -1 environment default, 0 three kernels per iteration, 1 persistent kernel");
+    A->pcg_mode = mode;
+    return PF2_OK;
 }
 
 int pf2_solve_host(pf2_csr* A, int solver, const double* b_host, double* x_host, int itrmax, double eps, int* iters_out, double* relres_out) {
@@ -525,10 +553,25 @@ int pf2_csr_solver_stats(pf2_csr* A, double out[8]) {
     out[0] = A->prof_ms[0] * k; out[1] = A->prof_ms[1] * k; out[2] = A->prof_ms[2] * k;
     out[3] = (double)A->prof_samples; out[4] = (double)A->total_iters; out[5] = (double)A->spmv_variant;
     out[6] = (double)A->rows; out[7] = (double)A->nnz;
+    if (A->prof_samples == 0 && A->pcg_iters > 0) {
+        // persistent kernel: per-iteration phase times from its in-kernel %globaltimer stamps (barriers included)
+        const double ki = 1.0e-6 / (double)A->pcg_iters;
+        for (int j = 0; j < 3; j++) out[j] = A->pcg_phase_ns[j] * ki;
+        out[3] = (double)A->pcg_iters;
+    }
     return PF2_OK;
 }
 int pf2_csr_solver_stats_reset(pf2_csr* A) {
     A->prof_ms[0] = A->prof_ms[1] = A->prof_ms[2] = 0.0; A->prof_samples = 0; A->total_iters = 0;
+    A->pcg_kernel_ms = 0.0; A->pcg_iters = 0; A->pcg_solves = 0;
+    A->pcg_phase_ns[0] = A->pcg_phase_ns[1] = A->pcg_phase_ns[2] = 0.0;
+    return PF2_OK;
+}
+int pf2_csr_pcg_stats(pf2_csr* A, double out[8]) {
+    out[0] = A->pcg_kernel_ms; out[1] = (double)A->pcg_iters; out[2] = (double)A->pcg_solves; out[3] = (double)A->pcg_grid;
+    const double ki = A->pcg_iters ? 1.0e-6 / (double)A->pcg_iters : 0.0;
+    for (int j = 0; j < 3; j++) out[4 + j] = A->pcg_phase_ns[j] * ki;
+    out[7] = (double)A->sell_entries;
     return PF2_OK;
 }
 

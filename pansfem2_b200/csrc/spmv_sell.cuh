@@ -28,18 +28,18 @@ __device__ __forceinline__ int sell_row(const int* __restrict__ perm, int rows, 
     return slot < rows ? slot : -1;
 }
 // sort key of row r: window | (65535 - length) | position in window  -> descending length inside each window, stable
-__global__ void sell_sort_keys_kernel(int rows, const long long* __restrict__ indptr, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+static __global__ void sell_sort_keys_kernel(int rows, const long long* __restrict__ indptr, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
         const unsigned long long len = (unsigned long long)min((long long)65535, indptr[r + 1] - indptr[r]);
         keys[r] = ((unsigned long long)(r / kSellSigma) << 32) | ((65535ull - len) << 12) | (unsigned long long)(r % kSellSigma);
         vals[r] = r;
     }
 }
-__global__ void sell_perm_tail_kernel(int rows, int slots, int* __restrict__ perm) {
+static __global__ void sell_perm_tail_kernel(int rows, int slots, int* __restrict__ perm) {
     for (int i = rows + blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += gridDim.x * blockDim.x) perm[i] = -1;
 }
 
-__global__ void sell_slice_len_kernel(int rows, int nslices, const long long* __restrict__ indptr, const int* __restrict__ perm, long long* __restrict__ slice_ptr) {
+static __global__ void sell_slice_len_kernel(int rows, int nslices, const long long* __restrict__ indptr, const int* __restrict__ perm, long long* __restrict__ slice_ptr) {
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nslices; s += gridDim.x * blockDim.x) {
         int m = 0;
         for (int l = 0; l < kSellC; l++) { const int r = sell_row(perm, rows, s * kSellC + l); if (r >= 0) m = max(m, (int)(indptr[r + 1] - indptr[r])); }
@@ -49,7 +49,7 @@ __global__ void sell_slice_len_kernel(int rows, int nslices, const long long* __
 }
 
 // fill indices (pattern) and the CSR->SELL position of every stored entry
-__global__ void sell_fill_kernel(int rows, int slots, const long long* __restrict__ indptr, const int* __restrict__ indices, const int* __restrict__ perm,
+static __global__ void sell_fill_kernel(int rows, int slots, const long long* __restrict__ indptr, const int* __restrict__ indices, const int* __restrict__ perm,
                                  const long long* __restrict__ slice_ptr, int* __restrict__ sell_idx, int* max_delta) {
     int md = 0;
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < slots; slot += gridDim.x * blockDim.x) {
@@ -70,7 +70,7 @@ __global__ void sell_fill_kernel(int rows, int slots, const long long* __restric
     if ((threadIdx.x & 31) == 0) atomicMax(max_delta, md);
 }
 // 16-bit column deltas (col - row): FEM matrices are banded, so the index stream shrinks from 4 to 2 bytes per nonzero
-__global__ void sell_delta16_kernel(int rows, long long entries, const long long* __restrict__ slice_ptr, const int* __restrict__ perm,
+static __global__ void sell_delta16_kernel(int rows, long long entries, const long long* __restrict__ slice_ptr, const int* __restrict__ perm,
                                     const int* __restrict__ sell_idx, short* __restrict__ sell_d16) {
     const int nslices = (rows + kSellC - 1) / kSellC;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -88,7 +88,7 @@ __global__ void sell_delta16_kernel(int rows, long long entries, const long long
 // ---- block deltas: rows of an NB-dof-per-node FEM matrix hold their columns in runs of NB consecutive indices (the dofs of one
 // neighbouring node), so ONE 16-bit delta per run is enough: the index stream shrinks from 2 to 2/NB bytes per nonzero.
 // Requires every row to consist of complete runs (true unless Dirichlet conditions fix only some dofs of a node).
-__global__ void sell_block_check_kernel(int rows, int nb, const long long* __restrict__ indptr, const int* __restrict__ indices, int* bad) {
+static __global__ void sell_block_check_kernel(int rows, int nb, const long long* __restrict__ indptr, const int* __restrict__ indices, int* bad) {
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
         const long long b = indptr[r];
         const int len = (int)(indptr[r + 1] - b);
@@ -103,7 +103,7 @@ __global__ void sell_block_check_kernel(int rows, int nb, const long long* __res
 // bidx[(slice_base / nb) + kb * 32 + lane] = (first column of run kb - first row of the lane's node) / nb : deltas in NODE units, so
 // they fit 16 bits up to 32 767 nodes of bandwidth (hex8 meshes with planes of up to ~10 900 nodes); wider meshes store them as int32
 template <class OUT>
-__global__ void sell_block_index_kernel(int rows, int nb, const long long* __restrict__ slice_ptr, const int* __restrict__ perm,
+static __global__ void sell_block_index_kernel(int rows, int nb, const long long* __restrict__ slice_ptr, const int* __restrict__ perm,
                                         const int* __restrict__ sell_idx, OUT* __restrict__ bidx) {
     const int nslices = (rows + kSellC - 1) / kSellC;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -121,7 +121,7 @@ __global__ void sell_block_index_kernel(int rows, int nb, const long long* __res
     }
 }
 // padding lanes of the last slice (slots beyond `rows`; with a permutation they are the last slots too)
-__global__ void sell_pad_tail_kernel(int rows, int nslices, const long long* __restrict__ slice_ptr, int* __restrict__ sell_idx, double* __restrict__ sell_val) {
+static __global__ void sell_pad_tail_kernel(int rows, int nslices, const long long* __restrict__ slice_ptr, int* __restrict__ sell_idx, double* __restrict__ sell_val) {
     const int s = nslices - 1;
     const long long base = slice_ptr[s];
     const int width = (int)((slice_ptr[s + 1] - base) / kSellC);
@@ -130,7 +130,7 @@ __global__ void sell_pad_tail_kernel(int rows, int nslices, const long long* __r
         if (s * kSellC + l >= rows) { if (sell_idx) sell_idx[base + t] = 0; sell_val[base + t] = 0.0; }
     }
 }
-__global__ void sell_values_kernel(int rows, const long long* __restrict__ indptr, const double* __restrict__ data, const int* __restrict__ perm,
+static __global__ void sell_values_kernel(int rows, const long long* __restrict__ indptr, const double* __restrict__ data, const int* __restrict__ perm,
                                    const long long* __restrict__ slice_ptr, double* __restrict__ sell_val) {
     // one warp per slice: lane l copies row l; reads are strided (row-contiguous), writes coalesced
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -147,7 +147,63 @@ __global__ void sell_values_kernel(int rows, const long long* __restrict__ indpt
     }
 }
 
-// IDX = int: absolute columns (4 B/nnz); IDX = short: column - row deltas (2 B/nnz)
+// loads of the matrix stream: evict-first (the matrix is far larger than L2) or plain (slabs small enough to stay L2-resident)
+template <bool CS, class T> __device__ __forceinline__ T sell_ld(const T* p) { return CS ? __ldcs(p) : __ldg(p); }
+
+// One lane's share of one slice: acc = sum_k val[k] * x[col[k]] for row `r` (lane `lane` of the slice starting at `base`, `width`
+// stored entries per row).  IDX = int: absolute columns (4 B/nnz); IDX = short: column - row deltas (2 B/nnz); NB > 1: one delta per
+// run of NB consecutive columns, in node units.  U independent value / index loads are in flight per round.
+// NC = false: x is written inside the same kernel by other CTAs (persistent PCG): plain coherent loads, never the read-only path.
+template <bool NC> __device__ __forceinline__ double sell_ldx(const double* x, int i) { return NC ? __ldg(x + i) : x[i]; }
+
+template <class IDX, int NB, int U, bool CS, bool NC = true>
+__device__ __forceinline__ double sell_slice_acc(const IDX* __restrict__ sell_idx, const double* __restrict__ sell_val, const double* x,
+                                                 long long base, int width, int lane, int r) {
+    const double* v = sell_val + base + lane;
+    const int off = (NB > 1) ? max(r, 0) - max(r, 0) % NB                // block deltas: node units relative to the first row of the lane's node
+                             : ((sizeof(IDX) == 2) ? max(r, 0) : 0);     // per-entry deltas are relative to the lane's row (padding lanes: delta 0, value 0)
+    double acc = 0.0;
+    if constexpr (NB > 1) {
+        // block deltas: one index per run of NB consecutive columns; the index stream of this slice starts at base / NB
+        const IDX* cb = sell_idx + base / NB + lane;
+        const int nblk = width / NB;
+        constexpr int UB = (NB == 2) ? 3 : 2;              // 6 values in flight per step, like the scalar path
+        int kb = 0;
+        for (; kb + UB <= nblk; kb += UB) {
+            double vv[UB * NB];
+            int cc[UB];
+#pragma unroll
+            for (int u = 0; u < UB; u++) {
+                cc[u] = off + NB * (int)sell_ld<CS>(cb + (kb + u) * kSellC);
+#pragma unroll
+                for (int j = 0; j < NB; j++) vv[u * NB + j] = sell_ld<CS>(v + ((kb + u) * NB + j) * kSellC);
+            }
+#pragma unroll
+            for (int u = 0; u < UB; u++)
+#pragma unroll
+                for (int j = 0; j < NB; j++) acc += vv[u * NB + j] * sell_ldx<NC>(x, cc[u] + j);
+        }
+        for (; kb < nblk; kb++) {
+            const int c0 = off + NB * (int)sell_ld<CS>(cb + kb * kSellC);
+#pragma unroll
+            for (int j = 0; j < NB; j++) acc += sell_ld<CS>(v + (kb * NB + j) * kSellC) * sell_ldx<NC>(x, c0 + j);
+        }
+    } else {
+        const IDX* c = sell_idx + base + lane;
+        int k = 0;
+        for (; k + U <= width; k += U) {
+            double vv[U];
+            int cc[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) { vv[u] = sell_ld<CS>(v + (k + u) * kSellC); cc[u] = off + (int)sell_ld<CS>(c + (k + u) * kSellC); }
+#pragma unroll
+            for (int u = 0; u < U; u++) acc += vv[u] * sell_ldx<NC>(x, cc[u]);
+        }
+        for (; k < width; k++) acc += sell_ld<CS>(v + k * kSellC) * sell_ldx<NC>(x, off + (int)sell_ld<CS>(c + k * kSellC));
+    }
+    return acc;
+}
+
 template <bool DOT, class IDX, bool PERM = false, int NB = 1, int U = 6>
 __global__ void __launch_bounds__(kThreads)
 spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* __restrict__ perm, const IDX* __restrict__ sell_idx, const double* __restrict__ sell_val,
@@ -162,49 +218,8 @@ spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* _
     for (int s = warp; s < nslices; s += nwarps) {
         const long long base = slice_ptr[s];
         const int width = (int)((slice_ptr[s + 1] - base) / kSellC);
-        const double* v = sell_val + base + lane;
-        const IDX* c = sell_idx + base + lane;
         const int r = PERM ? perm[s * kSellC + lane] : ((s * kSellC + lane < rows) ? s * kSellC + lane : -1);
-        const int off = (NB > 1) ? max(r, 0) - max(r, 0) % NB                // block deltas: node units relative to the first row of the lane's node
-                                 : ((sizeof(IDX) == 2) ? max(r, 0) : 0);     // per-entry deltas are relative to the lane's row (padding lanes: delta 0, value 0)
-        double acc = 0.0;
-        if constexpr (NB > 1) {
-            // block deltas: one index per run of NB consecutive columns; the index stream of this slice starts at base / NB
-            const IDX* cb = sell_idx + base / NB + lane;
-            const int nblk = width / NB;
-            constexpr int UB = (NB == 2) ? 3 : 2;              // 6 values in flight per step, like the scalar path
-            int kb = 0;
-            for (; kb + UB <= nblk; kb += UB) {
-                double vv[UB * NB];
-                int cc[UB];
-#pragma unroll
-                for (int u = 0; u < UB; u++) {
-                    cc[u] = off + NB * (int)__ldcs(cb + (kb + u) * kSellC);
-#pragma unroll
-                    for (int j = 0; j < NB; j++) vv[u * NB + j] = __ldcs(v + ((kb + u) * NB + j) * kSellC);
-                }
-#pragma unroll
-                for (int u = 0; u < UB; u++)
-#pragma unroll
-                    for (int j = 0; j < NB; j++) acc += vv[u * NB + j] * __ldg(x + cc[u] + j);
-            }
-            for (; kb < nblk; kb++) {
-                const int c0 = off + NB * (int)__ldcs(cb + kb * kSellC);
-#pragma unroll
-                for (int j = 0; j < NB; j++) acc += __ldcs(v + (kb * NB + j) * kSellC) * __ldg(x + c0 + j);
-            }
-        } else {
-        int k = 0;
-        for (; k + U <= width; k += U) {
-            double vv[U];
-            int cc[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) { vv[u] = __ldcs(v + (k + u) * kSellC); cc[u] = off + (int)__ldcs(c + (k + u) * kSellC); }
-#pragma unroll
-            for (int u = 0; u < U; u++) acc += vv[u] * __ldg(x + cc[u]);
-        }
-        for (; k < width; k++) acc += __ldcs(v + k * kSellC) * __ldg(x + off + (int)__ldcs(c + k * kSellC));
-        }
+        const double acc = sell_slice_acc<IDX, NB, U, true>(sell_idx, sell_val, x, base, width, lane, r);
         if (r >= 0) {
             y[r] = acc;
             if (DOT && r >= dot_lo && r < dot_hi) dot += acc * x[r];

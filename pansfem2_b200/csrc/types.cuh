@@ -77,6 +77,7 @@ struct pf2_csr {
     pf2::P2PView p2p_view;
     pf2::P2PView* p2p_dev = nullptr;      // device copy handed to the fused kernels (nullptr: single GPU or NCCL backend)
     unsigned long long* p2p_epoch = nullptr;
+    void* p2p_opened[2] = { nullptr, nullptr };   // IPC mappings of the left / right neighbour's Krylov slab
     long long nnz = 0;
     long long* indptr = nullptr;   // rows+1 (int64: config 5 has nnz > 2^31)
     int* indices = nullptr;        // nnz, sorted within a row
@@ -138,6 +139,14 @@ struct pf2_csr {
     void* bi_st = nullptr;
     void* bi_hst = nullptr;
     cudaEvent_t bi_ev[2] = { nullptr, nullptr };
+    // persistent PCG kernel (pcg_persistent.cuh): barrier / timer block, accumulated statistics
+    void* pcg_sync = nullptr;
+    void* h_pcg_sync = nullptr;        // pinned copy read back after every solve
+    int pcg_mode = -1;                 // -1: from the environment (PF2_PCG, default on), 0: three kernels per iteration, 1: persistent kernel
+    int pcg_grid = 0;                  // CTAs of the last persistent launch
+    double pcg_kernel_ms = 0.0;        // CUDA-event time of the persistent kernels since the last statistics reset
+    long long pcg_iters = 0, pcg_solves = 0;
+    double pcg_phase_ns[3] = { 0, 0, 0 };
     double prof_ms[3] = { 0, 0, 0 };   // spmv+dot, update, p-update
     long long prof_samples = 0;
     long long total_iters = 0;

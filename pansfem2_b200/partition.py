@@ -45,6 +45,15 @@ def _dofmap(nnode, ndof, fixed):
     return n2g.reshape(nnode, ndof)
 
 
+def _check_radius(radius, hx=1.0):
+    """One ghost element plane per side holds every filter neighbour of an owned element only while the radius stays below two
+    element widths; a wider filter would silently truncate the neighbour lists next to the cut."""
+    if int(np.floor(radius / hx + 1.0e-12)) > 1:
+        raise ValueError(f"filter radius {radius} reaches past the single ghost element plane of a slab (element width {hx}): "
+                         "the row-block partition supports radius < 2 element widths")
+    return radius
+
+
 def slab_from_factory(factory, grid, ndof, rank: int, nranks: int) -> Slab:
     """Build one slab WITHOUT materialising the global mesh: `factory(xr=(i0, i1))` returns the Problem restricted to element
     planes [i0, i1) with local ids (problems.cantilever2d / heat2d / cantilever3d all take `xr`).  Used for the big configs;
@@ -56,6 +65,7 @@ def slab_from_factory(factory, grid, ndof, rank: int, nranks: int) -> Slab:
     e0, e1 = rank * nx // nranks, (rank + 1) * nx // nranks
     le0, le1 = max(e0 - 1, 0), min(e1 + 1, nx)
     L = factory(xr=(le0, le1))
+    _check_radius(L.extra.get("radius", 1.5))
     on0, on1 = e0, (e1 if rank < nranks - 1 else nx + 1)
     own_node_lo, own_node_hi = (on0 - le0) * plane_n, (on1 - le0) * plane_n
     ln = np.asarray(L.loads[0], np.int64)
@@ -121,7 +131,7 @@ def slab(P: problems.Problem, rank: int, nranks: int) -> Slab:
     loads = ((ln[keep] - node_lo).astype(np.int32), np.asarray(P.loads[1])[keep].astype(np.int32), np.asarray(P.loads[2])[keep])
     # filter lists of the local grid (identical to the global lists for every owned element)
     lgrid = (le1 - le0,) + tuple(P.grid[1:])
-    radius = P.extra.get("radius", 1.5)
+    radius = _check_radius(P.extra.get("radius", 1.5))
     if len(P.grid) == 2:
         nbrs = mesher.filter_neighbors_2d(lgrid[0], lgrid[1], float(lgrid[0]), float(lgrid[1]), radius)
     else:

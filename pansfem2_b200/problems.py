@@ -83,7 +83,7 @@ def cantilever2d(nx=60, ny=40, opt_kind=OPT_OC, filter_kind=FILTER_HEAVISIDE, ra
     nxl = nx if xr is None else xr[1] - xr[0]
     nbrs = mesher.filter_neighbors_2d(nxl, ny, float(nxl), ly, radius)
     return Problem(f"cantilever2d_{nx}x{ny}", EQ_PLANESTRAIN, coords, conn, fixed, (ln, ld, lv), nbrs, (nxl, ny),
-                   filter_kind=filter_kind, opt_kind=opt_kind, extra={"global_grid": (nx, ny)})
+                   filter_kind=filter_kind, opt_kind=opt_kind, extra={"global_grid": (nx, ny), "radius": radius})
 
 
 def heat2d(nx=64, ny=64, opt_kind=OPT_OC, filter_kind=FILTER_DENSITY, radius=1.5, xr=None) -> Problem:
@@ -101,7 +101,7 @@ def heat2d(nx=64, ny=64, opt_kind=OPT_OC, filter_kind=FILTER_DENSITY, radius=1.5
     nbrs = mesher.filter_neighbors_2d(nxl, ny, float(nxl), ly, radius)
     return Problem(f"heat2d_{nx}x{ny}", EQ_HEAT, coords, conn, fixed, loads, nbrs, (nxl, ny),
                    filter_kind=filter_kind, opt_kind=opt_kind, E0=1.0e-3, E1=1.0, weightlimit=0.4, scale0=1.0,
-                   beta_period=0, extra={"global_grid": (nx, ny)})
+                   beta_period=0, extra={"global_grid": (nx, ny), "radius": radius})
 
 
 def cantilever3d(nx=16, ny=8, nz=8, opt_kind=OPT_OC, filter_kind=FILTER_DENSITY, radius=1.5, xr=None) -> Problem:
@@ -114,7 +114,7 @@ def cantilever3d(nx=16, ny=8, nz=8, opt_kind=OPT_OC, filter_kind=FILTER_DENSITY,
     nxl = nx if xr is None else xr[1] - xr[0]
     nbrs = mesher.filter_neighbors_3d(nxl, ny, nz, float(nxl), ly, lz, radius)
     return Problem(f"cantilever3d_{nx}x{ny}x{nz}", EQ_SOLID, coords, conn, fixed, (ln, ld, lv), nbrs, (nxl, ny, nz),
-                   filter_kind=filter_kind, opt_kind=opt_kind, beta_period=0, extra={"global_grid": (nx, ny, nz)})
+                   filter_kind=filter_kind, opt_kind=opt_kind, beta_period=0, extra={"global_grid": (nx, ny, nz), "radius": radius})
 
 
 def family_problem(eq, n, opt_kind=OPT_OC, filter_kind=FILTER_DENSITY, radius=1.5) -> Problem:

@@ -18,8 +18,9 @@ namespace PANSFEM2 { namespace B200 {
     //  shared device mirror of one CSR<double>; copies of a CSR share it until one of them is mutated
     struct CsrDevice {
         pf2_csr* handle;
-        CsrDevice() : handle(nullptr) {}
-        ~CsrDevice() { if (handle) pf2_csr_destroy(handle); }
+        bool owned;             //  false: adopted from a B200::Model, which destroys it itself
+        CsrDevice() : handle(nullptr), owned(true) {}
+        ~CsrDevice() { if (handle && owned) pf2_csr_destroy(handle); }
     };
 } }
 
@@ -37,10 +38,12 @@ public:
             for (const auto& e : row) { indices.push_back(e.first); data.push_back(e.second); }
         }
     }
-    //  adopt an already assembled device matrix (batched path): host arrays are filled on first host access
-    CSR(pf2_csr* _device) : ROWS(DeviceRows(_device)), COLS(DeviceRows(_device)) {
+    //  view of an already assembled device matrix (batched path; the handle stays owned by whoever built it, e.g. B200::Model):
+    //  host arrays are filled on first host access
+    explicit CSR(pf2_csr* _device) : ROWS(DeviceRows(_device)), COLS(DeviceRows(_device)) {
         device = std::make_shared<PANSFEM2::B200::CsrDevice>();
         device->handle = _device;
+        device->owned = false;
         host_stale = true;
     }
 
@@ -118,6 +121,7 @@ template<class T1, class T2>
 inline const CSR<T1> operator+(const CSR<T1>& _m1, const CSR<T2>& _m2) {
     assert(_m1.ROWS == _m2.ROWS && _m1.COLS == _m2.COLS);
     CSR<T1> m(_m1);
+    if (_m2.ROWS > 0) _m2.get(0, 0);      //  a device-adopted operand fills its host arrays first
     for (int i = 0; i < _m2.ROWS; i++) for (int k = _m2.indptr[i]; k < _m2.indptr[i + 1]; k++) m.set(i, _m2.indices[k], m.get(i, _m2.indices[k]) + _m2.data[k]);
     return m;
 }
@@ -125,6 +129,7 @@ template<class T1, class T2>
 inline const CSR<T1> operator-(const CSR<T1>& _m1, const CSR<T2>& _m2) {
     assert(_m1.ROWS == _m2.ROWS && _m1.COLS == _m2.COLS);
     CSR<T1> m(_m1);
+    if (_m2.ROWS > 0) _m2.get(0, 0);      //  a device-adopted operand fills its host arrays first
     for (int i = 0; i < _m2.ROWS; i++) for (int k = _m2.indptr[i]; k < _m2.indptr[i + 1]; k++) m.set(i, _m2.indices[k], m.get(i, _m2.indices[k]) - _m2.data[k]);
     return m;
 }

@@ -15,9 +15,3 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
-
-
-# Tests of device paths that were written after the last GPU slot of a round could not be run on hardware before the round closed.  They
-# run with the rest of the GPU suite, but a failure is reported as XFAIL (and a pass as XPASS) so that one unverified test cannot abort the
-# verified ones under `pytest -x`; the marker is removed once the test has passed on a B200.
-first_gpu_run = pytest.mark.xfail(reason="not yet run on a B200 (added after the last GPU slot of round 1)", strict=False)

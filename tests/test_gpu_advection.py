@@ -11,7 +11,6 @@ import pytest
 from pansfem2_b200 import capi
 from pansfem2_b200 import eqcode as ec
 
-from conftest import first_gpu_run  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -110,7 +109,6 @@ def test_dynamic_sample_time_loop_on_the_device(ctx, adv):
     P.close()
 
 
-@first_gpu_run
 def test_heat_conduction_theta_scheme_on_the_device(ctx, adv):
     """sample/heattransfer/sample_heattransfer_dynamic.cpp (HeatTransfer + HeatCapacity, Crank-Nicolson, ScalingCG, 500 steps) through the
     Diffusion + Mass pair of pf2_advdiff_assemble with the field resident on the device -> the committed dynamic.vtk and the oracle's run."""

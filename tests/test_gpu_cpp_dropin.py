@@ -12,7 +12,6 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import first_gpu_run  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -127,7 +126,6 @@ def test_unmodified_reference_planestrain_t3_driver_on_the_header_mirror(tmp_pat
     np.testing.assert_allclose(got["r"][:, :2], g["ps_r"], rtol=1e-5, atol=2e-3)
 
 
-@first_gpu_run
 def test_unmodified_reference_homogenization_driver_on_the_header_mirror(tmp_path, golden_dir):
     """sample/homogenization/sample_homogenization.cpp, unmodified: SquareAnnulusMesh2, ImportPeriodicFromCSV + SetPeriodic, per-element
     PlaneStrainStiffness on the device, HomogenizePlaneStrainBodyForce / WeakSpring / ...Constitutive on the host, three ScalingCG solves on

@@ -14,7 +14,6 @@ from pansfem2_b200 import capi, problems
 from pansfem2_b200 import eqcode as ec
 from test_families_pinned import CASES, t3_heat_problem, t3_planestrain_problem
 
-from conftest import first_gpu_run  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -48,7 +47,6 @@ def test_every_selection_element_matrix(ctx, fam):
         assert rel(ke, fam[f"ke_{eq}"]) < 1e-13, ec.describe(eq)
 
 
-@first_gpu_run
 def test_general_constitutive_matrix_selections(ctx, golden_dir):
     """PlaneStiffness / PlaneStiffnessBbar / PlaneStiffnessWilsonTaylor (Homogenization.h:141-280) through pf2_element_matrix_d: 80 live-reference
     cases (every 2-D shape / rule, every <ICV, ICD> pair, symmetric and non-symmetric D).  (Added after the last GPU slot of r01; the same
