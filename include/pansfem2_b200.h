@@ -201,8 +201,12 @@ int pf2_csr_set_pcg_mode(pf2_csr* A, int mode);
 int pf2_csr_solver_stats(pf2_csr* A, double out[8]);
 int pf2_csr_solver_stats_reset(pf2_csr* A);
 /* persistent PCG kernel since the last reset: out = {CUDA-event ms of the kernel launches (whole solves), iterations, solves,
- * CTAs of the last launch, product / update / p-update phase ms per iteration, stored SELL entries} */
-int pf2_csr_pcg_stats(pf2_csr* A, double out[8]);
+ * CTAs of the last launch, product / update / p-update phase ms per iteration, stored SELL entries, and the part of each of the
+ * three phases CTA 0 spent inside the grid exchange (tail of the grid + exchange latency), 0} */
+int pf2_csr_pcg_stats(pf2_csr* A, double out[12]);
+/* diagnostics: %globaltimer of every CTA at the start / end of its share of the three phases in iteration 5 of the last persistent
+ * solve: out_host[6][2048] (product start, end, update start, end, p-update start, end) */
+int pf2_csr_pcg_debug(pf2_csr* A, unsigned long long* out_host);
 /* ILU(0) factors of A (unit-L strictly lower + U with diagonal in A's pattern), cached on A until values change */
 int pf2_ilu0_factor(pf2_csr* A);
 int pf2_ilu0_download(pf2_csr* A, double* data_host);

@@ -15,7 +15,7 @@ from . import eqcode
 from .eqcode import eq_code  # noqa: F401
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpansfem2_b200.so")
+LIB_PATH = os.environ.get("PF2_LIB") or os.path.join(HERE, "libpansfem2_b200.so")      # PF2_LIB: an experimental build (tuning runs only)
 
 EQ_PLANESTRAIN, EQ_SOLID, EQ_HEAT = 0, 1, 2
 SOLVER_CG, SOLVER_SCALINGCG, SOLVER_ILU0CG = 0, 1, 2
@@ -280,10 +280,10 @@ class Csr:
         _ck(lib().pf2_csr_set_pcg_mode(self.h, int(mode)))
 
     def pcg_stats(self):
-        st = (C.c_double * 8)()
+        st = (C.c_double * 12)()
         _ck(lib().pf2_csr_pcg_stats(self.h, st))
         return dict(kernel_ms=st[0], iters=int(st[1]), solves=int(st[2]), grid=int(st[3]), product_ms=st[4], update_ms=st[5],
-                    pupdate_ms=st[6], sell_entries=int(st[7]))
+                    pupdate_ms=st[6], sell_entries=int(st[7]), product_wait_ms=st[8], update_wait_ms=st[9], pupdate_wait_ms=st[10])
 
     def solver_stats(self, reset=False):
         st = (C.c_double * 8)()

@@ -414,7 +414,9 @@ int pf2_dist_allreduce_sum(pf2_dist* d, double* dev, int count) { return dist_al
 
 // ---- peer-memory backend ------------------------------------------------------------------------------------------
 // export: this rank's IPC handles {arena (64 B), Krylov slab of A (64 B)} ; import: all ranks' handles + halo descriptors.
-static size_t arena_bytes(int world) { return sizeof(double) * 2 * world * 4 + sizeof(unsigned long long) * (2 * world + 2); }
+//   arena: slots[2][world][4] fp64 | flags[2][world] u64 | halo_flags[2] u64 | (16-byte aligned) ll[2][world][4][2] u64
+static size_t arena_ll_offset(int world) { return ((sizeof(double) * 2 * world * 4 + sizeof(unsigned long long) * (2 * world + 2)) + 15) & ~(size_t)15; }
+static size_t arena_bytes(int world) { return arena_ll_offset(world) + sizeof(unsigned long long) * 2 * world * 4 * 2; }
 
 int pf2_csr_p2p_export(pf2_csr* A, char handles_out[128]) {
     PF2_CHECK(A && A->dist, "call pf2_csr_set_partition first");
@@ -462,6 +464,7 @@ int pf2_csr_p2p_import(pf2_csr* A, const char* all_handles, const int* all_halo)
         v.slots[r] = (double*)base;
         v.flags[r] = (unsigned long long*)((char*)base + sizeof(double) * 2 * world * 4);
         v.halo_flags[r] = v.flags[r] + 2 * world;
+        v.ll[r] = (unsigned long long*)((char*)base + arena_ll_offset(world));
     }
     (void)np;
     for (int side = 0; side < 2; side++) {

@@ -13,10 +13,15 @@ int sell_refresh(pf2_csr* A);
 // PF2_E_UNSUPPORTED without an error message = "not applicable to this matrix": the caller falls back to the three-kernel loop.
 int ensure_workspace_pub(pf2_csr* A);
 
+// Which loop runs (pf2_csr_set_pcg_mode / PF2_PCG override): the persistent kernel removes the host-ordered synchronisation points, which
+// is what bounds a partitioned solve and a small system; on one GPU a LARGE system is bandwidth-bound either way and the three
+// stand-alone kernels keep a few per cent more of the HBM rate (measured, profiles/r02_pcg_tune.md), so they stay the default there.
 static bool pcg_enabled(const pf2_csr* A) {
     if (A->pcg_mode >= 0) return A->pcg_mode != 0;
-    static const int env = getenv("PF2_PCG") ? atoi(getenv("PF2_PCG")) : 1;
-    return env != 0;
+    static const int env = getenv("PF2_PCG") ? atoi(getenv("PF2_PCG")) : -1;
+    if (env >= 0) return env != 0;
+    static const long long auto_rows = getenv("PF2_PCG_AUTO_ROWS") ? atoll(getenv("PF2_PCG_AUTO_ROWS")) : 600000;
+    return A->dist != nullptr || (long long)A->rows <= auto_rows;
 }
 
 template <class IDX, int NB, int MODE, bool DIST, bool CS>
@@ -26,7 +31,7 @@ static int pcg_launch(pf2_csr* A, PcgArgs& args) {
     const int wave = c->wave_grid(fn, kThreads);
     const int s_lo = args.own_lo / kSellC, s_hi = (args.own_hi + kSellC - 1) / kSellC;
     const int want = std::max(1, (s_hi - s_lo + (kThreads / 32) - 1) / (kThreads / 32));
-    int grid = std::min(wave, want);
+    int grid = std::min(std::min(wave, want), kPcgMaxCtas);
     static const int cap = getenv("PF2_PCG_GRID") ? atoi(getenv("PF2_PCG_GRID")) : 0;      // tuning / tests: CTAs of the cooperative grid
     if (cap > 0) grid = std::min(grid, cap);
     A->pcg_grid = grid;
@@ -42,13 +47,14 @@ int pcg_persistent_solve(pf2_csr* A, int solver, const double* b, double* x, int
     const bool dist = A->dist != nullptr;
     if (dist && !A->p2p_ready) return PF2_E_UNSUPPORTED;                 // NCCL backend keeps the host-ordered loop
     PF2_TRY(plan_spmv_pub(A));
-    if (A->spmv_variant != 31 || A->sell_perm || A->sell_nb == 2) return PF2_E_UNSUPPORTED;
+    if (A->spmv_variant != 31 || A->sell_nb == 2 || (A->sell_perm && dist)) return PF2_E_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return PF2_E_UNSUPPORTED;      // the vector phases use 128-bit accesses
     PF2_CUDA(cudaSetDevice(c->device));
     PF2_TRY(ensure_workspace_pub(A));
     if (!A->sell_values_valid) PF2_TRY(sell_refresh(A));
     if (!A->pcg_sync) {
         PF2_CUDA(cudaMalloc(&A->pcg_sync, sizeof(PcgSync)));
-        PF2_CUDA(cudaHostAlloc(&A->h_pcg_sync, sizeof(PcgSync), cudaHostAllocDefault));
+        PF2_CUDA(cudaHostAlloc(&A->h_pcg_sync, sizeof(unsigned long long) * 8, cudaHostAllocDefault));
     }
     PF2_CHECK((reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(b) & 7) == 0, "x and b must be 8-byte aligned");
     PcgArgs a;
@@ -56,11 +62,11 @@ int pcg_persistent_solve(pf2_csr* A, int solver, const double* b, double* x, int
     a.rows = A->rows; a.nslices = (A->rows + kSellC - 1) / kSellC;
     a.own_lo = dist ? A->own_lo : 0; a.own_hi = dist ? A->own_hi : A->rows;
     a.itrmax = itrmax; a.warm = warm; a.eps = eps;
-    a.slice_ptr = A->sell_ptr; a.sell_val = A->sell_val;
+    a.slice_ptr = A->sell_ptr; a.sell_val = A->sell_val; a.perm = A->sell_perm;
     a.sell_idx = A->sell_b32 ? (const void*)A->sell_b32 : A->sell_d16 ? (const void*)A->sell_d16 : (const void*)A->sell_idx;
     a.indptr = A->indptr; a.diagpos = A->diagpos; a.data = A->data;
     a.b = b; a.x = x; a.r = A->r; a.z = A->z; a.p = A->p; a.y = A->y; a.dvec = A->dvec;
-    a.st = A->st; a.partials = c->red.partials; a.sync = (PcgSync*)A->pcg_sync;
+    a.st = A->st; a.sync = (PcgSync*)A->pcg_sync;
     a.p2p = A->p2p_dev; a.epoch = A->p2p_epoch;
     a.sendL = A->halo[0]; a.cntL = A->halo[2]; a.sendR = A->halo[3]; a.cntR = A->halo[5];
     if (dist) {
@@ -89,14 +95,14 @@ int pcg_persistent_solve(pf2_csr* A, int solver, const double* b, double* x, int
     PF2_TRY(rc);
     PF2_CUDA(cudaEventRecord(A->pev[0][1], c->stream));
     PF2_CUDA(cudaMemcpyAsync(&A->h_st[0], A->st, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
-    PF2_CUDA(cudaMemcpyAsync(A->h_pcg_sync, A->pcg_sync, sizeof(PcgSync), cudaMemcpyDeviceToHost, c->stream));
+    PF2_CUDA(cudaMemcpyAsync(A->h_pcg_sync, &((PcgSync*)A->pcg_sync)->t_ns[0], sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, c->stream));
     PF2_CUDA(cudaStreamSynchronize(c->stream));
     const CgState last = A->h_st[0];
-    const PcgSync* hs = (const PcgSync*)A->h_pcg_sync;
+    const unsigned long long* t_ns = (const unsigned long long*)A->h_pcg_sync;
     float ms = 0;
     if (cudaEventElapsedTime(&ms, A->pev[0][0], A->pev[0][1]) == cudaSuccess) A->pcg_kernel_ms += ms; else cudaGetLastError();
     A->pcg_iters += last.iter; A->pcg_solves++;
-    for (int j = 0; j < 3; j++) A->pcg_phase_ns[j] += (double)hs->t_ns[j];
+    for (int j = 0; j < 3; j++) { A->pcg_phase_ns[j] += (double)t_ns[j]; A->pcg_wait_ns[j] += (double)t_ns[4 + j]; }
     A->total_iters += last.iter;
     if (iters_out) *iters_out = last.iter;
     if (relres_out) *relres_out = sqrt(last.rr) / sqrt(last.bb);
@@ -109,3 +115,11 @@ int pcg_persistent_solve(pf2_csr* A, int solver, const double* b, double* x, int
 }
 
 }  // namespace pf2
+
+// diagnostics: per-CTA %globaltimer stamps of iteration kPcgDbgIter of the last persistent solve (6 x 2048 u64)
+extern "C" int pf2_csr_pcg_debug(pf2_csr* A, unsigned long long* out_host) {
+    using namespace pf2;
+    PF2_CHECK(A && A->pcg_sync && out_host, "no persistent solve yet");
+    PF2_CUDA(cudaMemcpy(out_host, &((PcgSync*)A->pcg_sync)->dbg[0][0], sizeof(unsigned long long) * 6 * kPcgMaxCtas, cudaMemcpyDeviceToHost));
+    return PF2_OK;
+}

@@ -1,27 +1,28 @@
 // pcg_persistent.cuh -- CG / ScalingCG (CG.h:124-154, 420-453) as ONE persistent cooperative kernel per solve.
 //
-// The three-kernel loop of solver.cu pays three launch boundaries (drain + ramp) per iteration and, on a partitioned
-// matrix, three host-ordered synchronisation points with the peers.  Here one cooperative grid (every CTA resident) runs the
-// whole solve:
+// The three-kernel loop of solver.cu is at the HBM bound on one GPU once the matrix is large, but every iteration has three
+// host-ordered synchronisation points: on a partitioned matrix (peers over NVLink) and on small systems those, not bytes, set the
+// time per iteration.  Here one cooperative grid (every CTA resident) runs the whole solve:
 //
-//     init      r = b - A x0 (x0 = 0: r = b) ; z = r / D ; p = z ; b.b, z.r, r.r                         reduce
-//     loop      y = A p on the SELL-32 mirror, p.y                                                       reduce  -> alpha
-//               x += alpha p ; r -= alpha y ; z = r / D ; z.r, r.r                                       reduce  -> beta, ||r|| test
-//               p = beta p + z  (boundary planes first: they are stored straight into the neighbours' ghost ranges)
-//                                                                                                        barrier
+//     init      r = b - A x0 (x0 = 0: r = b) ; z = r / D ; p = z ; b.b, z.r, r.r                         REDUCE + BARRIER
+//     loop      y = A p on the SELL-32 mirror (interior slices first), p.y                               REDUCE  -> alpha
+//               x += alpha p ; r -= alpha y ; z = r / D ; z.r, r.r                                       REDUCE  -> beta, ||r|| test
+//               p = beta p + z  (boundary slices first: they also go into the neighbours' ghost ranges)  BARRIER
 //
-// A `reduce` is a grid barrier that carries a deterministic sum: every CTA parks its partial, the LAST CTA to arrive folds
-// them in CTA order, (partitioned runs: allreduces the result with the peers over NVLink peer memory, rank order, bitwise
-// identical everywhere), publishes it and releases the others.  alpha, beta and the convergence decision are computed
-// redundantly by every thread from the published sums, so no state round-trips through the host: one launch per solve.
-// Row-block partition (DIST): the halo of p is pushed by the CTAs that update the boundary planes, and only the warps that
-// multiply the boundary slices of the NEXT product wait for the neighbours' planes (interior slices are processed first), i.e.
-// the exchange overlaps the interior rows.
+// Row ownership.  A warp owns the same SELL slices in every phase and lane l owns row l of each: y, z, x, r and D are only ever
+// touched by their owner thread, so the two REDUCE points need NO memory ordering at all.  A REDUCE moves values, not memory: every
+// CTA publishes its partial sums as self-validating 8-byte {half of the double, generation} words (the LL protocol of NCCL), CTA 0
+// collects them in CTA order (deterministic), exchanges the total with the peer GPUs the same way over NVLink (rank order: bitwise
+// identical on every rank) and publishes the result the same way: no atomics, no fences, one L2 round trip per hop.  Only p is read
+// by other threads (the gathers of the next product): the BARRIER after the p-update is the same exchange wrapped in a release
+// fence before and an acquire fence after (SASS: MEMBAR + CCTL.IVALL, which also drops the SM's L1 lines).
+// Row-block partition (DIST): the owner of a boundary-plane row stores the new p straight into the neighbour's ghost range; the
+// warp that completes a plane raises the neighbour's halo flag.  In the next product only the warps that reach a boundary slice
+// wait for that flag, after their interior slices: the exchange overlaps the interior rows.
+// alpha, beta and the convergence decision are computed redundantly by every thread from the published sums: one launch per solve.
 //
-// Memory-model notes.  Vectors written inside the kernel (p, x, r, z, y, D) are never read through the non-coherent path
-// (no __ldg / const __restrict__); every barrier ends with a gpu-scope fence executed after the release flag was observed
-// (SASS: MEMBAR + CCTL.IVALL, which drops the SM's L1 lines), the halo wait with a system-scope one.  Every spin is bounded
-// (kSpinLimitNs): a peer that died turns into PF2_E_CUDA on the host instead of a hung box.
+// Vectors written inside the kernel are never read through the non-coherent path (no __ldg / const __restrict__).  Every spin is
+// bounded (kSpinLimitNs): a peer that died turns into PF2_E_CUDA on the host instead of a hung box.
 #pragma once
 #include "types.cuh"
 #include "p2p.cuh"
@@ -29,26 +30,37 @@
 
 namespace pf2 {
 
+#ifndef PF2_PCG_BACKOFF
+#define PF2_PCG_BACKOFF 0
+#endif
 #ifndef PF2_PCG_MINB
 #define PF2_PCG_MINB 8
 #endif
 constexpr unsigned long long kSpinLimitNs = 4000000000ull;   // 4 s: three orders of magnitude above any legitimate wait
 
+constexpr int kPcgMaxCtas = 2048;        // >= CTAs of any cooperative grid on this part (148 SMs x 8)
+constexpr int kPcgTerms = 4;
+constexpr int kPcgDbgIter = 5;
+
 struct PcgSync {                     // device memory, zeroed before every launch
-    unsigned int arrive;             // barrier arrivals of the current generation (reset by the last arriver)
-    unsigned int abort;              // a bounded spin timed out: every CTA leaves at its next barrier
-    unsigned int halo_arrive[2];     // CTAs that finished pushing the left / right boundary plane
-    unsigned int pad0[28];
-    unsigned int release;            // last generation released
-    unsigned int pad1[31];
-    double result[2][4];             // published sums, double-buffered by generation parity
-    unsigned long long t_ns[4];      // CTA 0's view: ns in the product / update / p-update phases (barriers included), iterations
+    // LL words: [parity][term][CTA][2 halves]: a CTA's partial sums of the current generation; [parity][term][2]: the result
+    unsigned long long part[2][kPcgTerms][kPcgMaxCtas][2];
+    // the totals come back through one mailbox per CTA (same layout): thousands of threads polling ONE line would be served serially
+    // by its L2 slice (measured: 8-10 us per exchange), private lines are polled by one CTA each
+    unsigned long long mbox[2][kPcgTerms][kPcgMaxCtas][2];
+    unsigned int abort;              // a bounded spin timed out: every CTA leaves at its next synchronisation point
+    unsigned int halo_count[2];      // boundary-plane rows pushed to the left / right neighbour in the current exchange
+    unsigned int pad;
+    unsigned long long dbg[6][kPcgMaxCtas];   // iteration kPcgDbgIter: %globaltimer of every CTA at the start / end of its share of the three phases
+    unsigned long long t_ns[8];      // CTA 0's view: ns in the product / update / p-update phases (synchronisation included), iterations,
+                                     // and the part of each phase CTA 0 spent inside the exchange (tail of the grid + latency)
 };
 
 struct PcgArgs {
     int rows, nslices, own_lo, own_hi, itrmax, warm;
     double eps;
     const long long* slice_ptr;
+    const int* perm;                 // SELL-C-sigma: row of every slot (-1 = padding lane); nullptr = natural order
     const void* sell_idx;
     const double* sell_val;
     const long long* indptr;         // canonical CSR (GetDiagonal, CG.h:398-404)
@@ -57,7 +69,6 @@ struct PcgArgs {
     const double* b;
     double *x, *r, *z, *p, *y, *dvec;
     CgState* st;
-    double* partials;
     PcgSync* sync;
     // row-block partition (peer-memory backend)
     const P2PView* p2p;
@@ -70,9 +81,6 @@ __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -84,238 +92,336 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
-// spin until *flag >= target (gpu scope); false = timed out or another CTA aborted
-__device__ __forceinline__ bool spin_u32(const unsigned int* flag, unsigned int target, PcgSync* sync) {
-    if (ld_relaxed_u32(flag) >= target) return true;
+// ---- LL words: a double travels as two 8-byte words {32 bits of the value, 32-bit flag}; an 8-byte store is single-copy atomic on
+// every path (L2, NVLink), so a reader that sees the flag sees the data: no fence, no separate flag write.
+template <bool SYS>
+__device__ __forceinline__ void ll_store(unsigned long long* slot, double v, unsigned int flag) {
+    const unsigned long long f = (unsigned long long)flag << 32;
+    const unsigned long long w0 = f | (unsigned int)__double2loint(v), w1 = f | (unsigned int)__double2hiint(v);
+    if (SYS) asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+    else asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+}
+template <bool SYS>
+__device__ __forceinline__ bool ll_try_load(const unsigned long long* slot, unsigned int flag, double& v) {
+    unsigned long long w0, w1;
+    if (SYS) asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+    else asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+    if ((unsigned int)(w0 >> 32) != flag || (unsigned int)(w1 >> 32) != flag) return false;
+    v = __hiloint2double((int)(unsigned int)w1, (int)(unsigned int)w0);
+    return true;
+}
+// bounded wait for an LL word; false = timed out or another CTA aborted (v is then meaningless)
+template <bool SYS>
+__device__ __forceinline__ bool ll_wait(const unsigned long long* slot, unsigned int flag, double& v, PcgSync* sync) {
+    if (ll_try_load<SYS>(slot, flag, v)) return true;
     const unsigned long long t0 = global_ns();
     for (unsigned int n = 1;; n++) {
-        if (ld_relaxed_u32(flag) >= target) return true;
-        if ((n & 255u) == 0u) {
+        if (PF2_PCG_BACKOFF > 0) __nanosleep(PF2_PCG_BACKOFF);
+        if (ll_try_load<SYS>(slot, flag, v)) return true;
+        if ((n & 63u) == 0u) {
             if (ld_relaxed_u32(&sync->abort)) return false;
             if (global_ns() - t0 > kSpinLimitNs) { atomicExch(&sync->abort, 1u); return false; }
         }
     }
 }
-// the same on a flag a PEER GPU writes (system scope)
+// the same on a plain 8-byte flag a PEER GPU raises (halo epochs)
 __device__ __forceinline__ bool spin_sys_u64(const unsigned long long* flag, unsigned long long target, PcgSync* sync) {
     if (ld_relaxed_sys_u64(flag) >= target) return true;
     const unsigned long long t0 = global_ns();
     for (unsigned int n = 1;; n++) {
         if (ld_relaxed_sys_u64(flag) >= target) return true;
-        if ((n & 255u) == 0u) {
+        if ((n & 63u) == 0u) {
             if (ld_relaxed_u32(&sync->abort)) return false;
             if (global_ns() - t0 > kSpinLimitNs) { atomicExch(&sync->abort, 1u); return false; }
         }
     }
 }
 
-// Allreduce (sum) of <= 4 fp64 across the box by ONE WARP, bounded spins (protocol of p2p_allreduce_warp, p2p.cuh).
-__device__ __forceinline__ void pcg_allreduce_warp(const P2PView& P, unsigned long long* epoch_ctr, double* vals, int count, PcgSync* sync) {
-    const int lane = threadIdx.x & 31;
-    const unsigned long long epoch = *(volatile unsigned long long*)epoch_ctr + 1;
-    const int par = (int)(epoch & 1ull);
-    if (lane < P.world) {
-        double* dst = P.slots[lane] + ((size_t)par * P.world + P.rank) * 4;
-        for (int c = 0; c < count; c++) dst[c] = vals[c];
-        __threadfence_system();
-        *(volatile unsigned long long*)(P.flags[lane] + (size_t)par * P.world + P.rank) = epoch;
-        spin_sys_u64(P.flags[P.rank] + (size_t)par * P.world + lane, epoch, sync);
-    }
-    __syncwarp();
-    __threadfence_system();
-    if (lane == 0) {
-        const volatile double* src = (const volatile double*)(P.slots[P.rank] + (size_t)par * P.world * 4);
-        for (int c = 0; c < count; c++) {
-            double acc = 0.0;
-            for (int r = 0; r < P.world; r++) acc += src[r * 4 + c];
-            vals[c] = acc;
-        }
-        *(volatile unsigned long long*)epoch_ctr = epoch;
-    }
-    __syncwarp();
-}
+// Per-thread synchronisation state: generation of the grid exchange, epoch of the cross-GPU one.
+struct PcgGen {
+    unsigned int gen;
+    unsigned long long xepoch;
+};
 
-// Grid barrier carrying a deterministic sum of NT terms (NT = 0: plain barrier).  On return every thread of the grid holds the
-// totals in v.  Returns false when the solve must be abandoned (a bounded spin timed out somewhere).
-template <int NT, bool DIST>
-__device__ __noinline__ bool grid_reduce_bcast(double* v, const PcgArgs& a, unsigned int& gen) {
-    __shared__ int s_last;
-    __shared__ double s_tot[4];
+// Grid-wide sum of NT terms (NT = 0: nothing to sum) delivered to every thread; FENCE: also a memory barrier (everything written
+// before it by any thread of the grid is visible to every thread after it).  Returns false when the solve must be abandoned.
+template <int NT, bool DIST, bool FENCE>
+__device__ __noinline__ bool grid_exchange(double* v, const PcgArgs& a, PcgGen& g) {
+    __shared__ double s_tot[kPcgTerms];
     PcgSync* sync = a.sync;
-    if constexpr (NT > 0) {
-        double w[NT];
+    constexpr int NW = NT > 0 ? NT : 1;          // words on the wire (a plain barrier sends one dummy)
+    const unsigned int gen = ++g.gen;
+    const int par = (int)(gen & 1u);
+    double w[NW];
 #pragma unroll
-        for (int t = 0; t < NT; t++) w[t] = v[t];
-        block_sum<NT>(w);
-        if (threadIdx.x == 0) {
-#pragma unroll
-            for (int t = 0; t < NT; t++) a.partials[(size_t)t * kMaxBlocks + blockIdx.x] = w[t];
-        }
-    } else {
-        __syncthreads();
-    }
+    for (int t = 0; t < NW; t++) w[t] = (t < NT) ? v[t] : 0.0;
+    block_sum<NW>(w);                            // ends with __syncthreads: every thread of the CTA has issued its stores
     if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = (atomicAdd(&sync->arrive, 1u) == gridDim.x - 1);
+        if (FENCE) __threadfence();              // release: the CTA's stores (cumulative over the bar.sync) before the arrival word
+#pragma unroll
+        for (int t = 0; t < NW; t++) ll_store<false>(&sync->part[par][t][blockIdx.x][0], w[t], gen);
     }
-    __syncthreads();
-    if (s_last) {
-        if constexpr (NT > 0) {
-            __threadfence();
-            double w[NT];
+    if (blockIdx.x == 0) {
+        // collector: partials in CTA order -> per-thread sums in a fixed order -> block sum: deterministic for a given grid.
+        // A thread's words are all requested before the first is examined (one L2 round trip when everybody has arrived).
+        constexpr int kPer = kPcgMaxCtas / kThreads;
+        double acc[NW], got[NW][kPer];
+        unsigned int pending = 0u;
 #pragma unroll
-            for (int t = 0; t < NT; t++) {
-                double acc = 0.0;
-                for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) acc += __ldcg(a.partials + (size_t)t * kMaxBlocks + b);
-                w[t] = acc;
-            }
-            block_sum<NT>(w);
-            if (threadIdx.x == 0) {
+        for (int j = 0; j < kPer; j++) {
+            const unsigned int c = threadIdx.x + j * kThreads;
+            if (c < gridDim.x) {
 #pragma unroll
-                for (int t = 0; t < NT; t++) s_tot[t] = w[t];
+                for (int t = 0; t < NW; t++) { got[t][j] = 0.0; if (!ll_try_load<false>(&sync->part[par][t][c][0], gen, got[t][j])) pending |= 1u << (j * NW + t); }
             }
-            __syncthreads();
-            if (DIST && threadIdx.x < 32) pcg_allreduce_warp(*a.p2p, a.epoch, s_tot, NT, sync);
         }
+#pragma unroll
+        for (int j = 0; j < kPer; j++) {
+            const unsigned int c = threadIdx.x + j * kThreads;
+#pragma unroll
+            for (int t = 0; t < NW; t++) if (pending & (1u << (j * NW + t))) ll_wait<false>(&sync->part[par][t][c][0], gen, got[t][j], sync);
+        }
+#pragma unroll
+        for (int t = 0; t < NW; t++) {
+            acc[t] = 0.0;
+#pragma unroll
+            for (int j = 0; j < kPer; j++) if (threadIdx.x + j * kThreads < gridDim.x) acc[t] += got[t][j];
+        }
+        block_sum<NW>(acc);
         if (threadIdx.x == 0) {
 #pragma unroll
-            for (int t = 0; t < NT; t++) sync->result[gen & 1u][t] = s_tot[t];
-            sync->arrive = 0u;
-            st_release_u32(&sync->release, gen + 1u);
+            for (int t = 0; t < NW; t++) s_tot[t] = acc[t];
         }
-    } else if (threadIdx.x == 0) {
-        spin_u32(&sync->release, gen + 1u, sync);
-    }
-    if (threadIdx.x == 0) __threadfence();          // acquire side: also drops this SM's L1 lines (CCTL.IVALL)
+        __syncthreads();
+        if (DIST && NT > 0 && threadIdx.x < 32) {
+            // cross-GPU: lane r sends this rank's totals to rank r and receives rank r's; lane 0 adds them in rank order
+            const P2PView& P = *a.p2p;
+            const unsigned long long epoch = g.xepoch + 1;
+            const unsigned int flag = (unsigned int)epoch;
+            const int xpar = (int)(epoch & 1ull), lane = threadIdx.x;
+            double got[NW];
+#pragma unroll
+            for (int t = 0; t < NW; t++) got[t] = 0.0;
+            if (lane < P.world) {
+#pragma unroll
+                for (int t = 0; t < NW; t++) ll_store<true>(P.ll[lane] + (((size_t)xpar * P.world + P.rank) * kPcgTerms + t) * 2, s_tot[t], flag);
+#pragma unroll
+                for (int t = 0; t < NW; t++) ll_wait<true>(P.ll[P.rank] + (((size_t)xpar * P.world + lane) * kPcgTerms + t) * 2, flag, got[t], sync);
+            }
+#pragma unroll
+            for (int t = 0; t < NW; t++) {
+                double sum = 0.0;
+                for (int r = 0; r < P.world; r++) sum += __shfl_sync(0xffffffffu, got[t], r);
+                if (lane == 0) s_tot[t] = sum;
+            }
+            __syncwarp();
+        }
+        if (DIST && NT > 0) g.xepoch++;
+        __syncthreads();
+        for (unsigned int c = threadIdx.x; c < gridDim.x; c += blockDim.x) {
+#pragma unroll
+            for (int t = 0; t < NW; t++) ll_store<false>(&sync->mbox[par][t][c][0], s_tot[t], gen);
+        }
+    } else if (DIST && NT > 0) g.xepoch++;
+    if (blockIdx.x != 0 && threadIdx.x < NW) { double x = 0.0; ll_wait<false>(&sync->mbox[par][threadIdx.x][blockIdx.x][0], gen, x, sync); s_tot[threadIdx.x] = x; }
+    if (FENCE && threadIdx.x == 0) __threadfence();      // acquire side: drops this SM's L1 lines (CCTL.IVALL)
     __syncthreads();
 #pragma unroll
-    for (int t = 0; t < NT; t++) v[t] = __ldcg(&sync->result[gen & 1u][t]);
-    gen++;
+    for (int t = 0; t < NT; t++) v[t] = s_tot[t];
+    __syncthreads();                                     // s_tot is reused by the next exchange
     return ld_relaxed_u32(&sync->abort) == 0u;
 }
 
-// y = A x over the slices [s_lo, s_hi) of this rank's owned rows, interior slices first; returns this thread's share of x.y over
-// the owned rows.  DIST: a warp that reaches a slice touching a boundary plane first waits for that neighbour's plane (epoch).
-template <class IDX, int NB, bool DIST, bool CS, bool DOT>
+// ---- slice ownership --------------------------------------------------------------------------------------------------------
+// Slices [s_lo, s_hi) hold this rank's owned rows; those holding rows of the first / last owned node plane (the send ranges, whose
+// columns reach the ghosts) are "boundary" slices.  Virtual order: interior slices first, then left boundary, then right boundary.
+// Warp w owns the virtual indices w, w + nwarps, ... in EVERY phase.
+struct PcgSlices {
+    int s_lo, s_lb, s_rb, s_hi, n_int, n_left, n_all;
+};
+template <bool DIST>
+__device__ __forceinline__ PcgSlices pcg_slices(const PcgArgs& a) {
+    PcgSlices S;
+    S.s_lo = a.own_lo / kSellC; S.s_hi = (a.own_hi + kSellC - 1) / kSellC;
+    S.s_lb = S.s_lo; S.s_rb = S.s_hi;
+    if (DIST) {
+        if (a.cntL > 0) S.s_lb = min(S.s_hi, (a.sendL + a.cntL + kSellC - 1) / kSellC);
+        if (a.cntR > 0) S.s_rb = max(S.s_lb, a.sendR / kSellC);
+    }
+    S.n_int = S.s_rb - S.s_lb; S.n_left = S.s_lb - S.s_lo; S.n_all = S.s_hi - S.s_lo;
+    return S;
+}
+// slice of virtual index v; side = 0 interior, 1 left boundary, 2 right boundary
+__device__ __forceinline__ int pcg_slice_of(const PcgSlices& S, int v, int& side) {
+    if (v < S.n_int) { side = 0; return S.s_lb + v; }
+    const int w = v - S.n_int;
+    if (w < S.n_left) { side = 1; return S.s_lo + w; }
+    side = 2;
+    return S.s_rb + (w - S.n_left);
+}
+__device__ __forceinline__ int pcg_row(const PcgArgs& a, int s, int lane) {
+    const int slot = s * kSellC + lane;
+    const int r = a.perm ? a.perm[slot] : (slot < a.rows ? slot : -1);
+    return (r >= a.own_lo && r < a.own_hi) ? r : -1;
+}
+
+// y = A x over the owned slices, interior first; returns this thread's share of x.y over its rows.  DIST: a warp that reaches a
+// boundary slice first waits for that neighbour's plane of the current halo epoch.
+template <class IDX, int NB, bool DIST, bool WAIT, bool CS, bool DOT>
 __device__ __noinline__ double pcg_product(const PcgArgs& a, const double* x, unsigned long long halo_epoch) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int s_lo = a.own_lo / kSellC, s_hi = (a.own_hi + kSellC - 1) / kSellC;
-    // boundary slices: those holding rows of the first / last owned node plane (the send ranges; their columns reach the ghosts)
-    int s_lb = s_lo, s_rb = s_hi;
-    if (DIST) {
-        if (a.cntL > 0) s_lb = min(s_hi, (a.sendL + a.cntL + kSellC - 1) / kSellC);
-        if (a.cntR > 0) s_rb = max(s_lb, a.sendR / kSellC);
-    }
-    const int n_int = s_rb - s_lb, n_left = s_lb - s_lo, n_all = s_hi - s_lo;
+    const PcgSlices S = pcg_slices<DIST>(a);
     bool waitedL = false, waitedR = false;
     double dot = 0.0;
-    for (int v = warp; v < n_all; v += nwarps) {
-        int s;
-        if (v < n_int) s = s_lb + v;
-        else {
-            const int w = v - n_int;
-            const bool left = w < n_left;
-            s = left ? s_lo + w : s_rb + (w - n_left);
-            if (DIST) {
-                bool& waited = left ? waitedL : waitedR;
-                if (!waited) {
+    for (int v = warp; v < S.n_all; v += nwarps) {
+        int side;
+        const int s = pcg_slice_of(S, v, side);
+        if (DIST && WAIT && side != 0) {
+            // a slab thinner than two planes has slices that touch both ghost planes: wait for both sides then
+            const bool needL = (side == 1 || S.n_int == 0) && a.cntL > 0 && !waitedL;
+            const bool needR = (side == 2 || S.n_int == 0) && a.cntR > 0 && !waitedR;
+            if (needL || needR) {
+                if (lane == 0) {
                     const unsigned long long* mine = a.p2p->halo_flags[a.p2p->rank];
-                    if (lane == 0) { spin_sys_u64(mine + (left ? 0 : 1), halo_epoch, a.sync); __threadfence_system(); }
-                    __syncwarp();
-                    waited = true;
-                    // a slice can hold rows of both planes when the slab is a single plane thick: wait for both sides
-                    if (n_int == 0) {
-                        if (lane == 0) {
-                            if (a.cntL > 0) spin_sys_u64(mine + 0, halo_epoch, a.sync);
-                            if (a.cntR > 0) spin_sys_u64(mine + 1, halo_epoch, a.sync);
-                            __threadfence_system();
-                        }
-                        __syncwarp();
-                        waitedL = waitedR = true;
-                    }
+                    if (needL) spin_sys_u64(mine + 0, halo_epoch, a.sync);
+                    if (needR) spin_sys_u64(mine + 1, halo_epoch, a.sync);
+                    __threadfence_system();          // acquire: the planes the neighbour stored before raising the flag; drops stale L1 lines
                 }
+                __syncwarp();
+                waitedL = waitedL || needL; waitedR = waitedR || needR;
             }
         }
         const long long base = a.slice_ptr[s];
         const int width = (int)((a.slice_ptr[s + 1] - base) / kSellC);
-        const int r = (s * kSellC + lane < a.rows) ? s * kSellC + lane : -1;
-        const double acc = sell_slice_acc<IDX, NB, 6, CS, false>((const IDX*)a.sell_idx, a.sell_val, x, base, width, lane, r);
-        if (r >= a.own_lo && r < a.own_hi) {
-            a.y[r] = acc;
-            if (DOT) dot += acc * x[r];
+        const int slot = s * kSellC + lane;
+        const int rr = a.perm ? a.perm[slot] : (slot < a.rows ? slot : -1);
+        const double acc = sell_slice_acc<IDX, NB, 6, CS, false>((const IDX*)a.sell_idx, a.sell_val, x, base, width, lane, rr);
+        if (rr >= a.own_lo && rr < a.own_hi) {
+            a.y[rr] = acc;
+            if (DOT) dot += acc * x[rr];
         }
     }
     return dot;
 }
 
-// Push the boundary planes of p into the neighbours' ghost ranges and publish the halo epoch.  CTAs [0, nL) serve the left
-// plane, [nL, nL + nR) the right one; the last CTA of a side to finish raises the flag at that neighbour.
-// UPDATE: p = beta p + z on those rows first (iteration); otherwise p already holds the values (set-up).
-template <bool UPDATE>
-__device__ __noinline__ void pcg_push_halo(const PcgArgs& a, const double* zsrc, double beta, unsigned long long epoch) {
-    const P2PView& P = *a.p2p;
-    const int per = 2 * kThreads;
-    int nL = a.cntL > 0 ? min((a.cntL + per - 1) / per, max(1, (int)gridDim.x / 4)) : 0;
-    int nR = a.cntR > 0 ? min((a.cntR + per - 1) / per, max(1, (int)gridDim.x / 4)) : 0;
-    if (nL + nR > (int)gridDim.x) { nL = a.cntL > 0 ? 1 : 0; nR = 0; }      // tiny grids: CTA 0 serves both sides in turn
-    const bool tiny = (a.cntR > 0 && nR == 0);
-    for (int side = 0; side < 2; side++) {
-        const int cnt = side == 0 ? a.cntL : a.cntR;
-        if (cnt <= 0) continue;
-        const int first = side == 0 ? 0 : (tiny ? 0 : nL), ncta = side == 0 ? nL : (tiny ? 1 : nR);
-        const int me = (int)blockIdx.x - first;
-        if (me < 0 || me >= ncta) continue;
-        const int send = side == 0 ? a.sendL : a.sendR;
-        double* dst = side == 0 ? P.left_p + P.left_recv_off : P.right_p + P.right_recv_off;
-        for (int j = me * kThreads + threadIdx.x; j < cnt; j += ncta * kThreads) {
-            const int i = send + j;
-            double v = a.p[i];
-            if (UPDATE) { v = beta * v + zsrc[i]; a.p[i] = v; }
-            dst[j] = v;
+// x += alpha p ; r -= alpha y ; z = r / D ; this thread's share of {z.r, r.r}   (CG.h:434-437, 443).  Owner rows only.
+template <int MODE, bool DIST>
+__device__ __noinline__ void pcg_update(const PcgArgs& a, double alpha, double* w) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const PcgSlices S = pcg_slices<DIST>(a);
+    double* __restrict__ x = a.x;
+    double* __restrict__ r = a.r;
+    double* __restrict__ z = a.z;
+    const double* p = a.p;
+    const double* y = a.y;
+    const double* dv = a.dvec;
+    double zr = 0.0, rr = 0.0;
+    for (int v = warp; v < S.n_all; v += 2 * nwarps) {
+        int side;
+        int i[2];
+        i[0] = pcg_row(a, pcg_slice_of(S, v, side), lane);
+        i[1] = (v + nwarps < S.n_all) ? pcg_row(a, pcg_slice_of(S, v + nwarps, side), lane) : -1;
+        double xi[2], pi[2], ri[2], yi[2], di[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int k = max(i[u], 0);
+            xi[u] = x[k]; pi[u] = p[k]; ri[u] = r[k]; yi[u] = y[k];
+            di[u] = (MODE == 1) ? dv[k] : 1.0;
         }
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            if (atomicAdd(&a.sync->halo_arrive[side], 1u) == (unsigned int)ncta - 1u) {
-                a.sync->halo_arrive[side] = 0u;
-                __threadfence_system();
-                // I am the RIGHT neighbour of rank-1 (slot 1 there) and the LEFT neighbour of rank+1 (slot 0 there)
-                unsigned long long* flag = side == 0 ? P.halo_flags[P.rank - 1] + 1 : P.halo_flags[P.rank + 1] + 0;
-                *(volatile unsigned long long*)flag = epoch;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            if (i[u] < 0) continue;
+            const double xn = xi[u] + alpha * pi[u];
+            const double rn = ri[u] + (-alpha) * yi[u];
+            x[i[u]] = xn; r[i[u]] = rn;
+            rr += rn * rn;
+            if (MODE == 0) zr += rn * rn;
+            else { const double zi = rn / di[u]; z[i[u]] = zi; zr += zi * rn; }
+        }
+    }
+    w[0] = zr; w[1] = rr;
+}
+
+// p = beta p + z on the owner rows (CG.h:439), boundary slices first.  DIST: rows of a send range also go straight into the
+// neighbour's ghost range; the warp that completes a plane raises that neighbour's halo flag.  INIT: p already holds its values.
+template <bool DIST, bool INIT>
+__device__ __noinline__ void pcg_pupdate(const PcgArgs& a, const double* zv, double beta, unsigned long long halo_epoch) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const PcgSlices S = pcg_slices<DIST>(a);
+    if (S.n_all <= warp) return;
+    double* __restrict__ p = a.p;
+    if (DIST) {
+        // boundary slices of this warp (virtual indices >= n_int), then publish
+        int pushed[2] = { 0, 0 };
+        const P2PView& P = *a.p2p;
+        int vb = warp;
+        if (vb < S.n_int) vb += ((S.n_int - vb + nwarps - 1) / nwarps) * nwarps;
+        for (int v = vb; v < S.n_all; v += nwarps) {
+            int side;
+            const int i = pcg_row(a, pcg_slice_of(S, v, side), lane);
+            if (i < 0) continue;
+            double pi = p[i];
+            if (!INIT) { pi = beta * pi + zv[i]; p[i] = pi; }
+            if (i >= a.sendL && i < a.sendL + a.cntL) { P.left_p[P.left_recv_off + (i - a.sendL)] = pi; pushed[0]++; }
+            if (i >= a.sendR && i < a.sendR + a.cntR) { P.right_p[P.right_recv_off + (i - a.sendR)] = pi; pushed[1]++; }
+        }
+        const int nl = __reduce_add_sync(0xffffffffu, pushed[0]), nr = __reduce_add_sync(0xffffffffu, pushed[1]);
+        if (nl + nr > 0) {
+            __threadfence_system();              // the pushed rows are visible at the neighbours before they are accounted for
+            __syncwarp();
+            if (lane == 0) {
+                if (nl > 0 && atomicAdd(&a.sync->halo_count[0], (unsigned int)nl) + nl == (unsigned int)a.cntL) {
+                    a.sync->halo_count[0] = 0u;
+                    *(volatile unsigned long long*)(P.halo_flags[P.rank - 1] + 1) = halo_epoch;      // I am the RIGHT neighbour of rank-1
+                }
+                if (nr > 0 && atomicAdd(&a.sync->halo_count[1], (unsigned int)nr) + nr == (unsigned int)a.cntR) {
+                    a.sync->halo_count[1] = 0u;
+                    *(volatile unsigned long long*)(P.halo_flags[P.rank + 1] + 0) = halo_epoch;      // ... and the LEFT neighbour of rank+1
+                }
             }
         }
     }
+    if (INIT) return;
+    const int n_rest = DIST ? S.n_int : S.n_all;         // not partitioned: every slice is "interior"
+    for (int v = warp; v < n_rest; v += 4 * nwarps) {
+        int i[4];
+        double pi[4], zi[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            int side;
+            i[u] = (v + u * nwarps < n_rest) ? pcg_row(a, pcg_slice_of(S, v + u * nwarps, side), lane) : -1;
+            const int k = max(i[u], 0);
+            pi[u] = p[k]; zi[u] = zv[k];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (i[u] >= 0) p[i[u]] = beta * pi[u] + zi[u];
+    }
 }
 
-// MODE 0: CG (z = r), 1: ScalingCG (z = r / diag).  Launch cooperatively with gridDim.x <= resident CTAs.
-template <class IDX, int NB, int MODE, bool DIST, bool CS>
-__global__ void __launch_bounds__(kThreads, PF2_PCG_MINB)
-pcg_persistent_kernel(const __grid_constant__ PcgArgs a) {
+// set-up on the owner rows: r = b - A x0 (y holds A x0 of a warm start), D, z = r / D, p = z; share of {b.b, z.r, r.r}  (CG.h:422-428)
+template <int MODE, bool DIST>
+__device__ __noinline__ void pcg_setup(const PcgArgs& a, double* v) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    const int lo = a.own_lo, hi = a.own_hi;
-    double* const zv = (MODE == 1) ? a.z : a.r;
-    unsigned int gen = 0;
-    unsigned long long halo_epoch = 0;
-    if (DIST) halo_epoch = *(volatile unsigned long long*)(a.epoch + 1);
-    const bool timing = (blockIdx.x == 0 && threadIdx.x == 0);
-    unsigned long long t_acc[3] = { 0ull, 0ull, 0ull }, t_prev = 0ull;
-    bool ok = true;
-
-    // ---- set-up (CG.h:422-428) ---------------------------------------------------------------------------------------
-    if (a.warm) {
-        // r = b - A x0: the ghost entries of x0 are valid (they were exchanged with the previous solution)
-        pcg_product<IDX, NB, false, CS, false>(a, a.x, 0ull);
-        ok = grid_reduce_bcast<0, DIST>(nullptr, a, gen);
-    }
-    double v[3] = { 0.0, 0.0, 0.0 };
+    const int lane = threadIdx.x & 31;
+    const int warp = tid >> 5, nwarps = nth >> 5;
+    const PcgSlices S = pcg_slices<DIST>(a);
+    // ghost rows (partitioned matrix): p arrives by halo exchange, x of a cold start is defined as 0, the rest is never read
     for (int i = tid; i < a.rows; i += nth) {
-        if (i < lo || i >= hi) {            // ghost rows: p arrives by halo exchange, the rest is never read
-            if (!a.warm) a.x[i] = 0.0;
-            a.p[i] = 0.0;
-            continue;
-        }
+        if (i >= a.own_lo && i < a.own_hi) continue;
+        if (!a.warm) a.x[i] = 0.0;
+        a.p[i] = 0.0;
+    }
+    double bb = 0.0, zr = 0.0, rr = 0.0;
+    for (int vv = warp; vv < S.n_all; vv += nwarps) {
+        int side;
+        const int i = pcg_row(a, pcg_slice_of(S, vv, side), lane);
+        if (i < 0) continue;
         const double bi = a.b[i];
         double ri = bi;
         if (a.warm) ri = bi - a.y[i]; else a.x[i] = 0.0;
@@ -329,9 +435,29 @@ pcg_persistent_kernel(const __grid_constant__ PcgArgs a) {
             a.z[i] = zi;
         }
         a.p[i] = zi;
-        v[0] += bi * bi; v[1] += zi * ri; v[2] += ri * ri;
+        bb += bi * bi; zr += zi * ri; rr += ri * ri;
     }
-    ok = grid_reduce_bcast<3, DIST>(v, a, gen) && ok;
+    v[0] = bb; v[1] = zr; v[2] = rr;
+}
+
+// MODE 0: CG (z = r), 1: ScalingCG (z = r / diag).  Launch cooperatively with gridDim.x <= min(resident CTAs, kPcgMaxCtas).
+template <class IDX, int NB, int MODE, bool DIST, bool CS>
+__global__ void __launch_bounds__(kThreads, PF2_PCG_MINB)
+pcg_persistent_kernel(const __grid_constant__ PcgArgs a) {
+    double* const zv = (MODE == 1) ? a.z : a.r;
+    PcgGen g;
+    g.gen = 0u;
+    g.xepoch = DIST ? *(volatile unsigned long long*)(a.epoch + 0) : 0ull;
+    unsigned long long halo_epoch = DIST ? *(volatile unsigned long long*)(a.epoch + 1) : 0ull;
+    const bool timing = (blockIdx.x == 0 && threadIdx.x == 0);
+    unsigned long long t_acc[6] = { 0ull, 0ull, 0ull, 0ull, 0ull, 0ull }, t_prev = 0ull, t_x = 0ull;
+    bool ok = true;
+
+    // ---- set-up (CG.h:422-428) ---------------------------------------------------------------------------------------
+    if (a.warm) pcg_product<IDX, NB, DIST, false, CS, false>(a, a.x, 0ull);     // y = A x0 (ghost entries of x0 are valid); owner rows only
+    double v[3];
+    pcg_setup<MODE, DIST>(a, v);
+    ok = grid_exchange<3, DIST, true>(v, a, g);
     const double bb = v[0];
     double rho = v[1], rr = v[2], beta = 0.0;
     int iter = 0;
@@ -339,29 +465,30 @@ pcg_persistent_kernel(const __grid_constant__ PcgArgs a) {
     bool done = a.warm && (sqrt(rr) < a.eps * sqrt(bb));
     if (DIST && ok && !done) {
         halo_epoch++;
-        pcg_push_halo<false>(a, nullptr, 0.0, halo_epoch);
-        ok = grid_reduce_bcast<0, DIST>(nullptr, a, gen);
+        pcg_pupdate<true, true>(a, nullptr, 0.0, halo_epoch);            // first exchange of the boundary planes of p
     }
     if (timing) t_prev = global_ns();
 
     // ---- iterations (CG.h:430-449) -------------------------------------------------------------------------------------
     while (ok && !done && iter < a.itrmax) {
         double d1[1];
-        d1[0] = pcg_product<IDX, NB, DIST, CS, true>(a, a.p, halo_epoch);
-        ok = grid_reduce_bcast<1, DIST>(d1, a, gen);
+        const bool dbg = (iter == kPcgDbgIter && threadIdx.x == 0);
+        if (dbg) a.sync->dbg[0][blockIdx.x] = global_ns();
+        d1[0] = pcg_product<IDX, NB, DIST, DIST, CS, true>(a, a.p, halo_epoch);
+        if (dbg) a.sync->dbg[1][blockIdx.x] = global_ns();
+        if (timing) t_x = global_ns();
+        ok = grid_exchange<1, DIST, false>(d1, a, g);
+        if (timing) t_acc[3] += global_ns() - t_x;
         if (!ok) break;
         if (timing) { const unsigned long long t = global_ns(); t_acc[0] += t - t_prev; t_prev = t; }
         const double alpha = rho / d1[0];
-        double w[2] = { 0.0, 0.0 };
-        for (int i = lo + tid; i < hi; i += nth) {
-            a.x[i] = a.x[i] + alpha * a.p[i];
-            const double ri = a.r[i] + (-alpha) * a.y[i];
-            a.r[i] = ri;
-            w[1] += ri * ri;
-            if (MODE == 0) w[0] += ri * ri;
-            else { const double zi = ri / a.dvec[i]; a.z[i] = zi; w[0] += zi * ri; }
-        }
-        ok = grid_reduce_bcast<2, DIST>(w, a, gen);
+        double w[2];
+        if (dbg) a.sync->dbg[2][blockIdx.x] = global_ns();
+        pcg_update<MODE, DIST>(a, alpha, w);
+        if (dbg) a.sync->dbg[3][blockIdx.x] = global_ns();
+        if (timing) t_x = global_ns();
+        ok = grid_exchange<2, DIST, false>(w, a, g);
+        if (timing) t_acc[4] += global_ns() - t_x;
         if (!ok) break;
         if (timing) { const unsigned long long t = global_ns(); t_acc[1] += t - t_prev; t_prev = t; }
         beta = w[0] / rho;
@@ -370,20 +497,22 @@ pcg_persistent_kernel(const __grid_constant__ PcgArgs a) {
         iter++;
         if (sqrt(rr) < a.eps * sqrt(bb)) { done = true; break; }
         if (iter >= a.itrmax) break;
-        if (DIST) { halo_epoch++; pcg_push_halo<true>(a, zv, beta, halo_epoch); }
-        for (int i = lo + tid; i < hi; i += nth) {
-            if (DIST && ((i >= a.sendL && i < a.sendL + a.cntL) || (i >= a.sendR && i < a.sendR + a.cntR))) continue;   // pushed above
-            a.p[i] = beta * a.p[i] + zv[i];
-        }
-        ok = grid_reduce_bcast<0, DIST>(nullptr, a, gen);
+        if (DIST) halo_epoch++;
+        if (dbg) a.sync->dbg[4][blockIdx.x] = global_ns();
+        pcg_pupdate<DIST, false>(a, zv, beta, halo_epoch);
+        if (dbg) a.sync->dbg[5][blockIdx.x] = global_ns();
+        if (timing) t_x = global_ns();
+        ok = grid_exchange<0, DIST, true>(nullptr, a, g);
+        if (timing) t_acc[5] += global_ns() - t_x;
         if (timing) { const unsigned long long t = global_ns(); t_acc[2] += t - t_prev; t_prev = t; }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         CgState* st = a.st;
         st->bb = bb; st->rr = rr; st->rho = rho; st->beta = beta; st->pAp = 0.0;
         st->iter = iter; st->done = ok ? (done ? 1 : 0) : 2; st->maxit = a.itrmax; st->eps = a.eps;
-        if (DIST) *(volatile unsigned long long*)(a.epoch + 1) = halo_epoch;
+        if (DIST) { *(volatile unsigned long long*)(a.epoch + 0) = g.xepoch; *(volatile unsigned long long*)(a.epoch + 1) = halo_epoch; }
         a.sync->t_ns[0] = t_acc[0]; a.sync->t_ns[1] = t_acc[1]; a.sync->t_ns[2] = t_acc[2]; a.sync->t_ns[3] = (unsigned long long)iter;
+        a.sync->t_ns[4] = t_acc[3]; a.sync->t_ns[5] = t_acc[4]; a.sync->t_ns[6] = t_acc[5]; a.sync->t_ns[7] = 0ull;
     }
 }
 

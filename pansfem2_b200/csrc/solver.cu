@@ -565,13 +565,15 @@ int pf2_csr_solver_stats_reset(pf2_csr* A) {
     A->prof_ms[0] = A->prof_ms[1] = A->prof_ms[2] = 0.0; A->prof_samples = 0; A->total_iters = 0;
     A->pcg_kernel_ms = 0.0; A->pcg_iters = 0; A->pcg_solves = 0;
     A->pcg_phase_ns[0] = A->pcg_phase_ns[1] = A->pcg_phase_ns[2] = 0.0;
+    A->pcg_wait_ns[0] = A->pcg_wait_ns[1] = A->pcg_wait_ns[2] = 0.0;
     return PF2_OK;
 }
-int pf2_csr_pcg_stats(pf2_csr* A, double out[8]) {
+int pf2_csr_pcg_stats(pf2_csr* A, double out[12]) {
     out[0] = A->pcg_kernel_ms; out[1] = (double)A->pcg_iters; out[2] = (double)A->pcg_solves; out[3] = (double)A->pcg_grid;
     const double ki = A->pcg_iters ? 1.0e-6 / (double)A->pcg_iters : 0.0;
-    for (int j = 0; j < 3; j++) out[4 + j] = A->pcg_phase_ns[j] * ki;
+    for (int j = 0; j < 3; j++) { out[4 + j] = A->pcg_phase_ns[j] * ki; out[8 + j] = A->pcg_wait_ns[j] * ki; }
     out[7] = (double)A->sell_entries;
+    out[11] = 0.0;
     return PF2_OK;
 }
 

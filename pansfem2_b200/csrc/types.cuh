@@ -62,6 +62,7 @@ struct P2PView {          // must match pf2::P2P in dist.cu (kept POD here so th
     double* left_p;
     double* right_p;
     int left_recv_off, right_recv_off;
+    unsigned long long* ll[kMaxRanksT];    // LL words of the persistent PCG kernel's cross-GPU sums: [parity][sender][4 terms][2 halves]
 };
 }  // namespace pf2
 
@@ -146,7 +147,7 @@ struct pf2_csr {
     int pcg_grid = 0;                  // CTAs of the last persistent launch
     double pcg_kernel_ms = 0.0;        // CUDA-event time of the persistent kernels since the last statistics reset
     long long pcg_iters = 0, pcg_solves = 0;
-    double pcg_phase_ns[3] = { 0, 0, 0 };
+    double pcg_phase_ns[3] = { 0, 0, 0 }, pcg_wait_ns[3] = { 0, 0, 0 };
     double prof_ms[3] = { 0, 0, 0 };   // spmv+dot, update, p-update
     long long prof_samples = 0;
     long long total_iters = 0;

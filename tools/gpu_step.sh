@@ -16,6 +16,19 @@ for stage in "$@"; do
     pcg0)    PF2_PCG=0 timeout 600 python bench.py --steps 3 --warmup 2 --no-hex8 --no-extra-legs --no-cpu-baseline > "$out/bench_pcg0.json" 2> "$out/bench_pcg0.err"; tail -c 1500 "$out/bench_pcg0.json" ;;
     full)    timeout 1500 python bench.py --steps 20 --warmup 5 --record "$out/record_full.json" > "$out/bench_full.json" 2> "$out/bench_full.err"; tail -c 4000 "$out/bench_full.json"; tail -5 "$out/bench_full.err" ;;
     ref)     timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > "$out/bench_ref.json" 2> "$out/bench_ref.err"; tail -c 2500 "$out/bench_ref.json" ;;
+    san)     timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_pcg.py -x -q -k "three_kernel or iteration_cap or one_rank" > "$out/san_memcheck.log" 2>&1; echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|passed|failed" "$out/san_memcheck.log" | tail -3
+             timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_pcg.py -x -q -k "three_kernel and lambda3" > "$out/san_racecheck.log" 2>&1; echo "racecheck rc=$?"; grep -E "RACECHECK SUMMARY|passed|failed" "$out/san_racecheck.log" | tail -3 ;;
+    tune)    for w in ${TUNE_W:-2m c2 c4s}; do
+               PF2_PCG=0 timeout 120 python tools/pcg_tune.py $w 2>&1 | tail -1 | tee -a "$out/tune.jsonl"
+               for lib in pansfem2_b200/bin/libpf2_*.so; do PF2_LIB=$PWD/$lib timeout 120 python tools/pcg_tune.py $w 2>&1 | tail -1 | tee -a "$out/tune.jsonl"; done
+             done ;;
+    tune2)   for w in ${TUNE_W:-2m}; do
+               for lib in pansfem2_b200/bin/libpf2_*.so; do for g in 0 592 444 296; do
+                 PF2_PCG_GRID=$g PF2_LIB=$PWD/$lib timeout 120 python tools/pcg_tune.py $w 2>&1 | tail -1 | tee -a "$out/tune2.jsonl"; done; done
+             done ;;
+    dist2)   timeout 900 python -m pytest tests/test_gpu_dist.py -x -q -rs > "$out/dist2.log" 2>&1; tail -12 "$out/dist2.log" ;;
+    small)   for w in c1 pair c4s; do for m in 0 1; do PF2_PCG=$m timeout 120 python tools/pcg_tune.py $w 2 2>&1 | tail -1 | tee -a "$out/small.jsonl"; done; done ;;
+    b2)      for m in 1 0; do PF2_PCG=$m timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 2 --no-hex8 --no-extra-legs --no-headline-2m > "$out/bench_n2_pcg$m.json" 2> "$out/bench_n2_pcg$m.err"; tail -c 1800 "$out/bench_n2_pcg$m.json"; tail -3 "$out/bench_n2_pcg$m.err"; done ;;
     *)       echo "unknown stage $stage" ;;
   esac
 done
