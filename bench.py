@@ -408,7 +408,8 @@ class Runner:
                             "achieved_GBps": spmv_bytes / (pcg["product_ms"] * 1e-3) / 1e9 if pcg["product_ms"] > 0 else None,
                             "frac": spmv_bytes / (pcg["product_ms"] * 1e-3) / 1e9 / peak if pcg["product_ms"] > 0 else None,
                             "note": "product phase of the persistent kernel incl. its grid barrier (+ allreduce at N > 1), %globaltimer of CTA 0",
-                            "update_phase_ms": pcg["update_ms"], "pupdate_phase_ms": pcg["pupdate_ms"]}}
+                            "update_phase_ms": pcg["update_ms"], "pupdate_phase_ms": pcg["pupdate_ms"],
+                            "exchange_wait_ms_cta0": [pcg["product_wait_ms"], pcg["update_wait_ms"], pcg["pupdate_wait_ms"]]}}
             if world == 1:
                 try:
                     ms_alone = A.spmv_bench(0, reps=10, flush_l2=(12 * nnz < 400e6))

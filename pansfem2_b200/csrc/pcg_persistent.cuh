@@ -33,10 +33,13 @@ namespace pf2 {
 #ifndef PF2_PCG_BACKOFF
 #define PF2_PCG_BACKOFF 0
 #endif
+// resident CTAs per SM the kernel is compiled for: 6 -> 40 registers (the product and the vector phases then run without spills inside
+// their loops; at 8 -> 32 registers ncu showed as much local-memory traffic as algorithmic traffic)
 #ifndef PF2_PCG_MINB
-#define PF2_PCG_MINB 8
+#define PF2_PCG_MINB 6
 #endif
-constexpr unsigned long long kSpinLimitNs = 4000000000ull;   // 4 s: three orders of magnitude above any legitimate wait
+constexpr long long kSpinLimitClk = 8000000000ll;     // ~4 s of SM clocks: three orders of magnitude above any legitimate wait
+// (timeouts use clock64: %globaltimer costs a long round trip and must stay off the exchange's critical path)
 
 constexpr int kPcgMaxCtas = 2048;        // >= CTAs of any cooperative grid on this part (148 SMs x 8)
 constexpr int kPcgTerms = 4;
@@ -114,25 +117,26 @@ __device__ __forceinline__ bool ll_try_load(const unsigned long long* slot, unsi
 template <bool SYS>
 __device__ __forceinline__ bool ll_wait(const unsigned long long* slot, unsigned int flag, double& v, PcgSync* sync) {
     if (ll_try_load<SYS>(slot, flag, v)) return true;
-    const unsigned long long t0 = global_ns();
+    long long t0 = 0;
     for (unsigned int n = 1;; n++) {
-        if (PF2_PCG_BACKOFF > 0) __nanosleep(PF2_PCG_BACKOFF);
         if (ll_try_load<SYS>(slot, flag, v)) return true;
-        if ((n & 63u) == 0u) {
+        if ((n & 1023u) == 0u) {
+            if (t0 == 0) t0 = clock64();
             if (ld_relaxed_u32(&sync->abort)) return false;
-            if (global_ns() - t0 > kSpinLimitNs) { atomicExch(&sync->abort, 1u); return false; }
+            if (clock64() - t0 > kSpinLimitClk) { atomicExch(&sync->abort, 1u); return false; }
         }
     }
 }
 // the same on a plain 8-byte flag a PEER GPU raises (halo epochs)
 __device__ __forceinline__ bool spin_sys_u64(const unsigned long long* flag, unsigned long long target, PcgSync* sync) {
     if (ld_relaxed_sys_u64(flag) >= target) return true;
-    const unsigned long long t0 = global_ns();
+    long long t0 = 0;
     for (unsigned int n = 1;; n++) {
         if (ld_relaxed_sys_u64(flag) >= target) return true;
-        if ((n & 63u) == 0u) {
+        if ((n & 1023u) == 0u) {
+            if (t0 == 0) t0 = clock64();
             if (ld_relaxed_u32(&sync->abort)) return false;
-            if (global_ns() - t0 > kSpinLimitNs) { atomicExch(&sync->abort, 1u); return false; }
+            if (clock64() - t0 > kSpinLimitClk) { atomicExch(&sync->abort, 1u); return false; }
         }
     }
 }
@@ -148,7 +152,9 @@ struct PcgGen {
 template <int NT, bool DIST, bool FENCE>
 __device__ __noinline__ bool grid_exchange(double* v, const PcgArgs& a, PcgGen& g) {
     __shared__ double s_tot[kPcgTerms];
+    __shared__ int s_bad;
     PcgSync* sync = a.sync;
+    if (threadIdx.x == 0) s_bad = 0;
     constexpr int NW = NT > 0 ? NT : 1;          // words on the wire (a plain barrier sends one dummy)
     const unsigned int gen = ++g.gen;
     const int par = (int)(gen & 1u);
@@ -179,7 +185,7 @@ __device__ __noinline__ bool grid_exchange(double* v, const PcgArgs& a, PcgGen& 
         for (int j = 0; j < kPer; j++) {
             const unsigned int c = threadIdx.x + j * kThreads;
 #pragma unroll
-            for (int t = 0; t < NW; t++) if (pending & (1u << (j * NW + t))) ll_wait<false>(&sync->part[par][t][c][0], gen, got[t][j], sync);
+            for (int t = 0; t < NW; t++) if (pending & (1u << (j * NW + t))) { if (!ll_wait<false>(&sync->part[par][t][c][0], gen, got[t][j], sync)) s_bad = 1; }
         }
 #pragma unroll
         for (int t = 0; t < NW; t++) {
@@ -206,7 +212,7 @@ __device__ __noinline__ bool grid_exchange(double* v, const PcgArgs& a, PcgGen& 
 #pragma unroll
                 for (int t = 0; t < NW; t++) ll_store<true>(P.ll[lane] + (((size_t)xpar * P.world + P.rank) * kPcgTerms + t) * 2, s_tot[t], flag);
 #pragma unroll
-                for (int t = 0; t < NW; t++) ll_wait<true>(P.ll[P.rank] + (((size_t)xpar * P.world + lane) * kPcgTerms + t) * 2, flag, got[t], sync);
+                for (int t = 0; t < NW; t++) { if (!ll_wait<true>(P.ll[P.rank] + (((size_t)xpar * P.world + lane) * kPcgTerms + t) * 2, flag, got[t], sync)) s_bad = 1; }
             }
 #pragma unroll
             for (int t = 0; t < NW; t++) {
@@ -223,13 +229,18 @@ __device__ __noinline__ bool grid_exchange(double* v, const PcgArgs& a, PcgGen& 
             for (int t = 0; t < NW; t++) ll_store<false>(&sync->mbox[par][t][c][0], s_tot[t], gen);
         }
     } else if (DIST && NT > 0) g.xepoch++;
-    if (blockIdx.x != 0 && threadIdx.x < NW) { double x = 0.0; ll_wait<false>(&sync->mbox[par][threadIdx.x][blockIdx.x][0], gen, x, sync); s_tot[threadIdx.x] = x; }
+    if (blockIdx.x != 0 && threadIdx.x < NW) {
+        double x = 0.0;
+        if (!ll_wait<false>(&sync->mbox[par][threadIdx.x][blockIdx.x][0], gen, x, sync)) s_bad = 1;
+        s_tot[threadIdx.x] = x;
+    }
     if (FENCE && threadIdx.x == 0) __threadfence();      // acquire side: drops this SM's L1 lines (CCTL.IVALL)
     __syncthreads();
 #pragma unroll
     for (int t = 0; t < NT; t++) v[t] = s_tot[t];
-    __syncthreads();                                     // s_tot is reused by the next exchange
-    return ld_relaxed_u32(&sync->abort) == 0u;
+    const bool ok = (s_bad == 0);
+    __syncthreads();                                     // s_tot / s_bad are reused by the next exchange
+    return ok;
 }
 
 // ---- slice ownership --------------------------------------------------------------------------------------------------------
@@ -320,28 +331,17 @@ __device__ __noinline__ void pcg_update(const PcgArgs& a, double alpha, double* 
     const double* y = a.y;
     const double* dv = a.dvec;
     double zr = 0.0, rr = 0.0;
-    for (int v = warp; v < S.n_all; v += 2 * nwarps) {
+    for (int v = warp; v < S.n_all; v += nwarps) {
         int side;
-        int i[2];
-        i[0] = pcg_row(a, pcg_slice_of(S, v, side), lane);
-        i[1] = (v + nwarps < S.n_all) ? pcg_row(a, pcg_slice_of(S, v + nwarps, side), lane) : -1;
-        double xi[2], pi[2], ri[2], yi[2], di[2];
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int k = max(i[u], 0);
-            xi[u] = x[k]; pi[u] = p[k]; ri[u] = r[k]; yi[u] = y[k];
-            di[u] = (MODE == 1) ? dv[k] : 1.0;
-        }
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            if (i[u] < 0) continue;
-            const double xn = xi[u] + alpha * pi[u];
-            const double rn = ri[u] + (-alpha) * yi[u];
-            x[i[u]] = xn; r[i[u]] = rn;
-            rr += rn * rn;
-            if (MODE == 0) zr += rn * rn;
-            else { const double zi = rn / di[u]; z[i[u]] = zi; zr += zi * rn; }
-        }
+        const int i = pcg_row(a, pcg_slice_of(S, v, side), lane);
+        if (i < 0) continue;
+        const double xi = x[i], pi = p[i], ri = r[i], yi = y[i];
+        const double rn = ri + (-alpha) * yi;
+        x[i] = xi + alpha * pi;
+        r[i] = rn;
+        rr += rn * rn;
+        if (MODE == 0) zr += rn * rn;
+        else { const double zi = rn / dv[i]; z[i] = zi; zr += zi * rn; }
     }
     w[0] = zr; w[1] = rr;
 }
@@ -450,7 +450,9 @@ pcg_persistent_kernel(const __grid_constant__ PcgArgs a) {
     g.xepoch = DIST ? *(volatile unsigned long long*)(a.epoch + 0) : 0ull;
     unsigned long long halo_epoch = DIST ? *(volatile unsigned long long*)(a.epoch + 1) : 0ull;
     const bool timing = (blockIdx.x == 0 && threadIdx.x == 0);
-    unsigned long long t_acc[6] = { 0ull, 0ull, 0ull, 0ull, 0ull, 0ull }, t_prev = 0ull, t_x = 0ull;
+    // phase split in SM clocks (clock64 is local and cheap), converted with the kernel's own ns / clock ratio at the end
+    long long t_acc[6] = { 0, 0, 0, 0, 0, 0 }, t_prev = 0, t_x = 0, c_begin = 0;
+    unsigned long long ns_begin = 0ull;
     bool ok = true;
 
     // ---- set-up (CG.h:422-428) ---------------------------------------------------------------------------------------
@@ -467,7 +469,7 @@ pcg_persistent_kernel(const __grid_constant__ PcgArgs a) {
         halo_epoch++;
         pcg_pupdate<true, true>(a, nullptr, 0.0, halo_epoch);            // first exchange of the boundary planes of p
     }
-    if (timing) t_prev = global_ns();
+    if (timing) { ns_begin = global_ns(); c_begin = clock64(); t_prev = c_begin; }
 
     // ---- iterations (CG.h:430-449) -------------------------------------------------------------------------------------
     while (ok && !done && iter < a.itrmax) {
@@ -476,21 +478,21 @@ pcg_persistent_kernel(const __grid_constant__ PcgArgs a) {
         if (dbg) a.sync->dbg[0][blockIdx.x] = global_ns();
         d1[0] = pcg_product<IDX, NB, DIST, DIST, CS, true>(a, a.p, halo_epoch);
         if (dbg) a.sync->dbg[1][blockIdx.x] = global_ns();
-        if (timing) t_x = global_ns();
+        if (timing) t_x = clock64();
         ok = grid_exchange<1, DIST, false>(d1, a, g);
-        if (timing) t_acc[3] += global_ns() - t_x;
+        if (timing) t_acc[3] += clock64() - t_x;
         if (!ok) break;
-        if (timing) { const unsigned long long t = global_ns(); t_acc[0] += t - t_prev; t_prev = t; }
+        if (timing) { const long long t = clock64(); t_acc[0] += t - t_prev; t_prev = t; }
         const double alpha = rho / d1[0];
         double w[2];
         if (dbg) a.sync->dbg[2][blockIdx.x] = global_ns();
         pcg_update<MODE, DIST>(a, alpha, w);
         if (dbg) a.sync->dbg[3][blockIdx.x] = global_ns();
-        if (timing) t_x = global_ns();
+        if (timing) t_x = clock64();
         ok = grid_exchange<2, DIST, false>(w, a, g);
-        if (timing) t_acc[4] += global_ns() - t_x;
+        if (timing) t_acc[4] += clock64() - t_x;
         if (!ok) break;
-        if (timing) { const unsigned long long t = global_ns(); t_acc[1] += t - t_prev; t_prev = t; }
+        if (timing) { const long long t = clock64(); t_acc[1] += t - t_prev; t_prev = t; }
         beta = w[0] / rho;
         rho = w[0];
         rr = w[1];
@@ -501,18 +503,23 @@ pcg_persistent_kernel(const __grid_constant__ PcgArgs a) {
         if (dbg) a.sync->dbg[4][blockIdx.x] = global_ns();
         pcg_pupdate<DIST, false>(a, zv, beta, halo_epoch);
         if (dbg) a.sync->dbg[5][blockIdx.x] = global_ns();
-        if (timing) t_x = global_ns();
+        if (timing) t_x = clock64();
         ok = grid_exchange<0, DIST, true>(nullptr, a, g);
-        if (timing) t_acc[5] += global_ns() - t_x;
-        if (timing) { const unsigned long long t = global_ns(); t_acc[2] += t - t_prev; t_prev = t; }
+        if (timing) t_acc[5] += clock64() - t_x;
+        if (timing) { const long long t = clock64(); t_acc[2] += t - t_prev; t_prev = t; }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         CgState* st = a.st;
         st->bb = bb; st->rr = rr; st->rho = rho; st->beta = beta; st->pAp = 0.0;
         st->iter = iter; st->done = ok ? (done ? 1 : 0) : 2; st->maxit = a.itrmax; st->eps = a.eps;
         if (DIST) { *(volatile unsigned long long*)(a.epoch + 0) = g.xepoch; *(volatile unsigned long long*)(a.epoch + 1) = halo_epoch; }
-        a.sync->t_ns[0] = t_acc[0]; a.sync->t_ns[1] = t_acc[1]; a.sync->t_ns[2] = t_acc[2]; a.sync->t_ns[3] = (unsigned long long)iter;
-        a.sync->t_ns[4] = t_acc[3]; a.sync->t_ns[5] = t_acc[4]; a.sync->t_ns[6] = t_acc[5]; a.sync->t_ns[7] = 0ull;
+        const long long dclk = clock64() - c_begin;
+        const double ns_per_clk = dclk > 0 ? (double)(global_ns() - ns_begin) / (double)dclk : 0.0;
+        for (int j = 0; j < 3; j++) {
+            a.sync->t_ns[j] = (unsigned long long)((double)t_acc[j] * ns_per_clk);
+            a.sync->t_ns[4 + j] = (unsigned long long)((double)t_acc[3 + j] * ns_per_clk);
+        }
+        a.sync->t_ns[3] = (unsigned long long)iter; a.sync->t_ns[7] = 0ull;
     }
 }
 
