@@ -297,6 +297,14 @@ int sell_refresh(pf2_csr* A) {
     return PF2_OK;
 }
 
+// a slab whose SELL mirror (values + 16-bit deltas) fits the L2 next to the Krylov vectors is read with plain loads, so that it stays
+// resident from one product to the next (row-partitioned 2-D problems at 8 GPUs); larger ones stream through with evict-first loads
+static bool sell_l2_resident(const pf2_csr* A) {
+    static const double mb = getenv("PF2_SELL_L2_MB") ? atof(getenv("PF2_SELL_L2_MB")) : 115.0;
+    const double idx_bytes = A->sell_d16 ? 2.0 / A->sell_nb : 4.0 / A->sell_nb;
+    return (double)A->sell_entries * (8.0 + idx_bytes) + 40.0 * (double)A->rows <= mb * 1.0e6;
+}
+
 template <bool DOT>
 static int launch_sell(pf2_csr* A, const double* x, double* y, const CgState* st, double* dot_out) {
     pf2_ctx* c = A->ctx;
@@ -315,7 +323,15 @@ static int launch_sell(pf2_csr* A, const double* x, double* y, const CgState* st
         else { if (A->sell_perm) SELL(int, true, 2, A->sell_b32) else SELL(int, false, 2, A->sell_b32) }
     } else if (A->sell_d16) {
         if (A->sell_nb == 2) { if (A->sell_perm) SELL(short, true, 2, A->sell_d16) else SELL(short, false, 2, A->sell_d16) }
-        else if (A->sell_nb == 3) { if (A->sell_perm) SELL(short, true, 3, A->sell_d16) else SELL(short, false, 3, A->sell_d16) }
+        else if (A->sell_nb == 3) {
+            if (A->sell_perm) SELL(short, true, 3, A->sell_d16)
+            else if (DOT && sell_l2_resident(A)) {
+                const int grid = std::max(1, std::min(nb, c->wave_grid((const void*)spmv_sell_kernel<DOT, short, false, 3, 6, false>, kThreads)));
+                spmv_sell_kernel<DOT, short, false, 3, 6, false><<<grid, kThreads, 0, c->stream>>>(A->rows, A->sell_ptr, A->sell_perm, A->sell_d16, A->sell_val, x, y,
+                                                                                                st, dot_out, c->red.partials, c->red.ticket, A->own_lo,
+                                                                                                A->own_hi, A->p2p_dev, A->p2p_epoch);
+            } else SELL(short, false, 3, A->sell_d16)
+        }
         else if (A->sell_perm) SELL(short, true, 1, A->sell_d16)
         else {
             // independent loads in flight per lane and round; measured at 2 M dof: 3 -> 0.0843 ms, 6 -> 0.0778, 9 -> 0.0839, 18 -> 0.0895
@@ -327,7 +343,12 @@ static int launch_sell(pf2_csr* A, const double* x, double* y, const CgState* st
                                                                                      st, dot_out, c->red.partials, c->red.ticket, A->own_lo,     \
                                                                                      A->own_hi, A->p2p_dev, A->p2p_epoch);                       \
     }
-            if (unroll == 9) SELLU(9) else if (unroll == 18) SELLU(18) else if (unroll == 3) SELLU(3) else SELLU(6)
+            if (DOT && sell_l2_resident(A)) {
+                const int grid = std::max(1, std::min(nb, c->wave_grid((const void*)spmv_sell_kernel<DOT, short, false, 1, 6, false>, kThreads)));
+                spmv_sell_kernel<DOT, short, false, 1, 6, false><<<grid, kThreads, 0, c->stream>>>(A->rows, A->sell_ptr, A->sell_perm, A->sell_d16, A->sell_val, x, y,
+                                                                                                st, dot_out, c->red.partials, c->red.ticket, A->own_lo,
+                                                                                                A->own_hi, A->p2p_dev, A->p2p_epoch);
+            } else if (unroll == 9) SELLU(9) else if (unroll == 18) SELLU(18) else if (unroll == 3) SELLU(3) else SELLU(6)
 #undef SELLU
         }
     } else { if (A->sell_perm) SELL(int, true, 1, A->sell_idx) else SELL(int, false, 1, A->sell_idx) }

@@ -68,6 +68,7 @@ namespace pf2 {
 
 int spmv_dot(pf2_csr* A, const double* x, double* y, const CgState* st, double* dot_out);
 int ensure_workspace_pub(pf2_csr* A);
+int plan_spmv_pub(pf2_csr* A);
 
 #define PF2_NCCL(call)                                                                                   \
     do {                                                                                                 \
@@ -240,10 +241,14 @@ p2p_pupdate_halo_kernel(int lo, int hi, const double* __restrict__ z, double* __
         // I am the RIGHT neighbour of rank-1 (slot 1 there) and the LEFT neighbour of rank+1 (slot 0 there)
         if (P.rank > 0) *(volatile unsigned long long*)(P.halo_flags[P.rank - 1] + 1) = epoch;
         if (P.rank < P.world - 1) *(volatile unsigned long long*)(P.halo_flags[P.rank + 1] + 0) = epoch;
-        volatile unsigned long long* mine = (volatile unsigned long long*)P.halo_flags[P.rank];
-        if (P.rank > 0) while (mine[0] < epoch) {}
-        if (P.rank < P.world - 1) while (mine[1] < epoch) {}
-        __threadfence_system();
+        if (!P.defer_halo_wait) {
+            // wait here for the neighbours' planes (products that do not order their slices); otherwise the boundary slices of the
+            // next product wait, after its interior slices
+            const unsigned long long* mine = P.halo_flags[P.rank];
+            if (P.rank > 0) p2p_wait_flag(P, mine + 0, epoch);
+            if (P.rank < P.world - 1) p2p_wait_flag(P, mine + 1, epoch);
+            __threadfence_system();
+        }
         epoch_ctr[1] = epoch;
         *ticket = 0u;
     }
@@ -291,6 +296,15 @@ int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, d
     else dcg_init_kernel<1><<<grid, kThreads, 0, s>>>(lo, hi, n, b, A->indptr, A->diagpos, A->data, A->dvec, x, A->r, A->z, A->p, A->st, c->red.partials, c->red.ticket);
     PF2_LAUNCH_CHECK();
     const bool p2p = d->p2p && A->p2p_ready;
+    if (p2p) {
+        // products that order their slices (SELL-32, natural row order) take over the wait for the neighbours' planes
+        plan_spmv_pub(A);
+        const int defer = (A->spmv_variant == 31 && A->sell_perm == nullptr && getenv("PF2_HALO_NODEFER") == nullptr) ? 1 : 0;
+        if (defer != A->p2p_view.defer_halo_wait) {
+            A->p2p_view.defer_halo_wait = defer;
+            PF2_CUDA(cudaMemcpyAsync(A->p2p_dev, &A->p2p_view, sizeof(P2PView), cudaMemcpyHostToDevice, s));
+        }
+    }
     const int hgrid = std::min(c->grid_for(hi - lo, 2), c->sm_count * 4);
     if (p2p) {
         p2p_cg_scalars_kernel<<<1, 32, 0, s>>>(A->p2p_view, d->epoch, A->st, 1, itrmax, eps);
@@ -364,6 +378,11 @@ int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, d
     A->total_iters += last.iter;
     if (iters_out) *iters_out = last.iter;
     if (relres_out) *relres_out = sqrt(last.rr) / sqrt(last.bb);
+    if (p2p) {
+        unsigned long long aborted = 0;
+        PF2_CUDA(cudaMemcpy(&aborted, d->epoch + 2, sizeof aborted, cudaMemcpyDeviceToHost));
+        if (aborted) { set_error("partitioned PCG: a wait on a peer GPU timed out (a rank left the solve?)"); return PF2_E_CUDA; }
+    }
     if (!last.done) {
         set_error("Convergence:faild after %d iterations (relres %.3e)", last.iter, sqrt(last.rr) / sqrt(last.bb));
         return PF2_E_NOCONV;
@@ -427,8 +446,8 @@ int pf2_csr_p2p_export(pf2_csr* A, char handles_out[128]) {
     if (!d->arena) {
         PF2_CUDA(cudaMalloc(&d->arena, arena_bytes(d->nranks)));
         PF2_CUDA(cudaMemset(d->arena, 0, arena_bytes(d->nranks)));
-        PF2_CUDA(cudaMalloc((void**)&d->epoch, 2 * sizeof(unsigned long long)));
-        PF2_CUDA(cudaMemset(d->epoch, 0, 2 * sizeof(unsigned long long)));
+        PF2_CUDA(cudaMalloc((void**)&d->epoch, 4 * sizeof(unsigned long long)));      // [0] allreduce epoch, [1] halo epoch, [2] abort word
+        PF2_CUDA(cudaMemset(d->epoch, 0, 4 * sizeof(unsigned long long)));
     }
     cudaIpcMemHandle_t h0, h1;
     PF2_CUDA(cudaIpcGetMemHandle(&h0, d->arena));
@@ -483,6 +502,11 @@ int pf2_csr_p2p_import(pf2_csr* A, const char* all_handles, const int* all_halo)
         if (side == 0) { v.left_p = pvec; v.left_recv_off = hn[4]; }     // my left plane lands in their RIGHT ghost range (recvR_off)
         else { v.right_p = pvec; v.right_recv_off = hn[1]; }             // my right plane lands in their LEFT ghost range (recvL_off)
     }
+    v.abort = (unsigned int*)(d->epoch + 2);
+    v.epoch = d->epoch;
+    v.own_lo = A->own_lo; v.own_hi = A->own_hi;
+    v.sendL = A->halo[0]; v.cntL = me > 0 ? A->halo[2] : 0; v.sendR = A->halo[3]; v.cntR = me < world - 1 ? A->halo[5] : 0;
+    v.defer_halo_wait = 0;
     A->p2p_view = v;
     if (!A->p2p_dev) PF2_CUDA(cudaMalloc((void**)&A->p2p_dev, sizeof(P2PView)));
     PF2_CUDA(cudaMemcpy(A->p2p_dev, &v, sizeof(P2PView), cudaMemcpyHostToDevice));

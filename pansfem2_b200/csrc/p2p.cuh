@@ -4,35 +4,80 @@
 
 namespace pf2 {
 
-// Allreduce (sum) of <= 4 fp64 executed by ONE WARP: lane r stores this rank's values into rank r's arena, fences, raises its
-// flag there; then lane r waits for rank r's flag in the LOCAL arena and lane 0 sums the slots in rank order, so the result
-// is bitwise identical on every rank.  Slots and flags are double-buffered by epoch parity: a rank cannot run two epochs
-// ahead of a peer because finishing an epoch needs that peer's flag.  `vals` must be visible to the whole warp (shared).
+constexpr long long kP2pSpinLimitClk = 8000000000ll;      // ~4 s of SM clocks: a peer that left the solve becomes PF2_E_CUDA, not a hung box
+constexpr int kLlTerms = 4;                               // fp64 values per rank and exchange
+
+__device__ __forceinline__ unsigned long long p2p_ld_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// ---- LL words (the low-latency protocol of NCCL): a double travels as two 8-byte words {32 bits of the value, 32-bit flag}.  An
+// 8-byte store is single-copy atomic on every path (L2, NVLink), so a reader that sees the flag sees the data: no fence and no
+// separate flag write, i.e. one NVLink crossing per exchange instead of store + fence + flag.
+template <bool SYS>
+__device__ __forceinline__ void ll_store(unsigned long long* slot, double v, unsigned int flag) {
+    const unsigned long long f = (unsigned long long)flag << 32;
+    const unsigned long long w0 = f | (unsigned int)__double2loint(v), w1 = f | (unsigned int)__double2hiint(v);
+    if (SYS) asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+    else asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+}
+template <bool SYS>
+__device__ __forceinline__ bool ll_try_load(const unsigned long long* slot, unsigned int flag, double& v) {
+    unsigned long long w0, w1;
+    if (SYS) asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+    else asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+    if ((unsigned int)(w0 >> 32) != flag || (unsigned int)(w1 >> 32) != flag) return false;
+    v = __hiloint2double((int)(unsigned int)w1, (int)(unsigned int)w0);
+    return true;
+}
+
+// bounded wait on a flag word a PEER raises (halo epochs); false = timed out (the abort word of the view is set)
+__device__ __forceinline__ bool p2p_wait_flag(const P2PView& P, const unsigned long long* flag, unsigned long long target) {
+    if (p2p_ld_sys_u64(flag) >= target) return true;
+    long long t0 = 0;
+    for (unsigned int n = 1;; n++) {
+        if (p2p_ld_sys_u64(flag) >= target) return true;
+        if ((n & 1023u) == 0u) {
+            if (t0 == 0) t0 = clock64();
+            if (*(volatile unsigned int*)P.abort) return false;
+            if (clock64() - t0 > kP2pSpinLimitClk) { atomicExch(P.abort, 1u); return false; }
+        }
+    }
+}
+
+// Allreduce (sum) of <= 4 fp64 executed by ONE WARP: lane r sends this rank's values to rank r as LL words and receives rank r's;
+// lane 0 adds them in rank order, so the result is bitwise identical on every rank.  Words are double-buffered by epoch parity: a
+// rank cannot run two epochs ahead of a peer because finishing an epoch needs that peer's words.  `vals` must be visible to the
+// whole warp (shared memory).  Spins are bounded: on a timeout the view's abort word is set and the values are meaningless.
 __device__ __forceinline__ void p2p_allreduce_warp(const P2PView& P, unsigned long long* epoch_ctr, double* vals, int count) {
     const int lane = threadIdx.x & 31;
-    const unsigned long long epoch = *epoch_ctr + 1;
+    const unsigned long long epoch = *(volatile unsigned long long*)epoch_ctr + 1;
+    const unsigned int flag = (unsigned int)epoch;
     const int par = (int)(epoch & 1ull);
+    double got[kLlTerms] = { 0.0, 0.0, 0.0, 0.0 };
     if (lane < P.world) {
-        double* dst = P.slots[lane] + ((size_t)par * P.world + P.rank) * 4;
-        for (int c = 0; c < count; c++) dst[c] = vals[c];
-        __threadfence_system();
-        *(volatile unsigned long long*)(P.flags[lane] + (size_t)par * P.world + P.rank) = epoch;
-    }
-    if (lane < P.world) {
-        volatile unsigned long long* f = (volatile unsigned long long*)(P.flags[P.rank] + (size_t)par * P.world + lane);
-        while (*f < epoch) {}
+        for (int c = 0; c < count; c++) ll_store<true>(P.ll[lane] + (((size_t)par * P.world + P.rank) * kLlTerms + c) * 2, vals[c], flag);
+        for (int c = 0; c < count; c++) {
+            const unsigned long long* slot = P.ll[P.rank] + (((size_t)par * P.world + lane) * kLlTerms + c) * 2;
+            long long t0 = 0;
+            for (unsigned int n = 1; !ll_try_load<true>(slot, flag, got[c]); n++) {
+                if ((n & 1023u) == 0u) {
+                    if (t0 == 0) t0 = clock64();
+                    if (*(volatile unsigned int*)P.abort) break;
+                    if (clock64() - t0 > kP2pSpinLimitClk) { atomicExch(P.abort, 1u); break; }
+                }
+            }
+        }
     }
     __syncwarp();
-    __threadfence_system();
-    if (lane == 0) {
-        const volatile double* src = (const volatile double*)(P.slots[P.rank] + (size_t)par * P.world * 4);
-        for (int c = 0; c < count; c++) {
-            double acc = 0.0;
-            for (int r = 0; r < P.world; r++) acc += src[r * 4 + c];
-            vals[c] = acc;
-        }
-        *epoch_ctr = epoch;
+    for (int c = 0; c < count; c++) {
+        double sum = 0.0;
+        for (int r = 0; r < P.world; r++) sum += __shfl_sync(0xffffffffu, got[c], r);
+        if (lane == 0) vals[c] = sum;
     }
+    if (lane == 0) *(volatile unsigned long long*)epoch_ctr = epoch;
     __syncwarp();
 }
 

@@ -13,15 +13,16 @@ int sell_refresh(pf2_csr* A);
 // PF2_E_UNSUPPORTED without an error message = "not applicable to this matrix": the caller falls back to the three-kernel loop.
 int ensure_workspace_pub(pf2_csr* A);
 
-// Which loop runs (pf2_csr_set_pcg_mode / PF2_PCG override): the persistent kernel removes the host-ordered synchronisation points, which
-// is what bounds a partitioned solve and a small system; on one GPU a LARGE system is bandwidth-bound either way and the three
-// stand-alone kernels keep a few per cent more of the HBM rate (measured, profiles/r02_pcg_tune.md), so they stay the default there.
+// Which loop runs (pf2_csr_set_pcg_mode / PF2_PCG override).  Measured on B200 (profiles/r02_pcg_tune.md): a grid-wide exchange of the
+// persistent kernel costs 3 us on a 20-CTA grid and 6-10 us on a full one, a kernel boundary 2-3 us whatever the grid, and the
+// stand-alone kernels keep a few per cent more of the HBM rate; so the persistent kernel is the default only where launches dominate
+// (small systems: 60x40 sample 1.5x faster) and stays selectable everywhere else, partitioned matrices included.
 static bool pcg_enabled(const pf2_csr* A) {
     if (A->pcg_mode >= 0) return A->pcg_mode != 0;
     static const int env = getenv("PF2_PCG") ? atoi(getenv("PF2_PCG")) : -1;
     if (env >= 0) return env != 0;
-    static const long long auto_rows = getenv("PF2_PCG_AUTO_ROWS") ? atoll(getenv("PF2_PCG_AUTO_ROWS")) : 600000;
-    return A->dist != nullptr || (long long)A->rows <= auto_rows;
+    static const long long auto_rows = getenv("PF2_PCG_AUTO_ROWS") ? atoll(getenv("PF2_PCG_AUTO_ROWS")) : 50000;
+    return A->dist == nullptr && (long long)A->rows <= auto_rows;
 }
 
 template <class IDX, int NB, int MODE, bool DIST, bool CS>

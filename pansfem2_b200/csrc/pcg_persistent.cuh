@@ -84,35 +84,13 @@ __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) { return p2p_ld_sys_u64(p); }
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
 
-// ---- LL words: a double travels as two 8-byte words {32 bits of the value, 32-bit flag}; an 8-byte store is single-copy atomic on
-// every path (L2, NVLink), so a reader that sees the flag sees the data: no fence, no separate flag write.
-template <bool SYS>
-__device__ __forceinline__ void ll_store(unsigned long long* slot, double v, unsigned int flag) {
-    const unsigned long long f = (unsigned long long)flag << 32;
-    const unsigned long long w0 = f | (unsigned int)__double2loint(v), w1 = f | (unsigned int)__double2hiint(v);
-    if (SYS) asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
-    else asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
-}
-template <bool SYS>
-__device__ __forceinline__ bool ll_try_load(const unsigned long long* slot, unsigned int flag, double& v) {
-    unsigned long long w0, w1;
-    if (SYS) asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
-    else asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
-    if ((unsigned int)(w0 >> 32) != flag || (unsigned int)(w1 >> 32) != flag) return false;
-    v = __hiloint2double((int)(unsigned int)w1, (int)(unsigned int)w0);
-    return true;
-}
 // bounded wait for an LL word; false = timed out or another CTA aborted (v is then meaningless)
 template <bool SYS>
 __device__ __forceinline__ bool ll_wait(const unsigned long long* slot, unsigned int flag, double& v, PcgSync* sync) {

@@ -204,7 +204,11 @@ __device__ __forceinline__ double sell_slice_acc(const IDX* __restrict__ sell_id
     return acc;
 }
 
-template <bool DOT, class IDX, bool PERM = false, int NB = 1, int U = 6>
+// CS = false: plain (L2-allocating) loads of the matrix stream, for slabs small enough to stay L2-resident between products.
+// Partitioned matrix with the peer-memory backend (p2p != nullptr): only the slices of the owned rows are multiplied, interior slices
+// first; a warp that reaches a slice holding rows of a boundary plane first waits for that neighbour's plane of the current halo
+// epoch (deferred there by the p-update kernel), so the exchange overlaps the interior rows.
+template <bool DOT, class IDX, bool PERM = false, int NB = 1, int U = 6, bool CS = true>
 __global__ void __launch_bounds__(kThreads)
 spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* __restrict__ perm, const IDX* __restrict__ sell_idx, const double* __restrict__ sell_val,
                  const double* __restrict__ x, double* __restrict__ y, const CgState* __restrict__ st, double* dot_out,
@@ -215,11 +219,48 @@ spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* _
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int nslices = (rows + kSellC - 1) / kSellC;
     double dot = 0.0;
-    for (int s = warp; s < nslices; s += nwarps) {
+    // virtual slice order: [s_lb, s_rb) interior, then [s_lo, s_lb) left boundary, then [s_rb, s_hi) right boundary
+    int s_lo = 0, s_hi = nslices, s_lb = 0, s_rb = nslices;
+    bool ordered = false;
+    unsigned long long halo_epoch = 0ull;
+    if (!PERM && DOT && p2p != nullptr && p2p->defer_halo_wait) {
+        ordered = true;
+        s_lo = p2p->own_lo / kSellC; s_hi = (p2p->own_hi + kSellC - 1) / kSellC;
+        s_lb = s_lo; s_rb = s_hi;
+        if (p2p->cntL > 0) s_lb = min(s_hi, (p2p->sendL + p2p->cntL + kSellC - 1) / kSellC);
+        if (p2p->cntR > 0) s_rb = max(s_lb, p2p->sendR / kSellC);
+        halo_epoch = *(volatile unsigned long long*)(p2p->epoch + 1);
+    }
+    const int n_int = s_rb - s_lb, n_left = s_lb - s_lo, n_all = s_hi - s_lo;
+    bool waitedL = false, waitedR = false;
+    for (int v = warp; v < n_all; v += nwarps) {
+        int s = s_lo + v;
+        if (ordered) {
+            if (v < n_int) s = s_lb + v;
+            else {
+                const int w = v - n_int;
+                const bool left = w < n_left;
+                s = left ? s_lo + w : s_rb + (w - n_left);
+                const bool needL = (left || n_int == 0) && p2p->cntL > 0 && !waitedL;
+                const bool needR = (!left || n_int == 0) && p2p->cntR > 0 && !waitedR;
+                if (needL || needR) {
+                    if (lane == 0) {
+                        const unsigned long long* mine = p2p->halo_flags[p2p->rank];
+                        if (needL) p2p_wait_flag(*p2p, mine + 0, halo_epoch);
+                        if (needR) p2p_wait_flag(*p2p, mine + 1, halo_epoch);
+                        __threadfence_system();      // acquire: the plane the neighbour stored before raising its flag
+                    }
+                    __syncwarp();
+                    waitedL = waitedL || needL; waitedR = waitedR || needR;
+                }
+            }
+        }
         const long long base = slice_ptr[s];
         const int width = (int)((slice_ptr[s + 1] - base) / kSellC);
         const int r = PERM ? perm[s * kSellC + lane] : ((s * kSellC + lane < rows) ? s * kSellC + lane : -1);
-        const double acc = sell_slice_acc<IDX, NB, U, true>(sell_idx, sell_val, x, base, width, lane, r);
+        // ghost entries of x arrive from a peer GPU while this kernel runs: they must not come through the non-coherent path
+        const double acc = ordered ? sell_slice_acc<IDX, NB, U, CS, false>(sell_idx, sell_val, x, base, width, lane, r)
+                                   : sell_slice_acc<IDX, NB, U, CS, true>(sell_idx, sell_val, x, base, width, lane, r);
         if (r >= 0) {
             y[r] = acc;
             if (DOT && r >= dot_lo && r < dot_hi) dot += acc * x[r];

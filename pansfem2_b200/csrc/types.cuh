@@ -62,7 +62,12 @@ struct P2PView {          // must match pf2::P2P in dist.cu (kept POD here so th
     double* left_p;
     double* right_p;
     int left_recv_off, right_recv_off;
-    unsigned long long* ll[kMaxRanksT];    // LL words of the persistent PCG kernel's cross-GPU sums: [parity][sender][4 terms][2 halves]
+    unsigned long long* ll[kMaxRanksT];    // LL words of the cross-GPU sums: [parity][sender][4 terms][2 halves] in every rank's arena
+    unsigned int* abort;                   // local device word: a bounded spin timed out (a peer left the solve)
+    // halo geometry of the local matrix (rows): owned range, the two boundary planes this rank sends; defer = 1: the wait for the
+    // neighbours' planes happens in the boundary slices of the next product instead of at the end of the p-update
+    int own_lo, own_hi, sendL, cntL, sendR, cntR, defer_halo_wait, pad;
+    unsigned long long* epoch;             // local device words: [0] allreduce epoch, [1] halo epoch
 };
 }  // namespace pf2
 

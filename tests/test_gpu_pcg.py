@@ -124,6 +124,7 @@ def test_design_loop_with_warm_start_matches_the_oracle(ctx):
     tot = {}
     for warm in (False, True):
         S = capi.Simp(ctx, P)
+        S.A.set_pcg_mode(1 if warm else -1)          # the warm run also exercises the persistent kernel's x0 set-up
         S.set_warm_start(warm)
         st = [S.iterate(check_convergence=False) for _ in range(12)]
         out = S.get()
