@@ -330,8 +330,11 @@ int pf2_csr_set_partition(pf2_csr* A, pf2_dist* d, int own_lo, int own_hi, const
  * (boundary planes are stored straight into the neighbours' ghost ranges over NVLink) and the dot-product allreduces run
  * inside one-warp kernels over IPC-mapped arenas.  export: this rank's IPC handles {arena, Krylov slab} (2 x 64 bytes);
  * exchange them through any channel; import: all ranks' handles (world x 128 bytes) and all ranks' meta (world x 8 ints =
- * {row halo descriptor[6], local rows, 0}). */
+ * {row halo descriptor[6], local rows, pf2_csr_pcg_capable}). */
 int pf2_csr_p2p_export(pf2_csr* A, char handles_out[128]);
+/* meta[7] of pf2_csr_p2p_import: 1 when this rank's slab qualifies for the persistent PCG kernel's partitioned instantiation; the
+ * kernel is used only when every rank reports 1 (all ranks must run the same protocol) */
+int pf2_csr_pcg_capable(pf2_csr* A, int* out);
 int pf2_csr_p2p_import(pf2_csr* A, const char* all_handles, const int* all_meta);
 /* Unmap the neighbours' Krylov slabs again.  All ranks call it and synchronise before any of them destroys its matrix. */
 int pf2_csr_p2p_release(pf2_csr* A);

@@ -567,7 +567,9 @@ class Dist:
         import torch.distributed as tdist
         hb = (C.c_char * 128)()
         _ck(lib().pf2_csr_p2p_export(A.h, hb))
-        meta = [int(v) for v in row_halo] + [int(A.rows), 0]
+        cap = C.c_int(0)
+        _ck(lib().pf2_csr_pcg_capable(A.h, C.byref(cap)))
+        meta = [int(v) for v in row_halo] + [int(A.rows), int(cap.value)]
         gathered = [None] * self.world
         tdist.all_gather_object(gathered, (bytes(hb.raw), meta))
         allh = (C.c_char * (128 * self.world))()

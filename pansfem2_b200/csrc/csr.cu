@@ -300,7 +300,7 @@ int sell_refresh(pf2_csr* A) {
 // a slab whose SELL mirror (values + 16-bit deltas) fits the L2 next to the Krylov vectors is read with plain loads, so that it stays
 // resident from one product to the next (row-partitioned 2-D problems at 8 GPUs); larger ones stream through with evict-first loads
 static bool sell_l2_resident(const pf2_csr* A) {
-    static const double mb = getenv("PF2_SELL_L2_MB") ? atof(getenv("PF2_SELL_L2_MB")) : 115.0;
+    const double mb = getenv("PF2_SELL_L2_MB") ? atof(getenv("PF2_SELL_L2_MB")) : 115.0;      // read per launch: probes switch it
     const double idx_bytes = A->sell_d16 ? 2.0 / A->sell_nb : 4.0 / A->sell_nb;
     return (double)A->sell_entries * (8.0 + idx_bytes) + 40.0 * (double)A->rows <= mb * 1.0e6;
 }

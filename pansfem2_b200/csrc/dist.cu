@@ -502,6 +502,8 @@ int pf2_csr_p2p_import(pf2_csr* A, const char* all_handles, const int* all_halo)
         if (side == 0) { v.left_p = pvec; v.left_recv_off = hn[4]; }     // my left plane lands in their RIGHT ghost range (recvR_off)
         else { v.right_p = pvec; v.right_recv_off = hn[1]; }             // my right plane lands in their LEFT ghost range (recvL_off)
     }
+    A->pcg_dist_ok = true;
+    for (int r = 0; r < world; r++) if (all_halo[(size_t)r * 8 + 7] == 0) A->pcg_dist_ok = false;
     v.abort = (unsigned int*)(d->epoch + 2);
     v.epoch = d->epoch;
     v.own_lo = A->own_lo; v.own_hi = A->own_hi;

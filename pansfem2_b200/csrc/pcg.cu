@@ -46,7 +46,9 @@ int pcg_persistent_solve(pf2_csr* A, int solver, const double* b, double* x, int
     pf2_ctx* c = A->ctx;
     if (!pcg_enabled(A) || (solver != PF2_SOLVER_CG && solver != PF2_SOLVER_SCALINGCG)) return PF2_E_UNSUPPORTED;
     const bool dist = A->dist != nullptr;
-    if (dist && !A->p2p_ready) return PF2_E_UNSUPPORTED;                 // NCCL backend keeps the host-ordered loop
+    // partitioned: NCCL backend keeps the host-ordered loop; with peer memory EVERY rank must take the same path (the protocols differ),
+    // so the ranks agreed at import time on whether all of their slabs qualify (pf2_csr_pcg_capable -> meta[7])
+    if (dist && (!A->p2p_ready || !A->pcg_dist_ok)) return PF2_E_UNSUPPORTED;
     PF2_TRY(plan_spmv_pub(A));
     if (A->spmv_variant != 31 || A->sell_nb == 2 || (A->sell_perm && dist)) return PF2_E_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return PF2_E_UNSUPPORTED;      // the vector phases use 128-bit accesses
@@ -116,6 +118,16 @@ int pcg_persistent_solve(pf2_csr* A, int solver, const double* b, double* x, int
 }
 
 }  // namespace pf2
+
+// 1 when this matrix' SELL-32 mirror is one the persistent kernel's partitioned instantiation handles (natural row order, no 2-wide
+// block deltas); the ranks of a partition exchange it so that all of them take the same path
+extern "C" int pf2_csr_pcg_capable(pf2_csr* A, int* out) {
+    using namespace pf2;
+    PF2_CHECK(A && out, "null argument");
+    PF2_TRY(plan_spmv_pub(A));
+    *out = (A->spmv_variant == 31 && A->sell_perm == nullptr && A->sell_nb != 2) ? 1 : 0;
+    return PF2_OK;
+}
 
 // diagnostics: per-CTA %globaltimer stamps of iteration kPcgDbgIter of the last persistent solve (6 x 2048 u64)
 extern "C" int pf2_csr_pcg_debug(pf2_csr* A, unsigned long long* out_host) {

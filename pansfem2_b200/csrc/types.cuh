@@ -83,6 +83,7 @@ struct pf2_csr {
     pf2::P2PView p2p_view;
     pf2::P2PView* p2p_dev = nullptr;      // device copy handed to the fused kernels (nullptr: single GPU or NCCL backend)
     unsigned long long* p2p_epoch = nullptr;
+    bool pcg_dist_ok = false;             // every rank's slab qualifies for the persistent kernel's partitioned instantiation
     void* p2p_opened[2] = { nullptr, nullptr };   // IPC mappings of the left / right neighbour's Krylov slab
     long long nnz = 0;
     long long* indptr = nullptr;   // rows+1 (int64: config 5 has nnz > 2^31)

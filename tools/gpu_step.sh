@@ -30,6 +30,7 @@ for stage in "$@"; do
     small)   for w in c1 pair c4s; do for m in 0 1; do PF2_PCG=$m timeout 120 python tools/pcg_tune.py $w 2 2>&1 | tail -1 | tee -a "$out/small.jsonl"; done; done ;;
     b2)      for m in 1 0; do PF2_PCG=$m timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 2 --no-hex8 --no-extra-legs --no-headline-2m > "$out/bench_n2_pcg$m.json" 2> "$out/bench_n2_pcg$m.err"; tail -c 1800 "$out/bench_n2_pcg$m.json"; tail -3 "$out/bench_n2_pcg$m.err"; done ;;
     b8)      for m in 1 0; do PF2_PCG=$m timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NG:-8} --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus ${NG:-8} --steps 3 --warmup 2 --hex8 c4 --no-extra-legs --no-headline-2m > "$out/bench_n${NG:-8}_pcg$m.json" 2> "$out/bench_n${NG:-8}_pcg$m.err"; python tools/bench_brief.py "$out/bench_n${NG:-8}_pcg$m.json"; tail -3 "$out/bench_n${NG:-8}_pcg$m.err" | cut -c1-300; done ;;
+    probe)   for w in ${PROBE_W:-c2 c4}; do timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NG:-8} --master-addr 127.0.0.1 --master-port 29531 tools/dist_pcg_probe.py $w ${PROBE_IT:-1500} 2>"$out/probe_$w.err" | grep "^{" | tee -a "$out/probe.jsonl"; tail -2 "$out/probe_$w.err" | cut -c1-200; done ;;
     *)       echo "unknown stage $stage" ;;
   esac
 done
