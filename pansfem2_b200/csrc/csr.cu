@@ -297,10 +297,11 @@ int sell_refresh(pf2_csr* A) {
     return PF2_OK;
 }
 
-// a slab whose SELL mirror (values + 16-bit deltas) fits the L2 next to the Krylov vectors is read with plain loads, so that it stays
-// resident from one product to the next (row-partitioned 2-D problems at 8 GPUs); larger ones stream through with evict-first loads
+// Opt-in (PF2_SELL_L2_MB=<budget>): a slab whose SELL mirror (values + 16-bit deltas) fits that budget next to the Krylov vectors is read
+// with plain loads instead of evict-first ones, to stay L2-resident from one product to the next.  Measured on 8 B200s with a 110 MB slab
+// (2-D 4 M dof / 8): 0.0734 vs 0.0685 ms per PCG iteration -- the 126 MB L2 does not hold it next to the vectors, so it is off by default.
 static bool sell_l2_resident(const pf2_csr* A) {
-    const double mb = getenv("PF2_SELL_L2_MB") ? atof(getenv("PF2_SELL_L2_MB")) : 115.0;      // read per launch: probes switch it
+    const double mb = getenv("PF2_SELL_L2_MB") ? atof(getenv("PF2_SELL_L2_MB")) : 0.0;      // read per launch: probes switch it
     const double idx_bytes = A->sell_d16 ? 2.0 / A->sell_nb : 4.0 / A->sell_nb;
     return (double)A->sell_entries * (8.0 + idx_bytes) + 40.0 * (double)A->rows <= mb * 1.0e6;
 }
@@ -335,7 +336,10 @@ static int launch_sell(pf2_csr* A, const double* x, double* y, const CgState* st
         else if (A->sell_perm) SELL(short, true, 1, A->sell_d16)
         else {
             // independent loads in flight per lane and round; measured at 2 M dof: 3 -> 0.0843 ms, 6 -> 0.0778, 9 -> 0.0839, 18 -> 0.0895
-            static const int unroll = getenv("PF2_SELL_UNROLL") ? atoi(getenv("PF2_SELL_UNROLL")) : 6;
+            // small slabs (<= 2 slices per resident warp: row-partitioned 2-D problems at 8 GPUs) are bound by the rounds of dependent loads, not by
+            // occupancy: all 18 nonzeros of a Q4 row in one round measured 0.0658 vs 0.0685 ms per PCG iteration there (profiles/r02_dist_probe.md)
+            static const int unroll_env = getenv("PF2_SELL_UNROLL") ? atoi(getenv("PF2_SELL_UNROLL")) : 0;
+            const int unroll = unroll_env ? unroll_env : ((long long)nslices <= 2LL * c->sm_count * 8 * (kThreads / 32) ? 18 : 6);
 #define SELLU(UV)                                                                                                                          \
     {                                                                                                                                      \
         const int grid = std::max(1, std::min(nb, c->wave_grid((const void*)spmv_sell_kernel<DOT, short, false, 1, UV>, kThreads)));          \

@@ -299,7 +299,9 @@ int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, d
     if (p2p) {
         // products that order their slices (SELL-32, natural row order) take over the wait for the neighbours' planes
         plan_spmv_pub(A);
-        const int defer = (A->spmv_variant == 31 && A->sell_perm == nullptr && getenv("PF2_HALO_NODEFER") == nullptr) ? 1 : 0;
+        // opt-in (PF2_HALO_DEFER=1): measured SLOWER on 8 B200s (2-D 4 M dof: 0.0700 vs 0.0685 ms per iteration, hex8 12.8 M dof: 0.272 vs
+        // 0.261; profiles/r02_dist_probe.md) -- the system-scope acquire in every boundary warp costs more than the overlap wins
+        const int defer = (A->spmv_variant == 31 && A->sell_perm == nullptr && getenv("PF2_HALO_DEFER") != nullptr && getenv("PF2_HALO_NODEFER") == nullptr) ? 1 : 0;
         if (defer != A->p2p_view.defer_halo_wait) {
             A->p2p_view.defer_halo_wait = defer;
             PF2_CUDA(cudaMemcpyAsync(A->p2p_dev, &A->p2p_view, sizeof(P2PView), cudaMemcpyHostToDevice, s));

@@ -25,9 +25,9 @@ def _ngpu():
 
 
 CASES = [
-    # default: three-kernel loop over peer memory (LL allreduce in the last CTA, halo wait deferred into the product's boundary slices)
+    # default: three-kernel loop over peer memory (LL allreduce in the last CTA, halo planes pushed by the p-update kernel)
     ("2d 96 40", {}), ("2d 96 40 --mma", {}), ("3d 16 8 6", {}), ("3d 16 8 6 --mma", {}), ("heat 48 48", {}),
-    ("2d 96 40", {"PF2_HALO_NODEFER": "1"}),
+    ("2d 96 40", {"PF2_HALO_DEFER": "1"}), ("3d 16 8 6", {"PF2_HALO_DEFER": "1", "PF2_SELL_L2_MB": "100"}),      # opt-in variants
     # the persistent kernel's partitioned instantiation
     ("2d 96 40", {"PF2_PCG": "1"}), ("2d 96 40 --mma", {"PF2_PCG": "1"}), ("heat 48 48", {"PF2_PCG": "1"}), ("2d 96 40 --warm", {"PF2_PCG": "1"}),
     # NCCL backend

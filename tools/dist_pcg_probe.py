@@ -33,10 +33,12 @@ D.set_partition(A, S.own_rows, S.row_halo)
 D.enable_p2p(A, S.row_halo)
 x = ctx.empty(A.rows)
 out = {"workload": name, "world": world, "rows_local": A.rows, "nnz_local": A.nnz, "iterations": itr}
-variants = [("3k_defer_l2", 0, {}), ("3k_nodefer_l2", 0, {"PF2_HALO_NODEFER": "1"}), ("3k_defer_stream", 0, {"PF2_SELL_L2_MB": "0"}),
-            ("3k_nodefer_stream", 0, {"PF2_HALO_NODEFER": "1", "PF2_SELL_L2_MB": "0"}), ("persistent", 1, {})]
+variants = [("3k", 0, {}), ("3k_defer", 0, {"PF2_HALO_DEFER": "1"}), ("3k_l2", 0, {"PF2_SELL_L2_MB": "115"}), ("persistent", 1, {})]
+if os.environ.get("PROBE_ONLY"):
+    variants = [v for v in variants if v[0] in os.environ["PROBE_ONLY"].split(",")]
+out["sell_unroll"] = os.environ.get("PF2_SELL_UNROLL", "6")
 for tag, mode, env in variants:
-    for k in ("PF2_HALO_NODEFER", "PF2_SELL_L2_MB"):
+    for k in ("PF2_HALO_DEFER", "PF2_SELL_L2_MB"):
         os.environ.pop(k, None)
     os.environ.update(env)
     A.set_pcg_mode(mode)
