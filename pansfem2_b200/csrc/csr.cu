@@ -312,6 +312,19 @@ static int launch_sell(pf2_csr* A, const double* x, double* y, const CgState* st
     if (!A->sell_values_valid) PF2_TRY(sell_refresh(A));
     const int nslices = (A->rows + kSellC - 1) / kSellC;
     const int nb = (nslices + (kThreads / 32) - 1) / (kThreads / 32);
+    if (DOT && A->p2p_dev && A->p2p_view.defer_halo_wait && A->sell_d16 && !A->sell_perm && (A->sell_nb == 1 || A->sell_nb == 3)) {
+        // opt-in (PF2_HALO_DEFER): the boundary slices of this product wait for the neighbours' planes, after the interior slices
+#define SELLO(NBV)                                                                                                                         \
+    {                                                                                                                                      \
+        const int grid = std::max(1, std::min(nb, c->wave_grid((const void*)spmv_sell_kernel<DOT, short, false, NBV, 6, true, true>, kThreads))); \
+        spmv_sell_kernel<DOT, short, false, NBV, 6, true, true><<<grid, kThreads, 0, c->stream>>>(A->rows, A->sell_ptr, A->sell_perm, A->sell_d16, A->sell_val, x, y, \
+                                                                                               st, dot_out, c->red.partials, c->red.ticket, A->own_lo, \
+                                                                                               A->own_hi, A->p2p_dev, A->p2p_epoch);                   \
+    }
+        if (A->sell_nb == 3) SELLO(3) else SELLO(1)
+#undef SELLO
+        return PF2_OK;
+    }
 #define SELL(IDXT, PERMV, NBV, IDXPTR)                                                                                                     \
     {                                                                                                                                      \
         const int grid = std::max(1, std::min(nb, c->wave_grid((const void*)spmv_sell_kernel<DOT, IDXT, PERMV, NBV>, kThreads)));             \
@@ -575,7 +588,7 @@ int pf2_csr_destroy(pf2_csr* A) {
     cudaSetDevice(A->ctx->device);
     cudaStreamSynchronize(A->ctx->stream);
     void* ptrs[] = { A->indptr, A->indices, A->data, A->F, A->diagpos, A->bmap, A->slab, A->xw, A->bw, A->st, A->sell_ptr, A->sell_perm, A->sell_idx, A->sell_d16, A->sell_b32, A->sell_val, A->p2p_dev,
-                     A->ilu, A->level_rows, A->level_rows_u, A->n2e_ptr, A->n2e, A->node_row0 };
+                     A->ilu, A->level_rows, A->level_rows_u, A->ilu_ready, A->n2e_ptr, A->n2e, A->node_row0 };
     for (void* p : ptrs) if (p) cudaFree(p);
     if (A->h_st) cudaFreeHost(A->h_st);
     if (A->pcg_sync) cudaFree(A->pcg_sync);

@@ -284,10 +284,144 @@ int dist_allreduce_max(pf2_dist* d, double* dev, int count) {
     return PF2_OK;
 }
 
+// ---- ILU0CG on a partitioned matrix: block-Jacobi ILU(0) per rank (ilu.cu restricts factorisation and sweeps to the owned block) -------
+int ilu0_factor(pf2_csr* A);
+int ilu0_apply(pf2_csr* A, double* v, const CgState* st, const double* factors = nullptr);
+
+// x = 0 ; r = b ; z = r (the sweeps turn it into M^-1 r) ; b.b over the owned rows
+__global__ void __launch_bounds__(kThreads)
+dcg_ilu_init_kernel(int lo, int hi, int n, const double* __restrict__ b, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
+                    double* __restrict__ p, CgState* st, double* partials, unsigned int* ticket) {
+    double v[1] = { 0.0 };
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const bool own = (i >= lo && i < hi);
+        const double bi = own ? b[i] : 0.0;
+        x[i] = 0.0; r[i] = bi; z[i] = bi; p[i] = 0.0;
+        v[0] += bi * bi;
+    }
+    if (grid_sum_last<1>(v, partials, ticket) && threadIdx.x == 0) st->red[0] = v[0];
+}
+// z.r over the owned rows into red[slot]; init: p = z
+__global__ void __launch_bounds__(kThreads)
+dcg_ilu_dot_kernel(int lo, int hi, const double* __restrict__ z, const double* __restrict__ r, double* __restrict__ p, int init, int slot,
+                   CgState* st, double* partials, unsigned int* ticket) {
+    if (!init && st->done) return;
+    double v[1] = { 0.0 };
+    for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
+        v[0] += z[i] * r[i];
+        if (init) p[i] = z[i];
+    }
+    if (grid_sum_last<1>(v, partials, ticket) && threadIdx.x == 0) st->red[slot] = v[0];
+}
+// x += alpha p ; r -= alpha y ; z = r ; r.r over the owned rows into red[1]
+__global__ void __launch_bounds__(kThreads)
+dcg_ilu_update_kernel(int lo, int hi, const double* __restrict__ p, const double* __restrict__ y, double* __restrict__ x, double* __restrict__ r,
+                      double* __restrict__ z, CgState* st, double* partials, unsigned int* ticket) {
+    if (st->done) return;
+    const double alpha = st->rho / st->pAp;
+    double v[1] = { 0.0 };
+    for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
+        x[i] = x[i] + alpha * p[i];
+        const double ri = r[i] + (-alpha) * y[i];
+        r[i] = ri; z[i] = ri;
+        v[0] += ri * ri;
+    }
+    if (grid_sum_last<1>(v, partials, ticket) && threadIdx.x == 0) st->red[1] = v[0];
+}
+
+static int solve_dist_ilu(pf2_csr* A, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out) {
+    pf2_ctx* c = A->ctx;
+    pf2_dist* d = A->dist;
+    PF2_TRY(ensure_workspace_pub(A));
+    PF2_TRY(ilu0_factor(A));
+    const int n = A->rows, lo = A->own_lo, hi = A->own_hi;
+    cudaStream_t s = c->stream;
+    const bool p2p = d->p2p && A->p2p_ready;
+    if (p2p && A->p2p_view.defer_halo_wait) {
+        A->p2p_view.defer_halo_wait = 0;
+        PF2_CUDA(cudaMemcpyAsync(A->p2p_dev, &A->p2p_view, sizeof(P2PView), cudaMemcpyHostToDevice, s));
+    }
+    const int grid = std::min(c->grid_for(n, 2), c->sm_count * 4);
+    const int ugrid = std::min(c->grid_for(hi - lo, 2), c->sm_count * 4);
+    // the two scalar reductions of an iteration: peer memory -> one-warp LL allreduce kernel, else NCCL + a one-thread kernel
+    auto reduce_scalars = [&](int phase01) -> int {       // phase01 = 0: after set-up {b.b, z.r}; 1: inside an iteration {z.r, r.r}
+        if (p2p) p2p_cg_scalars_kernel<<<1, 32, 0, s>>>(A->p2p_view, d->epoch, A->st, phase01 == 0 ? 1 : 2, itrmax, eps);
+        else {
+            PF2_TRY(dist_allreduce(d, A->st->red, 2));
+            dcg_scalars_kernel<<<1, 1, 0, s>>>(A->st, phase01, itrmax, eps);
+        }
+        c->launches++;
+        return PF2_OK;
+    };
+    auto push_p = [&](int init) -> int {
+        if (p2p) p2p_pupdate_halo_kernel<<<ugrid, kThreads, 0, s>>>(lo, hi, A->z, A->p, A->st, init, A->p2p_view, A->halo[0], A->halo[2], A->halo[3], A->halo[5],
+                                                                   d->epoch, c->red.ticket + 1);
+        else {
+            if (!init) dcg_pupdate_kernel<<<ugrid, kThreads, 0, s>>>(lo, hi, A->z, A->p, A->st);
+            PF2_TRY(dist_halo(d, A->p, A->halo));
+        }
+        c->launches++;
+        return PF2_OK;
+    };
+    dcg_ilu_init_kernel<<<grid, kThreads, 0, s>>>(lo, hi, n, b, x, A->r, A->z, A->p, A->st, c->red.partials, c->red.ticket);
+    PF2_TRY(ilu0_apply(A, A->z, nullptr));
+    dcg_ilu_dot_kernel<<<ugrid, kThreads, 0, s>>>(lo, hi, A->z, A->r, A->p, 1, 1, A->st, c->red.partials, c->red.ticket);
+    c->launches += 2;
+    PF2_TRY(reduce_scalars(0));
+    PF2_TRY(push_p(1));
+    PF2_LAUNCH_CHECK();
+    const int chunk = 4;
+    int enq = 0, slot = 0;
+    bool have_prev = false, finished = false;
+    CgState last;
+    memset(&last, 0, sizeof last);
+    while (!finished) {
+        const int todo = std::min(chunk, itrmax - enq);
+        for (int k = 0; k < todo; k++) {
+            PF2_TRY(spmv_dot(A, A->p, A->y, A->st, &A->st->pAp));
+            if (!p2p) PF2_TRY(dist_allreduce(d, &A->st->pAp, 1));
+            dcg_ilu_update_kernel<<<ugrid, kThreads, 0, s>>>(lo, hi, A->p, A->y, x, A->r, A->z, A->st, c->red.partials, c->red.ticket);
+            PF2_TRY(ilu0_apply(A, A->z, A->st));
+            dcg_ilu_dot_kernel<<<ugrid, kThreads, 0, s>>>(lo, hi, A->z, A->r, A->p, 0, 0, A->st, c->red.partials, c->red.ticket);
+            c->launches += 2;
+            PF2_TRY(reduce_scalars(1));
+            PF2_TRY(push_p(0));
+        }
+        PF2_LAUNCH_CHECK();
+        enq += todo;
+        PF2_CUDA(cudaMemcpyAsync(&A->h_st[slot], A->st, sizeof(CgState), cudaMemcpyDeviceToHost, s));
+        PF2_CUDA(cudaEventRecord(A->ev[slot], s));
+        if (have_prev) {
+            PF2_CUDA(cudaEventSynchronize(A->ev[slot ^ 1]));
+            last = A->h_st[slot ^ 1];
+            if (last.done) finished = true;
+        }
+        if (!finished && (enq >= itrmax || todo == 0)) finished = true;
+        have_prev = true;
+        slot ^= 1;
+    }
+    PF2_CUDA(cudaMemcpyAsync(&A->h_st[0], A->st, sizeof(CgState), cudaMemcpyDeviceToHost, s));
+    PF2_CUDA(cudaStreamSynchronize(s));
+    last = A->h_st[0];
+    A->total_iters += last.iter;
+    if (iters_out) *iters_out = last.iter;
+    if (relres_out) *relres_out = sqrt(last.rr) / sqrt(last.bb);
+    if (p2p) {
+        unsigned long long aborted = 0;
+        PF2_CUDA(cudaMemcpy(&aborted, d->epoch + 2, sizeof aborted, cudaMemcpyDeviceToHost));
+        if (aborted) { set_error("partitioned PCG: a wait on a peer GPU timed out (a rank left the solve?)"); return PF2_E_CUDA; }
+    }
+    if (!last.done) {
+        set_error("Convergence:faild after %d iterations (relres %.3e)", last.iter, sqrt(last.rr) / sqrt(last.bb));
+        return PF2_E_NOCONV;
+    }
+    return PF2_OK;
+}
+
 int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out) {
     pf2_ctx* c = A->ctx;
     pf2_dist* d = A->dist;
-    if (solver == PF2_SOLVER_ILU0CG) { set_error("ILU0CG is not available on a partitioned matrix yet"); return PF2_E_UNSUPPORTED; }
+    if (solver == PF2_SOLVER_ILU0CG) return solve_dist_ilu(A, b, x, itrmax, eps, iters_out, relres_out);
     PF2_TRY(ensure_workspace_pub(A));
     const int n = A->rows, lo = A->own_lo, hi = A->own_hi;
     const int grid = std::min(c->grid_for(n, 2), c->sm_count * 4);
@@ -301,7 +435,8 @@ int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, d
         plan_spmv_pub(A);
         // opt-in (PF2_HALO_DEFER=1): measured SLOWER on 8 B200s (2-D 4 M dof: 0.0700 vs 0.0685 ms per iteration, hex8 12.8 M dof: 0.272 vs
         // 0.261; profiles/r02_dist_probe.md) -- the system-scope acquire in every boundary warp costs more than the overlap wins
-        const int defer = (A->spmv_variant == 31 && A->sell_perm == nullptr && getenv("PF2_HALO_DEFER") != nullptr && getenv("PF2_HALO_NODEFER") == nullptr) ? 1 : 0;
+        const int defer = (A->spmv_variant == 31 && A->sell_perm == nullptr && A->sell_d16 != nullptr && (A->sell_nb == 1 || A->sell_nb == 3) &&
+                           getenv("PF2_HALO_DEFER") != nullptr && getenv("PF2_HALO_NODEFER") == nullptr) ? 1 : 0;
         if (defer != A->p2p_view.defer_halo_wait) {
             A->p2p_view.defer_halo_wait = defer;
             PF2_CUDA(cudaMemcpyAsync(A->p2p_dev, &A->p2p_view, sizeof(P2PView), cudaMemcpyHostToDevice, s));
@@ -538,6 +673,9 @@ int pf2_dist_halo(pf2_dist* d, double* vec_dev, const int halo[6]) { return dist
 
 int pf2_csr_set_partition(pf2_csr* A, pf2_dist* d, int own_lo, int own_hi, const int halo[6]) {
     PF2_CHECK(A && own_lo >= 0 && own_lo <= own_hi && own_hi <= A->rows, "bad owned range");
+    // the ILU(0) level schedule and factors depend on the owned block (block-Jacobi ILU per rank): rebuild them lazily
+    if (A->level_rows) { cudaFree(A->level_rows); cudaFree(A->level_rows_u); A->level_rows = A->level_rows_u = nullptr; }
+    A->ilu_valid = false;
     A->dist = d; A->own_lo = own_lo; A->own_hi = own_hi;
     for (int i = 0; i < 6; i++) A->halo[i] = halo ? halo[i] : 0;
     return PF2_OK;

@@ -140,64 +140,6 @@ cg_pupdate_kernel(int n, const double* __restrict__ z, double* __restrict__ p, c
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = beta * p[n - 1] + z[n - 1];
 }
 
-// ---- ILU(0) ----------------------------------------------------------------------------------------------------
-// Row i depends on rows k < i that appear in its pattern.  Levels are computed on the host once per pattern; one
-// thread factors one row of the current level following the reference's entry order exactly (CG.h:262-281).
-__global__ void ilu0_level_kernel(int nrows_level, const int* __restrict__ rows_of_level, const long long* __restrict__ indptr,
-                                  const int* __restrict__ indices, const int* __restrict__ diagpos,
-                                  const double* __restrict__ a, double* __restrict__ q) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nrows_level) return;
-    const int i = rows_of_level[t];
-    const long long s = indptr[i], e = indptr[i + 1];
-    for (long long n = s; n < e; n++) {
-        const int j = indices[n];
-        double qij = a[n];
-        const int lim = (i <= j) ? i : j;
-        for (long long qq = s; qq < e; qq++) {
-            const int k = indices[qq];
-            if (k >= lim) break;
-            // find j in row k
-            long long lo = indptr[k], hi = indptr[k + 1] - 1;
-            while (lo <= hi) {
-                long long mid = (lo + hi) >> 1;
-                int cc = indices[mid];
-                if (cc == j) { qij -= q[qq] * q[mid]; break; }
-                if (cc < j) lo = mid + 1; else hi = mid - 1;
-            }
-        }
-        if (i > j) qij /= q[indptr[j] + diagpos[j]];
-        q[n] = qij;
-    }
-}
-
-// one level of the forward (unit-L) or backward (U) substitution of PreILU0 (CG.h:289-315); one thread per row
-template <bool FORWARD>
-__global__ void ilu0_sweep_level_kernel(int nrows_level, const int* __restrict__ rows_of_level,
-                                        const long long* __restrict__ indptr, const int* __restrict__ indices,
-                                        const int* __restrict__ diagpos, const double* __restrict__ q,
-                                        double* __restrict__ v, const CgState* __restrict__ st) {
-    if (st != nullptr && st->done) return;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nrows_level) return;
-    const int i = rows_of_level[t];
-    const long long s = indptr[i], e = indptr[i + 1];
-    double vi = v[i];
-    if (FORWARD) {
-        for (long long k = s; k < e; k++) {
-            const int c = indices[k];
-            if (c < i) vi -= q[k] * v[c]; else break;
-        }
-    } else {
-        for (long long k = e - 1; k >= s; k--) {
-            const int c = indices[k];
-            if (c > i) vi -= q[k] * v[c]; else break;
-        }
-        vi /= q[s + diagpos[i]];
-    }
-    v[i] = vi;
-}
-
 static int ensure_workspace(pf2_csr* A) {
     if (A->r) return PF2_OK;
     const size_t n = (size_t)A->rows;
@@ -213,88 +155,9 @@ static int ensure_workspace(pf2_csr* A) {
     return PF2_OK;
 }
 
-// host-side level schedule of the strictly-lower (forward) and strictly-upper (backward) dependency graphs
-static int schedule_levels(pf2_csr* A, const std::vector<long long>& indptr, const std::vector<int>& indices, bool lower,
-                           std::vector<int>& ptr, int** d_rows) {
-    const int n = A->rows;
-    std::vector<int> level(n, 0);
-    int maxl = 0;
-    if (lower) {
-        for (int i = 0; i < n; i++) {
-            int l = 0;
-            for (long long k = indptr[i]; k < indptr[i + 1] && indices[k] < i; k++) l = std::max(l, level[indices[k]] + 1);
-            level[i] = l; maxl = std::max(maxl, l);
-        }
-    } else {
-        for (int i = n - 1; i >= 0; i--) {
-            int l = 0;
-            for (long long k = indptr[i + 1] - 1; k >= indptr[i] && indices[k] > i; k--) l = std::max(l, level[indices[k]] + 1);
-            level[i] = l; maxl = std::max(maxl, l);
-        }
-    }
-    const int L = n ? maxl + 1 : 0;
-    ptr.assign((size_t)L + 1, 0);
-    std::vector<int> rows(n);
-    for (int i = 0; i < n; i++) ptr[level[i] + 1]++;
-    for (int l = 0; l < L; l++) ptr[l + 1] += ptr[l];
-    std::vector<int> cur(ptr.begin(), ptr.begin() + L);
-    for (int i = 0; i < n; i++) rows[cur[level[i]]++] = i;
-    PF2_TRY(dev_alloc(d_rows, (size_t)n));
-    PF2_CUDA(cudaMemcpy(*d_rows, rows.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
-    return PF2_OK;
-}
-
-static int build_levels(pf2_csr* A) {
-    if (A->level_rows) return PF2_OK;
-    pf2_ctx* c = A->ctx;
-    const int n = A->rows;
-    std::vector<long long> indptr((size_t)n + 1);
-    std::vector<int> indices((size_t)A->nnz);
-    PF2_CUDA(cudaMemcpyAsync(indptr.data(), A->indptr, sizeof(long long) * ((size_t)n + 1), cudaMemcpyDeviceToHost, c->stream));
-    PF2_CUDA(cudaMemcpyAsync(indices.data(), A->indices, sizeof(int) * (size_t)A->nnz, cudaMemcpyDeviceToHost, c->stream));
-    PF2_CUDA(cudaStreamSynchronize(c->stream));
-    PF2_TRY(schedule_levels(A, indptr, indices, true, A->h_level_ptr, &A->level_rows));
-    PF2_TRY(schedule_levels(A, indptr, indices, false, A->h_level_ptr_u, &A->level_rows_u));
-    return PF2_OK;
-}
-
-int ilu0_factor(pf2_csr* A) {
-    if (A->ilu_valid) return PF2_OK;
-    pf2_ctx* c = A->ctx;
-    PF2_TRY(build_levels(A));
-    if (!A->ilu) PF2_TRY(dev_alloc(&A->ilu, (size_t)A->nnz));
-    const int L = (int)A->h_level_ptr.size() - 1;
-    for (int l = 0; l < L; l++) {
-        const int cnt = A->h_level_ptr[l + 1] - A->h_level_ptr[l];
-        ilu0_level_kernel<<<(cnt + 127) / 128, 128, 0, c->stream>>>(cnt, A->level_rows + A->h_level_ptr[l], A->indptr, A->indices,
-                                                                    A->diagpos, A->data, A->ilu);
-        c->launches++;
-    }
-    PF2_LAUNCH_CHECK();
-    A->ilu_valid = true;
-    return PF2_OK;
-}
-
-// v = (LU)^-1 v in place; `factors` defaults to A's cached ILU(0)
-int ilu0_apply(pf2_csr* A, double* v, const CgState* st, const double* factors = nullptr) {
-    pf2_ctx* c = A->ctx;
-    const double* q = factors ? factors : A->ilu;
-    const int L = (int)A->h_level_ptr.size() - 1, Lu = (int)A->h_level_ptr_u.size() - 1;
-    for (int l = 1; l < L; l++) {      // level 0 rows have no strictly-lower entries
-        const int cnt = A->h_level_ptr[l + 1] - A->h_level_ptr[l];
-        ilu0_sweep_level_kernel<true><<<(cnt + 127) / 128, 128, 0, c->stream>>>(cnt, A->level_rows + A->h_level_ptr[l], A->indptr,
-                                                                                A->indices, A->diagpos, q, v, st);
-        c->launches++;
-    }
-    for (int l = 0; l < Lu; l++) {
-        const int cnt = A->h_level_ptr_u[l + 1] - A->h_level_ptr_u[l];
-        ilu0_sweep_level_kernel<false><<<(cnt + 127) / 128, 128, 0, c->stream>>>(cnt, A->level_rows_u + A->h_level_ptr_u[l], A->indptr,
-                                                                                 A->indices, A->diagpos, q, v, st);
-        c->launches++;
-    }
-    PF2_LAUNCH_CHECK();
-    return PF2_OK;
-}
+int ilu0_factor(pf2_csr* A);
+int ilu0_apply(pf2_csr* A, double* v, const CgState* st, const double* factors = nullptr);
+int ilu0_build_levels(pf2_csr* A);
 
 // enqueue one iteration
 // keep the Krylov vectors resident in L2 while the matrix streams through (evict-first loads): the vectors are a third
@@ -588,7 +451,7 @@ int pf2_ilu0_download(pf2_csr* A, double* data_host) {
 
 int pf2_preilu0_host(pf2_csr* M, const double* b_host, double* x_host) {
     pf2_ctx* c = M->ctx;
-    PF2_TRY(build_levels(M));
+    PF2_TRY(ilu0_build_levels(M));
     const size_t n = (size_t)M->rows;
     if (!M->xw) { PF2_TRY(dev_alloc(&M->xw, n)); PF2_TRY(dev_alloc(&M->bw, n)); }
     PF2_CUDA(cudaMemcpyAsync(M->xw, b_host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));

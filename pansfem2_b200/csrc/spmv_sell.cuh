@@ -208,7 +208,9 @@ __device__ __forceinline__ double sell_slice_acc(const IDX* __restrict__ sell_id
 // Partitioned matrix with the peer-memory backend (p2p != nullptr): only the slices of the owned rows are multiplied, interior slices
 // first; a warp that reaches a slice holding rows of a boundary plane first waits for that neighbour's plane of the current halo
 // epoch (deferred there by the p-update kernel), so the exchange overlaps the interior rows.
-template <bool DOT, class IDX, bool PERM = false, int NB = 1, int U = 6, bool CS = true>
+// (ORDERED is a separate instantiation: the plain kernel must keep its 32 registers -- 8 resident CTAs per SM; with the ordering logic
+// compiled in it needed 40 and the single-GPU product slowed down by 12 %.)
+template <bool DOT, class IDX, bool PERM = false, int NB = 1, int U = 6, bool CS = true, bool ORDERED = false>
 __global__ void __launch_bounds__(kThreads)
 spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* __restrict__ perm, const IDX* __restrict__ sell_idx, const double* __restrict__ sell_val,
                  const double* __restrict__ x, double* __restrict__ y, const CgState* __restrict__ st, double* dot_out,
@@ -221,10 +223,9 @@ spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* _
     double dot = 0.0;
     // virtual slice order: [s_lb, s_rb) interior, then [s_lo, s_lb) left boundary, then [s_rb, s_hi) right boundary
     int s_lo = 0, s_hi = nslices, s_lb = 0, s_rb = nslices;
-    bool ordered = false;
+    constexpr bool ordered = ORDERED;
     unsigned long long halo_epoch = 0ull;
-    if (!PERM && DOT && p2p != nullptr && p2p->defer_halo_wait) {
-        ordered = true;
+    if (ORDERED) {
         s_lo = p2p->own_lo / kSellC; s_hi = (p2p->own_hi + kSellC - 1) / kSellC;
         s_lb = s_lo; s_rb = s_hi;
         if (p2p->cntL > 0) s_lb = min(s_hi, (p2p->sendL + p2p->cntL + kSellC - 1) / kSellC);
@@ -235,7 +236,7 @@ spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* _
     bool waitedL = false, waitedR = false;
     for (int v = warp; v < n_all; v += nwarps) {
         int s = s_lo + v;
-        if (ordered) {
+        if constexpr (ORDERED) {
             if (v < n_int) s = s_lb + v;
             else {
                 const int w = v - n_int;

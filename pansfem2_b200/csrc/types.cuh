@@ -127,6 +127,8 @@ struct pf2_csr {
     int* level_rows = nullptr;     // rows sorted by dependency level of the forward (unit-L) sweep
     int* level_rows_u = nullptr;   // ... of the backward (U) sweep
     std::vector<int> h_level_ptr, h_level_ptr_u;   // host: first row of each level in the arrays above
+    unsigned int* ilu_ready = nullptr;   // sync-free sweeps: ready[i] == epoch <=> v[i] is final in the sweep numbered `epoch`
+    unsigned int ilu_epoch = 0;
     double* slab = nullptr;        // r | p | z | y | dvec contiguous (one L2 access-policy window)
     // instrumentation: every chunk one iteration is bracketed by events (sampled per-kernel device time)
     cudaEvent_t pev[2][4] = { { nullptr, nullptr, nullptr, nullptr }, { nullptr, nullptr, nullptr, nullptr } };

@@ -33,6 +33,8 @@ CASES = [
     # NCCL backend
     ("2d 96 40 --mma", {"PF2_P2P": "0"}), ("3d 16 8 6", {"PF2_P2P": "0"}),
     ("3d 16 8 6 --matrix-free", {}),
+    # ILU0CG under the partition: block-Jacobi ILU(0) per rank (CG.h:258-352), both backends
+    ("2d 96 40 --ilu", {}), ("3d 16 8 6 --ilu", {"PF2_P2P": "0"}),
 ]
 
 
@@ -55,7 +57,7 @@ def test_partitioned_loop_on_two_gpus_equals_single_gpu_loop(args, env):
 
 @pytest.mark.parametrize("make", [lambda: problems.cantilever2d(48, 32, opt_kind=problems.OPT_MMA, filter_kind=problems.FILTER_DENSITY),
                                   lambda: problems.cantilever3d(10, 6, 4)])
-@pytest.mark.parametrize("pcg", ["0", "1"])
+@pytest.mark.parametrize("pcg", ["0", "1", "ilu"])
 def test_partitioned_path_with_one_rank_equals_plain_loop(make, pcg, monkeypatch):
     """world size 1: no neighbours, but every reduction goes through the peer-memory LL allreduce of the partitioned kernels
     (pcg = 1: the persistent kernel's partitioned instantiation through pf2_csr_set_pcg_mode)."""
@@ -66,15 +68,16 @@ def test_partitioned_path_with_one_rank_equals_plain_loop(make, pcg, monkeypatch
         dist.init_process_group("gloo", rank=0, world_size=1)
     P = make()
     ctx = capi.Context(0)
-    ref = capi.Simp(ctx, P)
+    solver = capi.SOLVER_ILU0CG if pcg == "ilu" else capi.SOLVER_SCALINGCG
+    ref = capi.Simp(ctx, P, solver=solver)
     fr = [ref.iterate(check_convergence=False) for _ in range(3)]
     o = ref.get()
     ref.close()
     D = capi.Dist(ctx, 0, 1)
     S = partition.slab(P, 0, 1)
-    sim = capi.Simp(ctx, S.local)
+    sim = capi.Simp(ctx, S.local, solver=solver)
     D.set_simp_partition(sim, S, P.nelem)
-    sim.A.set_pcg_mode(int(pcg))
+    sim.A.set_pcg_mode(1 if pcg == "1" else 0)
     fd = [sim.iterate(check_convergence=False) for _ in range(3)]
     od = sim.get()
     assert pcg == "1" or sim.A.pcg_stats()["solves"] == 0      # (ragged SELL-C-sigma slabs fall back to the three-kernel loop under pcg = 1)

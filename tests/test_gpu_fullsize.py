@@ -94,3 +94,44 @@ def test_filter_partition_of_unity_and_oc_volume(ctx, big2d):
     g = flt.apply_host(x).sum() / (0.5 * P.nelem) - 1.0
     assert abs(g) < 5e-3                                        # bisection stops at 1e-3 relative lambda width
     oc.close()
+
+
+def test_mid_size_400x200_value_for_value_against_the_oracle(ctx):
+    """160 k dof (the largest mesh the CPU oracle solves in seconds): K (pattern and values), F, u, compliance and df/drho of one design
+    pass compared entry by entry with the oracle -- sample_optimize_density_oc.cpp:113-162 on a random density field."""
+    from oracle import portlib as orc
+    P = problems.cantilever2d(400, 200, opt_kind=problems.OPT_OC, filter_kind=problems.FILTER_DENSITY)
+    rng = np.random.Generator(np.random.MT19937(20201017))
+    rho = rng.uniform(0.01, 1.0, P.nelem)
+    Emod = P.E1 * rho ** P.penal + P.E0 * (1.0 - rho ** P.penal)
+    orc.set_num_threads(8)
+    So, n2g_o, ufix_o, _ = orc.assemble(P.eq, P.coords, P.conn, P.fixed, P.loads, Emod, P.poisson, P.thickness)
+    ip_o, ix_o, da_o, F_o = So.arrays()
+    S = capi.Simp(ctx, P)
+    rho_d = ctx.array(rho)
+    S.A.assemble(S.mesh, S.dofmap, P.eq, (P.E0, P.E1, P.poisson, P.penal, P.thickness), P.loads, rho=rho_d)
+    ip, ix, da, F = S.A.download()
+    assert S.A.rows == 160800 and np.array_equal(ip, ip_o) and np.array_equal(ix, ix_o)           # numbering and pattern: bit-exact
+    assert np.array_equal(S.dofmap.get(), n2g_o.reshape(P.nnode, P.ndof))
+    assert np.abs(da - da_o).max() < 1e-13 * np.abs(da_o).max() and np.array_equal(F, F_o)
+    xo, it_o, _ = So.solve(1, F_o)
+    x_d = ctx.empty(S.A.rows)
+    for mode in (0, 1):                                        # three-kernel loop and persistent kernel
+        S.A.set_pcg_mode(mode)
+        it, relres = S.A.solve(capi.SOLVER_SCALINGCG, S.A.device_F(), x_d)
+        x = x_d.download()
+        assert relres < 1e-10 and abs(it - it_o) <= max(3, it_o // 50), (mode, it, it_o)
+        assert np.linalg.norm(F_o - So.spmv(x)) < 2e-10 * np.linalg.norm(F_o)
+        assert np.abs(x - xo).max() < 1e-7 * np.abs(xo).max()                                   # two converged solves of a system with cond ~ 1e9
+    u = np.zeros((P.nnode, P.ndof))
+    free = n2g_o.reshape(P.nnode, P.ndof) >= 0
+    u[free] = xo[n2g_o.reshape(P.nnode, P.ndof)[free]]
+    f, dfdrho, _ = capi.compliance_sens(S.mesh, P.eq, ctx.array(u.ravel()), rho_d, (P.E0, P.E1, P.poisson, P.penal, P.thickness, P.scale0))
+    fo, _, dfo = orc.compliance_sens(P.eq, P.coords, P.conn, u, rho, P.E0, P.E1, P.poisson, P.thickness, P.penal, P.scale0)
+    assert abs(f - fo) < 1e-12 * abs(fo) and np.abs(dfdrho - dfo).max() < 1e-12 * np.abs(dfo).max()
+    # and through the GPU's own solution: compliance within the north_star tolerance
+    u_g = np.zeros((P.nnode, P.ndof))
+    u_g[free] = x[n2g_o.reshape(P.nnode, P.ndof)[free]]
+    f_g, _, _ = capi.compliance_sens(S.mesh, P.eq, ctx.array(u_g.ravel()), rho_d, (P.E0, P.E1, P.poisson, P.penal, P.thickness, P.scale0))
+    assert abs(f_g - fo) < 1e-8 * abs(fo)
+    S.close()
