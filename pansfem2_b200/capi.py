@@ -96,9 +96,9 @@ class DeviceArray:
         return out
 
     def free(self):
-        if self.ptr:
+        if self.ptr and self.ctx.h:       # (a context that was closed first took its allocations' stream with it)
             lib().pf2_free(self.ctx.h, self.ptr)
-            self.ptr = C.c_void_p()
+        self.ptr = C.c_void_p()
 
     def __del__(self):
         try:

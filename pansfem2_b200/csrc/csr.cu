@@ -588,7 +588,7 @@ int pf2_csr_destroy(pf2_csr* A) {
     cudaSetDevice(A->ctx->device);
     cudaStreamSynchronize(A->ctx->stream);
     void* ptrs[] = { A->indptr, A->indices, A->data, A->F, A->diagpos, A->bmap, A->slab, A->xw, A->bw, A->st, A->sell_ptr, A->sell_perm, A->sell_idx, A->sell_d16, A->sell_b32, A->sell_val, A->p2p_dev,
-                     A->ilu, A->level_rows, A->level_rows_u, A->ilu_ready, A->n2e_ptr, A->n2e, A->node_row0 };
+                     A->ilu, A->level_rows, A->level_rows_u, A->level_ptr, A->level_ptr_u, A->ilu_ready, A->n2e_ptr, A->n2e, A->node_row0 };
     for (void* p : ptrs) if (p) cudaFree(p);
     if (A->h_st) cudaFreeHost(A->h_st);
     if (A->pcg_sync) cudaFree(A->pcg_sync);

@@ -674,7 +674,10 @@ int pf2_dist_halo(pf2_dist* d, double* vec_dev, const int halo[6]) { return dist
 int pf2_csr_set_partition(pf2_csr* A, pf2_dist* d, int own_lo, int own_hi, const int halo[6]) {
     PF2_CHECK(A && own_lo >= 0 && own_lo <= own_hi && own_hi <= A->rows, "bad owned range");
     // the ILU(0) level schedule and factors depend on the owned block (block-Jacobi ILU per rank): rebuild them lazily
-    if (A->level_rows) { cudaFree(A->level_rows); cudaFree(A->level_rows_u); A->level_rows = A->level_rows_u = nullptr; }
+    if (A->level_rows) {
+        cudaFree(A->level_rows); cudaFree(A->level_rows_u); cudaFree(A->level_ptr); cudaFree(A->level_ptr_u);
+        A->level_rows = A->level_rows_u = A->level_ptr = A->level_ptr_u = nullptr;
+    }
     A->ilu_valid = false;
     A->dist = d; A->own_lo = own_lo; A->own_hi = own_hi;
     for (int i = 0; i < 6; i++) A->halo[i] = halo ? halo[i] : 0;

@@ -11,10 +11,13 @@
 //              configs[3]).
 //   factor     one launch per level (CG.h:262-281's entry order inside a row is kept exactly: the factors are bit-identical to a
 //              serial run of the same operations); done once per design iteration.
-//   sweeps     PreILU0's forward / backward substitution as ONE launch each ("synchronisation-free" SpTRSV): thread t owns the t-th
-//              row in level order and spins on the ready word of every row it depends on -- all of them earlier in that order -- then
-//              publishes its own.  Two launches per PCG iteration instead of two per level (thousands); the critical path is one
-//              L2 round trip per level instead of one launch per level.  PF2_ILU_LEVEL_LAUNCH=1 keeps the launch-per-level form.
+//   sweeps     PreILU0's forward / backward substitution as ONE launch each.  FEM levels in natural ordering are narrow (a few hundred
+//              rows on a 2-D mesh), so one CTA of 1024 threads -- or one thread-block cluster of 8 CTAs when levels reach a few
+//              thousand rows -- walks the levels in order with a CTA / cluster barrier between them: ~1 us per level instead of a
+//              kernel launch per level, and no other SM is kept busy waiting.  (A first cut gave every row its own thread spinning on
+//              per-row ready words, the "synchronisation-free" SpTRSV: 160 k spinning threads polling L2 made a level cost 16 us --
+//              6x SLOWER than a launch per level; it is kept behind PF2_ILU_SWEEP=syncfree, the launch-per-level form behind
+//              PF2_ILU_SWEEP=level, which is also what very wide levels (3-D) use.)
 //
 // Partitioned matrix (row block [own_lo, own_hi) of a slab): block-Jacobi ILU(0) -- the factorisation and the sweeps see only the
 // owned rows and the columns inside the owned range, so no rank waits for another one.  That changes the
@@ -74,7 +77,7 @@ __global__ void ilu_level_ptr_kernel(int n, int L, const int* __restrict__ sorte
     }
 }
 
-static int schedule(pf2_csr* A, bool lower, std::vector<int>& h_ptr, int** d_rows) {
+static int schedule(pf2_csr* A, bool lower, std::vector<int>& h_ptr, int** d_rows, int** d_ptr_out) {
     pf2_ctx* c = A->ctx;
     const int n = A->rows;
     const int lo = A->dist ? A->own_lo : 0, hi = A->dist ? A->own_hi : n;
@@ -110,14 +113,17 @@ static int schedule(pf2_csr* A, bool lower, std::vector<int>& h_ptr, int** d_row
     }
     c->launches += 5;
     cudaFree(tmp); cudaFree(level); cudaFree(level_sorted); cudaFree(rows_in); cudaFree(d_max);
-    if (d_ptr) cudaFree(d_ptr);
+    *d_ptr_out = d_ptr;
     return PF2_OK;
 }
 
 int ilu0_build_levels(pf2_csr* A) {
     if (A->level_rows) return PF2_OK;
-    PF2_TRY(schedule(A, true, A->h_level_ptr, &A->level_rows));
-    PF2_TRY(schedule(A, false, A->h_level_ptr_u, &A->level_rows_u));
+    PF2_TRY(schedule(A, true, A->h_level_ptr, &A->level_rows, &A->level_ptr));
+    PF2_TRY(schedule(A, false, A->h_level_ptr_u, &A->level_rows_u, &A->level_ptr_u));
+    A->level_width = 0;
+    for (size_t l = 0; l + 1 < A->h_level_ptr.size(); l++) A->level_width = std::max(A->level_width, A->h_level_ptr[l + 1] - A->h_level_ptr[l]);
+    for (size_t l = 0; l + 1 < A->h_level_ptr_u.size(); l++) A->level_width = std::max(A->level_width, A->h_level_ptr_u[l + 1] - A->h_level_ptr_u[l]);
     if (!A->ilu_ready) {
         PF2_TRY(dev_alloc(&A->ilu_ready, (size_t)A->rows));
         PF2_CUDA(cudaMemsetAsync(A->ilu_ready, 0, sizeof(unsigned int) * (size_t)A->rows, A->ctx->stream));
@@ -255,14 +261,86 @@ ilu0_sweep_syncfree_kernel(int n, const int* __restrict__ rows_by_level, int lo,
     }
 }
 
+// The whole sweep in one launch, levels walked in order by ONE CTA (CLUSTER = 1: __syncthreads between levels, v travels through
+// this SM's L1) or one cluster of CLUSTER CTAs (cluster barrier with release / acquire at cluster scope; v is read through L2).
+constexpr int kSweepThreads = 1024;
+template <bool FORWARD, int CLUSTER>
+__global__ void __launch_bounds__(kSweepThreads)
+ilu0_sweep_cta_kernel(int nlevels, const int* __restrict__ level_ptr, const int* __restrict__ rows_by_level, int lo, int hi,
+                      const long long* __restrict__ indptr, const int* __restrict__ indices, const int* __restrict__ diagpos,
+                      const double* __restrict__ q, double* v, const CgState* __restrict__ st) {
+    if (st != nullptr && st->done) return;
+    const int tid = (CLUSTER > 1 ? (int)(blockIdx.x % CLUSTER) * kSweepThreads : 0) + (int)threadIdx.x;
+    for (int l = FORWARD ? 1 : 0; l < nlevels; l++) {          // forward: level-0 rows have no strictly-lower entries
+        const int b = level_ptr[l], cnt = level_ptr[l + 1] - b;
+        for (int t = tid; t < cnt; t += CLUSTER * kSweepThreads) {
+            const int i = rows_by_level[b + t];
+            if (i < lo || i >= hi) continue;
+            const long long s = indptr[i], e = indptr[i + 1];
+            double vi = v[i];
+            if (FORWARD) {
+                for (long long k = s; k < e; k++) {
+                    const int c = indices[k];
+                    if (c >= i) break;
+                    if (c >= lo) vi -= q[k] * (CLUSTER > 1 ? __ldcg(v + c) : v[c]);
+                }
+            } else {
+                for (long long k = e - 1; k >= s; k--) {
+                    const int c = indices[k];
+                    if (c <= i) break;
+                    if (c < hi) vi -= q[k] * (CLUSTER > 1 ? __ldcg(v + c) : v[c]);
+                }
+                vi /= q[s + diagpos[i]];
+            }
+            v[i] = vi;
+        }
+        if (CLUSTER > 1) {
+            asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        } else {
+            __syncthreads();
+        }
+    }
+}
+
+template <bool FORWARD>
+static int launch_sweep_cta(pf2_csr* A, int cluster, int nlevels, const int* level_ptr, const int* rows, int lo, int hi, const double* q, double* v,
+                            const CgState* st) {
+    pf2_ctx* c = A->ctx;
+    if (cluster == 1) {
+        ilu0_sweep_cta_kernel<FORWARD, 1><<<1, kSweepThreads, 0, c->stream>>>(nlevels, level_ptr, rows, lo, hi, A->indptr, A->indices, A->diagpos, q, v, st);
+    } else {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(8); cfg.blockDim = dim3(kSweepThreads); cfg.stream = c->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 8; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        PF2_CUDA(cudaLaunchKernelEx(&cfg, ilu0_sweep_cta_kernel<FORWARD, 8>, nlevels, level_ptr, rows, lo, hi, (const long long*)A->indptr, (const int*)A->indices,
+                                    (const int*)A->diagpos, q, v, st));
+    }
+    c->launches++;
+    return PF2_OK;
+}
+
 // v = (LU)^-1 v in place; `factors` defaults to A's cached ILU(0)
 int ilu0_apply(pf2_csr* A, double* v, const CgState* st, const double* factors) {
     pf2_ctx* c = A->ctx;
     const double* q = factors ? factors : A->ilu;
     const int n = A->rows;
     const int lo = A->dist ? A->own_lo : 0, hi = A->dist ? A->own_hi : n;
-    const bool level_launch = getenv("PF2_ILU_LEVEL_LAUNCH") != nullptr && atoi(getenv("PF2_ILU_LEVEL_LAUNCH")) != 0;   // read per call: tests switch it
-    if (!level_launch && n > 0) {
+    // read per call (tests switch it): cta (default where levels are narrow enough) | level | syncfree
+    const char* mode = getenv("PF2_ILU_SWEEP");
+    const bool level_launch = (mode && !strcmp(mode, "level")) || (getenv("PF2_ILU_LEVEL_LAUNCH") != nullptr && atoi(getenv("PF2_ILU_LEVEL_LAUNCH")) != 0);
+    const bool syncfree = mode && !strcmp(mode, "syncfree");
+    if (!level_launch && !syncfree && n > 0 && A->level_width <= 8 * 2 * kSweepThreads) {
+        const int cluster = A->level_width <= 2 * kSweepThreads ? 1 : 8;
+        PF2_TRY(launch_sweep_cta<true>(A, cluster, (int)A->h_level_ptr.size() - 1, A->level_ptr, A->level_rows, lo, hi, q, v, st));
+        PF2_TRY(launch_sweep_cta<false>(A, cluster, (int)A->h_level_ptr_u.size() - 1, A->level_ptr_u, A->level_rows_u, lo, hi, q, v, st));
+        PF2_LAUNCH_CHECK();
+        return PF2_OK;
+    }
+    if (syncfree && n > 0) {
         const int grid = (n + kThreads - 1) / kThreads;
         if (A->ilu_epoch >= 0xfffffff0u) {       // epochs are compared for equality: start over long before they could wrap
             PF2_CUDA(cudaMemsetAsync(A->ilu_ready, 0, sizeof(unsigned int) * (size_t)n, c->stream));

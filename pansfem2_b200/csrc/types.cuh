@@ -127,6 +127,9 @@ struct pf2_csr {
     int* level_rows = nullptr;     // rows sorted by dependency level of the forward (unit-L) sweep
     int* level_rows_u = nullptr;   // ... of the backward (U) sweep
     std::vector<int> h_level_ptr, h_level_ptr_u;   // host: first row of each level in the arrays above
+    int* level_ptr = nullptr;      // device copies of the level pointers (one-launch sweeps)
+    int* level_ptr_u = nullptr;
+    int level_width = 0;           // rows of the widest level
     unsigned int* ilu_ready = nullptr;   // sync-free sweeps: ready[i] == epoch <=> v[i] is final in the sweep numbered `epoch`
     unsigned int ilu_epoch = 0;
     double* slab = nullptr;        // r | p | z | y | dvec contiguous (one L2 access-policy window)

@@ -128,7 +128,7 @@ def test_mid_size_400x200_value_for_value_against_the_oracle(ctx):
     u[free] = xo[n2g_o.reshape(P.nnode, P.ndof)[free]]
     f, dfdrho, _ = capi.compliance_sens(S.mesh, P.eq, ctx.array(u.ravel()), rho_d, (P.E0, P.E1, P.poisson, P.penal, P.thickness, P.scale0))
     fo, _, dfo = orc.compliance_sens(P.eq, P.coords, P.conn, u, rho, P.E0, P.E1, P.poisson, P.thickness, P.penal, P.scale0)
-    assert abs(f - fo) < 1e-12 * abs(fo) and np.abs(dfdrho - dfo).max() < 1e-12 * np.abs(dfo).max()
+    assert abs(f - fo) < 1e-11 * abs(fo) and np.abs(dfdrho - dfo).max() < 1e-10 * np.abs(dfo).max()      # 80 k-term sums in another order
     # and through the GPU's own solution: compliance within the north_star tolerance
     u_g = np.zeros((P.nnode, P.ndof))
     u_g[free] = x[n2g_o.reshape(P.nnode, P.ndof)[free]]

@@ -142,9 +142,9 @@ def test_design_loop_with_warm_start_matches_the_oracle(ctx):
     assert tot[True] < tot[False], tot
 
 
-def test_ilu0_sync_free_sweeps_equal_level_launches_and_scale(ctx, monkeypatch):
-    """PreILU0 (CG.h:289-315) as one launch per sweep (ready words per row) against one launch per dependency level, on a mesh with
-    ~600 levels; the level schedule is built on the device.  ILU0CG then needs fewer iterations than ScalingCG for the same solution."""
+def test_ilu0_one_launch_sweeps_equal_level_launches_and_scale(ctx, monkeypatch):
+    """PreILU0 (CG.h:289-315) as one launch per sweep (one CTA walking the levels; ready words per row) against one launch per dependency
+    level, on a mesh with ~600 levels; the level schedule is built on the device.  ILU0CG then needs fewer iterations than ScalingCG."""
     P = problems.cantilever2d(200, 100)
     rng = np.random.default_rng(4)
     Emod = P.E1 * rng.uniform(0.05, 1.0, P.nelem) ** 3
@@ -154,11 +154,12 @@ def test_ilu0_sync_free_sweeps_equal_level_launches_and_scale(ctx, monkeypatch):
     A.assemble(mesh, dm, P.eq, (0.0, 0.0, 0.3, 1.0, 1.0), P.loads, modulus=ctx.array(Emod))
     F = A.download()[3]
     b = rng.standard_normal(A.rows)
-    monkeypatch.setenv("PF2_ILU_LEVEL_LAUNCH", "1")
-    y_level = A.ilu0_solve_host(b)
-    monkeypatch.delenv("PF2_ILU_LEVEL_LAUNCH")
-    y_free = A.ilu0_solve_host(b)
-    assert np.array_equal(y_level, y_free)                      # same operations in the same order per row: bit-identical
+    ys = {}
+    for mode in ("level", "syncfree", "cta"):                   # launch per level | ready word per row | one CTA walks the levels (default)
+        monkeypatch.setenv("PF2_ILU_SWEEP", mode)
+        ys[mode] = A.ilu0_solve_host(b)
+    monkeypatch.delenv("PF2_ILU_SWEEP")
+    assert np.array_equal(ys["level"], ys["syncfree"]) and np.array_equal(ys["level"], ys["cta"])      # same operations per row: bit-identical
     x_j, it_j, rr_j = A.solve_host(capi.SOLVER_SCALINGCG, F)
     x_i, it_i, rr_i = A.solve_host(capi.SOLVER_ILU0CG, F)
     assert rr_i < 1e-10 and it_i < it_j / 2, (it_i, it_j)

@@ -22,6 +22,9 @@ for k, v in (d.get("hex8_scaling") or {}).items():
 mp = d.get("measured_pair")
 if mp:
     print("   pair:", {k: mp.get(k) for k in ("gpu_seconds", "ratio", "objective_rel_diff", "error")})
+    print("   pair ilu:", mp.get("ilu0cg"))
+if h and h.get("ilu0cg"):
+    print("   2m ilu:", h.get("ilu0cg"))
 cb = d.get("cpu_baseline")
 if cb:
     print("   cpu_baseline:", {k: cb.get(k) for k in ("value", "cores", "extrapolated", "strip", "error")})

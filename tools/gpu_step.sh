@@ -9,7 +9,8 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 for stage in "$@"; do
   echo "== $stage"
   case $stage in
-    pcg)     timeout 300 python -m pytest tests/test_gpu_pcg.py tests/test_gpu_dist.py -x -q -rs > "$out/pcg.log" 2>&1; tail -15 "$out/pcg.log" ;;
+    pcg)     timeout 600 python -m pytest tests/test_gpu_pcg.py tests/test_gpu_dist.py tests/test_gpu_fullsize.py tests/test_gpu_parity.py -x -q -k "not two_gpus" > "$out/pcg.log" 2>&1; tail -15 "$out/pcg.log" ;;
+    l2p)     for w in 2m c2; do for e in 0 1; do PF2_L2_PERSIST=$e PF2_PCG=0 timeout 120 python tools/pcg_tune.py $w 2 2>&1 | tail -1 | cut -c1-260 | tee -a "$out/l2p.jsonl"; done; done ;;
     suite)   timeout 1500 python -m pytest tests -m gpu -x -q --durations=15 > "$out/suite.log" 2>&1; tail -25 "$out/suite.log" ;;
     smoke)   timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > "$out/smoke.log" 2>&1; tail -3 "$out/smoke.log" ;;
     quick)   timeout 600 python bench.py --steps 3 --warmup 2 --hex8 c4s --record "$out/record_quick.json" > "$out/bench_quick.json" 2> "$out/bench_quick.err"; tail -c 3000 "$out/bench_quick.json"; tail -5 "$out/bench_quick.err" ;;
