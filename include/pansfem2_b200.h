@@ -60,9 +60,11 @@ enum { PF2_PHYS_PLANESTRAIN = 0, PF2_PHYS_SOLID = 1, PF2_PHYS_HEAT = 2, PF2_PHYS
  * Homogenization.h:141-280 - plane elements with a caller-supplied 3 x 3 constitutive matrix; one element through pf2_element_matrix_d. */
 enum { PF2_ADV_ADVECTION = 1, PF2_ADV_DIFFUSION = 2, PF2_ADV_SUPG = 4, PF2_ADV_SHOCK = 8, PF2_ADV_MASS = 16, PF2_ADV_MASS_SUPG = 32 };
 enum { PF2_SHAPE_DEFAULT = 0, PF2_SHAPE_T3 = 1, PF2_SHAPE_T6 = 2, PF2_SHAPE_Q4 = 3, PF2_SHAPE_Q8 = 4, PF2_SHAPE_TET4 = 5,
-       PF2_SHAPE_HEX8 = 6, PF2_SHAPE_HEX20 = 7 };
+       PF2_SHAPE_HEX8 = 6, PF2_SHAPE_HEX20 = 7,
+       PF2_SHAPE_LINE2 = 8, PF2_SHAPE_LINE3 = 9 };      /* ShapeFunction2Line / 3Line (ShapeFunction.h:20-84): edges carrying surface loads */
 enum { PF2_QUAD_DEFAULT = 0, PF2_QUAD_G1TRI = 1, PF2_QUAD_G3TRI = 2, PF2_QUAD_G1SQ = 3, PF2_QUAD_G4SQ = 4, PF2_QUAD_G9SQ = 5,
-       PF2_QUAD_G1TET = 6, PF2_QUAD_G8CUBE = 7, PF2_QUAD_G27CUBE = 8 };
+       PF2_QUAD_G1TET = 6, PF2_QUAD_G8CUBE = 7, PF2_QUAD_G27CUBE = 8,
+       PF2_QUAD_G1LINE = 9, PF2_QUAD_G2LINE = 10 };     /* Gauss1Line / Gauss2Line (GaussIntegration.h:18-60) */
 #define PF2_EQ_CODE(phys, shape, quad, quad2) ((phys) | ((shape) << 8) | ((quad) << 16) | ((quad2) << 24))
 /* solver selection: CG (CG.h:124), ScalingCG (CG.h:420), ILU0CG (CG.h:320); for non-symmetric systems BiCGSTAB (CG.h:159),
  * BiCGSTAB2 (CG.h:199), ScalingBiCGSTAB (CG.h:458), ILU0BiCGSTAB (CG.h:357) */
@@ -117,6 +119,9 @@ int pf2_flush_l2(pf2_ctx* ctx);
  * (std::vector<std::vector<int>> flattened).  dim/npe: 2/4 (Q4) or 3/8 (hex8). */
 int pf2_mesh_create(pf2_ctx* ctx, int dim, int nnode, const double* coords_host, int npe, int nelem,
                     const int* conn_host, pf2_mesh** out);
+/* a second element list over the nodes of `base` -- the edges that carry a surface load, a sub-region with a body force (the drivers'
+ * `edges` lists, sample_planestrain.cpp:23,52); shares the node coordinates on the device: destroy it before `base` */
+int pf2_mesh_create_on_nodes(pf2_mesh* base, int npe, int nelem, const int* conn_host, pf2_mesh** out);
 int pf2_mesh_destroy(pf2_mesh* mesh);
 /* SetDirichlet (BoundaryCondition.h:20-25) + Renumbering (Assembling.h:175-186): fixed dofs get -1, free dofs are
  * numbered node-major / dof-minor.  *kdegree_out = KDEGREE.  nfixed = 0 reproduces RemoveBoundaryConditions
@@ -214,6 +219,19 @@ int pf2_ilu0_solve_host(pf2_csr* A, const double* b_host, double* x_host);   /* 
 /* PreILU0(M, b) (CG.h:289-315) where the VALUES of M are the factors (what the reference's ILU0 returns) */
 int pf2_preilu0_host(pf2_csr* M, const double* b_host, double* x_host);
 
+/* ---- load vectors (PlaneStrainSurfaceForce / PlaneStrainBodyForce PlaneStrain.h:421,503; PlaneStressSurfaceForce / BodyForce
+ *      PlaneStress.h:98,134; HeatTransferSurfaceFlux HeatTransfer.h:76) for a whole batch of elements, assembled on the device ------ */
+/* The reference evaluates the caller's force functor at x_g = X_e^T N(r_g) (PlaneStrain.h:441,522).  A functor cannot cross the ABI, so
+ * the batched form is two calls: pf2_integration_points hands out every x_g (xg_dev[nelem][ngauss][2]), the caller evaluates its
+ * force density there in one go, pf2_load_vector integrates and assembles.  mesh: a pf2_mesh over the SAME node numbering whose
+ * elements are the loaded edges (PF2_SHAPE_LINE2 / _LINE3 with PF2_QUAD_G1LINE / _G2LINE) or areas (T3, T6, Q4, Q8 with their rules). */
+int pf2_integration_points(pf2_mesh* mesh, int shape, int quad, double* xg_dev);
+/* F[row(n, i)] += sum_g N_n(r_g) f_i(x_g) m_g t w_g   (Assembling(F, Fe, ...) Assembling.h:132-147), i < ndof of the dof map;
+ * m_g = |dX/dr| on edges (w_g = Weights[g][0]), det(dX/dr) on areas (w_g = Weights[g][0] * Weights[g][1]).
+ * f_gauss_dev[nelem][ngauss][ndof]: the force density at the integration points, or NULL: the constant vector f_const[ndof]. */
+int pf2_load_vector(pf2_mesh* mesh, pf2_dofmap* map, int shape, int quad, const double* f_const, const double* f_gauss_dev, double t,
+                    double* F_dev);
+
 /* Disassembling (Assembling.h:163-171): free dofs from the solution, fixed dofs keep their Dirichlet value */
 int pf2_disassemble(pf2_dofmap* map, const double* x_dev, double* u_nodal_dev);
 
@@ -290,6 +308,12 @@ int pf2_simp_iterate(pf2_simp* S, int check_convergence, double stats[8]);
 int pf2_simp_iterate_host(pf2_simp* S, int check_convergence, const double* s_in_host, double* s_out_host,
                           double* rho_out_host, double stats[8]);
 int pf2_simp_get(pf2_simp* S, double* s_host, double* rho_host, double* u_nodal_host, double* r_nodal_host);
+/* The drivers' VTK dump of one iteration (sample_optimize_density_oc.cpp:175-184 = MakeHeadderToVTK + AddPointsToVTK + AddElementToVTK +
+ * AddElementTypes + AddPointVectors u [+ r] + AddElementScalers rho as "s", ExportToVTK.h:19-137) written from the device-resident state:
+ * the fields are staged on the device in the writers' layout, cross in one copy and are formatted like `ostream << double`, so the file
+ * is byte-identical to what the reference's writers produce from the same values.  cell_type: VTK cell type of every element (9 = quad,
+ * 5 = triangle, 12 = hexahedron); with_reactions: also recompute and write the nodal reactions r = K(rho) u. */
+int pf2_simp_export_vtk(pf2_simp* S, const char* path, int cell_type, int with_reactions);
 /* per-phase device time of the last iteration, ms: {filter, assemble, solve, compliance+sens, filter-sens, update} */
 int pf2_simp_phase_ms(pf2_simp* S, double ms[6]);
 int pf2_simp_cg_stats(pf2_simp* S, double* spmv_ms_avg, long long* spmv_calls);

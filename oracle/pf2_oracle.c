@@ -740,6 +740,71 @@ void orc_advdiff_assemble(orc_system* S, int shape, int quad, int terms, const d
 }
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Load vectors: PlaneStrainSurfaceForce / PlaneStrainBodyForce (FEM/Equation/PlaneStrain.h:421-455, 503-537), PlaneStressSurfaceForce /
+ * PlaneStressBodyForce (PlaneStress.h:98-167, the same arithmetic) and HeatTransferSurfaceFlux (HeatTransfer.h:76-98).
+ *   per integration point:  N, dNdr ; x = X^T N ; dXdr = dNdr X ; m = sqrt((dXdr dXdr^T)(0,0)) on lines | det(dXdr) on areas
+ *                           Fe += B^T f(x) * m * t * w0 [* w1]         evaluated left to right like the reference's operator chain
+ * Line shapes ShapeFunction2Line / 3Line (ShapeFunction.h:20-84), rules Gauss1Line / Gauss2Line (GaussIntegration.h:18-60).
+ * The force functor is replaced by its values fg[g][ndof] at the integration points (orc_integration_points gives the x_g).
+ * ---------------------------------------------------------------------------------------------------------- */
+enum { SHAPE_LINE2 = 8, SHAPE_LINE3 = 9, QUAD_G1LINE = 9, QUAD_G2LINE = 10 };
+static int load_npe(int shape) { return shape == SHAPE_LINE2 ? 2 : shape == SHAPE_LINE3 ? 3 : npe_of_shape(shape); }
+static int load_ngauss(int quad) { return quad == QUAD_G1LINE ? 1 : quad == QUAD_G2LINE ? 2 : quad_count(quad); }
+static void load_point(int shape, int quad, int g, double* N, double* d /* [2][npe] */, double* w /* [2] */) {
+    const int npe = load_npe(shape);
+    if (shape == SHAPE_LINE2 || shape == SHAPE_LINE3) {
+        double x = 0.0;
+        w[0] = 2.0; w[1] = 1.0;
+        if (quad == QUAD_G2LINE) { x = (g == 0 ? -1.0 : 1.0) / sqrt(3.0); w[0] = 1.0; }
+        if (shape == SHAPE_LINE2) { N[0] = 0.5 * (1 - x); N[1] = 0.5 * (1 + x); d[0] = -0.5; d[1] = 0.5; }
+        else {
+            N[0] = -0.5 * (1.0 - x) * x; N[1] = 0.5 * x * (1.0 + x); N[2] = (1.0 - x) * (1.0 + x);
+            d[0] = -0.5 * (1.0 - 2.0 * x); d[1] = 0.5 * (1.0 + 2.0 * x); d[2] = -2.0 * x;
+        }
+        for (int n = 0; n < npe; n++) d[npe + n] = 0.0;
+        return;
+    }
+    double r[3], w3[3];
+    quad_point(quad, g, r, w3);
+    w[0] = w3[0]; w[1] = w3[1];
+    shape_n2d(shape, r, N);
+    shape_dndr(shape, r, d);
+}
+int orc_load_ngauss(int quad) { return load_ngauss(quad); }
+/* xg[g][2] = X^T N(r_g) for one element */
+void orc_integration_points(int shape, int quad, const double* xe, double* xg) {
+    const int npe = load_npe(shape), ng = load_ngauss(quad);
+    for (int g = 0; g < ng; g++) {
+        double N[8], d[16], w[2];
+        load_point(shape, quad, g, N, d, w);
+        double x0 = 0.0, x1 = 0.0;
+        for (int n = 0; n < npe; n++) { x0 += xe[2 * n] * N[n]; x1 += xe[2 * n + 1] * N[n]; }     /* X.Transpose()*N: Matrix*Vector sums over the nodes in order */
+        xg[2 * g] = x0; xg[2 * g + 1] = x1;
+    }
+}
+/* Fe[npe*ndof] of one element */
+void orc_load_vector(int shape, int quad, int ndof, const double* xe, const double* fg, double t, double* Fe) {
+    const int npe = load_npe(shape), ng = load_ngauss(quad);
+    const int line = (shape == SHAPE_LINE2 || shape == SHAPE_LINE3);
+    for (int k = 0; k < npe * ndof; k++) Fe[k] = 0.0;
+    for (int g = 0; g < ng; g++) {
+        double N[8], d[16], w[2];
+        load_point(shape, quad, g, N, d, w);
+        double j00 = 0.0, j01 = 0.0, j10 = 0.0, j11 = 0.0;
+        for (int n = 0; n < npe; n++) { j00 += d[n] * xe[2 * n]; j01 += d[n] * xe[2 * n + 1]; j10 += d[npe + n] * xe[2 * n]; j11 += d[npe + n] * xe[2 * n + 1]; }
+        const double m = line ? sqrt(j00 * j00 + j01 * j01) : (j00 * j11 - j01 * j10);
+        for (int n = 0; n < npe; n++)
+            for (int i = 0; i < ndof; i++) {
+                double v = N[n] * fg[g * ndof + i];           /* (B^T f)(ndof*n + i) */
+                v = v * m; v = v * t; v = v * w[0];
+                if (!line) v = v * w[1];
+                Fe[n * ndof + i] += v;
+            }
+    }
+}
+
+
+/* ------------------------------------------------------------------------------------------------------------
  * CSR<T>::operator*   src/LinearAlgebra/Models/CSR.h:109-122 (the reference's only OpenMP loop)
  * ---------------------------------------------------------------------------------------------------------- */
 void orc_spmv(const orc_system* S, const double* x, double* y) {

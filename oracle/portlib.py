@@ -322,3 +322,23 @@ def element_matrix_d(eq, xe, D, t=1.0):
     Ke = np.zeros((m, m))
     lib().orc_element_matrix_d(int(eq), _p(xe, np.float64), _p(D, np.float64), C.c_double(t), _p(Ke, np.float64))
     return Ke
+
+
+def load_ngauss(quad):
+    return lib().orc_load_ngauss(int(quad))
+
+
+def integration_points(shape, quad, xe):
+    """x_g = X^T N(r_g) of one element (where the reference evaluates the force functor)."""
+    xe = _f64(xe)
+    xg = np.zeros((load_ngauss(quad), 2))
+    lib().orc_integration_points(shape, quad, _p(xe, np.float64), _p(xg, np.float64))
+    return xg
+
+
+def load_vector(shape, quad, ndof, xe, fg, t=1.0):
+    """Fe[npe*ndof] of one element from the force density fg[ngauss][ndof] at its integration points."""
+    xe, fg = _f64(xe), _f64(fg)
+    Fe = np.zeros(xe.shape[0] * ndof)
+    lib().orc_load_vector(shape, quad, ndof, _p(xe, np.float64), _p(fg, np.float64), C.c_double(t), _p(Fe, np.float64))
+    return Fe

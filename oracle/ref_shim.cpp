@@ -868,3 +868,57 @@ void ref_squaremesh(double lx, double ly, int nx, int ny, double* coords, int* c
 }
 
 }  // extern "C"
+
+// ---- load vectors with the reference's own functor interface: PlaneStrainSurfaceForce / BodyForce (PlaneStrain.h:421, 503),
+//      PlaneStressSurfaceForce / BodyForce (PlaneStress.h:98, 134), HeatTransferSurfaceFlux (HeatTransfer.h:76).
+//      kind: 0 plane-strain, 1 plane-stress, 2 heat flux; the force density is the affine field f_i(x) = c[3i] + c[3i+1] x + c[3i+2] y ----
+namespace {
+struct AffineForce {
+    const double* c; int ndof;
+    Vector<double> operator()(Vector<double> x) const {
+        Vector<double> f(ndof);
+        for (int i = 0; i < ndof; i++) f(i) = c[3 * i] + c[3 * i + 1] * x(0) + c[3 * i + 2] * x(1);
+        return f;
+    }
+};
+struct AffineFlux {
+    const double* c;
+    double operator()(Vector<double> x) const { return c[0] + c[1] * x(0) + c[2] * x(1); }
+};
+template<template<class>class SF, template<class>class IC, bool BODY>
+void load_vec(int kind, Vector<double>& Fe, N2E& n2e, const std::vector<int>& el, std::vector<Vector<double> >& x, const double* c, double t) {
+    if (kind == 2) { HeatTransferSurfaceFlux<double, SF, IC>(Fe, n2e, el, { 0 }, x, AffineFlux{ c }, t); return; }
+    AffineForce f{ c, 2 };
+    if (BODY) { if (kind == 0) PlaneStrainBodyForce<double, SF, IC>(Fe, n2e, el, { 0, 1 }, x, f, t); else PlaneStressBodyForce<double, SF, IC>(Fe, n2e, el, { 0, 1 }, x, f, t); }
+    else { if (kind == 0) PlaneStrainSurfaceForce<double, SF, IC>(Fe, n2e, el, { 0, 1 }, x, f, t); else PlaneStressSurfaceForce<double, SF, IC>(Fe, n2e, el, { 0, 1 }, x, f, t); }
+}
+}   // namespace
+extern "C" {
+// shape: 8 = 2Line, 9 = 3Line (surface), 1 T3, 2 T6, 3 Q4, 4 Q8 (body); quad: 9 Gauss1Line, 10 Gauss2Line, else the area rules
+int ref_load_vector(int kind, int shape, int quad, int npe, const double* xe, const double* coef, double t, double* Fe_out) {
+    std::vector<Vector<double> > x = make_nodes(2, npe, xe);
+    std::vector<int> el(npe);
+    std::iota(el.begin(), el.end(), 0);
+    Vector<double> Fe;
+    N2E n2e;
+    switch (shape) {
+        case 8: if (quad == 10) load_vec<ShapeFunction2Line, Gauss2Line, false>(kind, Fe, n2e, el, x, coef, t); else load_vec<ShapeFunction2Line, Gauss1Line, false>(kind, Fe, n2e, el, x, coef, t); break;
+        case 9: if (quad == 10) load_vec<ShapeFunction3Line, Gauss2Line, false>(kind, Fe, n2e, el, x, coef, t); else load_vec<ShapeFunction3Line, Gauss1Line, false>(kind, Fe, n2e, el, x, coef, t); break;
+        case SHAPE_T3: if (quad == QUAD_G3TRI) load_vec<ShapeFunction3Triangle, Gauss3Triangle, true>(kind, Fe, n2e, el, x, coef, t); else load_vec<ShapeFunction3Triangle, Gauss1Triangle, true>(kind, Fe, n2e, el, x, coef, t); break;
+        case SHAPE_T6: if (quad == QUAD_G3TRI) load_vec<ShapeFunction6Triangle, Gauss3Triangle, true>(kind, Fe, n2e, el, x, coef, t); else load_vec<ShapeFunction6Triangle, Gauss1Triangle, true>(kind, Fe, n2e, el, x, coef, t); break;
+        case SHAPE_Q8:
+            if (quad == QUAD_G1SQ) load_vec<ShapeFunction8Square, Gauss1Square, true>(kind, Fe, n2e, el, x, coef, t);
+            else if (quad == QUAD_G9SQ) load_vec<ShapeFunction8Square, Gauss9Square, true>(kind, Fe, n2e, el, x, coef, t);
+            else load_vec<ShapeFunction8Square, Gauss4Square, true>(kind, Fe, n2e, el, x, coef, t);
+            break;
+        default:
+            if (quad == QUAD_G1SQ) load_vec<ShapeFunction4Square, Gauss1Square, true>(kind, Fe, n2e, el, x, coef, t);
+            else if (quad == QUAD_G9SQ) load_vec<ShapeFunction4Square, Gauss9Square, true>(kind, Fe, n2e, el, x, coef, t);
+            else load_vec<ShapeFunction4Square, Gauss4Square, true>(kind, Fe, n2e, el, x, coef, t);
+            break;
+    }
+    const int m = Fe.SIZE();
+    for (int i = 0; i < m; i++) Fe_out[i] = Fe(i);
+    return m;
+}
+}   // extern "C"

@@ -363,3 +363,13 @@ def plane_d_element(shape, quad, quad2, mode, xe, D, t=1.0):
     Ke = np.zeros((m, m))
     lib().ref_plane_d_element(shape, quad, quad2, mode, xe.shape[0], _p(xe, np.float64), _p(D, np.float64), C.c_double(t), _p(Ke, np.float64))
     return Ke
+
+
+def load_vector(kind, shape, quad, xe, coef, t=1.0):
+    """The reference's PlaneStrain / PlaneStress SurfaceForce / BodyForce (kind 0 / 1) or HeatTransferSurfaceFlux (kind 2) on one element with the
+    affine force density f_i(x) = coef[3i] + coef[3i+1] x + coef[3i+2] y.  shape 8 / 9: 2Line / 3Line, else the area shapes of eqcode."""
+    xe, coef = _f64(xe), _f64(coef)
+    ndof = 1 if kind == 2 else 2
+    Fe = np.zeros(xe.shape[0] * ndof)
+    lib().ref_load_vector(kind, shape, quad, xe.shape[0], _p(xe, np.float64), _p(coef, np.float64), C.c_double(t), _p(Fe, np.float64))
+    return Fe

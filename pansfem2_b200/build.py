@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libpansfem2_b200.so")
-SOURCES = ["ctx.cu", "csr.cu", "pcg.cu", "solver.cu", "ilu.cu", "bicgstab.cu", "pattern.cu", "assemble.cu", "assemble_generic.cu", "advdiff.cu", "filter.cu", "mma.cu", "simp.cu", "levelset.cu", "dist.cu"]
+SOURCES = ["ctx.cu", "csr.cu", "pcg.cu", "solver.cu", "ilu.cu", "bicgstab.cu", "pattern.cu", "assemble.cu", "assemble_generic.cu", "advdiff.cu", "filter.cu", "loadvec.cu", "mma.cu", "simp.cu", "levelset.cu", "dist.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]
 

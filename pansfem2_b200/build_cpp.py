@@ -21,7 +21,8 @@ LINK = ["-L" + HERE, "-lpansfem2_b200", "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGI
 OWN = [("sample/optimize/sample_optimize_density_batched.cpp", "sample_optimize_density_batched"),
        ("sample/optimize/sample_optimize_density_families.cpp", "sample_optimize_density_families"),
        ("sample/optimize/sample_optimize_levelset_batched.cpp", "sample_optimize_levelset_batched"),
-       ("sample/advection/sample_advectiondiffusion_batched.cpp", "sample_advectiondiffusion_batched")]
+       ("sample/advection/sample_advectiondiffusion_batched.cpp", "sample_advectiondiffusion_batched"),
+       ("sample/planestrain/sample_planestrain_batched.cpp", "sample_planestrain_batched")]
 DROPIN = [("sample/optimize/sample_optimize_density_oc.cpp", "dropin_density_oc"),
           ("sample/optimize/sample_optimize_density_mma.cpp", "dropin_density_mma"),
           ("sample/optimize/sample_optimize_density_CONLIN.cpp", "dropin_density_conlin"),

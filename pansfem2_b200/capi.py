@@ -171,6 +171,17 @@ class Mesh:
         self.h = C.c_void_p()
         _ck(lib().pf2_mesh_create(ctx.h, self.dim, self.nnode, _p(coords, np.float64), self.npe, self.nelem, _p(conn, np.int32), C.byref(self.h)))
 
+    @classmethod
+    def on_nodes(cls, base, conn):
+        """A second element list (edges, a sub-region) over the nodes of `base`; shares its coordinates on the device."""
+        conn = _i32(conn)
+        m = cls.__new__(cls)
+        m.ctx, m.nnode, m.dim = base.ctx, base.nnode, base.dim
+        m.nelem, m.npe = conn.shape
+        m.h = C.c_void_p()
+        _ck(lib().pf2_mesh_create_on_nodes(base.h, m.npe, m.nelem, _p(conn, np.int32), C.byref(m.h)))
+        return m
+
     def close(self):
         if self.h:
             lib().pf2_mesh_destroy(self.h)
@@ -407,6 +418,24 @@ class CONLIN(MMA):
 
     def set_parameters(self, move, epsvalue):
         _ck(lib().pf2_conlin_set_parameters(self.h, C.c_double(move), C.c_double(epsvalue)))
+
+
+SHAPE_LINE2, SHAPE_LINE3, QUAD_G1LINE, QUAD_G2LINE = 8, 9, 9, 10
+
+
+def integration_points(mesh, shape, quad, ngauss):
+    """x_g of every element of `mesh` (host array nelem x ngauss x 2): where the reference evaluates a load functor."""
+    xg = mesh.ctx.empty(mesh.nelem * ngauss * 2)
+    _ck(lib().pf2_integration_points(mesh.h, int(shape), int(quad), xg.ptr))
+    return xg.download().reshape(mesh.nelem, ngauss, 2)
+
+
+def load_vector(mesh, dofmap, shape, quad, F_dev, t=1.0, f_const=None, f_gauss=None):
+    """pf2_load_vector: adds the surface / body load vector of every element of `mesh` into the device vector F_dev."""
+    fc = _f64(f_const) if f_const is not None else None
+    fg = mesh.ctx.array(_f64(f_gauss).ravel()) if f_gauss is not None else None
+    _ck(lib().pf2_load_vector(mesh.h, dofmap.h, int(shape), int(quad), _p(fc, np.float64) if fc is not None else None,
+                              fg.ptr if fg is not None else None, C.c_double(t), F_dev.ptr))
 
 
 def compliance_sens(mesh, eq, u_dev, rho_dev, params6, want_r=False):

@@ -10,6 +10,7 @@
 #include <utility>
 #include <algorithm>
 #include <cmath>
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/pansfem2_b200.h"
 
 namespace pf2 {
@@ -42,6 +43,15 @@ void set_error(const char* fmt, ...);
 #define PF2_LAUNCH_CHECK() PF2_CUDA(cudaGetLastError())
 
 constexpr int kThreads = 256;
+
+// NVTX range around a phase of the path (header-only NVTX 3: a no-op of a few nanoseconds unless a tool -- nsys, ncu --nvtx -- is attached)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+    void next(const char* name) { nvtxRangePop(); nvtxRangePushA(name); }      // consecutive phases of one function; an early return still pops
+};
 
 // element routines (element.cuh, element_generic.cuh) also compile for the host so that tests/cpp/host_elements.cu can check the
 // SAME source against the reference fixtures on a machine without a GPU; the library itself only ever calls them from kernels

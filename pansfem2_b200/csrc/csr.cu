@@ -391,13 +391,25 @@ static int mf_constant(pf2_csr* A) {
 }
 
 // ---- nodal-space PCG pieces (called by solve_mf_nodal, solver.cu) ----
-int mf_nodal_begin(pf2_csr* A, int jacobi, const double* b, double* bn, double* dn, double* xn, double* r, double* z, double* p0, double* p1, int itrmax, double eps) {
+int mf_nodal_apply(pf2_csr* A, const double* p_old, const double* z, double* p_new, double* y);
+
+// x0 != nullptr: warm start from the reduced-numbering guess x0 (y is scratch for K x0)
+int mf_nodal_begin(pf2_csr* A, int jacobi, const double* b, double* bn, double* dn, double* xn, double* r, double* z, double* p0, double* p1, int itrmax, double eps,
+                   const double* x0, double* y) {
     pf2_ctx* c = A->ctx;
     PF2_TRY(mf_constant(A));
     const size_t nfull = (size_t)A->mf_n[0] * A->mf_n[1] * A->mf_n[2] * A->mf_ndof;
     const int g = c->grid_for((long long)nfull, 2);
     mf_expand_kernel<<<g, kThreads, 0, c->stream>>>(nfull, A->mf_n2g, b, A->indptr, A->diagpos, A->data, jacobi, bn, dn);
-    mf_init_kernel<<<std::min(g, c->sm_count * 4), kThreads, 0, c->stream>>>(nfull, bn, dn, xn, r, z, p0, p1, A->st, itrmax, eps, c->red.partials, c->red.ticket);
+    if (x0) {
+        // y = K x0 through the fused operator: with beta = 0 and done = 0 it forms p_new = 0 * p_old + x0 (into the scratch buffer p1) and y = K p_new
+        mf_expand_x_kernel<<<g, kThreads, 0, c->stream>>>(nfull, A->mf_n2g, x0, xn);
+        PF2_CUDA(cudaMemsetAsync(A->st, 0, sizeof(CgState), c->stream));
+        PF2_TRY(mf_nodal_apply(A, xn, xn, p1, y));
+        c->launches++;
+    }
+    mf_init_kernel<<<std::min(g, c->sm_count * 4), kThreads, 0, c->stream>>>(nfull, bn, dn, xn, r, z, p0, p1, A->st, itrmax, eps, c->red.partials, c->red.ticket,
+                                                                           x0 ? y : nullptr);
     PF2_LAUNCH_CHECK();
     c->launches += 2;
     return PF2_OK;

@@ -192,8 +192,8 @@ extern "C" {
 
 int pf2_mesh_create(pf2_ctx* ctx, int dim, int nnode, const double* coords_host, int npe, int nelem, const int* conn_host, pf2_mesh** out) {
     PF2_CHECK(ctx && out && coords_host && conn_host, "null argument");
-    PF2_CHECK((dim == 2 && (npe == 3 || npe == 4 || npe == 6 || npe == 8)) || (dim == 3 && (npe == 4 || npe == 8 || npe == 20)),
-              "supported elements: T3 / Q4 / T6 / Q8 (dim 2; 3, 4, 6, 8 nodes), tet4 / hex8 / hex20 (dim 3; 4, 8, 20 nodes)");
+    PF2_CHECK((dim == 2 && (npe == 2 || npe == 3 || npe == 4 || npe == 6 || npe == 8)) || (dim == 3 && (npe == 4 || npe == 8 || npe == 20)),
+              "supported elements: T3 / Q4 / T6 / Q8 (dim 2; 3, 4, 6, 8 nodes; 2- and 3-node edges as load carriers), tet4 / hex8 / hex20 (dim 3; 4, 8, 20 nodes)");
     PF2_CHECK(nnode > 0 && nelem > 0, "empty mesh");
     PF2_CUDA(cudaSetDevice(ctx->device));
     pf2_mesh* m = new pf2_mesh();
@@ -207,10 +207,29 @@ int pf2_mesh_create(pf2_ctx* ctx, int dim, int nnode, const double* coords_host,
     *out = m;
     return PF2_OK;
 }
+// a second element list over the nodes of `base` (edges carrying surface loads, a sub-region carrying a body force): shares the
+// coordinates on the device, so `base` must outlive it
+int pf2_mesh_create_on_nodes(pf2_mesh* base, int npe, int nelem, const int* conn_host, pf2_mesh** out) {
+    PF2_CHECK(base && out && conn_host && nelem > 0, "null argument");
+    PF2_CHECK((base->dim == 2 && (npe == 2 || npe == 3 || npe == 4 || npe == 6 || npe == 8)) || (base->dim == 3 && (npe == 4 || npe == 8 || npe == 20)), "unsupported nodes per element");
+    for (size_t k = 0; k < (size_t)nelem * npe; k++) PF2_CHECK(conn_host[k] >= 0 && conn_host[k] < base->nnode, "element node out of range");
+    pf2_ctx* ctx = base->ctx;
+    PF2_CUDA(cudaSetDevice(ctx->device));
+    pf2_mesh* m = new pf2_mesh();
+    m->ctx = ctx; m->dim = base->dim; m->nnode = base->nnode; m->npe = npe; m->nelem = nelem;
+    m->own_elem_lo = 0; m->own_elem_hi = nelem;
+    m->coords = base->coords; m->shares_coords = true;
+    PF2_TRY(dev_alloc(&m->conn, (size_t)nelem * npe));
+    PF2_CUDA(cudaMemcpyAsync(m->conn, conn_host, sizeof(int) * (size_t)nelem * npe, cudaMemcpyHostToDevice, ctx->stream));
+    PF2_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = m;
+    return PF2_OK;
+}
 int pf2_mesh_destroy(pf2_mesh* m) {
     if (!m) return PF2_OK;
     cudaStreamSynchronize(m->ctx->stream);
-    cudaFree(m->coords); cudaFree(m->conn);
+    if (!m->shares_coords) cudaFree(m->coords);
+    cudaFree(m->conn);
     delete m;
     return PF2_OK;
 }

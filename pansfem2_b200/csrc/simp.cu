@@ -31,6 +31,22 @@ int dist_allreduce(pf2_dist* d, double* dev, int count);
 
 using namespace pf2;
 
+// ---- VTK staging: one kernel lays the point and cell fields out exactly as ExportToVTK.h writes them (coordinates and vectors padded
+// to three components, ExportToVTK.h:31-37,112-117), so that ONE device-to-host copy into pinned memory feeds the writer ----
+__global__ void vtk_stage_kernel(int nnode, int dim, int ndof, int nelem, const double* __restrict__ coords, const double* __restrict__ u,
+                                 const double* __restrict__ r, const double* __restrict__ rho, double* __restrict__ out) {
+    const size_t np3 = (size_t)nnode * 3;
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < np3; k += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = k / 3;
+        const int d = (int)(k % 3);
+        out[k] = d < dim ? coords[i * dim + d] : 0.0;
+        out[np3 + k] = d < ndof ? u[i * ndof + d] : 0.0;
+        if (r) out[2 * np3 + k] = d < ndof ? r[i * ndof + d] : 0.0;
+    }
+    double* cell = out + (r ? 3 : 2) * np3;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < (size_t)nelem; e += (size_t)gridDim.x * blockDim.x) cell[e] = rho[e];
+}
+
 struct pf2_simp {
     pf2_ctx* ctx = nullptr;
     pf2_mesh* mesh = nullptr;
@@ -58,6 +74,9 @@ struct pf2_simp {
     pf2_dist* dist = nullptr;
     int ehalo[6] = { 0, 0, 0, 0, 0, 0 };
     long long n_global = 0;
+    double* vtk_dev = nullptr;       // staging of pf2_simp_export_vtk (device) and its pinned host mirror
+    double* vtk_host = nullptr;
+    int* vtk_conn_host = nullptr;    // connectivity, downloaded once (it never changes)
 };
 
 static int simp_iterate(pf2_simp* S, int check_convergence, double stats[8]) {
@@ -66,16 +85,20 @@ static int simp_iterate(pf2_simp* S, int check_convergence, double stats[8]) {
     pf2_dist* d = S->dist;
     const double nglob = (double)(S->n_global ? S->n_global : S->n);
     PF2_CUDA(cudaSetDevice(c->device));
+    NvtxRange nv_iter("pf2_simp_iterate");
     PF2_CUDA(cudaEventRecord(S->ev[0], s));
+    NvtxRange nv_phase("pf2 filter");
     if (S->beta_period > 0 && S->k % S->beta_period == 0) S->beta *= 2.0;       // driver :85-88
     S->filter->beta = S->beta;
     if (d) PF2_TRY(dist_halo(d, S->s, S->ehalo));                              // ghost element planes of the design
     PF2_TRY(filter_apply(S->filter, S->s, S->rho, c->scalars + 1, nullptr));
     if (d) { PF2_TRY(dist_allreduce(d, c->scalars + 1, 1)); PF2_TRY(dist_halo(d, S->rho, S->ehalo)); }
     PF2_CUDA(cudaEventRecord(S->ev[1], s));
+    nv_phase.next("pf2 assemble");
     const double ap[5] = { S->E0, S->E1, S->V, S->p, S->thick };
     PF2_TRY(assemble_device(S->A, S->mesh, S->map, S->eq, nullptr, S->rho, ap, S->nload, S->ld_node, S->ld_dof, S->ld_val));
     PF2_CUDA(cudaEventRecord(S->ev[2], s));
+    nv_phase.next("pf2 solve");
     int iters = 0;
     double relres = 0.0;
     int rc = solve_x0(S->A, S->solver, S->A->F, S->xsol, S->itrmax, S->cgeps, (S->warm_start && S->have_solution) ? 1 : 0, &iters, &relres);
@@ -84,14 +107,17 @@ static int simp_iterate(pf2_simp* S, int check_convergence, double stats[8]) {
     if (d) PF2_TRY(dist_halo(d, S->xsol, S->A->halo));                         // displacements of the ghost node planes
     PF2_TRY(pf2_disassemble(S->map, S->xsol, S->u));
     PF2_CUDA(cudaEventRecord(S->ev[3], s));
+    nv_phase.next("pf2 compliance+sensitivity");
     const double sp[6] = { S->E0, S->E1, S->V, S->p, S->thick, S->scale0 };
     PF2_TRY(compliance_sens_device(S->mesh, S->eq, S->u, S->rho, sp, c->scalars, S->dfdrho, nullptr));
     if (d) { PF2_TRY(dist_allreduce(d, c->scalars, 1)); PF2_TRY(dist_halo(d, S->dfdrho, S->ehalo)); }
     PF2_CUDA(cudaEventRecord(S->ev[4], s));
+    nv_phase.next("pf2 filter sensitivities");
     const double dgdrho = S->scale1 / (S->weightlimit * nglob);                 // driver :104
     PF2_TRY(filter_sens(S->filter, S->s, S->dfdrho, S->dfds, nullptr, dgdrho, S->dgds));
     if (d) { PF2_TRY(dist_halo(d, S->dfds, S->ehalo)); PF2_TRY(dist_halo(d, S->dgds, S->ehalo)); }
     PF2_CUDA(cudaEventRecord(S->ev[5], s));
+    nv_phase.next("pf2 optimiser update");
     PF2_CUDA(cudaMemcpyAsync(c->h_scalars, c->scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
     PF2_CUDA(cudaStreamSynchronize(s));
     const double f = c->h_scalars[0];
@@ -172,6 +198,9 @@ int pf2_simp_destroy(pf2_simp* S) {
     void* ptrs[] = { S->s, S->rho, S->xsol, S->u, S->r_nodal, S->dfdrho, S->dfds, S->dgds, S->ld_node, S->ld_dof, S->ld_val };
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 7; i++) if (S->ev[i]) cudaEventDestroy(S->ev[i]);
+    if (S->vtk_dev) cudaFree(S->vtk_dev);
+    if (S->vtk_host) cudaFreeHost(S->vtk_host);
+    if (S->vtk_conn_host) free(S->vtk_conn_host);
     delete S;
     return PF2_OK;
 }
@@ -242,6 +271,64 @@ int pf2_simp_get(pf2_simp* S, double* s_host, double* rho_host, double* u_nodal_
         PF2_CUDA(cudaMemcpyAsync(r_nodal_host, S->r_nodal, ndb, cudaMemcpyDeviceToHost, s));
     }
     PF2_CUDA(cudaStreamSynchronize(s));
+    return PF2_OK;
+}
+
+// The drivers' per-iteration dump (sample_optimize_density_oc.cpp:175-184): MakeHeadderToVTK, AddPointsToVTK, AddElementToVTK,
+// AddElementTypes, AddPointVectors u [, r], AddElementScalers rho as "s" (ExportToVTK.h:19-137), written from the device-resident
+// state.  The fields are staged on the device in the writer's layout and cross in one copy; numbers are formatted like the
+// reference's `ostream << double` (default float format = %g with 6 significant digits), so the file is byte-identical to the one
+// the reference's writers produce from the same values.
+int pf2_simp_export_vtk(pf2_simp* S, const char* path, int cell_type, int with_reactions) {
+    PF2_CHECK(S && path, "null argument");
+    pf2_ctx* c = S->ctx;
+    cudaStream_t s = c->stream;
+    PF2_CUDA(cudaSetDevice(c->device));
+    const int nnode = S->mesh->nnode, nelem = S->n, npe = S->mesh->npe, dim = S->mesh->dim, ndof = S->ndof;
+    const size_t np3 = (size_t)nnode * 3, total = 3 * np3 + (size_t)nelem;
+    if (!S->vtk_dev) {
+        PF2_TRY(dev_alloc(&S->vtk_dev, total));
+        PF2_CUDA(cudaHostAlloc((void**)&S->vtk_host, total * sizeof(double), cudaHostAllocDefault));
+        S->vtk_conn_host = (int*)malloc(sizeof(int) * (size_t)nelem * npe);
+        PF2_CHECK(S->vtk_conn_host, "out of host memory");
+        PF2_CUDA(cudaMemcpyAsync(S->vtk_conn_host, S->mesh->conn, sizeof(int) * (size_t)nelem * npe, cudaMemcpyDeviceToHost, s));
+    }
+    if (with_reactions) {
+        const double sp[6] = { S->E0, S->E1, S->V, S->p, S->thick, S->scale0 };
+        PF2_TRY(compliance_sens_device(S->mesh, S->eq, S->u, S->rho, sp, c->scalars + 2, nullptr, S->r_nodal));      // driver :136-150
+    }
+    vtk_stage_kernel<<<c->grid_for((long long)np3), kThreads, 0, s>>>(nnode, dim, ndof, nelem, S->mesh->coords, S->u, with_reactions ? S->r_nodal : nullptr,
+                                                                    S->rho, S->vtk_dev);
+    PF2_LAUNCH_CHECK();
+    c->launches++;
+    const size_t used = (with_reactions ? 3 : 2) * np3 + (size_t)nelem;
+    PF2_CUDA(cudaMemcpyAsync(S->vtk_host, S->vtk_dev, used * sizeof(double), cudaMemcpyDeviceToHost, s));
+    PF2_CUDA(cudaStreamSynchronize(s));
+    FILE* f = fopen(path, "w");
+    if (!f) { set_error("cannot open %s for writing", path); return PF2_E_INVALID; }
+    fputs("# vtk DataFile Version 4.1\nvtk output\nASCII\nDATASET UNSTRUCTURED_GRID\n", f);                  // ExportToVTK.h:19-24
+    fprintf(f, "\nPOINTS\t%d\tfloat\n", nnode);                                                                   // :29-40
+    const double* P = S->vtk_host;
+    for (int i = 0; i < nnode; i++) fprintf(f, "%g\t%g\t%g\t\n", P[3 * (size_t)i], P[3 * (size_t)i + 1], P[3 * (size_t)i + 2]);
+    fprintf(f, "\nCELLS %d\t%lld\n", nelem, (long long)nelem * (npe + 1));                                        // :44-57
+    for (int e = 0; e < nelem; e++) {
+        fprintf(f, "%d\t", npe);
+        for (int a = 0; a < npe; a++) fprintf(f, "%d\t", S->vtk_conn_host[(size_t)e * npe + a]);
+        fputc('\n', f);
+    }
+    fprintf(f, "\nCELL_TYPES\t%d\n", nelem);                                                                       // :61-66
+    for (int e = 0; e < nelem; e++) fprintf(f, "%d\n", cell_type);
+    fprintf(f, "\nPOINT_DATA\t%d\n", nnode);                                                                       // :103-119
+    const char* names[2] = { "u", "r" };
+    for (int v = 0; v < (with_reactions ? 2 : 1); v++) {
+        fprintf(f, "VECTORS %s float\n", names[v]);
+        const double* V = S->vtk_host + (size_t)(v + 1) * np3;
+        for (int i = 0; i < nnode; i++) fprintf(f, "%g\t%g\t%g\t\n", V[3 * (size_t)i], V[3 * (size_t)i + 1], V[3 * (size_t)i + 2]);
+    }
+    fprintf(f, "\nCELL_DATA\t%d\nSCALARS s float\nLOOKUP_TABLE default\n", nelem);                                // :125-135
+    const double* R = S->vtk_host + (with_reactions ? 3 : 2) * np3;
+    for (int e = 0; e < nelem; e++) fprintf(f, "%g\n", R[e]);
+    if (fclose(f) != 0) { set_error("write to %s failed", path); return PF2_E_INVALID; }
     return PF2_OK;
 }
 

@@ -225,11 +225,12 @@ int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, d
 int solve_bicgstab(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out);
 
 // ---- PCG in nodal numbering with the matrix-free operator (single GPU; csr.cu / spmv_mf.cuh) -----------------------------
-int mf_nodal_begin(pf2_csr* A, int jacobi, const double* b, double* bn, double* dn, double* xn, double* r, double* z, double* p0, double* p1, int itrmax, double eps);
+int mf_nodal_begin(pf2_csr* A, int jacobi, const double* b, double* bn, double* dn, double* xn, double* r, double* z, double* p0, double* p1, int itrmax, double eps,
+                   const double* x0, double* y);
 int mf_nodal_apply(pf2_csr* A, const double* p_old, const double* z, double* p_new, double* y);
 int mf_nodal_end(pf2_csr* A, const double* xn, double* x);
 
-static int solve_mf_nodal(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out) {
+static int solve_mf_nodal(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int warm, int* iters_out, double* relres_out) {
     pf2_ctx* c = A->ctx;
     PF2_CUDA(cudaSetDevice(c->device));
     PF2_TRY(ensure_workspace(A));          // device state, events, pinned mirror
@@ -239,7 +240,7 @@ static int solve_mf_nodal(pf2_csr* A, int solver, const double* b, double* x, in
     double *bn = A->mf_slab, *dn = bn + np, *xn = bn + 2 * np, *r = bn + 3 * np, *z = bn + 4 * np, *y = bn + 5 * np;
     double* P[2] = { bn + 6 * np, bn + 7 * np };
     const int n = (int)nfull;
-    PF2_TRY(mf_nodal_begin(A, solver == PF2_SOLVER_SCALINGCG ? 1 : 0, b, bn, dn, xn, r, z, P[0], P[1], itrmax, eps));
+    PF2_TRY(mf_nodal_begin(A, solver == PF2_SOLVER_SCALINGCG ? 1 : 0, b, bn, dn, xn, r, z, P[0], P[1], itrmax, eps, warm ? x : nullptr, y));
     const int gu = std::min(c->grid_for(n, 4), c->wave_grid((const void*)cg_update_kernel<1>, kThreads));
     const int chunk = 32;
     int enq = 0, slot = 0;
@@ -294,6 +295,7 @@ int pcg_persistent_solve(pf2_csr* A, int solver, const double* b, double* x, int
 // overload: same recurrences and stopping rule ||r|| < eps ||b||, parity is on the converged solution)
 int solve_x0(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int warm, int* iters_out, double* relres_out) {
     pf2_ctx* c = A->ctx;
+    NvtxRange nv("pf2_solve (Krylov loop)");
     PF2_CHECK(solver >= 0 && solver <= PF2_SOLVER_ILU0BICGSTAB, "unknown solver");
     PF2_CHECK(itrmax >= 0, "itrmax");
     if (solver >= PF2_SOLVER_BICGSTAB) return solve_bicgstab(A, solver, b, x, itrmax, eps, iters_out, relres_out);
@@ -304,7 +306,7 @@ int solve_x0(pf2_csr* A, int solver, const double* b, double* x, int itrmax, dou
     }
     if (A->dist) return solve_dist(A, solver, b, x, itrmax, eps, iters_out, relres_out);      // host-ordered loop: always from x0 = 0
     if (A->spmv_variant == 41 && A->mf_nodal && A->mf_version > 0 && solver != PF2_SOLVER_ILU0CG)
-        return solve_mf_nodal(A, solver, b, x, itrmax, eps, iters_out, relres_out);
+        return solve_mf_nodal(A, solver, b, x, itrmax, eps, warm, iters_out, relres_out);
     PF2_TRY(ensure_workspace(A));
     const int n = A->rows;
     if (solver == PF2_SOLVER_ILU0CG) warm = 0;

@@ -227,19 +227,32 @@ __global__ void mf_gather_kernel(size_t nfull, const int* __restrict__ n2g, cons
         if (r != -1) x[r] = xn[i];
     }
 }
-// x = 0 ; r = b ; z = r / D ; p = z ; bb ; rho = z.r      (CG.h:422-428 in nodal numbering; both p buffers start as z)
+// warm start: the initial guess in nodal numbering (fixed dofs are identity rows that stay 0)
+__global__ void mf_expand_x_kernel(size_t nfull, const int* __restrict__ n2g, const double* __restrict__ x, double* __restrict__ xn) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nfull; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = n2g[i];
+        xn[i] = (r != -1) ? x[r] : 0.0;
+    }
+}
+// x = x0 (0 without y0) ; r = b - K x0 ; z = r / D ; p = z ; bb ; rho = z.r ; rr      (CG.h:422-428 in nodal numbering; both p buffers
+// start as z).  y0 = K x0 of a warm start, nullptr: the reference's x0 = 0.
 __global__ void __launch_bounds__(kThreads)
 mf_init_kernel(size_t nfull, const double* __restrict__ bn, const double* __restrict__ dn, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
-               double* __restrict__ p0, double* __restrict__ p1, CgState* st, int maxit, double eps, double* partials, unsigned int* ticket) {
-    double v[2] = { 0.0, 0.0 };
+               double* __restrict__ p0, double* __restrict__ p1, CgState* st, int maxit, double eps, double* partials, unsigned int* ticket,
+               const double* __restrict__ y0) {
+    double v[3] = { 0.0, 0.0, 0.0 };
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nfull; i += (size_t)gridDim.x * blockDim.x) {
-        const double bi = bn[i], zi = bi / dn[i];
-        x[i] = 0.0; r[i] = bi; z[i] = zi; p0[i] = zi; p1[i] = zi;
-        v[0] += bi * bi; v[1] += zi * bi;
+        const double bi = bn[i];
+        double ri = bi;
+        if (y0) ri = bi - y0[i]; else x[i] = 0.0;
+        const double zi = ri / dn[i];
+        r[i] = ri; z[i] = zi; p0[i] = zi; p1[i] = zi;
+        v[0] += bi * bi; v[1] += zi * ri; v[2] += ri * ri;
     }
-    if (grid_sum_last<2>(v, partials, ticket) && threadIdx.x == 0) {
-        st->bb = v[0]; st->rr = v[0]; st->rho = v[1]; st->pAp = 0.0; st->beta = 0.0; st->zr_new = 0.0;
-        st->iter = 0; st->done = 0; st->maxit = maxit; st->eps = eps;
+    if (grid_sum_last<3>(v, partials, ticket) && threadIdx.x == 0) {
+        st->bb = v[0]; st->rr = v[2]; st->rho = v[1]; st->pAp = 0.0; st->beta = 0.0; st->zr_new = 0.0;
+        st->iter = 0; st->maxit = maxit; st->eps = eps;
+        st->done = (y0 != nullptr && sqrt(v[2]) < eps * sqrt(v[0])) ? 1 : 0;
     }
 }
 

@@ -21,6 +21,7 @@ struct pf2_mesh {
     int dim = 0, nnode = 0, npe = 0, nelem = 0;
     int own_elem_lo = 0, own_elem_hi = 0;   // multi-GPU: owned elements (compliance is summed over them only)
     double* coords = nullptr;   // nnode*dim, node-major (AoS as std::vector<Vector<T>>)
+    bool shares_coords = false; // pf2_mesh_create_on_nodes: the coordinates belong to another mesh
     int* conn = nullptr;        // nelem*npe
 };
 

@@ -73,6 +73,9 @@ int main(int argc, char** argv) {
         AddPointVectors(u, "u", fout, true);
         AddPointVectors(r, "r", fout, false);
         AddElementScalers(rho, "s", fout, true);
+        fout.close();
+        //  the same file written by the library from the device-resident fields (pf2_simp_export_vtk): byte-identical
+        loop.ExportVTK(out + ".device.vtk", 9, true);
     }
     return 0;
 }

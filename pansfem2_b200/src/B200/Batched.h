@@ -32,6 +32,10 @@ namespace PANSFEM2 { namespace B200 {
         for (const auto& b : _bc) { _node.push_back(b.first.first); _dof.push_back(b.first.second); _val.push_back(b.second); }
     }
 
+    //  what a load functor returns: Vector<double> (forces) or a scalar (HeatTransferSurfaceFlux's flux)
+    inline Vector<double> LoadValue(const Vector<double>& _v, int) { return _v; }
+    inline Vector<double> LoadValue(double _v, int) { Vector<double> f = { _v }; return f; }
+
     //  mesh + Dirichlet numbering + symbolic CSR pattern on the device: built once, reused every design iteration
     class Model {
 public:
@@ -80,6 +84,40 @@ public:
         _F.resize(_model.KDEGREE);
         Check(pf2_csr_download(_model.pattern, nullptr, nullptr, nullptr, _F.data()), "pf2_csr_download");
         return _model.pattern;
+    }
+
+    //  The load-vector loops of the drivers (sample_planestrain.cpp:41-61) in one call each: PlaneStrainBodyForce / PlaneStressBodyForce
+    //  over area elements, PlaneStrainSurfaceForce / PlaneStressSurfaceForce / HeatTransferSurfaceFlux over edges, each followed by
+    //  Assembling(F, Fe, ...).  _f is the reference's functor f(x) -> Vector<double> (size = dofs per node); it is evaluated on the host at
+    //  every integration point of the batch (the device hands the points out), integration and assembly run on the device, and the result
+    //  is ADDED to _F (size KDEGREE of the model) like the reference's Assembling does.
+    template<template<class>class SF, template<class>class IC, class F>
+    inline void AssembleLoadVector(Model& _model, const std::vector<std::vector<int> >& _elements, F _f, double _t, std::vector<double>& _F) {
+        static_assert(ShapeCode<SF<double> >::value > 0 && QuadCode<IC<double> >::value > 0, "pansfem2_b200: no load-vector kernel for this shape / rule");
+        static_assert(ShapeCode<SF<double> >::domain == QuadCode<IC<double> >::domain, "pansfem2_b200: integration rule does not belong to the shape function's reference domain");
+        static_assert(ShapeCode<SF<double> >::domain == 0 || ShapeCode<SF<double> >::domain == 1 || ShapeCode<SF<double> >::domain == 4, "pansfem2_b200: load vectors are 2-D");
+        if (_elements.empty()) return;
+        const int nel = (int)_elements.size(), npe = (int)_elements[0].size(), ng = IC<double>::N, ndof = _model.ndof;
+        //  a second element list over the model's nodes: the loaded edges / areas
+        std::vector<int> conn((size_t)nel*npe);
+        for (int e = 0; e < nel; e++) for (int a = 0; a < npe; a++) conn[(size_t)e*npe + a] = _elements[e][a];
+        pf2_mesh* carrier = nullptr;
+        Check(pf2_mesh_create_on_nodes(_model.mesh, npe, nel, conn.data(), &carrier), "pf2_mesh_create_on_nodes");
+        Buffer xg((size_t)nel*ng*2), fg, Fd;
+        Check(pf2_integration_points(carrier, ShapeCode<SF<double> >::value, QuadCode<IC<double> >::value, xg.Get()), "pf2_integration_points");
+        const std::vector<double> x = xg.Download();
+        std::vector<double> f((size_t)nel*ng*ndof);
+        for (size_t q = 0; q < (size_t)nel*ng; q++) {
+            Vector<double> xq = { x[2*q], x[2*q + 1] };
+            const Vector<double> fq = LoadValue(_f(xq), ndof);
+            for (int i = 0; i < ndof; i++) f[q*ndof + i] = fq(i);
+        }
+        fg.Upload(f);
+        _F.resize(_model.KDEGREE, 0.0);
+        Fd.Upload(_F);
+        Check(pf2_load_vector(carrier, _model.dofmap, ShapeCode<SF<double> >::value, QuadCode<IC<double> >::value, nullptr, fg.Get(), _t, Fd.Get()), "pf2_load_vector");
+        _F = Fd.Download();
+        pf2_mesh_destroy(carrier);
     }
 
     //  solve K u = F on the device with K still resident; kind = PF2_SOLVER_*
@@ -133,6 +171,10 @@ public:
             Check(pf2_simp_get(handle, _s.data(), _rho.data(), u.data(), r.data()), "pf2_simp_get");
             _u.assign(model.nnode, Vector<double>(model.ndof)); _r.assign(model.nnode, Vector<double>(model.ndof));
             for (int i = 0; i < model.nnode; i++) for (int d = 0; d < model.ndof; d++) { _u[i](d) = u[(size_t)i*model.ndof + d]; _r[i](d) = r[(size_t)i*model.ndof + d]; }
+        }
+        //  the drivers' per-iteration VTK file (sample_optimize_density_oc.cpp:175-184) straight from the device-resident state
+        void ExportVTK(const std::string& _path, int _celltype, bool _withreactions = true) {
+            Check(pf2_simp_export_vtk(handle, _path.c_str(), _celltype, _withreactions ? 1 : 0), "pf2_simp_export_vtk");
         }
 private:
         Model& model;

@@ -17,7 +17,12 @@ namespace PANSFEM2 { namespace B200 {
     template<> struct ShapeCode<ShapeFunction4Tetrahedron<double> > { static const int value = PF2_SHAPE_TET4, domain = 2; };
     template<> struct ShapeCode<ShapeFunction8Cubic<double> > { static const int value = PF2_SHAPE_HEX8, domain = 3; };
     template<> struct ShapeCode<ShapeFunction20Cubic<double> > { static const int value = PF2_SHAPE_HEX20, domain = 3; };
+    //  the two line shapes carry surface loads (domain 4: the line [-1, 1])
+    template<> struct ShapeCode<ShapeFunction2Line<double> > { static const int value = PF2_SHAPE_LINE2, domain = 4; };
+    template<> struct ShapeCode<ShapeFunction3Line<double> > { static const int value = PF2_SHAPE_LINE3, domain = 4; };
     template<class IC> struct QuadCode { static const int value = -1, domain = -1; };
+    template<> struct QuadCode<Gauss1Line<double> > { static const int value = PF2_QUAD_G1LINE, domain = 4; };
+    template<> struct QuadCode<Gauss2Line<double> > { static const int value = PF2_QUAD_G2LINE, domain = 4; };
     template<> struct QuadCode<Gauss1Triangle<double> > { static const int value = PF2_QUAD_G1TRI, domain = 0; };
     template<> struct QuadCode<Gauss3Triangle<double> > { static const int value = PF2_QUAD_G3TRI, domain = 0; };
     template<> struct QuadCode<Gauss1Square<double> > { static const int value = PF2_QUAD_G1SQ, domain = 1; };

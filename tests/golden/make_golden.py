@@ -505,6 +505,49 @@ def golden_plane_d():
     print("plane_d:", len(cases), "cases")
 
 
+def loadvec_cases():
+    """(kind, shape, quad) of every load-vector routine the mirror exposes: surface routines on the two line shapes x two line rules,
+    body routines on the four area shapes x the rules of their domain; kind 0 plane strain, 1 plane stress, 2 heat flux."""
+    from pansfem2_b200 import eqcode as ec
+    cases = []
+    for kind in (0, 1, 2):
+        for shape in (8, 9):
+            for quad in (9, 10):
+                cases.append((kind, shape, quad))
+    for kind in (0, 1):
+        for shape in (ec.SHAPE_T3, ec.SHAPE_T6, ec.SHAPE_Q4, ec.SHAPE_Q8):
+            for quad in ec.SHAPE_RULES[shape]:
+                cases.append((kind, shape, quad))
+    return cases
+
+
+LINE_NODES = {8: np.array([[0.0, 0.0], [1.0, 0.0]]), 9: np.array([[0.0, 0.0], [1.0, 0.0], [0.5, 0.0]])}
+
+
+def golden_loadvec():
+    """PlaneStrain / PlaneStress SurfaceForce + BodyForce and HeatTransferSurfaceFlux of the live reference (through their functor interface,
+    affine force density) on distorted elements."""
+    from pansfem2_b200 import eqcode as ec, mesher
+    rng = np.random.default_rng(20211104)
+    d, cases = {}, loadvec_cases()
+    for k, (kind, shape, quad) in enumerate(cases):
+        if shape in LINE_NODES:
+            th = rng.uniform(0, 2 * np.pi)
+            R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+            xe = (LINE_NODES[shape] * 1.7) @ R.T + rng.uniform(-1, 1, 2)
+            if shape == 9:
+                xe[2] += 0.1 * rng.uniform(-1, 1, 2)           # curved edge
+        else:
+            nat = mesher.NATURAL_NODES[ec.SHAPE_NAME[shape]]
+            xe = nat * np.array([1.3, 0.9]) + 0.08 * rng.uniform(-1, 1, nat.shape)
+        coef = rng.uniform(-2, 2, 6)
+        d[f"xe_{k}"], d[f"coef_{k}"] = xe, coef
+        d[f"fe_{k}"] = reflib.load_vector(kind, shape, quad, xe, coef, 0.7)
+    d["cases"] = np.array(cases, np.int64)
+    np.savez_compressed(f"{OUT}/live_loadvec.npz", **d)
+    print("loadvec:", len(cases), "cases")
+
+
 def golden_linalg():
     """Boundary types (Vector, Matrix, LILCSR, CSR host behaviour): tests/cpp/linalg_tables.cpp built against the reference's headers."""
     with tempfile.TemporaryDirectory() as tmp:
@@ -557,6 +600,9 @@ def _dense(indptr, indices, data):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "loadvec":
+        golden_loadvec()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "krylov":
         golden_krylov()
         sys.exit(0)

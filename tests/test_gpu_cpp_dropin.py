@@ -55,6 +55,9 @@ def test_batched_driver_reproduces_golden_vtk(tmp_path, golden_dir, opt, tag, it
     assert np.abs(got["s"] - g["rho"]).max() < 2e-6
     np.testing.assert_allclose(got["u"][:, :2], g["u"], rtol=1e-5, atol=1e-11)
     np.testing.assert_allclose(got["r"][:, :2], g["r"], rtol=1e-5, atol=1e-7)
+    # pf2_simp_export_vtk (fields staged on the device, C writer) against the mirror's ExportToVTK.h writers (pinned byte for byte to the
+    # reference's in tests/test_io_formats.py) on the same state
+    assert open(str(out) + ".device.vtk", "rb").read() == open(out, "rb").read()
 
 
 def test_unmodified_reference_oc_driver_on_the_header_mirror(tmp_path, golden_dir):
@@ -124,6 +127,17 @@ def test_unmodified_reference_planestrain_t3_driver_on_the_header_mirror(tmp_pat
     got, g = parse_vtk(tmp_path / "sample" / "planestrain" / "result.vtk"), np.load(os.path.join(golden_dir, "t3_samples.npz"))
     np.testing.assert_allclose(got["u"][:, :2], g["ps_u"], rtol=1e-5, atol=1e-9)
     np.testing.assert_allclose(got["r"][:, :2], g["ps_r"], rtol=1e-5, atol=2e-3)
+
+
+def test_batched_planestrain_driver_with_device_load_vectors(tmp_path, golden_dir):
+    """sample_planestrain.cpp through the batched API: B200::AssembleBatched + B200::AssembleLoadVector (body force on all T3 elements,
+    traction on the loaded edges, both integrated and assembled on the device with the sample's own functors) -> the committed result.vtk."""
+    exe = need("sample_planestrain_batched")
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    u = np.array([[float(v) for v in ln.split()[2:4]] for ln in r.stdout.splitlines() if ln.startswith("u ")])
+    g = np.load(os.path.join(golden_dir, "t3_samples.npz"))
+    np.testing.assert_allclose(u, g["ps_u"], rtol=1e-5, atol=1e-9)
 
 
 def test_unmodified_reference_homogenization_driver_on_the_header_mirror(tmp_path, golden_dir):

@@ -116,15 +116,17 @@ def test_warm_start_same_solution_fewer_iterations(ctx, mode):
     A2.close()
 
 
-def test_design_loop_with_warm_start_matches_the_oracle(ctx):
-    """rho after 12 design iterations within 1e-6 of the oracle, compliance 1e-8 relative (north_star tolerances), fewer CG iterations."""
+@pytest.mark.parametrize("matrix_free", [False, True])
+def test_design_loop_with_warm_start_matches_the_oracle(ctx, matrix_free):
+    """rho after 12 design iterations within 1e-6 of the oracle, compliance 1e-8 relative (north_star tolerances), fewer CG iterations;
+    also with K applied matrix-free (nodal-numbering PCG, whose set-up forms r0 = b - K x0 through the fused operator)."""
     P = problems.cantilever2d(60, 40, opt_kind=problems.OPT_MMA, filter_kind=problems.FILTER_DENSITY)
     R = orc.simp_run(P.eq, P.coords, P.conn, P.fixed, P.loads, P.filter_kind, P.nbrs, P.opt_kind, P.optp(), P.params(), 12,
                      np.full(P.nelem, P.s0), check_convergence=False)
     tot = {}
     for warm in (False, True):
-        S = capi.Simp(ctx, P)
-        S.A.set_pcg_mode(1 if warm else -1)          # the warm run also exercises the persistent kernel's x0 set-up
+        S = capi.Simp(ctx, P, matrix_free=matrix_free)
+        S.A.set_pcg_mode(1 if warm else -1)          # the warm run also exercises the persistent kernel's x0 set-up (assembled operator)
         S.set_warm_start(warm)
         st = [S.iterate(check_convergence=False) for _ in range(12)]
         out = S.get()
