@@ -255,7 +255,8 @@ int assemble_device(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq, const d
     cudaStream_t s = c->stream;
     const double E0 = params[0], E1 = params[1], V = params[2], p = params[3], t = params[4];
     // 2-D selections: row-gather kernel (every entry written once, no memset, bitwise reproducible) when the plan fits
-    const bool gather = q.dim == 2 && gather_usable(A, mesh);
+    const bool gather3 = q.fast && q.legacy == PF2_EQ_SOLID && gather3d_usable(A, mesh);
+    const bool gather = (q.dim == 2 && gather_usable(A, mesh)) || gather3;
     if (!gather) {
         PF2_CUDA(cudaMemsetAsync(A->data, 0, sizeof(double) * (size_t)A->nnz, s));
         PF2_CUDA(cudaMemsetAsync(A->F, 0, sizeof(double) * (size_t)A->rows, s));
@@ -267,6 +268,7 @@ int assemble_device(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, int eq, const d
     if (!q.fast) PF2_TRY(assemble_generic_launch(A, mesh, map, q, modulus_dev, rho_dev, params));
     else if (gather && q.legacy == PF2_EQ_PLANESTRAIN) PF2_TRY(assemble_gather_launch(A, mesh, map, ElemPlaneStrainQ4{ V, t }, modulus_dev, rho_dev, E0, E1, p));
     else if (gather && q.legacy == PF2_EQ_HEAT) PF2_TRY(assemble_gather_launch(A, mesh, map, ElemHeatQ4{ t }, modulus_dev, rho_dev, E0, E1, p));
+    else if (gather3) PF2_TRY(assemble_gather_hex8_launch(A, mesh, map, V, modulus_dev, rho_dev, E0, E1, p));
     else {
         if (q.legacy == PF2_EQ_PLANESTRAIN) LAUNCH(PF2_EQ_PLANESTRAIN);
         else if (q.legacy == PF2_EQ_SOLID) LAUNCH(PF2_EQ_SOLID);

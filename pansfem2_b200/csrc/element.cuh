@@ -185,4 +185,35 @@ PF2_HD void solid_rows(const double (&X)[8][3], int a, double V, double (&acc)[3
     }
 }
 
+// Row I of node a only (the hex8 gather assembly gives every dof row its own thread): the same operations in the same order per entry as
+// solid_rows, so an element's contribution to K is bit-identical whichever kernel adds it.
+template <int I>
+PF2_HD void solid_row(const double (&X)[8][3], int a, double V, double (&acc)[24]) {
+    const Iso c(V);
+#pragma unroll
+    for (int j = 0; j < 24; j++) acc[j] = 0.0;
+#pragma unroll 1
+    for (int g = 0; g < 8; g++) {
+        double r0, r1, r2, gx[8], gy[8], gz[8], det;
+        h8_gauss(g, r0, r1, r2);
+        h8_grad(X, r0, r1, r2, gx, gy, gz, det);
+        double ga[3] = { gx[0], gy[0], gz[0] };
+#pragma unroll
+        for (int n = 1; n < 8; n++) if (n == a) { ga[0] = gx[n]; ga[1] = gy[n]; ga[2] = gz[n]; }
+        double mg[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) mg[i] = c.mu * ga[i] * det;
+        const double cgi = c.cn * ga[I] * det, lgi = c.lam * ga[I] * det;
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const double gb[3] = { gx[b], gy[b], gz[b] };
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                if (I == j) { acc[3 * b + j] += cgi * gb[I]; acc[3 * b + j] += mg[(I + 1) % 3] * gb[(I + 1) % 3]; acc[3 * b + j] += mg[(I + 2) % 3] * gb[(I + 2) % 3]; }
+                else { acc[3 * b + j] += lgi * gb[j]; acc[3 * b + j] += mg[j] * gb[I]; }
+            }
+        }
+    }
+}
+
 }  // namespace pf2

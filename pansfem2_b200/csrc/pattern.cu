@@ -355,7 +355,8 @@ int pf2_csr_pattern(pf2_ctx* ctx, pf2_mesh* mesh, pf2_dofmap* map, pf2_csr** out
     ctx->launches += 7;
     // gather plan for the numeric phase (assemble_gather.cuh): kept for 2-D meshes only, where the kernel is used (a hex8 mesh would
     // carry 8 element ids per element for nothing: 0.45 GB on configs[4])
-    if (mesh->dim == 2) {
+    const bool plan3d = (mesh->dim == 3 && npe == 8 && ndof == 3 && gather3d_requested());       // hex8 row gather, on request (PF2_ASSEMBLE_GATHER3D)
+    if (mesh->dim == 2 || plan3d) {
         sort_n2e_kernel<<<gnode, kThreads, 0, s>>>(nnode, n2e_ptr, n2e);
         PF2_LAUNCH_CHECK();
         int* nfree = nullptr;
@@ -365,7 +366,7 @@ int pf2_csr_pattern(pf2_ctx* ctx, pf2_mesh* mesh, pf2_dofmap* map, pf2_csr** out
         PF2_LAUNCH_CHECK();
         PF2_TRY(exclusive_scan(ctx, nfree, A->node_row0, (size_t)nnode + 1));
         PF2_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned long long), s));
-        tile_nnz_max_kernel<<<gnode, kThreads, 0, s>>>(nnode, kGatherTile, A->node_row0, A->indptr, d_max);
+        tile_nnz_max_kernel<<<gnode, kThreads, 0, s>>>(nnode, plan3d ? kGather3Tile : kGatherTile, A->node_row0, A->indptr, d_max);
         PF2_LAUNCH_CHECK();
         unsigned long long h_max = 0;
         PF2_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, s));

@@ -34,6 +34,12 @@ struct pf2_dofmap {
 
 namespace pf2 {
 constexpr int kGatherTile = 128;   // nodes (= threads) per CTA of the gather assembly (assemble_gather.cuh)
+constexpr int kGather3Tile = 32;   // nodes per CTA of the hex8 gather assembly (three threads per node)
+// the hex8 gather plan is built on request (PF2_ASSEMBLE_GATHER3D=1 before pf2_csr_pattern): 4 bytes per element node on top of the pattern
+inline bool gather3d_requested() {
+    const char* e = getenv("PF2_ASSEMBLE_GATHER3D");
+    return e != nullptr && atoi(e) != 0;
+}
 constexpr int kCsrPad = 8;   // spare entries behind indptr / indices / data (see spmv_tma.cuh)
 // device-resident state of one Krylov solve (CG.h:124-154 / 420-453 / 320-352)
 struct CgState {

@@ -13,7 +13,11 @@ sys.path.insert(0, ROOT)
 
 CASES = [("Q4 plane strain 1000x1000 (specialised)", "ps", (1000, 1000)), ("Q4 heat 1024x1024 (specialised)", "heat", (1024, 1024)),
          ("T3 plane stress 1000x500", "t3", (1000, 500)), ("Q4 SRI 1000x500", "sri", (1000, 500)), ("Q8 plane strain Gauss9 600x300", "q8", (600, 300)),
-         ("Hex8 solid 96x48x48 (specialised; scatter in both modes: rows of 81 entries do not fit a tile)", "h8", (96, 48, 48))]
+         ("Hex8 solid 96x48x48 (specialised; gather = PF2_ASSEMBLE_GATHER3D=1: 32-node tiles, one thread per dof row)", "h8", (96, 48, 48))]
+
+
+if os.environ.get("ASM_ONLY"):
+    CASES = [c for c in CASES if c[1] in os.environ["ASM_ONLY"].split(",")]
 
 
 def worker(out_npz):
@@ -59,6 +63,7 @@ if __name__ == "__main__":
     for mode in ("gather", "scatter"):
         env = dict(os.environ)
         env.pop("PF2_ASSEMBLE_SCATTER", None)
+        env["PF2_ASSEMBLE_GATHER3D"] = "1"
         if mode == "scatter":
             env["PF2_ASSEMBLE_SCATTER"] = "1"
         r = subprocess.run([sys.executable, __file__, "--worker", f"/tmp/asm_{mode}.npz"], env=env, capture_output=True, text=True, check=True)

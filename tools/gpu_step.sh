@@ -32,6 +32,9 @@ for stage in "$@"; do
     b2)      for m in 1 0; do PF2_PCG=$m timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 2 --no-hex8 --no-extra-legs --no-headline-2m > "$out/bench_n2_pcg$m.json" 2> "$out/bench_n2_pcg$m.err"; tail -c 1800 "$out/bench_n2_pcg$m.json"; tail -3 "$out/bench_n2_pcg$m.err"; done ;;
     b8)      for m in 1 0; do PF2_PCG=$m timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NG:-8} --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus ${NG:-8} --steps 3 --warmup 2 --hex8 c4 --no-extra-legs --no-headline-2m > "$out/bench_n${NG:-8}_pcg$m.json" 2> "$out/bench_n${NG:-8}_pcg$m.err"; python tools/bench_brief.py "$out/bench_n${NG:-8}_pcg$m.json"; tail -3 "$out/bench_n${NG:-8}_pcg$m.err" | cut -c1-300; done ;;
     probe)   for w in ${PROBE_W:-c2 c4}; do timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NG:-8} --master-addr 127.0.0.1 --master-port 29531 tools/dist_pcg_probe.py $w ${PROBE_IT:-1500} 2>"$out/probe_$w.err" | grep "^{" | tee -a "$out/probe.jsonl"; tail -2 "$out/probe_$w.err" | cut -c1-200; done ;;
+    asm3)    ASM_ONLY=h8 timeout 300 python tools/assemble_probe.py "$out/assemble_probe_h8.json" > "$out/assemble_probe_h8.log" 2>&1; tail -25 "$out/assemble_probe_h8.log" ;;
+    new)     timeout 900 python -m pytest tests/test_gpu_loadvec.py tests/test_gpu_pcg.py tests/test_gpu_cpp_dropin.py tests/test_gpu_matrix_free.py -x -q -k "loadvec or load_vec or selection or assembled_loads or warm or batched or hex8_gather" > "$out/new.log" 2>&1; tail -8 "$out/new.log"
+             timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "hex8_gather or reproducible" >> "$out/new.log" 2>&1; tail -4 "$out/new.log" ;;
     *)       echo "unknown stage $stage" ;;
   esac
 done
