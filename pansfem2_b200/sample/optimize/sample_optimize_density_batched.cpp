@@ -74,8 +74,19 @@ int main(int argc, char** argv) {
         AddPointVectors(r, "r", fout, false);
         AddElementScalers(rho, "s", fout, true);
         fout.close();
-        //  the same file written by the library from the device-resident fields (pf2_simp_export_vtk): byte-identical
-        loop.ExportVTK(out + ".device.vtk", 9, true);
+        //  the same dump written by the library from the device-resident fields (pf2_simp_export_vtk).  Without the reactions it is
+        //  byte-identical to the host writers' file; with them only up to the summation order of the reaction pass (reactions at free
+        //  nodes are round-off noise, and two passes add the element contributions in different orders).
+        std::ofstream fnor(out + ".nor.vtk");
+        MakeHeadderToVTK(fnor);
+        AddPointsToVTK(x, fnor);
+        AddElementToVTK(elements, fnor);
+        AddElementTypes(std::vector<int>(elements.size(), 9), fnor);
+        AddPointVectors(u, "u", fnor, true);
+        AddElementScalers(rho, "s", fnor, true);
+        fnor.close();
+        loop.ExportVTK(out + ".device.vtk", 9, false);
+        loop.ExportVTK(out + ".device_r.vtk", 9, true);
     }
     return 0;
 }

@@ -35,6 +35,10 @@ for stage in "$@"; do
     asm3)    ASM_ONLY=h8 timeout 300 python tools/assemble_probe.py "$out/assemble_probe_h8.json" > "$out/assemble_probe_h8.log" 2>&1; tail -25 "$out/assemble_probe_h8.log" ;;
     new)     timeout 900 python -m pytest tests/test_gpu_loadvec.py tests/test_gpu_pcg.py tests/test_gpu_cpp_dropin.py tests/test_gpu_matrix_free.py -x -q -k "loadvec or load_vec or selection or assembled_loads or warm or batched or hex8_gather" > "$out/new.log" 2>&1; tail -8 "$out/new.log"
              timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "hex8_gather or reproducible" >> "$out/new.log" 2>&1; tail -4 "$out/new.log" ;;
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 400 --csv --log-file "$out/launches_c2.csv" python bench.py --steps 1 --warmup 1 --no-hex8 --no-extra-legs --no-headline-2m --no-cpu-baseline > "$out/launches_bench.log" 2>&1; tail -2 "$out/launches_bench.log" | cut -c1-200; wc -l "$out/launches_c2.csv" ;;
+    ncufull) PF2_PCG=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"spmv_sell_kernel|cg_update_kernel|cg_pupdate_kernel" -s 30 -c 3 -o "$out/cg_kernels_c2" python tools/ncu_target.py 2d 2000 1000 --itr 40 2>&1 | tail -3 ;;
+    san2)    timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_pcg.py tests/test_gpu_loadvec.py tests/test_gpu_dist.py -x -q -k "not two_gpus and not matches_the_oracle" > "$out/sanitizer_memcheck.log" 2>&1; echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|passed|failed" "$out/sanitizer_memcheck.log" | tail -3
+             timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_pcg.py -x -q -k "three_kernel_loop_and_oracle and lambda3 or one_launch_sweeps" > "$out/sanitizer_racecheck.log" 2>&1; echo "racecheck rc=$?"; grep -E "RACECHECK SUMMARY|passed|failed" "$out/sanitizer_racecheck.log" | tail -3 ;;
     *)       echo "unknown stage $stage" ;;
   esac
 done
