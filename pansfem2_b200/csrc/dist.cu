@@ -84,32 +84,37 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 dcg_init_kernel(int lo, int hi, int n, const double* __restrict__ b, const long long* __restrict__ indptr, const int* __restrict__ diagpos,
                 const double* __restrict__ data, double* __restrict__ dvec, double* __restrict__ x, double* __restrict__ r,
-                double* __restrict__ z, double* __restrict__ p, CgState* st, double* partials, unsigned int* ticket) {
-    double v[2] = { 0.0, 0.0 };
+                double* __restrict__ z, double* __restrict__ p, CgState* st, double* partials, unsigned int* ticket,
+                const double* __restrict__ y0) {
+    // y0 = A x0 of a warm start (x keeps x0, ghost entries included; r = b - y0); nullptr: the reference's x0 = 0
+    double v[3] = { 0.0, 0.0, 0.0 };
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        if (i < lo || i >= hi) { x[i] = 0.0; r[i] = 0.0; z[i] = 0.0; p[i] = 0.0; dvec[i] = 1.0; continue; }
+        if (i < lo || i >= hi) { if (!y0) x[i] = 0.0; r[i] = 0.0; z[i] = 0.0; p[i] = 0.0; dvec[i] = 1.0; continue; }
         const double bi = b[i];
-        x[i] = 0.0;
-        r[i] = bi;
-        double zi = bi;
+        double ri = bi;
+        if (y0) ri = bi - y0[i]; else x[i] = 0.0;
+        r[i] = ri;
+        double zi = ri;
         if (MODE == 1) {
             const int dp = diagpos[i];
             const double d = dp >= 0 ? data[indptr[i] + dp] : 0.0;
             dvec[i] = d;
-            zi = bi / d;
+            zi = ri / d;
         }
         z[i] = zi; p[i] = zi;
         v[0] += bi * bi;
-        v[1] += zi * bi;
+        v[1] += zi * ri;
+        v[2] += ri * ri;
     }
-    if (grid_sum_last<2>(v, partials, ticket) && threadIdx.x == 0) { st->red[0] = v[0]; st->red[1] = v[1]; }
+    if (grid_sum_last<3>(v, partials, ticket) && threadIdx.x == 0) { st->red[0] = v[0]; st->red[1] = v[1]; st->red[2] = v[2]; }
 }
 
 // phase 0: after the allreduce of {b.b, z.r} ; phase 1: after the allreduce of {z.r, r.r}
 __global__ void dcg_scalars_kernel(CgState* st, int phase, int maxit, double eps) {
-    if (phase == 0) {
-        st->bb = st->red[0]; st->rr = st->red[0]; st->rho = st->red[1]; st->pAp = 0.0; st->beta = 0.0;
-        st->iter = 0; st->done = 0; st->maxit = maxit; st->eps = eps;
+    if (phase == 0 || phase == 3) {       // 3: warm start -- r.r is its own sum and the solve may begin converged
+        st->bb = st->red[0]; st->rr = (phase == 3) ? st->red[2] : st->red[0]; st->rho = st->red[1]; st->pAp = 0.0; st->beta = 0.0;
+        st->iter = 0; st->maxit = maxit; st->eps = eps;
+        st->done = (phase == 3 && sqrt(st->red[2]) < eps * sqrt(st->red[0])) ? 1 : 0;
     } else {
         if (st->done) return;
         const double zr = st->red[0], rr = st->red[1];
@@ -189,21 +194,23 @@ dcg_pupdate_kernel(int lo, int hi, const double* __restrict__ z, double* __restr
 //   bitwise identical on every rank.  Slots and flags are double-buffered by epoch parity: a rank cannot run two epochs
 //   ahead of a peer because finishing an epoch needs that peer's flag.
 // ---------------------------------------------------------------------------------------------------------------
-// allreduce of st->pAp after the SpMV (phase 0), of {bb, zr} after init (phase 1), of {zr, rr} + the scalar tail (phase 2)
+// allreduce of st->pAp after the SpMV (phase 0), of {bb, zr} after init (phase 1; phase 3 = warm start: {bb, zr, rr}), of {zr, rr} + the
+// scalar tail (phase 2)
 __global__ void p2p_cg_scalars_kernel(P2P P, unsigned long long* epoch_ctr, CgState* st, int phase, int maxit, double eps) {
-    if (phase != 1 && st->done) return;
+    if (phase != 1 && phase != 3 && st->done) return;
     __shared__ double v[4];
     if (threadIdx.x == 0) {
         if (phase == 0) { v[0] = st->pAp; }
-        else { v[0] = st->red[0]; v[1] = st->red[1]; }
+        else { v[0] = st->red[0]; v[1] = st->red[1]; v[2] = st->red[2]; }
     }
     __syncwarp();
-    p2p_allreduce_warp(P, epoch_ctr, v, phase == 0 ? 1 : 2);
+    p2p_allreduce_warp(P, epoch_ctr, v, phase == 0 ? 1 : (phase == 3 ? 3 : 2));
     if (threadIdx.x == 0) {
         if (phase == 0) st->pAp = v[0];
-        else if (phase == 1) {
-            st->bb = v[0]; st->rr = v[0]; st->rho = v[1]; st->pAp = 0.0; st->beta = 0.0;
-            st->iter = 0; st->done = 0; st->maxit = maxit; st->eps = eps;
+        else if (phase == 1 || phase == 3) {
+            st->bb = v[0]; st->rr = (phase == 3) ? v[2] : v[0]; st->rho = v[1]; st->pAp = 0.0; st->beta = 0.0;
+            st->iter = 0; st->maxit = maxit; st->eps = eps;
+            st->done = (phase == 3 && sqrt(v[2]) < eps * sqrt(v[0])) ? 1 : 0;
         } else {
             const double zr = v[0], rr = v[1];
             st->beta = zr / st->rho;
@@ -418,7 +425,10 @@ static int solve_dist_ilu(pf2_csr* A, const double* b, double* x, int itrmax, do
     return PF2_OK;
 }
 
-int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out) {
+int spmv(pf2_csr* A, const double* x, double* y);
+
+// warm = 1: x holds the initial guess, ghost entries included (pf2_solve_x0); ILU0CG always starts from 0
+int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int warm, int* iters_out, double* relres_out) {
     pf2_ctx* c = A->ctx;
     pf2_dist* d = A->dist;
     if (solver == PF2_SOLVER_ILU0CG) return solve_dist_ilu(A, b, x, itrmax, eps, iters_out, relres_out);
@@ -426,8 +436,10 @@ int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, d
     const int n = A->rows, lo = A->own_lo, hi = A->own_hi;
     const int grid = std::min(c->grid_for(n, 2), c->sm_count * 4);
     cudaStream_t s = c->stream;
-    if (solver == PF2_SOLVER_CG) dcg_init_kernel<0><<<grid, kThreads, 0, s>>>(lo, hi, n, b, A->indptr, A->diagpos, A->data, A->dvec, x, A->r, A->z, A->p, A->st, c->red.partials, c->red.ticket);
-    else dcg_init_kernel<1><<<grid, kThreads, 0, s>>>(lo, hi, n, b, A->indptr, A->diagpos, A->data, A->dvec, x, A->r, A->z, A->p, A->st, c->red.partials, c->red.ticket);
+    const double* y0 = nullptr;
+    if (warm) { PF2_TRY(spmv(A, x, A->y)); y0 = A->y; }        // r0 = b - A x0: one extra product over the local rows
+    if (solver == PF2_SOLVER_CG) dcg_init_kernel<0><<<grid, kThreads, 0, s>>>(lo, hi, n, b, A->indptr, A->diagpos, A->data, A->dvec, x, A->r, A->z, A->p, A->st, c->red.partials, c->red.ticket, y0);
+    else dcg_init_kernel<1><<<grid, kThreads, 0, s>>>(lo, hi, n, b, A->indptr, A->diagpos, A->data, A->dvec, x, A->r, A->z, A->p, A->st, c->red.partials, c->red.ticket, y0);
     PF2_LAUNCH_CHECK();
     const bool p2p = d->p2p && A->p2p_ready;
     if (p2p) {
@@ -444,12 +456,12 @@ int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, d
     }
     const int hgrid = std::min(c->grid_for(hi - lo, 2), c->sm_count * 4);
     if (p2p) {
-        p2p_cg_scalars_kernel<<<1, 32, 0, s>>>(A->p2p_view, d->epoch, A->st, 1, itrmax, eps);
+        p2p_cg_scalars_kernel<<<1, 32, 0, s>>>(A->p2p_view, d->epoch, A->st, warm ? 3 : 1, itrmax, eps);
         p2p_pupdate_halo_kernel<<<hgrid, kThreads, 0, s>>>(lo, hi, A->z, A->p, A->st, 1, A->p2p_view, A->halo[0], A->halo[2], A->halo[3], A->halo[5],
                                                            d->epoch, c->red.ticket + 1);
     } else {
-        PF2_TRY(dist_allreduce(d, A->st->red, 2));
-        dcg_scalars_kernel<<<1, 1, 0, s>>>(A->st, 0, itrmax, eps);
+        PF2_TRY(dist_allreduce(d, A->st->red, warm ? 3 : 2));
+        dcg_scalars_kernel<<<1, 1, 0, s>>>(A->st, warm ? 3 : 0, itrmax, eps);
         PF2_TRY(dist_halo(d, A->p, A->halo));
     }
     c->launches += 2;

@@ -221,7 +221,7 @@ static void harvest_profile(pf2_csr* A, int slot) {
 }
 
 int ensure_workspace_pub(pf2_csr* A) { return ensure_workspace(A); }
-int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out);
+int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int warm, int* iters_out, double* relres_out);
 int solve_bicgstab(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int* iters_out, double* relres_out);
 
 // ---- PCG in nodal numbering with the matrix-free operator (single GPU; csr.cu / spmv_mf.cuh) -----------------------------
@@ -304,7 +304,7 @@ int solve_x0(pf2_csr* A, int solver, const double* b, double* x, int itrmax, dou
         const int rc = pcg_persistent_solve(A, solver, b, x, itrmax, eps, warm, iters_out, relres_out);
         if (rc != PF2_E_UNSUPPORTED) return rc;
     }
-    if (A->dist) return solve_dist(A, solver, b, x, itrmax, eps, iters_out, relres_out);      // host-ordered loop: always from x0 = 0
+    if (A->dist) return solve_dist(A, solver, b, x, itrmax, eps, warm, iters_out, relres_out);
     if (A->spmv_variant == 41 && A->mf_nodal && A->mf_version > 0 && solver != PF2_SOLVER_ILU0CG)
         return solve_mf_nodal(A, solver, b, x, itrmax, eps, warm, iters_out, relres_out);
     PF2_TRY(ensure_workspace(A));

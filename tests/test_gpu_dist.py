@@ -27,6 +27,7 @@ def _ngpu():
 CASES = [
     # default: three-kernel loop over peer memory (LL allreduce in the last CTA, halo planes pushed by the p-update kernel)
     ("2d 96 40", {}), ("2d 96 40 --mma", {}), ("3d 16 8 6", {}), ("3d 16 8 6 --mma", {}), ("heat 48 48", {}),
+    ("2d 96 40 --warm", {}), ("3d 16 8 6 --warm", {"PF2_P2P": "0"}),             # pf2_solve_x0 under the partition (ghost entries of x0 valid)
     ("2d 96 40", {"PF2_HALO_DEFER": "1"}), ("3d 16 8 6", {"PF2_HALO_DEFER": "1", "PF2_SELL_L2_MB": "100"}),      # opt-in variants
     # the persistent kernel's partitioned instantiation
     ("2d 96 40", {"PF2_PCG": "1"}), ("2d 96 40 --mma", {"PF2_PCG": "1"}), ("heat 48 48", {"PF2_PCG": "1"}), ("2d 96 40 --warm", {"PF2_PCG": "1"}),
