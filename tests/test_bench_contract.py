@@ -24,3 +24,23 @@ def test_reference_arm_prints_the_contract_line():
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
     e = d["e2e"]
     assert e["value"] == d["value"] and e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+    # the arm scales a strip to the full mesh and says so; one design iteration is run for real next to it
+    assert d["extrapolated"] is True and cb["extrapolated"] is True and cb["strip"] and "EXTRAPOLATED" in cb["sample"]
+    assert d["config"]["cg_iters_source"] and d["measured_pair"]["extrapolated"] is False and d["measured_pair"]["seconds"] > 0
+
+
+def test_reference_arm_uses_the_cg_count_the_native_arm_measured():
+    sys.path.insert(0, ROOT)
+    import bench
+    P = bench.make_problem("c1")
+    n, src = bench.reference_cg_count("c2", 5, 20, bench.make_problem("pair"))
+    rec = json.load(open(os.path.join(ROOT, "profiles", "measured_cg_iters.json")))["c2"]["cg_iters_by_k"]
+    assert abs(n - sum(rec[5:25]) / 20.0) < 1e-9 and "measured by the native arm" in src
+    n2, src2 = bench.reference_cg_count("c3", 5, 20, P)          # no record for that workload: the growth law, labelled as an estimate
+    assert "ESTIMATED" in src2 and n2 > 0
+
+
+def test_committed_n1_objective_histories_cover_the_bench_legs():
+    obj = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_objective_n1.json")))
+    assert len(obj["c2"]) >= 25 and len(obj["2m"]) >= 15 and len(obj["c4"]) >= 1 and len(obj["c5"]) >= 3
+    assert all(b < a for a, b in zip(obj["c2"][:10], obj["c2"][1:11]))          # the compliance falls monotonically over the first iterations

@@ -125,3 +125,13 @@ def test_slab_ranges_cover_elements_and_rows():
         assert rows[0][0] == 0 and rows[-1][1] == P.free_dofs()
         assert all(rows[i][1] == rows[i + 1][0] for i in range(world - 1))
         assert elems[0][0] == 0 and elems[-1][1] == P.grid[0]
+
+
+def test_slab_refuses_a_filter_radius_wider_than_the_ghost_plane():
+    """One ghost element plane per side holds the filter neighbours of an owned element only for radius < 2 element widths."""
+    import pytest
+    from pansfem2_b200 import partition, problems
+    P = problems.cantilever2d(24, 8, radius=2.5)
+    with pytest.raises(ValueError, match="ghost element plane"):
+        partition.slab(P, 0, 2)
+    assert partition.slab(problems.cantilever2d(24, 8, radius=1.5), 1, 2).local.nelem == 13 * 8
