@@ -463,8 +463,9 @@ class Runner:
         x.free()
         if out["ilu0cg"]["converged"]:
             out["ilu_vs_jacobi_time"] = out["ilu0cg"]["ms"] / out["scalingcg"]["ms"]
-        out["note"] = ("ILU0CG = level-scheduled factorisation once + two sync-free triangular sweeps (one launch each) per iteration; natural ordering gives "
-                       "~(nx+ny) dependency levels, so a sweep is latency-bound: a parity feature of the reference, not the fast path")
+        out["note"] = ("ILU0CG = factorisation once (one launch per dependency level) + two triangular sweeps per iteration, each ONE launch in which a CTA "
+                       "(or an 8-CTA cluster) walks the levels; natural ordering gives ~(nx+ny) levels, so a sweep is latency-bound: a parity feature of "
+                       "the reference, not the fast path")
         return out
 
     def parity_vs_n1(self, tag="value"):

@@ -278,7 +278,47 @@ ilu0_sweep_cta_kernel(int nlevels, const int* __restrict__ level_ptr, const int*
             if (i < lo || i >= hi) continue;
             const long long s = indptr[i], e = indptr[i + 1];
             double vi = v[i];
-            if (FORWARD) {
+            const int dp = diagpos[i];
+            if (dp >= 0) {
+                // the strictly-lower entries are [s, s + dp), the strictly-upper ones (s + dp, e): no data-dependent loop exit, so the
+                // column indices, the factors and the v entries of a chunk are all requested before the first is used (three dependent
+                // load rounds per row instead of one per entry); the subtractions keep the reference's order (ascending / descending k)
+                constexpr int CH = 8;
+                if (FORWARD) {
+                    for (int k0 = 0; k0 < dp; k0 += CH) {
+                        int cc[CH];
+                        double qq[CH], vv[CH];
+#pragma unroll
+                        for (int u = 0; u < CH; u++) {
+                            const bool in = k0 + u < dp;
+                            cc[u] = in ? indices[s + k0 + u] : -1;
+                            qq[u] = in ? q[s + k0 + u] : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < CH; u++) vv[u] = (cc[u] >= lo) ? (CLUSTER > 1 ? __ldcg(v + cc[u]) : v[cc[u]]) : 0.0;
+#pragma unroll
+                        for (int u = 0; u < CH; u++) if (cc[u] >= lo) vi -= qq[u] * vv[u];
+                    }
+                } else {
+                    const int nup = (int)(e - s) - dp - 1;
+                    for (int k0 = 0; k0 < nup; k0 += CH) {
+                        int cc[CH];
+                        double qq[CH], vv[CH];
+#pragma unroll
+                        for (int u = 0; u < CH; u++) {
+                            const bool in = k0 + u < nup;
+                            const long long k = e - 1 - (k0 + u);
+                            cc[u] = in ? indices[k] : -1;
+                            qq[u] = in ? q[k] : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < CH; u++) vv[u] = (cc[u] >= 0 && cc[u] < hi) ? (CLUSTER > 1 ? __ldcg(v + cc[u]) : v[cc[u]]) : 0.0;
+#pragma unroll
+                        for (int u = 0; u < CH; u++) if (cc[u] >= 0 && cc[u] < hi) vi -= qq[u] * vv[u];
+                    }
+                    vi /= q[s + dp];
+                }
+            } else if (FORWARD) {
                 for (long long k = s; k < e; k++) {
                     const int c = indices[k];
                     if (c >= i) break;
