@@ -16,7 +16,7 @@ stream, max over ranks) -- so `value`, `e2e` and the extra legs time the same de
     value          device-resident loop, the reference's algorithm as is (assembled CSR, ScalingCG from x0 = 0)
     e2e            the same iterations through pf2_simp_iterate_host (design uploaded from / downloaded to pinned host memory)
     legs           opt-in variants, each with its own cg_iters_per_step: warm_start (pf2_solve_x0), matrix_free
-                   (pf2_csr_matrix_free), warm_start+matrix_free
+                   (pf2_csr_matrix_free), warm_start+matrix_free; at N > 1 also single_reduction_cg (pf2_csr_set_cg_variant)
     headline_2m    BASELINE.json's metric size: 1000x1000 Q4 (2.0 M dof), value + e2e
     hex8_scaling   configs[3] 256x128x128 hex8 (one SIMP iteration from the uniform design) and configs[4] 384x192x192 hex8
                    (design loop), row-partitioned over the N GPUs like everything else at N > 1
@@ -312,7 +312,7 @@ class Runner:
         dist.all_reduce(t)
         return t.item()
 
-    def leg(self, steps, warmup, host=False, warm_start=False, matrix_free=False, repeat_first=False, tag="value"):
+    def leg(self, steps, warmup, host=False, warm_start=False, matrix_free=False, repeat_first=False, single_reduction=False, tag="value"):
         """Reset to the uniform design, `warmup` untimed iterations, `steps` timed ones.  repeat_first: every iteration (warm-up and
         timed) is design iteration k = 0 from the uniform design (configs[3]: 'single SIMP iteration'), resets outside the timer."""
         from pansfem2_b200 import capi
@@ -324,6 +324,7 @@ class Runner:
                 S.A.set_spmv_variant(0)
             self._mf = matrix_free
         S.set_warm_start(warm_start)
+        S.A.set_cg_variant(1 if single_reduction else 0)     # N > 1, peer-memory backend: one cross-GPU sum and two kernels per PCG iteration
         S.reset()
         if host and self.pinned is None:
             self.pinned = (capi.pinned_empty(self.nelem), capi.pinned_empty(self.nelem), capi.pinned_empty(self.nelem))
@@ -580,12 +581,16 @@ def main():
     legs = {}
     if not args.no_extra_legs:
         Kx = min(K, 8)
-        for tag, kw in (("warm_start", dict(warm_start=True)), ("matrix_free", dict(matrix_free=True)),
-                        ("warm_start+matrix_free", dict(warm_start=True, matrix_free=True))):
+        variants = [("warm_start", dict(warm_start=True)), ("matrix_free", dict(matrix_free=True)),
+                    ("warm_start+matrix_free", dict(warm_start=True, matrix_free=True))]
+        if world > 1 and os.environ.get("PF2_P2P", "1") != "0":
+            variants.append(("single_reduction_cg", dict(single_reduction=True)))
+        for tag, kw in variants:
             try:
                 Lx = R.leg(Kx, W, tag=tag, **kw)
                 n = min(len(Lx["objective"]), len(Lv["objective"]))
-                legs[tag] = brief(Lx, {"objective_max_rel_diff_vs_value_leg": max(abs(a - b) / abs(b) for a, b in zip(Lx["objective"][:n], Lv["objective"][:n])),
+                legs[tag] = brief(Lx, {"single_reduction_solves": Lx["pcg"].get("single_reduction_solves", 0),
+                                       "objective_max_rel_diff_vs_value_leg": max(abs(a - b) / abs(b) for a, b in zip(Lx["objective"][:n], Lv["objective"][:n])),
                                        "value_leg_same_window": (Kx / (1e-3 * sum(s["phase_ms"]["solve"] + s["phase_ms"]["assemble"] + s["phase_ms"]["update"] +
                                                                                     s["phase_ms"]["filter"] + s["phase_ms"]["sens"] + s["phase_ms"]["filter_sens"]
                                                                                     for s in Lv["steps"][:Kx]))) if Kx <= len(Lv["steps"]) else None})

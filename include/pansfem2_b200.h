@@ -200,6 +200,12 @@ int pf2_solve_x0(pf2_csr* A, int solver, const double* b_dev, double* x_dev, int
 /* How CG / ScalingCG iterate (CG.h:430-449): 1 = one persistent cooperative kernel per solve (grid barriers carry the dot
  * products; default where the SELL-32 mirror applies), 0 = three kernels per iteration, -1 = environment (PF2_PCG, default 1). */
 int pf2_csr_set_pcg_mode(pf2_csr* A, int mode);
+/* Recurrences of CG / ScalingCG on a ROW-PARTITIONED matrix with the peer-memory backend: 0 = the reference's (CG.h:430-449: two
+ * cross-GPU sums, three kernels per iteration; default), 1 = single-reduction (Chronopoulos-Gear: p = u + beta p, s = w + beta s,
+ * alpha = gamma / (delta - beta gamma / alpha_old); ONE sum, two kernels per iteration).  Same iterates in exact arithmetic and the
+ * same stopping rule; round-off differs, so results agree to the solver tolerance rather than bitwise.  -1 = environment
+ * (PF2_CG_SINGLE_REDUCTION=1).  Ignored on one GPU, with the NCCL backend and by the other solvers. */
+int pf2_csr_set_cg_variant(pf2_csr* A, int variant);
 /* per-kernel device times of the Krylov loop.  Three-kernel loop: CUDA events around one iteration per chunk; persistent kernel:
  * its in-kernel %globaltimer stamps per phase (barriers included), samples = iterations.
  * out = {spmv+dot ms, update ms, p-update ms, samples, total iterations, SpMV variant, rows, nnz} */
@@ -207,7 +213,8 @@ int pf2_csr_solver_stats(pf2_csr* A, double out[8]);
 int pf2_csr_solver_stats_reset(pf2_csr* A);
 /* persistent PCG kernel since the last reset: out = {CUDA-event ms of the kernel launches (whole solves), iterations, solves,
  * CTAs of the last launch, product / update / p-update phase ms per iteration, stored SELL entries, and the part of each of the
- * three phases CTA 0 spent inside the grid exchange (tail of the grid + exchange latency), 0} */
+ * three phases CTA 0 spent inside the grid exchange (tail of the grid + exchange latency), solves that ran the single-reduction
+ * recurrences (pf2_csr_set_cg_variant)} */
 int pf2_csr_pcg_stats(pf2_csr* A, double out[12]);
 /* diagnostics: %globaltimer of every CTA at the start / end of its share of the three phases in iteration 5 of the last persistent
  * solve: out_host[6][2048] (product start, end, update start, end, p-update start, end) */

@@ -286,6 +286,10 @@ class Csr:
                C.byref(it), C.byref(rr)))
         return it.value, rr.value
 
+    def set_cg_variant(self, variant):
+        """0: the reference's PCG recurrences, 1: single-reduction (partitioned matrix, peer-memory backend), -1: environment"""
+        _ck(lib().pf2_csr_set_cg_variant(self.h, int(variant)))
+
     def set_pcg_mode(self, mode):
         """1: persistent cooperative PCG kernel, 0: three kernels per iteration, -1: environment default (PF2_PCG)."""
         _ck(lib().pf2_csr_set_pcg_mode(self.h, int(mode)))
@@ -294,7 +298,8 @@ class Csr:
         st = (C.c_double * 12)()
         _ck(lib().pf2_csr_pcg_stats(self.h, st))
         return dict(kernel_ms=st[0], iters=int(st[1]), solves=int(st[2]), grid=int(st[3]), product_ms=st[4], update_ms=st[5],
-                    pupdate_ms=st[6], sell_entries=int(st[7]), product_wait_ms=st[8], update_wait_ms=st[9], pupdate_wait_ms=st[10])
+                    pupdate_ms=st[6], sell_entries=int(st[7]), product_wait_ms=st[8], update_wait_ms=st[9], pupdate_wait_ms=st[10],
+                    single_reduction_solves=int(st[11]))
 
     def solver_stats(self, reset=False):
         st = (C.c_double * 8)()

@@ -607,6 +607,7 @@ int pf2_csr_destroy(pf2_csr* A) {
     if (A->h_pcg_sync) cudaFreeHost(A->h_pcg_sync);
     if (A->mf_E) cudaFree(A->mf_E);
     if (A->mf_slab) cudaFree(A->mf_slab);
+    if (A->cg1_s) cudaFree(A->cg1_s);
     if (g_mf_owner == A) g_mf_owner = nullptr;
     if (A->bi_slab) cudaFree(A->bi_slab);
     if (A->bi_st) cudaFree(A->bi_st);

@@ -427,11 +427,201 @@ static int solve_dist_ilu(pf2_csr* A, const double* b, double* x, int itrmax, do
 
 int spmv(pf2_csr* A, const double* x, double* y);
 
+// ---------------------------------------------------------------------------------------------------------------
+// Single-reduction PCG under the partition (opt-in: pf2_csr_set_cg_variant(A, 1) / PF2_CG_SINGLE_REDUCTION=1; peer-memory backend).
+// Chronopoulos-Gear form of CG.h:124-154 / 420-453: with u = M^-1 r, w = A u the direction and its image follow recurrences
+//     p = u + beta p,  s = w + beta s  (= A p),  x += alpha p,  r -= alpha s,
+//     gamma = u.r, delta = w.u,  beta = gamma / gamma_old,  alpha = gamma / (delta - beta gamma / alpha_old),
+// so gamma, delta and r.r are reduced TOGETHER: one cross-GPU sum and two kernels per iteration (update + halo push | product + sum + tail)
+// instead of two sums and three kernels.  Same iterates as the reference in exact arithmetic; round-off differs, so the parity bar is the
+// solver tolerance (tests/test_gpu_dist.py), not bit equality, and the reference's recurrences stay the default.
+// Storage: A->p holds u (its ghost ranges are what the neighbours write), A->z the direction p, A->y holds w, A->cg1_s holds s.
+// ---------------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+cg1_init_kernel(int lo, int hi, int n, const double* __restrict__ b, const long long* __restrict__ indptr, const int* __restrict__ diagpos,
+                const double* __restrict__ data, double* __restrict__ dvec, double* __restrict__ x, double* __restrict__ r,
+                double* __restrict__ u, double* __restrict__ pd, double* __restrict__ sd, CgState* st, double* partials, unsigned int* ticket,
+                const double* __restrict__ y0, int maxit, double eps) {
+    double v[3] = { 0.0, 0.0, 0.0 };
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        pd[i] = 0.0; sd[i] = 0.0;
+        // ghost entries of u are NOT touched here: the neighbours' set-up pushes may already have landed (no cross-GPU sum separates this
+        // kernel from them, unlike the reference-form set-up), and every ghost row is written by its owner before the first product
+        if (i < lo || i >= hi) { if (!y0) x[i] = 0.0; r[i] = 0.0; dvec[i] = 1.0; continue; }
+        const double bi = b[i];
+        double ri = bi;
+        if (y0) ri = bi - y0[i]; else x[i] = 0.0;
+        r[i] = ri;
+        double ui = ri;
+        if (MODE == 1) {
+            const int dp = diagpos[i];
+            const double d = dp >= 0 ? data[indptr[i] + dp] : 0.0;
+            dvec[i] = d;
+            ui = ri / d;
+        }
+        u[i] = ui;
+        v[0] += bi * bi;
+        v[1] += ui * ri;
+        v[2] += ri * ri;
+    }
+    if (grid_sum_last<3>(v, partials, ticket) && threadIdx.x == 0) {
+        st->red[0] = v[0]; st->red[1] = v[1]; st->red[2] = v[2];
+        st->rho = 0.0; st->pAp = 0.0; st->beta = 0.0; st->zr_new = 0.0; st->rr = 0.0; st->bb = 0.0;
+        st->iter = 0; st->done = 0; st->maxit = maxit; st->eps = eps;
+        st->pad = 1;                     // the first product's tail takes {b.b, u.r, r.r} and starts the recurrences (beta = 0)
+    }
+}
+
+// update of p, s, x, r, u on the owned rows with the halo exchange of u fused (as p2p_pupdate_halo_kernel): partial {u.r, r.r} -> st->red
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+cg1_update_halo_kernel(int lo, int hi, const double* __restrict__ w, const double* __restrict__ dvec, double* __restrict__ u,
+                       double* __restrict__ pd, double* __restrict__ sd, double* __restrict__ x, double* __restrict__ r, CgState* st,
+                       double* partials, unsigned int* ticket, P2P P, int sendL, int cntL, int sendR, int cntR, unsigned long long* epoch_ctr) {
+    if (st->done) return;
+    const double alpha = st->zr_new, beta = st->beta;
+    double v[2] = { 0.0, 0.0 };
+    for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
+        const double pi = u[i] + beta * pd[i];
+        const double si = w[i] + beta * sd[i];
+        pd[i] = pi; sd[i] = si;
+        x[i] = x[i] + alpha * pi;
+        const double ri = r[i] + (-alpha) * si;
+        r[i] = ri;
+        const double ui = (MODE == 0) ? ri : ri / dvec[i];
+        u[i] = ui;
+        if (P.left_p && i >= sendL && i < sendL + cntL) P.left_p[P.left_recv_off + (i - sendL)] = ui;
+        if (P.right_p && i >= sendR && i < sendR + cntR) P.right_p[P.right_recv_off + (i - sendR)] = ui;
+        v[0] += ui * ri;
+        v[1] += ri * ri;
+    }
+    __threadfence_system();              // this CTA's remote stores are visible system-wide before its ticket
+    if (!grid_sum_last<2>(v, partials, ticket)) return;
+    if (threadIdx.x == 0) {
+        st->red[0] = v[0]; st->red[1] = v[1];
+        __threadfence_system();
+        const unsigned long long epoch = epoch_ctr[1] + 1;
+        if (P.rank > 0) *(volatile unsigned long long*)(P.halo_flags[P.rank - 1] + 1) = epoch;
+        if (P.rank < P.world - 1) *(volatile unsigned long long*)(P.halo_flags[P.rank + 1] + 0) = epoch;
+        const unsigned long long* mine = P.halo_flags[P.rank];
+        if (P.rank > 0) p2p_wait_flag(P, mine + 0, epoch);
+        if (P.rank < P.world - 1) p2p_wait_flag(P, mine + 1, epoch);
+        __threadfence_system();
+        epoch_ctr[1] = epoch;
+    }
+}
+
+static int set_cg1_state(pf2_csr* A, CgState* st, cudaStream_t s) {
+    if (A->p2p_view.cg1 == st) return PF2_OK;
+    A->p2p_view.cg1 = st;
+    PF2_CUDA(cudaMemcpyAsync(A->p2p_dev, &A->p2p_view, sizeof(P2PView), cudaMemcpyHostToDevice, s));
+    return PF2_OK;
+}
+
+bool cg1_requested(const pf2_csr* A) {
+    if (A->cg_variant >= 0) return A->cg_variant == 1;
+    static const int env = [] { const char* e = getenv("PF2_CG_SINGLE_REDUCTION"); return (e && atoi(e) != 0) ? 1 : 0; }();
+    return env == 1;
+}
+
+static int solve_dist_cg1(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int warm, int* iters_out, double* relres_out) {
+    pf2_ctx* c = A->ctx;
+    pf2_dist* d = A->dist;
+    PF2_TRY(ensure_workspace_pub(A));
+    const int n = A->rows, lo = A->own_lo, hi = A->own_hi;
+    cudaStream_t s = c->stream;
+    if (!A->cg1_s) PF2_CUDA(cudaMalloc((void**)&A->cg1_s, sizeof(double) * (size_t)n));
+    plan_spmv_pub(A);
+    if (A->p2p_view.cg1 != nullptr || A->p2p_view.defer_halo_wait) {
+        A->p2p_view.cg1 = nullptr; A->p2p_view.defer_halo_wait = 0;
+        PF2_CUDA(cudaMemcpyAsync(A->p2p_dev, &A->p2p_view, sizeof(P2PView), cudaMemcpyHostToDevice, s));
+    }
+    const double* y0 = nullptr;
+    if (warm) { PF2_TRY(spmv(A, x, A->y)); y0 = A->y; }
+    double* u = A->p; double* pd = A->z; double* w = A->y; double* sd = A->cg1_s;
+    const int grid = std::min(c->grid_for(n, 2), c->sm_count * 4);
+    if (solver == PF2_SOLVER_CG) cg1_init_kernel<0><<<grid, kThreads, 0, s>>>(lo, hi, n, b, A->indptr, A->diagpos, A->data, A->dvec, x, A->r, u, pd, sd, A->st, c->red.partials, c->red.ticket, y0, itrmax, eps);
+    else cg1_init_kernel<1><<<grid, kThreads, 0, s>>>(lo, hi, n, b, A->indptr, A->diagpos, A->data, A->dvec, x, A->r, u, pd, sd, A->st, c->red.partials, c->red.ticket, y0, itrmax, eps);
+    const int hgrid = std::min(c->grid_for(hi - lo, 2), c->sm_count * 4);
+    // ghost ranges of u: the p-update kernel's set-up form pushes the boundary planes of the array it is given and waits for the neighbours'
+    p2p_pupdate_halo_kernel<<<hgrid, kThreads, 0, s>>>(lo, hi, u, u, A->st, 1, A->p2p_view, A->halo[0], A->halo[2], A->halo[3], A->halo[5], d->epoch, c->red.ticket + 1);
+    PF2_LAUNCH_CHECK();
+    PF2_TRY(set_cg1_state(A, A->st, s));
+    PF2_TRY(spmv_dot(A, u, w, A->st, &A->st->pAp));          // w0 = A u0; its tail sums {w.u, b.b, u.r, r.r} and sets alpha0, beta0 = 0
+    c->launches += 3;
+
+    const int chunk = 32;
+    int enq = 0, slot = 0;
+    bool have_prev = false, finished = false;
+    CgState last;
+    memset(&last, 0, sizeof last);
+    int rc = PF2_OK;
+    while (!finished && rc == PF2_OK) {
+        const int todo = std::min(chunk, itrmax - enq);
+        for (int k = 0; k < todo && rc == PF2_OK; k++) {
+            if (solver == PF2_SOLVER_CG) cg1_update_halo_kernel<0><<<hgrid, kThreads, 0, s>>>(lo, hi, w, A->dvec, u, pd, sd, x, A->r, A->st, c->red.partials, c->red.ticket, A->p2p_view, A->halo[0], A->halo[2], A->halo[3], A->halo[5], d->epoch);
+            else cg1_update_halo_kernel<1><<<hgrid, kThreads, 0, s>>>(lo, hi, w, A->dvec, u, pd, sd, x, A->r, A->st, c->red.partials, c->red.ticket, A->p2p_view, A->halo[0], A->halo[2], A->halo[3], A->halo[5], d->epoch);
+            const bool sample = (k == todo / 2) && enq > 0;      // one product per chunk is bracketed by events (roofline)
+            if (sample) cudaEventRecord(A->pev[slot][0], s);
+            rc = spmv_dot(A, u, w, A->st, &A->st->pAp);
+            if (sample) { cudaEventRecord(A->pev[slot][1], s); A->pev_armed[slot] = true; }
+            c->launches += 2;
+        }
+        if (rc != PF2_OK) break;
+        if (cudaGetLastError() != cudaSuccess) { set_error("single-reduction PCG: launch failed"); rc = PF2_E_CUDA; break; }
+        enq += todo;
+        cudaMemcpyAsync(&A->h_st[slot], A->st, sizeof(CgState), cudaMemcpyDeviceToHost, s);
+        cudaEventRecord(A->ev[slot], s);
+        if (have_prev) {
+            cudaEventSynchronize(A->ev[slot ^ 1]);
+            last = A->h_st[slot ^ 1];
+            if (A->pev_armed[slot ^ 1]) {
+                A->pev_armed[slot ^ 1] = false;
+                float ms = 0;
+                if (!last.done && cudaEventElapsedTime(&ms, A->pev[slot ^ 1][0], A->pev[slot ^ 1][1]) == cudaSuccess) { A->prof_ms[0] += ms; A->prof_samples++; }
+                else cudaGetLastError();
+            }
+            if (last.done) finished = true;
+        }
+        if (!finished && (enq >= itrmax || todo == 0)) {
+            cudaEventSynchronize(A->ev[slot]);
+            last = A->h_st[slot];
+            finished = true;
+        }
+        have_prev = true;
+        slot ^= 1;
+    }
+    cudaStreamSynchronize(s);
+    A->pev_armed[0] = A->pev_armed[1] = false;
+    // products outside this solve (ILU0CG, BiCGSTAB, warm-start residuals) reduce their own dot only
+    A->p2p_view.cg1 = nullptr;
+    PF2_CUDA(cudaMemcpyAsync(A->p2p_dev, &A->p2p_view, sizeof(P2PView), cudaMemcpyHostToDevice, s));
+    if (rc != PF2_OK) return rc;
+    PF2_CUDA(cudaMemcpyAsync(&A->h_st[0], A->st, sizeof(CgState), cudaMemcpyDeviceToHost, s));
+    PF2_CUDA(cudaStreamSynchronize(s));
+    last = A->h_st[0];
+    A->total_iters += last.iter;
+    A->cg1_solves++;
+    if (iters_out) *iters_out = last.iter;
+    if (relres_out) *relres_out = sqrt(last.rr) / sqrt(last.bb);
+    unsigned long long aborted = 0;
+    PF2_CUDA(cudaMemcpy(&aborted, d->epoch + 2, sizeof aborted, cudaMemcpyDeviceToHost));
+    if (aborted) { set_error("partitioned PCG: a wait on a peer GPU timed out (a rank left the solve?)"); return PF2_E_CUDA; }
+    if (!last.done) {
+        set_error("Convergence:faild after %d iterations (relres %.3e)", last.iter, sqrt(last.rr) / sqrt(last.bb));
+        return PF2_E_NOCONV;
+    }
+    return PF2_OK;
+}
+
 // warm = 1: x holds the initial guess, ghost entries included (pf2_solve_x0); ILU0CG always starts from 0
 int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, double eps, int warm, int* iters_out, double* relres_out) {
     pf2_ctx* c = A->ctx;
     pf2_dist* d = A->dist;
     if (solver == PF2_SOLVER_ILU0CG) return solve_dist_ilu(A, b, x, itrmax, eps, iters_out, relres_out);
+    if (d->p2p && A->p2p_ready && cg1_requested(A) && (solver == PF2_SOLVER_CG || solver == PF2_SOLVER_SCALINGCG))
+        return solve_dist_cg1(A, solver, b, x, itrmax, eps, warm, iters_out, relres_out);
     PF2_TRY(ensure_workspace_pub(A));
     const int n = A->rows, lo = A->own_lo, hi = A->own_hi;
     const int grid = std::min(c->grid_for(n, 2), c->sm_count * 4);

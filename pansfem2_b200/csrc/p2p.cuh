@@ -90,10 +90,36 @@ __device__ __forceinline__ void finish_dot(double local_sum, double* dot_out, co
     }
     __shared__ double p2p_vals[4];
     if (threadIdx.x < 32) {
-        if (threadIdx.x == 0) p2p_vals[0] = local_sum;
+        CgState* st = p2p->cg1;
+        if (st == nullptr) {
+            if (threadIdx.x == 0) p2p_vals[0] = local_sum;
+            __syncwarp();
+            p2p_allreduce_warp(*p2p, epoch_ctr, p2p_vals, 1);
+            if (threadIdx.x == 0) *dot_out = p2p_vals[0];
+            return;
+        }
+        // single-reduction CG (dist.cu: solve_dist_cg1): w.u joins the {u.r, r.r} partials of the preceding update kernel ({b.b, u.r, r.r} of
+        // the set-up on the first product) in ONE cross-GPU sum, and the scalar tail runs here
+        const int first = st->pad;
+        if (threadIdx.x == 0) { p2p_vals[0] = local_sum; p2p_vals[1] = st->red[0]; p2p_vals[2] = st->red[1]; p2p_vals[3] = st->red[2]; }
         __syncwarp();
-        p2p_allreduce_warp(*p2p, epoch_ctr, p2p_vals, 1);
-        if (threadIdx.x == 0) *dot_out = p2p_vals[0];
+        p2p_allreduce_warp(*p2p, epoch_ctr, p2p_vals, first ? 4 : 3);
+        if (threadIdx.x == 0) {
+            const double delta = p2p_vals[0];
+            double gamma, rr, beta, alpha;
+            if (first) {
+                st->bb = p2p_vals[1]; gamma = p2p_vals[2]; rr = p2p_vals[3];
+                beta = 0.0; alpha = gamma / delta;
+                st->pad = 0;
+            } else {
+                gamma = p2p_vals[1]; rr = p2p_vals[2];
+                beta = gamma / st->rho;
+                alpha = gamma / (delta - beta * gamma / st->zr_new);
+                st->iter = st->iter + 1;
+            }
+            st->rho = gamma; st->beta = beta; st->zr_new = alpha; st->rr = rr; st->pAp = delta;
+            if (sqrt(rr) < st->eps * sqrt(st->bb)) st->done = 1;
+        }
     }
 }
 

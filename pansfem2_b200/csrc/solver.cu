@@ -401,6 +401,12 @@ int pf2_csr_set_pcg_mode(pf2_csr* A, int mode) {
     return PF2_OK;
 }
 
+int pf2_csr_set_cg_variant(pf2_csr* A, int variant) {
+    PF2_CHECK(A && variant >= -1 && variant <= 1, "variant: -1 environment default, 0 the reference's recurrences, 1 single-reduction");
+    A->cg_variant = variant;
+    return PF2_OK;
+}
+
 int pf2_solve_host(pf2_csr* A, int solver, const double* b_host, double* x_host, int itrmax, double eps, int* iters_out, double* relres_out) {
     pf2_ctx* c = A->ctx;
     const size_t n = (size_t)A->rows;
@@ -428,7 +434,7 @@ int pf2_csr_solver_stats(pf2_csr* A, double out[8]) {
 }
 int pf2_csr_solver_stats_reset(pf2_csr* A) {
     A->prof_ms[0] = A->prof_ms[1] = A->prof_ms[2] = 0.0; A->prof_samples = 0; A->total_iters = 0;
-    A->pcg_kernel_ms = 0.0; A->pcg_iters = 0; A->pcg_solves = 0;
+    A->pcg_kernel_ms = 0.0; A->pcg_iters = 0; A->pcg_solves = 0; A->cg1_solves = 0;
     A->pcg_phase_ns[0] = A->pcg_phase_ns[1] = A->pcg_phase_ns[2] = 0.0;
     A->pcg_wait_ns[0] = A->pcg_wait_ns[1] = A->pcg_wait_ns[2] = 0.0;
     return PF2_OK;
@@ -438,7 +444,7 @@ int pf2_csr_pcg_stats(pf2_csr* A, double out[12]) {
     const double ki = A->pcg_iters ? 1.0e-6 / (double)A->pcg_iters : 0.0;
     for (int j = 0; j < 3; j++) { out[4 + j] = A->pcg_phase_ns[j] * ki; out[8 + j] = A->pcg_wait_ns[j] * ki; }
     out[7] = (double)A->sell_entries;
-    out[11] = 0.0;
+    out[11] = (double)A->cg1_solves;
     return PF2_OK;
 }
 

@@ -75,6 +75,9 @@ struct P2PView {          // must match pf2::P2P in dist.cu (kept POD here so th
     // neighbours' planes happens in the boundary slices of the next product instead of at the end of the p-update
     int own_lo, own_hi, sendL, cntL, sendR, cntR, defer_halo_wait, pad;
     unsigned long long* epoch;             // local device words: [0] allreduce epoch, [1] halo epoch
+    // single-reduction CG (solve_dist_cg1): non-null while such a solve runs -- the product's last CTA then reduces {w.u, u.r, r.r} in ONE
+    // cross-GPU sum and runs the scalar tail (alpha, beta, stopping test) on this state
+    CgState* cg1;
 };
 }  // namespace pf2
 
@@ -90,6 +93,11 @@ struct pf2_csr {
     pf2::P2PView p2p_view;
     pf2::P2PView* p2p_dev = nullptr;      // device copy handed to the fused kernels (nullptr: single GPU or NCCL backend)
     unsigned long long* p2p_epoch = nullptr;
+    // partitioned PCG recurrences: 0 = the reference's (two cross-GPU sums per iteration), 1 = single-reduction (Chronopoulos-Gear: one sum,
+    // two kernels per iteration; same iterates in exact arithmetic, round-off differs), -1 = from the environment (PF2_CG_SINGLE_REDUCTION)
+    int cg_variant = -1;
+    double* cg1_s = nullptr;              // s = A p of the single-reduction recurrences
+    long long cg1_solves = 0;             // solves that ran them (pf2_csr_pcg_stats out[11])
     bool pcg_dist_ok = false;             // every rank's slab qualifies for the persistent kernel's partitioned instantiation
     void* p2p_opened[2] = { nullptr, nullptr };   // IPC mappings of the left / right neighbour's Krylov slab
     long long nnz = 0;

@@ -1,6 +1,6 @@
 """torchrun worker of tests/test_gpu_dist.py: the row-partitioned SIMP design loop on N GPUs vs the single-GPU loop of the same problem.
     torchrun --nproc-per-node N tests/dist_worker.py [2d NX NY | 3d NX NY NZ | heat NX NY] [--iters K] [--mma] [--matrix-free] [--warm] [--big]
-Environment: PF2_P2P=0 selects the NCCL backend, PF2_PCG=0 the three-kernel PCG loop.  Rank 0 prints one JSON line and asserts
+Environment: PF2_P2P=0 selects the NCCL backend, PF2_PCG=0 the three-kernel PCG loop, PF2_CG_SINGLE_REDUCTION=1 the single-reduction recurrences.  Rank 0 prints one JSON line and asserts
 K (through the objective), u, f and the design after K iterations against the single-GPU loop (1e-8 relative / 1e-6 max-abs)."""
 import json
 import os
@@ -42,6 +42,7 @@ sim.set_warm_start("--warm" in argv)
 if "--ilu" in argv:       # block-Jacobi ILU(0) per rank: another preconditioner, the same converged solution
     capi._ck(capi.lib().pf2_simp_set_solver(sim.h, capi.SOLVER_ILU0CG))
 hist = []
+launches0 = ctx.launch_count()
 ctx.sync(); dist.barrier()
 t0 = time.time()
 for k in range(iters):
@@ -53,6 +54,7 @@ wall = time.time() - t0
 out = sim.get()
 res = {"world": world, "problem": P.name, "iters": iters, "wall_s": wall, "f": [h["f"] for h in hist], "cg_iters": [h["cg_iters"] for h in hist],
        "opt_steps": [h["opt_steps"] for h in hist], "phase_ms_last": hist[-1]["phase_ms"], "it_per_s": iters / wall}
+res["launches_per_cg_iter"] = (ctx.launch_count() - launches0) / max(1, sum(res["cg_iters"]))
 if check:
     gathered = [None] * world
     lo, hi = S.own_elems
