@@ -560,12 +560,13 @@ static int solve_dist_cg1(pf2_csr* A, int solver, const double* b, double* x, in
     while (!finished && rc == PF2_OK) {
         const int todo = std::min(chunk, itrmax - enq);
         for (int k = 0; k < todo && rc == PF2_OK; k++) {
+            const bool sample = (k == todo / 2) && enq > 0;      // one iteration per chunk is bracketed by events: update + halo | product + sum
+            if (sample) cudaEventRecord(A->pev[slot][0], s);
             if (solver == PF2_SOLVER_CG) cg1_update_halo_kernel<0><<<hgrid, kThreads, 0, s>>>(lo, hi, w, A->dvec, u, pd, sd, x, A->r, A->st, c->red.partials, c->red.ticket, A->p2p_view, A->halo[0], A->halo[2], A->halo[3], A->halo[5], d->epoch);
             else cg1_update_halo_kernel<1><<<hgrid, kThreads, 0, s>>>(lo, hi, w, A->dvec, u, pd, sd, x, A->r, A->st, c->red.partials, c->red.ticket, A->p2p_view, A->halo[0], A->halo[2], A->halo[3], A->halo[5], d->epoch);
-            const bool sample = (k == todo / 2) && enq > 0;      // one product per chunk is bracketed by events (roofline)
-            if (sample) cudaEventRecord(A->pev[slot][0], s);
+            if (sample) cudaEventRecord(A->pev[slot][1], s);
             rc = spmv_dot(A, u, w, A->st, &A->st->pAp);
-            if (sample) { cudaEventRecord(A->pev[slot][1], s); A->pev_armed[slot] = true; }
+            if (sample) { cudaEventRecord(A->pev[slot][2], s); A->pev_armed[slot] = true; }
             c->launches += 2;
         }
         if (rc != PF2_OK) break;
@@ -578,8 +579,9 @@ static int solve_dist_cg1(pf2_csr* A, int solver, const double* b, double* x, in
             last = A->h_st[slot ^ 1];
             if (A->pev_armed[slot ^ 1]) {
                 A->pev_armed[slot ^ 1] = false;
-                float ms = 0;
-                if (!last.done && cudaEventElapsedTime(&ms, A->pev[slot ^ 1][0], A->pev[slot ^ 1][1]) == cudaSuccess) { A->prof_ms[0] += ms; A->prof_samples++; }
+                float mu = 0, mp = 0;
+                if (!last.done && cudaEventElapsedTime(&mu, A->pev[slot ^ 1][0], A->pev[slot ^ 1][1]) == cudaSuccess &&
+                    cudaEventElapsedTime(&mp, A->pev[slot ^ 1][1], A->pev[slot ^ 1][2]) == cudaSuccess) { A->prof_ms[0] += mp; A->prof_ms[1] += mu; A->prof_samples++; }
                 else cudaGetLastError();
             }
             if (last.done) finished = true;
@@ -668,13 +670,14 @@ int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, d
             const bool sample = (k == todo / 2) && enq > 0;      // one SpMV per chunk is bracketed by events (roofline)
             if (sample) PF2_CUDA(cudaEventRecord(A->pev[slot][0], s));
             PF2_TRY(spmv_dot(A, A->p, A->y, A->st, &A->st->pAp));
-            if (sample) { PF2_CUDA(cudaEventRecord(A->pev[slot][1], s)); A->pev_armed[slot] = true; }
+            if (sample) PF2_CUDA(cudaEventRecord(A->pev[slot][1], s));
             if (!p2p) PF2_TRY(dist_allreduce(d, &A->st->pAp, 1));      // peer-memory backend: fused into the SpMV's last CTA
             if (p2p) {
                 if (solver == PF2_SOLVER_CG) p2p_update_kernel<0><<<ugrid, kThreads, 0, s>>>(lo, hi, A->p, A->y, A->dvec, x, A->r, A->z, A->st, c->red.partials, c->red.ticket, A->p2p_dev, d->epoch);
                 else p2p_update_kernel<1><<<ugrid, kThreads, 0, s>>>(lo, hi, A->p, A->y, A->dvec, x, A->r, A->z, A->st, c->red.partials, c->red.ticket, A->p2p_dev, d->epoch);
             } else if (solver == PF2_SOLVER_CG) dcg_update_kernel<0><<<ugrid, kThreads, 0, s>>>(lo, hi, A->p, A->y, A->dvec, x, A->r, A->z, A->st, c->red.partials, c->red.ticket);
             else dcg_update_kernel<1><<<ugrid, kThreads, 0, s>>>(lo, hi, A->p, A->y, A->dvec, x, A->r, A->z, A->st, c->red.partials, c->red.ticket);
+            if (sample) PF2_CUDA(cudaEventRecord(A->pev[slot][2], s));      // update (NCCL backend: with the sum of p.Ap before it)
             if (p2p) {
                 p2p_pupdate_halo_kernel<<<hgrid, kThreads, 0, s>>>(lo, hi, solver == PF2_SOLVER_CG ? A->r : A->z, A->p, A->st, 0, A->p2p_view,
                                                                    A->halo[0], A->halo[2], A->halo[3], A->halo[5], d->epoch, c->red.ticket + 1);
@@ -684,6 +687,7 @@ int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, d
                 dcg_pupdate_kernel<<<ugrid, kThreads, 0, s>>>(lo, hi, solver == PF2_SOLVER_CG ? A->r : A->z, A->p, A->st);
                 PF2_TRY(dist_halo(d, A->p, A->halo));
             }
+            if (sample) { PF2_CUDA(cudaEventRecord(A->pev[slot][3], s)); A->pev_armed[slot] = true; }      // p-update + halo exchange (+ sums)
             c->launches += 3;
         }
         PF2_LAUNCH_CHECK();
@@ -695,8 +699,10 @@ int solve_dist(pf2_csr* A, int solver, const double* b, double* x, int itrmax, d
             last = A->h_st[slot ^ 1];
             if (A->pev_armed[slot ^ 1]) {
                 A->pev_armed[slot ^ 1] = false;
-                float ms = 0;
-                if (!last.done && cudaEventElapsedTime(&ms, A->pev[slot ^ 1][0], A->pev[slot ^ 1][1]) == cudaSuccess) { A->prof_ms[0] += ms; A->prof_samples++; }
+                float ms[3] = { 0, 0, 0 };
+                bool ok = !last.done;
+                for (int j = 0; j < 3 && ok; j++) ok = cudaEventElapsedTime(&ms[j], A->pev[slot ^ 1][j], A->pev[slot ^ 1][j + 1]) == cudaSuccess;
+                if (ok) { for (int j = 0; j < 3; j++) A->prof_ms[j] += ms[j]; A->prof_samples++; }
                 else cudaGetLastError();
             }
             if (last.done) finished = true;

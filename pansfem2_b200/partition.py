@@ -189,3 +189,45 @@ def pcg_partitioned(matvec, diag, b, S: Slab, comm, itrmax=100000, eps=1e-10):
         if np.sqrt(rr) < eps * np.sqrt(bb):
             return x, k + 1
     return x, itrmax
+
+
+def pcg_partitioned_single_reduction(matvec, diag, b, S: Slab, comm, itrmax=100000, eps=1e-10):
+    """Host statement of csrc/dist.cu: solve_dist_cg1 (pf2_csr_set_cg_variant(A, 1)): the Chronopoulos-Gear form of the same Jacobi-PCG with
+    ONE allreduce per iteration -- {w.u, u.r, r.r} together -- and the halo exchange of u instead of p.  Returns (x, iterations, allreduces)."""
+    lo, hi = S.own_rows
+    sL, rL, cL, sR, rR, cR = S.row_halo
+    n = b.shape[0]
+    own = slice(lo, hi)
+
+    def halo(v):
+        from_left, from_right = comm.sendrecv(v[sL:sL + cL].copy() if cL else None, v[sR:sR + cR].copy() if cR else None)
+        if cL:
+            v[rL:rL + cL] = from_left
+        if cR:
+            v[rR:rR + cR] = from_right
+
+    x, r, u, p, s = (np.zeros(n) for _ in range(5))
+    r[own] = b[own]
+    u[own] = r[own] / diag[own]
+    halo(u)
+    w = matvec(u)
+    delta, bb, gamma, rr = comm.allreduce(np.array([w[own] @ u[own], b[own] @ b[own], u[own] @ r[own], r[own] @ r[own]]))
+    sums = 1
+    alpha, beta = gamma / delta, 0.0
+    for k in range(itrmax):
+        p[own] = u[own] + beta * p[own]
+        s[own] = w[own] + beta * s[own]
+        x[own] += alpha * p[own]
+        r[own] -= alpha * s[own]
+        u[own] = r[own] / diag[own]
+        halo(u)
+        w = matvec(u)
+        delta, gamma_new, rr = comm.allreduce(np.array([w[own] @ u[own], u[own] @ r[own], r[own] @ r[own]]))
+        sums += 1
+        if np.sqrt(rr) < eps * np.sqrt(bb):
+            return x, k + 1, sums
+        beta = gamma_new / gamma
+        alpha = gamma_new / (delta - beta * gamma_new / alpha)
+        gamma = gamma_new
+    return x, itrmax, sums
+

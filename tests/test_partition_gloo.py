@@ -46,7 +46,7 @@ def _make(kind):
     return problems.cantilever3d(7, 4, 2)
 
 
-def _worker(rank, world, port, kind, out_dir):
+def _worker(rank, world, port, kind, out_dir, single_reduction=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -63,7 +63,11 @@ def _worker(rank, world, port, kind, out_dir):
         assert np.array_equal(n2g, S.n2g_local)
         indptr, indices, data, F = So.arrays()
         A = sp.csr_matrix((data, indices, indptr), shape=(So.rows, So.rows))
-        x, its = partition.pcg_partitioned(lambda v: A @ v, A.diagonal(), F, S, GlooComm(rank, world))
+        if single_reduction:      # csrc/dist.cu: solve_dist_cg1 -- one allreduce per iteration
+            x, its, sums = partition.pcg_partitioned_single_reduction(lambda v: A @ v, A.diagonal(), F, S, GlooComm(rank, world))
+            assert sums == its + 1
+        else:
+            x, its = partition.pcg_partitioned(lambda v: A @ v, A.diagonal(), F, S, GlooComm(rank, world))
         lo, hi = S.own_rows
         np.save(os.path.join(out_dir, f"x_{rank}.npy"), x[lo:hi])
         np.save(os.path.join(out_dir, f"meta_{rank}.npy"), np.array([S.global_rows[0], S.global_rows[1], its]))
@@ -79,9 +83,11 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("kind,world", [("2d", 2), ("3d", 2), ("heat", 3), ("2d", 4)])
-def test_partitioned_pcg_matches_single_domain(tmp_path, kind, world):
-    mp.spawn(_worker, args=(world, _free_port(), kind, str(tmp_path)), nprocs=world, join=True)
+@pytest.mark.parametrize("kind,world,single_reduction", [("2d", 2, False), ("3d", 2, False), ("heat", 3, False), ("2d", 4, False),
+                                                         ("2d", 4, True), ("heat", 3, True), ("3d", 3, True)])
+def test_partitioned_pcg_matches_single_domain(tmp_path, kind, world, single_reduction):
+    """single_reduction: the opt-in recurrences of solve_dist_cg1 -- same solution and iteration count as the reference's ScalingCG"""
+    mp.spawn(_worker, args=(world, _free_port(), kind, str(tmp_path), single_reduction), nprocs=world, join=True)
     P = _make(kind)
     rng = np.random.default_rng(5)
     rho = rng.uniform(0.2, 1.0, P.nelem)
