@@ -160,6 +160,112 @@ assemble_generic_kernel(int nelem, ElemSpec sp, const double* __restrict__ coord
     }
 }
 
+// Hex20 solid (Solid.h:30-72 with ShapeFunction20Cubic, Gauss27Cubic): one WARP per element.  The thread-per-(element, node) kernel above
+// carries 3 x 60 accumulators and evaluates all 27 gradient sets in every one of its 20 threads -- it spills (r01: 13.6 ms per 27.6 k
+// elements).  Here lane q evaluates the gradients of integration point q ONCE (the same shape_grad, so the same bits) into shared memory,
+// then lane a accumulates the three rows of node a against five column nodes at a time (45 accumulators, in registers), reading the
+// gradients back as broadcasts, in the same order over the points as the reference's loop -- the entries equal the generic kernel's.
+constexpr int kHex20Warps = 3, kHex20Chunk = 5;
+__global__ void __launch_bounds__(kHex20Warps * 32)
+assemble_hex20_warp_kernel(int nelem, ElemSpec sp, const double* __restrict__ coords, const int* __restrict__ conn, const int* __restrict__ n2g,
+                           const double* __restrict__ ufix, const int* __restrict__ bmap, const long long* __restrict__ indptr,
+                           const double* __restrict__ modulus, const double* __restrict__ rho, double E0, double E1, double p,
+                           double* __restrict__ data, double* __restrict__ F) {
+    constexpr int NPE = 20, DIM = 3, NDOF = 3, MAXQ = 27, CH = kHex20Chunk;
+    __shared__ double Xs[kHex20Warps][NPE][DIM];
+    __shared__ double Gs[kHex20Warps][MAXQ][DIM][NPE];
+    __shared__ double Ws[kHex20Warps][MAXQ];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int ng = quad_count(sp.quad[0]);
+    const double cn = sp.cn[0], lam = sp.lam[0], mu = sp.mu[0];
+    for (int e = blockIdx.x * kHex20Warps + wid; e < nelem; e += gridDim.x * kHex20Warps) {
+        const int* nd = conn + (size_t)e * NPE;
+        __syncwarp();                                   // the previous element's readers are done with this warp's tiles
+        if (lane < NPE) {
+            const int node = nd[lane];
+#pragma unroll
+            for (int k = 0; k < DIM; k++) Xs[wid][lane][k] = coords[(size_t)node * DIM + k];
+        }
+        __syncwarp();
+        if (lane < ng) {
+            double r[3], wq, det, g[DIM][NPE];
+            quad_point(sp.quad[0], lane, r, wq);
+            shape_grad<SH_HEX20>(Xs[wid], r, g, det);
+#pragma unroll
+            for (int k = 0; k < DIM; k++)
+#pragma unroll
+                for (int n = 0; n < NPE; n++) Gs[wid][lane][k][n] = g[k][n];
+            Ws[wid][lane] = det * wq;
+        }
+        __syncwarp();
+        if (lane >= NPE) continue;
+        const int a = lane, na = nd[a];
+        int rows[NDOF];
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < NDOF; i++) { rows[i] = n2g[(size_t)na * NDOF + i]; any |= (rows[i] != -1); }
+        if (!any) continue;
+        const double E = modulus ? modulus[e] : simp_modulus(rho[e], E0, E1, p);
+        const int* bm = bmap + ((size_t)e * NPE + a) * NPE;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NPE; c0 += CH) {
+            double acc[NDOF][CH * NDOF];
+#pragma unroll
+            for (int i = 0; i < NDOF; i++)
+#pragma unroll
+                for (int j = 0; j < CH * NDOF; j++) acc[i][j] = 0.0;
+#pragma unroll 1
+            for (int q = 0; q < ng; q++) {
+                const double w = Ws[wid][q];
+                double cg[DIM], lg[DIM], mg[DIM];
+#pragma unroll
+                for (int k = 0; k < DIM; k++) { const double ga = Gs[wid][q][k][a]; cg[k] = cn * ga * w; lg[k] = lam * ga * w; mg[k] = mu * ga * w; }
+#pragma unroll
+                for (int bb = 0; bb < CH; bb++) {
+                    double g[DIM];
+#pragma unroll
+                    for (int k = 0; k < DIM; k++) g[k] = Gs[wid][q][k][c0 + bb];
+#pragma unroll
+                    for (int i = 0; i < NDOF; i++)
+#pragma unroll
+                        for (int j = 0; j < NDOF; j++) {
+                            if (i == j) {
+                                acc[i][bb * NDOF + j] += cg[i] * g[i];
+#pragma unroll
+                                for (int k = 0; k < DIM; k++) if (k != i) acc[i][bb * NDOF + j] += mg[k] * g[k];
+                            } else { acc[i][bb * NDOF + j] += lg[i] * g[j]; acc[i][bb * NDOF + j] += mg[j] * g[i]; }
+                        }
+                }
+            }
+#pragma unroll
+            for (int bb = 0; bb < CH; bb++) {
+                const int b = c0 + bb, off = bm[b], nb = nd[b];
+                int cfree[NDOF];
+                int rank = 0;
+#pragma unroll
+                for (int j = 0; j < NDOF; j++) {
+                    const int c = n2g[(size_t)nb * NDOF + j];
+                    cfree[j] = (c != -1) ? rank++ : -1;
+                }
+#pragma unroll
+                for (int i = 0; i < NDOF; i++) {
+                    if (rows[i] == -1) continue;
+                    const long long base = indptr[rows[i]] + off;
+#pragma unroll
+                    for (int j = 0; j < NDOF; j++) {
+                        const double v = E * acc[i][bb * NDOF + j];
+                        if (cfree[j] >= 0) atomicAdd(&data[base + cfree[j]], v);                  // Assembling.h:55
+                        else {
+                            const double uf = ufix[(size_t)nb * NDOF + j];
+                            if (uf != 0.0) atomicAdd(&F[rows[i]], -(v * uf));                       // Assembling.h:59
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <int KIND, int SHAPE>
 __global__ void __launch_bounds__(kThreads)
 sens_generic_kernel(int nelem, ElemSpec sp, const double* __restrict__ coords, const int* __restrict__ conn, const double* __restrict__ u,
@@ -302,6 +408,18 @@ int assemble_generic_launch(pf2_csr* A, pf2_mesh* mesh, pf2_dofmap* map, const E
         }
 #undef CALL
         return PF2_OK;
+    }
+    if (q.kind == KIND_SOLID3D && q.shape == PF2_SHAPE_HEX20 && sp.npass == 1 && quad_count(sp.quad[0]) <= 27) {
+        const char* sw = getenv("PF2_HEX20_WARP");      // 0: the thread-per-(element, node) kernel (read per call: tools/hex20_probe.py toggles it)
+        const bool warp_kernel = sw == nullptr || atoi(sw) != 0;
+        if (warp_kernel) {
+            const int grid = std::max(1, std::min((mesh->nelem + kHex20Warps - 1) / kHex20Warps, c->sm_count * 5 * 4));
+            assemble_hex20_warp_kernel<<<grid, kHex20Warps * 32, 0, s>>>(mesh->nelem, sp, mesh->coords, mesh->conn, map->n2g, map->ufix, A->bmap, A->indptr,
+                                                                         modulus_dev, rho_dev, E0, E1, p, A->data, A->F);
+            PF2_LAUNCH_CHECK();
+            c->launches++;
+            return PF2_OK;
+        }
     }
     const long long work = (long long)mesh->nelem * mesh->npe;
     const int grid = (int)std::min<long long>((work + 127) / 128, (long long)c->sm_count * 32);

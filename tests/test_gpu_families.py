@@ -149,6 +149,32 @@ def test_family_compliance_sensitivity_and_loop_vs_oracle(ctx, eq, n):
     S.close()
 
 
+def test_hex20_warp_kernel_equals_the_thread_kernel_and_the_oracle(ctx, monkeypatch):
+    """Hex20 assembly: one warp per element (gradients of the 27 points staged once in shared memory; default) against the
+    thread-per-(element, node) kernel (PF2_HEX20_WARP=0) and the oracle, on a distorted mesh with Dirichlet values."""
+    eq = ec.eq_code(ec.PHYS_SOLID, ec.SHAPE_HEX20, ec.QUAD_G27CUBE)
+    P = problems.family_problem(eq, (5, 3, 4))
+    rng = np.random.default_rng(11)
+    coords = P.coords + rng.uniform(-0.08, 0.08, P.coords.shape)
+    fixed = (P.fixed[0], P.fixed[1], np.where(P.fixed[1] == 0, 0.01, -0.02))
+    Emod = rng.uniform(0.1, 2.0, P.nelem)
+    mesh = capi.Mesh(ctx, coords, P.conn)
+    dm = capi.DofMap(ctx, P.nnode, 3, fixed)
+    A = capi.Csr.pattern(ctx, mesh, dm)
+    got = {}
+    for sw in ("1", "0"):
+        monkeypatch.setenv("PF2_HEX20_WARP", sw)
+        A.assemble(mesh, dm, eq, (0.0, 0.0, 0.3, 1.0, 1.0), P.loads, modulus=ctx.array(Emod))
+        got[sw] = A.download()
+    assert rel(got["1"][2], got["0"][2]) < 1e-14 and np.abs(got["1"][3] - got["0"][3]).max() <= 1e-14 * np.abs(got["0"][2]).max()
+    So, *_ = orc.assemble(eq, coords, P.conn, fixed, P.loads, Emod, 0.3, 1.0)
+    indptr, indices, data, F = So.arrays()
+    assert np.array_equal(indices, got["1"][1]) and rel(got["1"][2], data) < 1e-13
+    assert np.abs(got["1"][3] - F).max() <= 1e-13 * max(np.abs(F).max(), np.abs(data).max())
+    for o in (A, dm, mesh):
+        o.close()
+
+
 def test_t3_heat_static_vtk_on_the_device(ctx, t3):
     """sample/heattransfer/sample_heattransfer_static.cpp (HeatTransfer<T3, Gauss1Triangle> + CG) against static.vtk."""
     coords, conn, fixed, loads = t3_heat_problem(t3)

@@ -41,6 +41,8 @@ for stage in "$@"; do
              timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_pcg.py -x -q -k "three_kernel_loop_and_oracle and lambda3 or one_launch_sweeps" > "$out/sanitizer_racecheck.log" 2>&1; echo "racecheck rc=$?"; grep -E "RACECHECK SUMMARY|passed|failed" "$out/sanitizer_racecheck.log" | tail -3 ;;
     cg1)     [ -n "${SKIP_TESTS:-}" ] || timeout 600 python -m pytest tests/test_gpu_dist.py -x -q -rs -k "cg1 or env18 or env19 or env20 or env21 or env22" > "$out/cg1.log" 2>&1; tail -12 "$out/cg1.log"
              [ -n "${SKIP_BENCH:-}" ] || timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NG:-2} --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus ${NG:-2} --steps 2 --warmup 1 --no-hex8 --no-headline-2m > "$out/bench_cg1_n${NG:-2}.json" 2> "$out/bench_cg1_n${NG:-2}.err"; python tools/bench_brief.py "$out/bench_cg1_n${NG:-2}.json"; tail -3 "$out/bench_cg1_n${NG:-2}.err" | cut -c1-300 ;;
+    hex20)   timeout 400 python -m pytest tests/test_gpu_families.py tests/test_gpu_dist.py -x -q -k "hex20 or one_rank" > "$out/hex20.log" 2>&1; tail -5 "$out/hex20.log"
+             timeout 200 python tools/hex20_probe.py "$out/hex20_probe.json" 2>&1 | tail -2 ;;
     *)       echo "unknown stage $stage" ;;
   esac
 done
