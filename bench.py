@@ -16,7 +16,7 @@ stream, max over ranks) -- so `value`, `e2e` and the extra legs time the same de
     value          device-resident loop, the reference's algorithm as is (assembled CSR, ScalingCG from x0 = 0)
     e2e            the same iterations through pf2_simp_iterate_host (design uploaded from / downloaded to pinned host memory)
     legs           opt-in variants, each with its own cg_iters_per_step: warm_start (pf2_solve_x0), matrix_free
-                   (pf2_csr_matrix_free), warm_start+matrix_free; at N > 1 also single_reduction_cg (pf2_csr_set_cg_variant)
+                   (pf2_csr_matrix_free), warm_start+matrix_free; at N > 1 also single_reduction_cg (pf2_csr_set_cg_variant) and all three together
     headline_2m    BASELINE.json's metric size: 1000x1000 Q4 (2.0 M dof), value + e2e
     hex8_scaling   configs[3] 256x128x128 hex8 (one SIMP iteration from the uniform design) and configs[4] 384x192x192 hex8
                    (design loop), row-partitioned over the N GPUs like everything else at N > 1
@@ -585,6 +585,7 @@ def main():
                     ("warm_start+matrix_free", dict(warm_start=True, matrix_free=True))]
         if world > 1 and os.environ.get("PF2_P2P", "1") != "0":
             variants.append(("single_reduction_cg", dict(single_reduction=True)))
+            variants.append(("warm_start+matrix_free+single_reduction_cg", dict(warm_start=True, matrix_free=True, single_reduction=True)))
         for tag, kw in variants:
             try:
                 Lx = R.leg(Kx, W, tag=tag, **kw)
