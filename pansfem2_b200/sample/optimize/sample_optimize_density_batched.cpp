@@ -2,6 +2,7 @@
 //  The SIMP cantilever of the reference's sample/optimize/sample_optimize_density_{oc,mma,CONLIN}.cpp driven through the batched,
 //  device-resident API (B200/Batched.h).  Same problem, same parameters, same VTK output; the design never leaves the GPU.
 //      usage: sample_optimize_density_batched [oc|mma|conlin] [nx ny] [output.vtk]
+#include <cstdlib>
 #include <iostream>
 #include <fstream>
 #include <string>
@@ -53,6 +54,10 @@ int main(int argc, char** argv) {
                                                  : std::vector<double>{ 1.0e-5, 0.1, 0.2, 0.5, 0.7, 1.2, 1.0e-6, 1.0, 0.0, 10000.0, 0.0, 0.01, 1.0 };
     const int optkind = optimizer == "oc" ? PF2_OPT_OC : (optimizer == "conlin" ? PF2_OPT_CONLIN : PF2_OPT_MMA);
     B200::DesignLoop<Equation> loop(model, filter, optkind, optp, prm, qfixed, std::vector<double>(elements.size(), 0.5));
+    if (std::getenv("PF2_SAMPLE_WARM_START")) {         //  opt-in: every solve starts from the previous displacements (the reference starts from 0)
+        loop.Reset(std::vector<double>(elements.size(), 0.5));
+        loop.SetWarmStart(true);
+    }
 
     int k = 0;
     for (; k < 500; k++) {

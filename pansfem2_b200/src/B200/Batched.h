@@ -176,6 +176,11 @@ public:
         void ExportVTK(const std::string& _path, int _celltype, bool _withreactions = true) {
             Check(pf2_simp_export_vtk(handle, _path.c_str(), _celltype, _withreactions ? 1 : 0), "pf2_simp_export_vtk");
         }
+        //  back to iteration 0 with the design _s0 (optimiser history, Heaviside beta and the warm-start state included)
+        void Reset(const std::vector<double>& _s0) { Check(pf2_simp_reset(handle, _s0.data()), "pf2_simp_reset"); }
+        //  every displacement solve starts from the previous iteration's u instead of 0 (the reference always starts from 0, CG.h:423): same
+        //  stopping rule, same converged solution to the solver tolerance, fewer ScalingCG iterations
+        void SetWarmStart(bool _on) { Check(pf2_simp_set_warm_start(handle, _on ? 1 : 0), "pf2_simp_set_warm_start"); }
 private:
         Model& model;
         pf2_simp* handle;
