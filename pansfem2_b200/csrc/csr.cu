@@ -306,6 +306,11 @@ static bool sell_l2_resident(const pf2_csr* A) {
     return (double)A->sell_entries * (8.0 + idx_bytes) + 40.0 * (double)A->rows <= mb * 1.0e6;
 }
 
+static bool sell_prefetch_requested() {
+    static const bool on = [] { const char* e = getenv("PF2_SELL_PREFETCH"); return e != nullptr && atoi(e) != 0; }();
+    return on;
+}
+
 template <bool DOT>
 static int launch_sell(pf2_csr* A, const double* x, double* y, const CgState* st, double* dot_out) {
     pf2_ctx* c = A->ctx;
@@ -365,6 +370,12 @@ static int launch_sell(pf2_csr* A, const double* x, double* y, const CgState* st
                 spmv_sell_kernel<DOT, short, false, 1, 6, false><<<grid, kThreads, 0, c->stream>>>(A->rows, A->sell_ptr, A->sell_perm, A->sell_d16, A->sell_val, x, y,
                                                                                                 st, dot_out, c->red.partials, c->red.ticket, A->own_lo,
                                                                                                 A->own_hi, A->p2p_dev, A->p2p_epoch);
+            } else if (unroll == 6 && sell_prefetch_requested()) {
+                // opt-in (PF2_SELL_PREFETCH=1): next round's index loads ahead of this round's gathers (spmv_sell.cuh, PF)
+                const int grid = std::max(1, std::min(nb, c->wave_grid((const void*)spmv_sell_kernel<DOT, short, false, 1, 6, true, false, true>, kThreads)));
+                spmv_sell_kernel<DOT, short, false, 1, 6, true, false, true><<<grid, kThreads, 0, c->stream>>>(A->rows, A->sell_ptr, A->sell_perm, A->sell_d16, A->sell_val, x, y,
+                                                                                                          st, dot_out, c->red.partials, c->red.ticket, A->own_lo,
+                                                                                                          A->own_hi, A->p2p_dev, A->p2p_epoch);
             } else if (unroll == 9) SELLU(9) else if (unroll == 18) SELLU(18) else if (unroll == 3) SELLU(3) else SELLU(6)
 #undef SELLU
         }

@@ -156,7 +156,9 @@ template <bool CS, class T> __device__ __forceinline__ T sell_ld(const T* p) { r
 // NC = false: x is written inside the same kernel by other CTAs (persistent PCG): plain coherent loads, never the read-only path.
 template <bool NC> __device__ __forceinline__ double sell_ldx(const double* x, int i) { return NC ? __ldg(x + i) : x[i]; }
 
-template <class IDX, int NB, int U, bool CS, bool NC = true>
+// PF = true (scalar deltas only): the NEXT round's U index loads are issued before this round's gathers, so that a round pays one
+// dependent memory latency (values + gathers together) instead of two (index, then gather) -- same sums in the same order.
+template <class IDX, int NB, int U, bool CS, bool NC = true, bool PF = false>
 __device__ __forceinline__ double sell_slice_acc(const IDX* __restrict__ sell_idx, const double* __restrict__ sell_val, const double* x,
                                                  long long base, int width, int lane, int r) {
     const double* v = sell_val + base + lane;
@@ -191,6 +193,25 @@ __device__ __forceinline__ double sell_slice_acc(const IDX* __restrict__ sell_id
     } else {
         const IDX* c = sell_idx + base + lane;
         int k = 0;
+        if constexpr (PF) {
+            int cn[U];
+            if (U <= width) {
+#pragma unroll
+                for (int u = 0; u < U; u++) cn[u] = off + (int)sell_ld<CS>(c + u * kSellC);
+            }
+            for (; k + U <= width; k += U) {
+                double vv[U];
+                int cc[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) { vv[u] = sell_ld<CS>(v + (k + u) * kSellC); cc[u] = cn[u]; }
+                if (k + 2 * U <= width) {
+#pragma unroll
+                    for (int u = 0; u < U; u++) cn[u] = off + (int)sell_ld<CS>(c + (k + U + u) * kSellC);
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) acc += vv[u] * sell_ldx<NC>(x, cc[u]);
+            }
+        }
         for (; k + U <= width; k += U) {
             double vv[U];
             int cc[U];
@@ -210,7 +231,7 @@ __device__ __forceinline__ double sell_slice_acc(const IDX* __restrict__ sell_id
 // epoch (deferred there by the p-update kernel), so the exchange overlaps the interior rows.
 // (ORDERED is a separate instantiation: the plain kernel must keep its 32 registers -- 8 resident CTAs per SM; with the ordering logic
 // compiled in it needed 40 and the single-GPU product slowed down by 12 %.)
-template <bool DOT, class IDX, bool PERM = false, int NB = 1, int U = 6, bool CS = true, bool ORDERED = false>
+template <bool DOT, class IDX, bool PERM = false, int NB = 1, int U = 6, bool CS = true, bool ORDERED = false, bool PF = false>
 __global__ void __launch_bounds__(kThreads)
 spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* __restrict__ perm, const IDX* __restrict__ sell_idx, const double* __restrict__ sell_val,
                  const double* __restrict__ x, double* __restrict__ y, const CgState* __restrict__ st, double* dot_out,
@@ -261,7 +282,7 @@ spmv_sell_kernel(int rows, const long long* __restrict__ slice_ptr, const int* _
         const int r = PERM ? perm[s * kSellC + lane] : ((s * kSellC + lane < rows) ? s * kSellC + lane : -1);
         // ghost entries of x arrive from a peer GPU while this kernel runs: they must not come through the non-coherent path
         const double acc = ordered ? sell_slice_acc<IDX, NB, U, CS, false>(sell_idx, sell_val, x, base, width, lane, r)
-                                   : sell_slice_acc<IDX, NB, U, CS, true>(sell_idx, sell_val, x, base, width, lane, r);
+                                   : sell_slice_acc<IDX, NB, U, CS, true, PF>(sell_idx, sell_val, x, base, width, lane, r);
         if (r >= 0) {
             y[r] = acc;
             if (DOT && r >= dot_lo && r < dot_hi) dot += acc * x[r];
